@@ -1,0 +1,217 @@
+/*
+ * vs_b200.h -- C-ABI of libvs_b200.so, the B200 (sm_100a) engine behind the
+ * video->spike encoder hot path of PPWangyc/video-spike.
+ *
+ * The reference is pure Python/PyTorch and has NO FFI of its own; each
+ * entry point below therefore names the reference Python code whose arithmetic it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer owned by the caller (PyTorch caching
+ *     allocator) unless the name ends in _host; the library allocates nothing persistent
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*), no
+ *     internal synchronisation unless stated
+ *   - return 0 on success, non-zero VS_ERR_* otherwise; vs_last_error() gives the
+ *     thread-local message.  No exceptions cross the ABI.
+ *   - one process per GPU; distinct streams may be used from distinct threads
+ */
+#ifndef VS_B200_H
+#define VS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_ABI_VERSION 1
+
+enum {
+  VS_OK = 0,
+  VS_ERR_INVALID = 1,     /* bad argument (null pointer, shape, alignment) */
+  VS_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed */
+  VS_ERR_UNSUPPORTED = 3, /* shape outside what the kernels cover */
+  VS_ERR_WORKSPACE = 4    /* caller workspace too small */
+};
+
+/* GEMM engine selector for the entry points that take `engine` */
+enum {
+  VS_ENGINE_AUTO = 0,    /* tcgen05 where the shape allows, else SIMT */
+  VS_ENGINE_SIMT = 1,    /* CUDA-core fp32 FMA path (bring-up / small layers / cross-check) */
+  VS_ENGINE_TCGEN05 = 2  /* force the tensor-core path; VS_ERR_UNSUPPORTED if it cannot run */
+};
+
+int vs_version(void);
+const char* vs_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only supported target) */
+int vs_device_ok(void);
+
+/* ------------------------------------------------------------------ loader (L1/L2)
+ * src/loader/base.py:39,54 (`.float()` on uint8 frames, values stay 0..255) followed by
+ * src/trainer/base.py:64-67 (`flatten(1)`): frames (B, T, 1, H, W) uint8, contiguous, is
+ * already the flattened (B, D) matrix; the cast is the only arithmetic.  Bit-exact. */
+int vs_u8_to_f32(const uint8_t* frames, float* out, int64_t n, void* stream);
+int vs_u8_to_bf16(const uint8_t* frames, uint16_t* out_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ Linear layers (M1-M3, G1)
+ * torch.nn.Linear / ReLU as used by src/model/linear.py:24-32,45-53.
+ *   y[b,o] = act( sum_i x[b,i] * W[o,i] + bias[o] ),  W is (out,in) row-major like nn.Linear.
+ * x may be given as fp32 (x_f32) or, for the first layer, as raw uint8 frames (x_u8; then
+ * x_f32 may be NULL).  workspace: vs_linear_fwd_workspace() bytes (split-K partials).   */
+size_t vs_linear_fwd_workspace(int64_t batch, int64_t in_dim, int64_t out_dim);
+int vs_linear_fwd(const float* x_f32, const uint8_t* x_u8, const float* W, const float* bias,
+                  float* y, int64_t batch, int64_t in_dim, int64_t out_dim, int relu,
+                  int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the same layer (autograd of src/trainer/base.py:150).  dy is the gradient
+ * w.r.t. the layer OUTPUT; if relu != 0, y (the forward output) masks it first.
+ * Any of dx / dW / dbias may be NULL to skip.  dy_masked (batch,out) receives the masked
+ * gradient when relu != 0 (may alias dy).                                               */
+int vs_linear_bwd(const float* dy, const float* y, const float* x_f32, const uint8_t* x_u8,
+                  const float* W, float* dy_masked, float* dx, float* dW, float* dbias,
+                  int64_t batch, int64_t in_dim, int64_t out_dim, int relu, void* stream);
+
+/* ------------------------------------------------------------------ Poisson NLL (C1)
+ * torch.nn.PoissonNLLLoss(reduction="none", log_input=True) + .mean()
+ * (src/train.py:59, src/trainer/base.py:141-143): loss = mean(exp(x) - t*x),
+ * dlogits = (exp(x) - t)/n.  loss_sum (1 double, zeroed by the call) receives the SUM;
+ * dlogits may be NULL (eval).                                                            */
+int vs_poisson_nll(const float* logits, const float* target, double* loss_sum, float* dlogits,
+                   int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ AdamW (O1)
+ * torch.optim.AdamW single-tensor update (src/train.py:44-49, src/trainer/base.py:151):
+ *   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * lr and beta1 are per-step arguments because OneCycleLR cycles both.       */
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step; /* 1-based step count AFTER this update (torch's state['step']) */
+} vs_adamw_hyper;
+
+int vs_adamw(float* p, const float* g, float* m, float* v, int64_t n, vs_adamw_hyper h, void* stream);
+
+/* G1 + O1 fused for the first layer: dW[o,i] = sum_b dy[b,o] x[b,i] is formed in registers
+ * and consumed by the AdamW update without ever being written to HBM.  x as in
+ * vs_linear_fwd.  batch <= 32.                                                           */
+int vs_dw_adamw_fused(const float* dy, const float* x_f32, const uint8_t* x_u8, float* W,
+                      float* m, float* v, int64_t batch, int64_t in_dim, int64_t out_dim,
+                      vs_adamw_hyper h, void* stream);
+
+/* ------------------------------------------------------------------ whole train step
+ * The step body of src/trainer/base.py:147-154 for the `Linear` model
+ * (src/model/linear.py:10-15): cast+flatten, 6 Linear layers with ReLUs, Poisson NLL,
+ * backward, AdamW on every parameter -- enqueued back-to-back on `stream`.
+ * Layers are listed first to last; relu[l] != 0 applies ReLU after layer l.
+ * act[l]  : (batch, dims[l+1]) fp32 scratch for the layer outputs (act[L-1] = logits)
+ * gact[l] : (batch, dims[l+1]) fp32 scratch for gradients
+ * Layer 0 takes uint8 frames directly and uses the fused dW+AdamW kernel.               */
+#define VS_MAX_LAYERS 16
+typedef struct {
+  int32_t n_layers;
+  int64_t dims[VS_MAX_LAYERS + 1]; /* dims[0] = D, dims[L] = 100*N */
+  int32_t relu[VS_MAX_LAYERS];
+  float* W[VS_MAX_LAYERS];
+  float* b[VS_MAX_LAYERS];
+  float* mW[VS_MAX_LAYERS];
+  float* vW[VS_MAX_LAYERS];
+  float* mb[VS_MAX_LAYERS];
+  float* vb[VS_MAX_LAYERS];
+  float* act[VS_MAX_LAYERS];
+  float* gact[VS_MAX_LAYERS];
+  float* gW[VS_MAX_LAYERS]; /* gradient scratch for layers >= 1 (layer 0 unused) */
+  float* gb[VS_MAX_LAYERS];
+} vs_mlp;
+
+size_t vs_mlp_workspace(const vs_mlp* net, int64_t batch);
+/* training step; loss_sum as in vs_poisson_nll (divide by batch*dims[L] for the mean) */
+int vs_mlp_train_step(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32,
+                      const float* target, int64_t batch, vs_adamw_hyper h, double* loss_sum,
+                      int engine, void* workspace, size_t workspace_bytes, void* stream);
+/* forward only (E1: src/trainer/base.py:161-206); logits land in net->act[L-1]; if target
+ * is non-NULL the Poisson loss sum is also produced.                                    */
+int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32,
+                   const float* target, int64_t batch, double* loss_sum, int engine,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ RRR (R0-R6)
+ * Reduced-rank regression of src/model/rrr.py.  Per session: X (K,T,C) with C = C1+1
+ * (last column = the ones/bias column of src/train_rrr.py:155-162), y (K,T,N),
+ * U (N,C1,r), V (r,T), b (N,1,T), all fp64 in the reference.
+ *
+ * Device layout built once per split by vs_rrr_pack (DESIGN.md "RRR data layout"):
+ *   Xa : planes x (K*T) x ldc   bf16, row (k*T+t), c contiguous     (forward  A operand)
+ *   Xb : planes x C1 x ldr      bf16, row c, (k*T+t) contiguous     (backward A operand)
+ *   xl : (K*T) fp32, the last column of X
+ * planes = 1 stores bf16(X); planes = 2 or 3 store the exact residual expansion
+ * X ~= X0 + X1 (+ X2), each bf16, giving ~16 / ~24 significant bits.                    */
+typedef struct {
+  int64_t K, T, C1, N, r; /* trials, time bins, features without the bias column, neurons, rank */
+  int32_t planes;         /* 1, 2 or 3 */
+  int64_t ldc;            /* row pitch of Xa in elements, multiple of 64, >= C1 */
+  int64_t ldr;            /* row pitch of Xb in elements, multiple of 64, >= K*T */
+} vs_rrr_dims;
+
+/* pitches the library wants for given sizes */
+int64_t vs_rrr_ldc(int64_t C1);
+int64_t vs_rrr_ldr(int64_t K, int64_t T);
+
+/* X_rows: rows [row0, row0+nrows) of the (K*T, C1+1) fp64 matrix the reference hands to RRRGD
+ * (src/model/rrr.py:37-39), on the device.  Writes the matching rows of Xa / columns of Xb / xl;
+ * call once with (0, K*T) or chunk by chunk to bound the fp64 staging buffer.             */
+int vs_rrr_pack(const double* X_rows, int64_t row0, int64_t nrows, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
+                float* xl, void* stream);
+
+/* R0 on device from raw frames (src/train_rrr.py:143-165 for the video modalities):
+ * frames (K, Tf, F) uint8; sorted_idx (T) int32 frame indices; mean/std (Tf*F) fp64 as
+ * produced by vs_rrr_colstats on the TRAIN split.  Writes the same Xa/Xb/xl as vs_rrr_pack
+ * would for X = ((frames - mean)/std)[:, sorted_idx] with a ones column appended.        */
+int vs_rrr_colstats(const uint8_t* frames, int64_t K, int64_t cols, double* mean, double* std_clipped, void* stream);
+int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
+                   const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb, float* xl, void* stream);
+/* y (K,T,N) = (gaussian_filter1d(counts, sigma, axis=1, mode='reflect') - mean)/std as
+ * src/train_rrr.py:118,145,165 (scipy.ndimage truncate=4).  counts (K,T,N) fp32; mean/std (T*N) fp64
+ * may be NULL to get the smoothed counts only (used to derive the train statistics).      */
+int vs_rrr_smooth_y(const float* counts, int64_t K, int64_t T, int64_t N, double sigma, const double* mean,
+                    const double* std_clipped, float* y_out, void* stream);
+/* mean / clipped population std over the K trials of a (K, cols) fp32 matrix (src/utils/utils.py:107-112) */
+int vs_colstats_f32(const float* x, int64_t K, int64_t cols, double* mean, double* std_clipped, void* stream);
+
+size_t vs_rrr_workspace(vs_rrr_dims d);
+
+/* One closure evaluation of src/model/rrr.py:165-175 for one session:
+ *   loss = sum (yhat - y)^2 + l2 * sum beta^2,   beta = cat(U@V, b)
+ * and its gradient.  y is (K,T,N) fp32 (z-scored, smoothed targets).  Outputs fp64:
+ * loss (1), sse_n (N) = per-neuron sum of squared residuals (rrr.py:151), dU (N,C1,r),
+ * dV (r,T) [ACCUMULATED into: caller zeroes it once per closure so that several sessions
+ * sharing V add up, rrr.py:46-49], db (N,1,T).  Any gradient pointer may be NULL
+ * (evaluation only: rrr.py:179-181).                                                    */
+int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const float* xl,
+                   const float* y, const double* U, const double* V, const double* b, double l2,
+                   double* loss, double* sse_n, double* dU, double* dV, double* db, int engine,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* src/model/rrr.py:105-130 (predict_y): yhat (K,T,N) fp64 for one split. */
+int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl, const double* U, const double* V,
+                   const double* b, double* yhat, int engine, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------ plain TN GEMM (test hook)
+ * C[M,N] (fp32, row-major, ldc) = A[M,K] * B[N,K]^T with bf16 or tf32(fp32) operands, both
+ * K-major with pitches lda/ldb (elements).  Exposed so tests can exercise the tcgen05 core
+ * against the SIMT engine on arbitrary shapes.  dtype: 0 = bf16, 1 = tf32.              */
+int vs_gemm_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+               int64_t ldb, int64_t ldc, int dtype, int engine, void* stream);
+
+/* ------------------------------------------------------------------ instrumentation
+ * Number of kernel launches this library has enqueued from the calling process since the
+ * last reset (bench.py's gpu_launches).                                                 */
+int64_t vs_launch_count(void);
+void vs_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VS_B200_H */

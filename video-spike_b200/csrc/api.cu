@@ -1,0 +1,53 @@
+// C-ABI plumbing: version, error string, launch counter, GEMM test hook.
+#include "common.cuh"
+#include "gemm.h"
+
+namespace vs {
+std::atomic<long long> g_launches{0};
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_version(void) { return VS_ABI_VERSION; }
+extern "C" const char* vs_last_error(void) { return err_buf(); }
+extern "C" int64_t vs_launch_count(void) { return g_launches.load(); }
+extern "C" void vs_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int vs_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+extern "C" int vs_gemm_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                          int64_t ldc, int dtype, int engine, void* stream) {
+  VS_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, VS_ERR_INVALID, "vs_gemm_tn: null pointer or empty shape");
+  VS_REQUIRE(dtype == 0 || dtype == 1, VS_ERR_INVALID, "vs_gemm_tn: dtype must be 0 (bf16) or 1 (tf32)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == VS_ENGINE_SIMT) {
+    simt::GemmDesc g;
+    g.A.ptr = A; g.A.type = dtype == 0 ? simt::BF16 : simt::F32; g.A.s_i = lda; g.A.s_k = 1;
+    g.B.ptr = B; g.B.type = g.A.type; g.B.s_i = ldb; g.B.s_k = 1;
+    g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc;
+    return simt::gemm(g, st);
+  }
+  tc::GemmDesc g;
+  g.A.ptr = A; g.A.rows = M; g.A.k = K; g.A.ld = lda;
+  g.B.ptr = B; g.B.rows = N; g.B.k = K; g.B.ld = ldb;
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.tf32 = dtype == 1;
+  return tc::gemm_tn(g, st);
+}

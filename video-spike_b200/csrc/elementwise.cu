@@ -1,0 +1,314 @@
+// HBM-bound kernels of the `Linear` train step: frame loader, Poisson-NLL epilogue, AdamW, and
+// the fused first-layer weight-gradient + AdamW update.  All are streaming kernels: 128-bit
+// coalesced accesses, L1 bypass for touch-once data, enough loads in flight per SM to cover HBM
+// latency, grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace vs {
+
+// ------------------------------------------------------------------ loader (L1/L2)
+// src/loader/base.py:39,54: uint8 -> float32 WITHOUT scaling; flatten(1) is a view.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, long long n4,
+                                                        long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(in) + i);
+    st_stream_f4(reinterpret_cast<float4*>(out) + i,
+                 make_float4((float)(w & 0xff), (float)((w >> 8) & 0xff), (float)((w >> 16) & 0xff), (float)(w >> 24)));
+  }
+  // ragged tail (n not a multiple of 4)
+  if (blockIdx.x == 0 && threadIdx.x < (n - n4 * 4)) out[n4 * 4 + threadIdx.x] = (float)in[n4 * 4 + threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) u8_to_bf16_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                         long long n8, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(in) + i);
+    uint32_t o[4];
+    const uint32_t src[2] = {w.x, w.y};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float lo = (float)((src[h] >> (16 * q)) & 0xff), hi = (float)((src[h] >> (16 * q + 8)) & 0xff);
+        // 0..255 is exact in bf16: take the upper 16 bits of the fp32 pattern
+        o[h * 2 + q] = (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n - n8 * 8))
+    out[n8 * 8 + threadIdx.x] = (uint16_t)(__float_as_uint((float)in[n8 * 8 + threadIdx.x]) >> 16);
+}
+
+static unsigned stream_grid(long long work_items, int per_block) {
+  long long blocks = ceil_div(work_items, per_block);
+  const long long cap = (long long)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ------------------------------------------------------------------ Poisson NLL (C1)
+__global__ void __launch_bounds__(256) poisson_nll_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                          double* __restrict__ loss_sum, float* __restrict__ dx, long long n,
+                                                          float inv_n) {
+  __shared__ double wsum[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  double local = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 xv = ld_stream_f4(reinterpret_cast<const float4*>(x) + i);
+    const float4 tv = ld_stream_f4(reinterpret_cast<const float4*>(t) + i);
+    const float e0 = expf(xv.x), e1 = expf(xv.y), e2 = expf(xv.z), e3 = expf(xv.w);
+    float s = (e0 - tv.x * xv.x) + (e1 - tv.y * xv.y);
+    s += (e2 - tv.z * xv.z) + (e3 - tv.w * xv.w);
+    local += (double)s;
+    if (dx)
+      st_stream_f4(reinterpret_cast<float4*>(dx) + i,
+                   make_float4((e0 - tv.x) * inv_n, (e1 - tv.y) * inv_n, (e2 - tv.z) * inv_n, (e3 - tv.w) * inv_n));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    const float e = expf(x[i]);
+    local += (double)(e - t[i] * x[i]);
+    if (dx) dx[i] = (e - t[i]) * inv_n;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? wsum[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+  }
+}
+
+// ------------------------------------------------------------------ AdamW (O1)
+struct AdamConsts {
+  float decay;      // 1 - lr*wd
+  float beta1, w1;  // w1 = 1 - beta1
+  float beta2, w2;  // w2 = 1 - beta2
+  float step_size;  // lr / (1 - beta1^t)
+  float inv_bc2s;   // 1 / sqrt(1 - beta2^t)
+  float eps;
+};
+
+static AdamConsts make_consts(const vs_adamw_hyper& h) {
+  // scalars in double like the Python floats torch.optim.AdamW computes them with
+  const double bc1 = 1.0 - pow((double)h.beta1, (double)h.step);
+  const double bc2 = 1.0 - pow((double)h.beta2, (double)h.step);
+  AdamConsts c;
+  c.decay = (float)(1.0 - (double)h.lr * (double)h.weight_decay);
+  c.beta1 = h.beta1; c.w1 = (float)(1.0 - (double)h.beta1);
+  c.beta2 = h.beta2; c.w2 = (float)(1.0 - (double)h.beta2);
+  c.step_size = (float)((double)h.lr / bc1);
+  c.inv_bc2s = (float)(1.0 / sqrt(bc2));
+  c.eps = h.eps;
+  return c;
+}
+
+__device__ __forceinline__ void adamw_elem(float& p, float& m, float& v, float g, const AdamConsts& c) {
+  p *= c.decay;
+  m = fmaf(g - m, c.w1, m);                    // lerp_(grad, 1-beta1)
+  v = fmaf(v, c.beta2, c.w2 * g * g);          // mul_(beta2).addcmul_(g, g, 1-beta2)
+  const float denom = sqrtf(v) * c.inv_bc2s + c.eps;
+  p -= c.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, const AdamConsts c) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = ld_f4(reinterpret_cast<float4*>(p) + i);
+    float4 mv = ld_f4(reinterpret_cast<float4*>(m) + i);
+    float4 vv = ld_f4(reinterpret_cast<float4*>(v) + i);
+    const float4 gv = ld_stream_f4(reinterpret_cast<const float4*>(g) + i);
+    adamw_elem(pv.x, mv.x, vv.x, gv.x, c);
+    adamw_elem(pv.y, mv.y, vv.y, gv.y, c);
+    adamw_elem(pv.z, mv.z, vv.z, gv.z, c);
+    adamw_elem(pv.w, mv.w, vv.w, gv.w, c);
+    st_stream_f4(reinterpret_cast<float4*>(p) + i, pv);
+    st_stream_f4(reinterpret_cast<float4*>(m) + i, mv);
+    st_stream_f4(reinterpret_cast<float4*>(v) + i, vv);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    adamw_elem(p[i], m[i], v[i], g[i], c);
+  }
+}
+
+// ------------------------------------------------------------------ fused dW + AdamW (G1 + O1)
+// W, m, v are (out, in) row-major.  A CTA owns a strip of 4*256 input columns and walks all
+// `out` rows; each thread keeps x[0..BT) for its 4 columns in registers (frames are read ONCE),
+// forms g = sum_b dy[b,o]*x[b,i] with BT FMAs per weight and applies AdamW on the spot.  HBM
+// traffic is exactly read p,m,v + write p,m,v (24 B/weight) + the frames; dW never exists.
+template <int BT, bool kU8>
+__global__ void __launch_bounds__(256, (BT <= 16 ? 2 : 1))
+dw_adamw_kernel(const float* __restrict__ dy, const float* __restrict__ xf, const uint8_t* __restrict__ xu,
+                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, int batch, long long in_dim, int out_dim,
+                const AdamConsts c) {
+  extern __shared__ float dys[];  // [out][BT], zero padded past batch
+  for (int e = threadIdx.x; e < out_dim * BT; e += 256) {
+    const int o = e / BT, b = e % BT;
+    dys[e] = b < batch ? dy[(long long)b * out_dim + o] : 0.f;
+  }
+  const long long col = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+  const bool active = col < in_dim;  // in_dim % 4 == 0 is required by the host wrapper
+  float x[BT][4];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    if (active && b < batch) {
+      if constexpr (kU8) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(xu + (long long)b * in_dim + col));
+        x[b][0] = (float)(w & 0xff); x[b][1] = (float)((w >> 8) & 0xff);
+        x[b][2] = (float)((w >> 16) & 0xff); x[b][3] = (float)(w >> 24);
+      } else {
+        const float4 w = ld_stream_f4(reinterpret_cast<const float4*>(xf + (long long)b * in_dim + col));
+        x[b][0] = w.x; x[b][1] = w.y; x[b][2] = w.z; x[b][3] = w.w;
+      }
+    } else {
+      x[b][0] = x[b][1] = x[b][2] = x[b][3] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  constexpr int UNROLL = 2;
+  for (int o0 = 0; o0 < out_dim; o0 += UNROLL) {
+    float4 pv[UNROLL], mv[UNROLL], vv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (o0 + u < out_dim) {
+        const long long off = (long long)(o0 + u) * in_dim + col;
+        pv[u] = ld_f4(reinterpret_cast<float4*>(W + off));
+        mv[u] = ld_f4(reinterpret_cast<float4*>(M + off));
+        vv[u] = ld_f4(reinterpret_cast<float4*>(V + off));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (o0 + u < out_dim) {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        const float4* d4 = reinterpret_cast<const float4*>(dys + (o0 + u) * BT);
+#pragma unroll
+        for (int b4 = 0; b4 < BT / 4; ++b4) {
+          const float4 d = d4[b4];  // broadcast read
+          const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int b = b4 * 4 + q;
+            g0 = fmaf(dd[q], x[b][0], g0); g1 = fmaf(dd[q], x[b][1], g1);
+            g2 = fmaf(dd[q], x[b][2], g2); g3 = fmaf(dd[q], x[b][3], g3);
+          }
+        }
+        adamw_elem(pv[u].x, mv[u].x, vv[u].x, g0, c);
+        adamw_elem(pv[u].y, mv[u].y, vv[u].y, g1, c);
+        adamw_elem(pv[u].z, mv[u].z, vv[u].z, g2, c);
+        adamw_elem(pv[u].w, mv[u].w, vv[u].w, g3, c);
+        const long long off = (long long)(o0 + u) * in_dim + col;
+        st_stream_f4(reinterpret_cast<float4*>(W + off), pv[u]);
+        st_stream_f4(reinterpret_cast<float4*>(M + off), mv[u]);
+        st_stream_f4(reinterpret_cast<float4*>(V + off), vv[u]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small helpers for backward
+// dy_masked = dy * (y > 0)   (threshold backward of ReLU)
+__global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+// dbias[o] = sum_b dy[b,o]
+__global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, long long batch, long long out_dim) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out_dim) return;
+  float s = 0.f;
+  for (long long b = 0; b < batch; ++b) s += dy[b * out_dim + o];
+  db[o] = s;
+}
+
+int launch_relu_mask(const float* dy, const float* y, float* out, long long n, cudaStream_t st) {
+  VS_LAUNCH(relu_mask_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, dy, y, out, n);
+  return VS_OK;
+}
+int launch_colsum(const float* dy, float* db, long long batch, long long out_dim, cudaStream_t st) {
+  VS_LAUNCH(colsum_kernel, (unsigned)ceil_div(out_dim, 128), 128, 0, st, dy, db, batch, out_dim);
+  return VS_OK;
+}
+
+template <int BT>
+static int launch_dw_adamw(const float* dy, const float* xf, const uint8_t* xu, float* W, float* m, float* v, int batch,
+                           long long in_dim, int out_dim, const AdamConsts& c, cudaStream_t st) {
+  const size_t smem = (size_t)out_dim * BT * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(in_dim, 1024);
+  if (xu) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH((dw_adamw_kernel<BT, true>), grid, 256, smem, st, dy, xf, xu, W, m, v, batch, in_dim, out_dim, c);
+  } else {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH((dw_adamw_kernel<BT, false>), grid, 256, smem, st, dy, xf, xu, W, m, v, batch, in_dim, out_dim, c);
+  }
+  return VS_OK;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_u8_to_f32(const uint8_t* frames, float* out, int64_t n, void* stream) {
+  VS_REQUIRE(frames && out && n >= 0, VS_ERR_INVALID, "vs_u8_to_f32: null pointer or negative size");
+  if (n == 0) return VS_OK;
+  VS_REQUIRE(((uintptr_t)frames & 3) == 0 && ((uintptr_t)out & 15) == 0, VS_ERR_INVALID, "vs_u8_to_f32: misaligned buffers");
+  const long long n4 = n / 4;
+  VS_LAUNCH(u8_to_f32_kernel, stream_grid(n4, 256 * 4), 256, 0, stream, frames, out, n4, (long long)n);
+  return VS_OK;
+}
+
+extern "C" int vs_u8_to_bf16(const uint8_t* frames, uint16_t* out, int64_t n, void* stream) {
+  VS_REQUIRE(frames && out && n >= 0, VS_ERR_INVALID, "vs_u8_to_bf16: null pointer or negative size");
+  if (n == 0) return VS_OK;
+  VS_REQUIRE(((uintptr_t)frames & 7) == 0 && ((uintptr_t)out & 15) == 0, VS_ERR_INVALID, "vs_u8_to_bf16: misaligned buffers");
+  const long long n8 = n / 8;
+  VS_LAUNCH(u8_to_bf16_kernel, stream_grid(n8, 256 * 4), 256, 0, stream, frames, out, n8, (long long)n);
+  return VS_OK;
+}
+
+extern "C" int vs_poisson_nll(const float* logits, const float* target, double* loss_sum, float* dlogits, int64_t n,
+                              void* stream) {
+  VS_REQUIRE(logits && target && loss_sum && n > 0, VS_ERR_INVALID, "vs_poisson_nll: null pointer or empty input");
+  VS_REQUIRE(((uintptr_t)logits & 15) == 0 && ((uintptr_t)target & 15) == 0 && ((uintptr_t)dlogits & 15) == 0, VS_ERR_INVALID,
+             "vs_poisson_nll: buffers must be 16-byte aligned");
+  VS_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), (cudaStream_t)stream));
+  VS_LAUNCH(poisson_nll_kernel, stream_grid(n / 4 + 1, 256 * 2), 256, 0, stream, logits, target, loss_sum, dlogits,
+            (long long)n, (float)(1.0 / (double)n));
+  return VS_OK;
+}
+
+extern "C" int vs_adamw(float* p, const float* g, float* m, float* v, int64_t n, vs_adamw_hyper h, void* stream) {
+  VS_REQUIRE(p && g && m && v && n > 0, VS_ERR_INVALID, "vs_adamw: null pointer or empty tensor");
+  VS_REQUIRE(h.step >= 1, VS_ERR_INVALID, "vs_adamw: step must be >= 1");
+  VS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, VS_ERR_INVALID,
+             "vs_adamw: buffers must be 16-byte aligned");
+  VS_LAUNCH(adamw_kernel, stream_grid(n / 4 + 1, 256 * 2), 256, 0, stream, p, g, m, v, (long long)n, make_consts(h));
+  return VS_OK;
+}
+
+extern "C" int vs_dw_adamw_fused(const float* dy, const float* x_f32, const uint8_t* x_u8, float* W, float* m, float* v,
+                                 int64_t batch, int64_t in_dim, int64_t out_dim, vs_adamw_hyper h, void* stream) {
+  VS_REQUIRE(dy && (x_f32 || x_u8) && W && m && v, VS_ERR_INVALID, "vs_dw_adamw_fused: null pointer");
+  VS_REQUIRE(h.step >= 1, VS_ERR_INVALID, "vs_dw_adamw_fused: step must be >= 1");
+  VS_REQUIRE(batch >= 1 && batch <= 32, VS_ERR_UNSUPPORTED, "vs_dw_adamw_fused: batch %lld outside 1..32", (long long)batch);
+  VS_REQUIRE(in_dim % 4 == 0, VS_ERR_UNSUPPORTED, "vs_dw_adamw_fused: in_dim must be a multiple of 4");
+  VS_REQUIRE(out_dim >= 1 && out_dim * 32 * 4 <= 200 * 1024, VS_ERR_UNSUPPORTED, "vs_dw_adamw_fused: out_dim too large");
+  VS_REQUIRE((((uintptr_t)W | (uintptr_t)m | (uintptr_t)v | (uintptr_t)x_f32) & 15) == 0 && ((uintptr_t)x_u8 & 3) == 0,
+             VS_ERR_INVALID, "vs_dw_adamw_fused: misaligned buffers");
+  const AdamConsts c = make_consts(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (batch <= 8) return launch_dw_adamw<8>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  if (batch <= 16) return launch_dw_adamw<16>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  return launch_dw_adamw<32>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+}

@@ -1,0 +1,65 @@
+// Internal GEMM interfaces shared by the translation units of libvs_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vs {
+
+constexpr int kMaxPass = 6;   // plane products accumulated into one tile (3 planes -> 6 products)
+constexpr int kMaxBN = 448;   // widest accumulator tile the tcgen05 kernel keeps in TMEM
+
+namespace tc {
+// K-major operand: rows x k elements, pitch ld (elements), optionally several residual planes
+struct Operand {
+  const void* ptr = nullptr;
+  long long rows = 0, k = 0, ld = 0;
+  int planes = 1;
+  long long plane_stride = 0;  // elements
+};
+struct GemmDesc {
+  Operand A, B;            // C[M,N] = sum_pass A_pa * B_pb^T
+  long long M = 0, N = 0, K = 0;
+  float* C = nullptr;
+  long long ldc = 0;
+  long long split_stride = 0;  // elements between split-K partials
+  int splits = 1;              // requested split-K factor
+  int* splits_out = nullptr;   // actual factor used
+  int BN = 0;                  // 0 = choose
+  bool tf32 = false;
+  int n_pass = 1;
+  int pa[kMaxPass] = {0, 0, 0, 0, 0, 0};
+  int pb[kMaxPass] = {0, 0, 0, 0, 0, 0};
+};
+bool gemm_supported(const GemmDesc& g);
+int pick_bn(long long N);
+int gemm_tn(const GemmDesc& g, cudaStream_t stream);
+}  // namespace tc
+
+namespace simt {
+enum ElemType { F32 = 0, U8 = 1, BF16 = 2 };
+// generic strided operand: element (i, k) at ptr[i*s_i + k*s_k] (+ plane*plane_stride summed over planes)
+struct Operand {
+  const void* ptr = nullptr;
+  int type = F32;
+  long long s_i = 0, s_k = 0;
+  int planes = 1;
+  long long plane_stride = 0;
+};
+struct GemmDesc {
+  Operand A, B;            // C[m,n] = sum_k A(m,k) * B(n,k)
+  long long M = 0, N = 0, K = 0;
+  float* C = nullptr;
+  long long ldc = 0;
+  long long split_stride = 0;
+  int splits = 1;
+  const float* bias = nullptr;  // per-n bias, only when splits == 1
+  int relu = 0;                 // only when splits == 1
+};
+int gemm(const GemmDesc& g, cudaStream_t stream);
+}  // namespace simt
+
+// y[b,o] = act(sum_s part[s][o*ld_o + b*ld_b] + bias[o]) -- deterministic split-K reduction
+int splitk_reduce_bias_act(const float* part, int splits, long long split_stride, long long ld_o, long long ld_b,
+                           const float* bias, float* y, long long batch, long long out_dim, int relu, cudaStream_t stream);
+
+}  // namespace vs

@@ -1,0 +1,356 @@
+// TN GEMM on the 5th-gen tensor cores:  C[M,N] (fp32) = sum over passes of A_pa[M,K] * B_pb[N,K]^T
+//
+//   * operands bf16 (kind::f16) or fp32 read as tf32 (kind::tf32), both K-major, fetched by TMA
+//     (cp.async.bulk.tensor.3d, SWIZZLE_128B) into a multi-stage shared-memory ring
+//   * one elected thread issues tcgen05.mma (UMMA 128 x N x 32B), accumulators live in TMEM
+//   * 4 epilogue warps read TMEM with tcgen05.ld.32x32b and store the fp32 tile
+//   * split-K: gridDim.y splits write partial tiles at C + split * split_stride
+//   * "planes": an operand may be stored as several bf16 residual planes (X = X0 + X1 + X2);
+//     the pass list (pa[i], pb[i]) names which plane products are accumulated
+//
+// Used for: first Linear layer forward (W0 x frames, split-K over pixels; src/model/linear.py:26),
+// the two RRR contractions (src/model/rrr.py:113 and its autograd), and vs_gemm_tn.
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm.h"
+
+namespace vs {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int KB_BYTES = 128;    // one 128B swizzle atom along K per k-block
+constexpr int A_TILE_BYTES = BM * KB_BYTES;
+constexpr int NUM_THREADS = 192; // warp0 TMA, warp1 MMA + TMEM owner, warps 2..5 epilogue
+constexpr int CTRL_BYTES = 1024; // barriers + tmem pointer
+
+struct KParams {
+  int M, N;         // logical extent of C
+  int BN;           // tile width (multiple of 16, <= kMaxBN)
+  int tb_rows;      // rows per TMA box of B
+  int n_tb;         // TMA boxes per B tile
+  int num_kb;       // k-blocks per pass
+  int kb_per_split; // k-blocks handled by one split
+  int n_pass;
+  int pa[kMaxPass], pb[kMaxPass];
+  int stages;
+  int tmem_cols;
+  float* C;
+  long long ldc, split_stride;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity), "r"(0x989680)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// start address >> 4 in [0,14), LBO unused (single atom along K), SBO = 8 rows * 128 B = 1024 B
+// in [32,46), version 1 in [46,48), layout type SWIZZLE_128B (= 2) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// UMMA instruction descriptor: D fp32 (c_format 1 @ [4,6)), A/B format @ [7,10)/[10,13)
+// (bf16 = 1, tf32 = 2), both K-major (bits 15,16 = 0), N>>3 @ [17,23), M>>4 @ [24,29).
+__device__ __forceinline__ uint32_t make_idesc(bool tf32, int n) {
+  uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ kernel
+template <bool kTF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)p.BN * KB_BYTES;
+  const uint32_t tiles0 = base + CTRL_BYTES;
+  const uint32_t bar_full0 = base;                 // stages x 8 B
+  const uint32_t bar_empty0 = base + 8u * 16;      // stages x 8 B (stages <= 16)
+  const uint32_t bar_tmem = base + 8u * 32;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 33);
+
+  const int n_tiles = (p.N + p.BN - 1) / p.BN;
+  const int m_tile = blockIdx.x / n_tiles, n_tile = blockIdx.x % n_tiles;
+  const int split = blockIdx.y;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  const int iters = (kb1 > kb0 ? kb1 - kb0 : 0) * p.n_pass;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full0 + 8u * s, 1);
+      mbar_init(bar_empty0 + 8u * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 33), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      const int elems_per_kb = kTF32 ? 32 : 64;
+      int it = 0;
+      for (int ps = 0; ps < p.n_pass; ++ps) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+          const uint32_t a_dst = tiles0 + s * stage_bytes;
+          const uint32_t b_dst = a_dst + A_TILE_BYTES;
+          const uint32_t full = bar_full0 + 8u * s;
+          mbar_arrive_expect_tx(full, stage_bytes);
+          tma_load_3d(a_dst, &tmA, full, kb * elems_per_kb, m_tile * BM, p.pa[ps]);
+          for (int t = 0; t < p.n_tb; ++t)
+            tma_load_3d(b_dst + (uint32_t)(t * p.tb_rows) * KB_BYTES, &tmB, full, kb * elems_per_kb,
+                        n_tile * p.BN + t * p.tb_rows, p.pb[ps]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      const int n0 = p.BN > 256 ? 256 : p.BN;      // first UMMA N chunk
+      const int n1 = p.BN - n0;                    // second chunk (0 or a multiple of 16)
+      const uint32_t idesc0 = make_idesc(kTF32, n0);
+      const uint32_t idesc1 = make_idesc(kTF32, n1 > 0 ? n1 : 16);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(bar_full0 + 8u * s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = tiles0 + s * stage_bytes;
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        const uint64_t da = make_smem_desc(a_addr);
+        const uint64_t db0 = make_smem_desc(b_addr);
+        const uint64_t db1 = make_smem_desc(b_addr + 256u * KB_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 UMMA K-steps of 32 B inside the 128 B atom
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          tc_mma<kTF32>(tmem_base, da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc0, acc);
+          if (n1 > 0) tc_mma<kTF32>(tmem_base + 256u, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc1, acc);
+        }
+        tc_commit(bar_empty0 + 8u * s);  // frees the smem slot when these MMAs retire
+      }
+      tc_commit(bar_tmem);               // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global =====
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int row = m_tile * BM + q * 32 + lane;
+    float* crow = p.C + (long long)split * p.split_stride + (long long)row * p.ldc;
+    if (iters > 0) {
+      mbar_wait(bar_tmem, 0);
+      tc_fence_after();
+    }
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      if (iters > 0) {
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      const int col = n_tile * p.BN + c;
+      if (row < p.M) {
+        if (col + 16 <= p.N && ((p.ldc & 3) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(crow + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col + i < p.N) crow[col + i] = v[i];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D map over a (planes, rows, K) K-major operand; box = (128 B of K, box_rows, 1)
+static int make_map(CUtensorMap* m, const Operand& op, bool tf32, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VS_REQUIRE(enc != nullptr, VS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int esz = tf32 ? 4 : 2;
+  VS_REQUIRE(((uintptr_t)op.ptr & 15) == 0, VS_ERR_INVALID, "GEMM operand must be 16-byte aligned");
+  VS_REQUIRE((op.ld * esz) % 16 == 0, VS_ERR_INVALID, "GEMM operand pitch must be a multiple of 16 bytes (ld=%lld)", (long long)op.ld);
+  const int planes = op.planes > 0 ? op.planes : 1;
+  VS_REQUIRE(planes == 1 || (op.plane_stride * esz) % 16 == 0, VS_ERR_INVALID, "plane stride must be a multiple of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)op.k, (cuuint64_t)op.rows, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)op.ld * esz, (cuuint64_t)(planes > 1 ? op.plane_stride : op.ld * op.rows) * esz};
+  cuuint32_t box[3] = {(cuuint32_t)(tf32 ? 32 : 64), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VS_REQUIRE(r == CUDA_SUCCESS, VS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rows=%lld k=%lld ld=%lld box_rows=%d",
+             (int)r, (long long)op.rows, (long long)op.k, (long long)op.ld, box_rows);
+  return VS_OK;
+}
+
+bool gemm_supported(const GemmDesc& g) {
+  const int esz = g.tf32 ? 4 : 2;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
+  if (((uintptr_t)g.A.ptr & 15) || ((uintptr_t)g.B.ptr & 15)) return false;
+  if ((g.A.ld * esz) % 16 || (g.B.ld * esz) % 16) return false;
+  if (g.n_pass < 1 || g.n_pass > kMaxPass) return false;
+  return true;
+}
+
+int pick_bn(long long N) {
+  long long n16 = round_up(N, 16);
+  if (n16 <= kMaxBN) return (int)n16;
+  long long tiles = ceil_div(n16, kMaxBN);
+  return (int)round_up(ceil_div(n16, tiles), 16);
+}
+
+int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
+  VS_REQUIRE(gemm_supported(g), VS_ERR_UNSUPPORTED, "tcgen05 GEMM: unsupported operand layout/shape");
+  const int BN = g.BN > 0 ? g.BN : pick_bn(g.N);
+  VS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= kMaxBN, VS_ERR_UNSUPPORTED, "tcgen05 GEMM: bad BN %d", BN);
+  // TMA boxes are limited to 256 rows: split the B tile into equal boxes of a multiple of 8 rows
+  int n_tb = 1;
+  while (BN / n_tb > 256 || BN % n_tb != 0 || (BN / n_tb) % 8 != 0) {
+    ++n_tb;
+    VS_REQUIRE(n_tb <= 8, VS_ERR_UNSUPPORTED, "tcgen05 GEMM: cannot box BN=%d", BN);
+  }
+  const int elems_per_kb = g.tf32 ? 32 : 64;
+  KParams p;
+  p.M = (int)g.M; p.N = (int)g.N; p.BN = BN; p.tb_rows = BN / n_tb; p.n_tb = n_tb;
+  p.num_kb = (int)ceil_div(g.K, elems_per_kb);
+  int splits = g.splits > 0 ? g.splits : 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (int)ceil_div(p.num_kb, splits);
+  splits = (int)ceil_div(p.num_kb, p.kb_per_split);
+  p.n_pass = g.n_pass;
+  for (int i = 0; i < kMaxPass; ++i) { p.pa[i] = i < g.n_pass ? g.pa[i] : 0; p.pb[i] = i < g.n_pass ? g.pb[i] : 0; }
+  const int stage_bytes = A_TILE_BYTES + BN * KB_BYTES;
+  const int max_smem = 227 * 1024;
+  int stages = (max_smem - CTRL_BYTES - 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  VS_REQUIRE(stages >= 2, VS_ERR_UNSUPPORTED, "tcgen05 GEMM: tile too large for shared memory");
+  p.stages = stages;
+  int tcols = 32;
+  while (tcols < BN) tcols <<= 1;
+  p.tmem_cols = tcols;
+  p.C = g.C; p.ldc = g.ldc; p.split_stride = g.split_stride;
+  VS_REQUIRE(splits == 1 || g.split_stride >= g.M * g.ldc, VS_ERR_INVALID, "split-K needs split_stride >= M*ldc");
+
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, g.A, g.tf32, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, g.B, g.tf32, p.tb_rows);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)CTRL_BYTES + 1024 + (size_t)stages * stage_bytes;
+  const int m_tiles = (int)ceil_div(g.M, BM), n_tiles = (int)ceil_div(g.N, BN);
+  dim3 grid(m_tiles * n_tiles, splits, 1);
+  if (g.tf32) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH(gemm_tn_kernel<true>, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
+  } else {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH(gemm_tn_kernel<false>, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
+  }
+  if (g.splits_out) *g.splits_out = splits;
+  return VS_OK;
+}
+
+}  // namespace tc
+}  // namespace vs

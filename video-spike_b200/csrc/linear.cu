@@ -1,0 +1,224 @@
+// Linear layers and the whole `Linear` MLP train step (src/model/linear.py, src/trainer/base.py:147-154).
+#include "common.cuh"
+#include "gemm.h"
+
+namespace vs {
+int launch_relu_mask(const float* dy, const float* y, float* out, long long n, cudaStream_t st);
+int launch_colsum(const float* dy, float* db, long long batch, long long out_dim, cudaStream_t st);
+
+// the tall contraction (K = pixels) goes to the tensor cores; everything else is launch-bound
+constexpr long long kBigK = 4096;
+
+static bool use_tc(int engine, long long batch, long long in_dim, long long out_dim, const float* W) {
+  if (engine == VS_ENGINE_SIMT) return false;
+  const bool ok = in_dim >= kBigK && in_dim % 4 == 0 && (((uintptr_t)W) & 15) == 0;
+  return ok;
+}
+
+static int tc_splits(long long out_dim, long long batch) {
+  const long long tiles = ceil_div(out_dim, 128) * ceil_div(batch, tc::pick_bn(batch));
+  long long s = kNumSMs / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  return (int)s;
+}
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" size_t vs_linear_fwd_workspace(int64_t batch, int64_t in_dim, int64_t out_dim) {
+  size_t ws = 0;
+  if (in_dim >= kBigK) {
+    const size_t part = (size_t)kNumSMs * (size_t)round_up(out_dim, 128) * (size_t)round_up(batch, 16) * sizeof(float);
+    const size_t xs = (size_t)round_up(batch * in_dim, 64) * sizeof(float);
+    ws = round_up((long long)part, 256) + xs + 256;
+  }
+  return ws;
+}
+
+extern "C" int vs_linear_fwd(const float* x_f32, const uint8_t* x_u8, const float* W, const float* bias, float* y,
+                             int64_t batch, int64_t in_dim, int64_t out_dim, int relu, int engine, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  VS_REQUIRE((x_f32 || x_u8) && W && y, VS_ERR_INVALID, "vs_linear_fwd: null pointer");
+  VS_REQUIRE(batch > 0 && in_dim > 0 && out_dim > 0, VS_ERR_INVALID, "vs_linear_fwd: empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool big = in_dim >= kBigK;
+  if (big) {
+    VS_REQUIRE(workspace && workspace_bytes >= vs_linear_fwd_workspace(batch, in_dim, out_dim), VS_ERR_WORKSPACE,
+               "vs_linear_fwd: workspace too small (%zu < %zu)", workspace_bytes, vs_linear_fwd_workspace(batch, in_dim, out_dim));
+  }
+  if (use_tc(engine, batch, in_dim, out_dim, W)) {
+    // out^T[o, b] = sum_i W[o,i] * x[b,i]  (W rows on the UMMA M axis, batch on N), split over pixels
+    float* part = reinterpret_cast<float*>(workspace);
+    const size_t part_bytes = round_up((long long)((size_t)kNumSMs * round_up(out_dim, 128) * round_up(batch, 16) * sizeof(float)), 256);
+    const float* xs = x_f32;
+    if (!xs) {
+      float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + part_bytes);
+      int rc = vs_u8_to_f32(x_u8, scratch, batch * in_dim, stream);
+      if (rc) return rc;
+      xs = scratch;
+    }
+    VS_REQUIRE((((uintptr_t)xs) & 15) == 0, VS_ERR_INVALID, "vs_linear_fwd: x must be 16-byte aligned");
+    const long long ldc = round_up(batch, 16);
+    tc::GemmDesc g;
+    g.A.ptr = W; g.A.rows = out_dim; g.A.k = in_dim; g.A.ld = in_dim;
+    g.B.ptr = xs; g.B.rows = batch; g.B.k = in_dim; g.B.ld = in_dim;
+    g.M = out_dim; g.N = batch; g.K = in_dim;
+    g.C = part; g.ldc = ldc; g.split_stride = round_up(out_dim, 128) * ldc;
+    g.splits = tc_splits(out_dim, batch);
+    int splits = 1; g.splits_out = &splits;
+    g.tf32 = true;
+    int rc = tc::gemm_tn(g, st);
+    if (rc) return rc;
+    return splitk_reduce_bias_act(part, splits, g.split_stride, ldc, 1, bias, y, batch, out_dim, relu, st);
+  }
+  VS_REQUIRE(engine != VS_ENGINE_TCGEN05, VS_ERR_UNSUPPORTED, "vs_linear_fwd: shape not supported by the tcgen05 engine");
+  simt::GemmDesc g;
+  g.A.ptr = x_f32 ? (const void*)x_f32 : (const void*)x_u8; g.A.type = x_f32 ? simt::F32 : simt::U8; g.A.s_i = in_dim; g.A.s_k = 1;
+  g.B.ptr = W; g.B.type = simt::F32; g.B.s_i = in_dim; g.B.s_k = 1;
+  g.M = batch; g.N = out_dim; g.K = in_dim;
+  if (big) {
+    float* part = reinterpret_cast<float*>(workspace);
+    long long tiles = ceil_div(batch, 64) * ceil_div(out_dim, 64);
+    int splits = (int)(4 * kNumSMs / (tiles > 0 ? tiles : 1));
+    if (splits < 1) splits = 1;
+    if (splits > kNumSMs) splits = kNumSMs;
+    g.C = part; g.ldc = out_dim; g.split_stride = batch * out_dim; g.splits = splits;
+    int rc = simt::gemm(g, st);
+    if (rc) return rc;
+    const long long kps = round_up(ceil_div(in_dim, splits), 16);
+    const int used = (int)ceil_div(in_dim, kps);
+    return splitk_reduce_bias_act(part, used, g.split_stride, 1, out_dim, bias, y, batch, out_dim, relu, st);
+  }
+  g.C = y; g.ldc = out_dim; g.bias = bias; g.relu = relu;
+  return simt::gemm(g, st);
+}
+
+extern "C" int vs_linear_bwd(const float* dy, const float* y, const float* x_f32, const uint8_t* x_u8, const float* W,
+                             float* dy_masked, float* dx, float* dW, float* dbias, int64_t batch, int64_t in_dim,
+                             int64_t out_dim, int relu, void* stream) {
+  VS_REQUIRE(dy, VS_ERR_INVALID, "vs_linear_bwd: dy is null");
+  VS_REQUIRE(batch > 0 && in_dim > 0 && out_dim > 0, VS_ERR_INVALID, "vs_linear_bwd: empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* g = dy;
+  if (relu) {
+    VS_REQUIRE(y && dy_masked, VS_ERR_INVALID, "vs_linear_bwd: relu backward needs y and dy_masked");
+    int rc = launch_relu_mask(dy, y, dy_masked, batch * out_dim, st);
+    if (rc) return rc;
+    g = dy_masked;
+  }
+  if (dbias) {
+    int rc = launch_colsum(g, dbias, batch, out_dim, st);
+    if (rc) return rc;
+  }
+  if (dW) {
+    VS_REQUIRE(x_f32 || x_u8, VS_ERR_INVALID, "vs_linear_bwd: dW needs the layer input");
+    simt::GemmDesc d;  // dW[o,i] = sum_b g[b,o] * x[b,i]
+    d.A.ptr = g; d.A.type = simt::F32; d.A.s_i = 1; d.A.s_k = out_dim;
+    d.B.ptr = x_f32 ? (const void*)x_f32 : (const void*)x_u8; d.B.type = x_f32 ? simt::F32 : simt::U8; d.B.s_i = 1; d.B.s_k = in_dim;
+    d.M = out_dim; d.N = in_dim; d.K = batch; d.C = dW; d.ldc = in_dim;
+    int rc = simt::gemm(d, st);
+    if (rc) return rc;
+  }
+  if (dx) {
+    VS_REQUIRE(W, VS_ERR_INVALID, "vs_linear_bwd: dx needs W");
+    simt::GemmDesc d;  // dx[b,i] = sum_o g[b,o] * W[o,i]
+    d.A.ptr = g; d.A.type = simt::F32; d.A.s_i = out_dim; d.A.s_k = 1;
+    d.B.ptr = W; d.B.type = simt::F32; d.B.s_i = 1; d.B.s_k = in_dim;
+    d.M = batch; d.N = in_dim; d.K = out_dim; d.C = dx; d.ldc = in_dim;
+    int rc = simt::gemm(d, st);
+    if (rc) return rc;
+  }
+  return VS_OK;
+}
+
+// ------------------------------------------------------------------ whole MLP
+static int check_net(const vs_mlp* net, int64_t batch, bool train) {
+  VS_REQUIRE(net && net->n_layers >= 1 && net->n_layers <= VS_MAX_LAYERS, VS_ERR_INVALID, "vs_mlp: bad layer count");
+  VS_REQUIRE(batch > 0, VS_ERR_INVALID, "vs_mlp: empty batch");
+  for (int l = 0; l < net->n_layers; ++l) {
+    VS_REQUIRE(net->W[l] && net->act[l] && net->dims[l] > 0 && net->dims[l + 1] > 0, VS_ERR_INVALID, "vs_mlp: layer %d incomplete", l);
+    if (train) {
+      VS_REQUIRE(net->mW[l] && net->vW[l] && net->gact[l], VS_ERR_INVALID, "vs_mlp: layer %d missing optimizer/grad buffers", l);
+      VS_REQUIRE(!net->b[l] || (net->mb[l] && net->vb[l] && net->gb[l]), VS_ERR_INVALID, "vs_mlp: layer %d missing bias buffers", l);
+    }
+  }
+  return VS_OK;
+}
+
+extern "C" size_t vs_mlp_workspace(const vs_mlp* net, int64_t batch) {
+  if (!net) return 0;
+  size_t ws = 0;
+  for (int l = 0; l < net->n_layers && l < VS_MAX_LAYERS; ++l) {
+    const size_t w = vs_linear_fwd_workspace(batch, net->dims[l], net->dims[l + 1]);
+    if (w > ws) ws = w;
+  }
+  return ws;
+}
+
+extern "C" int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target,
+                              int64_t batch, double* loss_sum, int engine, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  int rc = check_net(net, batch, false);
+  if (rc) return rc;
+  VS_REQUIRE(frames_u8 || x_f32, VS_ERR_INVALID, "vs_mlp_forward: no input");
+  const int L = net->n_layers;
+  for (int l = 0; l < L; ++l) {
+    const float* xin = l == 0 ? x_f32 : net->act[l - 1];
+    const uint8_t* xu = l == 0 && !x_f32 ? frames_u8 : nullptr;
+    rc = vs_linear_fwd(xin, xu, net->W[l], net->b[l], net->act[l], batch, net->dims[l], net->dims[l + 1], net->relu[l], engine,
+                       workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  if (target) {
+    VS_REQUIRE(loss_sum, VS_ERR_INVALID, "vs_mlp_forward: loss_sum is null");
+    rc = vs_poisson_nll(net->act[L - 1], target, loss_sum, nullptr, batch * net->dims[L], stream);
+  }
+  return rc;
+}
+
+extern "C" int vs_mlp_train_step(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target,
+                                 int64_t batch, vs_adamw_hyper h, double* loss_sum, int engine, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  int rc = check_net(net, batch, true);
+  if (rc) return rc;
+  VS_REQUIRE((frames_u8 || x_f32) && target && loss_sum, VS_ERR_INVALID, "vs_mlp_train_step: null pointer");
+  const int L = net->n_layers;
+  // forward (M1-M3)
+  rc = vs_mlp_forward(net, frames_u8, x_f32, nullptr, batch, nullptr, engine, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  // loss + dlogits (C1)
+  rc = vs_poisson_nll(net->act[L - 1], target, loss_sum, net->gact[L - 1], batch * net->dims[L], stream);
+  if (rc) return rc;
+  // backward (G1) through layers L-1 .. 1: needs the PRE-update weights, so all updates come after
+  for (int l = L - 1; l >= 1; --l) {
+    VS_REQUIRE(net->gW[l], VS_ERR_INVALID, "vs_mlp_train_step: layer %d has no gW scratch", l);
+    rc = vs_linear_bwd(net->gact[l], net->act[l], net->act[l - 1], nullptr, net->W[l], net->gact[l], net->gact[l - 1], net->gW[l],
+                       net->b[l] ? net->gb[l] : nullptr, batch, net->dims[l], net->dims[l + 1], net->relu[l], stream);
+    if (rc) return rc;
+  }
+  // layer 0: mask, bias gradient, then the fused weight-gradient + AdamW
+  const uint8_t* xu = x_f32 ? nullptr : frames_u8;
+  const bool fused = batch <= 32 && net->dims[0] % 4 == 0 && net->dims[1] * 32 * 4 <= 200 * 1024;
+  rc = vs_linear_bwd(net->gact[0], net->act[0], x_f32, xu, net->W[0], net->gact[0], nullptr, fused ? nullptr : net->gW[0],
+                     net->b[0] ? net->gb[0] : nullptr, batch, net->dims[0], net->dims[1], net->relu[0], stream);
+  if (rc) return rc;
+  if (fused) {
+    rc = vs_dw_adamw_fused(net->gact[0], x_f32, xu, net->W[0], net->mW[0], net->vW[0], batch, net->dims[0], net->dims[1], h, stream);
+  } else {
+    VS_REQUIRE(net->gW[0], VS_ERR_INVALID, "vs_mlp_train_step: unfused first layer needs gW[0]");
+    rc = vs_adamw(net->W[0], net->gW[0], net->mW[0], net->vW[0], net->dims[0] * net->dims[1], h, stream);
+  }
+  if (rc) return rc;
+  // O1 for the remaining parameters
+  for (int l = 0; l < L; ++l) {
+    if (l >= 1) {
+      rc = vs_adamw(net->W[l], net->gW[l], net->mW[l], net->vW[l], net->dims[l] * net->dims[l + 1], h, stream);
+      if (rc) return rc;
+    }
+    if (net->b[l]) {
+      rc = vs_adamw(net->b[l], net->gb[l], net->mb[l], net->vb[l], net->dims[l + 1], h, stream);
+      if (rc) return rc;
+    }
+  }
+  return VS_OK;
+}

@@ -1,0 +1,577 @@
+// Reduced-rank regression closure (src/model/rrr.py:79-155,165-175) on device.
+//
+// Factorised evaluation (DESIGN.md "RRR closure"; oracle/rrr_oracle.py loss_and_grad_lowrank):
+//   Z[(k,t),(j,n)] = sum_c X[k,t,c] U[n,c,j]                    GEMM-F  (tcgen05, bf16 planes)
+//   yhat = sum_j V[j,t] Z[..(j,n)] + xl * b[n,t];  R = yhat - y   epilogue-F (+ RV = R (x) V, dV partials)
+//   Gacc[c,(j,n)] = sum_(k,t) X[k,t,c] RV[(j,n),(k,t)]           GEMM-B  (tcgen05, bf16 planes)
+//   dU = 2 Gacc + 2 l2 U (V V^T);  dV = 2 sum R Z + 2 l2 (U^T U) V;  db = 2 sum_k xl R + 2 l2 b
+// beta = cat(U@V, b) (rrr.py:79-96) and its gradient are never materialised.
+// All reductions are ordered (no floating-point atomics): results are bit-reproducible run to run.
+#include "common.cuh"
+#include "gemm.h"
+
+namespace vs {
+namespace rrr {
+
+constexpr int kMaxR = 8;
+
+__device__ __forceinline__ uint16_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+
+// split v into `planes` bf16 residual planes: v ~= p0 + p1 + p2
+__device__ __forceinline__ void split_planes(double v, int planes, uint16_t out[3]) {
+  double rem = v;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    if (p < planes) {
+      const uint16_t b = bf16_bits((float)rem);
+      out[p] = b;
+      rem -= (double)bf16_val(b);
+    } else {
+      out[p] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pack X (R0 tail / RRRGD input)
+// One 32 x 32 tile of (row = k*T+t, c) per block; writes Xa (row-major in c) directly and Xb
+// (row-major in row) through a shared-memory transpose so both stores are coalesced.
+template <bool kFromU8>
+__global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X, const uint8_t* __restrict__ frames,
+                                                   const int32_t* __restrict__ sorted_idx, const double* __restrict__ mean,
+                                                   const double* __restrict__ sd, long long Tf, long long row_begin,
+                                                   long long row_end, long long KT, long long T,
+                                                   long long C1, int planes, long long ldc, long long ldr,
+                                                   uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xb, float* __restrict__ xl) {
+  __shared__ uint16_t tile[3][32][33];
+  // rows are GLOBAL row indices k*T+t in [row_begin, row_end); X (fp64 path) points at row_begin
+  const long long r0 = row_begin + (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const long long pa = KT * ldc, pb = C1 * ldr;
+  for (int rr = ly; rr < 32; rr += 8) {
+    const long long row = r0 + rr, c = c0 + lx;
+    uint16_t pl[3] = {0, 0, 0};
+    if (row < row_end && c < C1) {
+      double v;
+      if constexpr (kFromU8) {
+        const long long k = row / T, t = row % T;
+        const long long f = sorted_idx[t];
+        const long long col = f * C1 + c;
+        v = ((double)frames[(k * Tf + f) * C1 + c] - mean[col]) / sd[col];
+      } else {
+        v = X[(row - row_begin) * (C1 + 1) + c];
+      }
+      split_planes(v, planes, pl);
+      for (int p = 0; p < planes; ++p) Xa[p * pa + row * ldc + c] = pl[p];
+    }
+    for (int p = 0; p < planes; ++p) tile[p][rr][lx] = pl[p];
+  }
+  __syncthreads();
+  for (int cc = ly; cc < 32; cc += 8) {
+    const long long c = c0 + cc, row = r0 + lx;
+    if (c < C1 && row < row_end)
+      for (int p = 0; p < planes; ++p) Xb[p * pb + c * ldr + row] = tile[p][lx][cc];
+  }
+  if (blockIdx.y == 0 && threadIdx.x < 32) {
+    const long long row = r0 + threadIdx.x;
+    if (row < row_end) xl[row] = kFromU8 ? 1.0f : (float)X[(row - row_begin) * (C1 + 1) + C1];
+  }
+}
+
+// column mean / population std (clipped at 1e-8) over the K trials: src/utils/utils.py:107-112
+__global__ void colstats_kernel(const uint8_t* __restrict__ frames, long long K, long long cols, double* __restrict__ mean,
+                                double* __restrict__ sd) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  // integer sums are exact: sum x <= 255 K, sum x^2 <= 65025 K
+  unsigned long long s1 = 0, s2 = 0;
+  for (long long k = 0; k < K; ++k) {
+    const unsigned v = frames[k * cols + c];
+    s1 += v;
+    s2 += v * v;
+  }
+  const double m = (double)s1 / (double)K;
+  // var = E[(x-m)^2] evaluated from exact integer moments: (K*s2 - s1^2) / K^2
+  const double var = ((double)K * (double)s2 - (double)s1 * (double)s1) / ((double)K * (double)K);
+  double s = sqrt(var > 0.0 ? var : 0.0);
+  mean[c] = m;
+  sd[c] = s < 1e-8 ? 1e-8 : s;
+}
+
+
+// ------------------------------------------------------------------ y preprocessing (R0)
+// scipy.ndimage.gaussian_filter1d(sigma, axis=1, mode="reflect", truncate=4.0): radius = int(4 sigma + .5),
+// weights exp(-x^2 / (2 sigma^2)) normalised to sum 1, "reflect" = (d c b a | a b c d | d c b a).
+__global__ void smooth_y_kernel(const float* __restrict__ counts, long long K, long long T, long long N, double sigma,
+                                const double* __restrict__ mean, const double* __restrict__ sd, float* __restrict__ out) {
+  __shared__ double wts[65];
+  const int radius = (int)(4.0 * sigma + 0.5);
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = -radius; i <= radius; ++i) { wts[i + radius] = exp(-0.5 * (double)i * (double)i / (sigma * sigma)); s += wts[i + radius]; }
+    for (int i = 0; i <= 2 * radius; ++i) wts[i] /= s;
+  }
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * T * N) return;
+  const long long n = idx % N, t = (idx / N) % T, k = idx / (N * T);
+  double acc = 0.0;
+  for (int i = -radius; i <= radius; ++i) {
+    long long tt = t + i;
+    // reflect about the edges (period 2T)
+    while (tt < 0 || tt >= T) tt = tt < 0 ? -tt - 1 : 2 * T - 1 - tt;
+    acc += wts[i + radius] * (double)counts[(k * T + tt) * N + n];
+  }
+  if (mean) acc = (acc - mean[t * N + n]) / sd[t * N + n];
+  out[idx] = (float)acc;
+}
+
+__global__ void colstats_f32_kernel(const float* __restrict__ x, long long K, long long cols, double* __restrict__ mean,
+                                    double* __restrict__ sd) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0;
+  for (long long k = 0; k < K; ++k) s += (double)x[k * cols + c];
+  const double m = s / (double)K;
+  double v = 0.0;
+  for (long long k = 0; k < K; ++k) { const double dlt = (double)x[k * cols + c] - m; v += dlt * dlt; }
+  double sdev = sqrt(v / (double)K);
+  mean[c] = m;
+  sd[c] = sdev < 1e-8 ? 1e-8 : sdev;
+}
+
+// ------------------------------------------------------------------ closure stage 0: U -> Ub planes, Gram partials
+// Ub[p][j*Npad + n][c] = plane p of U[n][c][j];  Gp[block][i*r+j] = sum over the block's (n,c) of U_i U_j
+__global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ U, long long N, long long Npad, long long C1,
+                                                     int r, int planes, long long ldc, uint16_t* __restrict__ Ub,
+                                                     double* __restrict__ Gp) {
+  __shared__ double red[8][kMaxR * kMaxR];
+  const long long n = blockIdx.y;
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long pu = (long long)r * Npad * ldc;
+  double u[kMaxR];
+  const bool ok = c < C1;
+#pragma unroll
+  for (int j = 0; j < kMaxR; ++j) u[j] = (ok && j < r) ? U[(n * C1 + c) * r + j] : 0.0;
+  if (ok) {
+    for (int j = 0; j < r; ++j) {
+      uint16_t pl[3];
+      split_planes(u[j], planes, pl);
+      for (int p = 0; p < planes; ++p) Ub[p * pu + ((long long)j * Npad + n) * ldc + c] = pl[p];
+    }
+  }
+  if (Gp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < r; ++j) {
+        const double s = warp_sum(u[i] * u[j]);
+        if (lane == 0) red[warp][i * r + j] = s;
+      }
+    __syncthreads();
+    if (threadIdx.x < r * r) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      Gp[((long long)blockIdx.y * gridDim.x + blockIdx.x) * (r * r) + threadIdx.x] = s;
+    }
+  }
+}
+
+// G = sum of Gram partials (fixed order), W = V V^T
+__global__ void small_mats_kernel(const double* __restrict__ Gp, long long nblocks, const double* __restrict__ V, int r, long long T,
+                                  double* __restrict__ G, double* __restrict__ W) {
+  const int e = threadIdx.x;
+  if (e < r * r) {
+    double s = 0.0;
+    if (Gp)
+      for (long long b = 0; b < nblocks; ++b) s += Gp[b * (r * r) + e];
+    G[e] = s;
+    const int i = e / r, j = e % r;
+    double w = 0.0;
+    for (long long t = 0; t < T; ++t) w += V[i * T + t] * V[j * T + t];
+    W[e] = w;
+  }
+}
+
+// ------------------------------------------------------------------ closure stage 2: epilogue of GEMM-F
+// block = 32 rows (k,t) x all neurons (looped in tiles of 32).  Phase 1 (lanes over n): yhat, R, dV partials.
+// Phase 2 (lanes over rows): RV[p][(j,n)][row] = planes of V[j,t] * R   (B operand of GEMM-B).
+template <bool kPredict>
+__global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, const float* __restrict__ y,
+                                                    const float* __restrict__ xl, const double* __restrict__ V,
+                                                    const double* __restrict__ b, long long KT, long long T, long long N,
+                                                    long long Npad, int r, int planes, long long ldr, float* __restrict__ R,
+                                                    uint16_t* __restrict__ RV, float* __restrict__ pv, double* __restrict__ yhat) {
+  __shared__ float Rs[32][33];
+  __shared__ float Vs[32][kMaxR];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.x * 32;
+  if (threadIdx.x < 32) {
+    const long long row = r0 + threadIdx.x;
+    const long long t = row < KT ? row % T : 0;
+    for (int j = 0; j < r; ++j) Vs[threadIdx.x][j] = (float)V[(long long)j * T + t];
+  }
+  __syncthreads();
+  float pvacc[4][kMaxR];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) pvacc[i][j] = 0.f;
+  const long long prv = (long long)r * Npad * ldr;
+  for (long long n0 = 0; n0 < N; n0 += 32) {
+    const long long n = n0 + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = w + 8 * i;
+      const long long row = r0 + rl;
+      float res = 0.f;
+      if (row < KT && n < N) {
+        const long long t = row % T;
+        float acc = xl[row] * (float)b[n * T + t];
+        float z[kMaxR];
+        for (int j = 0; j < r; ++j) {
+          z[j] = Z[row * ldz + (long long)j * Npad + n];
+          acc = fmaf(Vs[rl][j], z[j], acc);
+        }
+        if constexpr (kPredict) {
+          yhat[row * N + n] = (double)acc;
+        } else {
+          res = acc - y[row * N + n];
+          R[row * Npad + n] = res;
+          for (int j = 0; j < r; ++j) pvacc[i][j] = fmaf(res, z[j], pvacc[i][j]);
+        }
+      }
+      Rs[rl][lane] = res;
+    }
+    if constexpr (!kPredict) {
+      __syncthreads();
+      // phase 2: lanes over rows
+      const long long row = r0 + lane;
+      if (row < KT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int nl = w + 8 * i;
+          const long long nn = n0 + nl;
+          if (nn < N) {
+            const float res = Rs[lane][nl];
+            for (int j = 0; j < r; ++j) {
+              uint16_t pl[3];
+              split_planes((double)(Vs[lane][j] * res), planes, pl);
+              for (int p = 0; p < planes; ++p) RV[p * prv + ((long long)j * Npad + nn) * ldr + row] = pl[p];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if constexpr (!kPredict) {
+    // dV partial per row: reduce over the 32 lanes (neurons)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long row = r0 + w + 8 * i;
+      for (int j = 0; j < r; ++j) {
+        const float s = warp_sum(pvacc[i][j]);
+        if (lane == 0 && row < KT) pv[row * r + j] = s;
+      }
+    }
+  }
+}
+
+// per (t, n): db and SSE partials, ordered sum over trials k
+__global__ void __launch_bounds__(128) reduce_k_kernel(const float* __restrict__ R, const float* __restrict__ xl,
+                                                       const double* __restrict__ b, long long K, long long T, long long N,
+                                                       long long Npad, double l2, double* __restrict__ db,
+                                                       double* __restrict__ sse_tn) {
+  const long long t = blockIdx.y;
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double sdb = 0.0, sse = 0.0;
+  for (long long k = 0; k < K; ++k) {
+    const long long row = k * T + t;
+    const double res = (double)R[row * Npad + n];
+    sdb += (double)xl[row] * res;
+    sse += res * res;
+  }
+  if (db) db[n * T + t] = 2.0 * sdb + 2.0 * l2 * b[n * T + t];
+  sse_tn[t * N + n] = sse;
+}
+
+// final scalars: sse_n, loss, dV
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv,
+                                                       const double* __restrict__ G, const double* __restrict__ W,
+                                                       const double* __restrict__ V, const double* __restrict__ b, long long K,
+                                                       long long T, long long N, int r, double l2, double* __restrict__ sse_n,
+                                                       double* __restrict__ loss, double* __restrict__ dV) {
+  __shared__ double red[256];
+  // per-neuron SSE (src/model/rrr.py:151) and its total
+  double tot = 0.0;
+  for (long long n = threadIdx.x; n < N; n += 256) {
+    double s = 0.0;
+    for (long long t = 0; t < T; ++t) s += sse_tn[t * N + n];
+    if (sse_n) sse_n[n] = s;
+    tot += s;
+  }
+  // sum b^2 (the intercept is part of beta: SURVEY A14)
+  double bsq = 0.0;
+  for (long long i = threadIdx.x; i < N * T; i += 256) bsq += b[i] * b[i];
+  red[threadIdx.x] = tot + l2 * bsq;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && loss) {
+    double gw = 0.0;
+    for (int e = 0; e < r * r; ++e) gw += G[e] * W[e];
+    *loss = red[0] + l2 * gw;
+  }
+  if (dV) {
+    for (long long e = threadIdx.x; e < (long long)r * T; e += 256) {
+      const long long j = e / T, t = e % T;
+      double s = 0.0;
+      for (long long k = 0; k < K; ++k) s += (double)pv[(k * T + t) * r + j];
+      double gv = 0.0;
+      for (int jj = 0; jj < r; ++jj) gv += G[j * r + jj] * V[(long long)jj * T + t];
+      dV[e] += 2.0 * s + 2.0 * l2 * gv;  // accumulated: V is shared across sessions (rrr.py:49)
+    }
+  }
+}
+
+// ------------------------------------------------------------------ closure stage 4: epilogue of GEMM-B
+// dU[n][c][j] = 2 Gacc[c][(j,n)] + 2 l2 sum_j' U[n][c][j'] W[j'][j]; 32 c x 32 n tile, smem transpose
+__global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Gacc, long long ldg, const double* __restrict__ U,
+                                                    const double* __restrict__ W, long long C1, long long N, long long Npad, int r,
+                                                    double l2, double* __restrict__ dU) {
+  __shared__ float Gs[kMaxR][32][33];
+  __shared__ double Ws[kMaxR * kMaxR];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long c0 = (long long)blockIdx.x * 32, n0 = (long long)blockIdx.y * 32;
+  if (threadIdx.x < r * r) Ws[threadIdx.x] = W[threadIdx.x];
+  for (int i = 0; i < 4; ++i) {
+    const int cl = w + 8 * i;
+    const long long c = c0 + cl, n = n0 + lane;
+    for (int j = 0; j < r; ++j) Gs[j][cl][lane] = (c < C1 && n < N) ? Gacc[c * ldg + (long long)j * Npad + n] : 0.f;
+  }
+  __syncthreads();
+  const long long c = c0 + lane;
+  if (c >= C1) return;
+  for (int i = 0; i < 4; ++i) {
+    const int nl = w + 8 * i;
+    const long long n = n0 + nl;
+    if (n >= N) continue;
+    double u[kMaxR];
+    for (int j = 0; j < r; ++j) u[j] = U[(n * C1 + c) * r + j];
+    for (int j = 0; j < r; ++j) {
+      double reg = 0.0;
+      for (int jj = 0; jj < r; ++jj) reg += u[jj] * Ws[jj * r + j];
+      dU[(n * C1 + c) * r + j] = 2.0 * (double)Gs[j][lane][nl] + 2.0 * l2 * reg;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host orchestration
+struct Ws {
+  uint16_t *Ub, *RV;
+  float *Z, *R, *Gacc, *pv;
+  double *Gp, *G, *W, *sse_tn;
+  long long Npad, ldz, gp_blocks;
+  size_t total;
+};
+
+static Ws carve(const vs_rrr_dims& d, void* base) {
+  Ws w;
+  const long long KT = d.K * d.T;
+  w.Npad = round_up(d.N, 16);
+  w.ldz = d.r * w.Npad;
+  w.gp_blocks = ceil_div(d.C1, 256) * d.N;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += (size_t)round_up((long long)bytes, 1024); return q; };
+  w.Ub = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldc * 2);
+  w.RV = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldr * 2);
+  w.Z = (float*)take((size_t)KT * w.ldz * 4);
+  w.R = (float*)take((size_t)KT * w.Npad * 4);
+  w.Gacc = (float*)take((size_t)d.C1 * w.ldz * 4);
+  w.pv = (float*)take((size_t)KT * d.r * 4);
+  w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
+  w.G = (double*)take(kMaxR * kMaxR * 8);
+  w.W = (double*)take(kMaxR * kMaxR * 8);
+  w.sse_tn = (double*)take((size_t)d.T * d.N * 8);
+  w.total = off;
+  return w;
+}
+
+static int check_dims(const vs_rrr_dims& d) {
+  VS_REQUIRE(d.K > 0 && d.T > 0 && d.C1 > 0 && d.N > 0 && d.r > 0, VS_ERR_INVALID, "rrr: empty dimension");
+  VS_REQUIRE(d.r <= kMaxR, VS_ERR_UNSUPPORTED, "rrr: rank %lld > %d", (long long)d.r, kMaxR);
+  VS_REQUIRE(d.planes >= 1 && d.planes <= 3, VS_ERR_INVALID, "rrr: planes must be 1..3");
+  VS_REQUIRE(d.ldc >= d.C1 && d.ldc % 8 == 0 && d.ldr >= d.K * d.T && d.ldr % 8 == 0, VS_ERR_INVALID, "rrr: bad pitches");
+  VS_REQUIRE(d.K * d.T < (1ll << 31) && d.C1 < (1ll << 31), VS_ERR_UNSUPPORTED, "rrr: dimension exceeds 2^31");
+  return VS_OK;
+}
+
+static void set_passes(tc::GemmDesc& g, int planes) {
+  // plane products kept: everything down to ~2^-8(planes) relative
+  static const int pa3[6] = {0, 0, 1, 0, 1, 2}, pb3[6] = {0, 1, 0, 2, 1, 0};
+  g.n_pass = planes == 1 ? 1 : (planes == 2 ? 3 : 6);
+  for (int i = 0; i < g.n_pass; ++i) { g.pa[i] = pa3[i]; g.pb[i] = pb3[i]; }
+}
+
+// Z = Xa * Ub^T  (M = K*T, N = r*Npad, contraction C1)
+static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int engine, cudaStream_t st) {
+  const long long KT = d.K * d.T;
+  if (engine == VS_ENGINE_SIMT) {
+    simt::GemmDesc g;
+    g.A.ptr = Xa; g.A.type = simt::BF16; g.A.s_i = d.ldc; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = KT * d.ldc;
+    g.B.ptr = w.Ub; g.B.type = simt::BF16; g.B.s_i = d.ldc; g.B.s_k = 1; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldc;
+    g.M = KT; g.N = w.ldz; g.K = d.C1; g.C = w.Z; g.ldc = w.ldz;
+    return simt::gemm(g, st);
+  }
+  tc::GemmDesc g;
+  g.A.ptr = Xa; g.A.rows = KT; g.A.k = d.C1; g.A.ld = d.ldc; g.A.planes = d.planes; g.A.plane_stride = KT * d.ldc;
+  g.B.ptr = w.Ub; g.B.rows = w.ldz; g.B.k = d.C1; g.B.ld = d.ldc; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldc;
+  g.M = KT; g.N = w.ldz; g.K = d.C1; g.C = w.Z; g.ldc = w.ldz;
+  set_passes(g, d.planes);
+  return tc::gemm_tn(g, st);
+}
+
+// Gacc = Xb * RV^T  (M = C1, N = r*Npad, contraction K*T)
+static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int engine, cudaStream_t st) {
+  const long long KT = d.K * d.T;
+  if (engine == VS_ENGINE_SIMT) {
+    simt::GemmDesc g;
+    g.A.ptr = Xb; g.A.type = simt::BF16; g.A.s_i = d.ldr; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = d.C1 * d.ldr;
+    g.B.ptr = w.RV; g.B.type = simt::BF16; g.B.s_i = d.ldr; g.B.s_k = 1; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldr;
+    g.M = d.C1; g.N = w.ldz; g.K = KT; g.C = w.Gacc; g.ldc = w.ldz;
+    return simt::gemm(g, st);
+  }
+  tc::GemmDesc g;
+  g.A.ptr = Xb; g.A.rows = d.C1; g.A.k = KT; g.A.ld = d.ldr; g.A.planes = d.planes; g.A.plane_stride = d.C1 * d.ldr;
+  g.B.ptr = w.RV; g.B.rows = w.ldz; g.B.k = KT; g.B.ld = d.ldr; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldr;
+  g.M = d.C1; g.N = w.ldz; g.K = KT; g.C = w.Gacc; g.ldc = w.ldz;
+  set_passes(g, d.planes);
+  return tc::gemm_tn(g, st);
+}
+
+}  // namespace rrr
+}  // namespace vs
+
+using namespace vs;
+using namespace vs::rrr;
+
+extern "C" int64_t vs_rrr_ldc(int64_t C1) { return round_up(C1, 64); }
+extern "C" int64_t vs_rrr_ldr(int64_t K, int64_t T) { return round_up(K * T, 64); }
+
+extern "C" size_t vs_rrr_workspace(vs_rrr_dims d) {
+  if (d.K <= 0 || d.T <= 0 || d.C1 <= 0 || d.N <= 0 || d.r <= 0 || d.planes < 1) return 0;
+  return carve(d, nullptr).total;
+}
+
+extern "C" int vs_rrr_pack(const double* X_rows, int64_t row0, int64_t nrows, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
+                           float* xl, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(X_rows && Xa && Xb && xl, VS_ERR_INVALID, "vs_rrr_pack: null pointer");
+  const long long KT = d.K * d.T;
+  VS_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= KT, VS_ERR_INVALID, "vs_rrr_pack: row range outside the matrix");
+  dim3 grid((unsigned)ceil_div(nrows, 32), (unsigned)ceil_div(d.C1, 32));
+  VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack: too many columns");
+  VS_LAUNCH((pack_kernel<false>), grid, 256, 0, stream, X_rows, nullptr, nullptr, nullptr, nullptr, 0ll, (long long)row0,
+            (long long)(row0 + nrows), KT, (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl);
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_colstats(const uint8_t* frames, int64_t K, int64_t cols, double* mean, double* std_clipped, void* stream) {
+  VS_REQUIRE(frames && mean && std_clipped && K > 0 && cols > 0, VS_ERR_INVALID, "vs_rrr_colstats: bad arguments");
+  VS_LAUNCH(colstats_kernel, (unsigned)ceil_div(cols, 256), 256, 0, stream, frames, (long long)K, (long long)cols, mean, std_clipped);
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
+                              const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb, float* xl, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(frames && sorted_idx && mean && std_clipped && Xa && Xb && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8: bad arguments");
+  const long long KT = d.K * d.T;
+  dim3 grid((unsigned)ceil_div(KT, 32), (unsigned)ceil_div(d.C1, 32));
+  VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8: too many columns");
+  VS_LAUNCH((pack_kernel<true>), grid, 256, 0, stream, nullptr, frames, sorted_idx, mean, std_clipped, (long long)Tf, 0ll, KT, KT,
+            (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl);
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const float* xl, const float* y,
+                              const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,
+                              double* dU, double* dV, double* db, int engine, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(Xa && xl && y && U && V && b, VS_ERR_INVALID, "vs_rrr_closure: null pointer");
+  VS_REQUIRE(!dU || Xb, VS_ERR_INVALID, "vs_rrr_closure: dU needs Xb");
+  VS_REQUIRE(workspace && workspace_bytes >= vs_rrr_workspace(d), VS_ERR_WORKSPACE, "vs_rrr_closure: workspace too small (%zu < %zu)",
+             workspace_bytes, vs_rrr_workspace(d));
+  VS_REQUIRE(((uintptr_t)workspace & 1023) == 0, VS_ERR_INVALID, "vs_rrr_closure: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = carve(d, workspace);
+  const long long KT = d.K * d.T;
+  const int r = (int)d.r;
+  // stage 0: U planes + Gram partials, then G and W = V V^T
+  dim3 g0((unsigned)ceil_div(d.C1, 256), (unsigned)d.N);
+  VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
+  VS_LAUNCH(small_mats_kernel, 1, 64, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
+  // stage 1: Z
+  rc = gemm_f(d, Xa, w, engine, st);
+  if (rc) return rc;
+  // stage 2: residuals, RV, dV partials
+  VS_LAUNCH((epi_f_kernel<false>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, y, xl, V, b, KT, (long long)d.T,
+            (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.R, w.RV, w.pv, nullptr);
+  dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
+  VS_LAUNCH(reduce_k_kernel, g2, 128, 0, st, w.R, xl, b, (long long)d.K, (long long)d.T, (long long)d.N, w.Npad, l2, db, w.sse_tn);
+  VS_LAUNCH(finalize_kernel, 1, 256, 0, st, w.sse_tn, w.pv, w.G, w.W, V, b, (long long)d.K, (long long)d.T, (long long)d.N, r, l2,
+            sse_n, loss, dV);
+  if (dU) {
+    // stage 3/4: Gacc and dU
+    rc = gemm_b(d, Xb, w, engine, st);
+    if (rc) return rc;
+    dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
+    VS_LAUNCH(epi_b_kernel, g4, 256, 0, st, w.Gacc, w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU);
+  }
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl, const double* U, const double* V,
+                              const double* b, double* yhat, int engine, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(Xa && xl && U && V && b && yhat, VS_ERR_INVALID, "vs_rrr_predict: null pointer");
+  VS_REQUIRE(workspace && workspace_bytes >= vs_rrr_workspace(d), VS_ERR_WORKSPACE, "vs_rrr_predict: workspace too small");
+  VS_REQUIRE(((uintptr_t)workspace & 1023) == 0, VS_ERR_INVALID, "vs_rrr_predict: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = carve(d, workspace);
+  const long long KT = d.K * d.T;
+  dim3 g0((unsigned)ceil_div(d.C1, 256), (unsigned)d.N);
+  VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
+            (double*)nullptr);
+  rc = gemm_f(d, Xa, w, engine, st);
+  if (rc) return rc;
+  VS_LAUNCH((epi_f_kernel<true>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, nullptr, xl, V, b, KT, (long long)d.T,
+            (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, yhat);
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_smooth_y(const float* counts, int64_t K, int64_t T, int64_t N, double sigma, const double* mean,
+                               const double* std_clipped, float* y_out, void* stream) {
+  VS_REQUIRE(counts && y_out && K > 0 && T > 0 && N > 0, VS_ERR_INVALID, "vs_rrr_smooth_y: bad arguments");
+  VS_REQUIRE(sigma > 0.0 && (int)(4.0 * sigma + 0.5) <= 32, VS_ERR_UNSUPPORTED, "vs_rrr_smooth_y: sigma out of range");
+  VS_REQUIRE((mean == nullptr) == (std_clipped == nullptr), VS_ERR_INVALID, "vs_rrr_smooth_y: mean and std go together");
+  const long long n = K * T * N;
+  VS_LAUNCH(smooth_y_kernel, (unsigned)ceil_div(n, 256), 256, 0, stream, counts, (long long)K, (long long)T, (long long)N, sigma, mean,
+            std_clipped, y_out);
+  return VS_OK;
+}
+
+extern "C" int vs_colstats_f32(const float* x, int64_t K, int64_t cols, double* mean, double* std_clipped, void* stream) {
+  VS_REQUIRE(x && mean && std_clipped && K > 0 && cols > 0, VS_ERR_INVALID, "vs_colstats_f32: bad arguments");
+  VS_LAUNCH(colstats_f32_kernel, (unsigned)ceil_div(cols, 256), 256, 0, stream, x, (long long)K, (long long)cols, mean, std_clipped);
+  return VS_OK;
+}

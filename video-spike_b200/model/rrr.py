@@ -1,0 +1,277 @@
+"""Reduced-rank regression: drop-in for the reference's src/model/rrr.py.
+
+Same public surface -- `RRRGD(train_data, ncomp, l2)`, `.model` (an nn.ParameterDict with keys
+"{eid}_U" (N,C-1,r), "{eid}_b" (N,1,T), "V" (r,T), float64, initialised under np.random.seed(0)
+exactly as rrr.py:35-49), `predict_y`, `predict_y_fr`, `compute_MSE_RRRGD`, `regression_loss`,
+`state_dict` (rrr.py:64-71), `train_model`, `train_model_main` -- and the same optimiser: ONE
+`torch.optim.LBFGS(...).step(closure)` (rrr.py:177,199).
+
+What changed is the closure.  The reference rebuilds beta = cat(U@V, b) twice, re-uploads X and y
+on every evaluation and differentiates an einsum with autograd (rrr.py:122-155).  Here each split
+of each session is packed ONCE into device-resident bf16 operand planes (vs_rrr_pack) and every
+closure evaluation is one vs_rrr_closure call: two tcgen05 GEMMs plus ordered reductions that
+return the loss and write dU, dV, db straight into `param.grad`.  No CPU path exists.
+
+Precision: `planes` (env VS_RRR_PLANES, default 1) selects how many bf16 residual planes represent
+each tensor-core operand: 1 = plain bf16 (fast path, BASELINE config "bf16"), 3 = ~fp32 operand
+accuracy.  Accumulation is fp32 in TMEM, reductions fp64.  See DESIGN.md "RRR precision".
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import optim
+
+import vsb200 as vs
+
+
+def np2tensor(v):
+    return torch.from_numpy(v)
+
+
+def np2param(v, grad=True):
+    return nn.Parameter(np2tensor(v), requires_grad=grad)
+
+
+def tensor2np(v):
+    return v.numpy()
+
+
+def get_device():
+    """rrr.py:16-26, minus the CPU branch: this implementation only runs on a B200."""
+    vs.require_b200()
+    print("GPU is available")
+    return torch.device("cuda")
+
+
+class _PackedSplit:
+    """Device-resident operands of one (session, split): built once, reused by every closure."""
+
+    CHUNK_BYTES = 1 << 30   # fp64 staging buffer bound for the host->device upload
+
+    def __init__(self, X, y, r, planes, device):
+        X = np.ascontiguousarray(X)
+        K, T, C = X.shape
+        N = y.shape[2]
+        self.K, self.T, self.C1, self.N = K, T, C - 1, N
+        d = vs.RrrDims(K, T, C - 1, N, r, planes, vs.lib.vs_rrr_ldc(C - 1), vs.lib.vs_rrr_ldr(K, T))
+        self.dims = d
+        KT = K * T
+        self.Xa = torch.empty((planes, KT, d.ldc), dtype=torch.bfloat16, device=device)
+        self.Xb = torch.empty((planes, C - 1, d.ldr), dtype=torch.bfloat16, device=device)
+        self.xl = torch.empty(KT, dtype=torch.float32, device=device)
+        rows_per_chunk = max(1, min(KT, self.CHUNK_BYTES // (8 * C)))
+        flat = X.reshape(KT, C)
+        st = vs.stream()
+        for r0 in range(0, KT, rows_per_chunk):
+            r1 = min(KT, r0 + rows_per_chunk)
+            chunk = torch.from_numpy(flat[r0:r1]).to(device=device, dtype=torch.float64)
+            vs.check(vs.lib.vs_rrr_pack(vs.ptr(chunk), r0, r1 - r0, d, vs.ptr(self.Xa), vs.ptr(self.Xb), vs.ptr(self.xl), st))
+            del chunk
+        self.y = torch.from_numpy(np.ascontiguousarray(y)).to(device=device, dtype=torch.float32).contiguous()
+
+    @classmethod
+    def from_device(cls, dims, Xa, Xb, xl, y):
+        """Wrap operands that were produced on the device (vs_rrr_pack_u8 path)."""
+        self = cls.__new__(cls)
+        self.K, self.T, self.C1, self.N = dims.K, dims.T, dims.C1, dims.N
+        self.dims, self.Xa, self.Xb, self.xl, self.y = dims, Xa, Xb, xl, y
+        return self
+
+
+class RRRGD():
+    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None):
+        self.l2 = l2
+        self.eids = list(train_data.keys())
+        self.withbias = True
+        self.planes = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
+        self.engine = int(engine if engine is not None else os.environ.get("VS_ENGINE", str(vs.ENGINE_AUTO)))
+
+        np.random.seed(0)                      # rrr.py:35 -- regardless of the global seed
+        self.N = 0
+        params = {}
+        V = None
+        for eid in train_data:
+            _X = train_data[eid]['X'][0]       # (K, T, ncoef); the last coefficient is the bias column
+            _y = train_data[eid]['y'][0]       # (K, T, N)
+            K, T, ncoef = _X.shape
+            K, T, N = _y.shape
+            U = np.random.normal(size=(N, ncoef - 1, ncomp)) / np.sqrt(T * ncomp)
+            V = np.random.normal(size=(ncomp, T)) / np.sqrt(T * ncomp)   # redrawn per eid, last one kept
+            b = np.ascontiguousarray(np.expand_dims(_y.mean(0).T, 1))
+            params[f"{eid}_U"] = np2param(U)
+            params[f"{eid}_b"] = np2param(b)
+            self.N += N
+        params['V'] = np2param(V)
+        self.n_comp, self.T = params['V'].shape
+        self.model = nn.ParameterDict(params)
+        self._packed = {}
+        self._ws = None
+        self.n_closure_evals = 0
+
+    def train(self):
+        self.model.train()
+
+    def eval(self):
+        self.model.eval()
+
+    def to(self, device):
+        self.model.to(device)
+
+    def state_dict(self):
+        return {"model": {k: v.cpu() for k, v in self.model.state_dict().items()},
+                "l2": self.l2, "eids": self.eids, "N": self.N, "T": self.T, "n_comp": self.n_comp}
+
+    def load_state_dict(self, f):
+        self.model.load_state_dict(f)
+
+    # ---- reference helpers kept for API compatibility (small torch ops, not on the hot path) ----
+    def compute_beta_m(self, U, V, b, withbias=True, tonp=False):
+        if tonp:
+            U, V = np2tensor(U), np2tensor(V)
+        beta = U @ V
+        if withbias:
+            if tonp:
+                b = np2tensor(b)
+        else:
+            b = torch.zeros((U.shape[0], 1, V.shape[1]), dtype=beta.dtype, device=beta.device)
+        beta = torch.cat((beta, b), 1)
+        return tensor2np(beta) if tonp else beta
+
+    def compute_beta(self, eid, withbias=True):
+        return self.compute_beta_m(self.model[f"{eid}_U"], self.model['V'], self.model[f"{eid}_b"], withbias=withbias)
+
+    def predict(self, beta, X, tonp=False):
+        if tonp:
+            X, beta = np2tensor(X), np2tensor(beta)
+        y_pred = torch.einsum("ktc,nct->ktn", X, beta)
+        return tensor2np(y_pred) if tonp else y_pred
+
+    # ---- device-resident data --------------------------------------------------------------
+    def _device(self):
+        dev = self.model['V'].device
+        if dev.type != "cuda":
+            raise vs.VsError("RRRGD parameters are not on a CUDA device: call .to(get_device()) first (no CPU path)")
+        return dev
+
+    def _split(self, data, eid, k):
+        X = data[eid]['X'][k]
+        if isinstance(X, _PackedSplit):
+            return X
+        key = (eid, k, id(X))
+        hit = self._packed.get(key)
+        if hit is None:
+            hit = _PackedSplit(X, data[eid]['y'][k], self.n_comp, self.planes, self._device())
+            self._packed[key] = hit
+        return hit
+
+    def _workspace(self, dims):
+        need = int(vs.lib.vs_rrr_workspace(dims))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self._device())
+        off = (-self._ws.data_ptr()) % 1024
+        return self._ws[off:off + need]
+
+    def _closure_eval(self, data, eid, k, want_grad, dV=None):
+        """loss (0-dim), sse_n (N,) and -- if want_grad -- dU, db written into .grad, dV accumulated."""
+        sp = self._split(data, eid, k)
+        U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
+        dev = V.device
+        loss = torch.empty(1, dtype=torch.float64, device=dev)
+        sse = torch.empty(sp.N, dtype=torch.float64, device=dev)
+        dU = db = None
+        if want_grad:
+            dU, db = torch.empty_like(U), torch.empty_like(b)
+        ws = self._workspace(sp.dims)
+        vs.check(vs.lib.vs_rrr_closure(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
+                                       vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
+                                       vs.ptr(dV), vs.ptr(db), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
+        return loss[0], sse, dU, db
+
+    def loss_and_grad(self, data, k=0):
+        """The closure body of rrr.py:165-175: total loss over sessions, gradients into .grad."""
+        V = self.model['V']
+        dV = torch.zeros_like(V)
+        total = None
+        for eid in data:
+            loss, _, dU, db = self._closure_eval(data, eid, k, True, dV)
+            self.model[f"{eid}_U"].grad = dU
+            self.model[f"{eid}_b"].grad = db
+            total = loss if total is None else total + loss
+        V.grad = dV
+        self.n_closure_evals += 1
+        return total
+
+    # ---- reference API ------------------------------------------------------------------------
+    def predict_y(self, data, eid, k):
+        """rrr.py:122-130.  Returns (X, y, ypred); y / ypred are float64 CUDA tensors.  X is returned
+        as the caller's own array wrapped in a CPU tensor (the reference copies it to the device on
+        every call; no caller in the reference uses that copy)."""
+        sp = self._split(data, eid, k)
+        U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
+        yhat = torch.empty((sp.K, sp.T, sp.N), dtype=torch.float64, device=V.device)
+        ws = self._workspace(sp.dims)
+        vs.check(vs.lib.vs_rrr_predict(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.xl), vs.ptr(U.data), vs.ptr(V.data), vs.ptr(b.data),
+                                       vs.ptr(yhat), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
+        Xraw = data[eid]['X'][k]
+        X = np2tensor(Xraw) if isinstance(Xraw, np.ndarray) else None
+        y = np2tensor(np.ascontiguousarray(data[eid]['y'][k])).to(V.device) if isinstance(data[eid]['y'][k], np.ndarray) \
+            else sp.y.double()
+        return X, y, yhat
+
+    def predict_y_fr(self, data, eid, k):
+        """rrr.py:136-142: back to firing-rate units with the stored z-score statistics."""
+        X, y, ypred = self.predict_y(data, eid, k)
+        mean_y = torch.as_tensor(data[eid]['setup']['mean_y_TN']).to(y.device)
+        std_y = torch.as_tensor(data[eid]['setup']['std_y_TN']).to(y.device)
+        return X, y * std_y + mean_y, ypred * std_y + mean_y
+
+    def compute_MSE_RRRGD(self, data, k):
+        """rrr.py:147-152: {eid: per-neuron sum of squared residuals (N,)}."""
+        return {eid: self._closure_eval(data, eid, k, False)[1] for eid in data}
+
+    def regression_loss(self):
+        """rrr.py:154-155: {eid: l2 * sum(beta^2)} -- evaluated from the r x r Gram matrices, beta is
+        never materialised: sum (U V)^2 = <U^T U, V V^T>."""
+        V = self.model['V']
+        W = V @ V.T
+        out = {}
+        for eid in self.eids:
+            U, b = self.model[f"{eid}_U"], self.model[f"{eid}_b"]
+            G = torch.einsum("nci,ncj->ij", U, U)
+            out[eid] = self.l2 * (torch.sum(G * W) + torch.sum(b ** 2))
+        return out
+
+
+def train_model(model, train_data, optimizer, model_fname, save=True):
+    """rrr.py:164-190: one optimizer.step(closure) on split 0, validation SSE on split 1."""
+    def closure():
+        optimizer.zero_grad()
+        model.train()
+        return model.loss_and_grad(train_data, 0)
+
+    optimizer.step(closure)
+
+    model.eval()
+    mses_val = model.compute_MSE_RRRGD(train_data, 1)
+    best_loss = torch.sum(torch.cat([mses_val[k] for k in mses_val]))
+
+    if save:
+        print('saving model')
+        torch.save({"RRRGD_model": model.state_dict(), "optimizer": optimizer.state_dict()}, model_fname)
+
+    return model, {"mses_val": mses_val, "mse_val_mean": best_loss}
+
+
+def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None, engine=None):
+    """rrr.py:192-202."""
+    area_model = RRRGD(train_data, n_comp, l2=l2, planes=planes, engine=engine)
+    device = get_device()
+    area_model.to(device)
+    print(f"training on device: {device}")
+    optimizer = optim.LBFGS(area_model.model.parameters(),)
+    _, mse_val = train_model(area_model, train_data, optimizer, model_fname=model_fname, save=save)
+    return area_model, mse_val

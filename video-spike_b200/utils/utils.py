@@ -1,0 +1,93 @@
+"""Host-side helpers with the behaviour of the reference's src/utils/utils.py for the symbols the
+hot path touches: model registry (:28-34), CLI flags (:36-47), seeding (:49-59), batch device move
+(:61-66), z-score statistics (:107-112), one-hot (:114-119) and the per-epoch metric loop (:122-181).
+CEBRA / PCA / plotting helpers of that file are outside the hot path and not provided.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+
+import numpy as np
+import torch
+from sklearn.metrics import r2_score as r2_score_sklearn
+
+from model.linear import Linear
+from model.rrr import train_model, train_model_main  # noqa: F401  (re-exported like the reference)
+from utils.metric_utils import bits_per_spike
+
+NAME2MODEL = {"Linear": Linear}
+
+
+def get_args(argv=None):
+    p = argparse.ArgumentParser(description="IBL Spike Video Project")
+    p.add_argument("--model_config", type=str, default="configs/model/model_config.yaml", help="Model config file")
+    p.add_argument("--train_config", type=str, default="configs/train/train_config.yaml", help="Train config file")
+    p.add_argument("--seed", type=int, default=42, help="Random seed")
+    p.add_argument("--log_dir", type=str, default="logs", help="Log directory")
+    p.add_argument("--eid", type=str, default="d57df551-6dcb-4242-9c72-b806cff5613a")
+    p.add_argument("--input_mod", type=str, default="whisker-motion-energy", help="Input modality")
+    p.add_argument("--model", type=str, default="cm", help="Model name")
+    p.add_argument("--save_plot", action="store_true", help="Save plot")
+    return p.parse_args(argv)
+
+
+def set_seed(seed):
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    print("seed set to {}".format(seed))
+
+
+def move_batch_to_device(batch, device):
+    for key, val in batch.items():
+        if isinstance(val, torch.Tensor):
+            batch[key] = val.to(device, non_blocking=True)
+    return batch
+
+
+def _std(arr):
+    mean = np.mean(arr, axis=0)
+    std = np.clip(np.std(arr, axis=0), 1e-8, None)
+    return (arr - mean) / std, mean, std
+
+
+def _one_hot(arr, T):
+    levels = np.sort(np.unique(arr))
+    out = np.zeros((len(arr), T, len(levels)))
+    for i, lvl in enumerate(levels):
+        out[:, :, i] = arr == lvl
+    return out
+
+
+def metrics_list(gt, pred, metrics=("bps", "rsquared"), device="cpu"):
+    """gt / pred arrive as (N, T, K) (the trainer transposes, src/trainer/base.py:190-191).
+
+    Kept on purpose: both loops run over gt.shape[-1] -- the TRIAL count -- while "bps"
+    indexes the neuron axis of the re-transposed arrays, so it covers the first K neurons and raises
+    IndexError when K > N; "rsquared" is sklearn's R2 of the (N, T) slice of trial i."""
+    results = {}
+    if "bps" in metrics:
+        g = gt.transpose(-1, 0).cpu().numpy()
+        p = pred.transpose(-1, 0).cpu().numpy()
+        vals = []
+        for i in range(gt.shape[-1]):
+            bps = bits_per_spike(p[:, :, [i]], g[:, :, [i]])
+            vals.append(np.nan if np.isinf(bps) else bps)
+        results["bps"] = np.nanmean(vals)
+    if "rsquared" in metrics:
+        g, p = gt.cpu().clone(), pred.cpu().numpy()
+        vals = [r2_score_sklearn(y_true=g[:, :, i], y_pred=p[:, :, i]) for i in range(gt.shape[-1])]
+        results["rsquared"] = np.nanmean(vals)
+    if "mse" in metrics:
+        results["mse"] = torch.mean((gt - pred) ** 2)
+    if "mae" in metrics:
+        results["mae"] = torch.mean(torch.abs(gt - pred))
+    return results

@@ -1,0 +1,153 @@
+"""ctypes binding of libvs_b200.so (include/vs_b200.h) -- the only door from the Python host
+code into the sm_100a kernels.  PyTorch supplies device memory and streams; every pointer handed
+to the library is `tensor.data_ptr()` of a CUDA tensor owned by the caller.
+
+There is NO CPU fallback: importing this module without the built library raises, and every
+wrapper raises if a tensor is not on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvs_b200.so")
+
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+MAX_LAYERS = 16
+
+
+class VsError(RuntimeError):
+    pass
+
+
+class AdamWHyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int32)]
+
+
+class Mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int64 * (MAX_LAYERS + 1)), ("relu", C.c_int32 * MAX_LAYERS)] + \
+               [(name, C.c_void_p * MAX_LAYERS) for name in
+                ("W", "b", "mW", "vW", "mb", "vb", "act", "gact", "gW", "gb")]
+
+
+class RrrDims(C.Structure):
+    _fields_ = [("K", C.c_int64), ("T", C.c_int64), ("C1", C.c_int64), ("N", C.c_int64), ("r", C.c_int64),
+                ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C video-spike_b200/csrc`).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
+    sig = {
+        "vs_version": (C.c_int, []),
+        "vs_last_error": (C.c_char_p, []),
+        "vs_device_ok": (C.c_int, []),
+        "vs_u8_to_f32": (C.c_int, [vp, vp, i64, vp]),
+        "vs_u8_to_bf16": (C.c_int, [vp, vp, i64, vp]),
+        "vs_linear_fwd_workspace": (sz, [i64, i64, i64]),
+        "vs_linear_fwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, sz, vp]),
+        "vs_linear_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]),
+        "vs_poisson_nll": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+        "vs_adamw": (C.c_int, [vp, vp, vp, vp, i64, AdamWHyper, vp]),
+        "vs_dw_adamw_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, AdamWHyper, vp]),
+        "vs_mlp_workspace": (sz, [C.POINTER(Mlp), i64]),
+        "vs_mlp_train_step": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, AdamWHyper, vp, i32, vp, sz, vp]),
+        "vs_mlp_forward": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, vp, i32, vp, sz, vp]),
+        "vs_rrr_ldc": (i64, [i64]),
+        "vs_rrr_ldr": (i64, [i64, i64]),
+        "vs_rrr_pack": (C.c_int, [vp, i64, i64, RrrDims, vp, vp, vp, vp]),
+        "vs_rrr_colstats": (C.c_int, [vp, i64, i64, vp, vp, vp]),
+        "vs_rrr_pack_u8": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, vp, vp, vp]),
+        "vs_rrr_smooth_y": (C.c_int, [vp, i64, i64, i64, dbl, vp, vp, vp, vp]),
+        "vs_colstats_f32": (C.c_int, [vp, i64, i64, vp, vp, vp]),
+        "vs_rrr_workspace": (sz, [RrrDims]),
+        "vs_rrr_closure": (C.c_int, [RrrDims, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
+        "vs_rrr_predict": (C.c_int, [RrrDims, vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
+        "vs_gemm_tn": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]),
+        "vs_launch_count": (i64, []),
+        "vs_launch_count_reset": (None, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib, tuple(sig.keys())
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise VsError(f"libvs_b200 error {rc}: {lib.vs_last_error().decode()}")
+
+
+def ptr(t):
+    """Raw device pointer of a CUDA tensor (None -> NULL).  Refuses CPU tensors: no fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise VsError("libvs_b200 only takes CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise VsError("libvs_b200 needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_b200() -> None:
+    if not torch.cuda.is_available():
+        raise VsError("no CUDA device: video-spike_b200 has no CPU path")
+    if not lib.vs_device_ok():
+        raise VsError("video-spike_b200 kernels are built for sm_100a (B200) only")
+
+
+# ---------------------------------------------------------------- thin typed wrappers
+def u8_to_f32(frames: torch.Tensor) -> torch.Tensor:
+    """src/loader/base.py:39,54 -- uint8 frames -> float32, values stay 0..255."""
+    assert frames.dtype == torch.uint8
+    out = torch.empty(frames.shape, dtype=torch.float32, device=frames.device)
+    if frames.numel():
+        check(lib.vs_u8_to_f32(ptr(frames), ptr(out), frames.numel(), stream()))
+    return out
+
+
+def u8_to_bf16(frames: torch.Tensor) -> torch.Tensor:
+    assert frames.dtype == torch.uint8
+    out = torch.empty(frames.shape, dtype=torch.bfloat16, device=frames.device)
+    if frames.numel():
+        check(lib.vs_u8_to_bf16(ptr(frames), ptr(out), frames.numel(), stream()))
+    return out
+
+
+def poisson_nll(logits: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
+    """Returns (loss_sum double[1], dlogits or None); mean loss = loss_sum / numel."""
+    loss = torch.empty(1, dtype=torch.float64, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    check(lib.vs_poisson_nll(ptr(logits), ptr(target), ptr(loss), ptr(dl), logits.numel(), stream()))
+    return loss, dl
+
+
+def adamw(p, g, m, v, hyper: AdamWHyper) -> None:
+    check(lib.vs_adamw(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), hyper, stream()))
+
+
+def gemm_tn(A: torch.Tensor, B: torch.Tensor, engine: int = ENGINE_AUTO) -> torch.Tensor:
+    """C = A @ B.T for K-major A (M,K), B (N,K); bf16 or fp32(tf32) operands.  Test hook."""
+    assert A.dtype == B.dtype and A.dtype in (torch.bfloat16, torch.float32)
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(lib.vs_gemm_tn(ptr(A), ptr(B), ptr(Cm), M, N, K, A.stride(0), B.stride(0), N,
+                         0 if A.dtype == torch.bfloat16 else 1, engine, stream()))
+    return Cm
