@@ -87,8 +87,8 @@ int vs_poisson_nll(const float* logits, const float* target, double* loss_sum, f
  *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  * lr and beta1 are per-step arguments because OneCycleLR cycles both.       */
 typedef struct {
-  float lr, beta1, beta2, eps, weight_decay;
-  int32_t step; /* 1-based step count AFTER this update (torch's state['step']) */
+  double lr, beta1, beta2, eps, weight_decay; /* doubles: torch derives 1-beta, lr*wd, ... from Python floats */
+  int64_t step; /* 1-based step count AFTER this update (torch's state['step']) */
 } vs_adamw_hyper;
 
 int vs_adamw(float* p, const float* g, float* m, float* v, int64_t n, vs_adamw_hyper h, void* stream);

@@ -1,0 +1,190 @@
+"""-m gpu: every kernel behind the C-ABI against the CPU oracle / exact arithmetic.
+Bit-exact for the byte/index work (loader, frame selection), stated tolerances for floating point."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vs(cuda):
+    import vsb200
+    return vsb200
+
+
+# ----------------------------------------------------------------------------- loader (L1/L2)
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 7, 1024, 120 * 32 * 32 * 3 + 5])
+def test_loader_bit_exact(vs, cuda, n):
+    g = torch.Generator().manual_seed(n)
+    frames = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+    d = frames.to(cuda)
+    # reference: .float() keeps 0..255 (src/loader/base.py:39)
+    assert torch.equal(vs.u8_to_f32(d).cpu(), frames.float())
+    assert torch.equal(vs.u8_to_bf16(d).cpu(), frames.float().to(torch.bfloat16))
+
+
+def test_loader_full_frame_batch(vs, cuda):
+    frames = torch.randint(0, 256, (16, 120, 1, 128, 128), dtype=torch.uint8, device=cuda)
+    out = vs.u8_to_f32(frames)
+    assert out.shape == frames.shape and torch.equal(out, frames.float())
+    assert float(out.max()) <= 255.0 and float(out.min()) >= 0.0          # never rescaled
+
+
+def test_cpu_tensor_is_refused(vs):
+    with pytest.raises(vs.VsError):
+        vs.u8_to_f32(torch.zeros(8, dtype=torch.uint8))
+
+
+# ----------------------------------------------------------------------------- GEMM engines
+def _gemm_ref(A, B):
+    return A.double() @ B.double().t()
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (70, 33, 50), (16, 600, 256), (256, 16, 4099)])
+def test_gemm_simt(vs, cuda, M, N, K):
+    torch.manual_seed(0)
+    A, B = torch.randn(M, K, device=cuda), torch.randn(N, K, device=cuda)
+    Cm = vs.gemm_tn(A, B, vs.ENGINE_SIMT)
+    torch.testing.assert_close(Cm.double(), _gemm_ref(A, B), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 64), (128, 64, 256), (256, 16, 8192), (300, 432, 1000), (130, 448, 520),
+                                   (1000, 1344, 192), (128, 256, 64), (128, 272, 128)])
+def test_gemm_tcgen05_bf16(vs, cuda, M, N, K):
+    """tensor-core engine vs exact: bf16 products are exact in fp32, only the summation order differs."""
+    torch.manual_seed(1)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device=cuda, dtype=torch.bfloat16); A[:, :K] = torch.randn(M, K, device=cuda)
+    B = torch.zeros(N, Kp, device=cuda, dtype=torch.bfloat16); B[:, :K] = torch.randn(N, K, device=cuda)
+    Cm = vs.gemm_tn(A, B, vs.ENGINE_TCGEN05)
+    torch.testing.assert_close(Cm.double(), _gemm_ref(A, B), rtol=1e-4, atol=2e-3)
+    Cs = vs.gemm_tn(A, B, vs.ENGINE_SIMT)
+    torch.testing.assert_close(Cm, Cs, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (256, 16, 4096), (256, 48, 10000), (200, 100, 260)])
+def test_gemm_tcgen05_tf32(vs, cuda, M, N, K):
+    """tf32 path: integer-valued B (like 0..255 frames) is exact, A is rounded to 10 mantissa bits."""
+    torch.manual_seed(2)
+    A = torch.randn(M, K, device=cuda)
+    B = torch.randint(0, 256, (N, K), device=cuda).float()
+    Cm = vs.gemm_tn(A, B, vs.ENGINE_TCGEN05)
+    ref = _gemm_ref(A, B)
+    scale = (A.double().abs() @ B.double().t())
+    assert float(((Cm.double() - ref).abs() / scale).max()) < 6e-4     # 2^-11 per product, worst case
+    # and exactly the fp32 result when A is already representable in tf32
+    At = (A.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    Ct = vs.gemm_tn(At.contiguous(), B, vs.ENGINE_TCGEN05)
+    reft = _gemm_ref(At, B)
+    assert float(((Ct.double() - reft).abs() / scale).max()) < 2e-6    # fp32 accumulation only
+
+
+# ----------------------------------------------------------------------------- Linear layer fwd/bwd
+@pytest.mark.parametrize("batch,in_dim,out_dim,relu", [(16, 256, 128, 1), (5, 64, 128, 0), (16, 256, 1400, 0), (3, 120, 256, 1)])
+def test_linear_fwd_bwd_small(vs, cuda, batch, in_dim, out_dim, relu):
+    torch.manual_seed(3)
+    x = torch.randn(batch, in_dim, device=cuda)
+    W = torch.randn(out_dim, in_dim, device=cuda) / math.sqrt(in_dim)
+    b = torch.randn(out_dim, device=cuda)
+    y = torch.empty(batch, out_dim, device=cuda)
+    vs.check(vs.lib.vs_linear_fwd(vs.ptr(x), None, vs.ptr(W), vs.ptr(b), vs.ptr(y), batch, in_dim, out_dim, relu, 0, None, 0, vs.stream()))
+    ref = x @ W.t() + b
+    if relu:
+        ref = ref.clamp_min(0)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+    dy = torch.randn(batch, out_dim, device=cuda)
+    gm = torch.empty_like(dy); dx = torch.empty_like(x); dW = torch.empty_like(W); db = torch.empty_like(b)
+    vs.check(vs.lib.vs_linear_bwd(vs.ptr(dy), vs.ptr(y), vs.ptr(x), None, vs.ptr(W), vs.ptr(gm), vs.ptr(dx), vs.ptr(dW), vs.ptr(db),
+                                  batch, in_dim, out_dim, relu, vs.stream()))
+    g = dy * (ref > 0) if relu else dy
+    torch.testing.assert_close(dW, g.t() @ x, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(db, g.sum(0), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dx, g @ W, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("batch,D", [(16, 120 * 16 * 16), (4, 8192), (16, 120 * 32 * 32 + 4)])
+def test_first_layer_fwd_from_u8(vs, cuda, engine, batch, D):
+    """tall contraction over pixels, uint8 frames in, both engines, vs fp64."""
+    torch.manual_seed(4)
+    frames = torch.randint(0, 256, (batch, D), dtype=torch.uint8, device=cuda)
+    W = (torch.rand(256, D, device=cuda) * 2 - 1) / math.sqrt(D)
+    b = torch.randn(256, device=cuda) * 0.01
+    y = torch.empty(batch, 256, device=cuda)
+    ws = torch.empty(vs.lib.vs_linear_fwd_workspace(batch, D, 256), dtype=torch.uint8, device=cuda)
+    vs.check(vs.lib.vs_linear_fwd(None, vs.ptr(frames), vs.ptr(W), vs.ptr(b), vs.ptr(y), batch, D, 256, 1, engine, vs.ptr(ws), ws.numel(), vs.stream()))
+    ref = (frames.double() @ W.double().t() + b.double()).clamp_min(0)
+    tol = 2e-4 if engine == 1 else 2e-2        # tf32 rounds W to 10 bits: |err| <~ 2^-11 * sum|w x|/sqrt(D) ...
+    torch.testing.assert_close(y.double(), ref, rtol=1e-3, atol=tol * float(ref.abs().max()))
+
+
+# ----------------------------------------------------------------------------- Poisson / AdamW
+@pytest.mark.parametrize("n", [5, 16 * 100 * 144, 4 * 100 * 7 + 3])
+def test_poisson_nll(vs, cuda, n):
+    torch.manual_seed(5)
+    x = torch.randn(n, device=cuda) * 0.5
+    t = torch.poisson(torch.full((n,), 0.3, device=cuda))
+    loss, dx = vs.poisson_nll(x, t)
+    crit = torch.nn.PoissonNLLLoss(reduction="none", log_input=True)
+    ref = crit(x.double(), t.double())
+    assert float(loss[0]) / n == pytest.approx(float(ref.mean()), rel=1e-6)
+    torch.testing.assert_close(dx.double(), (torch.exp(x.double()) - t.double()) / n, rtol=1e-5, atol=1e-10)
+    # KAT from SURVEY section 4: x=[0.5,-1], y=[2,0] -> [0.6487, 0.3679]
+    xk = torch.tensor([0.5, -1.0, 0.0, 0.0], device=cuda); tk = torch.tensor([2.0, 0.0, 0.0, 0.0], device=cuda)
+    lk, _ = vs.poisson_nll(xk, tk, want_grad=False)
+    assert float(lk[0]) == pytest.approx(math.exp(0.5) - 1.0 + math.exp(-1.0) + 2.0, rel=1e-6)
+
+
+@pytest.mark.parametrize("n", [7, 4096, 100003])
+def test_adamw_matches_torch(vs, cuda, n):
+    torch.manual_seed(6)
+    p = torch.randn(n, device=cuda); p_ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([p_ref], lr=5e-5, weight_decay=0.01, eps=1e-8, betas=(0.95, 0.999))
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(n, device=cuda) * 1e-3
+        beta1 = 0.95 - 0.03 * step                      # OneCycleLR cycles beta1
+        lr = 5e-6 * step
+        opt.param_groups[0]["betas"] = (beta1, 0.999); opt.param_groups[0]["lr"] = lr
+        p_ref.grad = g.clone(); opt.step()
+        vs.adamw(p, g, m, v, vs.AdamWHyper(lr, beta1, 0.999, 1e-8, 0.01, step))
+        torch.testing.assert_close(p, p_ref.data, rtol=1e-6, atol=1e-8)
+    st = opt.state[p_ref]
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-10)
+    torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-14)
+
+
+@pytest.mark.parametrize("batch,in_dim,out_dim,u8", [(16, 120 * 16 * 16, 256, True), (4, 2048, 256, False), (32, 4100, 64, True), (8, 1024, 256, True)])
+def test_dw_adamw_fused(vs, cuda, batch, in_dim, out_dim, u8):
+    """G1+O1: same result as materialising dW = dy^T x and running torch.optim.AdamW on it."""
+    torch.manual_seed(7)
+    x8 = torch.randint(0, 9, (batch, in_dim), dtype=torch.uint8, device=cuda)
+    xf = x8.float() if u8 else torch.randn(batch, in_dim, device=cuda)
+    dy = torch.randn(batch, out_dim, device=cuda) * 1e-4
+    W = torch.randn(out_dim, in_dim, device=cuda) * 0.01
+    m = torch.randn_like(W) * 1e-4; v = torch.rand_like(W) * 1e-8
+    Wr = torch.nn.Parameter(W.clone())
+    opt = torch.optim.AdamW([Wr], lr=3e-5, weight_decay=0.01, eps=1e-8, betas=(0.93, 0.999))
+    Wr.grad = dy.t() @ xf
+    opt.state[Wr] = {"step": torch.tensor(4.0), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+    opt.step()
+    vs.check(vs.lib.vs_dw_adamw_fused(vs.ptr(dy), None if u8 else vs.ptr(xf), vs.ptr(x8) if u8 else None, vs.ptr(W), vs.ptr(m), vs.ptr(v),
+                                      batch, in_dim, out_dim, vs.AdamWHyper(3e-5, 0.93, 0.999, 1e-8, 0.01, 5), vs.stream()))
+    torch.testing.assert_close(W, Wr.data, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(m, opt.state[Wr]["exp_avg"], rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(v, opt.state[Wr]["exp_avg_sq"], rtol=1e-4, atol=1e-13)
+
+
+def test_error_paths(vs, cuda):
+    x = torch.zeros(8, device=cuda)
+    rc = vs.lib.vs_adamw(vs.ptr(x), vs.ptr(x), vs.ptr(x), vs.ptr(x), 8, vs.AdamWHyper(1e-3, 0.9, 0.999, 1e-8, 0.0, 0), vs.stream())
+    assert rc == 1 and b"step" in vs.lib.vs_last_error()
+    rc = vs.lib.vs_dw_adamw_fused(vs.ptr(x), vs.ptr(x), None, vs.ptr(x), vs.ptr(x), vs.ptr(x), 64, 8, 1,
+                                  vs.AdamWHyper(1e-3, 0.9, 0.999, 1e-8, 0.0, 1), vs.stream())
+    assert rc == 3
+    rc = vs.lib.vs_linear_fwd(vs.ptr(x), None, vs.ptr(x), None, vs.ptr(x), 1, 8192, 1, 0, 0, None, 0, vs.stream())
+    assert rc == 4                                             # workspace too small

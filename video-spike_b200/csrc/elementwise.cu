@@ -97,15 +97,15 @@ struct AdamConsts {
 
 static AdamConsts make_consts(const vs_adamw_hyper& h) {
   // scalars in double like the Python floats torch.optim.AdamW computes them with
-  const double bc1 = 1.0 - pow((double)h.beta1, (double)h.step);
-  const double bc2 = 1.0 - pow((double)h.beta2, (double)h.step);
+  const double bc1 = 1.0 - pow(h.beta1, (double)h.step);
+  const double bc2 = 1.0 - pow(h.beta2, (double)h.step);
   AdamConsts c;
-  c.decay = (float)(1.0 - (double)h.lr * (double)h.weight_decay);
-  c.beta1 = h.beta1; c.w1 = (float)(1.0 - (double)h.beta1);
-  c.beta2 = h.beta2; c.w2 = (float)(1.0 - (double)h.beta2);
-  c.step_size = (float)((double)h.lr / bc1);
+  c.decay = (float)(1.0 - h.lr * h.weight_decay);
+  c.beta1 = (float)h.beta1; c.w1 = (float)(1.0 - h.beta1);
+  c.beta2 = (float)h.beta2; c.w2 = (float)(1.0 - h.beta2);
+  c.step_size = (float)(h.lr / bc1);
   c.inv_bc2s = (float)(1.0 / sqrt(bc2));
-  c.eps = h.eps;
+  c.eps = (float)h.eps;
   return c;
 }
 

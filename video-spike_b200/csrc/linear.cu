@@ -165,7 +165,9 @@ extern "C" int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const
   for (int l = 0; l < L; ++l) {
     const float* xin = l == 0 ? x_f32 : net->act[l - 1];
     const uint8_t* xu = l == 0 && !x_f32 ? frames_u8 : nullptr;
-    rc = vs_linear_fwd(xin, xu, net->W[l], net->b[l], net->act[l], batch, net->dims[l], net->dims[l + 1], net->relu[l], engine,
+    // `engine` selects the engine of the tall (pixel) contraction; the small layers always take the SIMT kernels
+    const int eng = net->dims[l] >= kBigK ? engine : VS_ENGINE_AUTO;
+    rc = vs_linear_fwd(xin, xu, net->W[l], net->b[l], net->act[l], batch, net->dims[l], net->dims[l + 1], net->relu[l], eng,
                        workspace, workspace_bytes, stream);
     if (rc) return rc;
   }

@@ -196,7 +196,8 @@ __global__ void small_mats_kernel(const double* __restrict__ Gp, long long nbloc
 // block = 32 rows (k,t) x all neurons (looped in tiles of 32).  Phase 1 (lanes over n): yhat, R, dV partials.
 // Phase 2 (lanes over rows): RV[p][(j,n)][row] = planes of V[j,t] * R   (B operand of GEMM-B).
 template <bool kPredict>
-__global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, const float* __restrict__ y,
+__global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, int splits, long long split_stride,
+                                                    const float* __restrict__ y,
                                                     const float* __restrict__ xl, const double* __restrict__ V,
                                                     const double* __restrict__ b, long long KT, long long T, long long N,
                                                     long long Npad, int r, int planes, long long ldr, float* __restrict__ R,
@@ -229,7 +230,14 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
         float acc = xl[row] * (float)b[n * T + t];
         float z[kMaxR];
         for (int j = 0; j < r; ++j) {
-          z[j] = Z[row * ldz + (long long)j * Npad + n];
+          const float* zp = Z + row * ldz + (long long)j * Npad + n;
+          if (splits == 1) {
+            z[j] = *zp;
+          } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator
+            double zs = 0.0;
+            for (int sp = 0; sp < splits; ++sp) zs += (double)zp[(long long)sp * split_stride];
+            z[j] = (float)zs;
+          }
           acc = fmaf(Vs[rl][j], z[j], acc);
         }
         if constexpr (kPredict) {
@@ -339,7 +347,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
 
 // ------------------------------------------------------------------ closure stage 4: epilogue of GEMM-B
 // dU[n][c][j] = 2 Gacc[c][(j,n)] + 2 l2 sum_j' U[n][c][j'] W[j'][j]; 32 c x 32 n tile, smem transpose
-__global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Gacc, long long ldg, const double* __restrict__ U,
+__global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Gacc, long long ldg, int splits,
+                                                    long long split_stride, const double* __restrict__ U,
                                                     const double* __restrict__ W, long long C1, long long N, long long Npad, int r,
                                                     double l2, double* __restrict__ dU) {
   __shared__ float Gs[kMaxR][32][33];
@@ -350,7 +359,12 @@ __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Ga
   for (int i = 0; i < 4; ++i) {
     const int cl = w + 8 * i;
     const long long c = c0 + cl, n = n0 + lane;
-    for (int j = 0; j < r; ++j) Gs[j][cl][lane] = (c < C1 && n < N) ? Gacc[c * ldg + (long long)j * Npad + n] : 0.f;
+    for (int j = 0; j < r; ++j) {
+      double gsum = 0.0;
+      if (c < C1 && n < N)
+        for (int sp = 0; sp < splits; ++sp) gsum += (double)Gacc[(long long)sp * split_stride + c * ldg + (long long)j * Npad + n];
+      Gs[j][cl][lane] = (float)gsum;
+    }
   }
   __syncthreads();
   const long long c = c0 + lane;
@@ -375,8 +389,19 @@ struct Ws {
   float *Z, *R, *Gacc, *pv;
   double *Gp, *G, *W, *sse_tn;
   long long Npad, ldz, gp_blocks;
+  int splits_f, splits_b;  // split-K factors of the two GEMMs
   size_t total;
 };
+
+// The tensor cores accumulate in fp32 with truncation, so a long contraction drifts by about
+// (#MMA steps) * 2^-24.  That is far below bf16 operand noise (planes == 1) but not below the
+// ~2^-24 the 3-plane mode is after: there each TMEM accumulation run is limited to 16 k-blocks and
+// the partial tiles are summed in fp64 by the epilogue kernels.
+static int hp_splits(long long k_elems, int planes) {
+  if (planes < 2) return 1;
+  long long s = ceil_div(ceil_div(k_elems, 64), 16);
+  return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));
+}
 
 static Ws carve(const vs_rrr_dims& d, void* base) {
   Ws w;
@@ -384,14 +409,16 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.Npad = round_up(d.N, 16);
   w.ldz = d.r * w.Npad;
   w.gp_blocks = ceil_div(d.C1, 256) * d.N;
+  w.splits_f = hp_splits(d.C1, d.planes);
+  w.splits_b = hp_splits(KT, d.planes);
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += (size_t)round_up((long long)bytes, 1024); return q; };
   w.Ub = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldc * 2);
   w.RV = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldr * 2);
-  w.Z = (float*)take((size_t)KT * w.ldz * 4);
+  w.Z = (float*)take((size_t)w.splits_f * KT * w.ldz * 4);
   w.R = (float*)take((size_t)KT * w.Npad * 4);
-  w.Gacc = (float*)take((size_t)d.C1 * w.ldz * 4);
+  w.Gacc = (float*)take((size_t)w.splits_b * d.C1 * w.ldz * 4);
   w.pv = (float*)take((size_t)KT * d.r * 4);
   w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
   w.G = (double*)take(kMaxR * kMaxR * 8);
@@ -411,14 +438,19 @@ static int check_dims(const vs_rrr_dims& d) {
 }
 
 static void set_passes(tc::GemmDesc& g, int planes) {
-  // plane products kept: everything down to ~2^-8(planes) relative
-  static const int pa3[6] = {0, 0, 1, 0, 1, 2}, pb3[6] = {0, 1, 0, 2, 1, 0};
-  g.n_pass = planes == 1 ? 1 : (planes == 2 ? 3 : 6);
-  for (int i = 0; i < g.n_pass; ++i) { g.pa[i] = pa3[i]; g.pb[i] = pb3[i]; }
+  // plane products kept: everything down to ~2^-8(planes) relative.  Small corrections first, the
+  // dominant (0,0) product last: the accumulator is truncated at every MMA, so it should be small
+  // for as many of those truncations as possible.
+  static const int pa3[6] = {2, 1, 0, 1, 0, 0}, pb3[6] = {0, 1, 2, 0, 1, 0};
+  static const int pa2[3] = {1, 0, 0}, pb2[3] = {0, 1, 0};
+  if (planes == 1) { g.n_pass = 1; g.pa[0] = g.pb[0] = 0; return; }
+  g.n_pass = planes == 2 ? 3 : 6;
+  for (int i = 0; i < g.n_pass; ++i) { g.pa[i] = planes == 2 ? pa2[i] : pa3[i]; g.pb[i] = planes == 2 ? pb2[i] : pb3[i]; }
 }
 
 // Z = Xa * Ub^T  (M = K*T, N = r*Npad, contraction C1)
-static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int engine, cudaStream_t st) {
+static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int engine, cudaStream_t st, int* splits_used) {
+  *splits_used = 1;
   const long long KT = d.K * d.T;
   if (engine == VS_ENGINE_SIMT) {
     simt::GemmDesc g;
@@ -431,12 +463,14 @@ static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int eng
   g.A.ptr = Xa; g.A.rows = KT; g.A.k = d.C1; g.A.ld = d.ldc; g.A.planes = d.planes; g.A.plane_stride = KT * d.ldc;
   g.B.ptr = w.Ub; g.B.rows = w.ldz; g.B.k = d.C1; g.B.ld = d.ldc; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldc;
   g.M = KT; g.N = w.ldz; g.K = d.C1; g.C = w.Z; g.ldc = w.ldz;
+  g.splits = w.splits_f; g.split_stride = KT * w.ldz; g.splits_out = splits_used;
   set_passes(g, d.planes);
   return tc::gemm_tn(g, st);
 }
 
 // Gacc = Xb * RV^T  (M = C1, N = r*Npad, contraction K*T)
-static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int engine, cudaStream_t st) {
+static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int engine, cudaStream_t st, int* splits_used) {
+  *splits_used = 1;
   const long long KT = d.K * d.T;
   if (engine == VS_ENGINE_SIMT) {
     simt::GemmDesc g;
@@ -449,6 +483,7 @@ static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int eng
   g.A.ptr = Xb; g.A.rows = d.C1; g.A.k = KT; g.A.ld = d.ldr; g.A.planes = d.planes; g.A.plane_stride = d.C1 * d.ldr;
   g.B.ptr = w.RV; g.B.rows = w.ldz; g.B.k = KT; g.B.ld = d.ldr; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldr;
   g.M = d.C1; g.N = w.ldz; g.K = KT; g.C = w.Gacc; g.ldc = w.ldz;
+  g.splits = w.splits_b; g.split_stride = d.C1 * w.ldz; g.splits_out = splits_used;
   set_passes(g, d.planes);
   return tc::gemm_tn(g, st);
 }
@@ -520,10 +555,11 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
   VS_LAUNCH(small_mats_kernel, 1, 64, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   // stage 1: Z
-  rc = gemm_f(d, Xa, w, engine, st);
+  int sf = 1, sb = 1;
+  rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
   // stage 2: residuals, RV, dV partials
-  VS_LAUNCH((epi_f_kernel<false>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, y, xl, V, b, KT, (long long)d.T,
+  VS_LAUNCH((epi_f_kernel<false>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, KT, (long long)d.T,
             (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.R, w.RV, w.pv, nullptr);
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
   VS_LAUNCH(reduce_k_kernel, g2, 128, 0, st, w.R, xl, b, (long long)d.K, (long long)d.T, (long long)d.N, w.Npad, l2, db, w.sse_tn);
@@ -531,10 +567,10 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
             sse_n, loss, dV);
   if (dU) {
     // stage 3/4: Gacc and dU
-    rc = gemm_b(d, Xb, w, engine, st);
+    rc = gemm_b(d, Xb, w, engine, st, &sb);
     if (rc) return rc;
     dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
-    VS_LAUNCH(epi_b_kernel, g4, 256, 0, st, w.Gacc, w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU);
+    VS_LAUNCH(epi_b_kernel, g4, 256, 0, st, w.Gacc, w.ldz, sb, (long long)d.C1 * w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU);
   }
   return VS_OK;
 }
@@ -552,9 +588,10 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   dim3 g0((unsigned)ceil_div(d.C1, 256), (unsigned)d.N);
   VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
             (double*)nullptr);
-  rc = gemm_f(d, Xa, w, engine, st);
+  int sf = 1;
+  rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
-  VS_LAUNCH((epi_f_kernel<true>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, nullptr, xl, V, b, KT, (long long)d.T,
+  VS_LAUNCH((epi_f_kernel<true>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, KT, (long long)d.T,
             (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, yhat);
   return VS_OK;
 }

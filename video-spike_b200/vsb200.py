@@ -24,8 +24,8 @@ class VsError(RuntimeError):
 
 
 class AdamWHyper(C.Structure):
-    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("weight_decay", C.c_float), ("step", C.c_int32)]
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("step", C.c_int64)]
 
 
 class Mlp(C.Structure):
