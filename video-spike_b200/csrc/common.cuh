@@ -39,6 +39,11 @@ extern std::atomic<long long> g_launches;
       return vs::set_err(VS_ERR_CUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_e)); \
   } while (0)
 
+// ---- optional per-kernel timing (bench.py roofline): event pairs on the launching stream -------
+enum { PROF_GEMM_TC = 0, PROF_DW_ADAMW = 1, PROF_NUM_TAGS = 2 };
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+
 constexpr int kNumSMs = 148;  // B200
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

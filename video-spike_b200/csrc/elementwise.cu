@@ -308,7 +308,11 @@ extern "C" int vs_dw_adamw_fused(const float* dy, const float* x_f32, const uint
              VS_ERR_INVALID, "vs_dw_adamw_fused: misaligned buffers");
   const AdamConsts c = make_consts(h);
   cudaStream_t st = (cudaStream_t)stream;
-  if (batch <= 8) return launch_dw_adamw<8>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
-  if (batch <= 16) return launch_dw_adamw<16>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
-  return launch_dw_adamw<32>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  prof_begin(PROF_DW_ADAMW, st);
+  int rc;
+  if (batch <= 8) rc = launch_dw_adamw<8>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  else if (batch <= 16) rc = launch_dw_adamw<16>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  else rc = launch_dw_adamw<32>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  prof_end(PROF_DW_ADAMW, st);
+  return rc;
 }

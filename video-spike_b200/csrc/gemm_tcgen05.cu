@@ -348,6 +348,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   const size_t smem = (size_t)CTRL_BYTES + 1024 + (size_t)stages * stage_bytes;
   const int m_tiles = (int)ceil_div(g.M, BM), n_tiles = (int)ceil_div(g.N, BN);
   dim3 grid(m_tiles * n_tiles, splits, 1);
+  prof_begin(PROF_GEMM_TC, stream);
   if (g.tf32) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_LAUNCH(gemm_tn_kernel<true>, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
@@ -355,6 +356,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_LAUNCH(gemm_tn_kernel<false>, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
   }
+  prof_end(PROF_GEMM_TC, stream);
   if (g.splits_out) *g.splits_out = splits;
   return VS_OK;
 }

@@ -81,6 +81,11 @@ class _PackedSplit:
         self.dims, self.Xa, self.Xb, self.xl, self.y = dims, Xa, Xb, xl, y
         return self
 
+    @property
+    def shape(self):
+        """(K, T, ncoef) of the matrix this split stands for (ncoef counts the bias column)."""
+        return (self.K, self.T, self.C1 + 1)
+
 
 class RRRGD():
     def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None):
@@ -101,7 +106,10 @@ class RRRGD():
             K, T, N = _y.shape
             U = np.random.normal(size=(N, ncoef - 1, ncomp)) / np.sqrt(T * ncomp)
             V = np.random.normal(size=(ncomp, T)) / np.sqrt(T * ncomp)   # redrawn per eid, last one kept
-            b = np.ascontiguousarray(np.expand_dims(_y.mean(0).T, 1))
+            if isinstance(_y, torch.Tensor):   # targets already on the device (pack_session_from_frames)
+                b = _y.double().mean(0).T.unsqueeze(1).contiguous().cpu().numpy()
+            else:
+                b = np.ascontiguousarray(np.expand_dims(_y.mean(0).T, 1))
             params[f"{eid}_U"] = np2param(U)
             params[f"{eid}_b"] = np2param(b)
             self.N += N
@@ -275,3 +283,60 @@ def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None
     optimizer = optim.LBFGS(area_model.model.parameters(),)
     _, mse_val = train_model(area_model, train_data, optimizer, model_fname=model_fname, save=save)
     return area_model, mse_val
+
+
+# ------------------------------------------------------------------------------------------------
+# R0 on the device: the preprocessing of src/train_rrr.py:108-171 for the video modalities, from raw
+# uint8 frames, without ever forming the float64 (K, T, C) matrix on the host.
+def pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=1,
+                             smooth_w=2.0, device=None):
+    """frames_*: uint8 (K, Tf, ...) torch tensors (pinned host or CUDA); counts_*: (K, T, N) spike counts.
+    Mirrors train_rrr.py: y smoothed with gaussian_filter1d(sigma=smooth_w, axis=1); X and y z-scored with
+    the TRAIN statistics (std clipped at 1e-8); ones column; frames `sorted_idx` selected AFTER the z-score.
+    Returns the per-session entry of the `train_data` dict RRRGD consumes, with device-resident splits."""
+    vs.require_b200()
+    device = device or torch.device("cuda")
+    st = vs.stream()
+    idx = torch.as_tensor(np.asarray(sorted_idx), dtype=torch.int32).to(device)
+    T = int(idx.numel())
+    splits, ys = [], []
+    mean = sd = my = sy = None
+    for which, (fr, cnt) in enumerate(((frames_train, counts_train), (frames_test, counts_test))):
+        fr = fr.to(device, non_blocking=True).reshape(fr.shape[0], fr.shape[1], -1).contiguous()
+        cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
+        K, Tf, F = fr.shape
+        N = cnt.shape[2]
+        if which == 0:
+            mean = torch.empty(Tf * F, dtype=torch.float64, device=device)
+            sd = torch.empty_like(mean)
+            vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf * F, vs.ptr(mean), vs.ptr(sd), st))
+            sm = torch.empty_like(cnt)
+            vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
+            my = torch.empty(T * N, dtype=torch.float64, device=device)
+            sy = torch.empty_like(my)
+            vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
+            del sm
+        d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T))
+        Xa = torch.empty((planes, K * T, d.ldc), dtype=torch.bfloat16, device=device)
+        Xb = torch.empty((planes, F, d.ldr), dtype=torch.bfloat16, device=device)
+        xl = torch.empty(K * T, dtype=torch.float32, device=device)
+        vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
+                                       vs.ptr(xl), st))
+        y = torch.empty_like(cnt)
+        vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
+        splits.append(_PackedSplit.from_device(d, Xa, Xb, xl, y))
+        ys.append(y)
+        del fr
+    Tf_F = mean.numel()
+    return {"X": splits, "y": ys,
+            "setup": {"mean_X_Tv": mean, "std_X_Tv": sd, "mean_y_TN": my.reshape(T, -1), "std_y_TN": sy.reshape(T, -1)}}
+
+
+def train_model_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, l2=100.0, n_comp=3,
+                            eid="session", planes=None, engine=None, model_fname="tmp", save=False):
+    """R0 + train_model_main (rrr.py:192-202) in one call, from raw uint8 frames."""
+    pl = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
+    entry = pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=pl)
+    train_data = {eid: entry}
+    model, mse_val = train_model_main(train_data, l2, n_comp, model_fname, save=save, planes=pl, engine=engine)
+    return model, mse_val, train_data

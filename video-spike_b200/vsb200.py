@@ -74,6 +74,8 @@ def _load():
         "vs_gemm_tn": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]),
         "vs_launch_count": (i64, []),
         "vs_launch_count_reset": (None, []),
+        "vs_profile_enable": (None, [i32]),
+        "vs_profile_read": (i64, [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -151,3 +153,10 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, engine: int = ENGINE_AUTO) -> torc
     check(lib.vs_gemm_tn(ptr(A), ptr(B), ptr(Cm), M, N, K, A.stride(0), B.stride(0), N,
                          0 if A.dtype == torch.bfloat16 else 1, engine, stream()))
     return Cm
+
+
+def profile_read(tag: int):
+    """(count, total_ms, min_ms, max_ms) of the event-bracketed launches of one kernel class."""
+    tot, mn, mx = C.c_double(), C.c_double(), C.c_double()
+    cnt = lib.vs_profile_read(tag, C.byref(tot), C.byref(mn), C.byref(mx))
+    return int(cnt), tot.value, mn.value, mx.value
