@@ -210,7 +210,7 @@ def linear_config(args, world):
 def run_rrr(args, rank, world, local):
     import vsb200 as vs
     from model.rrr import RRRGD, pack_session_from_frames, train_model, train_model_from_frames
-    from torch import optim
+    from optim import FusedLBFGS
     vs.require_b200()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -230,7 +230,7 @@ def run_rrr(args, rank, world, local):
         with torch.no_grad():
             for k, v in init.items():
                 model.model[k].copy_(v)
-        opt = optim.LBFGS(model.model.parameters())
+        opt = FusedLBFGS(model.model.parameters())         # what train_model_main builds (rrr.py:199 semantics)
         _, res = train_model(model, td, opt, "tmp", save=False)
         return res["mse_val_mean"]
 

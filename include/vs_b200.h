@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 1
+#define VS_ABI_VERSION 2
 
 enum {
   VS_OK = 0,
@@ -68,10 +68,13 @@ int vs_linear_fwd(const float* x_f32, const uint8_t* x_u8, const float* W, const
 /* Backward of the same layer (autograd of src/trainer/base.py:150).  dy is the gradient
  * w.r.t. the layer OUTPUT; if relu != 0, y (the forward output) masks it first.
  * Any of dx / dW / dbias may be NULL to skip.  dy_masked (batch,out) receives the masked
- * gradient when relu != 0 (may alias dy).                                               */
+ * gradient when relu != 0 (may alias dy).  workspace: vs_linear_bwd_workspace() bytes
+ * (row-range partials of dx for batch <= 32); NULL selects the generic kernels.          */
+size_t vs_linear_bwd_workspace(int64_t batch, int64_t in_dim, int64_t out_dim);
 int vs_linear_bwd(const float* dy, const float* y, const float* x_f32, const uint8_t* x_u8,
                   const float* W, float* dy_masked, float* dx, float* dW, float* dbias,
-                  int64_t batch, int64_t in_dim, int64_t out_dim, int relu, void* stream);
+                  int64_t batch, int64_t in_dim, int64_t out_dim, int relu, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ Poisson NLL (C1)
  * torch.nn.PoissonNLLLoss(reduction="none", log_input=True) + .mean()
@@ -95,10 +98,11 @@ int vs_adamw(float* p, const float* g, float* m, float* v, int64_t n, vs_adamw_h
 
 /* G1 + O1 fused for the first layer: dW[o,i] = sum_b dy[b,o] x[b,i] is formed in registers
  * and consumed by the AdamW update without ever being written to HBM.  x as in
- * vs_linear_fwd.  batch <= 32.                                                           */
+ * vs_linear_fwd.  batch <= 32.  bias (out) with its moments mb, vb is updated in the same
+ * launch from dbias[o] = sum_b dy[b,o]; pass NULL to leave the bias alone.                */
 int vs_dw_adamw_fused(const float* dy, const float* x_f32, const uint8_t* x_u8, float* W,
-                      float* m, float* v, int64_t batch, int64_t in_dim, int64_t out_dim,
-                      vs_adamw_hyper h, void* stream);
+                      float* m, float* v, float* bias, float* mb, float* vb, int64_t batch,
+                      int64_t in_dim, int64_t out_dim, vs_adamw_hyper h, void* stream);
 
 /* ------------------------------------------------------------------ whole train step
  * The step body of src/trainer/base.py:147-154 for the `Linear` model
@@ -121,7 +125,7 @@ typedef struct {
   float* vb[VS_MAX_LAYERS];
   float* act[VS_MAX_LAYERS];
   float* gact[VS_MAX_LAYERS];
-  float* gW[VS_MAX_LAYERS]; /* gradient scratch for layers >= 1 (layer 0 unused) */
+  float* gW[VS_MAX_LAYERS]; /* gradient scratch, only read when batch > 32 (materialised-gradient route) */
   float* gb[VS_MAX_LAYERS];
 } vs_mlp;
 
@@ -141,10 +145,11 @@ int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f
  * (last column = the ones/bias column of src/train_rrr.py:155-162), y (K,T,N),
  * U (N,C1,r), V (r,T), b (N,1,T), all fp64 in the reference.
  *
- * Device layout built once per split by vs_rrr_pack (DESIGN.md "RRR data layout"):
- *   Xa : planes x (K*T) x ldc   bf16, row (k*T+t), c contiguous     (forward  A operand)
- *   Xb : planes x C1 x ldr      bf16, row c, (k*T+t) contiguous     (backward A operand)
- *   xl : (K*T) fp32, the last column of X
+ * Device layout built once per split by vs_rrr_pack (DESIGN.md "RRR data layout"); operand
+ * rows are TIME-MAJOR, d = t*K + k, so the trials of one time bin are adjacent:
+ *   Xa : planes x (K*T) x ldc   bf16, row d, c contiguous           (forward  A operand)
+ *   Xb : planes x C1 x ldr      bf16, row c, d contiguous           (backward A operand)
+ *   xl : (K*T) fp32, the last column of X, indexed by d
  * planes = 1 stores bf16(X); planes = 2 or 3 store the exact residual expansion
  * X ~= X0 + X1 (+ X2), each bf16, giving ~16 / ~24 significant bits.                    */
 typedef struct {
@@ -158,10 +163,10 @@ typedef struct {
 int64_t vs_rrr_ldc(int64_t C1);
 int64_t vs_rrr_ldr(int64_t K, int64_t T);
 
-/* X_rows: rows [row0, row0+nrows) of the (K*T, C1+1) fp64 matrix the reference hands to RRRGD
+/* X_trials: trials [k0, k0+nk) of the (K, T, C1+1) fp64 array the reference hands to RRRGD
  * (src/model/rrr.py:37-39), on the device.  Writes the matching rows of Xa / columns of Xb / xl;
- * call once with (0, K*T) or chunk by chunk to bound the fp64 staging buffer.             */
-int vs_rrr_pack(const double* X_rows, int64_t row0, int64_t nrows, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
+ * call once with (0, K) or chunk by chunk to bound the fp64 staging buffer.               */
+int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
                 float* xl, void* stream);
 
 /* R0 on device from raw frames (src/train_rrr.py:143-165 for the video modalities):
@@ -197,6 +202,31 @@ int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const 
 int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl, const double* U, const double* V,
                    const double* b, double* yhat, int engine, void* workspace, size_t workspace_bytes,
                    void* stream);
+
+/* ------------------------------------------------------------------ L-BFGS vector passes (R5)
+ * torch.optim.LBFGS(...).step(closure) without line search, as src/model/rrr.py:177,199 uses it, on flat
+ * fp64 vectors of n elements.  The two-loop recursion itself runs on the host in coefficient space
+ * (optim.py, FusedLBFGS); the device does two streaming passes per iteration.  History vectors live in one
+ * buffer `hist` of slots of `hist_stride` elements; s_slots_host / y_slots_host (HOST arrays, m entries,
+ * oldest pair first) name the slots holding s_i and y_i.
+ *
+ * vs_lbfgs_dots: y_out = g - g_prev (skipped if y_out is NULL; g_prev / s_new may be NULL on the very first
+ * evaluation) and out[0..8+6m) =
+ *   [0] g.g  [1] sum|g|  [2] max|g|  [3] y.y  [4] y.s_new  [5] s_new.g  [6] y.g  [7] 0
+ *   [8+3i+{0,1,2}]       s_i.g, s_i.y, s_i.s_new          i < m
+ *   [8+3(m+i)+{0,1,2}]   y_i.g, y_i.y, y_i.s_new          i < m
+ * vs_lbfgs_direction: d = coef[0]*g + sum_i coef[1+i]*s_i + coef[1+m+i]*y_i (coef_host: 2m+1 HOST doubles);
+ * s_out = t*d; x += t*d (skipped when x is NULL); *dmax_out = max|t*d|.                               */
+#define VS_LBFGS_MAX_HIST 100
+size_t vs_lbfgs_workspace(int64_t n, int m);
+int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, const double* s_new, double* y_out,
+                  const double* hist, int64_t hist_stride, const int32_t* s_slots_host,
+                  const int32_t* y_slots_host, int m, double* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+int vs_lbfgs_direction(int64_t n, const double* g, const double* hist, int64_t hist_stride,
+                       const int32_t* s_slots_host, const int32_t* y_slots_host, int m,
+                       const double* coef_host, double t, double* x, double* s_out, double* dmax_out,
+                       void* stream);
 
 /* ------------------------------------------------------------------ plain TN GEMM (test hook)
  * C[M,N] (fp32, row-major, ldc) = A[M,K] * B[N,K]^T with bf16 or tf32(fp32) operands, both

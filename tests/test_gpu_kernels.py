@@ -84,8 +84,13 @@ def test_gemm_tcgen05_tf32(vs, cuda, M, N, K):
 
 
 # ----------------------------------------------------------------------------- Linear layer fwd/bwd
-@pytest.mark.parametrize("batch,in_dim,out_dim,relu", [(16, 256, 128, 1), (5, 64, 128, 0), (16, 256, 1400, 0), (3, 120, 256, 1)])
-def test_linear_fwd_bwd_small(vs, cuda, batch, in_dim, out_dim, relu):
+@pytest.mark.parametrize("use_ws", [True, False])
+@pytest.mark.parametrize("batch,in_dim,out_dim,relu", [(16, 256, 128, 1), (5, 64, 128, 0), (16, 256, 1400, 0), (3, 120, 256, 1),
+                                                       (16, 256, 14400, 0), (32, 128, 64, 1), (1, 4, 1, 0), (9, 2052, 77, 1),
+                                                       (40, 64, 96, 1), (7, 250, 33, 0)])
+def test_linear_fwd_bwd_small(vs, cuda, batch, in_dim, out_dim, relu, use_ws):
+    """small-batch weight-streaming kernels (batch <= 32, in_dim % 4 == 0) and the generic SIMT route
+    (batch 40, in_dim 250) against plain torch fp32"""
     torch.manual_seed(3)
     x = torch.randn(batch, in_dim, device=cuda)
     W = torch.randn(out_dim, in_dim, device=cuda) / math.sqrt(in_dim)
@@ -98,8 +103,10 @@ def test_linear_fwd_bwd_small(vs, cuda, batch, in_dim, out_dim, relu):
     torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
     dy = torch.randn(batch, out_dim, device=cuda)
     gm = torch.empty_like(dy); dx = torch.empty_like(x); dW = torch.empty_like(W); db = torch.empty_like(b)
+    need = int(vs.lib.vs_linear_bwd_workspace(batch, in_dim, out_dim)) if use_ws else 0
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=cuda)
     vs.check(vs.lib.vs_linear_bwd(vs.ptr(dy), vs.ptr(y), vs.ptr(x), None, vs.ptr(W), vs.ptr(gm), vs.ptr(dx), vs.ptr(dW), vs.ptr(db),
-                                  batch, in_dim, out_dim, relu, vs.stream()))
+                                  batch, in_dim, out_dim, relu, vs.ptr(ws) if need else None, need, vs.stream()))
     g = dy * (ref > 0) if relu else dy
     torch.testing.assert_close(dW, g.t() @ x, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(db, g.sum(0), rtol=1e-4, atol=1e-4)
@@ -172,8 +179,18 @@ def test_dw_adamw_fused(vs, cuda, batch, in_dim, out_dim, u8):
     Wr.grad = dy.t() @ xf
     opt.state[Wr] = {"step": torch.tensor(4.0), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
     opt.step()
+    bias = torch.randn(out_dim, device=cuda) * 0.01
+    mb = torch.randn_like(bias) * 1e-4; vb = torch.rand_like(bias) * 1e-8
+    br = torch.nn.Parameter(bias.clone())
+    optb = torch.optim.AdamW([br], lr=3e-5, weight_decay=0.01, eps=1e-8, betas=(0.93, 0.999))
+    br.grad = dy.sum(0)
+    optb.state[br] = {"step": torch.tensor(4.0), "exp_avg": mb.clone(), "exp_avg_sq": vb.clone()}
+    optb.step()
     vs.check(vs.lib.vs_dw_adamw_fused(vs.ptr(dy), None if u8 else vs.ptr(xf), vs.ptr(x8) if u8 else None, vs.ptr(W), vs.ptr(m), vs.ptr(v),
-                                      batch, in_dim, out_dim, vs.AdamWHyper(3e-5, 0.93, 0.999, 1e-8, 0.01, 5), vs.stream()))
+                                      vs.ptr(bias), vs.ptr(mb), vs.ptr(vb), batch, in_dim, out_dim,
+                                      vs.AdamWHyper(3e-5, 0.93, 0.999, 1e-8, 0.01, 5), vs.stream()))
+    torch.testing.assert_close(bias, br.data, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(mb, optb.state[br]["exp_avg"], rtol=1e-4, atol=1e-9)
     torch.testing.assert_close(W, Wr.data, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(m, opt.state[Wr]["exp_avg"], rtol=1e-4, atol=1e-9)
     torch.testing.assert_close(v, opt.state[Wr]["exp_avg_sq"], rtol=1e-4, atol=1e-13)
@@ -183,7 +200,7 @@ def test_error_paths(vs, cuda):
     x = torch.zeros(8, device=cuda)
     rc = vs.lib.vs_adamw(vs.ptr(x), vs.ptr(x), vs.ptr(x), vs.ptr(x), 8, vs.AdamWHyper(1e-3, 0.9, 0.999, 1e-8, 0.0, 0), vs.stream())
     assert rc == 1 and b"step" in vs.lib.vs_last_error()
-    rc = vs.lib.vs_dw_adamw_fused(vs.ptr(x), vs.ptr(x), None, vs.ptr(x), vs.ptr(x), vs.ptr(x), 64, 8, 1,
+    rc = vs.lib.vs_dw_adamw_fused(vs.ptr(x), vs.ptr(x), None, vs.ptr(x), vs.ptr(x), vs.ptr(x), None, None, None, 64, 8, 1,
                                   vs.AdamWHyper(1e-3, 0.9, 0.999, 1e-8, 0.0, 1), vs.stream())
     assert rc == 3
     rc = vs.lib.vs_linear_fwd(vs.ptr(x), None, vs.ptr(x), None, vs.ptr(x), 1, 8192, 1, 0, 0, None, 0, vs.stream())

@@ -1,0 +1,119 @@
+"""-m gpu: FusedLBFGS (device vector passes + host coefficient-space recursion) against torch.optim.LBFGS
+driven by the same deterministic closure -- the optimiser src/model/rrr.py:177,199 uses."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import small_rrr_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vs(cuda):
+    import vsb200
+    return vsb200
+
+
+def _problem(dev, seed=0):
+    """Ill-conditioned smooth non-quadratic objective over three parameters of different shapes."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(7, 50, 3), (7, 1, 20), (3, 20)]
+    init = [torch.randn(s, generator=g, dtype=torch.float64) * 0.3 for s in shapes]
+    n = sum(int(np.prod(s)) for s in shapes)
+    A = torch.randn(n, n, generator=g, dtype=torch.float64)
+    A = (A @ A.T / n + torch.diag(torch.linspace(0.05, 5.0, n, dtype=torch.float64))).to(dev)
+    c = torch.randn(n, generator=g, dtype=torch.float64).to(dev)
+
+    def make():
+        ps = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+
+        def f():
+            x = torch.cat([p.reshape(-1) for p in ps])
+            return 0.5 * x @ (A @ x) - c @ x + 0.1 * torch.sum(torch.log1p(x * x))
+        return ps, f
+    return make
+
+
+@pytest.mark.parametrize("history,steps,max_iter", [(100, 1, 20), (3, 1, 20), (5, 3, 7), (100, 2, 1)])
+def test_fused_lbfgs_matches_torch(vs, cuda, history, steps, max_iter):
+    from optim import FusedLBFGS
+    make = _problem(cuda)
+    traj = {}
+    for name, cls in (("torch", torch.optim.LBFGS), ("fused", FusedLBFGS)):
+        ps, f = make()
+        opt = cls(ps, history_size=history, max_iter=max_iter)
+        losses = []
+
+        def closure():
+            opt.zero_grad()
+            loss = f()
+            loss.backward()
+            losses.append(float(loss))
+            return loss
+        for _ in range(steps):
+            opt.step(closure)
+        st = opt.state[ps[0]]
+        traj[name] = (losses, [p.detach().cpu().numpy() for p in ps], st["func_evals"], st["n_iter"])
+    lt, pt, et, it = traj["torch"]
+    lf, pf, ef, itf = traj["fused"]
+    assert (et, it) == (ef, itf) and len(lt) == len(lf)
+    np.testing.assert_allclose(lf, lt, rtol=1e-9)
+    for a, b in zip(pf, pt):
+        np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-9)
+
+
+def test_fused_lbfgs_converged_start_and_tolerances(vs, cuda):
+    """opt_cond on the first evaluation returns immediately; tolerance_change stops like torch."""
+    from optim import FusedLBFGS
+    for cls in (torch.optim.LBFGS, FusedLBFGS):
+        p = torch.nn.Parameter(torch.zeros(10, dtype=torch.float64, device=cuda))
+        opt = cls([p])
+        n = [0]
+
+        def closure():
+            opt.zero_grad()
+            loss = (p * p).sum()
+            loss.backward()
+            n[0] += 1
+            return loss
+        opt.step(closure)
+        assert n[0] == 1 and opt.state[p]["n_iter"] == 0
+    # a quadratic is solved in a couple of iterations, then |loss - prev_loss| < 1e-9 ends the loop
+    res = {}
+    for name, cls in (("t", torch.optim.LBFGS), ("f", FusedLBFGS)):
+        p = torch.nn.Parameter(torch.full((16,), 0.01, dtype=torch.float64, device=cuda))
+        opt = cls([p], max_iter=50)
+        n = [0]
+
+        def closure():
+            opt.zero_grad()
+            loss = ((p - 0.02) ** 2).sum()
+            loss.backward()
+            n[0] += 1
+            return loss
+        opt.step(closure)
+        res[name] = (n[0], opt.state[p]["n_iter"], p.detach().cpu().numpy())
+    assert res["t"][:2] == res["f"][:2]
+    np.testing.assert_allclose(res["f"][2], res["t"][2], rtol=1e-9)
+
+
+def test_rrr_fit_same_with_both_optimisers(vs, cuda):
+    """One RRR fit (rrr.py:164-202) driven by torch.optim.LBFGS and by FusedLBFGS through the same device closure."""
+    from model.rrr import RRRGD, train_model
+    from optim import FusedLBFGS
+    td = small_rrr_problem(seed=7, K=30, Kt=10, F=150, N=12)
+    out = {}
+    for name, cls in (("torch", torch.optim.LBFGS), ("fused", FusedLBFGS)):
+        m = RRRGD(td, 3, l2=100.0, planes=1)
+        m.to(cuda)
+        opt = cls(m.model.parameters())
+        _, res = train_model(m, td, opt, "tmp", save=False)
+        out[name] = (float(res["mse_val_mean"]), m.n_closure_evals, m.model["V"].detach().cpu().numpy(),
+                     m.model["e1_U"].detach().cpu().numpy())
+    assert out["torch"][1] == out["fused"][1] == 20
+    assert out["fused"][0] == pytest.approx(out["torch"][0], rel=1e-8)
+    np.testing.assert_allclose(out["fused"][2], out["torch"][2], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(out["fused"][3], out["torch"][3], rtol=1e-6, atol=1e-9)
+    # the parameters handed out by the model are still the ParameterDict entries the reference exposes
+    assert set(m.model.keys()) == {"e1_U", "e1_b", "V"} and m.model["e1_U"].shape == (12, 150, 3)

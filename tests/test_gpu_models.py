@@ -254,7 +254,8 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     xl = torch.empty(K * T, dtype=torch.float32, device=cuda)
     idx = torch.from_numpy(sidx.astype(np.int32)).to(cuda)
     vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb), vs.ptr(xl), vs.stream()))
-    ref = data["X"][0][:, :, :-1].reshape(K * T, F)
+    # operand rows are TIME-MAJOR (row d = t*K + k, include/vs_b200.h "RRR"): reorder the reference the same way
+    ref = np.ascontiguousarray(data["X"][0][:, :, :-1].transpose(1, 0, 2)).reshape(T * K, F)
     got = Xa.double().sum(0)[:, :F].cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)              # 3 bf16 planes ~ 24 bits
     np.testing.assert_array_equal(Xb.double().sum(0)[:, :K * T].cpu().numpy().T, got)

@@ -1,0 +1,121 @@
+"""CPU: host-side logic and the C-ABI surface (no kernel is launched here: there is no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "vs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib_path = os.path.join(ROOT, "video-spike_b200", "lib", "libvs_b200.so")
+    assert os.path.exists(lib_path), "build it: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(lib_path)
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vs_b200.h but not exported"
+    lib.vs_version.restype = ctypes.c_int
+    hdr = open(os.path.join(ROOT, "include", "vs_b200.h")).read()
+    assert lib.vs_version() == int(re.search(r"#define VS_ABI_VERSION (\d+)", hdr).group(1))
+
+
+def test_python_binding_covers_the_header():
+    import vsb200
+    assert sorted(vsb200.EXPORTS) == _declared_symbols()
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused by every wrapper: the product path cannot silently run without the GPU."""
+    import vsb200 as vs
+    with pytest.raises(vs.VsError):
+        vs.ptr(torch.zeros(4))
+    with pytest.raises(vs.VsError):
+        vs.require_b200()
+    from tests.helpers import make_linear_model
+    model, opt, _ = make_linear_model(120 * 4 * 4, 2, torch.device("cpu"))
+    with pytest.raises(vs.VsError):
+        model(torch.zeros(2, 120 * 4 * 4))
+    with pytest.raises(vs.VsError):
+        model.fused_train_step(torch.zeros(2, 120 * 4 * 4, dtype=torch.uint8), torch.zeros(2, 100, 2), opt)
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "video-spike_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+                assert "/root/reference" not in src, os.path.join(dirpath, f)
+
+
+# ----------------------------------------------------------------------------- L-BFGS coefficient-space recursion
+def _explicit_two_loop(g, S, Y, H):
+    """torch.optim.LBFGS.step's direction computation, on explicit vectors."""
+    m = len(S)
+    ro = [1.0 / float(Y[i] @ S[i]) for i in range(m)]
+    al = [0.0] * m
+    q = -g.copy()
+    for i in range(m - 1, -1, -1):
+        al[i] = float(S[i] @ q) * ro[i]
+        q -= al[i] * Y[i]
+    r = q * H
+    for i in range(m):
+        be = float(Y[i] @ r) * ro[i]
+        r += (al[i] - be) * S[i]
+    return r
+
+
+@pytest.mark.parametrize("m", [0, 1, 4, 19])
+def test_lbfgs_two_loop_matches_vector_recursion(m):
+    from optim import lbfgs_two_loop
+    rng = np.random.default_rng(m)
+    n = 300
+    A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n)      # SPD "Hessian": y = A s keeps y.s > 0
+    S = [rng.standard_normal(n) for _ in range(m)]
+    Y = [A @ s for s in S]
+    g = rng.standard_normal(n)
+    H = 0.37
+    d_ref = _explicit_two_loop(g, S, Y, H)
+    SY = [[float(S[i] @ Y[j]) for j in range(m)] for i in range(m)]
+    YY = [[float(Y[i] @ Y[j]) for j in range(m)] for i in range(m)]
+    cg, cs, cy, gtd = lbfgs_two_loop(float(g @ g), [float(s @ g) for s in S], [float(y @ g) for y in Y], SY, YY, H)
+    d = cg * g
+    for i in range(m):
+        d = d + cs[i] * S[i] + cy[i] * Y[i]
+    np.testing.assert_allclose(d, d_ref, rtol=1e-9, atol=1e-9 * np.abs(d_ref).max())
+    assert gtd == pytest.approx(float(g @ d_ref), rel=1e-9)
+
+
+# ----------------------------------------------------------------------------- config / schedule host logic
+def test_config_include_and_update_semantics():
+    """src/utils/config_utils.py:20-42: `include:` pulls a YAML file in, update_config(path) merges, and
+    update_config(args, config) is a no-op."""
+    from tests.helpers import linear_config
+    cfg = linear_config(1234, 7)
+    assert cfg.model.encoder.input_dim == 1234 and cfg.model.decoder.output_dim == 700
+    assert cfg.model.encoder.hidden_dims == [256, 128] and cfg.model.decoder.hidden_dims == [128, 256]
+    assert cfg.optimizer.lr == pytest.approx(5e-5) and cfg.optimizer.wd == pytest.approx(0.01)
+    assert cfg.training.train_batch_size == 16 and cfg.seed == 42
+
+
+def test_model_structure_matches_reference_layout():
+    from tests.helpers import make_linear_model
+    model, opt, sched = make_linear_model(120 * 4 * 4, 3, torch.device("cpu"))
+    keys = list(model.state_dict().keys())
+    assert keys == [f"{p}.layers.{i}.{w}" for p in ("encoder", "decoder") for i in (0, 2, 4) for w in ("weight", "bias")]
+    assert model.state_dict()["encoder.layers.0.weight"].shape == (256, 1920)
+    assert model.state_dict()["decoder.layers.4.weight"].shape == (300, 256)
+    assert model.output_dim == 3
+    assert opt.param_groups[0]["lr"] == pytest.approx(5e-6)            # OneCycleLR start = max_lr / div_factor
+    assert opt.param_groups[0]["betas"][0] == pytest.approx(0.95)       # cycle_momentum drives beta1

@@ -3,6 +3,7 @@
 // coalesced accesses, L1 bypass for touch-once data, enough loads in flight per SM to cover HBM
 // latency, grids sized in multiples of the SM count.
 #include "common.cuh"
+#include "adam.cuh"
 
 namespace vs {
 
@@ -86,37 +87,6 @@ __global__ void __launch_bounds__(256) poisson_nll_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ AdamW (O1)
-struct AdamConsts {
-  float decay;      // 1 - lr*wd
-  float beta1, w1;  // w1 = 1 - beta1
-  float beta2, w2;  // w2 = 1 - beta2
-  float step_size;  // lr / (1 - beta1^t)
-  float inv_bc2s;   // 1 / sqrt(1 - beta2^t)
-  float eps;
-};
-
-static AdamConsts make_consts(const vs_adamw_hyper& h) {
-  // scalars in double like the Python floats torch.optim.AdamW computes them with
-  const double bc1 = 1.0 - pow(h.beta1, (double)h.step);
-  const double bc2 = 1.0 - pow(h.beta2, (double)h.step);
-  AdamConsts c;
-  c.decay = (float)(1.0 - h.lr * h.weight_decay);
-  c.beta1 = (float)h.beta1; c.w1 = (float)(1.0 - h.beta1);
-  c.beta2 = (float)h.beta2; c.w2 = (float)(1.0 - h.beta2);
-  c.step_size = (float)(h.lr / bc1);
-  c.inv_bc2s = (float)(1.0 / sqrt(bc2));
-  c.eps = (float)h.eps;
-  return c;
-}
-
-__device__ __forceinline__ void adamw_elem(float& p, float& m, float& v, float g, const AdamConsts& c) {
-  p *= c.decay;
-  m = fmaf(g - m, c.w1, m);                    // lerp_(grad, 1-beta1)
-  v = fmaf(v, c.beta2, c.w2 * g * g);          // mul_(beta2).addcmul_(g, g, 1-beta2)
-  const float denom = sqrtf(v) * c.inv_bc2s + c.eps;
-  p -= c.step_size * (m / denom);
-}
-
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, const AdamConsts c) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -148,8 +118,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 template <int BT, bool kU8>
 __global__ void __launch_bounds__(256, (BT <= 16 ? 2 : 1))
 dw_adamw_kernel(const float* __restrict__ dy, const float* __restrict__ xf, const uint8_t* __restrict__ xu,
-                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, int batch, long long in_dim, int out_dim,
-                const AdamConsts c) {
+                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ bias,
+                float* __restrict__ mb, float* __restrict__ vb, int batch, long long in_dim, int out_dim, const AdamConsts c) {
   extern __shared__ float dys[];  // [out][BT], zero padded past batch
   for (int e = threadIdx.x; e < out_dim * BT; e += 256) {
     const int o = e / BT, b = e % BT;
@@ -174,6 +144,17 @@ dw_adamw_kernel(const float* __restrict__ dy, const float* __restrict__ xf, cons
     }
   }
   __syncthreads();
+  // bias of the layer: dbias[o] = sum_b dy[b,o] -> AdamW, by the first column strip
+  if (blockIdx.x == 0 && bias != nullptr) {
+    for (int o = threadIdx.x; o < out_dim; o += 256) {
+      float gb = 0.f;
+#pragma unroll
+      for (int b = 0; b < BT; ++b) gb += dys[o * BT + b];
+      float p = bias[o], m = mb[o], v = vb[o];
+      adamw_elem(p, m, v, gb, c);
+      bias[o] = p; mb[o] = m; vb[o] = v;
+    }
+  }
   if (!active) return;
   constexpr int UNROLL = 2;
   for (int o0 = 0; o0 < out_dim; o0 += UNROLL) {
@@ -241,16 +222,16 @@ int launch_colsum(const float* dy, float* db, long long batch, long long out_dim
 }
 
 template <int BT>
-static int launch_dw_adamw(const float* dy, const float* xf, const uint8_t* xu, float* W, float* m, float* v, int batch,
-                           long long in_dim, int out_dim, const AdamConsts& c, cudaStream_t st) {
+static int launch_dw_adamw(const float* dy, const float* xf, const uint8_t* xu, float* W, float* m, float* v, float* bias,
+                           float* mb, float* vb, int batch, long long in_dim, int out_dim, const AdamConsts& c, cudaStream_t st) {
   const size_t smem = (size_t)out_dim * BT * sizeof(float);
   const unsigned grid = (unsigned)ceil_div(in_dim, 1024);
   if (xu) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dw_adamw_kernel<BT, true>), grid, 256, smem, st, dy, xf, xu, W, m, v, batch, in_dim, out_dim, c);
+    VS_LAUNCH((dw_adamw_kernel<BT, true>), grid, 256, smem, st, dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c);
   } else {
     VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dw_adamw_kernel<BT, false>), grid, 256, smem, st, dy, xf, xu, W, m, v, batch, in_dim, out_dim, c);
+    VS_LAUNCH((dw_adamw_kernel<BT, false>), grid, 256, smem, st, dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c);
   }
   return VS_OK;
 }
@@ -298,8 +279,10 @@ extern "C" int vs_adamw(float* p, const float* g, float* m, float* v, int64_t n,
 }
 
 extern "C" int vs_dw_adamw_fused(const float* dy, const float* x_f32, const uint8_t* x_u8, float* W, float* m, float* v,
-                                 int64_t batch, int64_t in_dim, int64_t out_dim, vs_adamw_hyper h, void* stream) {
+                                 float* bias, float* mb, float* vb, int64_t batch, int64_t in_dim, int64_t out_dim,
+                                 vs_adamw_hyper h, void* stream) {
   VS_REQUIRE(dy && (x_f32 || x_u8) && W && m && v, VS_ERR_INVALID, "vs_dw_adamw_fused: null pointer");
+  VS_REQUIRE(!bias || (mb && vb), VS_ERR_INVALID, "vs_dw_adamw_fused: bias needs its moment buffers");
   VS_REQUIRE(h.step >= 1, VS_ERR_INVALID, "vs_dw_adamw_fused: step must be >= 1");
   VS_REQUIRE(batch >= 1 && batch <= 32, VS_ERR_UNSUPPORTED, "vs_dw_adamw_fused: batch %lld outside 1..32", (long long)batch);
   VS_REQUIRE(in_dim % 4 == 0, VS_ERR_UNSUPPORTED, "vs_dw_adamw_fused: in_dim must be a multiple of 4");
@@ -310,9 +293,9 @@ extern "C" int vs_dw_adamw_fused(const float* dy, const float* x_f32, const uint
   cudaStream_t st = (cudaStream_t)stream;
   prof_begin(PROF_DW_ADAMW, st);
   int rc;
-  if (batch <= 8) rc = launch_dw_adamw<8>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
-  else if (batch <= 16) rc = launch_dw_adamw<16>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
-  else rc = launch_dw_adamw<32>(dy, x_f32, x_u8, W, m, v, (int)batch, in_dim, (int)out_dim, c, st);
+  if (batch <= 8) rc = launch_dw_adamw<8>(dy, x_f32, x_u8, W, m, v, bias, mb, vb, (int)batch, in_dim, (int)out_dim, c, st);
+  else if (batch <= 16) rc = launch_dw_adamw<16>(dy, x_f32, x_u8, W, m, v, bias, mb, vb, (int)batch, in_dim, (int)out_dim, c, st);
+  else rc = launch_dw_adamw<32>(dy, x_f32, x_u8, W, m, v, bias, mb, vb, (int)batch, in_dim, (int)out_dim, c, st);
   prof_end(PROF_DW_ADAMW, st);
   return rc;
 }

@@ -29,7 +29,12 @@ struct GemmDesc {
   int n_pass = 1;
   int pa[kMaxPass] = {0, 0, 0, 0, 0, 0};
   int pb[kMaxPass] = {0, 0, 0, 0, 0, 0};
+  // Tail-wave balancing (only when splits == 1): with balance_ws (balance_ws_bytes() bytes) the tiles of the
+  // last, partially filled wave are split along K over the idle SMs and summed back into C by a small
+  // ordered reduction, instead of costing a whole wave.
+  void* balance_ws = nullptr;
 };
+size_t balance_ws_bytes();
 bool gemm_supported(const GemmDesc& g);
 int pick_bn(long long N);
 int gemm_tn(const GemmDesc& g, cudaStream_t stream);

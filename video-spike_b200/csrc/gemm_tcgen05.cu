@@ -36,6 +36,10 @@ struct KParams {
   int tmem_cols;
   float* C;
   long long ldc, split_stride;
+  // tail-wave balancing: CTAs with blockIdx.x >= tail_cta0 work on tile tail_cta0 + u / tail_splits,
+  // k-range u % tail_splits, and write dense (BM x BN) partial tiles to tail_ws
+  int tail_cta0, tail_splits, tail_kb_per_split;
+  float* tail_ws;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -140,10 +144,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 33);
 
   const int n_tiles = (p.N + p.BN - 1) / p.BN;
-  const int m_tile = blockIdx.x / n_tiles, n_tile = blockIdx.x % n_tiles;
-  const int split = blockIdx.y;
-  const int kb0 = split * p.kb_per_split;
-  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  int tile = blockIdx.x, split = blockIdx.y, kbps = p.kb_per_split;
+  const bool is_tail = p.tail_splits > 1 && (int)blockIdx.x >= p.tail_cta0;
+  if (is_tail) {
+    const int u = blockIdx.x - p.tail_cta0;
+    tile = p.tail_cta0 + u / p.tail_splits;
+    split = u % p.tail_splits;
+    kbps = p.tail_kb_per_split;
+  }
+  const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
+  const int kb0 = split * kbps;
+  const int kb1 = min(p.num_kb, kb0 + kbps);
   const int iters = (kb1 > kb0 ? kb1 - kb0 : 0) * p.n_pass;
 
   if (warp == 0 && lane == 0) {
@@ -219,6 +230,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     const int row = m_tile * BM + q * 32 + lane;
     float* crow = p.C + (long long)split * p.split_stride + (long long)row * p.ldc;
+    if (is_tail) {
+      // dense partial tile [tail tile][split][BM][BN]
+      float* trow = p.tail_ws + ((long long)((tile - p.tail_cta0) * p.tail_splits + split) * BM + (q * 32 + lane)) * p.BN;
+      for (int c = 0; c < p.BN; c += 16) {
+        float v[16];
+        if (iters > 0) {
+          if (c == 0) { mbar_wait(bar_tmem, 0); tc_fence_after(); }
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(trow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      tc_fence_before();
+    } else {
     if (iters > 0) {
       mbar_wait(bar_tmem, 0);
       tc_fence_after();
@@ -245,11 +273,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     tc_fence_before();
+    }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// C tile = ordered sum of the tail-wave partial tiles
+__global__ void __launch_bounds__(256) tail_reduce_kernel(const float* __restrict__ ws, int tail_cta0, int splits, int n_tiles, int BN,
+                                                          int M, int N, float* __restrict__ C, long long ldc) {
+  const int tt = blockIdx.y;
+  const int tile = tail_cta0 + tt, m_tile = tile / n_tiles, n_tile = tile % n_tiles;
+  const int e4 = blockIdx.x * 256 + threadIdx.x;           // float4 index inside the BM x BN tile
+  if (e4 * 4 >= BM * BN) return;
+  const int rl = (e4 * 4) / BN, c = (e4 * 4) % BN;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int sp = 0; sp < splits; ++sp) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ws + ((long long)(tt * splits + sp) * BM + rl) * BN + c));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const int row = m_tile * BM + rl, col = n_tile * BN + c;
+  if (row >= M) return;
+  float* dst = C + (long long)row * ldc + col;
+  const float sv[4] = {s.x, s.y, s.z, s.w};
+  if (col + 4 <= N && ((ldc & 3) == 0)) {
+    *reinterpret_cast<float4*>(dst) = s;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (col + i < N) dst[i] = sv[i];
   }
 }
 
@@ -290,6 +345,8 @@ static int make_map(CUtensorMap* m, const Operand& op, bool tf32, int box_rows) 
              (int)r, (long long)op.rows, (long long)op.k, (long long)op.ld, box_rows);
   return VS_OK;
 }
+
+size_t balance_ws_bytes() { return (size_t)kNumSMs * BM * kMaxBN * sizeof(float); }
 
 bool gemm_supported(const GemmDesc& g) {
   const int esz = g.tf32 ? 4 : 2;
@@ -348,6 +405,22 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   const size_t smem = (size_t)CTRL_BYTES + 1024 + (size_t)stages * stage_bytes;
   const int m_tiles = (int)ceil_div(g.M, BM), n_tiles = (int)ceil_div(g.N, BN);
   dim3 grid(m_tiles * n_tiles, splits, 1);
+  // tail-wave balancing: one CTA per SM is resident (the ring takes the whole shared memory), so a grid of
+  // full*148 + tail tiles costs full+1 waves; split the tail tiles along K across the SMs the last wave leaves idle
+  p.tail_cta0 = 0; p.tail_splits = 1; p.tail_kb_per_split = p.num_kb; p.tail_ws = nullptr;
+  const int tiles = m_tiles * n_tiles;
+  const int full = (tiles / kNumSMs) * kNumSMs, tail = tiles - full;
+  if (g.balance_ws && splits == 1 && full > 0 && tail > 0 && tail <= kNumSMs / 2) {
+    int ts = kNumSMs / tail;
+    if (ts > 16) ts = 16;
+    if (ts > p.num_kb / 8) ts = p.num_kb / 8;             // keep >= 8 k-blocks per CTA
+    if (ts >= 2) {
+      p.tail_kb_per_split = (int)ceil_div(p.num_kb, ts);
+      ts = (int)ceil_div(p.num_kb, p.tail_kb_per_split);
+      p.tail_cta0 = full; p.tail_splits = ts; p.tail_ws = reinterpret_cast<float*>(g.balance_ws);
+      grid.x = full + tail * ts;
+    }
+  }
   prof_begin(PROF_GEMM_TC, stream);
   if (g.tf32) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -355,6 +428,10 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   } else {
     VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_LAUNCH(gemm_tn_kernel<false>, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
+  }
+  if (p.tail_splits > 1) {
+    dim3 rg((unsigned)ceil_div((long long)BM * BN / 4, 256), (unsigned)tail);
+    VS_LAUNCH(tail_reduce_kernel, rg, 256, 0, stream, p.tail_ws, p.tail_cta0, p.tail_splits, n_tiles, BN, p.M, p.N, p.C, p.ldc);
   }
   prof_end(PROF_GEMM_TC, stream);
   if (g.splits_out) *g.splits_out = splits;

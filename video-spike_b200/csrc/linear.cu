@@ -1,6 +1,7 @@
 // Linear layers and the whole `Linear` MLP train step (src/model/linear.py, src/trainer/base.py:147-154).
 #include "common.cuh"
 #include "gemm.h"
+#include "smallbatch.h"
 
 namespace vs {
 int launch_relu_mask(const float* dy, const float* y, float* out, long long n, cudaStream_t st);
@@ -72,6 +73,9 @@ extern "C" int vs_linear_fwd(const float* x_f32, const uint8_t* x_u8, const floa
     return splitk_reduce_bias_act(part, splits, g.split_stride, ldc, 1, bias, y, batch, out_dim, relu, st);
   }
   VS_REQUIRE(engine != VS_ENGINE_TCGEN05, VS_ERR_UNSUPPORTED, "vs_linear_fwd: shape not supported by the tcgen05 engine");
+  // the small layers at training batch sizes: weight-streaming kernel (smallbatch.cu)
+  if (!big && x_f32 && sb::fwd_supported(batch, in_dim, out_dim) && ((((uintptr_t)x_f32) | ((uintptr_t)W)) & 15) == 0)
+    return sb::fwd(x_f32, W, bias, y, batch, in_dim, out_dim, relu, st);
   simt::GemmDesc g;
   g.A.ptr = x_f32 ? (const void*)x_f32 : (const void*)x_u8; g.A.type = x_f32 ? simt::F32 : simt::U8; g.A.s_i = in_dim; g.A.s_k = 1;
   g.B.ptr = W; g.B.type = simt::F32; g.B.s_i = in_dim; g.B.s_k = 1;
@@ -93,9 +97,13 @@ extern "C" int vs_linear_fwd(const float* x_f32, const uint8_t* x_u8, const floa
   return simt::gemm(g, st);
 }
 
+extern "C" size_t vs_linear_bwd_workspace(int64_t batch, int64_t in_dim, int64_t out_dim) {
+  return sb::dx_workspace(batch, in_dim, out_dim);
+}
+
 extern "C" int vs_linear_bwd(const float* dy, const float* y, const float* x_f32, const uint8_t* x_u8, const float* W,
                              float* dy_masked, float* dx, float* dW, float* dbias, int64_t batch, int64_t in_dim,
-                             int64_t out_dim, int relu, void* stream) {
+                             int64_t out_dim, int relu, void* workspace, size_t workspace_bytes, void* stream) {
   VS_REQUIRE(dy, VS_ERR_INVALID, "vs_linear_bwd: dy is null");
   VS_REQUIRE(batch > 0 && in_dim > 0 && out_dim > 0, VS_ERR_INVALID, "vs_linear_bwd: empty shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -106,9 +114,22 @@ extern "C" int vs_linear_bwd(const float* dy, const float* y, const float* x_f32
     if (rc) return rc;
     g = dy_masked;
   }
+  const bool small = sb::supported(batch, in_dim, out_dim) && ((((uintptr_t)x_f32) | ((uintptr_t)W) | ((uintptr_t)dW) | ((uintptr_t)dx)) & 15) == 0 &&
+                     (((uintptr_t)x_u8) & 3) == 0;
+  if (small && dW && (x_f32 || x_u8)) {
+    // dW (and dbias) in one pass over the output, the batch rows held in registers
+    int rc = sb::dw_store(g, x_f32, x_u8, dW, dbias, batch, in_dim, out_dim, st);
+    if (rc) return rc;
+    dW = nullptr; dbias = nullptr;
+  }
   if (dbias) {
     int rc = launch_colsum(g, dbias, batch, out_dim, st);
     if (rc) return rc;
+  }
+  if (dx && small && W && workspace && workspace_bytes >= sb::dx_workspace(batch, in_dim, out_dim) && (((uintptr_t)workspace) & 15) == 0) {
+    int rc = sb::dx(g, W, nullptr, dx, batch, in_dim, out_dim, workspace, workspace_bytes, st);
+    if (rc) return rc;
+    dx = nullptr;
   }
   if (dW) {
     VS_REQUIRE(x_f32 || x_u8, VS_ERR_INVALID, "vs_linear_bwd: dW needs the layer input");
@@ -133,13 +154,16 @@ extern "C" int vs_linear_bwd(const float* dy, const float* y, const float* x_f32
 
 // ------------------------------------------------------------------ whole MLP
 static int check_net(const vs_mlp* net, int64_t batch, bool train) {
+  // gradients are only materialised (gW/gb) on the large-batch route; at batch <= 32 they live in registers
+  const bool need_grads = train && batch > 32;
   VS_REQUIRE(net && net->n_layers >= 1 && net->n_layers <= VS_MAX_LAYERS, VS_ERR_INVALID, "vs_mlp: bad layer count");
   VS_REQUIRE(batch > 0, VS_ERR_INVALID, "vs_mlp: empty batch");
   for (int l = 0; l < net->n_layers; ++l) {
     VS_REQUIRE(net->W[l] && net->act[l] && net->dims[l] > 0 && net->dims[l + 1] > 0, VS_ERR_INVALID, "vs_mlp: layer %d incomplete", l);
     if (train) {
       VS_REQUIRE(net->mW[l] && net->vW[l] && net->gact[l], VS_ERR_INVALID, "vs_mlp: layer %d missing optimizer/grad buffers", l);
-      VS_REQUIRE(!net->b[l] || (net->mb[l] && net->vb[l] && net->gb[l]), VS_ERR_INVALID, "vs_mlp: layer %d missing bias buffers", l);
+      VS_REQUIRE(!net->b[l] || (net->mb[l] && net->vb[l]), VS_ERR_INVALID, "vs_mlp: layer %d missing bias moment buffers", l);
+      VS_REQUIRE(!need_grads || (net->gW[l] && (!net->b[l] || net->gb[l])), VS_ERR_INVALID, "vs_mlp: layer %d missing gW/gb scratch (batch > 32)", l);
     }
   }
   return VS_OK;
@@ -151,6 +175,8 @@ extern "C" size_t vs_mlp_workspace(const vs_mlp* net, int64_t batch) {
   for (int l = 0; l < net->n_layers && l < VS_MAX_LAYERS; ++l) {
     const size_t w = vs_linear_fwd_workspace(batch, net->dims[l], net->dims[l + 1]);
     if (w > ws) ws = w;
+    const size_t wb = l >= 1 ? vs_linear_bwd_workspace(batch, net->dims[l], net->dims[l + 1]) : 0;
+    if (wb > ws) ws = wb;
   }
   return ws;
 }
@@ -191,32 +217,51 @@ extern "C" int vs_mlp_train_step(const vs_mlp* net, const uint8_t* frames_u8, co
   // loss + dlogits (C1)
   rc = vs_poisson_nll(net->act[L - 1], target, loss_sum, net->gact[L - 1], batch * net->dims[L], stream);
   if (rc) return rc;
-  // backward (G1) through layers L-1 .. 1: needs the PRE-update weights, so all updates come after
+  cudaStream_t st = (cudaStream_t)stream;
+  // small-batch route (the reference batch size): masked dx per layer, then dW+AdamW fused per layer
+  bool small = batch <= 32;
+  for (int l = 0; l < L && small; ++l) small = sb::supported(batch, net->dims[l], net->dims[l + 1]);
+  if (small) {
+    // backward data (G1) through layers L-1 .. 1 with the PRE-update weights; the ReLU mask of the layer
+    // below is folded into the reduction, so gact[l-1] is the gradient w.r.t. that layer's pre-activation
+    for (int l = L - 1; l >= 1; --l) {
+      rc = sb::dx(net->gact[l], net->W[l], net->relu[l - 1] ? net->act[l - 1] : nullptr, net->gact[l - 1], batch, net->dims[l],
+                  net->dims[l + 1], workspace, workspace_bytes, st);
+      if (rc) return rc;
+    }
+    // weight gradient + AdamW (O1), gradient never written: layer 0 from the uint8 frames
+    const uint8_t* xu0 = x_f32 ? nullptr : frames_u8;
+    const bool fused0 = net->dims[1] * 32 * 4 <= 200 * 1024;
+    if (fused0) {
+      rc = vs_dw_adamw_fused(net->gact[0], x_f32, xu0, net->W[0], net->mW[0], net->vW[0], net->b[0], net->mb[0], net->vb[0], batch,
+                             net->dims[0], net->dims[1], h, stream);
+    } else {
+      rc = sb::dw_adamw(net->gact[0], x_f32, xu0, net->W[0], net->mW[0], net->vW[0], net->b[0], net->mb[0], net->vb[0], batch,
+                        net->dims[0], net->dims[1], h, st);
+    }
+    if (rc) return rc;
+    for (int l = 1; l < L; ++l) {
+      rc = sb::dw_adamw(net->gact[l], net->act[l - 1], nullptr, net->W[l], net->mW[l], net->vW[l], net->b[l], net->mb[l], net->vb[l],
+                        batch, net->dims[l], net->dims[l + 1], h, st);
+      if (rc) return rc;
+    }
+    return VS_OK;
+  }
+  // general route (large batches): per-layer backward with materialised gradients
   for (int l = L - 1; l >= 1; --l) {
     VS_REQUIRE(net->gW[l], VS_ERR_INVALID, "vs_mlp_train_step: layer %d has no gW scratch", l);
     rc = vs_linear_bwd(net->gact[l], net->act[l], net->act[l - 1], nullptr, net->W[l], net->gact[l], net->gact[l - 1], net->gW[l],
-                       net->b[l] ? net->gb[l] : nullptr, batch, net->dims[l], net->dims[l + 1], net->relu[l], stream);
+                       net->b[l] ? net->gb[l] : nullptr, batch, net->dims[l], net->dims[l + 1], net->relu[l], nullptr, 0, stream);
     if (rc) return rc;
   }
-  // layer 0: mask, bias gradient, then the fused weight-gradient + AdamW
   const uint8_t* xu = x_f32 ? nullptr : frames_u8;
-  const bool fused = batch <= 32 && net->dims[0] % 4 == 0 && net->dims[1] * 32 * 4 <= 200 * 1024;
-  rc = vs_linear_bwd(net->gact[0], net->act[0], x_f32, xu, net->W[0], net->gact[0], nullptr, fused ? nullptr : net->gW[0],
-                     net->b[0] ? net->gb[0] : nullptr, batch, net->dims[0], net->dims[1], net->relu[0], stream);
+  VS_REQUIRE(net->gW[0], VS_ERR_INVALID, "vs_mlp_train_step: large-batch route needs gW[0]");
+  rc = vs_linear_bwd(net->gact[0], net->act[0], x_f32, xu, net->W[0], net->gact[0], nullptr, net->gW[0],
+                     net->b[0] ? net->gb[0] : nullptr, batch, net->dims[0], net->dims[1], net->relu[0], nullptr, 0, stream);
   if (rc) return rc;
-  if (fused) {
-    rc = vs_dw_adamw_fused(net->gact[0], x_f32, xu, net->W[0], net->mW[0], net->vW[0], batch, net->dims[0], net->dims[1], h, stream);
-  } else {
-    VS_REQUIRE(net->gW[0], VS_ERR_INVALID, "vs_mlp_train_step: unfused first layer needs gW[0]");
-    rc = vs_adamw(net->W[0], net->gW[0], net->mW[0], net->vW[0], net->dims[0] * net->dims[1], h, stream);
-  }
-  if (rc) return rc;
-  // O1 for the remaining parameters
   for (int l = 0; l < L; ++l) {
-    if (l >= 1) {
-      rc = vs_adamw(net->W[l], net->gW[l], net->mW[l], net->vW[l], net->dims[l] * net->dims[l + 1], h, stream);
-      if (rc) return rc;
-    }
+    rc = vs_adamw(net->W[l], net->gW[l], net->mW[l], net->vW[l], net->dims[l] * net->dims[l + 1], h, stream);
+    if (rc) return rc;
     if (net->b[l]) {
       rc = vs_adamw(net->b[l], net->gb[l], net->mb[l], net->vb[l], net->dims[l + 1], h, stream);
       if (rc) return rc;

@@ -6,6 +6,8 @@
 //   Gacc[c,(j,n)] = sum_(k,t) X[k,t,c] RV[(j,n),(k,t)]           GEMM-B  (tcgen05, bf16 planes)
 //   dU = 2 Gacc + 2 l2 U (V V^T);  dV = 2 sum R Z + 2 l2 (U^T U) V;  db = 2 sum_k xl R + 2 l2 b
 // beta = cat(U@V, b) (rrr.py:79-96) and its gradient are never materialised.
+// Operand rows are TIME-MAJOR: row d = t*K + k, so the K trials of one time bin are contiguous and every
+// reduction over trials (db, SSE, dV) is a reduction over adjacent rows done inside the epilogue block.
 // All reductions are ordered (no floating-point atomics): results are bit-reproducible run to run.
 #include "common.cuh"
 #include "gemm.h"
@@ -20,6 +22,10 @@ __device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((
 
 // split v into `planes` bf16 residual planes: v ~= p0 + p1 + p2
 __device__ __forceinline__ void split_planes(double v, int planes, uint16_t out[3]) {
+  if (planes == 1) {  // fast path: one rounding, no fp64 arithmetic
+    out[0] = bf16_bits((float)v); out[1] = 0; out[2] = 0;
+    return;
+  }
   double rem = v;
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
@@ -34,47 +40,50 @@ __device__ __forceinline__ void split_planes(double v, int planes, uint16_t out[
 }
 
 // ------------------------------------------------------------------ pack X (R0 tail / RRRGD input)
-// One 32 x 32 tile of (row = k*T+t, c) per block; writes Xa (row-major in c) directly and Xb
-// (row-major in row) through a shared-memory transpose so both stores are coalesced.
+// One tile of 32 trials (of ONE time bin t) x 32 features per block.  Source: X[(k*T + t), c] (fp64 path) or
+// frames[k, sorted_idx[t], c] (uint8 path).  Destination rows are time-major d = t*K + k: Xa[d][c] is written
+// directly (coalesced in c) and Xb[c][d] through a shared-memory transpose (coalesced in d).
 template <bool kFromU8>
 __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X, const uint8_t* __restrict__ frames,
                                                    const int32_t* __restrict__ sorted_idx, const double* __restrict__ mean,
-                                                   const double* __restrict__ sd, long long Tf, long long row_begin,
-                                                   long long row_end, long long KT, long long T,
-                                                   long long C1, int planes, long long ldc, long long ldr,
-                                                   uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xb, float* __restrict__ xl) {
+                                                   const double* __restrict__ sd, long long Tf, long long k_begin, long long k_end,
+                                                   long long K, long long T, long long C1, int planes, long long ldc,
+                                                   long long ldr, uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xb,
+                                                   float* __restrict__ xl) {
   __shared__ uint16_t tile[3][32][33];
-  // rows are GLOBAL row indices k*T+t in [row_begin, row_end); X (fp64 path) points at row_begin
-  const long long r0 = row_begin + (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;
+  const long long kblocks = (k_end - k_begin + 31) / 32;
+  const long long t = blockIdx.x / kblocks, k0 = k_begin + (blockIdx.x % kblocks) * 32;
+  const long long c0 = (long long)blockIdx.y * 32;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const long long pa = KT * ldc, pb = C1 * ldr;
+  const long long pa = K * T * ldc, pb = C1 * ldr;
+  long long f = 0;
+  if constexpr (kFromU8) f = sorted_idx[t];
   for (int rr = ly; rr < 32; rr += 8) {
-    const long long row = r0 + rr, c = c0 + lx;
+    const long long k = k0 + rr, c = c0 + lx;
     uint16_t pl[3] = {0, 0, 0};
-    if (row < row_end && c < C1) {
+    if (k < k_end && c < C1) {
       double v;
       if constexpr (kFromU8) {
-        const long long k = row / T, t = row % T;
-        const long long f = sorted_idx[t];
         const long long col = f * C1 + c;
         v = ((double)frames[(k * Tf + f) * C1 + c] - mean[col]) / sd[col];
       } else {
-        v = X[(row - row_begin) * (C1 + 1) + c];
+        v = X[((k - k_begin) * T + t) * (C1 + 1) + c];   // X points at trial k_begin
       }
       split_planes(v, planes, pl);
-      for (int p = 0; p < planes; ++p) Xa[p * pa + row * ldc + c] = pl[p];
+      const long long d = t * K + k;
+      for (int p = 0; p < planes; ++p) Xa[p * pa + d * ldc + c] = pl[p];
     }
     for (int p = 0; p < planes; ++p) tile[p][rr][lx] = pl[p];
   }
   __syncthreads();
   for (int cc = ly; cc < 32; cc += 8) {
-    const long long c = c0 + cc, row = r0 + lx;
-    if (c < C1 && row < row_end)
-      for (int p = 0; p < planes; ++p) Xb[p * pb + c * ldr + row] = tile[p][lx][cc];
+    const long long c = c0 + cc, k = k0 + lx;
+    if (c < C1 && k < k_end)
+      for (int p = 0; p < planes; ++p) Xb[p * pb + c * ldr + t * K + k] = tile[p][lx][cc];
   }
   if (blockIdx.y == 0 && threadIdx.x < 32) {
-    const long long row = r0 + threadIdx.x;
-    if (row < row_end) xl[row] = kFromU8 ? 1.0f : (float)X[(row - row_begin) * (C1 + 1) + C1];
+    const long long k = k0 + threadIdx.x;
+    if (k < k_end) xl[t * K + k] = kFromU8 ? 1.0f : (float)X[((k - k_begin) * T + t) * (C1 + 1) + C1];
   }
 }
 
@@ -176,138 +185,181 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
   }
 }
 
-// G = sum of Gram partials (fixed order), W = V V^T
-__global__ void small_mats_kernel(const double* __restrict__ Gp, long long nblocks, const double* __restrict__ V, int r, long long T,
-                                  double* __restrict__ G, double* __restrict__ W) {
-  const int e = threadIdx.x;
-  if (e < r * r) {
+// G = sum of Gram partials, W = V V^T.  One block; thread i sums partials i, i+256, ... and the 256 lane sums
+// are then added in a fixed tree order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) small_mats_kernel(const double* __restrict__ Gp, long long nblocks, const double* __restrict__ V,
+                                                         int r, long long T, double* __restrict__ G, double* __restrict__ W) {
+  __shared__ double red[256];
+  const int rr = r * r;
+  for (int e = 0; e < rr; ++e) {
     double s = 0.0;
     if (Gp)
-      for (long long b = 0; b < nblocks; ++b) s += Gp[b * (r * r) + e];
-    G[e] = s;
-    const int i = e / r, j = e % r;
+      for (long long b = threadIdx.x; b < nblocks; b += 256) s += Gp[b * rr + e];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+      if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) G[e] = red[0];
+    __syncthreads();
+  }
+  if (threadIdx.x < rr) {
+    const int i = threadIdx.x / r, j = threadIdx.x % r;
     double w = 0.0;
     for (long long t = 0; t < T; ++t) w += V[i * T + t] * V[j * T + t];
-    W[e] = w;
+    W[threadIdx.x] = w;
   }
 }
 
 // ------------------------------------------------------------------ closure stage 2: epilogue of GEMM-F
-// block = 32 rows (k,t) x all neurons (looped in tiles of 32).  Phase 1 (lanes over n): yhat, R, dV partials.
-// Phase 2 (lanes over rows): RV[p][(j,n)][row] = planes of V[j,t] * R   (B operand of GEMM-B).
-template <bool kPredict>
+// block (kb, t) = 64 trials of time bin t x all neurons (tiles of 32).  Phase 1 (lanes over n): yhat, residual,
+// per-block partials of SSE, db and dV.  Phase 2 (lanes over trial pairs): RV[p][(j,n)][d] = planes of
+// V[j,t] * R, the B operand of GEMM-B, written as bf16x2.  The residual itself never goes to HBM.
+constexpr int kEpiRows = 64;
+
+template <bool kPredict, int RMAX>
 __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, int splits, long long split_stride,
-                                                    const float* __restrict__ y,
-                                                    const float* __restrict__ xl, const double* __restrict__ V,
-                                                    const double* __restrict__ b, long long KT, long long T, long long N,
-                                                    long long Npad, int r, int planes, long long ldr, float* __restrict__ R,
-                                                    uint16_t* __restrict__ RV, float* __restrict__ pv, double* __restrict__ yhat) {
-  __shared__ float Rs[32][33];
-  __shared__ float Vs[32][kMaxR];
+                                                    const float* __restrict__ y, const float* __restrict__ xl,
+                                                    const double* __restrict__ V, const double* __restrict__ b, long long K,
+                                                    long long T, long long N, long long Npad, int r, int planes, long long ldr,
+                                                    uint16_t* __restrict__ RV, float* __restrict__ sse_part,
+                                                    float* __restrict__ db_part, float* __restrict__ pv_part,
+                                                    double* __restrict__ yhat) {
+  __shared__ float Rs[kEpiRows][33];
+  __shared__ float red[8][32][2];
+  __shared__ float xls[kEpiRows];
+  __shared__ float pvs[8][RMAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long r0 = (long long)blockIdx.x * 32;
-  if (threadIdx.x < 32) {
-    const long long row = r0 + threadIdx.x;
-    const long long t = row < KT ? row % T : 0;
-    for (int j = 0; j < r; ++j) Vs[threadIdx.x][j] = (float)V[(long long)j * T + t];
-  }
+  const long long t = blockIdx.y, kb = blockIdx.x, KB = gridDim.x;
+  const long long k0 = kb * kEpiRows, d0 = t * K + k0;
+  float vt[RMAX];
+#pragma unroll
+  for (int j = 0; j < RMAX; ++j) vt[j] = j < r ? (float)V[(long long)j * T + t] : 0.f;
+  if (threadIdx.x < kEpiRows) xls[threadIdx.x] = (k0 + threadIdx.x < K) ? xl[d0 + threadIdx.x] : 0.f;
   __syncthreads();
-  float pvacc[4][kMaxR];
+  float pvacc[RMAX];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < kMaxR; ++j) pvacc[i][j] = 0.f;
+  for (int j = 0; j < RMAX; ++j) pvacc[j] = 0.f;
   const long long prv = (long long)r * Npad * ldr;
+  const bool pair_ok = ((d0 & 1) == 0);
   for (long long n0 = 0; n0 < N; n0 += 32) {
     const long long n = n0 + lane;
+    const float bn = n < N ? (float)b[n * T + t] : 0.f;
+    float sse = 0.f, sdb = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rl = w + 8 * i;
-      const long long row = r0 + rl;
+    for (int i = 0; i < kEpiRows / 8; ++i) {
+      const int rl = w * (kEpiRows / 8) + i;
+      const long long k = k0 + rl, d = d0 + rl;
       float res = 0.f;
-      if (row < KT && n < N) {
-        const long long t = row % T;
-        float acc = xl[row] * (float)b[n * T + t];
-        float z[kMaxR];
-        for (int j = 0; j < r; ++j) {
-          const float* zp = Z + row * ldz + (long long)j * Npad + n;
-          if (splits == 1) {
-            z[j] = *zp;
-          } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator
-            double zs = 0.0;
-            for (int sp = 0; sp < splits; ++sp) zs += (double)zp[(long long)sp * split_stride];
-            z[j] = (float)zs;
+      if (k < K && n < N) {
+        float acc = xls[rl] * bn;
+        float z[RMAX];
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) {
+          if (j < r) {
+            const float* zp = Z + d * ldz + (long long)j * Npad + n;
+            if (splits == 1) {
+              z[j] = __ldg(zp);
+            } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator
+              double zs = 0.0;
+#pragma unroll 1
+              for (int sp = 0; sp < splits; ++sp) zs += (double)zp[(long long)sp * split_stride];
+              z[j] = (float)zs;
+            }
+            acc = fmaf(vt[j], z[j], acc);
           }
-          acc = fmaf(Vs[rl][j], z[j], acc);
         }
         if constexpr (kPredict) {
-          yhat[row * N + n] = (double)acc;
+          yhat[(k * T + t) * N + n] = (double)acc;
         } else {
-          res = acc - y[row * N + n];
-          R[row * Npad + n] = res;
-          for (int j = 0; j < r; ++j) pvacc[i][j] = fmaf(res, z[j], pvacc[i][j]);
+          res = acc - __ldg(y + (k * T + t) * N + n);
+          sse = fmaf(res, res, sse);
+          sdb = fmaf(xls[rl], res, sdb);
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j)
+            if (j < r) pvacc[j] = fmaf(res, z[j], pvacc[j]);
         }
       }
-      Rs[rl][lane] = res;
+      if constexpr (!kPredict) Rs[rl][lane] = res;
     }
     if constexpr (!kPredict) {
+      red[w][lane][0] = sse;
+      red[w][lane][1] = sdb;
       __syncthreads();
-      // phase 2: lanes over rows
-      const long long row = r0 + lane;
-      if (row < KT) {
+      // phase 2: lane = trial pair (2*lane, 2*lane+1), warp w covers neurons w*4 .. w*4+3 of the tile
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int nl = w + 8 * i;
-          const long long nn = n0 + nl;
-          if (nn < N) {
-            const float res = Rs[lane][nl];
-            for (int j = 0; j < r; ++j) {
-              uint16_t pl[3];
-              split_planes((double)(Vs[lane][j] * res), planes, pl);
-              for (int p = 0; p < planes; ++p) RV[p * prv + ((long long)j * Npad + nn) * ldr + row] = pl[p];
+      for (int i = 0; i < 4; ++i) {
+        const int nl = w * 4 + i;
+        const long long nn = n0 + nl;
+        if (nn >= N) continue;
+        const float r0v = Rs[2 * lane][nl], r1v = Rs[2 * lane + 1][nl];
+        const long long ka = k0 + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < RMAX; ++j) {
+          if (j >= r) continue;
+          uint16_t pl0[3], pl1[3];
+          split_planes((double)(vt[j] * r0v), planes, pl0);
+          split_planes((double)(vt[j] * r1v), planes, pl1);
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            if (p >= planes) continue;
+            uint16_t* dst = RV + p * prv + ((long long)j * Npad + nn) * ldr + d0 + 2 * lane;
+            if (pair_ok && ka + 1 < K) {
+              *reinterpret_cast<uint32_t*>(dst) = (uint32_t)pl0[p] | ((uint32_t)pl1[p] << 16);
+            } else {
+              if (ka < K) dst[0] = pl0[p];
+              if (ka + 1 < K) dst[1] = pl1[p];
             }
           }
         }
+      }
+      // phase 3: per-(t, kb, n) partials, the 8 warps' sums added in a fixed order
+      if (w == 0 && n < N) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) { s0 += red[w2][lane][0]; s1 += red[w2][lane][1]; }
+        sse_part[(t * KB + kb) * N + n] = s0;
+        db_part[(t * KB + kb) * N + n] = s1;
       }
       __syncthreads();
     }
   }
   if constexpr (!kPredict) {
-    // dV partial per row: reduce over the 32 lanes (neurons)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long row = r0 + w + 8 * i;
-      for (int j = 0; j < r; ++j) {
-        const float s = warp_sum(pvacc[i][j]);
-        if (lane == 0 && row < KT) pv[row * r + j] = s;
-      }
+    for (int j = 0; j < RMAX; ++j) {
+      const float s = warp_sum(pvacc[j]);
+      if (lane == 0) pvs[w][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < r) {
+      float s = 0.f;
+      for (int w2 = 0; w2 < 8; ++w2) s += pvs[w2][threadIdx.x];
+      pv_part[(t * KB + kb) * r + threadIdx.x] = s;
     }
   }
 }
 
-// per (t, n): db and SSE partials, ordered sum over trials k
-__global__ void __launch_bounds__(128) reduce_k_kernel(const float* __restrict__ R, const float* __restrict__ xl,
-                                                       const double* __restrict__ b, long long K, long long T, long long N,
-                                                       long long Npad, double l2, double* __restrict__ db,
-                                                       double* __restrict__ sse_tn) {
+// per (t, n): db and SSE from the per-block partials (ordered sum over the trial blocks)
+__global__ void __launch_bounds__(128) reduce_part_kernel(const float* __restrict__ sse_part, const float* __restrict__ db_part,
+                                                          const double* __restrict__ b, long long KB, long long T, long long N,
+                                                          double l2, double* __restrict__ db, double* __restrict__ sse_tn) {
   const long long t = blockIdx.y;
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double sdb = 0.0, sse = 0.0;
-  for (long long k = 0; k < K; ++k) {
-    const long long row = k * T + t;
-    const double res = (double)R[row * Npad + n];
-    sdb += (double)xl[row] * res;
-    sse += res * res;
+  for (long long kb = 0; kb < KB; ++kb) {
+    sse += (double)sse_part[(t * KB + kb) * N + n];
+    sdb += (double)db_part[(t * KB + kb) * N + n];
   }
   if (db) db[n * T + t] = 2.0 * sdb + 2.0 * l2 * b[n * T + t];
   sse_tn[t * N + n] = sse;
 }
 
 // final scalars: sse_n, loss, dV
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv,
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv_part,
                                                        const double* __restrict__ G, const double* __restrict__ W,
-                                                       const double* __restrict__ V, const double* __restrict__ b, long long K,
+                                                       const double* __restrict__ V, const double* __restrict__ b, long long KB,
                                                        long long T, long long N, int r, double l2, double* __restrict__ sse_n,
                                                        double* __restrict__ loss, double* __restrict__ dV) {
   __shared__ double red[256];
@@ -337,7 +389,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     for (long long e = threadIdx.x; e < (long long)r * T; e += 256) {
       const long long j = e / T, t = e % T;
       double s = 0.0;
-      for (long long k = 0; k < K; ++k) s += (double)pv[(k * T + t) * r + j];
+      for (long long kb = 0; kb < KB; ++kb) s += (double)pv_part[(t * KB + kb) * r + j];
       double gv = 0.0;
       for (int jj = 0; jj < r; ++jj) gv += G[j * r + jj] * V[(long long)jj * T + t];
       dV[e] += 2.0 * s + 2.0 * l2 * gv;  // accumulated: V is shared across sessions (rrr.py:49)
@@ -386,9 +438,10 @@ __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Ga
 // ------------------------------------------------------------------ host orchestration
 struct Ws {
   uint16_t *Ub, *RV;
-  float *Z, *R, *Gacc, *pv;
+  float *Z, *Gacc, *sse_part, *db_part, *pv_part;
+  void* bal;                 // tail-wave split-K scratch of the GEMMs
   double *Gp, *G, *W, *sse_tn;
-  long long Npad, ldz, gp_blocks;
+  long long Npad, ldz, gp_blocks, KB;
   int splits_f, splits_b;  // split-K factors of the two GEMMs
   size_t total;
 };
@@ -409,6 +462,7 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.Npad = round_up(d.N, 16);
   w.ldz = d.r * w.Npad;
   w.gp_blocks = ceil_div(d.C1, 256) * d.N;
+  w.KB = ceil_div(d.K, kEpiRows);
   w.splits_f = hp_splits(d.C1, d.planes);
   w.splits_b = hp_splits(KT, d.planes);
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
@@ -417,9 +471,11 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.Ub = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldc * 2);
   w.RV = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldr * 2);
   w.Z = (float*)take((size_t)w.splits_f * KT * w.ldz * 4);
-  w.R = (float*)take((size_t)KT * w.Npad * 4);
   w.Gacc = (float*)take((size_t)w.splits_b * d.C1 * w.ldz * 4);
-  w.pv = (float*)take((size_t)KT * d.r * 4);
+  w.sse_part = (float*)take((size_t)d.T * w.KB * d.N * 4);
+  w.db_part = (float*)take((size_t)d.T * w.KB * d.N * 4);
+  w.pv_part = (float*)take((size_t)d.T * w.KB * d.r * 4);
+  w.bal = take(tc::balance_ws_bytes());
   w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
   w.G = (double*)take(kMaxR * kMaxR * 8);
   w.W = (double*)take(kMaxR * kMaxR * 8);
@@ -464,6 +520,7 @@ static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int eng
   g.B.ptr = w.Ub; g.B.rows = w.ldz; g.B.k = d.C1; g.B.ld = d.ldc; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldc;
   g.M = KT; g.N = w.ldz; g.K = d.C1; g.C = w.Z; g.ldc = w.ldz;
   g.splits = w.splits_f; g.split_stride = KT * w.ldz; g.splits_out = splits_used;
+  g.balance_ws = w.bal;
   set_passes(g, d.planes);
   return tc::gemm_tn(g, st);
 }
@@ -484,6 +541,7 @@ static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int eng
   g.B.ptr = w.RV; g.B.rows = w.ldz; g.B.k = KT; g.B.ld = d.ldr; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldr;
   g.M = d.C1; g.N = w.ldz; g.K = KT; g.C = w.Gacc; g.ldc = w.ldz;
   g.splits = w.splits_b; g.split_stride = d.C1 * w.ldz; g.splits_out = splits_used;
+  g.balance_ws = w.bal;
   set_passes(g, d.planes);
   return tc::gemm_tn(g, st);
 }
@@ -502,17 +560,17 @@ extern "C" size_t vs_rrr_workspace(vs_rrr_dims d) {
   return carve(d, nullptr).total;
 }
 
-extern "C" int vs_rrr_pack(const double* X_rows, int64_t row0, int64_t nrows, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
+extern "C" int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
                            float* xl, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
-  VS_REQUIRE(X_rows && Xa && Xb && xl, VS_ERR_INVALID, "vs_rrr_pack: null pointer");
-  const long long KT = d.K * d.T;
-  VS_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= KT, VS_ERR_INVALID, "vs_rrr_pack: row range outside the matrix");
-  dim3 grid((unsigned)ceil_div(nrows, 32), (unsigned)ceil_div(d.C1, 32));
+  VS_REQUIRE(X_trials && Xa && Xb && xl, VS_ERR_INVALID, "vs_rrr_pack: null pointer");
+  VS_REQUIRE(k0 >= 0 && nk > 0 && k0 + nk <= d.K, VS_ERR_INVALID, "vs_rrr_pack: trial range outside the matrix");
+  dim3 grid((unsigned)(ceil_div(nk, 32) * d.T), (unsigned)ceil_div(d.C1, 32));
   VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack: too many columns");
-  VS_LAUNCH((pack_kernel<false>), grid, 256, 0, stream, X_rows, nullptr, nullptr, nullptr, nullptr, 0ll, (long long)row0,
-            (long long)(row0 + nrows), KT, (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl);
+  VS_LAUNCH((pack_kernel<false>), grid, 256, 0, stream, X_trials, nullptr, nullptr, nullptr, nullptr, 0ll, (long long)k0,
+            (long long)(k0 + nk), (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb,
+            xl);
   return VS_OK;
 }
 
@@ -527,11 +585,10 @@ extern "C" int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* 
   int rc = check_dims(d);
   if (rc) return rc;
   VS_REQUIRE(frames && sorted_idx && mean && std_clipped && Xa && Xb && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8: bad arguments");
-  const long long KT = d.K * d.T;
-  dim3 grid((unsigned)ceil_div(KT, 32), (unsigned)ceil_div(d.C1, 32));
+  dim3 grid((unsigned)(ceil_div(d.K, 32) * d.T), (unsigned)ceil_div(d.C1, 32));
   VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8: too many columns");
-  VS_LAUNCH((pack_kernel<true>), grid, 256, 0, stream, nullptr, frames, sorted_idx, mean, std_clipped, (long long)Tf, 0ll, KT, KT,
-            (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl);
+  VS_LAUNCH((pack_kernel<true>), grid, 256, 0, stream, nullptr, frames, sorted_idx, mean, std_clipped, (long long)Tf, 0ll,
+            (long long)d.K, (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl);
   return VS_OK;
 }
 
@@ -553,17 +610,23 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   // stage 0: U planes + Gram partials, then G and W = V V^T
   dim3 g0((unsigned)ceil_div(d.C1, 256), (unsigned)d.N);
   VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
-  VS_LAUNCH(small_mats_kernel, 1, 64, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
+  VS_LAUNCH(small_mats_kernel, 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   // stage 1: Z
   int sf = 1, sb = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
-  // stage 2: residuals, RV, dV partials
-  VS_LAUNCH((epi_f_kernel<false>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, KT, (long long)d.T,
-            (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.R, w.RV, w.pv, nullptr);
+  // stage 2: residuals -> RV operand, per-block partials of SSE / db / dV
+  dim3 ge((unsigned)w.KB, (unsigned)d.T);
+  if (r <= 4) {
+    VS_LAUNCH((epi_f_kernel<false, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
+              (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
+  } else {
+    VS_LAUNCH((epi_f_kernel<false, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
+              (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
+  }
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
-  VS_LAUNCH(reduce_k_kernel, g2, 128, 0, st, w.R, xl, b, (long long)d.K, (long long)d.T, (long long)d.N, w.Npad, l2, db, w.sse_tn);
-  VS_LAUNCH(finalize_kernel, 1, 256, 0, st, w.sse_tn, w.pv, w.G, w.W, V, b, (long long)d.K, (long long)d.T, (long long)d.N, r, l2,
+  VS_LAUNCH(reduce_part_kernel, g2, 128, 0, st, w.sse_part, w.db_part, b, w.KB, (long long)d.T, (long long)d.N, l2, db, w.sse_tn);
+  VS_LAUNCH(finalize_kernel, 1, 256, 0, st, w.sse_tn, w.pv_part, w.G, w.W, V, b, w.KB, (long long)d.T, (long long)d.N, r, l2,
             sse_n, loss, dV);
   if (dU) {
     // stage 3/4: Gacc and dU
@@ -591,8 +654,14 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   int sf = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
-  VS_LAUNCH((epi_f_kernel<true>), (unsigned)ceil_div(KT, 32), 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, KT, (long long)d.T,
-            (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, yhat);
+  dim3 ge((unsigned)w.KB, (unsigned)d.T);
+  if (d.r <= 4) {
+    VS_LAUNCH((epi_f_kernel<true, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
+  } else {
+    VS_LAUNCH((epi_f_kernel<true, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
+  }
   return VS_OK;
 }
 

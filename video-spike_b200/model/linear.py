@@ -72,8 +72,11 @@ class _MlpBuffers:
         self.batch = batch
         self.act = [torch.empty((batch, lin.out_features), dtype=torch.float32, device=device) for lin, _ in layers]
         self.gact = [torch.empty_like(a) for a in self.act] if train else [None] * n
-        self.gW = ([None] + [torch.empty_like(lin.weight) for lin, _ in layers[1:]]) if train else [None] * n
-        self.gb = [torch.empty_like(lin.bias) if (train and lin.bias is not None) else None for lin, _ in layers]
+        # gradients are only materialised on the large-batch route (batch > 32); at the reference batch
+        # size they live in registers inside the fused dW+AdamW kernels
+        big = train and batch > 32
+        self.gW = [torch.empty_like(lin.weight) if big else None for lin, _ in layers]
+        self.gb = [torch.empty_like(lin.bias) if (big and lin.bias is not None) else None for lin, _ in layers]
         self.loss = torch.zeros(1, dtype=torch.float64, device=device)
 
 
@@ -106,9 +109,11 @@ class _MlpFunction(torch.autograd.Function):
                      and lin.in_features % 4 == 0 and lin.out_features * 128 <= 200 * 1024)
             dW = None if defer else torch.empty_like(lin.weight)
             db = torch.empty_like(lin.bias) if lin.bias is not None else None
+            need = int(vs.lib.vs_linear_bwd_workspace(batch, lin.in_features, lin.out_features)) if dx is not None else 0
+            ws = torch.empty(need, dtype=torch.uint8, device=g.device) if need else None
             vs.check(vs.lib.vs_linear_bwd(vs.ptr(g), vs.ptr(acts[l]), vs.ptr(x_f32), vs.ptr(x_u8), vs.ptr(lin.weight),
                                           vs.ptr(gm), vs.ptr(dx), vs.ptr(dW), vs.ptr(db), batch, lin.in_features,
-                                          lin.out_features, int(relu), st))
+                                          lin.out_features, int(relu), vs.ptr(ws), need, st))
             if defer:
                 # the first-layer gradient stays factored as (dy, x); FusedAdamW consumes it without
                 # ever materialising the (256, D) matrix

@@ -26,6 +26,7 @@ import torch.nn as nn
 from torch import optim
 
 import vsb200 as vs
+from optim import FusedLBFGS
 
 
 def np2tensor(v):
@@ -63,13 +64,12 @@ class _PackedSplit:
         self.Xa = torch.empty((planes, KT, d.ldc), dtype=torch.bfloat16, device=device)
         self.Xb = torch.empty((planes, C - 1, d.ldr), dtype=torch.bfloat16, device=device)
         self.xl = torch.empty(KT, dtype=torch.float32, device=device)
-        rows_per_chunk = max(1, min(KT, self.CHUNK_BYTES // (8 * C)))
-        flat = X.reshape(KT, C)
+        trials_per_chunk = max(1, min(K, self.CHUNK_BYTES // (8 * C * T)))
         st = vs.stream()
-        for r0 in range(0, KT, rows_per_chunk):
-            r1 = min(KT, r0 + rows_per_chunk)
-            chunk = torch.from_numpy(flat[r0:r1]).to(device=device, dtype=torch.float64)
-            vs.check(vs.lib.vs_rrr_pack(vs.ptr(chunk), r0, r1 - r0, d, vs.ptr(self.Xa), vs.ptr(self.Xb), vs.ptr(self.xl), st))
+        for k0 in range(0, K, trials_per_chunk):
+            k1 = min(K, k0 + trials_per_chunk)
+            chunk = torch.from_numpy(X[k0:k1]).to(device=device, dtype=torch.float64).contiguous()
+            vs.check(vs.lib.vs_rrr_pack(vs.ptr(chunk), k0, k1 - k0, d, vs.ptr(self.Xa), vs.ptr(self.Xb), vs.ptr(self.xl), st))
             del chunk
         self.y = torch.from_numpy(np.ascontiguousarray(y)).to(device=device, dtype=torch.float32).contiguous()
 
@@ -192,24 +192,32 @@ class RRRGD():
         sse = torch.empty(sp.N, dtype=torch.float64, device=dev)
         dU = db = None
         if want_grad:
-            dU, db = torch.empty_like(U), torch.empty_like(b)
+            dU, db = self._grad_buffer(U), self._grad_buffer(b)
         ws = self._workspace(sp.dims)
         vs.check(vs.lib.vs_rrr_closure(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
                                        vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
                                        vs.ptr(dV), vs.ptr(db), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
         return loss[0], sse, dU, db
 
+    @staticmethod
+    def _grad_buffer(p):
+        """`p.grad` if it can be written in place (FusedLBFGS keeps views of its flat gradient there), else a
+        fresh tensor installed as `p.grad`.  The kernels overwrite every element."""
+        g = p.grad
+        if g is None or not g.is_contiguous() or g.dtype != p.dtype or g.device != p.device or g.shape != p.shape:
+            g = torch.empty_like(p.data)
+            p.grad = g
+        return g
+
     def loss_and_grad(self, data, k=0):
         """The closure body of rrr.py:165-175: total loss over sessions, gradients into .grad."""
         V = self.model['V']
-        dV = torch.zeros_like(V)
+        dV = self._grad_buffer(V)
+        dV.zero_()                                  # accumulated over the sessions sharing V (rrr.py:46-49)
         total = None
         for eid in data:
             loss, _, dU, db = self._closure_eval(data, eid, k, True, dV)
-            self.model[f"{eid}_U"].grad = dU
-            self.model[f"{eid}_b"].grad = db
             total = loss if total is None else total + loss
-        V.grad = dV
         self.n_closure_evals += 1
         return total
 
@@ -280,7 +288,7 @@ def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None
     device = get_device()
     area_model.to(device)
     print(f"training on device: {device}")
-    optimizer = optim.LBFGS(area_model.model.parameters(),)
+    optimizer = FusedLBFGS(area_model.model.parameters(),)     # torch.optim.LBFGS semantics, device-side vector algebra
     _, mse_val = train_model(area_model, train_data, optimizer, model_fname=model_fname, save=save)
     return area_model, mse_val
 

@@ -15,6 +15,8 @@ Two ways to consume gradients:
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 import vsb200 as vs
@@ -76,7 +78,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     x_f32 = x if x.dtype == torch.float32 else None
                     x_u8 = x if x.dtype == torch.uint8 else None
                     vs.check(vs.lib.vs_dw_adamw_fused(vs.ptr(dy), vs.ptr(x_f32), vs.ptr(x_u8), vs.ptr(p.data),
-                                                      vs.ptr(st["exp_avg"]), vs.ptr(st["exp_avg_sq"]), dy.shape[0],
+                                                      vs.ptr(st["exp_avg"]), vs.ptr(st["exp_avg_sq"]), None, None, None, dy.shape[0],
                                                       p.shape[1], p.shape[0], h, stream))
                     p._vs_lowrank_grad = None
                 else:
@@ -91,3 +93,266 @@ class FusedAdamW(torch.optim.Optimizer):
                 if getattr(p, "_vs_lowrank_grad", None) is not None:
                     p._vs_lowrank_grad = None
         super().zero_grad(set_to_none=set_to_none)
+
+
+# =====================================================================================================
+# L-BFGS (R5)
+def lbfgs_two_loop(gg, sg, yg, SY, YY, H_diag):
+    """torch.optim.LBFGS's two-loop recursion in COEFFICIENT space (host, float64, m <= 100).
+
+    The direction d = -H*g is a linear combination of the basis {g, s_0..s_{m-1}, y_0..y_{m-1}}; the
+    recursion only needs inner products of basis vectors:  sg[i] = s_i.g, yg[i] = y_i.g,
+    SY[i][j] = s_i.y_j, YY[i][j] = y_i.y_j, gg = g.g.  Returns (cg, cs[m], cy[m], gtd) with
+    d = cg*g + sum cs[i]*s_i + cy[i]*y_i and gtd = g.d.  Pure numpy: unit-tested on the CPU against
+    the explicit vector recursion."""
+    import numpy as np
+    m = len(sg)
+    ro = [1.0 / SY[i][i] for i in range(m)]
+    al = [0.0] * m
+    # q = -g - sum_j al_j y_j  (coefficients: g -> -1, y_j -> -al_j)
+    for i in range(m - 1, -1, -1):
+        sq = -sg[i]
+        for j in range(i + 1, m):
+            sq -= al[j] * SY[i][j]
+        al[i] = sq * ro[i]
+    # r = H*q + sum_j (al_j - be_j) s_j
+    cs = [0.0] * m
+    for i in range(m):
+        yr = -yg[i]
+        for j in range(m):
+            yr -= al[j] * YY[i][j]
+        yr *= H_diag
+        for j in range(i):
+            yr += cs[j] * SY[j][i]
+        cs[i] = al[i] - yr * ro[i]
+    cg = -H_diag
+    cy = [-H_diag * a for a in al]
+    gtd = cg * gg + float(np.dot(cs, sg)) + float(np.dot(cy, yg)) if m else cg * gg
+    return cg, cs, cy, gtd
+
+
+class FusedLBFGS(torch.optim.Optimizer):
+    """torch.optim.LBFGS (no line search) as src/model/rrr.py:177,199 uses it -- same constructor, same
+    `step(closure)` contract, same iteration/termination logic -- with the vector algebra on libvs_b200:
+
+      * all parameters live in ONE flat float64 buffer (each `p.data` is rebound to a view of it) and the
+        gradient in a second one (`p.grad` views): no gather/scatter per iteration.  Two gradient buffers
+        ping-pong so "prev_flat_grad" is never copied.
+      * per iteration the device makes two streaming passes (vs_lbfgs_dots, vs_lbfgs_direction); the
+        two-loop recursion runs on the host in coefficient space (lbfgs_two_loop).
+      * one host<->device synchronisation per iteration (the scalars of vs_lbfgs_dots + the loss).
+
+    A closure that wants to avoid allocations writes gradients INTO the existing `p.grad` views
+    (model.rrr.RRRGD.loss_and_grad does); autograd closures work too (`zero_grad()` zeroes the views)."""
+
+    def __init__(self, params, lr=1, max_iter=20, max_eval=None, tolerance_grad=1e-7, tolerance_change=1e-9,
+                 history_size=100, line_search_fn=None):
+        if line_search_fn is not None:
+            raise vs.VsError("FusedLBFGS implements the fixed-step variant only (the reference never sets line_search_fn)")
+        if history_size > 100:
+            raise vs.VsError("FusedLBFGS: history_size > 100 (VS_LBFGS_MAX_HIST) is not supported")
+        if max_eval is None:
+            max_eval = max_iter * 5 // 4
+        super().__init__(params, dict(lr=lr, max_iter=max_iter, max_eval=max_eval, tolerance_grad=tolerance_grad,
+                                      tolerance_change=tolerance_change, history_size=history_size,
+                                      line_search_fn=line_search_fn))
+        if len(self.param_groups) != 1:
+            raise ValueError("LBFGS doesn't support per-parameter options (parameter groups)")
+        self._params = self.param_groups[0]["params"]
+        self._flat = None
+        self._pairs = []          # [(s_slot, y_slot)] oldest first
+        self._SY = []             # _SY[i][j] = s_i . y_j
+        self._YY = []             # _YY[i][j] = y_i . y_j
+        self._hist = None
+        self._free = []
+
+    # ---- flat storage -----------------------------------------------------------------------------
+    def _bind(self):
+        ps = self._params
+        dev = ps[0].device
+        for p in ps:
+            if not p.is_cuda or p.dtype != torch.float64 or p.device != dev:
+                raise vs.VsError("FusedLBFGS needs float64 CUDA parameters on one device (no CPU path)")
+        fl = self._flat
+        if fl is not None and all(p.data_ptr() == fl["x"].data_ptr() + 8 * a for p, (a, _) in zip(ps, fl["span"])):
+            return fl
+        n = sum(p.numel() for p in ps)
+        x = torch.empty(n, dtype=torch.float64, device=dev)
+        g = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(2)]
+        span, a = [], 0
+        for p in ps:
+            b = a + p.numel()
+            x[a:b].copy_(p.data.reshape(-1))
+            if p.grad is not None:
+                g[0][a:b].copy_(p.grad.reshape(-1))
+            p.data = x[a:b].view(p.shape)
+            span.append((a, b))
+            a = b
+        self._flat = fl = {"x": x, "g": g, "cur": 0, "span": span, "n": n}
+        self._point_grads(0)
+        m = self.param_groups[0]["history_size"]
+        self._scal = torch.zeros(8 + 6 * m + 8, dtype=torch.float64, device=dev)      # dots out | dmax | loss
+        self._ws = torch.empty(int(vs.lib.vs_lbfgs_workspace(n, m)), dtype=torch.uint8, device=dev)
+        self._pairs, self._SY, self._YY, self._hist, self._free = [], [], [], None, []
+        self.state[ps[0]].clear()
+        return fl
+
+    def _point_grads(self, which):
+        fl = self._flat
+        fl["cur"] = which
+        for p, (a, b) in zip(self._params, fl["span"]):
+            p.grad = fl["g"][which][a:b].view(p.shape)
+
+    def zero_grad(self, set_to_none: bool = True):
+        """Keeps the `p.grad` views alive (a reference-style closure calls this first, rrr.py:166)."""
+        if self._flat is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        self._flat["g"][self._flat["cur"]].zero_()
+
+    def _slot(self):
+        """A free history slot; the buffer grows in pairs-of-8 steps (each slot is one flat vector)."""
+        if not self._free:
+            n = self._flat["n"]
+            old = self._hist
+            have = 0 if old is None else old.shape[0]
+            grow = 2 * min(self.param_groups[0]["history_size"] + 1, max(8, self.param_groups[0]["max_iter"] + 1))
+            new = torch.empty((have + grow, n), dtype=torch.float64, device=self._flat["x"].device)
+            if old is not None:
+                new[:have].copy_(old)
+            self._hist = new
+            self._free = list(range(have, have + grow))
+        return self._free.pop(0)
+
+    # ---- device passes ----------------------------------------------------------------------------
+    def _dots(self, g, g_prev, s_slot, y_slot, loss_t):
+        """-> host numpy array [dots out (8+6m) ..., dmax, loss] after ONE synchronisation."""
+        import numpy as np
+        fl = self._flat
+        m = len(self._pairs)
+        ss = (C.c_int32 * max(m, 1))(*[p[0] for p in self._pairs])
+        ys = (C.c_int32 * max(m, 1))(*[p[1] for p in self._pairs])
+        hist = self._hist
+        vs.check(vs.lib.vs_lbfgs_dots(fl["n"], vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist[s_slot]) if s_slot is not None else None,
+                                      vs.ptr(hist[y_slot]) if y_slot is not None else None, vs.ptr(hist) if hist is not None else None,
+                                      fl["n"], ss, ys, m, vs.ptr(self._scal), vs.ptr(self._ws), self._ws.numel(), vs.stream()))
+        k = 8 + 6 * m
+        self._scal[-1:].copy_(torch.as_tensor(loss_t).detach().reshape(1))
+        host = self._scal.cpu().numpy()
+        return host[:k], float(host[-2]), float(host[-1])
+
+    @torch.no_grad()
+    def step(self, closure):
+        import numpy as np
+        closure = torch.enable_grad()(closure)
+        group = self.param_groups[0]
+        lr, max_iter, max_eval = float(group["lr"]), group["max_iter"], group["max_eval"]
+        tol_g, tol_c, hsize = group["tolerance_grad"], group["tolerance_change"], group["history_size"]
+        fl = self._bind()
+        state = self.state[self._params[0]]
+        state.setdefault("func_evals", 0)
+        state.setdefault("n_iter", 0)
+        n = fl["n"]
+
+        def evaluate():
+            """closure at the current x, written into the gradient buffer that does NOT hold torch's
+            `prev_flat_grad` (state["prev_buf"]); returns the scalars of one vs_lbfgs_dots pass."""
+            prev = state.get("prev_buf")
+            if prev is not None and fl["cur"] == prev:
+                self._point_grads(1 - prev)
+            loss_t = closure()
+            g = fl["g"][fl["cur"]]
+            g_prev = fl["g"][prev] if prev is not None else None
+            s_slot = state.get("s_slot")
+            y_slot = self._slot() if (g_prev is not None and s_slot is not None) else None
+            out, dmax, loss = self._dots(g, g_prev, s_slot if y_slot is not None else None, y_slot, loss_t)
+            return loss_t, loss, out, dmax, y_slot
+
+        orig_loss, loss, out, _, y_slot = evaluate()
+        current_evals = 1
+        state["func_evals"] += 1
+        if out[2] <= tol_g:
+            if y_slot is not None:
+                self._free.append(y_slot)
+            return orig_loss
+        H_diag = state.get("H_diag", 1.0)
+        prev_loss = state.get("prev_loss")
+        n_iter = 0
+        while n_iter < max_iter:
+            n_iter += 1
+            state["n_iter"] += 1
+            m = len(self._pairs)
+            gg, g1 = float(out[0]), float(out[1])
+            sg = [float(out[8 + 3 * i]) for i in range(m)]
+            yg = [float(out[8 + 3 * (m + i)]) for i in range(m)]
+            if state["n_iter"] == 1:
+                H_diag = 1.0
+            elif y_slot is not None:
+                yy, ys_new = float(out[3]), float(out[4])
+                s_slot = state["s_slot"]
+                if ys_new > 1e-10:
+                    sy_col = [float(out[8 + 3 * i + 1]) for i in range(m)]            # s_i . y_new
+                    yy_col = [float(out[8 + 3 * (m + i) + 1]) for i in range(m)]      # y_i . y_new
+                    ys_row = [float(out[8 + 3 * (m + i) + 2]) for i in range(m)]      # y_i . s_new = s_new . y_i
+                    if m == hsize:                                                     # limited memory: drop the oldest
+                        old = self._pairs.pop(0)
+                        self._free.extend(old)
+                        self._SY = [row[1:] for row in self._SY[1:]]
+                        self._YY = [row[1:] for row in self._YY[1:]]
+                        sy_col, yy_col, ys_row, sg, yg = sy_col[1:], yy_col[1:], ys_row[1:], sg[1:], yg[1:]
+                        m -= 1
+                    for i in range(m):
+                        self._SY[i].append(sy_col[i])
+                        self._YY[i].append(yy_col[i])
+                    self._SY.append(ys_row + [ys_new])
+                    self._YY.append(yy_col + [yy])
+                    self._pairs.append((s_slot, y_slot))
+                    sg.append(float(out[5]))
+                    yg.append(float(out[6]))
+                    H_diag = ys_new / yy
+                    state["s_slot"] = None
+                else:
+                    self._free.extend([s_slot, y_slot])
+                    state["s_slot"] = None
+                y_slot = None
+            m = len(self._pairs)
+            cg, cs, cy, gtd = lbfgs_two_loop(gg, sg, yg, self._SY, self._YY, H_diag)
+            state["prev_buf"] = fl["cur"]          # torch: prev_flat_grad.copy_(flat_grad) -- here a buffer swap
+            prev_loss = loss
+            t = min(1.0, 1.0 / g1) * lr if state["n_iter"] == 1 else lr
+            g = fl["g"][fl["cur"]]
+            ss = (C.c_int32 * max(m, 1))(*[p[0] for p in self._pairs])
+            ysl = (C.c_int32 * max(m, 1))(*[p[1] for p in self._pairs])
+            coef = (C.c_double * (2 * m + 1))(cg, *cs, *cy)
+            if state.get("s_slot") is not None:
+                self._free.append(state["s_slot"])
+            s_slot = self._slot()
+            hist = self._hist
+            stop_gtd = gtd > -tol_c
+            vs.check(vs.lib.vs_lbfgs_direction(n, vs.ptr(g), vs.ptr(hist), n, ss, ysl, m, coef, float(t),
+                                               None if stop_gtd else vs.ptr(fl["x"]), vs.ptr(hist[s_slot]),
+                                               vs.ptr(self._scal[-2:-1]), vs.stream()))
+            state["s_slot"] = s_slot
+            if stop_gtd:
+                break
+            ls_func_evals = 0
+            if n_iter != max_iter:
+                _, loss, out, dmax, y_slot = evaluate()
+                ls_func_evals = 1
+            current_evals += ls_func_evals
+            state["func_evals"] += ls_func_evals
+            if n_iter == max_iter:
+                break
+            if current_evals >= max_eval:
+                break
+            if out[2] <= tol_g:
+                break
+            if dmax <= tol_c:
+                break
+            if abs(loss - prev_loss) < tol_c:
+                break
+        # a y vector computed by the last evaluation but not consumed: recomputed by the next step()'s first pass
+        if y_slot is not None:
+            self._free.append(y_slot)
+        state["H_diag"] = H_diag
+        state["prev_loss"] = prev_loss
+        return orig_loss

@@ -54,10 +54,11 @@ def _load():
         "vs_u8_to_bf16": (C.c_int, [vp, vp, i64, vp]),
         "vs_linear_fwd_workspace": (sz, [i64, i64, i64]),
         "vs_linear_fwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, sz, vp]),
-        "vs_linear_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]),
+        "vs_linear_bwd_workspace": (sz, [i64, i64, i64]),
+        "vs_linear_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp, sz, vp]),
         "vs_poisson_nll": (C.c_int, [vp, vp, vp, vp, i64, vp]),
         "vs_adamw": (C.c_int, [vp, vp, vp, vp, i64, AdamWHyper, vp]),
-        "vs_dw_adamw_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i64, i64, AdamWHyper, vp]),
+        "vs_dw_adamw_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, AdamWHyper, vp]),
         "vs_mlp_workspace": (sz, [C.POINTER(Mlp), i64]),
         "vs_mlp_train_step": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, AdamWHyper, vp, i32, vp, sz, vp]),
         "vs_mlp_forward": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, vp, i32, vp, sz, vp]),
@@ -71,6 +72,9 @@ def _load():
         "vs_rrr_workspace": (sz, [RrrDims]),
         "vs_rrr_closure": (C.c_int, [RrrDims, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
         "vs_rrr_predict": (C.c_int, [RrrDims, vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
+        "vs_lbfgs_workspace": (sz, [i64, i32]),
+        "vs_lbfgs_dots": (C.c_int, [i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, sz, vp]),
+        "vs_lbfgs_direction": (C.c_int, [i64, vp, vp, i64, vp, vp, i32, vp, dbl, vp, vp, vp, vp]),
         "vs_gemm_tn": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]),
         "vs_launch_count": (i64, []),
         "vs_launch_count_reset": (None, []),
