@@ -55,6 +55,14 @@ int vs_device_ok(void);
 int vs_u8_to_f32(const uint8_t* frames, float* out, int64_t n, void* stream);
 int vs_u8_to_bf16(const uint8_t* frames, uint16_t* out_bf16, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ trial windows (L0)
+ * src/utils/ibl_data_utils.py:958-967 defines each trial as frames [start, start + 120) of the session video with
+ * start = searchsorted(timestamps, t0) (host, utils/dataset_utils.py::load_video_index).  This cuts the windows on
+ * the device: frames (n_frames, row_bytes) uint8, start_idx (n_trials) int64 -> out (n_trials, frames_per_trial,
+ * row_bytes).  Byte copy, bit-exact; frames past the end of the video read as 0.                              */
+int vs_gather_windows(const uint8_t* frames, int64_t n_frames, int64_t row_bytes, const int64_t* start_idx,
+                      int64_t n_trials, int64_t frames_per_trial, uint8_t* out, void* stream);
+
 /* ------------------------------------------------------------------ Linear layers (M1-M3, G1)
  * torch.nn.Linear / ReLU as used by src/model/linear.py:24-32,45-53.
  *   y[b,o] = act( sum_i x[b,i] * W[o,i] + bias[o] ),  W is (out,in) row-major like nn.Linear.
@@ -227,6 +235,22 @@ int vs_lbfgs_direction(int64_t n, const double* g, const double* hist, int64_t h
                        const int32_t* s_slots_host, const int32_t* y_slots_host, int m,
                        const double* coef_host, double t, double* x, double* s_out, double* dmax_out,
                        void* stream);
+
+/* ------------------------------------------------------------------ RRR initialisation stream (R1, HOST)
+ * src/model/rrr.py:35,42-43 draws U and V from numpy's global legacy RandomState after np.random.seed(0).
+ * These HOST functions (the only entry points that take host pointers and launch nothing) reproduce that
+ * stream bit for bit -- MT19937 seeded like RandomState.seed(uint32), 53-bit doubles from two words, the polar
+ * legacy_gauss with its cached second value, libm log/sqrt -- with the transform spread over `threads` host
+ * threads (0 = all cores); only the MT19937 recurrence is sequential.
+ * state: caller-allocated blob of VS_HOST_RNG_STATE_BYTES.  vs_host_rng_normal writes the next n normals,
+ * each divided by `divisor` (rrr.py divides by sqrt(T*ncomp); pass 1.0 for plain draws).
+ * get/set_state exchange numpy's ('MT19937', key[624], pos, has_gauss, cached_gaussian) tuple so the global
+ * numpy stream can be left exactly where the reference would leave it.                              */
+#define VS_HOST_RNG_STATE_BYTES 2560
+int vs_host_rng_seed(void* state, uint32_t seed);
+int vs_host_rng_normal(void* state, int64_t n, double divisor, double* out_host, int threads);
+int vs_host_rng_get_state(const void* state, uint32_t* key624, int32_t* pos, int32_t* has_gauss, double* cached);
+int vs_host_rng_set_state(void* state, const uint32_t* key624, int32_t pos, int32_t has_gauss, double cached);
 
 /* ------------------------------------------------------------------ plain TN GEMM (test hook)
  * C[M,N] (fp32, row-major, ldc) = A[M,K] * B[N,K]^T with bf16 or tf32(fp32) operands, both

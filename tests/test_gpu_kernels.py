@@ -205,3 +205,24 @@ def test_error_paths(vs, cuda):
     assert rc == 3
     rc = vs.lib.vs_linear_fwd(vs.ptr(x), None, vs.ptr(x), None, vs.ptr(x), 1, 8192, 1, 0, 0, None, 0, vs.stream())
     assert rc == 4                                             # workspace too small
+
+
+# ----------------------------------------------------------------------------- trial windows (L0)
+@pytest.mark.parametrize("hw", [(16, 16), (11, 166 // 2), (5, 3)])      # 16-byte, 4-byte... and byte-granular rows
+def test_gather_windows_bit_exact(vs, cuda, hw):
+    from oracle import loader_oracle as lo
+    from utils.dataset_utils import gather_trial_windows, load_video_index
+    rng = np.random.default_rng(1)
+    n_frames = 3000
+    video = rng.integers(0, 256, size=(n_frames,) + hw, dtype=np.uint8)
+    ts = np.cumsum(rng.uniform(0.95, 1.05, size=n_frames) / 60.0)
+    t0 = np.sort(rng.uniform(ts[10], ts[-300], size=13))
+    idx = load_video_index(ts, np.stack([t0, t0 + 2.0], 1), 60.0)
+    ref = lo.cut_windows(video, lo.load_video_index(ts, np.stack([t0, t0 + 2.0], 1), 60.0))
+    got = gather_trial_windows(torch.from_numpy(video).to(cuda), idx[:, 0])
+    assert got.shape == ref.shape and got.dtype == torch.uint8
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    # a window that runs off the end of the video is zero-filled
+    tail = gather_trial_windows(torch.from_numpy(video).to(cuda), np.array([n_frames - 50]))
+    assert torch.equal(tail[0, :50].cpu(), torch.from_numpy(video[-50:])) and int(tail[0, 50:].max()) == 0
+    assert gather_trial_windows(torch.from_numpy(video).to(cuda), np.zeros(0, dtype=np.int64)).shape[0] == 0

@@ -119,3 +119,83 @@ def test_model_structure_matches_reference_layout():
     assert model.output_dim == 3
     assert opt.param_groups[0]["lr"] == pytest.approx(5e-6)            # OneCycleLR start = max_lr / div_factor
     assert opt.param_groups[0]["betas"][0] == pytest.approx(0.95)       # cycle_momentum drives beta1
+
+
+# ----------------------------------------------------------------------------- RRR initialisation stream (R1)
+@pytest.mark.parametrize("shapes", [[(7, 50, 3), (3, 100)], [(1,), (2,), (3,), (1, 1), (5000, 3)], [(3, 5, 3), (3, 100)] * 3])
+def test_host_normal_stream_is_numpys_legacy_stream_bit_for_bit(shapes):
+    """csrc/host_rng.cpp vs np.random.seed(0); np.random.normal(size)/sqrt(300) (src/model/rrr.py:35,42-43):
+    identical doubles, identical generator state afterwards (key, pos, cached gaussian), any thread count."""
+    import vsb200 as vs
+    div = float(np.sqrt(300))
+    np.random.seed(0)
+    ref = [np.random.normal(size=s) / np.sqrt(300) for s in shapes]
+    st_ref = np.random.get_state()
+    for threads in (1, 3, 0):
+        g = vs.LegacyNormalStream(0)
+        got = [g.normal(s, div, threads) for s in shapes]
+        for a, b in zip(ref, got):
+            np.testing.assert_array_equal(a, b)
+        np.random.seed(12345)
+        g.export_to_numpy()
+        st = np.random.get_state()
+        assert st[0] == st_ref[0] and st[2:] == st_ref[2:]
+        np.testing.assert_array_equal(st[1], st_ref[1])
+
+
+def test_host_normal_stream_long_run_and_other_seed():
+    import vsb200 as vs
+    np.random.seed(42)
+    ref = np.random.normal(size=1_000_003)
+    tail = np.random.normal(size=5)
+    g = vs.LegacyNormalStream(42)
+    np.testing.assert_array_equal(g.normal((1_000_003,)), ref)
+    np.testing.assert_array_equal(g.normal((5,)), tail)          # odd count: the cached second value comes first
+
+
+def test_rrrgd_init_equals_reference_init():
+    """RRRGD.__init__ (rrr.py:30-54) through the host generator == the oracle's numpy transcription, and the
+    global numpy stream is left where the reference leaves it."""
+    from model.rrr import RRRGD
+    from oracle import rrr_oracle as ro
+    from tests.helpers import small_rrr_problem
+    td = {**small_rrr_problem(seed=4, K=16, Kt=5, F=70, N=6, eid="s1"), **small_rrr_problem(seed=5, K=12, Kt=5, F=90, N=11, eid="s2")}
+    ref = ro.rrr_init(td, 3)
+    after_ref = np.random.normal()
+    m = RRRGD(td, 3, l2=100.0)
+    after = np.random.normal()
+    assert set(m.model.keys()) == set(ref.keys())       # nn.ParameterDict sorts a plain dict by key, here as in the reference
+    for k, v in ref.items():
+        np.testing.assert_array_equal(m.model[k].detach().numpy(), v)
+    assert after == after_ref
+
+
+# ----------------------------------------------------------------------------- frame windows (L0)
+def test_load_video_index_matches_oracle_bit_exact():
+    from oracle import loader_oracle as lo
+    from utils.dataset_utils import load_video_index
+    rng = np.random.default_rng(3)
+    fps = 60.0
+    ts = np.cumsum(rng.uniform(0.9, 1.1, size=20000) / fps)             # jittered camera clock
+    t0 = np.sort(rng.uniform(ts[200], ts[-400], size=57))
+    intervals = np.stack([t0, t0 + 2.0], axis=1)
+    ref = lo.load_video_index(ts, intervals, fps)
+    got = load_video_index(ts, intervals, fps)
+    assert got.dtype == np.int64 and got.shape == (57, 120)
+    np.testing.assert_array_equal(got, ref)
+    # a start that coincides with a timestamp takes that very frame (searchsorted side='left')
+    intervals[0] = (ts[1000], ts[1000] + 2.0)
+    assert load_video_index(ts, intervals, fps)[0, 0] == 1000 == lo.load_video_index(ts, intervals, fps)[0, 0]
+    # dropped frames -> the reference raises, so do we
+    bad = np.delete(ts, np.arange(3000, 3030))
+    with pytest.raises(ValueError):
+        load_video_index(bad, np.array([[bad[2990], bad[2990] + 2.0]]), fps)
+    with pytest.raises(ValueError):
+        lo.load_video_index(bad, np.array([[bad[2990], bad[2990] + 2.0]]), fps)
+
+
+def test_select_frames_is_the_reference_draw(golden_dir):
+    from utils.utils import select_frames, set_seed
+    g = np.load(os.path.join(golden_dir, "metrics_kat.npz"))
+    set_seed(42)
+    np.testing.assert_array_equal(select_frames(), g["sorted_idx"])

@@ -1,0 +1,27 @@
+"""Phase breakdown of the RRR end-to-end fit (bench.py's e2e path) with a synchronize after each phase."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "video-spike_b200"), ROOT]
+import numpy as np, torch
+import bench
+import vsb200 as vs
+from model.rrr import RRRGD, pack_session_from_frames, train_model
+from optim import FusedLBFGS
+
+K, Kt, F, N = 400, 80, 110 * 166, 144
+ftr, ctr, fte, cte = bench.rrr_inputs(K, Kt, F, N, 0, pinned=True)
+sidx = bench.sorted_idx_42()
+dev = torch.device("cuda")
+for it in range(3):
+    T = {}
+    def tick(name, t0):
+        torch.cuda.synchronize(); T[name] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); a = ftr.to(dev, non_blocking=True); b = fte.to(dev, non_blocking=True); tick("h2d_frames", t0)
+    del a, b
+    t0 = time.perf_counter(); entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=1); tick("pack(h2d+R0)", t0)
+    td = {"s": entry}
+    t0 = time.perf_counter(); model = RRRGD(td, 3, l2=100.0, planes=1); tick("RRRGD.__init__", t0)
+    t0 = time.perf_counter(); model.to(dev); tick("to(device)", t0)
+    t0 = time.perf_counter(); opt = FusedLBFGS(model.model.parameters()); _, res = train_model(model, td, opt, "tmp", save=False); v = float(res["mse_val_mean"]); tick("fit+val", t0)
+    print(it, {k: round(v, 2) for k, v in T.items()}, "sum", round(sum(list(T.values())[1:]), 1))
+    del model, opt, td, entry

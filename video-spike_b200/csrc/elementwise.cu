@@ -43,6 +43,36 @@ __global__ void __launch_bounds__(256) u8_to_bf16_kernel(const uint8_t* __restri
     out[n8 * 8 + threadIdx.x] = (uint16_t)(__float_as_uint((float)in[n8 * 8 + threadIdx.x]) >> 16);
 }
 
+// ------------------------------------------------------------------ trial windows (L0)
+// out[trial][f][:] = frames[start[trial] + f][:] for f < F: F consecutive frames are contiguous in the session video,
+// so every window is ONE contiguous copy of F*row bytes.  VEC = bytes per access (16, 4 or 1, chosen by the host from
+// the alignment row guarantees).  Frames past the end of the video read as 0.
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_windows_kernel(const uint8_t* __restrict__ frames, long long n_frames, long long row,
+                                                             const long long* __restrict__ start, long long F,
+                                                             uint8_t* __restrict__ out) {
+  const long long trial = blockIdx.y;
+  const long long s0 = start[trial];
+  const long long bytes = F * row, units = bytes / VEC;
+  const long long src0 = s0 * row, limit = n_frames * row;
+  uint8_t* dst = out + trial * bytes;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+    const long long off = src0 + u * VEC;
+    const bool in = off >= 0 && off + VEC <= limit;
+    if constexpr (VEC == 16) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (in) v = ld_stream_u4(reinterpret_cast<const uint4*>(frames + off));
+      *reinterpret_cast<uint4*>(dst + u * 16) = v;
+    } else if constexpr (VEC == 4) {
+      uint32_t v = 0;
+      if (in) v = __ldg(reinterpret_cast<const uint32_t*>(frames + off));
+      *reinterpret_cast<uint32_t*>(dst + u * 4) = v;
+    } else {
+      dst[u] = in ? __ldg(frames + off) : (uint8_t)0;
+    }
+  }
+}
+
 static unsigned stream_grid(long long work_items, int per_block) {
   long long blocks = ceil_div(work_items, per_block);
   const long long cap = (long long)kNumSMs * 16;
@@ -255,6 +285,30 @@ extern "C" int vs_u8_to_bf16(const uint8_t* frames, uint16_t* out, int64_t n, vo
   VS_REQUIRE(((uintptr_t)frames & 7) == 0 && ((uintptr_t)out & 15) == 0, VS_ERR_INVALID, "vs_u8_to_bf16: misaligned buffers");
   const long long n8 = n / 8;
   VS_LAUNCH(u8_to_bf16_kernel, stream_grid(n8, 256 * 4), 256, 0, stream, frames, out, n8, (long long)n);
+  return VS_OK;
+}
+
+extern "C" int vs_gather_windows(const uint8_t* frames, int64_t n_frames, int64_t row_bytes, const int64_t* start_idx,
+                                 int64_t n_trials, int64_t frames_per_trial, uint8_t* out, void* stream) {
+  VS_REQUIRE(frames && start_idx && out && n_frames > 0 && row_bytes > 0 && frames_per_trial > 0 && n_trials >= 0, VS_ERR_INVALID,
+             "vs_gather_windows: bad arguments");
+  if (n_trials == 0) return VS_OK;
+  VS_REQUIRE(n_trials <= 65535, VS_ERR_UNSUPPORTED, "vs_gather_windows: more than 65535 trials per call");
+  const long long bytes = frames_per_trial * row_bytes;
+  const uintptr_t al = (uintptr_t)frames | (uintptr_t)out;
+  if (row_bytes % 16 == 0 && (al & 15) == 0) {
+    dim3 grid(stream_grid(bytes / 16, 256 * 4) > 64 ? 64 : stream_grid(bytes / 16, 256 * 4), (unsigned)n_trials);
+    VS_LAUNCH(gather_windows_kernel<16>, grid, 256, 0, stream, frames, (long long)n_frames, (long long)row_bytes,
+              reinterpret_cast<const long long*>(start_idx), (long long)frames_per_trial, out);
+  } else if (row_bytes % 4 == 0 && (al & 3) == 0) {
+    dim3 grid(stream_grid(bytes / 4, 256 * 4) > 64 ? 64 : stream_grid(bytes / 4, 256 * 4), (unsigned)n_trials);
+    VS_LAUNCH(gather_windows_kernel<4>, grid, 256, 0, stream, frames, (long long)n_frames, (long long)row_bytes,
+              reinterpret_cast<const long long*>(start_idx), (long long)frames_per_trial, out);
+  } else {
+    dim3 grid(stream_grid(bytes, 256 * 4) > 64 ? 64 : stream_grid(bytes, 256 * 4), (unsigned)n_trials);
+    VS_LAUNCH(gather_windows_kernel<1>, grid, 256, 0, stream, frames, (long long)n_frames, (long long)row_bytes,
+              reinterpret_cast<const long long*>(start_idx), (long long)frames_per_trial, out);
+  }
   return VS_OK;
 }
 

@@ -150,48 +150,69 @@ __global__ void colstats_f32_kernel(const float* __restrict__ x, long long K, lo
 }
 
 // ------------------------------------------------------------------ closure stage 0: U -> Ub planes, Gram partials
-// Ub[p][j*Npad + n][c] = plane p of U[n][c][j];  Gp[block][i*r+j] = sum over the block's (n,c) of U_i U_j
+// Ub[p][j*Npad + n][c] = plane p of U[n][c][j];  Gp[block][i*r+j] = sum over the block's (n,c) of U_i U_j.
+// One thread owns kPrepC consecutive features of one neuron: its r*kPrepC doubles are contiguous in U.
+constexpr int kPrepC = 4;
+template <int RMAX>
 __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ U, long long N, long long Npad, long long C1,
                                                      int r, int planes, long long ldc, uint16_t* __restrict__ Ub,
                                                      double* __restrict__ Gp) {
-  __shared__ double red[8][kMaxR * kMaxR];
+  __shared__ double red[8][RMAX * RMAX];
   const long long n = blockIdx.y;
-  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long c0 = ((long long)blockIdx.x * 256 + threadIdx.x) * kPrepC;
   const long long pu = (long long)r * Npad * ldc;
-  double u[kMaxR];
-  const bool ok = c < C1;
+  double g[RMAX * RMAX];
 #pragma unroll
-  for (int j = 0; j < kMaxR; ++j) u[j] = (ok && j < r) ? U[(n * C1 + c) * r + j] : 0.0;
-  if (ok) {
-    for (int j = 0; j < r; ++j) {
+  for (int e = 0; e < RMAX * RMAX; ++e) g[e] = 0.0;
+#pragma unroll
+  for (int q = 0; q < kPrepC; ++q) {
+    const long long c = c0 + q;
+    if (c >= C1) break;
+    double u[RMAX];
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) u[j] = j < r ? U[(n * C1 + c) * r + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      if (j >= r) break;
       uint16_t pl[3];
       split_planes(u[j], planes, pl);
       for (int p = 0; p < planes; ++p) Ub[p * pu + ((long long)j * Npad + n) * ldc + c] = pl[p];
     }
+    if (Gp) {
+#pragma unroll
+      for (int i = 0; i < RMAX; ++i)
+#pragma unroll
+        for (int j = i; j < RMAX; ++j)
+          if (j < r) g[i * RMAX + j] = fma(u[i], u[j], g[i * RMAX + j]);
+    }
   }
   if (Gp) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = 0; i < r; ++i)
-      for (int j = 0; j < r; ++j) {
-        const double s = warp_sum(u[i] * u[j]);
-        if (lane == 0) red[warp][i * r + j] = s;
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+#pragma unroll
+      for (int j = i; j < RMAX; ++j) {
+        if (j >= r) continue;
+        const double sum = warp_sum(g[i * RMAX + j]);
+        if (lane == 0) { red[warp][i * r + j] = sum; red[warp][j * r + i] = sum; }
       }
     __syncthreads();
     if (threadIdx.x < r * r) {
-      double s = 0.0;
-      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-      Gp[((long long)blockIdx.y * gridDim.x + blockIdx.x) * (r * r) + threadIdx.x] = s;
+      double sum = 0.0;
+      for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+      Gp[((long long)blockIdx.y * gridDim.x + blockIdx.x) * (r * r) + threadIdx.x] = sum;
     }
   }
 }
 
-// G = sum of Gram partials, W = V V^T.  One block; thread i sums partials i, i+256, ... and the 256 lane sums
-// are then added in a fixed tree order, so the result does not depend on scheduling.
+// G = sum of Gram partials (block e < r*r: thread i sums partials i, i+256, ... then a fixed tree, so the result does
+// not depend on scheduling); the last block forms W = V V^T.
 __global__ void __launch_bounds__(256) small_mats_kernel(const double* __restrict__ Gp, long long nblocks, const double* __restrict__ V,
                                                          int r, long long T, double* __restrict__ G, double* __restrict__ W) {
   __shared__ double red[256];
   const int rr = r * r;
-  for (int e = 0; e < rr; ++e) {
+  const int e = blockIdx.x;
+  if (e < rr) {
     double s = 0.0;
     if (Gp)
       for (long long b = threadIdx.x; b < nblocks; b += 256) s += Gp[b * rr + e];
@@ -202,9 +223,7 @@ __global__ void __launch_bounds__(256) small_mats_kernel(const double* __restric
       __syncthreads();
     }
     if (threadIdx.x == 0) G[e] = red[0];
-    __syncthreads();
-  }
-  if (threadIdx.x < rr) {
+  } else if (threadIdx.x < rr) {
     const int i = threadIdx.x / r, j = threadIdx.x % r;
     double w = 0.0;
     for (long long t = 0; t < T; ++t) w += V[i * T + t] * V[j * T + t];
@@ -213,11 +232,11 @@ __global__ void __launch_bounds__(256) small_mats_kernel(const double* __restric
 }
 
 // ------------------------------------------------------------------ closure stage 2: epilogue of GEMM-F
-// block (kb, t) = 64 trials of time bin t x all neurons (tiles of 32).  Phase 1 (lanes over n): yhat, residual,
-// per-block partials of SSE, db and dV.  Phase 2 (lanes over trial pairs): RV[p][(j,n)][d] = planes of
-// V[j,t] * R, the B operand of GEMM-B, written as bf16x2.  The residual itself never goes to HBM.
 constexpr int kEpiRows = 64;
 
+// block (kb, t, nt) = 64 trials of time bin t x 32 neurons.  Phase 1 (lanes over n): yhat, residual, per-block
+// partials of SSE, db and dV.  Phase 2 (lanes over trial pairs): RV[p][(j,n)][d] = planes of V[j,t] * R, the B
+// operand of GEMM-B, written as bf16x2.  The residual itself never goes to HBM.
 template <bool kPredict, int RMAX>
 __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, int splits, long long split_stride,
                                                     const float* __restrict__ y, const float* __restrict__ xl,
@@ -231,8 +250,8 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
   __shared__ float xls[kEpiRows];
   __shared__ float pvs[8][RMAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long t = blockIdx.y, kb = blockIdx.x, KB = gridDim.x;
-  const long long k0 = kb * kEpiRows, d0 = t * K + k0;
+  const long long kb = blockIdx.x, t = blockIdx.y, nt = blockIdx.z, KB = gridDim.x, NT = gridDim.z;
+  const long long k0 = kb * kEpiRows, d0 = t * K + k0, n0 = nt * 32;
   float vt[RMAX];
 #pragma unroll
   for (int j = 0; j < RMAX; ++j) vt[j] = j < r ? (float)V[(long long)j * T + t] : 0.f;
@@ -241,101 +260,107 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
   float pvacc[RMAX];
 #pragma unroll
   for (int j = 0; j < RMAX; ++j) pvacc[j] = 0.f;
-  const long long prv = (long long)r * Npad * ldr;
-  const bool pair_ok = ((d0 & 1) == 0);
-  for (long long n0 = 0; n0 < N; n0 += 32) {
-    const long long n = n0 + lane;
-    const float bn = n < N ? (float)b[n * T + t] : 0.f;
-    float sse = 0.f, sdb = 0.f;
+  const long long n = n0 + lane;
+  const float bn = n < N ? (float)b[n * T + t] : 0.f;
+  float sse = 0.f, sdb = 0.f;
+  constexpr int RPW = kEpiRows / 8;   // rows per warp
+  // all loads of the block's tile are issued before the first use
+  float z[RPW][RMAX], yv[RPW];
 #pragma unroll
-    for (int i = 0; i < kEpiRows / 8; ++i) {
-      const int rl = w * (kEpiRows / 8) + i;
-      const long long k = k0 + rl, d = d0 + rl;
-      float res = 0.f;
-      if (k < K && n < N) {
-        float acc = xls[rl] * bn;
-        float z[RMAX];
+  for (int i = 0; i < RPW; ++i) {
+    const int rl = w * RPW + i;
+    const long long k = k0 + rl, d = d0 + rl;
+    const bool ok = k < K && n < N;
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j) {
-          if (j < r) {
-            const float* zp = Z + d * ldz + (long long)j * Npad + n;
-            if (splits == 1) {
-              z[j] = __ldg(zp);
-            } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator
-              double zs = 0.0;
+    for (int j = 0; j < RMAX; ++j) {
+      z[i][j] = 0.f;
+      if (ok && j < r) {
+        const float* zp = Z + d * ldz + (long long)j * Npad + n;
+        if (splits == 1) {
+          z[i][j] = __ldg(zp);
+        } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator
+          double zs = 0.0;
 #pragma unroll 1
-              for (int sp = 0; sp < splits; ++sp) zs += (double)zp[(long long)sp * split_stride];
-              z[j] = (float)zs;
-            }
-            acc = fmaf(vt[j], z[j], acc);
-          }
-        }
-        if constexpr (kPredict) {
-          yhat[(k * T + t) * N + n] = (double)acc;
-        } else {
-          res = acc - __ldg(y + (k * T + t) * N + n);
-          sse = fmaf(res, res, sse);
-          sdb = fmaf(xls[rl], res, sdb);
-#pragma unroll
-          for (int j = 0; j < RMAX; ++j)
-            if (j < r) pvacc[j] = fmaf(res, z[j], pvacc[j]);
+          for (int sp = 0; sp < splits; ++sp) zs += (double)zp[(long long)sp * split_stride];
+          z[i][j] = (float)zs;
         }
       }
-      if constexpr (!kPredict) Rs[rl][lane] = res;
     }
-    if constexpr (!kPredict) {
-      red[w][lane][0] = sse;
-      red[w][lane][1] = sdb;
-      __syncthreads();
-      // phase 2: lane = trial pair (2*lane, 2*lane+1), warp w covers neurons w*4 .. w*4+3 of the tile
+    if constexpr (!kPredict) yv[i] = ok ? __ldg(y + (k * T + t) * N + n) : 0.f;
+  }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int nl = w * 4 + i;
-        const long long nn = n0 + nl;
-        if (nn >= N) continue;
-        const float r0v = Rs[2 * lane][nl], r1v = Rs[2 * lane + 1][nl];
-        const long long ka = k0 + 2 * lane;
+  for (int i = 0; i < RPW; ++i) {
+    const int rl = w * RPW + i;
+    const long long k = k0 + rl;
+    float res = 0.f;
+    if (k < K && n < N) {
+      float acc = xls[rl] * bn;
 #pragma unroll
-        for (int j = 0; j < RMAX; ++j) {
-          if (j >= r) continue;
-          uint16_t pl0[3], pl1[3];
-          split_planes((double)(vt[j] * r0v), planes, pl0);
-          split_planes((double)(vt[j] * r1v), planes, pl1);
+      for (int j = 0; j < RMAX; ++j)
+        if (j < r) acc = fmaf(vt[j], z[i][j], acc);
+      if constexpr (kPredict) {
+        yhat[(k * T + t) * N + n] = (double)acc;
+      } else {
+        res = acc - yv[i];
+        sse = fmaf(res, res, sse);
+        sdb = fmaf(xls[rl], res, sdb);
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            if (p >= planes) continue;
-            uint16_t* dst = RV + p * prv + ((long long)j * Npad + nn) * ldr + d0 + 2 * lane;
-            if (pair_ok && ka + 1 < K) {
-              *reinterpret_cast<uint32_t*>(dst) = (uint32_t)pl0[p] | ((uint32_t)pl1[p] << 16);
-            } else {
-              if (ka < K) dst[0] = pl0[p];
-              if (ka + 1 < K) dst[1] = pl1[p];
-            }
-          }
-        }
+        for (int j = 0; j < RMAX; ++j)
+          if (j < r) pvacc[j] = fmaf(res, z[i][j], pvacc[j]);
       }
-      // phase 3: per-(t, kb, n) partials, the 8 warps' sums added in a fixed order
-      if (w == 0 && n < N) {
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) { s0 += red[w2][lane][0]; s1 += red[w2][lane][1]; }
-        sse_part[(t * KB + kb) * N + n] = s0;
-        db_part[(t * KB + kb) * N + n] = s1;
-      }
-      __syncthreads();
     }
+    if constexpr (!kPredict) Rs[rl][lane] = res;
   }
   if constexpr (!kPredict) {
+    red[w][lane][0] = sse;
+    red[w][lane][1] = sdb;
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
       const float s = warp_sum(pvacc[j]);
       if (lane == 0) pvs[w][j] = s;
     }
     __syncthreads();
+    // phase 2: lane = trial pair (2*lane, 2*lane+1), warp w covers neurons w*4 .. w*4+3 of the tile
+    const long long prv = (long long)r * Npad * ldr;
+    const bool pair_ok = ((d0 & 1) == 0);
+    const long long ka = k0 + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int nl = w * 4 + i;
+      const long long nn = n0 + nl;
+      if (nn >= N) continue;
+      const float r0v = Rs[2 * lane][nl], r1v = Rs[2 * lane + 1][nl];
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        if (j >= r) continue;
+        uint16_t pl0[3], pl1[3];
+        split_planes((double)(vt[j] * r0v), planes, pl0);
+        split_planes((double)(vt[j] * r1v), planes, pl1);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          if (p >= planes) continue;
+          uint16_t* dst = RV + p * prv + ((long long)j * Npad + nn) * ldr + d0 + 2 * lane;
+          if (pair_ok && ka + 1 < K) {
+            *reinterpret_cast<uint32_t*>(dst) = (uint32_t)pl0[p] | ((uint32_t)pl1[p] << 16);
+          } else {
+            if (ka < K) dst[0] = pl0[p];
+            if (ka + 1 < K) dst[1] = pl1[p];
+          }
+        }
+      }
+    }
+    // phase 3: per-(t, kb, n) partials, the 8 warps' sums added in a fixed order
+    if (w == 0 && n < N) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < 8; ++w2) { s0 += red[w2][lane][0]; s1 += red[w2][lane][1]; }
+      sse_part[(t * KB + kb) * N + n] = s0;
+      db_part[(t * KB + kb) * N + n] = s1;
+    }
     if (threadIdx.x < r) {
       float s = 0.f;
       for (int w2 = 0; w2 < 8; ++w2) s += pvs[w2][threadIdx.x];
-      pv_part[(t * KB + kb) * r + threadIdx.x] = s;
+      pv_part[((t * KB + kb) * NT + nt) * r + threadIdx.x] = s;
     }
   }
 }
@@ -360,7 +385,7 @@ __global__ void __launch_bounds__(128) reduce_part_kernel(const float* __restric
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv_part,
                                                        const double* __restrict__ G, const double* __restrict__ W,
                                                        const double* __restrict__ V, const double* __restrict__ b, long long KB,
-                                                       long long T, long long N, int r, double l2, double* __restrict__ sse_n,
+                                                       long long NT, long long T, long long N, int r, double l2, double* __restrict__ sse_n,
                                                        double* __restrict__ loss, double* __restrict__ dV) {
   __shared__ double red[256];
   // per-neuron SSE (src/model/rrr.py:151) and its total
@@ -389,7 +414,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     for (long long e = threadIdx.x; e < (long long)r * T; e += 256) {
       const long long j = e / T, t = e % T;
       double s = 0.0;
-      for (long long kb = 0; kb < KB; ++kb) s += (double)pv_part[(t * KB + kb) * r + j];
+      for (long long q = 0; q < KB * NT; ++q) s += (double)pv_part[(t * KB * NT + q) * r + j];
       double gv = 0.0;
       for (int jj = 0; jj < r; ++jj) gv += G[j * r + jj] * V[(long long)jj * T + t];
       dV[e] += 2.0 * s + 2.0 * l2 * gv;  // accumulated: V is shared across sessions (rrr.py:49)
@@ -461,7 +486,7 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   const long long KT = d.K * d.T;
   w.Npad = round_up(d.N, 16);
   w.ldz = d.r * w.Npad;
-  w.gp_blocks = ceil_div(d.C1, 256) * d.N;
+  w.gp_blocks = ceil_div(d.C1, 256 * kPrepC) * d.N;
   w.KB = ceil_div(d.K, kEpiRows);
   w.splits_f = hp_splits(d.C1, d.planes);
   w.splits_b = hp_splits(KT, d.planes);
@@ -474,7 +499,7 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.Gacc = (float*)take((size_t)w.splits_b * d.C1 * w.ldz * 4);
   w.sse_part = (float*)take((size_t)d.T * w.KB * d.N * 4);
   w.db_part = (float*)take((size_t)d.T * w.KB * d.N * 4);
-  w.pv_part = (float*)take((size_t)d.T * w.KB * d.r * 4);
+  w.pv_part = (float*)take((size_t)d.T * w.KB * ceil_div(d.N, 32) * d.r * 4);
   w.bal = take(tc::balance_ws_bytes());
   w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
   w.G = (double*)take(kMaxR * kMaxR * 8);
@@ -608,15 +633,19 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   const long long KT = d.K * d.T;
   const int r = (int)d.r;
   // stage 0: U planes + Gram partials, then G and W = V V^T
-  dim3 g0((unsigned)ceil_div(d.C1, 256), (unsigned)d.N);
-  VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
-  VS_LAUNCH(small_mats_kernel, 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
+  dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
+  if (r <= 4) {
+    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
+  } else {
+    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
+  }
+  VS_LAUNCH(small_mats_kernel, r * r + 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   // stage 1: Z
   int sf = 1, sb = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
   // stage 2: residuals -> RV operand, per-block partials of SSE / db / dV
-  dim3 ge((unsigned)w.KB, (unsigned)d.T);
+  dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (r <= 4) {
     VS_LAUNCH((epi_f_kernel<false, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
               (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
@@ -626,8 +655,8 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   }
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
   VS_LAUNCH(reduce_part_kernel, g2, 128, 0, st, w.sse_part, w.db_part, b, w.KB, (long long)d.T, (long long)d.N, l2, db, w.sse_tn);
-  VS_LAUNCH(finalize_kernel, 1, 256, 0, st, w.sse_tn, w.pv_part, w.G, w.W, V, b, w.KB, (long long)d.T, (long long)d.N, r, l2,
-            sse_n, loss, dV);
+  VS_LAUNCH(finalize_kernel, 1, 256, 0, st, w.sse_tn, w.pv_part, w.G, w.W, V, b, w.KB, (long long)ceil_div(d.N, 32), (long long)d.T,
+            (long long)d.N, r, l2, sse_n, loss, dV);
   if (dU) {
     // stage 3/4: Gacc and dU
     rc = gemm_b(d, Xb, w, engine, st, &sb);
@@ -648,13 +677,18 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   cudaStream_t st = (cudaStream_t)stream;
   const Ws w = carve(d, workspace);
   const long long KT = d.K * d.T;
-  dim3 g0((unsigned)ceil_div(d.C1, 256), (unsigned)d.N);
-  VS_LAUNCH(prep_u_kernel, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
-            (double*)nullptr);
+  dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
+  if (d.r <= 4) {
+    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
+              (double*)nullptr);
+  } else {
+    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
+              (double*)nullptr);
+  }
   int sf = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
-  dim3 ge((unsigned)w.KB, (unsigned)d.T);
+  dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (d.r <= 4) {
     VS_LAUNCH((epi_f_kernel<true, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
               (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);

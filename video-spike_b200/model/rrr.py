@@ -30,7 +30,7 @@ from optim import FusedLBFGS
 
 
 def np2tensor(v):
-    return torch.from_numpy(v)
+    return v if isinstance(v, torch.Tensor) else torch.from_numpy(v)
 
 
 def np2param(v, grad=True):
@@ -95,7 +95,11 @@ class RRRGD():
         self.planes = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
         self.engine = int(engine if engine is not None else os.environ.get("VS_ENGINE", str(vs.ENGINE_AUTO)))
 
-        np.random.seed(0)                      # rrr.py:35 -- regardless of the global seed
+        # rrr.py:35 seeds numpy's GLOBAL legacy stream with 0 regardless of the user's seed and draws
+        # U then V per session from it.  The same stream -- bit for bit -- comes from the multi-threaded host
+        # generator of libvs_b200 (numpy's scalar loop costs more than the whole GPU fit); numpy's global state
+        # is then left exactly where the reference would leave it.
+        rng = vs.LegacyNormalStream(0)
         self.N = 0
         params = {}
         V = None
@@ -104,15 +108,17 @@ class RRRGD():
             _y = train_data[eid]['y'][0]       # (K, T, N)
             K, T, ncoef = _X.shape
             K, T, N = _y.shape
-            U = np.random.normal(size=(N, ncoef - 1, ncomp)) / np.sqrt(T * ncomp)
-            V = np.random.normal(size=(ncomp, T)) / np.sqrt(T * ncomp)   # redrawn per eid, last one kept
+            scale = float(np.sqrt(T * ncomp))
+            U = rng.normal((N, ncoef - 1, ncomp), scale)
+            V = rng.normal((ncomp, T), scale)                  # redrawn per eid, the last one is kept (rrr.py:43,49)
             if isinstance(_y, torch.Tensor):   # targets already on the device (pack_session_from_frames)
-                b = _y.double().mean(0).T.unsqueeze(1).contiguous().cpu().numpy()
+                b = _y.double().mean(0).T.unsqueeze(1).contiguous()
             else:
                 b = np.ascontiguousarray(np.expand_dims(_y.mean(0).T, 1))
             params[f"{eid}_U"] = np2param(U)
             params[f"{eid}_b"] = np2param(b)
             self.N += N
+        rng.export_to_numpy()
         params['V'] = np2param(V)
         self.n_comp, self.T = params['V'].shape
         self.model = nn.ParameterDict(params)

@@ -216,7 +216,8 @@ class FusedLBFGS(torch.optim.Optimizer):
             old = self._hist
             have = 0 if old is None else old.shape[0]
             grow = 2 * min(self.param_groups[0]["history_size"] + 1, max(8, self.param_groups[0]["max_iter"] + 1))
-            new = torch.empty((have + grow, n), dtype=torch.float64, device=self._flat["x"].device)
+            npad = (n + 1) // 2 * 2                                     # even pitch: every slot 16-byte aligned (128-bit loads)
+            new = torch.empty((have + grow, npad), dtype=torch.float64, device=self._flat["x"].device)
             if old is not None:
                 new[:have].copy_(old)
             self._hist = new
@@ -234,7 +235,7 @@ class FusedLBFGS(torch.optim.Optimizer):
         hist = self._hist
         vs.check(vs.lib.vs_lbfgs_dots(fl["n"], vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist[s_slot]) if s_slot is not None else None,
                                       vs.ptr(hist[y_slot]) if y_slot is not None else None, vs.ptr(hist) if hist is not None else None,
-                                      fl["n"], ss, ys, m, vs.ptr(self._scal), vs.ptr(self._ws), self._ws.numel(), vs.stream()))
+                                      hist.shape[1] if hist is not None else fl["n"], ss, ys, m, vs.ptr(self._scal), vs.ptr(self._ws), self._ws.numel(), vs.stream()))
         k = 8 + 6 * m
         self._scal[-1:].copy_(torch.as_tensor(loss_t).detach().reshape(1))
         host = self._scal.cpu().numpy()
@@ -328,7 +329,7 @@ class FusedLBFGS(torch.optim.Optimizer):
             s_slot = self._slot()
             hist = self._hist
             stop_gtd = gtd > -tol_c
-            vs.check(vs.lib.vs_lbfgs_direction(n, vs.ptr(g), vs.ptr(hist), n, ss, ysl, m, coef, float(t),
+            vs.check(vs.lib.vs_lbfgs_direction(n, vs.ptr(g), vs.ptr(hist), hist.shape[1], ss, ysl, m, coef, float(t),
                                                None if stop_gtd else vs.ptr(fl["x"]), vs.ptr(hist[s_slot]),
                                                vs.ptr(self._scal[-2:-1]), vs.stream()))
             state["s_slot"] = s_slot

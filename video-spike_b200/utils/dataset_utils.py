@@ -42,3 +42,36 @@ def get_metadata_from_loader(data_loader, config):
     ap = batch["ap"]
     return {"num_neurons": ap.shape[2], "input_dim": width, "input_mods": input_mods,
             "output_dim": ap.shape[1] * ap.shape[2]}
+
+
+def load_video_index(timestamps, intervals, fps):
+    """Frame window of every trial (src/utils/ibl_data_utils.py:958-967): `int(fps * interval_len)` frames
+    (120 at 60 Hz x 2 s) starting at the first frame whose timestamp is >= the interval start
+    (`np.searchsorted`, side='left').  Integer work, bit-exact by construction; raises like the reference
+    when a trial holds more than 10 frames too many/few."""
+    import numpy as np
+    ts = np.asarray(timestamps)
+    intervals = np.asarray(intervals)
+    reg_frame_num = int(fps * (intervals[0, 1] - intervals[0, 0]))
+    out = np.empty((len(intervals), reg_frame_num), dtype=np.int64)
+    for i, (t0, t1) in enumerate(intervals):
+        n_in = int(np.count_nonzero((ts > t0) & (ts < t1)))
+        if abs(n_in - reg_frame_num) > 10:
+            raise ValueError(f"Number of frames in the video does not match the expected number of frames {reg_frame_num}. Bias > 10")
+        start = int(np.searchsorted(ts, t0))
+        out[i] = np.arange(start, start + reg_frame_num)
+    return out
+
+
+def gather_trial_windows(session_frames_u8, start_idx, frames_per_trial=120):
+    """(n_frames, ...) uint8 session video on the DEVICE + per-trial start indices -> (n_trials, 120, ...) uint8:
+    the windows `load_video_index` defines, cut by the vs_gather_windows kernel (bit-exact byte copy)."""
+    import vsb200 as vs
+    fr = session_frames_u8
+    starts = torch.as_tensor(start_idx, dtype=torch.int64, device=fr.device).contiguous()
+    row = int(fr[0].numel())
+    out = torch.empty((starts.numel(), frames_per_trial) + tuple(fr.shape[1:]), dtype=torch.uint8, device=fr.device)
+    if starts.numel():
+        vs.check(vs.lib.vs_gather_windows(vs.ptr(fr.contiguous()), fr.shape[0], row, vs.ptr(starts), starts.numel(),
+                                          frames_per_trial, vs.ptr(out), vs.stream()))
+    return out

@@ -91,3 +91,10 @@ def metrics_list(gt, pred, metrics=("bps", "rsquared"), device="cpu"):
     if "mae" in metrics:
         results["mae"] = torch.mean(torch.abs(gt - pred))
     return results
+
+
+def select_frames(n_total=119, n_keep=100):
+    """src/train_rrr.py:48-49: 100 of frames 0..118, drawn from the GLOBAL numpy stream (right after
+    `set_seed(config.seed)` in the reference driver), returned sorted."""
+    idx = np.random.choice(n_total, n_keep, replace=False)
+    return np.sort(idx)

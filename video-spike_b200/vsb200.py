@@ -52,6 +52,7 @@ def _load():
         "vs_device_ok": (C.c_int, []),
         "vs_u8_to_f32": (C.c_int, [vp, vp, i64, vp]),
         "vs_u8_to_bf16": (C.c_int, [vp, vp, i64, vp]),
+        "vs_gather_windows": (C.c_int, [vp, i64, i64, vp, i64, i64, vp, vp]),
         "vs_linear_fwd_workspace": (sz, [i64, i64, i64]),
         "vs_linear_fwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, sz, vp]),
         "vs_linear_bwd_workspace": (sz, [i64, i64, i64]),
@@ -75,6 +76,10 @@ def _load():
         "vs_lbfgs_workspace": (sz, [i64, i32]),
         "vs_lbfgs_dots": (C.c_int, [i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, sz, vp]),
         "vs_lbfgs_direction": (C.c_int, [i64, vp, vp, i64, vp, vp, i32, vp, dbl, vp, vp, vp, vp]),
+        "vs_host_rng_seed": (C.c_int, [vp, C.c_uint32]),
+        "vs_host_rng_normal": (C.c_int, [vp, i64, dbl, vp, i32]),
+        "vs_host_rng_get_state": (C.c_int, [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+        "vs_host_rng_set_state": (C.c_int, [vp, vp, C.c_int32, C.c_int32, dbl]),
         "vs_gemm_tn": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp]),
         "vs_launch_count": (i64, []),
         "vs_launch_count_reset": (None, []),
@@ -164,3 +169,28 @@ def profile_read(tag: int):
     tot, mn, mx = C.c_double(), C.c_double(), C.c_double()
     cnt = lib.vs_profile_read(tag, C.byref(tot), C.byref(mn), C.byref(mx))
     return int(cnt), tot.value, mn.value, mx.value
+
+
+class LegacyNormalStream:
+    """numpy's legacy global stream (`np.random.seed(s)`; `np.random.normal(size=...)`) reproduced bit for bit
+    by the multi-threaded host generator of libvs_b200 (csrc/host_rng.cpp).  Used by RRRGD.__init__
+    (src/model/rrr.py:35,42-43 draws ~8 M normals per session; numpy needs ~0.2 s for that)."""
+    STATE_BYTES = 2560
+
+    def __init__(self, seed: int):
+        self._state = C.create_string_buffer(self.STATE_BYTES)
+        check(lib.vs_host_rng_seed(self._state, int(seed) & 0xFFFFFFFF))
+
+    def normal(self, size, divisor: float = 1.0, threads: int = 0):
+        import numpy as np
+        out = np.empty(size, dtype=np.float64)
+        check(lib.vs_host_rng_normal(self._state, out.size, float(divisor), out.ctypes.data_as(C.c_void_p), int(threads)))
+        return out
+
+    def export_to_numpy(self):
+        """Leave numpy's GLOBAL RandomState exactly where the reference's draws would have left it."""
+        import numpy as np
+        key = np.empty(624, dtype=np.uint32)
+        pos, has, cached = C.c_int32(), C.c_int32(), C.c_double()
+        check(lib.vs_host_rng_get_state(self._state, key.ctypes.data_as(C.c_void_p), C.byref(pos), C.byref(has), C.byref(cached)))
+        np.random.set_state(("MT19937", key, int(pos.value), int(has.value), float(cached.value)))
