@@ -195,7 +195,7 @@ def reference_arm(args, rank, world):
 def rrr_config(args, world):
     return {"workload": "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
-            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes, "lbfgs": "1 step, max_iter 20 (20 closure evals)",
+            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes, "lbfgs": "1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64",
             "sessions": world, "parallelism": f"session-sharded x{world}" if world > 1 else "single GPU",
             "l2_cache": "operands (1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
 
@@ -230,7 +230,7 @@ def run_rrr(args, rank, world, local):
         with torch.no_grad():
             for k, v in init.items():
                 model.model[k].copy_(v)
-        opt = FusedLBFGS(model.model.parameters())         # what train_model_main builds (rrr.py:199 semantics)
+        opt = model.make_optimizer()                       # what train_model_main builds (rrr.py:199 semantics)
         _, res = train_model(model, td, opt, "tmp", save=False)
         return res["mse_val_mean"]
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 2
+#define VS_ABI_VERSION 3
 
 enum {
   VS_OK = 0,
@@ -227,13 +227,16 @@ int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl, const dou
  * s_out = t*d; x += t*d (skipped when x is NULL); *dmax_out = max|t*d|.                               */
 #define VS_LBFGS_MAX_HIST 100
 size_t vs_lbfgs_workspace(int64_t n, int m);
-int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, const double* s_new, double* y_out,
-                  const double* hist, int64_t hist_stride, const int32_t* s_slots_host,
+/* hist_f32 != 0: the history buffer (and therefore s_new / y_out / s_out, which are history slots) holds float32
+ * instead of float64 -- half the traffic of both passes; arithmetic stays fp64 and every inner product is taken with
+ * the stored (rounded) vectors.  hist_stride in elements; a multiple of 4 enables the 128-bit path.            */
+int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, const void* s_new, void* y_out,
+                  const void* hist, int64_t hist_stride, int hist_f32, const int32_t* s_slots_host,
                   const int32_t* y_slots_host, int m, double* out, void* workspace, size_t workspace_bytes,
                   void* stream);
-int vs_lbfgs_direction(int64_t n, const double* g, const double* hist, int64_t hist_stride,
+int vs_lbfgs_direction(int64_t n, const double* g, const void* hist, int64_t hist_stride, int hist_f32,
                        const int32_t* s_slots_host, const int32_t* y_slots_host, int m,
-                       const double* coef_host, double t, double* x, double* s_out, double* dmax_out,
+                       const double* coef_host, double t, double* x, void* s_out, double* dmax_out,
                        void* stream);
 
 /* ------------------------------------------------------------------ RRR initialisation stream (R1, HOST)

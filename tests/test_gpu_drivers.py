@@ -1,0 +1,91 @@
+"""-m gpu: the drivers and the trainer (drop-in surface of src/train.py, src/train_rrr.py, src/trainer/base.py) end to end
+on synthetic shards, against the oracle run on the very same batches."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import linear_oracle as lo
+from oracle import metrics_oracle as mo
+from oracle import rrr_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "video-spike_b200")
+
+
+def _train_yaml(tmp_path, **training):
+    cfg = yaml.safe_load(open(os.path.join(PKG, "config", "train", "linear_video.yaml")))
+    cfg["dirs"]["data_dir"] = "synthetic:n=40,h=8,w=8,neurons=12,seed=3"
+    cfg["dirs"]["log_dir"] = str(tmp_path / "results")
+    cfg["training"].update(dict(num_epochs=2, train_batch_size=8, test_batch_size=4, num_workers=0), **training)
+    path = tmp_path / "train.yaml"
+    yaml.safe_dump(cfg, open(path, "w"))
+    return str(path)
+
+
+def test_train_driver_runs_and_matches_oracle(cuda, tmp_path, capsys):
+    import train as train_driver
+    argv = ["--model_config", os.path.join(PKG, "config", "model", "linear_video.yaml"), "--train_config", _train_yaml(tmp_path),
+            "--eid", "abcde-synthetic"]
+    trainer = train_driver.main(argv)
+    log_dir = trainer.log_dir
+    assert os.path.exists(os.path.join(log_dir, "model_last.pt")) and os.path.exists(os.path.join(log_dir, "model_best.pt"))
+    assert os.path.exists(os.path.join(log_dir, "test_results.npy"))
+    assert log_dir.endswith(os.path.join("abcde", "video", "Linear"))                  # base.py: <log_dir>/<eid[:5]>/<mods>/<Model>
+    out = capsys.readouterr().out
+    losses = [float(l.split("train loss:")[1]) for l in out.splitlines() if "train loss:" in l]
+    assert len(losses) == 2
+    # the same two epochs on the oracle: same seed, same split, same batches, same recipe
+    from loader.make import make_loader
+    from utils.config_utils import config_from_kwargs, update_config
+    from utils.utils import set_seed
+    cfg = update_config(argv[3], config_from_kwargs({"model": "include:" + argv[1]}))
+    set_seed(cfg.seed)
+    split = train_driver.synthetic_split(str(cfg.dirs.data_dir)[len("synthetic:"):], "abcde-synthetic")
+    tr_loader, val_loader, _ = make_loader(cfg, split)
+    tr = lo.Trainer(lo.init_params(120 * 8 * 8, 12, seed=42), total_steps=len(split["train"]) // 8 * 2)
+    ref_epochs = []
+    for _ in range(2):
+        ls = [tr.step(b["video"], b["ap"]) for b in tr_loader]
+        ref_epochs.append(round(float(np.mean(ls)), 5))
+    assert losses == pytest.approx(ref_epochs, rel=1e-4)
+    # evaluation: exp(logits) of the final model on the val split, bps / R2 with the reference's metric loop
+    gt = torch.cat([b["ap"] for b in val_loader]).numpy().astype(np.float64)
+    final = torch.load(os.path.join(log_dir, "model_last.pt"), weights_only=False)["model"]
+    trainer.model = final                      # test_model() left the best checkpoint in place (base.py:212)
+    res = trainer.eval_epoch()
+    with torch.no_grad():
+        pred_gpu = torch.exp(torch.cat([final(b["video"].to(cuda)) for b in val_loader])).cpu().numpy().astype(np.float64)
+    pred_or = torch.cat([tr.predict_rates(b["video"], 12) for b in val_loader]).numpy().astype(np.float64)
+    np.testing.assert_allclose(pred_gpu, pred_or, rtol=1e-3)
+    m_or = mo.metrics_list(gt, pred_or)
+    assert res["eval_res"]["eval_bps"] == pytest.approx(round(m_or["bps"], 5), rel=1e-3, abs=2e-5)
+    assert res["eval_res"]["eval_rsquared"] == pytest.approx(round(m_or["rsquared"], 5), rel=1e-3, abs=2e-5)
+
+
+def test_train_rrr_driver_matches_oracle(cuda, tmp_path, monkeypatch):
+    import train_rrr
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("VS_RRR_PLANES", "3")
+    argv = ["--model_config", os.path.join(PKG, "config", "model", "linear_video.yaml"),
+            "--train_config", os.path.join(PKG, "config", "train", "rrr.yaml"), "--input_mod", "synthetic"]
+    result = train_rrr.main(argv)
+    assert os.path.exists(tmp_path / "synthetic_result.npy")
+    eid = "synthetic00"
+    # oracle on the same synthetic session
+    from utils.utils import set_seed
+    set_seed(42)
+    sidx = np.sort(np.random.choice(119, 100, replace=False))
+    d = train_rrr.synthetic_sessions()[eid]
+    data, gt = ro.preprocess_session([d["X"][0].reshape(64, 120, -1), d["X"][1].reshape(16, 120, -1)], [d["y"][0], d["y"][1]], sidx)
+    params, _, _ = ro.train_model_main({eid: data}, 100.0, 3)
+    _, _, pred = ro.predict_y_fr(params, {eid: data}, eid, 1)
+    ev = ro.eval_session(pred, gt)
+    assert np.nanmean(result[eid]["co_bps"]) == pytest.approx(ev["co_bps"], rel=1e-3, abs=1e-5)
+    assert np.nanmean(result[eid]["r2"]) == pytest.approx(ev["r2"], rel=1e-3, abs=1e-5)
+    np.testing.assert_allclose(result[eid]["pred"], np.clip(pred, 1e-3, None), rtol=1e-3, atol=1e-6)

@@ -219,10 +219,11 @@ def test_gather_windows_bit_exact(vs, cuda, hw):
     t0 = np.sort(rng.uniform(ts[10], ts[-300], size=13))
     idx = load_video_index(ts, np.stack([t0, t0 + 2.0], 1), 60.0)
     ref = lo.cut_windows(video, lo.load_video_index(ts, np.stack([t0, t0 + 2.0], 1), 60.0))
-    got = gather_trial_windows(torch.from_numpy(video).to(cuda), idx[:, 0])
+    # reg_frame_num = int(fps * (t1 - t0)) is 119 or 120 depending on float rounding of t0 + 2.0 - t0: reference quirk, kept
+    got = gather_trial_windows(torch.from_numpy(video).to(cuda), idx[:, 0], frames_per_trial=idx.shape[1])
     assert got.shape == ref.shape and got.dtype == torch.uint8
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
     # a window that runs off the end of the video is zero-filled
-    tail = gather_trial_windows(torch.from_numpy(video).to(cuda), np.array([n_frames - 50]))
+    tail = gather_trial_windows(torch.from_numpy(video).to(cuda), np.array([n_frames - 50]), frames_per_trial=120)
     assert torch.equal(tail[0, :50].cpu(), torch.from_numpy(video[-50:])) and int(tail[0, 50:].max()) == 0
     assert gather_trial_windows(torch.from_numpy(video).to(cuda), np.zeros(0, dtype=np.int64)).shape[0] == 0

@@ -117,3 +117,38 @@ def test_rrr_fit_same_with_both_optimisers(vs, cuda):
     np.testing.assert_allclose(out["fused"][3], out["torch"][3], rtol=1e-6, atol=1e-9)
     # the parameters handed out by the model are still the ParameterDict entries the reference exposes
     assert set(m.model.keys()) == {"e1_U", "e1_b", "V"} and m.model["e1_U"].shape == (12, 150, 3)
+
+
+def test_float32_history_tracks_float64_history(vs, cuda):
+    """history_dtype=float32 halves the L-BFGS traffic; the optimisation path stays the same to ~1e-6."""
+    from optim import FusedLBFGS
+    make = _problem(cuda, seed=3)
+    res = {}
+    for name, hd in (("f64", torch.float64), ("f32", torch.float32)):
+        ps, f = make()
+        opt = FusedLBFGS(ps, history_dtype=hd)
+        losses = []
+
+        def closure():
+            opt.zero_grad()
+            loss = f()
+            loss.backward()
+            losses.append(float(loss.detach()))
+            return loss
+        opt.step(closure)
+        res[name] = (losses, torch.cat([p.detach().reshape(-1) for p in ps]).cpu().numpy(), opt.state[ps[0]]["func_evals"])
+    assert res["f32"][2] == res["f64"][2]
+    np.testing.assert_allclose(res["f32"][0], res["f64"][0], rtol=1e-5)
+    np.testing.assert_allclose(res["f32"][1], res["f64"][1], rtol=1e-4, atol=1e-6)
+
+
+def test_rrr_fit_float32_history(vs, cuda):
+    from model.rrr import RRRGD, train_model
+    td = small_rrr_problem(seed=8, K=30, Kt=10, F=150, N=12)
+    out = {}
+    for hd in (torch.float64, torch.float32):
+        m = RRRGD(td, 3, l2=100.0, planes=1)
+        m.to(cuda)
+        _, res = train_model(m, td, m.make_optimizer(history_dtype=hd), "tmp", save=False)
+        out[hd] = float(res["mse_val_mean"])
+    assert out[torch.float32] == pytest.approx(out[torch.float64], rel=1e-5)

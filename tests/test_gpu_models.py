@@ -272,3 +272,24 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, 5, 2.0, vs.ptr(my), vs.ptr(sy), vs.ptr(yz), vs.stream()))
     np.testing.assert_allclose(my.cpu().numpy().reshape(T, 5), data["setup"]["mean_y_TN"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(yz.cpu().numpy(), data["y"][0], rtol=2e-4, atol=2e-5)
+
+
+def test_joint_model_through_sharded_optimizer_world1(vs, cuda):
+    """parallel.train_joint_model on one rank == train_model with FusedLBFGS on the same joint two-session model
+    (the world_size-2 equivalence of ShardedLBFGS is covered on CPU/gloo in tests/test_distributed_cpu.py and on two
+    GPUs by tools/joint_2gpu_check.py)."""
+    from model.rrr import RRRGD, train_model
+    from parallel import train_joint_model
+    td = {**small_rrr_problem(seed=4, K=16, Kt=5, F=70, N=6, eid="s1"), **small_rrr_problem(seed=5, K=12, Kt=5, F=90, N=11, eid="s2")}
+    a = RRRGD(td, 3, l2=100.0, planes=3); a.to(cuda)
+    _, ra = train_model(a, td, a.make_optimizer(), "tmp", save=False)
+    b = RRRGD(td, 3, l2=100.0, planes=3); b.to(cuda)
+    _, rb = train_joint_model(b, td)
+    assert float(rb["mse_val_mean"]) == pytest.approx(float(ra["mse_val_mean"]), rel=1e-8)
+    for k in a.model.keys():
+        np.testing.assert_allclose(b.model[k].detach().cpu().numpy(), a.model[k].detach().cpu().numpy(), rtol=1e-6, atol=1e-9)
+    # a rank that holds only session s2 still draws s1's init from the stream (init_plan): same U_s2 and V
+    plan = [(e, td[e]["y"][0].shape[2], td[e]["X"][0].shape[2], td[e]["y"][0].shape[1]) for e in td]
+    c = RRRGD({"s2": td["s2"]}, 3, l2=100.0, planes=3, init_plan=plan)
+    ref = RRRGD(td, 3, l2=100.0, planes=3)
+    assert torch.equal(c.model["s2_U"], ref.model["s2_U"]) and torch.equal(c.model["V"], ref.model["V"])

@@ -9,7 +9,7 @@
 //   vs_lbfgs_dots       one pass over g, g_prev, s_new and the 2m history vectors: writes y_new = g - g_prev
 //                       and every inner product the Gram update needs, plus |g|_inf and |g|_1
 //   vs_lbfgs_direction  one pass: d = cg*g + sum cs_i s_i + cy_i y_i;  s_out = t*d;  x += t*d;  max|t*d|
-// Both are HBM-bound (8 B/element/vector).  Reductions are two-stage with a fixed order: bit-reproducible.
+// Both are HBM-bound (8 or 4 B/element/history vector: the history may be stored in float32).  Reductions are two-stage with a fixed order: bit-reproducible.
 #include "common.cuh"
 
 namespace vs {
@@ -18,7 +18,6 @@ namespace lbfgs {
 constexpr int kBase = 8;      // base scalars: g.g, |g|_1, |g|_inf, y.y, y.s, s.g, y.g, (unused)
 
 struct Slots { int32_t s[2 * VS_LBFGS_MAX_HIST]; };              // element offsets / stride of the 2m vectors
-struct Coef { double c[2 * VS_LBFGS_MAX_HIST + 1]; };            // cg, then one coefficient per history vector
 
 __device__ __forceinline__ double block_max(double v, double* sh) {
 #pragma unroll
@@ -32,58 +31,117 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
   return s;
 }
 
-// One block per chunk of kChunk elements.  Each thread keeps its 8 elements of g, y = g - g_prev and s_new in
-// registers (also writes y), then streams the 2m history vectors ONCE each with 128-bit loads, two vectors in
-// flight at a time; per-warp partial sums go to shared memory without intermediate barriers and are combined
-// in a fixed order at the end.  part[c * nout + o].
-constexpr int kChunk = 2048;           // elements per block: 256 threads x 4 double2
-constexpr int kPerThread = 4;          // double2 per thread
+// One block per chunk of kChunk elements.  Each thread keeps its 8 elements (two groups of 4 consecutive) of g,
+// y = g - g_prev and s_new in registers (also writes y), then streams the 2m history vectors ONCE each with 128-bit
+// loads, two vectors in flight at a time; per-warp partial sums go to shared memory without intermediate barriers and
+// are combined in a fixed order at the end.  part[c * nout + o].
+// HT = storage type of the history vectors (s_i, y_i, and therefore s_new / y_out): double, or float to halve the
+// traffic of both passes.  All arithmetic is fp64; with float storage every inner product is taken with the STORED
+// (rounded) vectors so the Gram matrix stays consistent with what later iterations read back.
+constexpr int kChunk = 2048;           // elements per block: 256 threads x 2 groups x 4
+constexpr int kGroups = 2;
 
-__device__ __forceinline__ double2 ld_stream_d2(const double* p) {
-  double2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-  return r;
-}
+struct D4 { double v[4]; };
 
 template <bool kVec>
-__device__ __forceinline__ double2 load2(const double* base, long long i, long long n) {
-  if constexpr (kVec) {
-    if (i + 1 < n) return ld_stream_d2(base + i);
+__device__ __forceinline__ D4 load4(const double* base, long long i, long long n) {
+  D4 r;
+  if (kVec && i + 3 < n) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(base + i));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[2]), "=d"(r.v[3]) : "l"(base + i + 2));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.v[q] = i + q < n ? base[i + q] : 0.0;
   }
-  double2 r;
-  r.x = i < n ? base[i] : 0.0;
-  r.y = i + 1 < n ? base[i + 1] : 0.0;
   return r;
 }
-
 template <bool kVec>
+__device__ __forceinline__ D4 load4(const float* base, long long i, long long n) {
+  D4 r;
+  if (kVec && i + 3 < n) {
+    float4 f;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(base + i));
+    r.v[0] = f.x; r.v[1] = f.y; r.v[2] = f.z; r.v[3] = f.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.v[q] = i + q < n ? (double)base[i + q] : 0.0;
+  }
+  return r;
+}
+template <bool kVec>
+__device__ __forceinline__ void store4(double* base, long long i, long long n, const D4& v) {
+  if (kVec && i + 3 < n) {
+    *reinterpret_cast<double2*>(base + i) = make_double2(v.v[0], v.v[1]);
+    *reinterpret_cast<double2*>(base + i + 2) = make_double2(v.v[2], v.v[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i + q < n) base[i + q] = v.v[q];
+  }
+}
+template <bool kVec>
+__device__ __forceinline__ void store4(float* base, long long i, long long n, const D4& v) {
+  if (kVec && i + 3 < n) {
+    *reinterpret_cast<float4*>(base + i) = make_float4((float)v.v[0], (float)v.v[1], (float)v.v[2], (float)v.v[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i + q < n) base[i + q] = (float)v.v[q];
+  }
+}
+template <typename T> struct H4 { T v[4]; };
+template <bool kVec>
+__device__ __forceinline__ H4<double> load4h(const double* base, long long i, long long n) {
+  const D4 d = load4<kVec>(base, i, n);
+  H4<double> r;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r.v[q] = d.v[q];
+  return r;
+}
+template <bool kVec>
+__device__ __forceinline__ H4<float> load4h(const float* base, long long i, long long n) {
+  H4<float> r;
+  if (kVec && i + 3 < n) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(base + i));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.v[q] = i + q < n ? base[i + q] : 0.f;
+  }
+  return r;
+}
+__device__ __forceinline__ double round_to(double v, const double*) { return v; }
+__device__ __forceinline__ double round_to(double v, const float*) { return (double)(float)v; }
+
+template <typename HT, bool kVec>
 __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __restrict__ g, const double* __restrict__ gp,
-                                                   const double* __restrict__ s_new, double* __restrict__ y_out,
-                                                   const double* __restrict__ hist, long long stride, const Slots slots, int nh,
+                                                   const HT* __restrict__ s_new, HT* __restrict__ y_out,
+                                                   const HT* __restrict__ hist, long long stride, const Slots slots, int nh,
                                                    int nout, double* __restrict__ part) {
   extern __shared__ double red[];          // [nout][8 warps]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long i0 = (long long)blockIdx.x * kChunk + 2 * threadIdx.x;
-  double2 gv[kPerThread], yv[kPerThread], sv[kPerThread];
+  const long long i0 = (long long)blockIdx.x * kChunk + 4 * threadIdx.x;
+  D4 gv[kGroups], yv[kGroups], sv[kGroups];
   double gg = 0.0, g1 = 0.0, gm = 0.0, yy = 0.0, ys = 0.0, sg = 0.0, yg = 0.0;
 #pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    const long long i = i0 + 512 * j;
-    gv[j] = load2<kVec>(g, i, n);
-    const double2 pv = gp ? load2<kVec>(gp, i, n) : make_double2(0.0, 0.0);
-    sv[j] = s_new ? load2<kVec>(s_new, i, n) : make_double2(0.0, 0.0);
-    yv[j] = make_double2(gv[j].x - pv.x, gv[j].y - pv.y);
-    if (y_out) {
-      if (kVec && i + 1 < n) *reinterpret_cast<double2*>(y_out + i) = yv[j];
-      else { if (i < n) y_out[i] = yv[j].x; if (i + 1 < n) y_out[i + 1] = yv[j].y; }
+  for (int j = 0; j < kGroups; ++j) {
+    const long long i = i0 + 1024 * j;
+    gv[j] = load4<kVec>(g, i, n);
+    D4 pv;
+    if (gp) pv = load4<kVec>(gp, i, n);
+    if (s_new) sv[j] = load4<kVec>(s_new, i, n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!gp) pv.v[q] = 0.0;
+      if (!s_new) sv[j].v[q] = 0.0;
+      yv[j].v[q] = round_to(gv[j].v[q] - pv.v[q], hist);
     }
-    gg = fma(gv[j].x, gv[j].x, gg); gg = fma(gv[j].y, gv[j].y, gg);
-    g1 += fabs(gv[j].x) + fabs(gv[j].y);
-    gm = fmax(gm, fmax(fabs(gv[j].x), fabs(gv[j].y)));
-    yy = fma(yv[j].x, yv[j].x, yy); yy = fma(yv[j].y, yv[j].y, yy);
-    ys = fma(yv[j].x, sv[j].x, ys); ys = fma(yv[j].y, sv[j].y, ys);
-    sg = fma(sv[j].x, gv[j].x, sg); sg = fma(sv[j].y, gv[j].y, sg);
-    yg = fma(yv[j].x, gv[j].x, yg); yg = fma(yv[j].y, gv[j].y, yg);
+    if (y_out) store4<kVec>(y_out, i, n, yv[j]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double a = gv[j].v[q], y = yv[j].v[q], sn = sv[j].v[q];
+      gg = fma(a, a, gg); g1 += fabs(a); gm = fmax(gm, fabs(a));
+      yy = fma(y, y, yy); ys = fma(y, sn, ys); sg = fma(sn, a, sg); yg = fma(y, a, yg);
+    }
   }
   {
     const double b0 = warp_sum(gg), b1 = warp_sum(g1), b3 = warp_sum(yy), b4 = warp_sum(ys), b5 = warp_sum(sg), b6 = warp_sum(yg);
@@ -95,38 +153,48 @@ __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __
       red[4 * 8 + warp] = b4; red[5 * 8 + warp] = b5; red[6 * 8 + warp] = b6; red[7 * 8 + warp] = 0.0;
     }
   }
-  // history vectors, two per iteration so 8 independent 128-bit loads are in flight per thread
+  // history vectors, two per iteration so several independent 128-bit loads are in flight per thread.  The vector
+  // fp64 pipe of the B200 is narrow (measured ~6 ops/clk/SM: a float64 history is bandwidth-bound at 3 DFMA per
+  // element, a float32 one would be conversion+DFMA-bound), so with float storage the 8 products of a thread are
+  // accumulated in fp32 -- the same order of rounding as the storage itself -- and only the per-thread partials are
+  // widened; every cross-thread sum stays fp64.
+  using AT = HT;                                  // per-thread accumulation type
+  AT gf[kGroups][4], yf[kGroups][4], sf[kGroups][4];
+#pragma unroll
+  for (int j = 0; j < kGroups; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { gf[j][q] = (AT)gv[j].v[q]; yf[j][q] = (AT)yv[j].v[q]; sf[j][q] = (AT)sv[j].v[q]; }
   for (int h = 0; h < nh; h += 2) {
-    const double* h0 = hist + (long long)slots.s[h] * stride;
+    const HT* h0 = hist + (long long)slots.s[h] * stride;
     const bool two = h + 1 < nh;
-    const double* h1 = two ? hist + (long long)slots.s[h + 1] * stride : h0;
-    double2 a[kPerThread], b[kPerThread];
+    const HT* h1 = two ? hist + (long long)slots.s[h + 1] * stride : h0;
+    H4<HT> a[kGroups], b[kGroups];
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) a[j] = load2<kVec>(h0, i0 + 512 * j, n);
+    for (int j = 0; j < kGroups; ++j) a[j] = load4h<kVec>(h0, i0 + 1024 * j, n);
     if (two) {
 #pragma unroll
-      for (int j = 0; j < kPerThread; ++j) b[j] = load2<kVec>(h1, i0 + 512 * j, n);
+      for (int j = 0; j < kGroups; ++j) b[j] = load4h<kVec>(h1, i0 + 1024 * j, n);
     }
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    AT a0 = 0, a1 = 0, a2 = 0, c0 = 0, c1 = 0, c2 = 0;
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-      a0 = fma(a[j].x, gv[j].x, a0); a0 = fma(a[j].y, gv[j].y, a0);
-      a1 = fma(a[j].x, yv[j].x, a1); a1 = fma(a[j].y, yv[j].y, a1);
-      a2 = fma(a[j].x, sv[j].x, a2); a2 = fma(a[j].y, sv[j].y, a2);
-    }
-    if (two) {
+    for (int j = 0; j < kGroups; ++j)
 #pragma unroll
-      for (int j = 0; j < kPerThread; ++j) {
-        c0 = fma(b[j].x, gv[j].x, c0); c0 = fma(b[j].y, gv[j].y, c0);
-        c1 = fma(b[j].x, yv[j].x, c1); c1 = fma(b[j].y, yv[j].y, c1);
-        c2 = fma(b[j].x, sv[j].x, c2); c2 = fma(b[j].y, sv[j].y, c2);
+      for (int q = 0; q < 4; ++q) {
+        a0 = fma(a[j].v[q], gf[j][q], a0); a1 = fma(a[j].v[q], yf[j][q], a1); a2 = fma(a[j].v[q], sf[j][q], a2);
       }
-    }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane == 0) { red[(kBase + 3 * h + 0) * 8 + warp] = a0; red[(kBase + 3 * h + 1) * 8 + warp] = a1; red[(kBase + 3 * h + 2) * 8 + warp] = a2; }
     if (two) {
-      c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
-      if (lane == 0) { red[(kBase + 3 * h + 3) * 8 + warp] = c0; red[(kBase + 3 * h + 4) * 8 + warp] = c1; red[(kBase + 3 * h + 5) * 8 + warp] = c2; }
+#pragma unroll
+      for (int j = 0; j < kGroups; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          c0 = fma(b[j].v[q], gf[j][q], c0); c1 = fma(b[j].v[q], yf[j][q], c1); c2 = fma(b[j].v[q], sf[j][q], c2);
+        }
+    }
+    const double d0 = warp_sum((double)a0), d1 = warp_sum((double)a1), d2 = warp_sum((double)a2);
+    if (lane == 0) { red[(kBase + 3 * h + 0) * 8 + warp] = d0; red[(kBase + 3 * h + 1) * 8 + warp] = d1; red[(kBase + 3 * h + 2) * 8 + warp] = d2; }
+    if (two) {
+      const double e0 = warp_sum((double)c0), e1 = warp_sum((double)c1), e2 = warp_sum((double)c2);
+      if (lane == 0) { red[(kBase + 3 * h + 3) * 8 + warp] = e0; red[(kBase + 3 * h + 4) * 8 + warp] = e1; red[(kBase + 3 * h + 5) * 8 + warp] = e2; }
     }
   }
   __syncthreads();
@@ -162,19 +230,26 @@ __global__ void __launch_bounds__(128) dots_reduce_kernel(const double* __restri
   if (threadIdx.x == 0) out[o] = sh[0];
 }
 
-__global__ void __launch_bounds__(256) direction_kernel(long long n, const double* __restrict__ g, const double* __restrict__ hist,
-                                                        long long stride, const Slots slots, int nh, const Coef coef, double t,
-                                                        double* __restrict__ x, double* __restrict__ s_out,
+// CT = arithmetic of the linear combination: double with a float64 history; float with a float32 one (the combination
+// is then rounded like its operands; the parameter update x += t*d itself is always fp64)
+template <typename HT>
+struct CoefT { HT c[2 * VS_LBFGS_MAX_HIST + 1]; };
+
+template <typename HT>
+__global__ void __launch_bounds__(256) direction_kernel(long long n, const double* __restrict__ g, const HT* __restrict__ hist,
+                                                        long long stride, const Slots slots, int nh, const CoefT<HT> coef, double cg,
+                                                        double t, double* __restrict__ x, HT* __restrict__ s_out,
                                                         unsigned long long* __restrict__ dmax_bits) {
   __shared__ double sh[8];
   double m = 0.0;
   const long long step = (long long)gridDim.x * 256;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
-    double d = coef.c[0] * g[i];
+    HT acc = 0;
 #pragma unroll 8
-    for (int h = 0; h < nh; ++h) d = fma(coef.c[1 + h], hist[(long long)slots.s[h] * stride + i], d);
+    for (int h = 0; h < nh; ++h) acc = fma(coef.c[1 + h], hist[(long long)slots.s[h] * stride + i], acc);
+    const double d = fma(cg, g[i], (double)acc);
     const double sd = t * d;
-    s_out[i] = sd;
+    s_out[i] = (HT)sd;
     if (x) x[i] += sd;
     m = fmax(m, fabs(sd));
   }
@@ -196,48 +271,65 @@ extern "C" size_t vs_lbfgs_workspace(int64_t n, int m) {
   return (size_t)num_chunks(n) * (kBase + 6 * (size_t)m) * sizeof(double) + 64;
 }
 
-extern "C" int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, const double* s_new, double* y_out,
-                             const double* hist, int64_t hist_stride, const int32_t* s_slots_host, const int32_t* y_slots_host,
-                             int m, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+template <typename HT>
+static int launch_dots(long long n, const double* g, const double* g_prev, const void* s_new, void* y_out, const void* hist,
+                       long long hist_stride, const Slots& sl, int nh, int nout, double* part, int chunks, void* stream) {
+  const size_t smem = (size_t)nout * 8 * sizeof(double);
+  // 128-bit loads need every vector base 16-byte aligned (hist slots: pitch a multiple of 4 elements)
+  const bool vec = ((((uintptr_t)g | (uintptr_t)g_prev | (uintptr_t)s_new | (uintptr_t)y_out | (uintptr_t)hist) & 15) == 0) &&
+                   (hist_stride % 4 == 0 || nh == 0);
+  if (vec) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<HT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH((dots_kernel<HT, true>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part);
+  } else {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<HT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH((dots_kernel<HT, false>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part);
+  }
+  return VS_OK;
+}
+
+extern "C" int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, const void* s_new, void* y_out,
+                             const void* hist, int64_t hist_stride, int hist_f32, const int32_t* s_slots_host,
+                             const int32_t* y_slots_host, int m, double* out, void* workspace, size_t workspace_bytes, void* stream) {
   VS_REQUIRE(n > 0 && g && out, VS_ERR_INVALID, "vs_lbfgs_dots: null pointer or empty vector");
   VS_REQUIRE(m >= 0 && m <= VS_LBFGS_MAX_HIST, VS_ERR_UNSUPPORTED, "vs_lbfgs_dots: history %d outside 0..%d", m, VS_LBFGS_MAX_HIST);
   VS_REQUIRE(m == 0 || (hist && s_slots_host && y_slots_host && hist_stride >= n), VS_ERR_INVALID, "vs_lbfgs_dots: history arguments");
   VS_REQUIRE(workspace && workspace_bytes >= vs_lbfgs_workspace(n, m), VS_ERR_WORKSPACE, "vs_lbfgs_dots: workspace too small");
   VS_REQUIRE(((uintptr_t)workspace & 7) == 0, VS_ERR_INVALID, "vs_lbfgs_dots: workspace must be 8-byte aligned");
+  VS_REQUIRE(n < (1ll << 40), VS_ERR_UNSUPPORTED, "vs_lbfgs_dots: vector too long");
   Slots sl;
   for (int i = 0; i < m; ++i) { sl.s[i] = s_slots_host[i]; sl.s[m + i] = y_slots_host[i]; }
   const int nh = 2 * m, nout = kBase + 3 * nh;
-  VS_REQUIRE(n < (1ll << 40), VS_ERR_UNSUPPORTED, "vs_lbfgs_dots: vector too long");
   const int chunks = num_chunks(n);
   double* part = reinterpret_cast<double*>(workspace);
-  const size_t smem = (size_t)nout * 8 * sizeof(double);
-  // 128-bit loads need every vector base 16-byte aligned (hist slots: even stride)
-  const bool vec = ((((uintptr_t)g | (uintptr_t)g_prev | (uintptr_t)s_new | (uintptr_t)y_out | (uintptr_t)hist) & 15) == 0) && (hist_stride % 2 == 0 || m == 0);
-  if (vec) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH(dots_kernel<true>, chunks, 256, smem, stream, (long long)n, g, g_prev, s_new, y_out, hist, (long long)hist_stride, sl, nh, nout, part);
-  } else {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH(dots_kernel<false>, chunks, 256, smem, stream, (long long)n, g, g_prev, s_new, y_out, hist, (long long)hist_stride, sl, nh, nout, part);
-  }
+  int rc = hist_f32 ? launch_dots<float>(n, g, g_prev, s_new, y_out, hist, hist_stride, sl, nh, nout, part, chunks, stream)
+                    : launch_dots<double>(n, g, g_prev, s_new, y_out, hist, hist_stride, sl, nh, nout, part, chunks, stream);
+  if (rc) return rc;
   VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, out);
   return VS_OK;
 }
 
-extern "C" int vs_lbfgs_direction(int64_t n, const double* g, const double* hist, int64_t hist_stride, const int32_t* s_slots_host,
-                                  const int32_t* y_slots_host, int m, const double* coef_host, double t, double* x, double* s_out,
-                                  double* dmax_out, void* stream) {
+extern "C" int vs_lbfgs_direction(int64_t n, const double* g, const void* hist, int64_t hist_stride, int hist_f32,
+                                  const int32_t* s_slots_host, const int32_t* y_slots_host, int m, const double* coef_host,
+                                  double t, double* x, void* s_out, double* dmax_out, void* stream) {
   VS_REQUIRE(n > 0 && g && s_out && dmax_out && coef_host, VS_ERR_INVALID, "vs_lbfgs_direction: null pointer or empty vector");
   VS_REQUIRE(m >= 0 && m <= VS_LBFGS_MAX_HIST, VS_ERR_UNSUPPORTED, "vs_lbfgs_direction: history %d outside 0..%d", m, VS_LBFGS_MAX_HIST);
   VS_REQUIRE(m == 0 || (hist && s_slots_host && y_slots_host && hist_stride >= n), VS_ERR_INVALID, "vs_lbfgs_direction: history arguments");
   Slots sl;
-  Coef cf;
   for (int i = 0; i < m; ++i) { sl.s[i] = s_slots_host[i]; sl.s[m + i] = y_slots_host[i]; }
-  for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = coef_host[i];
   VS_CHECK_CUDA(cudaMemsetAsync(dmax_out, 0, sizeof(double), (cudaStream_t)stream));
   long long blocks = ceil_div(n, 256 * 4);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-  VS_LAUNCH(direction_kernel, (unsigned)blocks, 256, 0, stream, (long long)n, g, hist, (long long)hist_stride, sl, 2 * m, cf, t, x, s_out,
-            reinterpret_cast<unsigned long long*>(dmax_out));
+  if (hist_f32) {
+    CoefT<float> cf;
+    for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = (float)coef_host[i];
+    VS_LAUNCH(direction_kernel<float>, (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf,
+              coef_host[0], t, x, (float*)s_out, reinterpret_cast<unsigned long long*>(dmax_out));
+  } else {
+    CoefT<double> cf;
+    for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = coef_host[i];
+    VS_LAUNCH(direction_kernel<double>, (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf,
+              coef_host[0], t, x, (double*)s_out, reinterpret_cast<unsigned long long*>(dmax_out));
+  }
   return VS_OK;
 }

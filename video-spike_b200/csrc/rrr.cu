@@ -334,8 +334,13 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
       for (int j = 0; j < RMAX; ++j) {
         if (j >= r) continue;
         uint16_t pl0[3], pl1[3];
-        split_planes((double)(vt[j] * r0v), planes, pl0);
-        split_planes((double)(vt[j] * r1v), planes, pl1);
+        if (planes == 1) {   // plain bf16 operand: no fp64 on this path (the vector fp64 pipe is narrow)
+          pl0[0] = bf16_bits(vt[j] * r0v); pl1[0] = bf16_bits(vt[j] * r1v);
+          pl0[1] = pl0[2] = pl1[1] = pl1[2] = 0;
+        } else {
+          split_planes((double)(vt[j] * r0v), planes, pl0);
+          split_planes((double)(vt[j] * r1v), planes, pl1);
+        }
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           if (p >= planes) continue;

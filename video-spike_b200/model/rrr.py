@@ -88,7 +88,11 @@ class _PackedSplit:
 
 
 class RRRGD():
-    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None):
+    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None):
+        """`init_plan` (session-sharded joint model, parallel.py): [(eid, N, ncoef, T)] of ALL sessions of the joint
+        model in the reference's iteration order.  The init stream is drawn for every session in that order so that
+        this rank's U_s and the shared V are bit-identical to the single-process joint model; sessions that are not
+        in `train_data` are drawn and dropped."""
         self.l2 = l2
         self.eids = list(train_data.keys())
         self.withbias = True
@@ -103,14 +107,17 @@ class RRRGD():
         self.N = 0
         params = {}
         V = None
-        for eid in train_data:
-            _X = train_data[eid]['X'][0]       # (K, T, ncoef); the last coefficient is the bias column
-            _y = train_data[eid]['y'][0]       # (K, T, N)
-            K, T, ncoef = _X.shape
-            K, T, N = _y.shape
+        if init_plan is None:
+            init_plan = [(eid, train_data[eid]['y'][0].shape[2], train_data[eid]['X'][0].shape[2], train_data[eid]['y'][0].shape[1])
+                         for eid in train_data]
+        self.eids = [eid for eid, *_ in init_plan if eid in train_data]
+        for eid, N, ncoef, T in init_plan:
             scale = float(np.sqrt(T * ncomp))
             U = rng.normal((N, ncoef - 1, ncomp), scale)
             V = rng.normal((ncomp, T), scale)                  # redrawn per eid, the last one is kept (rrr.py:43,49)
+            if eid not in train_data:
+                continue
+            _y = train_data[eid]['y'][0]       # (K, T, N)
             if isinstance(_y, torch.Tensor):   # targets already on the device (pack_session_from_frames)
                 b = _y.double().mean(0).T.unsqueeze(1).contiguous()
             else:
@@ -125,6 +132,19 @@ class RRRGD():
         self._packed = {}
         self._ws = None
         self.n_closure_evals = 0
+
+    def make_optimizer(self, history_dtype=None):
+        """The optimiser `train_model_main` builds (rrr.py:199: `optim.LBFGS(params)` with torch's defaults).
+        Curvature-pair storage follows the operand precision: float32 with plain-bf16 operands (planes == 1, where a
+        closure evaluation carries ~1e-3 of rounding anyway), float64 with residual planes (parity mode).  Override
+        with `history_dtype` or the environment variable VS_LBFGS_HIST=f32|f64."""
+        if history_dtype is None:
+            env = os.environ.get("VS_LBFGS_HIST")
+            if env:
+                history_dtype = torch.float32 if env.lower() in ("f32", "float32", "fp32") else torch.float64
+            else:
+                history_dtype = torch.float32 if self.planes == 1 else torch.float64
+        return FusedLBFGS(self.model.parameters(), history_dtype=history_dtype)
 
     def train(self):
         self.model.train()
@@ -294,7 +314,7 @@ def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None
     device = get_device()
     area_model.to(device)
     print(f"training on device: {device}")
-    optimizer = FusedLBFGS(area_model.model.parameters(),)     # torch.optim.LBFGS semantics, device-side vector algebra
+    optimizer = area_model.make_optimizer()                    # torch.optim.LBFGS semantics, device-side vector algebra
     _, mse_val = train_model(area_model, train_data, optimizer, model_fname=model_fname, save=save)
     return area_model, mse_val
 

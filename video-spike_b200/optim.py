@@ -142,11 +142,17 @@ class FusedLBFGS(torch.optim.Optimizer):
         two-loop recursion runs on the host in coefficient space (lbfgs_two_loop).
       * one host<->device synchronisation per iteration (the scalars of vs_lbfgs_dots + the loss).
 
+    `history_dtype=torch.float32` stores the curvature pairs (s_i, y_i) in float32 (all arithmetic stays float64):
+    half the HBM traffic of both passes; the default float64 reproduces torch.optim.LBFGS to rounding.
+
     A closure that wants to avoid allocations writes gradients INTO the existing `p.grad` views
     (model.rrr.RRRGD.loss_and_grad does); autograd closures work too (`zero_grad()` zeroes the views)."""
 
     def __init__(self, params, lr=1, max_iter=20, max_eval=None, tolerance_grad=1e-7, tolerance_change=1e-9,
-                 history_size=100, line_search_fn=None):
+                 history_size=100, line_search_fn=None, history_dtype=torch.float64):
+        if history_dtype not in (torch.float64, torch.float32):
+            raise ValueError("history_dtype must be torch.float64 or torch.float32")
+        self._hdtype = history_dtype
         if line_search_fn is not None:
             raise vs.VsError("FusedLBFGS implements the fixed-step variant only (the reference never sets line_search_fn)")
         if history_size > 100:
@@ -171,8 +177,7 @@ class FusedLBFGS(torch.optim.Optimizer):
         ps = self._params
         dev = ps[0].device
         for p in ps:
-            if not p.is_cuda or p.dtype != torch.float64 or p.device != dev:
-                raise vs.VsError("FusedLBFGS needs float64 CUDA parameters on one device (no CPU path)")
+            self._check_param(p, dev)
         fl = self._flat
         if fl is not None and all(p.data_ptr() == fl["x"].data_ptr() + 8 * a for p, (a, _) in zip(ps, fl["span"])):
             return fl
@@ -192,7 +197,7 @@ class FusedLBFGS(torch.optim.Optimizer):
         self._point_grads(0)
         m = self.param_groups[0]["history_size"]
         self._scal = torch.zeros(8 + 6 * m + 8, dtype=torch.float64, device=dev)      # dots out | dmax | loss
-        self._ws = torch.empty(int(vs.lib.vs_lbfgs_workspace(n, m)), dtype=torch.uint8, device=dev)
+        self._alloc_workspace(n, m, dev)
         self._pairs, self._SY, self._YY, self._hist, self._free = [], [], [], None, []
         self.state[ps[0]].clear()
         return fl
@@ -216,27 +221,60 @@ class FusedLBFGS(torch.optim.Optimizer):
             old = self._hist
             have = 0 if old is None else old.shape[0]
             grow = 2 * min(self.param_groups[0]["history_size"] + 1, max(8, self.param_groups[0]["max_iter"] + 1))
-            npad = (n + 1) // 2 * 2                                     # even pitch: every slot 16-byte aligned (128-bit loads)
-            new = torch.empty((have + grow, npad), dtype=torch.float64, device=self._flat["x"].device)
+            npad = (n + 3) // 4 * 4                                     # pitch of 4 elements: every slot 16-byte aligned
+            new = torch.empty((have + grow, npad), dtype=self._hdtype, device=self._flat["x"].device)
             if old is not None:
                 new[:have].copy_(old)
             self._hist = new
             self._free = list(range(have, have + grow))
         return self._free.pop(0)
 
-    # ---- device passes ----------------------------------------------------------------------------
-    def _dots(self, g, g_prev, s_slot, y_slot, loss_t):
-        """-> host numpy array [dots out (8+6m) ..., dmax, loss] after ONE synchronisation."""
-        import numpy as np
-        fl = self._flat
+    # ---- vector passes (libvs_b200; the hooks exist so parallel.ShardedLBFGS can restrict / all-reduce them and
+    #      the CPU tests can drive the host logic with a torch backend) -----------------------------------------
+    def _check_param(self, p, dev):
+        if not p.is_cuda or p.dtype != torch.float64 or p.device != dev:
+            raise vs.VsError("FusedLBFGS needs float64 CUDA parameters on one device (no CPU path)")
+
+    def _alloc_workspace(self, n, m, dev):
+        self._ws = torch.empty(int(vs.lib.vs_lbfgs_workspace(n, m)), dtype=torch.uint8, device=dev)
+
+    def _slot_arrays(self):
         m = len(self._pairs)
         ss = (C.c_int32 * max(m, 1))(*[p[0] for p in self._pairs])
         ys = (C.c_int32 * max(m, 1))(*[p[1] for p in self._pairs])
+        return m, ss, ys
+
+    def _pass_dots(self, lo, hi, g, g_prev, s_slot, y_slot, out):
+        """vs_lbfgs_dots over elements [lo, hi) of the flat vectors: y_slot <- g - g_prev, scalars -> out."""
+        m, ss, ys = self._slot_arrays()
         hist = self._hist
-        vs.check(vs.lib.vs_lbfgs_dots(fl["n"], vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist[s_slot]) if s_slot is not None else None,
-                                      vs.ptr(hist[y_slot]) if y_slot is not None else None, vs.ptr(hist) if hist is not None else None,
-                                      hist.shape[1] if hist is not None else fl["n"], ss, ys, m, vs.ptr(self._scal), vs.ptr(self._ws), self._ws.numel(), vs.stream()))
-        k = 8 + 6 * m
+        esz = 4 if self._hdtype == torch.float32 else 8
+        off = lambda t, e: None if t is None else t.data_ptr() + lo * e        # noqa: E731
+        for t in (g, g_prev, hist):
+            if t is not None:
+                vs.ptr(t)                                                        # CUDA + contiguity check
+        vs.check(vs.lib.vs_lbfgs_dots(hi - lo, off(g, 8), off(g_prev, 8), off(hist[s_slot], esz) if s_slot is not None else None,
+                                      off(hist[y_slot], esz) if y_slot is not None else None, off(hist, esz),
+                                      hist.shape[1] if hist is not None else hi - lo, int(self._hdtype == torch.float32), ss, ys, m,
+                                      vs.ptr(out), vs.ptr(self._ws), self._ws.numel(), vs.stream()))
+
+    def _pass_direction(self, g, coef, t, x, s_slot, dmax_out):
+        """vs_lbfgs_direction over the whole flat vector: d = sum coef*basis; hist[s_slot] <- t*d; x += t*d."""
+        m, ss, ys = self._slot_arrays()
+        hist = self._hist
+        cf = (C.c_double * (2 * m + 1))(*coef)
+        vs.check(vs.lib.vs_lbfgs_direction(self._flat["n"], vs.ptr(g), vs.ptr(hist), hist.shape[1], int(self._hdtype == torch.float32),
+                                           ss, ys, m, cf, float(t), vs.ptr(x) if x is not None else None, vs.ptr(hist[s_slot]),
+                                           vs.ptr(dmax_out), vs.stream()))
+
+    def _reduce_scalars(self, k):
+        """Hook: combine self._scal[:k] (sums; index 2 is a max) and self._scal[-2] (max) across ranks."""
+
+    def _dots(self, g, g_prev, s_slot, y_slot, loss_t):
+        """-> host numpy array [dots out (8+6m) ..., dmax, loss] after ONE synchronisation."""
+        k = 8 + 6 * len(self._pairs)
+        self._pass_dots(0, self._flat["n"], g, g_prev, s_slot, y_slot, self._scal)
+        self._reduce_scalars(k)
         self._scal[-1:].copy_(torch.as_tensor(loss_t).detach().reshape(1))
         host = self._scal.cpu().numpy()
         return host[:k], float(host[-2]), float(host[-1])
@@ -321,17 +359,11 @@ class FusedLBFGS(torch.optim.Optimizer):
             prev_loss = loss
             t = min(1.0, 1.0 / g1) * lr if state["n_iter"] == 1 else lr
             g = fl["g"][fl["cur"]]
-            ss = (C.c_int32 * max(m, 1))(*[p[0] for p in self._pairs])
-            ysl = (C.c_int32 * max(m, 1))(*[p[1] for p in self._pairs])
-            coef = (C.c_double * (2 * m + 1))(cg, *cs, *cy)
             if state.get("s_slot") is not None:
                 self._free.append(state["s_slot"])
             s_slot = self._slot()
-            hist = self._hist
             stop_gtd = gtd > -tol_c
-            vs.check(vs.lib.vs_lbfgs_direction(n, vs.ptr(g), vs.ptr(hist), hist.shape[1], ss, ysl, m, coef, float(t),
-                                               None if stop_gtd else vs.ptr(fl["x"]), vs.ptr(hist[s_slot]),
-                                               vs.ptr(self._scal[-2:-1]), vs.stream()))
+            self._pass_direction(g, [cg, *cs, *cy], t, None if stop_gtd else fl["x"], s_slot, self._scal[-2:-1])
             state["s_slot"] = s_slot
             if stop_gtd:
                 break
