@@ -50,6 +50,16 @@ def peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+            ent = json.load(fh).get(key)
+        return int(ent["bytes_per_launch_avg"]) if ent else None            # bytes per launch
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
@@ -263,11 +273,26 @@ def run_rrr(args, rank, world, local):
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_kernel<bf16> (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak if peak else None, "traffic": None, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+            "frac": ach / peak if peak else None,
+            "traffic": ncu_traffic(f"rrr_K{K}_F{F}_N{N}_planes{args.planes}"), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} bf16_tflops_sustained",
             "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
             "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
             "note": "achieved counts ALGORITHMIC flops of the dense formulation; the factorised kernels execute r=3x that "
                     "(executed_tflops)"}
+
+    # ---- parity of the timed configuration (outside every timed region): the same fit with 3 operand planes and a float64
+    # L-BFGS history -- the mode the tests pin against the float64 reference to ~1e-6 -- on the same session
+    parity = None
+    if rank == 0 and not args.no_parity and args.planes == 1:
+        entry3 = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=3, device=dev)
+        m3 = RRRGD({"s": entry3}, 3, l2=100.0, planes=3)
+        m3.to(dev)
+        _, r3 = train_model(m3, {"s": entry3}, m3.make_optimizer(), "tmp", save=False)
+        ref_sse = float(r3["mse_val_mean"])
+        parity = {"val_sse": float(mse), "val_sse_3plane_f64hist": ref_sse, "rel_diff": abs(float(mse) - ref_sse) / ref_sse,
+                  "tolerance": 1e-3, "note": "validation SSE after the whole fit (20 closure evaluations)"}
+        del entry3, m3, r3
+        torch.cuda.empty_cache()
 
     # ---- end to end: pinned host uint8 frames -> R0 on device -> init -> fit -> validation loss on the host
     def e2e_fit():
@@ -276,16 +301,23 @@ def run_rrr(args, rank, world, local):
 
     del model, td, entry
     torch.cuda.empty_cache()
-    e2e_fit()
+    import gc
+    e2e_fit(); e2e_fit()
+    gc.collect(); gc.disable()                      # no collector pauses inside the timed region (re-enabled below)
     torch.cuda.synchronize(); barrier(world)
+    n_e2e = max(3, args.steps)
+    each = []
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
     for _ in range(n_e2e):
+        t1 = time.perf_counter()
         val = e2e_fit()
+        each.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize(); barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / n_e2e
+    gc.enable()
     e2e = {"value": world * K * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-           "ms_per_step": e2e_s * 1e3, "path": "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)"}
+           "ms_per_step": e2e_s * 1e3, "ms_each_rank0": [round(x, 2) for x in each],
+           "path": "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)"}
 
     if rank != 0:
         return
@@ -298,7 +330,7 @@ def run_rrr(args, rank, world, local):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": rrr_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu, "closure_evals_per_step": evals, "val_sse": float(mse), "val_sse_e2e": val}
+            "roofline": roof, "cpu_baseline": cpu, "closure_evals_per_step": evals, "val_sse": float(mse), "val_sse_e2e": val, "parity": parity}
     print(json.dumps(line))
 
 
@@ -349,7 +381,7 @@ def run_linear(args, rank, world, local):
     pk, pk_kind = peaks()
     ach = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roof = {"bound": "hbm", "kernel": "vs::dw_adamw_kernel (fused first-layer dW + AdamW)", "achieved": ach, "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
+            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(f"linear_B{B}_D{D}_N{N}"), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
             "avg_launch_ms": k_ms / max(n_k, 1), "share_of_step": k_ms / (ms * args.steps)}
 
     # e2e: per step pinned host uint8 frames + targets -> device on a copy stream (double buffered so the copy of
@@ -424,6 +456,7 @@ def main():
     ap.add_argument("--input-dim", dest="input_dim", type=int, default=120 * 128 * 128)
     ap.add_argument("--cpu-trials", dest="cpu_trials", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 5 if args.workload == "rrr" else 50

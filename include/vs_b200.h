@@ -239,6 +239,13 @@ int vs_lbfgs_direction(int64_t n, const double* g, const void* hist, int64_t his
                        const double* coef_host, double t, double* x, void* s_out, double* dmax_out,
                        void* stream);
 
+/* HOST: the two-loop recursion of torch.optim.LBFGS in coefficient space, between the two device passes.  Inputs are
+ * the inner products vs_lbfgs_dots gathered (SY[i*ld+j] = s_i.y_j, YY[i*ld+j] = y_i.y_j, sg[i] = s_i.g,
+ * yg[i] = y_i.g, gg = g.g) and torch's H_diag; coef_out (2m+1) receives [cg, cs_0.., cy_0..] for
+ * vs_lbfgs_direction and *gtd_out the directional derivative g.d.                                            */
+int vs_host_lbfgs_two_loop(int m, double gg, const double* sg, const double* yg, const double* SY, const double* YY,
+                           int ld, double H_diag, double* coef_out, double* gtd_out);
+
 /* ------------------------------------------------------------------ RRR initialisation stream (R1, HOST)
  * src/model/rrr.py:35,42-43 draws U and V from numpy's global legacy RandomState after np.random.seed(0).
  * These HOST functions (the only entry points that take host pointers and launch nothing) reproduce that

@@ -26,8 +26,11 @@ STATE_KEYS = ("encoder.layers.0", "encoder.layers.2", "encoder.layers.4",
 def init_params(input_dim: int, n_neurons: int, seed: int = 42, enc_hidden=(256, 128), bottleneck=64,
                 dec_hidden=(128, 256)):
     """Default nn.Linear initialisation in the reference's construction order (encoder then decoder,
-    linear.py:6-7) under torch.manual_seed(seed).  Returns [(W, b)] in forward order."""
-    torch.manual_seed(seed)
+    linear.py:6-7) under torch.manual_seed(seed) (seed=None: continue the current global stream, which is what
+    src/train.py does -- the DataLoader iterator created by get_metadata_from_loader, train.py:35, draws its base seed
+    from torch's global generator BEFORE the model is built).  Returns [(W, b)] in forward order."""
+    if seed is not None:
+        torch.manual_seed(seed)
     dims = [input_dim, *enc_hidden, bottleneck, *dec_hidden, 100 * n_neurons]
     params = []
     for i in range(len(dims) - 1):

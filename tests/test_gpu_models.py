@@ -293,3 +293,84 @@ def test_joint_model_through_sharded_optimizer_world1(vs, cuda):
     c = RRRGD({"s2": td["s2"]}, 3, l2=100.0, planes=3, init_plan=plan)
     ref = RRRGD(td, 3, l2=100.0, planes=3)
     assert torch.equal(c.model["s2_U"], ref.model["s2_U"]) and torch.equal(c.model["V"], ref.model["V"])
+
+
+# ----------------------------------------------------------------------------- RRR at BASELINE sizes
+def _full_size_session(K, Kt, seed=0):
+    import bench
+    F, N = 110 * 166, 144
+    ftr, ctr, fte, cte = bench.rrr_inputs(K, Kt, F, N, seed, pinned=False)
+    return ftr, ctr, fte, cte, bench.sorted_idx_42()
+
+
+def test_rrr_full_width_closure_vs_oracle(vs, cuda):
+    """Full feature width (C = 110*166 + 1 = 18,261) and N = 144 neurons on a short session (K = 24), device R0 from
+    uint8 frames, against the float64 oracle fed the same raw arrays: loss and every gradient."""
+    from model.rrr import RRRGD, pack_session_from_frames
+    ftr, ctr, fte, cte, sidx = _full_size_session(24, 8)
+    data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)], sidx)
+    td_o = {"s": data}
+    params = ro.rrr_init(td_o, 3)
+    rng = np.random.default_rng(1)
+    for k in params:
+        params[k] = params[k] + 0.02 * rng.standard_normal(params[k].shape)
+    loss_o, g_o, sse_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
+    for planes, rtol in ((1, 3e-3), (3, 1e-5)):
+        entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=cuda)
+        td = {"s": entry}
+        m = RRRGD(td, 3, l2=100.0, planes=planes); m.to(cuda)
+        _params_to_model(m, params, cuda)
+        loss = float(m.loss_and_grad(td, 0))
+        assert loss == pytest.approx(loss_o, rel=rtol)
+        for k in g_o:
+            got = m.model[k].grad.cpu().numpy()
+            assert np.abs(got - g_o[k]).max() <= rtol * np.abs(g_o[k]).max(), (planes, k)
+        del m, td, entry
+
+
+def test_rrr_full_size_properties(vs, cuda):
+    """BASELINE configs[1] at full size (K = 400, C = 18,261, N = 144, bf16 operands): properties that need no oracle.
+    (a) bit-reproducible; (b) loss == sum of the per-neuron SSE + the L2 term evaluated independently with torch;
+    (c) the gradient is the derivative of the loss: central difference along a random direction;
+    (d) predict_y reproduces the closure's residuals."""
+    from model.rrr import RRRGD, pack_session_from_frames
+    ftr, ctr, fte, cte, sidx = _full_size_session(400, 80)
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=1, device=cuda)
+    td = {"s": entry}
+    m = RRRGD(td, 3, l2=100.0, planes=1); m.to(cuda)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    with torch.no_grad():
+        for p in m.model.values():
+            p.add_(0.02 * torch.randn(p.shape, generator=g, dtype=torch.float64).to(cuda))
+    l0 = m.loss_and_grad(td, 0)
+    grads = {k: p.grad.clone() for k, p in m.model.items()}
+    l1 = m.loss_and_grad(td, 0)
+    assert float(l0) == float(l1) and all(torch.equal(grads[k], m.model[k].grad) for k in grads)           # (a)
+    sse = m.compute_MSE_RRRGD(td, 0)["s"]
+    reg = m.regression_loss()["s"]
+    assert float(l0) == pytest.approx(float(sse.sum() + reg), rel=1e-9)                                       # (b)
+    _, y, yhat = m.predict_y(td, "s", 0)
+    assert float(((yhat - y) ** 2).sum()) == pytest.approx(float(sse.sum()), rel=1e-5)                        # (d)
+    # (c) with 3 operand planes (bf16 rounding of U makes the 1-plane loss piecewise; its gradient is checked against the
+    # oracle at full width above): central difference along a random direction
+    x0 = {k: p.detach().clone() for k, p in m.model.items()}
+    del m, td, entry
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=3, device=cuda)
+    td = {"s": entry}
+    m = RRRGD(td, 3, l2=100.0, planes=3); m.to(cuda)
+    with torch.no_grad():
+        for k, p in m.model.items():
+            p.copy_(x0[k])
+    m.loss_and_grad(td, 0)
+    grads = {k: p.grad.clone() for k, p in m.model.items()}
+    d = {k: torch.randn(p.shape, generator=g, dtype=torch.float64).to(cuda) for k, p in m.model.items()}
+    gd = sum(float((grads[k] * d[k]).sum()) for k in d)
+    eps = 1e-3
+    vals = []
+    for sgn in (+1, -1):
+        with torch.no_grad():
+            for k, p in m.model.items():
+                p.copy_(x0[k] + sgn * eps * d[k])
+        vals.append(float(m.loss_and_grad(td, 0)))
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    assert fd == pytest.approx(gd, rel=2e-4)

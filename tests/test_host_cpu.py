@@ -97,6 +97,28 @@ def test_lbfgs_two_loop_matches_vector_recursion(m):
     assert gtd == pytest.approx(float(g @ d_ref), rel=1e-9)
 
 
+@pytest.mark.parametrize("m", [0, 1, 7, 30])
+def test_compiled_two_loop_equals_python_statement(m):
+    import ctypes as C
+    import vsb200 as vs
+    from optim import lbfgs_two_loop
+    rng = np.random.default_rng(m + 10)
+    n, ld = 200, 40
+    A = rng.standard_normal((n, n)); A = A @ A.T / n + np.eye(n)
+    S = rng.standard_normal((m, n)); Y = S @ A
+    g = rng.standard_normal(n)
+    SY = np.zeros((ld, ld)); YY = np.zeros((ld, ld))
+    SY[:m, :m] = S @ Y.T; YY[:m, :m] = Y @ Y.T
+    sg, yg = S @ g, Y @ g
+    cg, cs, cy, gtd = lbfgs_two_loop(float(g @ g), list(sg), list(yg), SY[:m, :m].tolist(), YY[:m, :m].tolist(), 0.7)
+    coef = np.zeros(2 * m + 1); out = C.c_double()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)                                      # noqa: E731
+    vs.check(vs.lib.vs_host_lbfgs_two_loop(m, float(g @ g), vp(np.ascontiguousarray(sg)), vp(np.ascontiguousarray(yg)), vp(SY), vp(YY), ld, 0.7,
+                                           vp(coef), C.byref(out)))
+    np.testing.assert_allclose(coef, [cg, *cs, *cy], rtol=1e-12, atol=1e-300)
+    assert out.value == pytest.approx(gtd, rel=1e-12)
+
+
 # ----------------------------------------------------------------------------- config / schedule host logic
 def test_config_include_and_update_semantics():
     """src/utils/config_utils.py:20-42: `include:` pulls a YAML file in, update_config(path) merges, and

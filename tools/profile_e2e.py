@@ -23,5 +23,21 @@ for it in range(3):
     t0 = time.perf_counter(); model = RRRGD(td, 3, l2=100.0, planes=1); tick("RRRGD.__init__", t0)
     t0 = time.perf_counter(); model.to(dev); tick("to(device)", t0)
     t0 = time.perf_counter(); opt = FusedLBFGS(model.model.parameters()); _, res = train_model(model, td, opt, "tmp", save=False); v = float(res["mse_val_mean"]); tick("fit+val", t0)
-    print(it, {k: round(v, 2) for k, v in T.items()}, "sum", round(sum(list(T.values())[1:]), 1))
-    del model, opt, td, entry
+    ms = torch.cuda.memory_stats()
+    print(it, {k: round(v, 2) for k, v in T.items()}, "sum", round(sum(list(T.values())[1:]), 1),
+          "| cudaMalloc calls so far", ms.get("num_device_alloc"), "frees", ms.get("num_device_free"), "reserved GB", round(ms["reserved_bytes.all.current"] / 2**30, 2))
+    del model, opt, td, entry, res
+# same thing through the one-call public API, timed as bench.py's e2e does
+from model.rrr import train_model_from_frames
+import gc
+gc_events = []
+gc.callbacks.append(lambda phase, info: gc_events.append((phase, info.get('generation'), time.perf_counter())))
+for it in range(24):
+    if it == 12: gc.collect(); gc.disable(); print('--- gc disabled')
+    n_ev = len(gc_events)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    m, res, _ = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3, planes=1)
+    v = float(res["mse_val_mean"]); dt = (time.perf_counter() - t0) * 1e3
+    ms = torch.cuda.memory_stats()
+    print("api", it, round(dt, 2), "ms | gc events", [(p, g) for p, g, _ in gc_events[n_ev:]], "| cudaMalloc", ms.get("num_device_alloc"), "frees", ms.get("num_device_free"), "reserved GB", round(ms["reserved_bytes.all.current"] / 2**30, 2))
+    del m, res, _

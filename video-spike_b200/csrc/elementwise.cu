@@ -2,6 +2,7 @@
 // the fused first-layer weight-gradient + AdamW update.  All are streaming kernels: 128-bit
 // coalesced accesses, L1 bypass for touch-once data, enough loads in flight per SM to cover HBM
 // latency, grids sized in multiples of the SM count.
+#include <stdlib.h>
 #include "common.cuh"
 #include "adam.cuh"
 
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 // `out` rows; each thread keeps x[0..BT) for its 4 columns in registers (frames are read ONCE),
 // forms g = sum_b dy[b,o]*x[b,i] with BT FMAs per weight and applies AdamW on the spot.  HBM
 // traffic is exactly read p,m,v + write p,m,v (24 B/weight) + the frames; dW never exists.
-template <int BT, bool kU8>
-__global__ void __launch_bounds__(256, (BT <= 16 ? 2 : 1))
+template <int BT, bool kU8, int UNROLL>
+__global__ void __launch_bounds__(256, ((BT <= 16 && UNROLL <= 2) ? 2 : 1))
 dw_adamw_kernel(const float* __restrict__ dy, const float* __restrict__ xf, const uint8_t* __restrict__ xu,
                 float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ bias,
                 float* __restrict__ mb, float* __restrict__ vb, int batch, long long in_dim, int out_dim, const AdamConsts c) {
@@ -186,7 +187,6 @@ dw_adamw_kernel(const float* __restrict__ dy, const float* __restrict__ xf, cons
     }
   }
   if (!active) return;
-  constexpr int UNROLL = 2;
   for (int o0 = 0; o0 < out_dim; o0 += UNROLL) {
     float4 pv[UNROLL], mv[UNROLL], vv[UNROLL];
 #pragma unroll
@@ -251,19 +251,40 @@ int launch_colsum(const float* dy, float* db, long long batch, long long out_dim
   return VS_OK;
 }
 
+// rows of W in flight per thread: 2 keeps two CTAs per SM resident, 8 trades occupancy for 96 KB of loads in flight
+// per SM (measured on B200: see DESIGN.md "Linear step")
+static int dw_unroll() {
+  static int u = -1;
+  if (u < 0) {
+    const char* e = getenv("VS_DW_UNROLL");
+    u = e ? atoi(e) : 2;
+    if (u != 2 && u != 4 && u != 8) u = 2;
+  }
+  return u;
+}
+
+template <int BT, bool kU8, int UNROLL>
+static int launch_dw_adamw_u(const float* dy, const float* xf, const uint8_t* xu, float* W, float* m, float* v, float* bias,
+                             float* mb, float* vb, int batch, long long in_dim, int out_dim, const AdamConsts& c, cudaStream_t st) {
+  const size_t smem = (size_t)out_dim * BT * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div(in_dim, 1024);
+  VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, kU8, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VS_LAUNCH((dw_adamw_kernel<BT, kU8, UNROLL>), grid, 256, smem, st, dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c);
+  return VS_OK;
+}
+
 template <int BT>
 static int launch_dw_adamw(const float* dy, const float* xf, const uint8_t* xu, float* W, float* m, float* v, float* bias,
                            float* mb, float* vb, int batch, long long in_dim, int out_dim, const AdamConsts& c, cudaStream_t st) {
-  const size_t smem = (size_t)out_dim * BT * sizeof(float);
-  const unsigned grid = (unsigned)ceil_div(in_dim, 1024);
-  if (xu) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dw_adamw_kernel<BT, true>), grid, 256, smem, st, dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c);
-  } else {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(dw_adamw_kernel<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dw_adamw_kernel<BT, false>), grid, 256, smem, st, dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c);
-  }
-  return VS_OK;
+  const int u = dw_unroll();
+#define VS_DW_CASE(U)                                                                                                   \
+  if (u == U) return xu ? launch_dw_adamw_u<BT, true, U>(dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c, st) \
+                        : launch_dw_adamw_u<BT, false, U>(dy, xf, xu, W, m, v, bias, mb, vb, batch, in_dim, out_dim, c, st);
+  VS_DW_CASE(2)
+  VS_DW_CASE(4)
+  VS_DW_CASE(8)
+#undef VS_DW_CASE
+  return VS_ERR_INVALID;
 }
 
 }  // namespace vs

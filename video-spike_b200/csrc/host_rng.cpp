@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -165,13 +166,15 @@ extern "C" int vs_host_rng_normal(void* state, int64_t n, double divisor, double
     // pass 1: accepted attempts per chunk
     std::vector<size_t> counts(n_chunks + 1, 0);
     const int nthr = (int)std::min<size_t>((size_t)threads, n_chunks);
+    // chunks are handed out dynamically (a shared counter): on a busy host a descheduled thread simply takes fewer
     auto for_chunks = [&](auto fn) {
       if (nthr <= 1) { std::vector<uint32_t> buf((size_t)(kSnap + 1) * kN); for (size_t k = 0; k < n_chunks; ++k) fn(k, buf.data()); return; }
+      std::atomic<size_t> next{0};
       std::vector<std::thread> pool;
       for (int t = 0; t < nthr; ++t)
-        pool.emplace_back([&, t] {
+        pool.emplace_back([&] {
           std::vector<uint32_t> buf((size_t)(kSnap + 1) * kN);
-          for (size_t k = (size_t)t; k < n_chunks; k += (size_t)nthr) fn(k, buf.data());
+          for (size_t k = next.fetch_add(1); k < n_chunks; k = next.fetch_add(1)) fn(k, buf.data());
         });
       for (auto& th : pool) th.join();
     };

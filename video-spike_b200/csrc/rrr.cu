@@ -428,39 +428,73 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
 }
 
 // ------------------------------------------------------------------ closure stage 4: epilogue of GEMM-B
-// dU[n][c][j] = 2 Gacc[c][(j,n)] + 2 l2 sum_j' U[n][c][j'] W[j'][j]; 32 c x 32 n tile, smem transpose
+// dU[n][c][j] = 2 Gacc[c][(j,n)] + 2 l2 sum_j' U[n][c][j'] W[j'][j]; 32 c x 32 n tile, smem transpose.
+// kFast (plain bf16 operands, one split): the whole combination runs in fp32 and is widened once per output -- the
+// vector fp64 pipe of the B200 is narrow and the gradient carries the ~1e-3 operand rounding anyway.  Otherwise
+// (residual planes / split-K partials) everything is summed in fp64.
+template <bool kFast, int RMAX>
 __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Gacc, long long ldg, int splits,
                                                     long long split_stride, const double* __restrict__ U,
                                                     const double* __restrict__ W, long long C1, long long N, long long Npad, int r,
                                                     double l2, double* __restrict__ dU) {
-  __shared__ float Gs[kMaxR][32][33];
-  __shared__ double Ws[kMaxR * kMaxR];
+  __shared__ float Gs[RMAX][32][33];
+  __shared__ double Ws[RMAX * RMAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long c0 = (long long)blockIdx.x * 32, n0 = (long long)blockIdx.y * 32;
   if (threadIdx.x < r * r) Ws[threadIdx.x] = W[threadIdx.x];
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = w + 8 * i;
     const long long c = c0 + cl, n = n0 + lane;
-    for (int j = 0; j < r; ++j) {
-      double gsum = 0.0;
-      if (c < C1 && n < N)
-        for (int sp = 0; sp < splits; ++sp) gsum += (double)Gacc[(long long)sp * split_stride + c * ldg + (long long)j * Npad + n];
-      Gs[j][cl][lane] = (float)gsum;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      if (j >= r) break;
+      float gv = 0.f;
+      if (c < C1 && n < N) {
+        const float* gp = Gacc + c * ldg + (long long)j * Npad + n;
+        if constexpr (kFast) {
+          gv = __ldg(gp);
+        } else {
+          double gsum = 0.0;
+          for (int sp = 0; sp < splits; ++sp) gsum += (double)gp[(long long)sp * split_stride];
+          gv = (float)gsum;
+        }
+      }
+      Gs[j][cl][lane] = gv;
     }
   }
   __syncthreads();
   const long long c = c0 + lane;
   if (c >= C1) return;
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int nl = w + 8 * i;
     const long long n = n0 + nl;
     if (n >= N) continue;
-    double u[kMaxR];
-    for (int j = 0; j < r; ++j) u[j] = U[(n * C1 + c) * r + j];
-    for (int j = 0; j < r; ++j) {
-      double reg = 0.0;
-      for (int jj = 0; jj < r; ++jj) reg += u[jj] * Ws[jj * r + j];
-      dU[(n * C1 + c) * r + j] = 2.0 * (double)Gs[j][lane][nl] + 2.0 * l2 * reg;
+    const double* up = U + (n * C1 + c) * r;
+    double* gp = dU + (n * C1 + c) * r;
+    if constexpr (kFast) {
+      float u[RMAX];
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) u[j] = j < r ? (float)up[j] : 0.f;
+      const float l2f = (float)(2.0 * l2);
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        if (j >= r) break;
+        float reg = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < RMAX; ++jj)
+          if (jj < r) reg = fmaf(u[jj], (float)Ws[jj * r + j], reg);
+        gp[j] = (double)fmaf(l2f, reg, 2.f * Gs[j][lane][nl]);
+      }
+    } else {
+      double u[RMAX];
+      for (int j = 0; j < r; ++j) u[j] = up[j];
+      for (int j = 0; j < r; ++j) {
+        double reg = 0.0;
+        for (int jj = 0; jj < r; ++jj) reg += u[jj] * Ws[jj * r + j];
+        gp[j] = 2.0 * (double)Gs[j][lane][nl] + 2.0 * l2 * reg;
+      }
     }
   }
 }
@@ -667,7 +701,11 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
     rc = gemm_b(d, Xb, w, engine, st, &sb);
     if (rc) return rc;
     dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
-    VS_LAUNCH(epi_b_kernel, g4, 256, 0, st, w.Gacc, w.ldz, sb, (long long)d.C1 * w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU);
+    const bool fast = d.planes == 1 && sb == 1;
+#define VS_EPI_B(FAST, RM) VS_LAUNCH((epi_b_kernel<FAST, RM>), g4, 256, 0, st, w.Gacc, w.ldz, sb, (long long)d.C1 * w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU)
+    if (r <= 4) { if (fast) { VS_EPI_B(true, 4); } else { VS_EPI_B(false, 4); } }
+    else { if (fast) { VS_EPI_B(true, kMaxR); } else { VS_EPI_B(false, kMaxR); } }
+#undef VS_EPI_B
   }
   return VS_OK;
 }

@@ -167,10 +167,27 @@ class FusedLBFGS(torch.optim.Optimizer):
         self._params = self.param_groups[0]["params"]
         self._flat = None
         self._pairs = []          # [(s_slot, y_slot)] oldest first
-        self._SY = []             # _SY[i][j] = s_i . y_j
-        self._YY = []             # _YY[i][j] = y_i . y_j
+        self._new_gram()          # _SY[i, j] = s_i . y_j, _YY[i, j] = y_i . y_j for the pairs in _pairs
         self._hist = None
         self._free = []
+
+    def _new_gram(self):
+        import numpy as np
+        h = self.param_groups[0]["history_size"]
+        self._SY = np.zeros((h, h))
+        self._YY = np.zeros((h, h))
+        self._coef = np.zeros(2 * h + 1)
+
+    def _two_loop(self, m, gg, sg, yg, H_diag):
+        """-> (coef[0 .. 2m], gtd): the compiled copy of lbfgs_two_loop (csrc/host_lbfgs.cpp)."""
+        import numpy as np
+        sg = np.ascontiguousarray(sg, dtype=np.float64)
+        yg = np.ascontiguousarray(yg, dtype=np.float64)
+        gtd = C.c_double()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)                                  # noqa: E731
+        vs.check(vs.lib.vs_host_lbfgs_two_loop(m, float(gg), vp(sg), vp(yg), vp(self._SY), vp(self._YY), self._SY.shape[1],
+                                               float(H_diag), vp(self._coef), C.byref(gtd)))
+        return self._coef[:2 * m + 1], gtd.value
 
     # ---- flat storage -----------------------------------------------------------------------------
     def _bind(self):
@@ -198,7 +215,8 @@ class FusedLBFGS(torch.optim.Optimizer):
         m = self.param_groups[0]["history_size"]
         self._scal = torch.zeros(8 + 6 * m + 8, dtype=torch.float64, device=dev)      # dots out | dmax | loss
         self._alloc_workspace(n, m, dev)
-        self._pairs, self._SY, self._YY, self._hist, self._free = [], [], [], None, []
+        self._pairs, self._hist, self._free = [], None, []
+        self._new_gram()
         self.state[ps[0]].clear()
         return fl
 
@@ -262,7 +280,8 @@ class FusedLBFGS(torch.optim.Optimizer):
         """vs_lbfgs_direction over the whole flat vector: d = sum coef*basis; hist[s_slot] <- t*d; x += t*d."""
         m, ss, ys = self._slot_arrays()
         hist = self._hist
-        cf = (C.c_double * (2 * m + 1))(*coef)
+        import numpy as np
+        cf = np.ascontiguousarray(coef, dtype=np.float64).ctypes.data_as(C.c_void_p)
         vs.check(vs.lib.vs_lbfgs_direction(self._flat["n"], vs.ptr(g), vs.ptr(hist), hist.shape[1], int(self._hdtype == torch.float32),
                                            ss, ys, m, cf, float(t), vs.ptr(x) if x is not None else None, vs.ptr(hist[s_slot]),
                                            vs.ptr(dmax_out), vs.stream()))
@@ -321,32 +340,30 @@ class FusedLBFGS(torch.optim.Optimizer):
             state["n_iter"] += 1
             m = len(self._pairs)
             gg, g1 = float(out[0]), float(out[1])
-            sg = [float(out[8 + 3 * i]) for i in range(m)]
-            yg = [float(out[8 + 3 * (m + i)]) for i in range(m)]
+            hs = out[8:8 + 6 * m].reshape(2 * m, 3)        # rows: s_0..s_{m-1}, y_0..y_{m-1}; cols: .g, .y_new, .s_new
+            sg, yg = hs[:m, 0].copy(), hs[m:, 0].copy()
             if state["n_iter"] == 1:
                 H_diag = 1.0
             elif y_slot is not None:
                 yy, ys_new = float(out[3]), float(out[4])
                 s_slot = state["s_slot"]
                 if ys_new > 1e-10:
-                    sy_col = [float(out[8 + 3 * i + 1]) for i in range(m)]            # s_i . y_new
-                    yy_col = [float(out[8 + 3 * (m + i) + 1]) for i in range(m)]      # y_i . y_new
-                    ys_row = [float(out[8 + 3 * (m + i) + 2]) for i in range(m)]      # y_i . s_new = s_new . y_i
+                    sy_col, yy_col, ys_row = hs[:m, 1], hs[m:, 1], hs[m:, 2]           # s_i.y_new, y_i.y_new, y_i.s_new
+                    lo = 0
                     if m == hsize:                                                     # limited memory: drop the oldest
-                        old = self._pairs.pop(0)
-                        self._free.extend(old)
-                        self._SY = [row[1:] for row in self._SY[1:]]
-                        self._YY = [row[1:] for row in self._YY[1:]]
-                        sy_col, yy_col, ys_row, sg, yg = sy_col[1:], yy_col[1:], ys_row[1:], sg[1:], yg[1:]
-                        m -= 1
-                    for i in range(m):
-                        self._SY[i].append(sy_col[i])
-                        self._YY[i].append(yy_col[i])
-                    self._SY.append(ys_row + [ys_new])
-                    self._YY.append(yy_col + [yy])
+                        self._free.extend(self._pairs.pop(0))
+                        self._SY[:m - 1, :m - 1] = self._SY[1:m, 1:m].copy()
+                        self._YY[:m - 1, :m - 1] = self._YY[1:m, 1:m].copy()
+                        lo, m = 1, m - 1
+                    self._SY[:m, m] = sy_col[lo:]
+                    self._SY[m, :m] = ys_row[lo:]
+                    self._SY[m, m] = ys_new
+                    self._YY[:m, m] = yy_col[lo:]
+                    self._YY[m, :m] = yy_col[lo:]
+                    self._YY[m, m] = yy
                     self._pairs.append((s_slot, y_slot))
-                    sg.append(float(out[5]))
-                    yg.append(float(out[6]))
+                    sg = np.append(sg[lo:], out[5])
+                    yg = np.append(yg[lo:], out[6])
                     H_diag = ys_new / yy
                     state["s_slot"] = None
                 else:
@@ -354,7 +371,7 @@ class FusedLBFGS(torch.optim.Optimizer):
                     state["s_slot"] = None
                 y_slot = None
             m = len(self._pairs)
-            cg, cs, cy, gtd = lbfgs_two_loop(gg, sg, yg, self._SY, self._YY, H_diag)
+            coef, gtd = self._two_loop(m, gg, sg, yg, H_diag)
             state["prev_buf"] = fl["cur"]          # torch: prev_flat_grad.copy_(flat_grad) -- here a buffer swap
             prev_loss = loss
             t = min(1.0, 1.0 / g1) * lr if state["n_iter"] == 1 else lr
@@ -363,7 +380,7 @@ class FusedLBFGS(torch.optim.Optimizer):
                 self._free.append(state["s_slot"])
             s_slot = self._slot()
             stop_gtd = gtd > -tol_c
-            self._pass_direction(g, [cg, *cs, *cy], t, None if stop_gtd else fl["x"], s_slot, self._scal[-2:-1])
+            self._pass_direction(g, coef, t, None if stop_gtd else fl["x"], s_slot, self._scal[-2:-1])
             state["s_slot"] = s_slot
             if stop_gtd:
                 break

@@ -129,15 +129,17 @@ def main(argv=None):
     if not device_r0:
         train_data = preprocess_host(train_data, my_eids, args.input_mod, sorted_idx)
     l2, n_comp = 100, 3
+    planes = int(os.environ.get("VS_RRR_PLANES", "1"))            # 1 = plain bf16 operands (BASELINE config), 3 = parity mode
     print('start training')
     result, test_bps = {}, []
     for eid in my_eids:
         if device_r0:   # uint8 frames: smoothing, z-scoring, frame selection and packing on the device
             d = train_data[eid]
             entry = pack_session_from_frames(torch.from_numpy(d["X"][0]), d["y"][0], torch.from_numpy(d["X"][1]), d["y"][1],
-                                             sorted_idx, n_comp, smooth_w=2.0)
+                                             sorted_idx, n_comp, planes=planes, smooth_w=2.0)
             train_data[eid] = entry
-        model, mse_val = train_model_main(train_data={eid: train_data[eid]}, l2=l2, n_comp=n_comp, model_fname='tmp', save=True)
+        model, mse_val = train_model_main(train_data={eid: train_data[eid]}, l2=l2, n_comp=n_comp, model_fname='tmp', save=True,
+                                          planes=planes)
         print('finished training')
         print('eid:', eid)
         _, _, pred_orig = model.predict_y_fr(train_data, eid, 1)

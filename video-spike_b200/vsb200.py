@@ -76,6 +76,7 @@ def _load():
         "vs_lbfgs_workspace": (sz, [i64, i32]),
         "vs_lbfgs_dots": (C.c_int, [i64, vp, vp, vp, vp, vp, i64, i32, vp, vp, i32, vp, vp, sz, vp]),
         "vs_lbfgs_direction": (C.c_int, [i64, vp, vp, i64, i32, vp, vp, i32, vp, dbl, vp, vp, vp, vp]),
+        "vs_host_lbfgs_two_loop": (C.c_int, [i32, dbl, vp, vp, vp, vp, i32, dbl, vp, vp]),
         "vs_host_rng_seed": (C.c_int, [vp, C.c_uint32]),
         "vs_host_rng_normal": (C.c_int, [vp, i64, dbl, vp, i32]),
         "vs_host_rng_get_state": (C.c_int, [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
