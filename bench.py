@@ -126,14 +126,30 @@ def max_over_ranks(x, world, device):
 
 
 # ----------------------------------------------------------------------------- synthetic inputs
-def rrr_inputs(K, Kt, F, N, seed, pinned):
-    """uint8 frames of the loader's shape (K,120,1,h,w flattened to F) + Poisson(0.4) counts; host, pinned."""
+def rrr_inputs(K, Kt, F, N, seed, pinned, signal=False):
+    """Synthetic session of the loader's shape: dense uniform 0..255 uint8 frames (K,120,1,h,w
+    flattened to F) and Poisson(0.4) spike counts (K,100,N).  signal=True plants a rank-3 dependence of the rate on the
+    frames instead (used by tools/parity_probe.py: on it the reference's un-line-searched L-BFGS is chaotic even in
+    float64 -- profiles/r01_parity_probe_signal_data.txt).  Host tensors, optionally pinned."""
     g = torch.Generator().manual_seed(seed)
     mk = (lambda *s, **k: torch.empty(*s, **k).pin_memory()) if pinned else torch.empty
     ftr = mk((K, FRAMES_PER_TRIAL, F), dtype=torch.uint8); ftr.random_(0, 256, generator=g)
     fte = mk((Kt, FRAMES_PER_TRIAL, F), dtype=torch.uint8); fte.random_(0, 256, generator=g)
-    ctr = mk((K, 100, N), dtype=torch.float32); ctr.copy_(torch.poisson(torch.full((K, 100, N), 0.4), generator=g))
-    cte = mk((Kt, 100, N), dtype=torch.float32); cte.copy_(torch.poisson(torch.full((Kt, 100, N), 0.4), generator=g))
+    ctr = mk((K, 100, N), dtype=torch.float32)
+    cte = mk((Kt, 100, N), dtype=torch.float32)
+    if not signal:
+        ctr.copy_(torch.poisson(torch.full((K, 100, N), 0.4), generator=g))
+        cte.copy_(torch.poisson(torch.full((Kt, 100, N), 0.4), generator=g))
+        return ftr, ctr, fte, cte
+    Wt = torch.randn((F, 3), generator=g) / float(np.sqrt(F))
+    Vt = torch.randn((3, 100), generator=g)
+    A = torch.randn((3, N), generator=g)
+    for fr, cnt in ((ftr, ctr), (fte, cte)):
+        for k0 in range(0, fr.shape[0], 32):                     # chunked: the float copy of the frames is 4x their size
+            x = (fr[k0:k0 + 32, :100].float() - 127.5) / 74.0     # frames 0..99 drive bins 0..99
+            lat = torch.einsum("ktf,fj->ktj", x, Wt) * Vt.T.unsqueeze(0)
+            rate = torch.exp(torch.clamp(0.3 * torch.einsum("ktj,jn->ktn", lat, A), -3.0, 2.0) - 1.0)
+            cnt[k0:k0 + 32].copy_(torch.poisson(rate, generator=g))
     return ftr, ctr, fte, cte
 
 
@@ -205,14 +221,16 @@ def reference_arm(args, rank, world):
 def rrr_config(args, world):
     return {"workload": "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
-            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes, "lbfgs": "1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64",
+            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes,
+            "operand_format": (os.environ.get("VS_RRR_OPERAND") or "bf16") + " (16-bit tensor-core operands, fp32 accumulate in TMEM)", "lbfgs": "1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64",
             "sessions": world, "parallelism": f"session-sharded x{world}" if world > 1 else "single GPU",
             "l2_cache": "operands (1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
 
 
 def linear_config(args, world):
     return {"workload": "linear_mlp_train_step (BASELINE configs[0] on B200)", "batch": args.batch, "input_dim": args.input_dim,
-            "neurons": args.neurons, "optimizer": "AdamW+OneCycleLR", "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+            "neurons": args.neurons, "optimizer": "AdamW+OneCycleLR",
+            "parallelism": f"first layer row-parallel over {world} GPUs (pixel shards), one 16 KB all-reduce per step" if world > 1 else "single GPU",
             "l2_cache": "weights+Adam state (6 GB) exceed the 126 MB L2; no flush needed"}
 
 
@@ -234,6 +252,7 @@ def run_rrr(args, rank, world, local):
     td = {"s": entry}
     model = RRRGD(td, 3, l2=100.0, planes=args.planes)
     model.to(dev)
+    model_fmt = model.fmt
     init = {k: v.detach().clone() for k, v in model.model.items()}
 
     def one_fit():
@@ -272,7 +291,7 @@ def run_rrr(args, rank, world, local):
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_kernel<bf16> (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_kernel (tcgen05 kind::f16, 16-bit operands)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak if peak else None,
             "traffic": ncu_traffic(f"rrr_K{K}_F{F}_N{N}_planes{args.planes}"), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} bf16_tflops_sustained",
             "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
@@ -287,10 +306,26 @@ def run_rrr(args, rank, world, local):
         entry3 = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=3, device=dev)
         m3 = RRRGD({"s": entry3}, 3, l2=100.0, planes=3)
         m3.to(dev)
+        # (1) one closure evaluation at identical (initial) parameters: loss and gradient, timed mode vs 3 planes
+        gp = torch.Generator().manual_seed(1)
+        with torch.no_grad():                      # perturbed start (at the exact init the gradient of b is ~0 by construction)
+            for k, v in init.items():
+                x = v + (0.02 * torch.randn(v.shape, generator=gp, dtype=torch.float64)).to(dev)
+                model.model[k].copy_(x)
+                m3.model[k].copy_(x)
+        l1, l3 = float(model.loss_and_grad(td, 0)), float(m3.loss_and_grad({"s": entry3}, 0))
+        gerr = {k.split("_")[-1]: float((model.model[k].grad - m3.model[k].grad).abs().max() / m3.model[k].grad.abs().max()) for k in init}
+        with torch.no_grad():
+            for k, v in init.items():
+                m3.model[k].copy_(v)
+        # (2) the whole fit (20 closure evaluations of an un-line-searched L-BFGS amplify any perturbation)
         _, r3 = train_model(m3, {"s": entry3}, m3.make_optimizer(), "tmp", save=False)
         ref_sse = float(r3["mse_val_mean"])
-        parity = {"val_sse": float(mse), "val_sse_3plane_f64hist": ref_sse, "rel_diff": abs(float(mse) - ref_sse) / ref_sse,
-                  "tolerance": 1e-3, "note": "validation SSE after the whole fit (20 closure evaluations)"}
+        parity = {"per_eval_loss_rel_diff": abs(l1 - l3) / abs(l3), "per_eval_grad_max_abs_diff_over_max_abs": gerr,
+                  "fit_val_sse": float(mse), "fit_val_sse_3plane_f64hist": ref_sse, "fit_rel_diff": abs(float(mse) - ref_sse) / ref_sse,
+                  "tolerance": 1e-3,
+                  "note": "reference = 3 bf16 residual planes + float64 L-BFGS history (pinned to the float64 reference by the tests; "
+                          "1.0e-4 from a float64 dense torch fit at this size, profiles/r01_parity_probe_noise_data.txt)"}
         del entry3, m3, r3
         torch.cuda.empty_cache()
 
@@ -305,7 +340,7 @@ def run_rrr(args, rank, world, local):
     e2e_fit(); e2e_fit()
     gc.collect(); gc.disable()                      # no collector pauses inside the timed region (re-enabled below)
     torch.cuda.synchronize(); barrier(world)
-    n_e2e = max(3, args.steps)
+    n_e2e = max(5, args.steps)
     each = []
     t0 = time.perf_counter()
     for _ in range(n_e2e):
@@ -313,10 +348,15 @@ def run_rrr(args, rank, world, local):
         val = e2e_fit()
         each.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize(); barrier(world)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / n_e2e
+    mean_s = max_over_ranks(time.perf_counter() - t0, world, dev) / n_e2e
+    # this path crosses the host 20+ times per fit (init stream threads, one sync per L-BFGS iteration, PCIe): on a shared
+    # box single iterations are hit by 100+ ms of host jitter, so the headline uses the MEDIAN iteration (max over ranks);
+    # the mean and every sample are reported next to it
+    e2e_s = max_over_ranks(float(np.median(each)) * 1e-3, world, dev)
     gc.enable()
     e2e = {"value": world * K * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-           "ms_per_step": e2e_s * 1e3, "ms_each_rank0": [round(x, 2) for x in each],
+           "ms_per_step": e2e_s * 1e3, "statistic": f"median of {n_e2e} fits", "mean_ms_per_step": mean_s * 1e3,
+           "ms_each_rank0": [round(x, 2) for x in each],
            "path": "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)"}
 
     if rank != 0:
@@ -328,7 +368,8 @@ def run_rrr(args, rank, world, local):
                "sample": f"oracle autograd closure (torch fp64 CPU), {args.cpu_trials} trials x 120 frames at full C={C}, N={N}: "
                          f"2 timed closure evals ({ev_s:.2f} s each), fit = 20 evals"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16" if model_fmt == 1 else "bf16",
             "data": "synthetic", "config": rrr_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "closure_evals_per_step": evals, "val_sse": float(mse), "val_sse_e2e": val, "parity": parity}
     print(json.dumps(line))
@@ -343,18 +384,32 @@ def run_linear(args, rank, world, local):
     torch.cuda.set_device(dev)
     B, D, N = args.batch, args.input_dim, args.neurons
     model, opt, sched = make_linear_model(D, N, dev, total_steps=5000)
-    g = torch.Generator().manual_seed(rank)
+    lo_px, hi_px = 0, D
+    if world > 1:
+        # row-parallel first layer: rank g keeps W0[:, D_g] and receives only the pixels D_g of every frame;
+        # ONE all-reduce of the (B, 256) pre-activation per step; the global batch and the optimisation are those of 1 GPU
+        from optim import FusedAdamW
+        lo_px, hi_px = model.shard_first_layer(rank, world)
+        o = opt.defaults
+        opt = FusedAdamW(model.parameters(), lr=o["lr"], weight_decay=o["weight_decay"], eps=o["eps"])
+        sched = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, total_steps=5000, max_lr=5e-5, pct_start=0.15, div_factor=10)
+        torch.cuda.empty_cache()
+    Dl = hi_px - lo_px
+    g = torch.Generator().manual_seed(0)                    # the SAME batches on every rank (each keeps its pixel slice)
     nbuf = 4
-    frames_h = [torch.empty((B, D), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+    frames_h = [torch.empty((B, Dl), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
     ap_h = [torch.empty((B, 100, N), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
     for f, a in zip(frames_h, ap_h):
-        f.random_(0, 9, generator=g)           # small values: the reference diverges on dense 0..255 frames
+        full = torch.empty((B, D), dtype=torch.uint8)
+        full.random_(0, 9, generator=g)        # small values: the reference diverges on dense 0..255 frames
+        f.copy_(full[:, lo_px:hi_px])
         a.copy_(torch.poisson(torch.full((B, 100, N), 0.3), generator=g))
     frames_d = [f.to(dev) for f in frames_h]
     ap_d = [a.to(dev) for a in ap_h]
+    train_step = model.fused_train_step_rowpar if world > 1 else model.fused_train_step
 
     def step(i, fr, ap):
-        loss = model.fused_train_step(fr[i % nbuf], ap[i % nbuf], opt)
+        loss = train_step(fr[i % nbuf], ap[i % nbuf], opt)
         sched.step()
         return loss
 
@@ -375,19 +430,19 @@ def run_linear(args, rank, world, local):
     launches = int(vs.lib.vs_launch_count())
     n_k, k_ms, _, _ = vs.profile_read(1)
     vs.lib.vs_profile_enable(0)
-    value = world * B * FRAMES_PER_TRIAL / (ms * 1e-3)
-    P0 = D * 256
-    algo_bytes = n_k * (24.0 * P0 + B * D + 4.0 * B * 256)     # p,m,v read+write, frames once, dH1
+    value = B * FRAMES_PER_TRIAL / (ms * 1e-3)              # ONE global batch per step whatever the world size (strong scaling)
+    P0 = Dl * 256
+    algo_bytes = n_k * (24.0 * P0 + B * Dl + 4.0 * B * 256)    # p,m,v read+write, frames once, dH1 (this rank's slice)
     pk, pk_kind = peaks()
     ach = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roof = {"bound": "hbm", "kernel": "vs::dw_adamw_kernel (fused first-layer dW + AdamW)", "achieved": ach, "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(f"linear_B{B}_D{D}_N{N}"), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
+            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(f"linear_B{B}_D{D}_N{N}") if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
             "avg_launch_ms": k_ms / max(n_k, 1), "share_of_step": k_ms / (ms * args.steps)}
 
     # e2e: per step pinned host uint8 frames + targets -> device on a copy stream (double buffered so the copy of
     # batch i+1 overlaps the compute of batch i), loss -> host every step like src/trainer/base.py:154
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [(torch.empty((B, D), dtype=torch.uint8, device=dev), torch.empty((B, 100, N), dtype=torch.float32, device=dev))
+    slots = [(torch.empty((B, Dl), dtype=torch.uint8, device=dev), torch.empty((B, 100, N), dtype=torch.float32, device=dev))
              for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     free = [None, None]
@@ -408,7 +463,7 @@ def run_linear(args, rank, world, local):
         for i in range(n):
             fr, ap = slots[i % 2]
             cur.wait_event(ready[i % 2])
-            loss = model.fused_train_step(fr, ap, opt)
+            loss = train_step(fr, ap, opt)
             sched.step()
             free[i % 2] = torch.cuda.Event()
             free[i % 2].record(cur)
@@ -423,7 +478,7 @@ def run_linear(args, rank, world, local):
     e2e_loop(args.steps)
     torch.cuda.synchronize(); barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / args.steps
-    e2e = {"value": world * B * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * D + 4 * B * 100 * N),
+    e2e = {"value": B * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * Dl + 4 * B * 100 * N),
            "d2h_bytes_per_step": 8, "ms_per_step": e2e_s * 1e3,
            "path": "Linear.fused_train_step(pinned uint8 frames -> device copy stream) + float(loss) every step"}
     if rank != 0:
@@ -434,7 +489,8 @@ def run_linear(args, rank, world, local):
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"oracle Trainer.step (torch fp32 CPU port of the reference step), B={B}, D={D}, N={N}, 2 timed steps ({dt:.2f} s each)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 fwd / f32 update",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "tf32 fwd / f32 update",
             "data": "synthetic", "config": linear_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "loss": float(loss)}
     print(json.dumps(line))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 3
+#define VS_ABI_VERSION 4
 
 enum {
   VS_OK = 0,
@@ -92,6 +92,15 @@ int vs_linear_bwd(const float* dy, const float* y, const float* x_f32, const uin
 int vs_poisson_nll(const float* logits, const float* target, double* loss_sum, float* dlogits,
                    int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ evaluation metrics (E2)
+ * src/utils/metric_utils.py:36-102 + the loops of src/utils/utils.py:122-181, on the device.  rates / spikes / gt / pred
+ * are (K, T, N) fp32 (what src/trainer/base.py:180-189 concatenates; rates = exp(logits)).
+ * vs_bits_per_spike: bps_n[n] for every neuron (zero rates -> 1e-9, NaN spike bins masked, like the reference).
+ * vs_r2_rows: r2_kt[k*T + t] = sklearn r2_score over the N neurons of (trial k, bin t); averaging over t gives the
+ * `r2_score(gt[:, :, k], pred[:, :, k])` of utils.py:158.                                                        */
+int vs_bits_per_spike(const float* rates, const float* spikes, int64_t K, int64_t T, int64_t N, double* bps_n, void* stream);
+int vs_r2_rows(const float* gt, const float* pred, int64_t K, int64_t T, int64_t N, double* r2_kt, void* stream);
+
 /* ------------------------------------------------------------------ AdamW (O1)
  * torch.optim.AdamW single-tensor update (src/train.py:44-49, src/trainer/base.py:151):
  *   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
@@ -142,6 +151,15 @@ size_t vs_mlp_workspace(const vs_mlp* net, int64_t batch);
 int vs_mlp_train_step(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32,
                       const float* target, int64_t batch, vs_adamw_hyper h, double* loss_sum,
                       int engine, void* workspace, size_t workspace_bytes, void* stream);
+/* The same step with the FIRST layer row-parallel over ranks: this rank holds the pixel slice dims[0] of
+ * every frame and the matching columns of W0 with their Adam moments; all later layers are replicated.
+ *   phase 0: act[0] <- frames_slice . W0_slice^T (no bias, no ReLU).  The caller then all-reduces (sum) act[0], a
+ *            (batch, dims[1]) fp32 matrix -- 16 KB at the reference sizes -- over NCCL.
+ *   phase 1: act[0] <- act(act[0] + b0), layers 1.., loss, backward, AdamW on every local parameter (dW0 needs no
+ *            collective: dH1 is replicated and the pixel slice is local).                                          */
+int vs_mlp_train_step_rowpar(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target,
+                             int64_t batch, vs_adamw_hyper h, double* loss_sum, int engine, void* workspace,
+                             size_t workspace_bytes, void* stream, int phase);
 /* forward only (E1: src/trainer/base.py:161-206); logits land in net->act[L-1]; if target
  * is non-NULL the Poisson loss sum is also produced.                                    */
 int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32,
@@ -158,13 +176,20 @@ int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f
  *   Xa : planes x (K*T) x ldc   bf16, row d, c contiguous           (forward  A operand)
  *   Xb : planes x C1 x ldr      bf16, row c, d contiguous           (backward A operand)
  *   xl : (K*T) fp32, the last column of X, indexed by d
- * planes = 1 stores bf16(X); planes = 2 or 3 store the exact residual expansion
- * X ~= X0 + X1 (+ X2), each bf16, giving ~16 / ~24 significant bits.                    */
+ * planes = 1 stores the 16-bit rounding of X; planes = 2 or 3 store the exact residual expansion
+ * X ~= X0 + X1 (+ X2), each 16-bit, giving ~16 / ~24 significant bits with bf16 planes.  d.fmt selects bf16 or
+ * IEEE half for all planes; with half, *overflow_flag (device int32, may be NULL; OR-ed, never cleared) becomes
+ * non-zero when a value exceeds the half range (e.g. the exploding test features of SURVEY A18).          */
+enum {
+  VS_OPERAND_BF16 = 0, /* 8 significant bits, fp32 range */
+  VS_OPERAND_F16 = 1   /* 11 significant bits at the same tensor-core rate; |x| <= 65504 (the pack calls report overflow) */
+};
 typedef struct {
   int64_t K, T, C1, N, r; /* trials, time bins, features without the bias column, neurons, rank */
   int32_t planes;         /* 1, 2 or 3 */
   int64_t ldc;            /* row pitch of Xa in elements, multiple of 64, >= C1 */
   int64_t ldr;            /* row pitch of Xb in elements, multiple of 64, >= K*T */
+  int32_t fmt;            /* VS_OPERAND_*: 16-bit format of every tensor-core operand plane (X, U, residuals) */
 } vs_rrr_dims;
 
 /* pitches the library wants for given sizes */
@@ -175,7 +200,7 @@ int64_t vs_rrr_ldr(int64_t K, int64_t T);
  * (src/model/rrr.py:37-39), on the device.  Writes the matching rows of Xa / columns of Xb / xl;
  * call once with (0, K) or chunk by chunk to bound the fp64 staging buffer.               */
 int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
-                float* xl, void* stream);
+                float* xl, int32_t* overflow_flag, void* stream);
 
 /* R0 on device from raw frames (src/train_rrr.py:143-165 for the video modalities):
  * frames (K, Tf, F) uint8; sorted_idx (T) int32 frame indices; mean/std (Tf*F) fp64 as
@@ -183,7 +208,8 @@ int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rrr_dims d, u
  * would for X = ((frames - mean)/std)[:, sorted_idx] with a ones column appended.        */
 int vs_rrr_colstats(const uint8_t* frames, int64_t K, int64_t cols, double* mean, double* std_clipped, void* stream);
 int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
-                   const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb, float* xl, void* stream);
+                   const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb, float* xl,
+                   int32_t* overflow_flag, void* stream);
 /* y (K,T,N) = (gaussian_filter1d(counts, sigma, axis=1, mode='reflect') - mean)/std as
  * src/train_rrr.py:118,145,165 (scipy.ndimage truncate=4).  counts (K,T,N) fp32; mean/std (T*N) fp64
  * may be NULL to get the smoothed counts only (used to derive the train statistics).      */
@@ -265,7 +291,7 @@ int vs_host_rng_set_state(void* state, const uint32_t* key624, int32_t pos, int3
 /* ------------------------------------------------------------------ plain TN GEMM (test hook)
  * C[M,N] (fp32, row-major, ldc) = A[M,K] * B[N,K]^T with bf16 or tf32(fp32) operands, both
  * K-major with pitches lda/ldb (elements).  Exposed so tests can exercise the tcgen05 core
- * against the SIMT engine on arbitrary shapes.  dtype: 0 = bf16, 1 = tf32.              */
+ * against the SIMT engine on arbitrary shapes.  dtype: 0 = bf16, 1 = tf32, 2 = f16.     */
 int vs_gemm_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                int64_t ldb, int64_t ldc, int dtype, int engine, void* stream);
 

@@ -2,6 +2,7 @@
 Bit-exact for the byte/index work (loader, frame selection), stated tolerances for floating point."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -64,6 +65,18 @@ def test_gemm_tcgen05_bf16(vs, cuda, M, N, K):
     torch.testing.assert_close(Cm.double(), _gemm_ref(A, B), rtol=1e-4, atol=2e-3)
     Cs = vs.gemm_tn(A, B, vs.ENGINE_SIMT)
     torch.testing.assert_close(Cm, Cs, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 64), (300, 432, 1000), (130, 448, 520)])
+def test_gemm_tcgen05_f16(vs, cuda, M, N, K):
+    """IEEE-half operands (kind::f16 with a/b format 0): products exact in fp32, same tolerance as bf16."""
+    torch.manual_seed(11)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device=cuda, dtype=torch.float16); A[:, :K] = torch.randn(M, K, device=cuda)
+    B = torch.zeros(N, Kp, device=cuda, dtype=torch.float16); B[:, :K] = torch.randn(N, K, device=cuda)
+    Cm = vs.gemm_tn(A, B, vs.ENGINE_TCGEN05)
+    torch.testing.assert_close(Cm.double(), _gemm_ref(A, B), rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(Cm, vs.gemm_tn(A, B, vs.ENGINE_SIMT), rtol=1e-4, atol=2e-3)
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 16, 32), (256, 16, 4096), (256, 48, 10000), (200, 100, 260)])
@@ -227,3 +240,37 @@ def test_gather_windows_bit_exact(vs, cuda, hw):
     tail = gather_trial_windows(torch.from_numpy(video).to(cuda), np.array([n_frames - 50]), frames_per_trial=120)
     assert torch.equal(tail[0, :50].cpu(), torch.from_numpy(video[-50:])) and int(tail[0, 50:].max()) == 0
     assert gather_trial_windows(torch.from_numpy(video).to(cuda), np.zeros(0, dtype=np.int64)).shape[0] == 0
+
+
+# ----------------------------------------------------------------------------- evaluation metrics (E2)
+def test_device_metrics_match_oracle(vs, cuda, golden_dir):
+    from oracle import metrics_oracle as mo
+    from utils.metric_utils import device_bits_per_spike, device_r2_per_trial
+    from utils.utils import metrics_list
+    rng = np.random.default_rng(5)
+    K, T, N = 9, 100, 37
+    spikes = rng.poisson(0.4, size=(K, T, N)).astype(np.float32)
+    spikes[:, :, 5] = 0                                                  # a silent neuron: bps is nan/inf like the reference
+    rates = np.clip(0.4 + 0.2 * rng.standard_normal((K, T, N)), 0.0, None).astype(np.float32)   # includes exact zeros
+    got = device_bits_per_spike(torch.from_numpy(rates).to(cuda), torch.from_numpy(spikes).to(cuda)).cpu().numpy()
+    with np.errstate(all="ignore"):
+        ref = np.array([mo.bits_per_spike(rates[:, :, [n]].astype(np.float64), spikes[:, :, [n]].astype(np.float64)) for n in range(N)])
+    ok = np.isfinite(ref)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-12)
+    assert not np.isfinite(got[5]) and not np.isfinite(ref[5])
+    r2 = device_r2_per_trial(torch.from_numpy(spikes).to(cuda), torch.from_numpy(rates).to(cuda)).cpu().numpy()
+    ref_r2 = np.array([mo.r2_score_multi(spikes[k].T.astype(np.float64), rates[k].T.astype(np.float64)) for k in range(K)])
+    np.testing.assert_allclose(r2, ref_r2, rtol=1e-9)
+    # the trainer-facing loop (utils.metrics_list) on CUDA tensors == the oracle's transcription, quirk A8 included
+    g = torch.from_numpy(spikes).to(cuda).transpose(-1, 0)              # (N, T, K) as src/trainer/base.py:190 passes it
+    p = torch.from_numpy(rates).to(cuda).transpose(-1, 0)
+    res = metrics_list(gt=g, pred=p, metrics=["bps", "rsquared"], device=cuda)
+    with np.errstate(all="ignore"):
+        want = mo.metrics_list(spikes.astype(np.float64), rates.astype(np.float64))
+    assert res["bps"] == pytest.approx(want["bps"], rel=1e-9) and res["rsquared"] == pytest.approx(want["rsquared"], rel=1e-9)
+    with pytest.raises(IndexError):
+        metrics_list(gt=torch.ones(3, 100, 5, device=cuda), pred=torch.ones(3, 100, 5, device=cuda))
+    # golden KAT of SURVEY section 4 through the device kernel
+    gk = np.load(os.path.join(golden_dir, "metrics_kat.npz"))
+    b0 = device_bits_per_spike(torch.from_numpy(gk["rates"]).to(cuda), torch.from_numpy(gk["spikes"]).to(cuda))[0]
+    assert float(b0) == pytest.approx(float(gk["bps_n0"]), rel=1e-6)     # rates pass through float32 on this route

@@ -11,6 +11,8 @@ from oracle import linear_oracle as lo
 from oracle import rrr_oracle as ro
 from tests.helpers import make_linear_model, small_rrr_problem
 
+lo_synth = lo.synth_batch
+
 pytestmark = pytest.mark.gpu
 
 
@@ -149,9 +151,10 @@ def _params_to_model(model, params, dev):
 
 
 @pytest.mark.parametrize("engine", [1, 2])
-@pytest.mark.parametrize("planes,rtol", [(1, 2e-3), (2, 2e-5), (3, 2e-6)])
-def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, rtol):
-    """One closure evaluation (loss, per-neuron SSE, dU, dV, db) at perturbed parameters vs float64."""
+@pytest.mark.parametrize("planes,operand,rtol", [(1, "bf16", 2e-3), (1, "f16", 3e-4), (2, "bf16", 2e-5), (3, "bf16", 2e-6), (2, "f16", 2e-5)])
+def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, operand, rtol):
+    """One closure evaluation (loss, per-neuron SSE, dU, dV, db) at perturbed parameters vs float64, for every operand
+    mode: plain bf16 (8 bits), plain IEEE half (11 bits: the default fast mode), residual planes (parity modes)."""
     from model.rrr import RRRGD
     td = small_rrr_problem(seed=1, K=30, Kt=9, F=200, N=21)
     params = ro.rrr_init(td, 3)
@@ -159,7 +162,7 @@ def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, rtol):
     for k in params:
         params[k] = params[k] + 0.05 * rng.standard_normal(params[k].shape)
     loss_o, g_o, sse_o = ro.loss_and_grad_dense(params, td, 100.0, 0)
-    m = RRRGD(td, 3, l2=100.0, planes=planes, engine=engine)
+    m = RRRGD(td, 3, l2=100.0, planes=planes, engine=engine, operand=operand)
     m.to(cuda)
     _params_to_model(m, params, cuda)
     loss = m.loss_and_grad(td, 0)
@@ -175,7 +178,7 @@ def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, rtol):
     ref = ro.predict(ro.compute_beta(params["e1_U"], params["V"], params["e1_b"]), td["e1"]["X"][1])
     err = yhat.cpu().numpy() - ref
     # plain bf16 operands: each product carries ~2^-9 relative rounding, so z-scored predictions agree to
-    # ~2e-3 in relative L2 (loss to ~3e-4); two planes give ~1e-5, three ~1e-6 (DESIGN.md "RRR precision")
+    # ~2e-3 in relative L2 (loss to ~3e-4); plain half ~3e-4; two bf16 planes ~1e-5, three ~1e-6 (DESIGN.md "RRR precision")
     assert np.linalg.norm(err) <= 2.0 * rtol * np.linalg.norm(ref)
     assert np.abs(err).max() <= 3.0 * rtol * np.abs(ref).max()
 
@@ -210,15 +213,33 @@ def test_rrr_fit_matches_reference_golden(vs, cuda, golden_dir, name):
     assert ev["r2"] == pytest.approx(ev_o["r2"], rel=1e-3, abs=1e-5)
 
 
-def test_rrr_bf16_single_plane_fit_runs_and_tracks(vs, cuda):
-    """BASELINE config 2 precision (plain bf16 operands): every closure evaluation is within 1e-3 of
-    float64 at the same parameters (test above); the fit itself follows the reference's un-line-searched
-    LBFGS trajectory only approximately (DESIGN.md 'RRR precision'), so it is checked loosely."""
+def test_rrr_single_plane_fits_track_the_reference(vs, cuda):
+    """The fast single-plane modes through a whole fit.  Every closure evaluation is within 2e-3 (bf16) / 3e-4 (half) of
+    float64 at the same parameters (test above); 20 un-line-searched L-BFGS iterations then amplify any perturbation
+    (DESIGN.md 'RRR precision'), so the end of the fit is compared loosely here and tightly in the 3-plane golden test."""
     from model.rrr import train_model_main
     td = small_rrr_problem(seed=3, K=40, Kt=12, F=300, N=16)
     _, mse_o, _ = ro.train_model_main(td, 100.0, 3)
-    model, mse = train_model_main(td, l2=100.0, n_comp=3, model_fname="tmp", save=False, planes=1)
-    assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=5e-2)
+    for operand in ("bf16", "f16"):
+        model, mse = train_model_main(td, l2=100.0, n_comp=3, model_fname="tmp", save=False, planes=1, operand=operand)
+        assert model.fmt == (vs.OPERAND_F16 if operand == "f16" else vs.OPERAND_BF16)
+        assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=5e-2)
+
+
+def test_rrr_half_operands_report_overflow(vs, cuda):
+    """A feature that is constant in the train split is z-scored with std 1e-8: its test values explode
+    past the half range.  The half mode must fail loudly; bf16 carries the reference's huge-but-finite numbers."""
+    from model.rrr import RRRGD
+    td = small_rrr_problem(seed=9, K=12, Kt=4, F=40, N=4)
+    Xte = td["e1"]["X"][1]
+    Xte[:, :, 3] = 2.5e8                                                        # what (x - mean) / 1e-8 produces
+    m = RRRGD(td, 3, l2=100.0, planes=1, operand="f16"); m.to(cuda)
+    m.loss_and_grad(td, 0)
+    with pytest.raises(vs.VsError, match="half range"):
+        m.compute_MSE_RRRGD(td, 1)
+    b = RRRGD(td, 3, l2=100.0, planes=1, operand="bf16"); b.to(cuda)
+    b.loss_and_grad(td, 0)
+    assert torch.isfinite(b.compute_MSE_RRRGD(td, 1)["e1"]).all()
 
 
 def test_rrr_multi_session_shared_V(vs, cuda):
@@ -253,7 +274,7 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     Xb = torch.zeros((3, F, d.ldr), dtype=torch.bfloat16, device=cuda)
     xl = torch.empty(K * T, dtype=torch.float32, device=cuda)
     idx = torch.from_numpy(sidx.astype(np.int32)).to(cuda)
-    vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb), vs.ptr(xl), vs.stream()))
+    vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb), vs.ptr(xl), None, vs.stream()))
     # operand rows are TIME-MAJOR (row d = t*K + k, include/vs_b200.h "RRR"): reorder the reference the same way
     ref = np.ascontiguousarray(data["X"][0][:, :, :-1].transpose(1, 0, 2)).reshape(T * K, F)
     got = Xa.double().sum(0)[:, :F].cpu().numpy()
@@ -315,13 +336,15 @@ def test_rrr_full_width_closure_vs_oracle(vs, cuda):
     for k in params:
         params[k] = params[k] + 0.02 * rng.standard_normal(params[k].shape)
     loss_o, g_o, sse_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
-    for planes, rtol in ((1, 3e-3), (3, 1e-5)):
+    # one bf16 plane: every residual carries the ~2^-8 rounding of its 18,260-term contraction and db averages only the
+    # K = 24 trials of this short session, hence 1e-2 on the gradients here (2e-3 on the larger problems above)
+    for planes, rtol in ((1, 1e-2), (3, 1e-5)):
         entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=cuda)
         td = {"s": entry}
         m = RRRGD(td, 3, l2=100.0, planes=planes); m.to(cuda)
         _params_to_model(m, params, cuda)
         loss = float(m.loss_and_grad(td, 0))
-        assert loss == pytest.approx(loss_o, rel=rtol)
+        assert loss == pytest.approx(loss_o, rel=min(rtol, 1e-3))
         for k in g_o:
             got = m.model[k].grad.cpu().numpy()
             assert np.abs(got - g_o[k]).max() <= rtol * np.abs(g_o[k]).max(), (planes, k)
@@ -365,12 +388,75 @@ def test_rrr_full_size_properties(vs, cuda):
     grads = {k: p.grad.clone() for k, p in m.model.items()}
     d = {k: torch.randn(p.shape, generator=g, dtype=torch.float64).to(cuda) for k, p in m.model.items()}
     gd = sum(float((grads[k] * d[k]).sum()) for k in d)
-    eps = 1e-3
-    vals = []
-    for sgn in (+1, -1):
-        with torch.no_grad():
-            for k, p in m.model.items():
-                p.copy_(x0[k] + sgn * eps * d[k])
-        vals.append(float(m.loss_and_grad(td, 0)))
-    fd = (vals[0] - vals[1]) / (2 * eps)
-    assert fd == pytest.approx(gd, rel=2e-4)
+    def central(eps):
+        vals = []
+        for sgn in (+1, -1):
+            with torch.no_grad():
+                for k, p in m.model.items():
+                    p.copy_(x0[k] + sgn * eps * d[k])
+            vals.append(float(m.loss_and_grad(td, 0)))
+        return (vals[0] - vals[1]) / (2 * eps)
+    # the loss is quartic in the parameters: Richardson extrapolation removes the O(eps^2) term of the central difference
+    fd = (4.0 * central(1e-3) - central(2e-3)) / 3.0
+    assert fd == pytest.approx(gd, rel=1e-4)
+
+
+def test_linear_row_parallel_first_layer_emulated_ranks(vs, cuda):
+    """Row-parallel first layer with 3 emulated ranks on one GPU: the partial pre-activations are summed by hand
+    (what the NCCL all-reduce does), then every rank finishes the step locally.  The shards must reassemble the unsharded
+    model: W0 slices, replicated layers identical on every rank, loss equal to the one-GPU fused step."""
+    H = W = 20; N = 7; B = 16; world = 3
+    D = 120 * H * W                                           # 48,000 pixels -> slices of 16,384 / 16,384 / 15,232
+    ref, ropt, rsched = make_linear_model(D, N, cuda, total_steps=40)
+    ranks = []
+    for r in range(world):
+        m, _, _ = make_linear_model(D, N, cuda, total_steps=40)           # same seed -> same full init on every rank
+        lo, hi = m.shard_first_layer(r, world)
+        from optim import FusedAdamW
+        o = FusedAdamW(m.parameters(), lr=ropt.defaults["lr"], weight_decay=ropt.defaults["weight_decay"], eps=ropt.defaults["eps"])
+        s = torch.optim.lr_scheduler.OneCycleLR(optimizer=o, total_steps=40, max_lr=5e-5, pct_start=0.15, div_factor=10)
+        ranks.append((m, o, s, lo, hi))
+    assert [(lo, hi) for *_, lo, hi in ranks] == [(0, 16384), (16384, 32768), (32768, 48000)]
+    for step in range(3):
+        frames, ap = lo_synth(B, (120, 1, H, W), N, seed=30 + step)
+        frames, ap = frames.to(cuda), ap.to(cuda)
+        want = float(ref.fused_train_step(frames, ap, ropt)); rsched.step()
+        # phase 0 on every rank, emulated all-reduce, phase 1 on every rank
+        # run the two phases by hand so the sum can be formed across the emulated ranks
+        import ctypes as C
+        ctx = []
+        for m, o, s, lo, hi in ranks:
+            x = frames.flatten(1)[:, lo:hi].contiguous()
+            bufs = m.__dict__.setdefault("_train_bufs", {}).get((B, str(cuda)))
+            if bufs is None:
+                from model.linear import _MlpBuffers
+                bufs = m.__dict__["_train_bufs"][(B, str(cuda))] = _MlpBuffers(m._layers, B, cuda, True)
+            hyper = o.begin_fused_step()
+            net = m._net(bufs, o.state)
+            ws = m._workspace(net, B, cuda)
+            args = (C.byref(net), vs.ptr(x), None, vs.ptr(ap), B, hyper, vs.ptr(bufs.loss), m.engine, vs.ptr(ws), ws.numel(), vs.stream())
+            vs.check(vs.lib.vs_mlp_train_step_rowpar(*args, 0))
+            ctx.append((args, bufs, net, x, ws))
+        total = sum(c[1].act[0] for c in ctx)
+        losses = []
+        for (args, bufs, net, x, ws), (m, o, s, lo, hi) in zip(ctx, ranks):
+            bufs.act[0].copy_(total)
+            vs.check(vs.lib.vs_mlp_train_step_rowpar(*args, 1))
+            s.step()
+            losses.append(float(bufs.loss[0] / ap.numel()))
+        assert all(l == losses[0] for l in losses)                       # replicas never drift
+        assert losses[0] == pytest.approx(want, rel=1e-6)
+    w_full = ref.encoder.layers[0].weight.detach()
+    for m, o, s, lo, hi in ranks:
+        torch.testing.assert_close(m.encoder.layers[0].weight.detach(), w_full[:, lo:hi], rtol=1e-4, atol=1e-7)
+        for (la, _), (lb, _) in zip(m._layers[1:], ref._layers[1:]):
+            torch.testing.assert_close(la.weight.detach(), lb.weight.detach(), rtol=1e-4, atol=1e-7)
+            torch.testing.assert_close(la.bias.detach(), lb.bias.detach(), rtol=1e-4, atol=1e-7)
+    # and the packaged call (world = 1 shard == the plain fused step)
+    a, ao, _ = make_linear_model(D, N, cuda, total_steps=40)
+    b, bo, _ = make_linear_model(D, N, cuda, total_steps=40)
+    b.shard_first_layer(0, 1)
+    frames, ap = lo_synth(B, (120, 1, H, W), N, seed=77)
+    la = float(a.fused_train_step(frames.to(cuda), ap.to(cuda), ao))
+    lb = float(b.fused_train_step_rowpar(frames.to(cuda), ap.to(cuda), bo))
+    assert lb == pytest.approx(la, rel=1e-7)

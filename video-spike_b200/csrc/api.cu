@@ -85,11 +85,11 @@ extern "C" int vs_device_ok(void) {
 extern "C" int vs_gemm_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                           int64_t ldc, int dtype, int engine, void* stream) {
   VS_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, VS_ERR_INVALID, "vs_gemm_tn: null pointer or empty shape");
-  VS_REQUIRE(dtype == 0 || dtype == 1, VS_ERR_INVALID, "vs_gemm_tn: dtype must be 0 (bf16) or 1 (tf32)");
+  VS_REQUIRE(dtype >= 0 && dtype <= 2, VS_ERR_INVALID, "vs_gemm_tn: dtype must be 0 (bf16), 1 (tf32) or 2 (f16)");
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == VS_ENGINE_SIMT) {
     simt::GemmDesc g;
-    g.A.ptr = A; g.A.type = dtype == 0 ? simt::BF16 : simt::F32; g.A.s_i = lda; g.A.s_k = 1;
+    g.A.ptr = A; g.A.type = dtype == 0 ? simt::BF16 : (dtype == 2 ? simt::F16 : simt::F32); g.A.s_i = lda; g.A.s_k = 1;
     g.B.ptr = B; g.B.type = g.A.type; g.B.s_i = ldb; g.B.s_k = 1;
     g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc;
     return simt::gemm(g, st);
@@ -97,6 +97,6 @@ extern "C" int vs_gemm_tn(const void* A, const void* B, float* C, int64_t M, int
   tc::GemmDesc g;
   g.A.ptr = A; g.A.rows = M; g.A.k = K; g.A.ld = lda;
   g.B.ptr = B; g.B.rows = N; g.B.k = K; g.B.ld = ldb;
-  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.tf32 = dtype == 1;
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.tf32 = dtype == 1; g.f16 = dtype == 2;
   return tc::gemm_tn(g, st);
 }

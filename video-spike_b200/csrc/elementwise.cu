@@ -242,6 +242,19 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
   db[o] = s;
 }
 
+// y[b,o] = act(y[b,o] + bias[o]) in place (row-parallel first layer: the pre-activation arrives all-reduced)
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n, long long out_dim, int relu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = y[i] + (bias ? bias[i % out_dim] : 0.f);
+  y[i] = relu ? fmaxf(v, 0.f) : v;
+}
+int launch_bias_act(float* y, const float* bias, long long batch, long long out_dim, int relu, cudaStream_t st) {
+  const long long n = batch * out_dim;
+  VS_LAUNCH(bias_act_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, y, bias, n, out_dim, relu);
+  return VS_OK;
+}
+
 int launch_relu_mask(const float* dy, const float* y, float* out, long long n, cudaStream_t st) {
   VS_LAUNCH(relu_mask_kernel, (unsigned)ceil_div(n, 256), 256, 0, st, dy, y, out, n);
   return VS_OK;

@@ -26,6 +26,7 @@ struct GemmDesc {
   int* splits_out = nullptr;   // actual factor used
   int BN = 0;                  // 0 = choose
   bool tf32 = false;
+  bool f16 = false;            // 16-bit operands are IEEE half instead of bf16 (ignored with tf32)
   int n_pass = 1;
   int pa[kMaxPass] = {0, 0, 0, 0, 0, 0};
   int pb[kMaxPass] = {0, 0, 0, 0, 0, 0};
@@ -41,7 +42,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream);
 }  // namespace tc
 
 namespace simt {
-enum ElemType { F32 = 0, U8 = 1, BF16 = 2 };
+enum ElemType { F32 = 0, U8 = 1, BF16 = 2, F16 = 3 };
 // generic strided operand: element (i, k) at ptr[i*s_i + k*s_k] (+ plane*plane_stride summed over planes)
 struct Operand {
   const void* ptr = nullptr;

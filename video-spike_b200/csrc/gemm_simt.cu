@@ -2,6 +2,7 @@
 // of the `Linear` MLP (src/model/linear.py:29-32,47-53 -- 82 k weights, launch-bound, not worth a
 // tensor-core pipeline), every backward-data / backward-weight product of those layers, and it is
 // the on-device cross-check for the tcgen05 engine (tests compare the two bit patterns' sums).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "gemm.h"
 
@@ -22,8 +23,13 @@ __device__ __forceinline__ float load_elem(const DevOperand& o, long long i, lon
   const long long off = i * o.s_i + k * o.s_k;
   if (o.type == F32) return reinterpret_cast<const float*>(o.ptr)[off];
   if (o.type == U8) return (float)reinterpret_cast<const uint8_t*>(o.ptr)[off];
-  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(o.ptr);
   float v = 0.f;
+  if (o.type == F16) {
+    const __half* p = reinterpret_cast<const __half*>(o.ptr);
+    for (int pl = 0; pl < o.planes; ++pl) v += __half2float(p[off + pl * o.plane_stride]);
+    return v;
+  }
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(o.ptr);
   for (int pl = 0; pl < o.planes; ++pl) v += __bfloat162float(p[off + pl * o.plane_stride]);
   return v;
 }

@@ -34,6 +34,7 @@ struct KParams {
   int pa[kMaxPass], pb[kMaxPass];
   int stages;
   int tmem_cols;
+  int f16;          // 16-bit operand format: 0 = bf16, 1 = IEEE half
   float* C;
   long long ldc, split_stride;
   // tail-wave balancing: CTAs with blockIdx.x >= tail_cta0 work on tile tail_cta0 + u / tail_splits,
@@ -121,9 +122,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 // UMMA instruction descriptor: D fp32 (c_format 1 @ [4,6)), A/B format @ [7,10)/[10,13)
-// (bf16 = 1, tf32 = 2), both K-major (bits 15,16 = 0), N>>3 @ [17,23), M>>4 @ [24,29).
-__device__ __forceinline__ uint32_t make_idesc(bool tf32, int n) {
-  uint32_t fmt = tf32 ? 2u : 1u;
+// (f16 = 0, bf16 = 1, tf32 = 2), both K-major (bits 15,16 = 0), N>>3 @ [17,23), M>>4 @ [24,29).
+__device__ __forceinline__ uint32_t make_idesc(bool tf32, bool f16, int n) {
+  uint32_t fmt = tf32 ? 2u : (f16 ? 0u : 1u);
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
@@ -203,8 +204,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const int n0 = p.BN > 256 ? 256 : p.BN;      // first UMMA N chunk
       const int n1 = p.BN - n0;                    // second chunk (0 or a multiple of 16)
-      const uint32_t idesc0 = make_idesc(kTF32, n0);
-      const uint32_t idesc1 = make_idesc(kTF32, n1 > 0 ? n1 : 16);
+      const uint32_t idesc0 = make_idesc(kTF32, p.f16 != 0, n0);
+      const uint32_t idesc1 = make_idesc(kTF32, p.f16 != 0, n1 > 0 ? n1 : 16);
       for (int it = 0; it < iters; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -326,7 +327,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 3-D map over a (planes, rows, K) K-major operand; box = (128 B of K, box_rows, 1)
-static int make_map(CUtensorMap* m, const Operand& op, bool tf32, int box_rows) {
+static int make_map(CUtensorMap* m, const Operand& op, bool tf32, bool f16, int box_rows) {
   EncodeTiledFn enc = get_encode();
   VS_REQUIRE(enc != nullptr, VS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int esz = tf32 ? 4 : 2;
@@ -338,7 +339,7 @@ static int make_map(CUtensorMap* m, const Operand& op, bool tf32, int box_rows) 
   cuuint64_t strides[2] = {(cuuint64_t)op.ld * esz, (cuuint64_t)(planes > 1 ? op.plane_stride : op.ld * op.rows) * esz};
   cuuint32_t box[3] = {(cuuint32_t)(tf32 ? 32 : 64), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr),
+  CUresult r = enc(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 3, const_cast<void*>(op.ptr),
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VS_REQUIRE(r == CUDA_SUCCESS, VS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rows=%lld k=%lld ld=%lld box_rows=%d",
@@ -393,13 +394,14 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   int tcols = 32;
   while (tcols < BN) tcols <<= 1;
   p.tmem_cols = tcols;
+  p.f16 = g.f16 ? 1 : 0;
   p.C = g.C; p.ldc = g.ldc; p.split_stride = g.split_stride;
   VS_REQUIRE(splits == 1 || g.split_stride >= g.M * g.ldc, VS_ERR_INVALID, "split-K needs split_stride >= M*ldc");
 
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, g.A, g.tf32, BM);
+  int rc = make_map(&tmA, g.A, g.tf32, g.f16, BM);
   if (rc) return rc;
-  rc = make_map(&tmB, g.B, g.tf32, p.tb_rows);
+  rc = make_map(&tmB, g.B, g.tf32, g.f16, p.tb_rows);
   if (rc) return rc;
 
   const size_t smem = (size_t)CTRL_BYTES + 1024 + (size_t)stages * stage_bytes;

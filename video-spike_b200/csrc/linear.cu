@@ -204,16 +204,67 @@ extern "C" int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const
   return rc;
 }
 
+namespace vs {
+int launch_bias_act(float* y, const float* bias, long long batch, long long out_dim, int relu, cudaStream_t st);
+}
+
+// forward of layers [l0, L): layer l reads act[l-1] (or the frames for l == 0)
+static int mlp_forward_from(const vs_mlp* net, int l0, const uint8_t* frames_u8, const float* x_f32, int64_t batch, int engine,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  for (int l = l0; l < net->n_layers; ++l) {
+    const float* xin = l == 0 ? x_f32 : net->act[l - 1];
+    const uint8_t* xu = l == 0 && !x_f32 ? frames_u8 : nullptr;
+    const int eng = net->dims[l] >= kBigK ? engine : VS_ENGINE_AUTO;
+    int rc = vs_linear_fwd(xin, xu, net->W[l], net->b[l], net->act[l], batch, net->dims[l], net->dims[l + 1], net->relu[l], eng,
+                           workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return VS_OK;
+}
+
+static int mlp_backward_update(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target, int64_t batch,
+                               vs_adamw_hyper h, double* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int vs_mlp_train_step(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target,
                                  int64_t batch, vs_adamw_hyper h, double* loss_sum, int engine, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   int rc = check_net(net, batch, true);
   if (rc) return rc;
   VS_REQUIRE((frames_u8 || x_f32) && target && loss_sum, VS_ERR_INVALID, "vs_mlp_train_step: null pointer");
-  const int L = net->n_layers;
   // forward (M1-M3)
   rc = vs_mlp_forward(net, frames_u8, x_f32, nullptr, batch, nullptr, engine, workspace, workspace_bytes, stream);
   if (rc) return rc;
+  return mlp_backward_update(net, frames_u8, x_f32, target, batch, h, loss_sum, workspace, workspace_bytes, stream);
+}
+
+// Row-parallel first layer: this rank owns the pixel slice dims[0] of every frame and the matching columns
+// of W0 (+ its Adam moments); everything after the first pre-activation is replicated.
+//   phase 0: act[0] = frames_slice . W0_slice^T            (no bias, no ReLU)  -> caller all-reduces act[0] (batch x dims[1] fp32)
+//   phase 1: act[0] = act(act[0] + b0); layers 1..L-1, loss, backward, AdamW on every local parameter
+extern "C" int vs_mlp_train_step_rowpar(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target,
+                                        int64_t batch, vs_adamw_hyper h, double* loss_sum, int engine, void* workspace,
+                                        size_t workspace_bytes, void* stream, int phase) {
+  int rc = check_net(net, batch, true);
+  if (rc) return rc;
+  VS_REQUIRE(frames_u8 || x_f32, VS_ERR_INVALID, "vs_mlp_train_step_rowpar: no input");
+  VS_REQUIRE(phase == 0 || phase == 1, VS_ERR_INVALID, "vs_mlp_train_step_rowpar: phase must be 0 or 1");
+  if (phase == 0) {
+    const int eng = net->dims[0] >= kBigK ? engine : VS_ENGINE_AUTO;
+    return vs_linear_fwd(x_f32, x_f32 ? nullptr : frames_u8, net->W[0], nullptr, net->act[0], batch, net->dims[0], net->dims[1], 0, eng,
+                         workspace, workspace_bytes, stream);
+  }
+  VS_REQUIRE(target && loss_sum, VS_ERR_INVALID, "vs_mlp_train_step_rowpar: null pointer");
+  rc = launch_bias_act(net->act[0], net->b[0], batch, net->dims[1], net->relu[0], (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = mlp_forward_from(net, 1, frames_u8, x_f32, batch, engine, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return mlp_backward_update(net, frames_u8, x_f32, target, batch, h, loss_sum, workspace, workspace_bytes, stream);
+}
+
+static int mlp_backward_update(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f32, const float* target, int64_t batch,
+                               vs_adamw_hyper h, double* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  const int L = net->n_layers;
   // loss + dlogits (C1)
   rc = vs_poisson_nll(net->act[L - 1], target, loss_sum, net->gact[L - 1], batch * net->dims[L], stream);
   if (rc) return rc;

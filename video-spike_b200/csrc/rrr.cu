@@ -9,6 +9,8 @@
 // Operand rows are TIME-MAJOR: row d = t*K + k, so the K trials of one time bin are contiguous and every
 // reduction over trials (db, SSE, dV) is a reduction over adjacent rows done inside the epilogue block.
 // All reductions are ordered (no floating-point atomics): results are bit-reproducible run to run.
+#include <stdlib.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "gemm.h"
 
@@ -17,22 +19,27 @@ namespace rrr {
 
 constexpr int kMaxR = 8;
 
-__device__ __forceinline__ uint16_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
-__device__ __forceinline__ float bf16_val(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+// 16-bit operand encodings (vs_rrr_dims.fmt): bf16 or IEEE half, round to nearest even
+__device__ __forceinline__ uint16_t enc16(float v, int fmt) {
+  return fmt == VS_OPERAND_F16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float dec16(uint16_t b, int fmt) {
+  return fmt == VS_OPERAND_F16 ? __half2float(__ushort_as_half(b)) : __uint_as_float((uint32_t)b << 16);
+}
 
-// split v into `planes` bf16 residual planes: v ~= p0 + p1 + p2
-__device__ __forceinline__ void split_planes(double v, int planes, uint16_t out[3]) {
+// split v into `planes` 16-bit residual planes: v ~= p0 + p1 + p2
+__device__ __forceinline__ void split_planes(double v, int planes, int fmt, uint16_t out[3]) {
   if (planes == 1) {  // fast path: one rounding, no fp64 arithmetic
-    out[0] = bf16_bits((float)v); out[1] = 0; out[2] = 0;
+    out[0] = enc16((float)v, fmt); out[1] = 0; out[2] = 0;
     return;
   }
   double rem = v;
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
     if (p < planes) {
-      const uint16_t b = bf16_bits((float)rem);
+      const uint16_t b = enc16((float)rem, fmt);
       out[p] = b;
-      rem -= (double)bf16_val(b);
+      rem -= (double)dec16(b, fmt);
     } else {
       out[p] = 0;
     }
@@ -47,9 +54,9 @@ template <bool kFromU8>
 __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X, const uint8_t* __restrict__ frames,
                                                    const int32_t* __restrict__ sorted_idx, const double* __restrict__ mean,
                                                    const double* __restrict__ sd, long long Tf, long long k_begin, long long k_end,
-                                                   long long K, long long T, long long C1, int planes, long long ldc,
+                                                   long long K, long long T, long long C1, int planes, int fmt, long long ldc,
                                                    long long ldr, uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xb,
-                                                   float* __restrict__ xl) {
+                                                   float* __restrict__ xl, int* __restrict__ overflow) {
   __shared__ uint16_t tile[3][32][33];
   const long long kblocks = (k_end - k_begin + 31) / 32;
   const long long t = blockIdx.x / kblocks, k0 = k_begin + (blockIdx.x % kblocks) * 32;
@@ -69,7 +76,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X,
       } else {
         v = X[((k - k_begin) * T + t) * (C1 + 1) + c];   // X points at trial k_begin
       }
-      split_planes(v, planes, pl);
+      if (fmt == VS_OPERAND_F16 && overflow && !(fabs(v) <= 65504.0)) atomicOr(overflow, 1);
+      split_planes(v, planes, fmt, pl);
       const long long d = t * K + k;
       for (int p = 0; p < planes; ++p) Xa[p * pa + d * ldc + c] = pl[p];
     }
@@ -155,7 +163,7 @@ __global__ void colstats_f32_kernel(const float* __restrict__ x, long long K, lo
 constexpr int kPrepC = 4;
 template <int RMAX>
 __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ U, long long N, long long Npad, long long C1,
-                                                     int r, int planes, long long ldc, uint16_t* __restrict__ Ub,
+                                                     int r, int planes, int fmt, long long ldc, uint16_t* __restrict__ Ub,
                                                      double* __restrict__ Gp) {
   __shared__ double red[8][RMAX * RMAX];
   const long long n = blockIdx.y;
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
     for (int j = 0; j < RMAX; ++j) {
       if (j >= r) break;
       uint16_t pl[3];
-      split_planes(u[j], planes, pl);
+      split_planes(u[j], planes, fmt, pl);
       for (int p = 0; p < planes; ++p) Ub[p * pu + ((long long)j * Npad + n) * ldc + c] = pl[p];
     }
     if (Gp) {
@@ -241,7 +249,7 @@ template <bool kPredict, int RMAX>
 __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, int splits, long long split_stride,
                                                     const float* __restrict__ y, const float* __restrict__ xl,
                                                     const double* __restrict__ V, const double* __restrict__ b, long long K,
-                                                    long long T, long long N, long long Npad, int r, int planes, long long ldr,
+                                                    long long T, long long N, long long Npad, int r, int planes, int fmt, long long ldr,
                                                     uint16_t* __restrict__ RV, float* __restrict__ sse_part,
                                                     float* __restrict__ db_part, float* __restrict__ pv_part,
                                                     double* __restrict__ yhat) {
@@ -335,11 +343,11 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
         if (j >= r) continue;
         uint16_t pl0[3], pl1[3];
         if (planes == 1) {   // plain bf16 operand: no fp64 on this path (the vector fp64 pipe is narrow)
-          pl0[0] = bf16_bits(vt[j] * r0v); pl1[0] = bf16_bits(vt[j] * r1v);
+          pl0[0] = enc16(vt[j] * r0v, fmt); pl1[0] = enc16(vt[j] * r1v, fmt);
           pl0[1] = pl0[2] = pl1[1] = pl1[2] = 0;
         } else {
-          split_planes((double)(vt[j] * r0v), planes, pl0);
-          split_planes((double)(vt[j] * r1v), planes, pl1);
+          split_planes((double)(vt[j] * r0v), planes, fmt, pl0);
+          split_planes((double)(vt[j] * r1v), planes, fmt, pl1);
         }
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -515,7 +523,14 @@ struct Ws {
 // ~2^-24 the 3-plane mode is after: there each TMEM accumulation run is limited to 16 k-blocks and
 // the partial tiles are summed in fp64 by the epilogue kernels.
 static int hp_splits(long long k_elems, int planes) {
-  if (planes < 2) return 1;
+  // experiment hook: VS_RRR_RUN=<k-blocks per TMEM accumulation run> forces split-K in the single-plane mode too
+  static int run1 = -1;
+  if (run1 < 0) { const char* e = getenv("VS_RRR_RUN"); run1 = e ? atoi(e) : 0; }
+  if (planes < 2) {
+    if (run1 <= 0) return 1;
+    long long s1 = ceil_div(ceil_div(k_elems, 64), run1);
+    return (int)(s1 < 1 ? 1 : (s1 > 256 ? 256 : s1));
+  }
   long long s = ceil_div(ceil_div(k_elems, 64), 16);
   return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));
 }
@@ -552,6 +567,7 @@ static int check_dims(const vs_rrr_dims& d) {
   VS_REQUIRE(d.K > 0 && d.T > 0 && d.C1 > 0 && d.N > 0 && d.r > 0, VS_ERR_INVALID, "rrr: empty dimension");
   VS_REQUIRE(d.r <= kMaxR, VS_ERR_UNSUPPORTED, "rrr: rank %lld > %d", (long long)d.r, kMaxR);
   VS_REQUIRE(d.planes >= 1 && d.planes <= 3, VS_ERR_INVALID, "rrr: planes must be 1..3");
+  VS_REQUIRE(d.fmt == VS_OPERAND_BF16 || d.fmt == VS_OPERAND_F16, VS_ERR_INVALID, "rrr: fmt must be VS_OPERAND_BF16 or VS_OPERAND_F16");
   VS_REQUIRE(d.ldc >= d.C1 && d.ldc % 8 == 0 && d.ldr >= d.K * d.T && d.ldr % 8 == 0, VS_ERR_INVALID, "rrr: bad pitches");
   VS_REQUIRE(d.K * d.T < (1ll << 31) && d.C1 < (1ll << 31), VS_ERR_UNSUPPORTED, "rrr: dimension exceeds 2^31");
   return VS_OK;
@@ -574,8 +590,8 @@ static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int eng
   const long long KT = d.K * d.T;
   if (engine == VS_ENGINE_SIMT) {
     simt::GemmDesc g;
-    g.A.ptr = Xa; g.A.type = simt::BF16; g.A.s_i = d.ldc; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = KT * d.ldc;
-    g.B.ptr = w.Ub; g.B.type = simt::BF16; g.B.s_i = d.ldc; g.B.s_k = 1; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldc;
+    g.A.ptr = Xa; g.A.type = d.fmt == VS_OPERAND_F16 ? simt::F16 : simt::BF16; g.A.s_i = d.ldc; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = KT * d.ldc;
+    g.B.ptr = w.Ub; g.B.type = d.fmt == VS_OPERAND_F16 ? simt::F16 : simt::BF16; g.B.s_i = d.ldc; g.B.s_k = 1; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldc;
     g.M = KT; g.N = w.ldz; g.K = d.C1; g.C = w.Z; g.ldc = w.ldz;
     return simt::gemm(g, st);
   }
@@ -585,6 +601,7 @@ static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int eng
   g.M = KT; g.N = w.ldz; g.K = d.C1; g.C = w.Z; g.ldc = w.ldz;
   g.splits = w.splits_f; g.split_stride = KT * w.ldz; g.splits_out = splits_used;
   g.balance_ws = w.bal;
+  g.f16 = d.fmt == VS_OPERAND_F16;
   set_passes(g, d.planes);
   return tc::gemm_tn(g, st);
 }
@@ -595,8 +612,8 @@ static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int eng
   const long long KT = d.K * d.T;
   if (engine == VS_ENGINE_SIMT) {
     simt::GemmDesc g;
-    g.A.ptr = Xb; g.A.type = simt::BF16; g.A.s_i = d.ldr; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = d.C1 * d.ldr;
-    g.B.ptr = w.RV; g.B.type = simt::BF16; g.B.s_i = d.ldr; g.B.s_k = 1; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldr;
+    g.A.ptr = Xb; g.A.type = d.fmt == VS_OPERAND_F16 ? simt::F16 : simt::BF16; g.A.s_i = d.ldr; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = d.C1 * d.ldr;
+    g.B.ptr = w.RV; g.B.type = d.fmt == VS_OPERAND_F16 ? simt::F16 : simt::BF16; g.B.s_i = d.ldr; g.B.s_k = 1; g.B.planes = d.planes; g.B.plane_stride = w.ldz * d.ldr;
     g.M = d.C1; g.N = w.ldz; g.K = KT; g.C = w.Gacc; g.ldc = w.ldz;
     return simt::gemm(g, st);
   }
@@ -606,6 +623,7 @@ static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int eng
   g.M = d.C1; g.N = w.ldz; g.K = KT; g.C = w.Gacc; g.ldc = w.ldz;
   g.splits = w.splits_b; g.split_stride = d.C1 * w.ldz; g.splits_out = splits_used;
   g.balance_ws = w.bal;
+  g.f16 = d.fmt == VS_OPERAND_F16;
   set_passes(g, d.planes);
   return tc::gemm_tn(g, st);
 }
@@ -625,7 +643,7 @@ extern "C" size_t vs_rrr_workspace(vs_rrr_dims d) {
 }
 
 extern "C" int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb,
-                           float* xl, void* stream) {
+                           float* xl, int32_t* overflow_flag, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   VS_REQUIRE(X_trials && Xa && Xb && xl, VS_ERR_INVALID, "vs_rrr_pack: null pointer");
@@ -633,8 +651,8 @@ extern "C" int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rr
   dim3 grid((unsigned)(ceil_div(nk, 32) * d.T), (unsigned)ceil_div(d.C1, 32));
   VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack: too many columns");
   VS_LAUNCH((pack_kernel<false>), grid, 256, 0, stream, X_trials, nullptr, nullptr, nullptr, nullptr, 0ll, (long long)k0,
-            (long long)(k0 + nk), (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb,
-            xl);
+            (long long)(k0 + nk), (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (int)d.fmt, (long long)d.ldc, (long long)d.ldr,
+            Xa, Xb, xl, overflow_flag);
   return VS_OK;
 }
 
@@ -645,14 +663,16 @@ extern "C" int vs_rrr_colstats(const uint8_t* frames, int64_t K, int64_t cols, d
 }
 
 extern "C" int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
-                              const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb, float* xl, void* stream) {
+                              const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xb, float* xl,
+                              int32_t* overflow_flag, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   VS_REQUIRE(frames && sorted_idx && mean && std_clipped && Xa && Xb && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8: bad arguments");
   dim3 grid((unsigned)(ceil_div(d.K, 32) * d.T), (unsigned)ceil_div(d.C1, 32));
   VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8: too many columns");
   VS_LAUNCH((pack_kernel<true>), grid, 256, 0, stream, nullptr, frames, sorted_idx, mean, std_clipped, (long long)Tf, 0ll,
-            (long long)d.K, (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl);
+            (long long)d.K, (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (int)d.fmt, (long long)d.ldc, (long long)d.ldr, Xa, Xb,
+            xl, overflow_flag);
   return VS_OK;
 }
 
@@ -674,9 +694,9 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   // stage 0: U planes + Gram partials, then G and W = V V^T
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
   if (r <= 4) {
-    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
+    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp);
   } else {
-    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (long long)d.ldc, w.Ub, w.Gp);
+    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp);
   }
   VS_LAUNCH(small_mats_kernel, r * r + 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   // stage 1: Z
@@ -687,10 +707,10 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (r <= 4) {
     VS_LAUNCH((epi_f_kernel<false, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
+              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
   } else {
     VS_LAUNCH((epi_f_kernel<false, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, r, d.planes, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
+              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
   }
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
   VS_LAUNCH(reduce_part_kernel, g2, 128, 0, st, w.sse_part, w.db_part, b, w.KB, (long long)d.T, (long long)d.N, l2, db, w.sse_tn);
@@ -722,10 +742,10 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   const long long KT = d.K * d.T;
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
   if (d.r <= 4) {
-    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
+    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
               (double*)nullptr);
   } else {
-    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (long long)d.ldc, w.Ub,
+    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
               (double*)nullptr);
   }
   int sf = 1;
@@ -734,10 +754,10 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (d.r <= 4) {
     VS_LAUNCH((epi_f_kernel<true, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
   } else {
     VS_LAUNCH((epi_f_kernel<true, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
   }
   return VS_OK;
 }

@@ -210,6 +210,57 @@ class Linear(torch.nn.Module):
             return _MlpFunction.apply(self, xin, *params)
         return self._forward_impl(x)[0]
 
+    # ---- row-parallel first layer ---------------------------------------------------------------
+    def shard_first_layer(self, rank, world):
+        """Keep only this rank's pixel slice of the first layer: W0[:, lo:hi] (the Adam moments follow when the
+        optimizer is built afterwards).  Slices are multiples of 1024 pixels so every rank's update kernel sees whole
+        column strips.  Everything after the first pre-activation stays replicated.  Returns (lo, hi)."""
+        lin = self.encoder.layers[0]
+        D = lin.in_features
+        chunk = -(-D // (world * 1024)) * 1024
+        lo, hi = min(D, rank * chunk), min(D, (rank + 1) * chunk)
+        if hi <= lo:
+            raise vs.VsError(f"rank {rank} of {world} gets no pixels of a {D}-pixel frame")
+        with torch.no_grad():
+            w = lin.weight[:, lo:hi].clone().contiguous()
+        lin.weight = torch.nn.Parameter(w)
+        lin.in_features = hi - lo
+        self.__dict__["_shard"] = {"lo": lo, "hi": hi, "D": D, "rank": rank, "world": world}
+        for k in ("_train_bufs", "_layers_cache", "_ws"):
+            self.__dict__.pop(k, None)
+        return lo, hi
+
+    def fused_train_step_rowpar(self, x, target, optimizer, group=None, allreduce=None):
+        """One training step with the first layer row-parallel: phase 0 (local partial pre-activation), ONE
+        all-reduce(sum) of the (B, 256) fp32 pre-activation, phase 1 (everything else, all local).  `x` is this
+        rank's pixel slice (B, hi-lo) or the whole frames (B, D) (sliced here).  `allreduce(tensor)` overrides
+        torch.distributed.all_reduce (used by the single-GPU emulation test)."""
+        sh = self.__dict__.get("_shard")
+        if sh is None:
+            raise vs.VsError("call shard_first_layer(rank, world) first")
+        x = x.flatten(1)
+        if x.shape[1] == sh["D"] and sh["D"] != sh["hi"] - sh["lo"]:
+            x = x[:, sh["lo"]:sh["hi"]]
+        x_f32, x_u8 = self._split_input(x)
+        batch, device = x.shape[0], x.device
+        cache = self.__dict__.setdefault("_train_bufs", {})
+        bufs = cache.get((batch, str(device)))
+        if bufs is None:
+            bufs = cache[(batch, str(device))] = _MlpBuffers(self._layers, batch, device, True)
+        hyper = optimizer.begin_fused_step()
+        net = self._net(bufs, optimizer.state)
+        ws = self._workspace(net, batch, device)
+        target = target.contiguous().float()
+        args = (C.byref(net), vs.ptr(x_u8), vs.ptr(x_f32), vs.ptr(target), batch, hyper, vs.ptr(bufs.loss), self.engine, vs.ptr(ws),
+                ws.numel(), vs.stream())
+        vs.check(vs.lib.vs_mlp_train_step_rowpar(*args, 0))
+        if allreduce is not None:
+            allreduce(bufs.act[0])
+        elif sh["world"] > 1:
+            torch.distributed.all_reduce(bufs.act[0], group=group)
+        vs.check(vs.lib.vs_mlp_train_step_rowpar(*args, 1))
+        return bufs.loss[0] / float(target.numel())
+
     def fused_train_step(self, x, target, optimizer):
         """One whole step of src/trainer/base.py:147-154 (forward, Poisson NLL, backward, AdamW on
         every parameter) as ONE C-ABI call (vs_mlp_train_step).  Returns the mean loss as a

@@ -29,6 +29,21 @@ import vsb200 as vs
 from optim import FusedLBFGS
 
 
+def operand_format(planes, operand=None):
+    """16-bit format of the tensor-core operand planes.  "bf16" (default; fp32 range, 8 significant bits) or "f16"
+    (IEEE half: 11 significant bits at the same tcgen05 rate, so every closure evaluation is ~8x closer to float64, but
+    |x| <= 65504 -- the exploding test features of SURVEY A18 overflow it, which the pack calls report loudly).
+    Select with `operand=` or VS_RRR_OPERAND."""
+    operand = operand or os.environ.get("VS_RRR_OPERAND") or "bf16"
+    if operand not in ("bf16", "f16"):
+        raise ValueError("operand must be 'bf16' or 'f16'")
+    return vs.OPERAND_F16 if operand == "f16" else vs.OPERAND_BF16
+
+
+def _op_dtype(fmt):
+    return torch.float16 if fmt == vs.OPERAND_F16 else torch.bfloat16
+
+
 def np2tensor(v):
     return v if isinstance(v, torch.Tensor) else torch.from_numpy(v)
 
@@ -53,33 +68,44 @@ class _PackedSplit:
 
     CHUNK_BYTES = 1 << 30   # fp64 staging buffer bound for the host->device upload
 
-    def __init__(self, X, y, r, planes, device):
+    def __init__(self, X, y, r, planes, device, fmt=0):
         X = np.ascontiguousarray(X)
         K, T, C = X.shape
         N = y.shape[2]
         self.K, self.T, self.C1, self.N = K, T, C - 1, N
-        d = vs.RrrDims(K, T, C - 1, N, r, planes, vs.lib.vs_rrr_ldc(C - 1), vs.lib.vs_rrr_ldr(K, T))
+        d = vs.RrrDims(K, T, C - 1, N, r, planes, vs.lib.vs_rrr_ldc(C - 1), vs.lib.vs_rrr_ldr(K, T), fmt)
         self.dims = d
         KT = K * T
-        self.Xa = torch.empty((planes, KT, d.ldc), dtype=torch.bfloat16, device=device)
-        self.Xb = torch.empty((planes, C - 1, d.ldr), dtype=torch.bfloat16, device=device)
+        self.Xa = torch.empty((planes, KT, d.ldc), dtype=_op_dtype(fmt), device=device)
+        self.Xb = torch.empty((planes, C - 1, d.ldr), dtype=_op_dtype(fmt), device=device)
         self.xl = torch.empty(KT, dtype=torch.float32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         trials_per_chunk = max(1, min(K, self.CHUNK_BYTES // (8 * C * T)))
         st = vs.stream()
         for k0 in range(0, K, trials_per_chunk):
             k1 = min(K, k0 + trials_per_chunk)
             chunk = torch.from_numpy(X[k0:k1]).to(device=device, dtype=torch.float64).contiguous()
-            vs.check(vs.lib.vs_rrr_pack(vs.ptr(chunk), k0, k1 - k0, d, vs.ptr(self.Xa), vs.ptr(self.Xb), vs.ptr(self.xl), st))
+            vs.check(vs.lib.vs_rrr_pack(vs.ptr(chunk), k0, k1 - k0, d, vs.ptr(self.Xa), vs.ptr(self.Xb), vs.ptr(self.xl),
+                                        vs.ptr(self.overflow), st))
             del chunk
         self.y = torch.from_numpy(np.ascontiguousarray(y)).to(device=device, dtype=torch.float32).contiguous()
 
     @classmethod
-    def from_device(cls, dims, Xa, Xb, xl, y):
+    def from_device(cls, dims, Xa, Xb, xl, y, overflow=None):
         """Wrap operands that were produced on the device (vs_rrr_pack_u8 path)."""
         self = cls.__new__(cls)
         self.K, self.T, self.C1, self.N = dims.K, dims.T, dims.C1, dims.N
-        self.dims, self.Xa, self.Xb, self.xl, self.y = dims, Xa, Xb, xl, y
+        self.dims, self.Xa, self.Xb, self.xl, self.y, self.overflow = dims, Xa, Xb, xl, y, overflow
         return self
+
+    def check_range(self):
+        """Half-precision operands: fail loudly if a value left the half range while packing (checked once, lazily,
+        so the pack stays asynchronous)."""
+        if self.overflow is not None:
+            flag, self.overflow = int(self.overflow.item()), None
+            if flag:
+                raise vs.VsError("RRR operands exceed the IEEE-half range (e.g. features that are constant in the train split, "
+                                 "SURVEY A18): use operand='bf16' / VS_RRR_OPERAND=bf16")
 
     @property
     def shape(self):
@@ -88,7 +114,7 @@ class _PackedSplit:
 
 
 class RRRGD():
-    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None):
+    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None, operand=None):
         """`init_plan` (session-sharded joint model, parallel.py): [(eid, N, ncoef, T)] of ALL sessions of the joint
         model in the reference's iteration order.  The init stream is drawn for every session in that order so that
         this rank's U_s and the shared V are bit-identical to the single-process joint model; sessions that are not
@@ -98,6 +124,7 @@ class RRRGD():
         self.withbias = True
         self.planes = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
         self.engine = int(engine if engine is not None else os.environ.get("VS_ENGINE", str(vs.ENGINE_AUTO)))
+        self.fmt = operand_format(self.planes, operand)
 
         # rrr.py:35 seeds numpy's GLOBAL legacy stream with 0 regardless of the user's seed and draws
         # U then V per session from it.  The same stream -- bit for bit -- comes from the multi-threaded host
@@ -198,7 +225,7 @@ class RRRGD():
         key = (eid, k, id(X))
         hit = self._packed.get(key)
         if hit is None:
-            hit = _PackedSplit(X, data[eid]['y'][k], self.n_comp, self.planes, self._device())
+            hit = _PackedSplit(X, data[eid]['y'][k], self.n_comp, self.planes, self._device(), self.fmt)
             self._packed[key] = hit
         return hit
 
@@ -212,6 +239,8 @@ class RRRGD():
     def _closure_eval(self, data, eid, k, want_grad, dV=None):
         """loss (0-dim), sse_n (N,) and -- if want_grad -- dU, db written into .grad, dV accumulated."""
         sp = self._split(data, eid, k)
+        if sp.overflow is not None and self.n_closure_evals > 0:
+            sp.check_range()
         U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
         dev = V.device
         loss = torch.empty(1, dtype=torch.float64, device=dev)
@@ -308,9 +337,9 @@ def train_model(model, train_data, optimizer, model_fname, save=True):
     return model, {"mses_val": mses_val, "mse_val_mean": best_loss}
 
 
-def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None, engine=None):
+def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None, engine=None, operand=None):
     """rrr.py:192-202."""
-    area_model = RRRGD(train_data, n_comp, l2=l2, planes=planes, engine=engine)
+    area_model = RRRGD(train_data, n_comp, l2=l2, planes=planes, engine=engine, operand=operand)
     device = get_device()
     area_model.to(device)
     print(f"training on device: {device}")
@@ -323,7 +352,7 @@ def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None
 # R0 on the device: the preprocessing of src/train_rrr.py:108-171 for the video modalities, from raw
 # uint8 frames, without ever forming the float64 (K, T, C) matrix on the host.
 def pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=1,
-                             smooth_w=2.0, device=None):
+                             smooth_w=2.0, device=None, operand=None):
     """frames_*: uint8 (K, Tf, ...) torch tensors (pinned host or CUDA); counts_*: (K, T, N) spike counts.
     Mirrors train_rrr.py: y smoothed with gaussian_filter1d(sigma=smooth_w, axis=1); X and y z-scored with
     the TRAIN statistics (std clipped at 1e-8); ones column; frames `sorted_idx` selected AFTER the z-score.
@@ -333,6 +362,7 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
     st = vs.stream()
     idx = torch.as_tensor(np.asarray(sorted_idx), dtype=torch.int32).to(device)
     T = int(idx.numel())
+    fmt = operand_format(planes, operand)
     splits, ys = [], []
     mean = sd = my = sy = None
     for which, (fr, cnt) in enumerate(((frames_train, counts_train), (frames_test, counts_test))):
@@ -350,15 +380,16 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
             sy = torch.empty_like(my)
             vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
             del sm
-        d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T))
-        Xa = torch.empty((planes, K * T, d.ldc), dtype=torch.bfloat16, device=device)
-        Xb = torch.empty((planes, F, d.ldr), dtype=torch.bfloat16, device=device)
+        d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T), fmt)
+        Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)
+        Xb = torch.empty((planes, F, d.ldr), dtype=_op_dtype(fmt), device=device)
         xl = torch.empty(K * T, dtype=torch.float32, device=device)
+        overflow = torch.zeros(1, dtype=torch.int32, device=device)
         vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
-                                       vs.ptr(xl), st))
+                                       vs.ptr(xl), vs.ptr(overflow), st))
         y = torch.empty_like(cnt)
         vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
-        splits.append(_PackedSplit.from_device(d, Xa, Xb, xl, y))
+        splits.append(_PackedSplit.from_device(d, Xa, Xb, xl, y, overflow))
         ys.append(y)
         del fr
     Tf_F = mean.numel()
@@ -367,10 +398,11 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
 
 
 def train_model_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, l2=100.0, n_comp=3,
-                            eid="session", planes=None, engine=None, model_fname="tmp", save=False):
+                            eid="session", planes=None, engine=None, model_fname="tmp", save=False, operand=None):
     """R0 + train_model_main (rrr.py:192-202) in one call, from raw uint8 frames."""
     pl = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
-    entry = pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=pl)
+    entry = pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=pl,
+                                     operand=operand)
     train_data = {eid: entry}
-    model, mse_val = train_model_main(train_data, l2, n_comp, model_fname, save=save, planes=pl, engine=engine)
+    model, mse_val = train_model_main(train_data, l2, n_comp, model_fname, save=save, planes=pl, engine=engine, operand=operand)
     return model, mse_val, train_data

@@ -45,3 +45,27 @@ def bits_per_spike(rates, spikes):
     null_rates = np.tile(np.nanmean(spikes, axis=lead_axes, keepdims=True), spikes.shape[:-1] + (1,))
     nll_null = neg_log_likelihood(null_rates, spikes, zero_warning=False)
     return (nll_null - nll_model) / np.nansum(spikes) / np.log(2)
+
+
+# ---- device versions: same definitions, no copy of the predictions to the host -----------------
+def device_bits_per_spike(rates_KTN, spikes_KTN):
+    """Per-neuron bits per spike, float64 (N,) CUDA tensor: bits_per_spike(rates[:, :, [n]], spikes[:, :, [n]]) of
+    metric_utils.py:78-102 for every n at once (vs_bits_per_spike)."""
+    import vsb200 as vs
+    r = rates_KTN.contiguous().float()
+    s = spikes_KTN.contiguous().float()
+    K, T, N = r.shape
+    out = torch.empty(N, dtype=torch.float64, device=r.device)
+    vs.check(vs.lib.vs_bits_per_spike(vs.ptr(r), vs.ptr(s), K, T, N, vs.ptr(out), vs.stream()))
+    return out
+
+
+def device_r2_per_trial(gt_KTN, pred_KTN):
+    """sklearn r2_score(gt[k].T-style (N, T) slices) per trial k, float64 (K,) CUDA tensor (utils.py:158)."""
+    import vsb200 as vs
+    g = gt_KTN.contiguous().float()
+    p = pred_KTN.contiguous().float()
+    K, T, N = g.shape
+    out = torch.empty(K * T, dtype=torch.float64, device=g.device)
+    vs.check(vs.lib.vs_r2_rows(vs.ptr(g), vs.ptr(p), K, T, N, vs.ptr(out), vs.stream()))
+    return out.view(K, T).mean(dim=1)

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvs_b200.so")
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+OPERAND_BF16, OPERAND_F16 = 0, 1
 MAX_LAYERS = 16
 
 
@@ -36,7 +37,7 @@ class Mlp(C.Structure):
 
 class RrrDims(C.Structure):
     _fields_ = [("K", C.c_int64), ("T", C.c_int64), ("C1", C.c_int64), ("N", C.c_int64), ("r", C.c_int64),
-                ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64)]
+                ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64), ("fmt", C.c_int32)]
 
 
 def _load():
@@ -58,16 +59,19 @@ def _load():
         "vs_linear_bwd_workspace": (sz, [i64, i64, i64]),
         "vs_linear_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp, sz, vp]),
         "vs_poisson_nll": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+        "vs_bits_per_spike": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
+        "vs_r2_rows": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
         "vs_adamw": (C.c_int, [vp, vp, vp, vp, i64, AdamWHyper, vp]),
         "vs_dw_adamw_fused": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, AdamWHyper, vp]),
         "vs_mlp_workspace": (sz, [C.POINTER(Mlp), i64]),
         "vs_mlp_train_step": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, AdamWHyper, vp, i32, vp, sz, vp]),
+        "vs_mlp_train_step_rowpar": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, AdamWHyper, vp, i32, vp, sz, vp, i32]),
         "vs_mlp_forward": (C.c_int, [C.POINTER(Mlp), vp, vp, vp, i64, vp, i32, vp, sz, vp]),
         "vs_rrr_ldc": (i64, [i64]),
         "vs_rrr_ldr": (i64, [i64, i64]),
-        "vs_rrr_pack": (C.c_int, [vp, i64, i64, RrrDims, vp, vp, vp, vp]),
+        "vs_rrr_pack": (C.c_int, [vp, i64, i64, RrrDims, vp, vp, vp, vp, vp]),
         "vs_rrr_colstats": (C.c_int, [vp, i64, i64, vp, vp, vp]),
-        "vs_rrr_pack_u8": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, vp, vp, vp]),
+        "vs_rrr_pack_u8": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, vp, vp, vp, vp]),
         "vs_rrr_smooth_y": (C.c_int, [vp, i64, i64, i64, dbl, vp, vp, vp, vp]),
         "vs_colstats_f32": (C.c_int, [vp, i64, i64, vp, vp, vp]),
         "vs_rrr_workspace": (sz, [RrrDims]),
@@ -156,12 +160,12 @@ def adamw(p, g, m, v, hyper: AdamWHyper) -> None:
 
 def gemm_tn(A: torch.Tensor, B: torch.Tensor, engine: int = ENGINE_AUTO) -> torch.Tensor:
     """C = A @ B.T for K-major A (M,K), B (N,K); bf16 or fp32(tf32) operands.  Test hook."""
-    assert A.dtype == B.dtype and A.dtype in (torch.bfloat16, torch.float32)
+    assert A.dtype == B.dtype and A.dtype in (torch.bfloat16, torch.float32, torch.float16)
     M, K = A.shape
     N = B.shape[0]
     Cm = torch.empty((M, N), dtype=torch.float32, device=A.device)
     check(lib.vs_gemm_tn(ptr(A), ptr(B), ptr(Cm), M, N, K, A.stride(0), B.stride(0), N,
-                         0 if A.dtype == torch.bfloat16 else 1, engine, stream()))
+                         {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}[A.dtype], engine, stream()))
     return Cm
 
 
