@@ -460,3 +460,25 @@ def test_linear_row_parallel_first_layer_emulated_ranks(vs, cuda):
     la = float(a.fused_train_step(frames.to(cuda), ap.to(cuda), ao))
     lb = float(b.fused_train_step_rowpar(frames.to(cuda), ap.to(cuda), bo))
     assert lb == pytest.approx(la, rel=1e-7)
+
+
+@pytest.mark.parametrize("K,Kt,F,N,r", [(7, 3, 3, 5, 3), (33, 9, 1, 17, 2), (5, 2, 130, 1, 3), (19, 4, 65, 33, 5)])
+def test_rrr_ragged_shapes_vs_oracle(vs, cuda, K, Kt, F, N, r):
+    """Edge shapes: scalar modalities (C = 2..4 columns, src/train_rrr.py one-hot branch widths), odd trial counts,
+    a single neuron, N and C1 that are no multiple of any tile size, rank != 3 -- closure and fit vs float64."""
+    from model.rrr import RRRGD, train_model_main
+    td = small_rrr_problem(seed=K + F, K=K, Kt=Kt, F=F, N=N)
+    params = ro.rrr_init(td, r)
+    rng = np.random.default_rng(2)
+    for k in params:
+        params[k] = params[k] + 0.05 * rng.standard_normal(params[k].shape)
+    loss_o, g_o, sse_o = ro.loss_and_grad_dense(params, td, 100.0, 0)
+    m = RRRGD(td, r, l2=100.0, planes=3); m.to(cuda)
+    _params_to_model(m, params, cuda)
+    assert float(m.loss_and_grad(td, 0)) == pytest.approx(loss_o, rel=1e-6)
+    gmax = max(np.abs(v).max() for v in g_o.values())
+    for k in g_o:
+        assert np.abs(m.model[k].grad.cpu().numpy() - g_o[k]).max() <= 1e-5 * np.abs(g_o[k]).max() + 1e-7 * gmax, k
+    _, mse_o, _ = ro.train_model_main(td, 100.0, r)
+    _, mse = train_model_main(td, l2=100.0, n_comp=r, model_fname="tmp", save=False, planes=3)
+    assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=1e-3)

@@ -221,6 +221,9 @@ class Linear(torch.nn.Module):
         lo, hi = min(D, rank * chunk), min(D, (rank + 1) * chunk)
         if hi <= lo:
             raise vs.VsError(f"rank {rank} of {world} gets no pixels of a {D}-pixel frame")
+        self.__dict__["_shard"] = {"lo": lo, "hi": hi, "D": D, "rank": rank, "world": world}
+        if lo == 0 and hi == D:
+            return lo, hi                      # the whole layer: keep the Parameter (an existing optimizer stays valid)
         with torch.no_grad():
             w = lin.weight[:, lo:hi].clone().contiguous()
         lin.weight = torch.nn.Parameter(w)

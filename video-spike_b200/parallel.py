@@ -124,3 +124,114 @@ def train_joint_model(model, train_data_local, model_fname="tmp", save=False, gr
     if save and world()[0] == 0:
         torch.save({"RRRGD_model": model.state_dict(), "optimizer": {}}, model_fname)
     return model, {"mses_val": mses_val, "mse_val_mean": total}
+
+
+# =====================================================================================================
+# ONE session over n GPUs (third row): trials are sharded, the parameters are replicated.
+def _combine_stats(mean, std, k_local, group=None):
+    """Global mean / clipped population std over all ranks' trials from the local ones (Chan's parallel formula,
+    float64): what src/utils/utils.py:107-112 computes over the whole train split."""
+    k = torch.tensor([float(k_local)], dtype=torch.float64, device=mean.device)
+    s1 = mean * k_local
+    s2 = (std * std + mean * mean) * k_local          # sum x^2 = K (var + mean^2)
+    for t in (k, s1, s2):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    gmean = s1 / k
+    gvar = (s2 / k - gmean * gmean).clamp_min(0.0)
+    return gmean, gvar.sqrt().clamp_min(1e-8), int(k.item())
+
+
+def pack_trial_shard(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=1, smooth_w=2.0,
+                     device=None, operand=None, group=None):
+    """`model.rrr.pack_session_from_frames` for THIS rank's trials of a session whose trials are spread over the ranks:
+    the z-score statistics (frames and smoothed counts) are those of the WHOLE train split (three small all-reduces),
+    so every rank's operands are exactly the rows it would own in the single-GPU pack."""
+    from model.rrr import _PackedSplit, _op_dtype, operand_format
+    vs.require_b200()
+    device = device or torch.device("cuda")
+    st = vs.stream()
+    idx = torch.as_tensor(np.asarray(sorted_idx), dtype=torch.int32).to(device)
+    T = int(idx.numel())
+    fmt = operand_format(planes, operand)
+    splits, ys = [], []
+    mean = sd = my = sy = None
+    for which, (fr, cnt) in enumerate(((frames_train, counts_train), (frames_test, counts_test))):
+        fr = fr.to(device, non_blocking=True).reshape(fr.shape[0], fr.shape[1], -1).contiguous()
+        cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
+        K, Tf, F = fr.shape
+        N = cnt.shape[2]
+        if which == 0:
+            mean = torch.empty(Tf * F, dtype=torch.float64, device=device)
+            sd = torch.empty_like(mean)
+            vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf * F, vs.ptr(mean), vs.ptr(sd), st))
+            sm = torch.empty_like(cnt)
+            vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
+            my = torch.empty(T * N, dtype=torch.float64, device=device)
+            sy = torch.empty_like(my)
+            vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
+            del sm
+            if world()[1] > 1:
+                # the kernels clip std at 1e-8 before returning it: a locally constant column reports 1e-8, whose square
+                # (1e-16) is far below float64 noise of the combined second moment -- harmless in the combination
+                mean, sd, _ = _combine_stats(mean, sd, K, group)
+                my, sy, _ = _combine_stats(my, sy, K, group)
+        d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T), fmt)
+        Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)
+        Xb = torch.empty((planes, F, d.ldr), dtype=_op_dtype(fmt), device=device)
+        xl = torch.empty(K * T, dtype=torch.float32, device=device)
+        overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
+                                       vs.ptr(xl), vs.ptr(overflow), st))
+        y = torch.empty_like(cnt)
+        vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
+        splits.append(_PackedSplit.from_device(d, Xa, Xb, xl, y, overflow))
+        ys.append(y)
+        del fr
+    return {"X": splits, "y": ys,
+            "setup": {"mean_X_Tv": mean, "std_X_Tv": sd, "mean_y_TN": my.reshape(T, -1), "std_y_TN": sy.reshape(T, -1)}}
+
+
+def train_trial_sharded(entry_local, l2, n_comp, eid="session", planes=1, operand=None, group=None, history_dtype=None):
+    """`train_model_main` (rrr.py:192-202) for ONE session whose trials are sharded over the ranks.
+    Parameters and the whole L-BFGS state are replicated; each closure evaluation runs on the local trials with
+    l2 / world (the penalty is linear in l2, so the ranks' losses and gradients SUM to the single-GPU ones) followed by
+    ONE all-reduce of [flat gradient, loss]; every rank then takes the identical L-BFGS step."""
+    from model.rrr import RRRGD, get_device
+    rank, ws = world()
+    td = {eid: entry_local}
+    model = RRRGD(td, n_comp, l2=l2 / ws, planes=planes, operand=operand)
+    device = get_device()
+    # b = mean over ALL trials of the session (rrr.py:47): combine the local means
+    yl = entry_local["y"][0]
+    kk = torch.tensor([float(yl.shape[0])], dtype=torch.float64, device=yl.device)
+    bsum = yl.double().sum(0).T.unsqueeze(1).contiguous()
+    if ws > 1:
+        dist.all_reduce(kk, group=group)
+        dist.all_reduce(bsum, group=group)
+    with torch.no_grad():
+        model.model[f"{eid}_b"].copy_((bsum / kk).cpu())
+    model.to(device)
+    optimizer = model.make_optimizer(history_dtype=history_dtype)
+
+    def closure():
+        optimizer.zero_grad()
+        model.train()
+        loss = model.loss_and_grad(td, 0)
+        if ws > 1:
+            fl = optimizer._flat
+            g = fl["g"][fl["cur"]]                                  # every p.grad is a view of this one buffer
+            buf = loss.reshape(1).clone()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            loss = buf[0]
+        return loss
+
+    optimizer.step(closure)
+    model.eval()
+    mses_val = model.compute_MSE_RRRGD(td, 1)
+    total = torch.sum(mses_val[eid]).clone()
+    per_neuron = mses_val[eid].clone()
+    if ws > 1:
+        dist.all_reduce(total, group=group)
+        dist.all_reduce(per_neuron, group=group)
+    return model, {"mses_val": {eid: per_neuron}, "mse_val_mean": total}
