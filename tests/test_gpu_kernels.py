@@ -274,3 +274,23 @@ def test_device_metrics_match_oracle(vs, cuda, golden_dir):
     gk = np.load(os.path.join(golden_dir, "metrics_kat.npz"))
     b0 = device_bits_per_spike(torch.from_numpy(gk["rates"]).to(cuda), torch.from_numpy(gk["spikes"]).to(cuda))[0]
     assert float(b0) == pytest.approx(float(gk["bps_n0"]), rel=1e-6)     # rates pass through float32 on this route
+
+
+# ----------------------------------------------------------------------------- large-batch dW on the tensor cores
+@pytest.mark.parametrize("batch,in_dim,out_dim,u8", [(64, 8192, 256, True), (100, 4096 + 64, 256, True), (40, 5000, 96, False)])
+def test_large_batch_dw_tensor_core_route(vs, cuda, batch, in_dim, out_dim, u8):
+    """batch > 32 on the tall layer: dW = g^T x through the tcgen05 engine (g as two bf16 planes, frames exact in bf16)."""
+    torch.manual_seed(12)
+    x8 = torch.randint(0, 256, (batch, in_dim), dtype=torch.uint8, device=cuda)
+    xf = x8.float() if u8 else torch.randn(batch, in_dim, device=cuda).to(torch.bfloat16).float()   # bf16-representable input
+    dy = torch.randn(batch, out_dim, device=cuda) * 1e-3
+    W = torch.randn(out_dim, in_dim, device=cuda) * 0.01
+    dW = torch.empty_like(W); db = torch.empty(out_dim, device=cuda)
+    need = int(vs.lib.vs_linear_bwd_workspace(batch, in_dim, out_dim))
+    assert need >= in_dim * 64 * 2
+    ws = torch.empty(need, dtype=torch.uint8, device=cuda)
+    vs.check(vs.lib.vs_linear_bwd(vs.ptr(dy), None, None if u8 else vs.ptr(xf), vs.ptr(x8) if u8 else None, vs.ptr(W), None, None,
+                                  vs.ptr(dW), vs.ptr(db), batch, in_dim, out_dim, 0, vs.ptr(ws), need, vs.stream()))
+    ref = dy.double().t() @ xf.double()
+    assert float((dW.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())      # 16 significant bits on g
+    torch.testing.assert_close(db, dy.sum(0), rtol=1e-4, atol=1e-6)

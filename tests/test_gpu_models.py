@@ -482,3 +482,17 @@ def test_rrr_ragged_shapes_vs_oracle(vs, cuda, K, Kt, F, N, r):
     _, mse_o, _ = ro.train_model_main(td, 100.0, r)
     _, mse = train_model_main(td, l2=100.0, n_comp=r, model_fname="tmp", save=False, planes=3)
     assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=1e-3)
+
+
+def test_linear_large_batch_step_vs_oracle(vs, cuda):
+    """batch 48 (> 32: materialised-gradient route, tall-layer dW on the tensor cores) vs the fp32 oracle."""
+    H = W = 12; N = 5; B = 48
+    D = 120 * H * W
+    model, opt, sched = make_linear_model(D, N, cuda, total_steps=30)
+    tr = lo.Trainer(lo.init_params(D, N, seed=42), total_steps=30)
+    for s in range(3):
+        frames, ap = lo.synth_batch(B, (120, 1, H, W), N, seed=40 + s)
+        ref = tr.step(frames, ap)
+        got = float(model.fused_train_step(frames.to(cuda), ap.to(cuda), opt)); sched.step()
+        assert got == pytest.approx(ref, rel=1e-4)
+    _assert_weights_close(tr.params, model)

@@ -1,4 +1,5 @@
 // Linear layers and the whole `Linear` MLP train step (src/model/linear.py, src/trainer/base.py:147-154).
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "gemm.h"
 #include "smallbatch.h"
@@ -21,6 +22,76 @@ static int tc_splits(long long out_dim, long long batch) {
   long long s = kNumSMs / (tiles > 0 ? tiles : 1);
   if (s < 1) s = 1;
   return (int)s;
+}
+
+// ---- large-batch weight gradient of the tall layer on the tensor cores -----------------------------------------------
+// dW[o, i] = sum_b g[b, o] x[b, i]  (M = out, N = pixels, contraction = batch).  Operands for the TN engine:
+//   A = g^T   (out x Bpad) as TWO bf16 residual planes (16 significant bits: g is a gradient, not a pixel)
+//   B = x^T   (pixels x Bpad) bf16 -- exact for uint8 frames (0..255 fit in 8 significant bits)
+// Both are produced by small transpose kernels into the workspace; C = dW (out x pixels) fp32 is written once.
+constexpr long long kTcBatchMin = 33;     // below: the register kernels (smallbatch.cu / dw_adamw_kernel) are HBM-bound already
+
+__device__ __forceinline__ uint16_t to_bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+// xT[i][b] = bf16(x[b][i]); 32 x 32 tiles through shared memory, both sides coalesced
+template <bool kU8>
+__global__ void __launch_bounds__(256) xT_bf16_kernel(const uint8_t* __restrict__ xu, const float* __restrict__ xf, long long batch,
+                                                      long long in_dim, long long bpad, uint16_t* __restrict__ xT) {
+  __shared__ uint16_t tile[32][33];
+  const long long i0 = (long long)blockIdx.x * 32, b0 = (long long)blockIdx.y * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int r = ly; r < 32; r += 8) {
+    const long long b = b0 + r, i = i0 + lx;
+    float v = 0.f;
+    if (b < batch && i < in_dim) v = kU8 ? (float)xu[b * in_dim + i] : xf[b * in_dim + i];
+    tile[r][lx] = to_bf16_bits(v);
+  }
+  __syncthreads();
+  for (int r = ly; r < 32; r += 8) {
+    const long long i = i0 + r, b = b0 + lx;
+    if (i < in_dim && b < bpad) xT[i * bpad + b] = tile[lx][r];
+  }
+}
+// gT planes: gT[p][o][b] = plane p of g[b][o]
+__global__ void gT_planes_kernel(const float* __restrict__ g, long long batch, long long out_dim, long long bpad,
+                                 uint16_t* __restrict__ gT) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= out_dim * bpad) return;
+  const long long o = idx / bpad, b = idx % bpad;
+  const float v = b < batch ? g[b * out_dim + o] : 0.f;
+  const uint16_t hi = to_bf16_bits(v);
+  const float lo = v - __uint_as_float((uint32_t)hi << 16);
+  gT[idx] = hi;
+  gT[out_dim * bpad + idx] = to_bf16_bits(lo);
+}
+
+static size_t dw_tc_workspace(long long batch, long long in_dim, long long out_dim) {
+  const long long bpad = round_up(batch, 64);
+  return (size_t)round_up(in_dim * bpad * 2, 1024) + (size_t)round_up(2 * out_dim * bpad * 2, 1024) + 1024;
+}
+static bool dw_tc_ok(long long batch, long long in_dim, long long out_dim, const float* dW) {
+  return batch >= kTcBatchMin && in_dim >= kBigK && in_dim % 4 == 0 && (((uintptr_t)dW) & 15) == 0;
+}
+static int dw_tc(const float* g, const float* x_f32, const uint8_t* x_u8, float* dW, long long batch, long long in_dim,
+                 long long out_dim, void* workspace, cudaStream_t st) {
+  const long long bpad = round_up(batch, 64);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  uint16_t* xT = reinterpret_cast<uint16_t*>(base);
+  uint16_t* gT = reinterpret_cast<uint16_t*>(base + round_up(in_dim * bpad * 2, 1024));
+  dim3 gx((unsigned)ceil_div(in_dim, 32), (unsigned)ceil_div(bpad, 32));
+  if (x_f32) {
+    VS_LAUNCH((xT_bf16_kernel<false>), gx, 256, 0, st, nullptr, x_f32, batch, in_dim, bpad, xT);
+  } else {
+    VS_LAUNCH((xT_bf16_kernel<true>), gx, 256, 0, st, x_u8, nullptr, batch, in_dim, bpad, xT);
+  }
+  VS_LAUNCH(gT_planes_kernel, (unsigned)ceil_div(out_dim * bpad, 256), 256, 0, st, g, batch, out_dim, bpad, gT);
+  tc::GemmDesc d;
+  d.A.ptr = gT; d.A.rows = out_dim; d.A.k = bpad; d.A.ld = bpad; d.A.planes = 2; d.A.plane_stride = out_dim * bpad;
+  d.B.ptr = xT; d.B.rows = in_dim; d.B.k = bpad; d.B.ld = bpad;
+  d.M = out_dim; d.N = in_dim; d.K = bpad; d.C = dW; d.ldc = in_dim;
+  d.n_pass = 2; d.pa[0] = 1; d.pb[0] = 0; d.pa[1] = 0; d.pb[1] = 0;      // low plane first, dominant product last
+  d.BN = 256;
+  return tc::gemm_tn(d, st);
 }
 }  // namespace vs
 
@@ -98,7 +169,9 @@ extern "C" int vs_linear_fwd(const float* x_f32, const uint8_t* x_u8, const floa
 }
 
 extern "C" size_t vs_linear_bwd_workspace(int64_t batch, int64_t in_dim, int64_t out_dim) {
-  return sb::dx_workspace(batch, in_dim, out_dim);
+  size_t ws = sb::dx_workspace(batch, in_dim, out_dim);
+  if (batch >= kTcBatchMin && in_dim >= kBigK) ws = ws > dw_tc_workspace(batch, in_dim, out_dim) ? ws : dw_tc_workspace(batch, in_dim, out_dim);
+  return ws;
 }
 
 extern "C" int vs_linear_bwd(const float* dy, const float* y, const float* x_f32, const uint8_t* x_u8, const float* W,
@@ -130,6 +203,13 @@ extern "C" int vs_linear_bwd(const float* dy, const float* y, const float* x_f32
     int rc = sb::dx(g, W, nullptr, dx, batch, in_dim, out_dim, workspace, workspace_bytes, st);
     if (rc) return rc;
     dx = nullptr;
+  }
+  if (dW && (x_f32 || x_u8) && dw_tc_ok(batch, in_dim, out_dim, dW) && workspace &&
+      workspace_bytes >= dw_tc_workspace(batch, in_dim, out_dim)) {
+    // large batch on the tall layer: tensor cores (the SIMT engine would be FMA-bound at 2*B flops per weight)
+    int rc = dw_tc(g, x_f32, x_u8, dW, batch, in_dim, out_dim, workspace, st);
+    if (rc) return rc;
+    dW = nullptr;
   }
   if (dW) {
     VS_REQUIRE(x_f32 || x_u8, VS_ERR_INVALID, "vs_linear_bwd: dW needs the layer input");
@@ -175,7 +255,7 @@ extern "C" size_t vs_mlp_workspace(const vs_mlp* net, int64_t batch) {
   for (int l = 0; l < net->n_layers && l < VS_MAX_LAYERS; ++l) {
     const size_t w = vs_linear_fwd_workspace(batch, net->dims[l], net->dims[l + 1]);
     if (w > ws) ws = w;
-    const size_t wb = l >= 1 ? vs_linear_bwd_workspace(batch, net->dims[l], net->dims[l + 1]) : 0;
+    const size_t wb = (l >= 1 || batch > 32) ? vs_linear_bwd_workspace(batch, net->dims[l], net->dims[l + 1]) : 0;
     if (wb > ws) ws = wb;
   }
   return ws;
@@ -308,7 +388,8 @@ static int mlp_backward_update(const vs_mlp* net, const uint8_t* frames_u8, cons
   const uint8_t* xu = x_f32 ? nullptr : frames_u8;
   VS_REQUIRE(net->gW[0], VS_ERR_INVALID, "vs_mlp_train_step: large-batch route needs gW[0]");
   rc = vs_linear_bwd(net->gact[0], net->act[0], x_f32, xu, net->W[0], net->gact[0], nullptr, net->gW[0],
-                     net->b[0] ? net->gb[0] : nullptr, batch, net->dims[0], net->dims[1], net->relu[0], nullptr, 0, stream);
+                     net->b[0] ? net->gb[0] : nullptr, batch, net->dims[0], net->dims[1], net->relu[0], workspace, workspace_bytes,
+                     stream);
   if (rc) return rc;
   for (int l = 0; l < L; ++l) {
     rc = vs_adamw(net->W[l], net->gW[l], net->mW[l], net->vW[l], net->dims[l] * net->dims[l + 1], h, stream);
