@@ -95,3 +95,32 @@ def test_train_rrr_driver_matches_oracle(cuda, tmp_path, monkeypatch):
     assert np.mean(np.abs(result[eid]["pred"] - ref_pred) > 1e-3 * np.abs(ref_pred)) < 1e-3     # rare, all among the smallest rates
     assert np.nanmean(result[eid]["co_bps"]) == pytest.approx(ev["co_bps"], abs=5e-4)
     assert np.nanmean(result[eid]["r2"]) == pytest.approx(ev["r2"], abs=5e-4)
+
+
+def test_utils_train_rrr_matches_oracle(cuda, monkeypatch):
+    """utils.train_rrr (src/utils/utils.py:376-456, the fit the contrastive trainer's validation runs) on float embeddings."""
+    from utils.utils import train_rrr
+    monkeypatch.setenv("VS_RRR_PLANES", "3")
+    rng = np.random.default_rng(11)
+    K, Kt, T, C, N = 36, 10, 100, 24, 9
+    W = rng.standard_normal((C, 3)); A = rng.standard_normal((3, N))
+    def make(k):
+        X = rng.standard_normal((k, T, C))
+        y = rng.poisson(np.exp(0.3 * (X @ W) @ A / np.sqrt(C) - 1.0)).astype(np.float64)
+        return X, y
+    Xtr, ytr = make(K); Xte, yte = make(Kt)
+    dd = {"e1": {"X": [Xtr.copy(), Xte.copy()], "y": [ytr.copy(), yte.copy()], "setup": {}}}
+    res = train_rrr(dd)
+    # oracle: same preprocessing (no smoothing, no frame subset in this entry point), same fit, same scoring
+    mX, sX = ro.zscore_stats(Xtr); my, sy = ro.zscore_stats(ytr)
+    Xo = [np.concatenate([(x - mX) / sX, np.ones(x.shape[:2] + (1,))], 2) for x in (Xtr, Xte)]
+    yo = [(y - my) / sy for y in (ytr, yte)]
+    td = {"e1": {"X": Xo, "y": yo, "setup": {"mean_X_Tv": mX, "std_X_Tv": sX, "mean_y_TN": my, "std_y_TN": sy}}}
+    params, _, _ = ro.train_model_main(td, 100.0, 3)
+    _, _, pred = ro.predict_y_fr(params, td, "e1", 1)
+    ev = ro.eval_session(pred, yte)
+    ref_pred = np.clip(pred, 1e-3, None)
+    assert np.abs(res["e1"]["pred"] - ref_pred).max() <= 1e-3 * np.abs(ref_pred).max()
+    assert np.nanmean(res["e1"]["bps"]) == pytest.approx(ev["co_bps"], abs=5e-4)
+    assert np.nanmean(res["e1"]["r2"]) == pytest.approx(ev["r2"], abs=5e-4)
+    assert set(res["e1"].keys()) == {"gt", "pred", "bps", "r2", "eid"}

@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from model.rrr import pack_session_from_frames, train_model_main  # noqa: E402
 from utils.config_utils import config_from_kwargs, update_config  # noqa: E402
 from utils.metric_utils import bits_per_spike  # noqa: E402
-from utils.utils import _one_hot, _std, get_args, select_frames, set_seed  # noqa: E402
+from utils.utils import _one_hot, _std, evaluate_rrr_session, get_args, select_frames, set_seed  # noqa: E402
 
 VIDEO_LIKE = ['cebra', 'pca', 'ws', 'whisker-video', 'vit', 'cm', 'm', 'c', 'synthetic']
 
@@ -97,16 +97,8 @@ def preprocess_host(train_data, eids, input_mod, sorted_idx, smooth_w=2):
 
 
 def evaluate_session(pred, gt_held_out, threshold=1e-3):
-    """src/train_rrr.py:198-224: clip at 1e-3, per-neuron co-bps against the UNSMOOTHED test counts and the mean over
-    trials of sklearn's R2."""
-    pred = np.clip(pred, threshold, None)
-    bps_list, r2_list = [], []
-    for n_i in tqdm(range(pred.shape[2]), desc='co-bps'):
-        bps = bits_per_spike(pred[:, :, [n_i]], gt_held_out[:, :, [n_i]])
-        r2 = np.nanmean([r2_score(gt_held_out[k, :, n_i], pred[k, :, n_i]) for k in range(pred.shape[0])])
-        r2_list.append(r2)
-        bps_list.append(np.nan if np.isinf(bps) else bps)
-    return pred, bps_list, r2_list
+    """src/train_rrr.py:198-224 (shared with utils.train_rrr)."""
+    return evaluate_rrr_session(pred, gt_held_out, threshold)
 
 
 def main(argv=None):

@@ -113,3 +113,55 @@ def select_frames(n_total=119, n_keep=100):
     `set_seed(config.seed)` in the reference driver), returned sorted."""
     idx = np.random.choice(n_total, n_keep, replace=False)
     return np.sort(idx)
+
+
+def evaluate_rrr_session(pred, gt_held_out, threshold=1e-3):
+    """src/train_rrr.py:198-224 and src/utils/utils.py:417-447: clip the de-z-scored prediction at 1e-3, per-neuron
+    bits/spike against the held-out counts, mean over trials of sklearn's R2 per neuron (inf bps -> nan)."""
+    from tqdm import tqdm
+    pred = np.clip(pred, threshold, None)
+    bps_list, r2_list = [], []
+    for n_i in tqdm(range(pred.shape[2]), desc='co-bps'):
+        bps = bits_per_spike(pred[:, :, [n_i]], gt_held_out[:, :, [n_i]])
+        r2 = np.nanmean([r2_score_sklearn(gt_held_out[k, :, n_i], pred[k, :, n_i]) for k in range(pred.shape[0])])
+        r2_list.append(r2)
+        bps_list.append(np.nan if np.isinf(bps) else bps)
+    return pred, bps_list, r2_list
+
+
+def train_rrr(data_dict):
+    """Drop-in for src/utils/utils.py:376-456 (the RRR fit ContrastTrainer._validate runs every validation round,
+    src/trainer/contrast.py:129-162): z-score X and y with the train statistics, append the ones column, fit every
+    session separately with l2 = 100, rank 3, and score the de-z-scored test prediction.  Same in-place mutation of
+    `data_dict`, same result dictionary."""
+    ground_truth = {}
+    for eid in data_dict:
+        _, mean_X, std_X = _std(data_dict[eid]["X"][0])
+        _, mean_y, std_y = _std(data_dict[eid]["y"][0])
+        ground_truth[eid] = data_dict[eid]["y"][1].copy()
+        for i in range(2):
+            K = data_dict[eid]["X"][i].shape[0]
+            T = data_dict[eid]["X"][i].shape[1]
+            data_dict[eid]["X"][i] = (data_dict[eid]["X"][i] - mean_X) / std_X
+            if len(data_dict[eid]["X"][i].shape) == 2:
+                data_dict[eid]["X"][i] = np.expand_dims(data_dict[eid]["X"][i], axis=0)
+            data_dict[eid]["X"][i] = np.concatenate([data_dict[eid]["X"][i], np.ones((K, T, 1))], axis=2)
+            data_dict[eid]["y"][i] = (data_dict[eid]["y"][i] - mean_y) / std_y
+            print(f"X shape: {data_dict[eid]['X'][i].shape}, y shape: {data_dict[eid]['y'][i].shape}")
+        data_dict[eid]["setup"]["mean_X_Tv"] = mean_X
+        data_dict[eid]["setup"]["std_X_Tv"] = std_X
+        data_dict[eid]["setup"]["mean_y_TN"] = mean_y
+        data_dict[eid]["setup"]["std_y_TN"] = std_y
+    l2, n_comp = 100, 3
+    print("Training RRR")
+    result = {}
+    for eid in data_dict:
+        model, mse_val = train_model_main(train_data={eid: data_dict[eid]}, l2=l2, n_comp=n_comp, model_fname='tmp', save=False)
+        print(f"Model {eid} trained")
+        with torch.no_grad():
+            _, _, pred_orig = model.predict_y_fr(data_dict, eid, 1)
+        pred, bps_list, r2_list = evaluate_rrr_session(pred_orig.cpu().numpy(), ground_truth[eid])
+        print(f"Co-BPS: {np.nanmean(bps_list)}")
+        print(f"r2: {np.nanmean(r2_list)}")
+        result[eid] = {'gt': ground_truth[eid], 'pred': pred, 'bps': bps_list, 'r2': r2_list, 'eid': eid}
+    return result
