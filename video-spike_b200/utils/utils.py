@@ -129,39 +129,39 @@ def evaluate_rrr_session(pred, gt_held_out, threshold=1e-3):
     return pred, bps_list, r2_list
 
 
+def _zscore_session_inplace(entry):
+    """z-score X and y of one session with the TRAIN statistics (std clipped at 1e-8), append the ones column and record
+    the statistics under entry["setup"] -- the per-session body of src/utils/utils.py:378-396.  Returns the raw test y."""
+    _, mean_X, std_X = _std(entry["X"][0])
+    _, mean_y, std_y = _std(entry["y"][0])
+    held_out = entry["y"][1].copy()
+    for split in range(2):
+        X = (entry["X"][split] - mean_X) / std_X
+        K, T = entry["X"][split].shape[0], entry["X"][split].shape[1]
+        if X.ndim == 2:                                   # the reference expands a 2-D array to (1, K, T) here; kept
+            X = np.expand_dims(X, axis=0)
+        entry["X"][split] = np.concatenate([X, np.ones((K, T, 1))], axis=2)
+        entry["y"][split] = (entry["y"][split] - mean_y) / std_y
+        print(f"X shape: {entry['X'][split].shape}, y shape: {entry['y'][split].shape}")
+    entry["setup"].update(mean_X_Tv=mean_X, std_X_Tv=std_X, mean_y_TN=mean_y, std_y_TN=std_y)
+    return held_out
+
+
 def train_rrr(data_dict):
-    """Drop-in for src/utils/utils.py:376-456 (the RRR fit ContrastTrainer._validate runs every validation round,
-    src/trainer/contrast.py:129-162): z-score X and y with the train statistics, append the ones column, fit every
-    session separately with l2 = 100, rank 3, and score the de-z-scored test prediction.  Same in-place mutation of
-    `data_dict`, same result dictionary."""
-    ground_truth = {}
-    for eid in data_dict:
-        _, mean_X, std_X = _std(data_dict[eid]["X"][0])
-        _, mean_y, std_y = _std(data_dict[eid]["y"][0])
-        ground_truth[eid] = data_dict[eid]["y"][1].copy()
-        for i in range(2):
-            K = data_dict[eid]["X"][i].shape[0]
-            T = data_dict[eid]["X"][i].shape[1]
-            data_dict[eid]["X"][i] = (data_dict[eid]["X"][i] - mean_X) / std_X
-            if len(data_dict[eid]["X"][i].shape) == 2:
-                data_dict[eid]["X"][i] = np.expand_dims(data_dict[eid]["X"][i], axis=0)
-            data_dict[eid]["X"][i] = np.concatenate([data_dict[eid]["X"][i], np.ones((K, T, 1))], axis=2)
-            data_dict[eid]["y"][i] = (data_dict[eid]["y"][i] - mean_y) / std_y
-            print(f"X shape: {data_dict[eid]['X'][i].shape}, y shape: {data_dict[eid]['y'][i].shape}")
-        data_dict[eid]["setup"]["mean_X_Tv"] = mean_X
-        data_dict[eid]["setup"]["std_X_Tv"] = std_X
-        data_dict[eid]["setup"]["mean_y_TN"] = mean_y
-        data_dict[eid]["setup"]["std_y_TN"] = std_y
-    l2, n_comp = 100, 3
+    """Drop-in for src/utils/utils.py:376-456 -- the RRR fit that ContrastTrainer._validate runs every validation round
+    (src/trainer/contrast.py:129-162): per session, z-score with the train statistics, ones column, an independent fit
+    with l2 = 100 and rank 3, and the co-bps / R2 of the de-z-scored test prediction.  `data_dict` is mutated in place
+    like in the reference and the result dictionary has the same keys."""
+    held_out = {eid: _zscore_session_inplace(data_dict[eid]) for eid in data_dict}
     print("Training RRR")
     result = {}
     for eid in data_dict:
-        model, mse_val = train_model_main(train_data={eid: data_dict[eid]}, l2=l2, n_comp=n_comp, model_fname='tmp', save=False)
+        model, _ = train_model_main(train_data={eid: data_dict[eid]}, l2=100, n_comp=3, model_fname='tmp', save=False)
         print(f"Model {eid} trained")
         with torch.no_grad():
-            _, _, pred_orig = model.predict_y_fr(data_dict, eid, 1)
-        pred, bps_list, r2_list = evaluate_rrr_session(pred_orig.cpu().numpy(), ground_truth[eid])
+            pred_fr = model.predict_y_fr(data_dict, eid, 1)[2]
+        pred, bps_list, r2_list = evaluate_rrr_session(pred_fr.cpu().numpy(), held_out[eid])
         print(f"Co-BPS: {np.nanmean(bps_list)}")
         print(f"r2: {np.nanmean(r2_list)}")
-        result[eid] = {'gt': ground_truth[eid], 'pred': pred, 'bps': bps_list, 'r2': r2_list, 'eid': eid}
+        result[eid] = {'gt': held_out[eid], 'pred': pred, 'bps': bps_list, 'r2': r2_list, 'eid': eid}
     return result
