@@ -405,12 +405,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
   double tot = 0.0;
   for (long long n = threadIdx.x; n < N; n += 256) {
     double s = 0.0;
-    for (long long t = 0; t < T; ++t) s += sse_tn[t * N + n];
+#pragma unroll 10
+    for (long long t = 0; t < T; ++t) s += sse_tn[t * N + n];      // independent loads: unrolled so they overlap
     if (sse_n) sse_n[n] = s;
     tot += s;
   }
   // sum b^2 (the intercept is part of beta: SURVEY A14)
   double bsq = 0.0;
+#pragma unroll 8
   for (long long i = threadIdx.x; i < N * T; i += 256) bsq += b[i] * b[i];
   red[threadIdx.x] = tot + l2 * bsq;
   __syncthreads();
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     for (long long e = threadIdx.x; e < (long long)r * T; e += 256) {
       const long long j = e / T, t = e % T;
       double s = 0.0;
+#pragma unroll 7
       for (long long q = 0; q < KB * NT; ++q) s += (double)pv_part[(t * KB * NT + q) * r + j];
       double gv = 0.0;
       for (int jj = 0; jj < r; ++jj) gv += G[j * r + jj] * V[(long long)jj * T + t];

@@ -63,6 +63,40 @@ def get_device():
     return torch.device("cuda")
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+class _LazyY:
+    """The z-scored targets of a split that is still being produced on the side stream: behaves like the tensor once
+    touched (joins the stream first).  Only `shape` is available without joining (RRRGD.__init__ reads it)."""
+
+    def __init__(self, split):
+        self._split = split
+
+    @property
+    def shape(self):
+        return self._split.y.shape
+
+    def tensor(self):
+        self._split.wait_ready()
+        return self._split.y
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.tensor(), name)
+
+    def __getitem__(self, i):
+        return self.tensor()[i]
+
+
 class _PackedSplit:
     """Device-resident operands of one (session, split): built once, reused by every closure."""
 
@@ -96,7 +130,15 @@ class _PackedSplit:
         self = cls.__new__(cls)
         self.K, self.T, self.C1, self.N = dims.K, dims.T, dims.C1, dims.N
         self.dims, self.Xa, self.Xb, self.xl, self.y, self.overflow = dims, Xa, Xb, xl, y, overflow
+        self.ready = None
         return self
+
+    def wait_ready(self):
+        """Join the side stream that produced this split (pack_session_from_frames) before the first read."""
+        ev = getattr(self, "ready", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self.ready = None
 
     def check_range(self):
         """Half-precision operands: fail loudly if a value left the half range while packing (checked once, lazily,
@@ -239,6 +281,7 @@ class RRRGD():
     def _closure_eval(self, data, eid, k, want_grad, dV=None):
         """loss (0-dim), sse_n (N,) and -- if want_grad -- dU, db written into .grad, dV accumulated."""
         sp = self._split(data, eid, k)
+        sp.wait_ready()
         if sp.overflow is not None and self.n_closure_evals > 0:
             sp.check_range()
         U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
@@ -282,6 +325,7 @@ class RRRGD():
         as the caller's own array wrapped in a CPU tensor (the reference copies it to the device on
         every call; no caller in the reference uses that copy)."""
         sp = self._split(data, eid, k)
+        sp.wait_ready()
         U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
         yhat = torch.empty((sp.K, sp.T, sp.N), dtype=torch.float64, device=V.device)
         ws = self._workspace(sp.dims)
@@ -365,33 +409,49 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
     fmt = operand_format(planes, operand)
     splits, ys = [], []
     mean = sd = my = sy = None
+    main = torch.cuda.current_stream(device)
+    side = _side_stream(device)
     for which, (fr, cnt) in enumerate(((frames_train, counts_train), (frames_test, counts_test))):
-        fr = fr.to(device, non_blocking=True).reshape(fr.shape[0], fr.shape[1], -1).contiguous()
-        cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
-        K, Tf, F = fr.shape
-        N = cnt.shape[2]
-        if which == 0:
-            mean = torch.empty(Tf * F, dtype=torch.float64, device=device)
-            sd = torch.empty_like(mean)
-            vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf * F, vs.ptr(mean), vs.ptr(sd), st))
-            sm = torch.empty_like(cnt)
-            vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
-            my = torch.empty(T * N, dtype=torch.float64, device=device)
-            sy = torch.empty_like(my)
-            vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
-            del sm
+        # the fit needs the TRAIN split only: the test split (H2D + pack) goes to a side stream that starts once the train
+        # statistics exist, overlaps the parameter upload and the first closure evaluations, and is joined lazily
+        # (_PackedSplit.wait_ready) by the first kernel that reads it
+        K, Tf = int(fr.shape[0]), int(fr.shape[1])
+        F = int(fr[0, 0].numel())
+        N = int(cnt.shape[2])
         d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T), fmt)
-        Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)
+        Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)          # allocated on the main stream
         Xb = torch.empty((planes, F, d.ldr), dtype=_op_dtype(fmt), device=device)
         xl = torch.empty(K * T, dtype=torch.float32, device=device)
+        y = torch.empty((K, T, N), dtype=torch.float32, device=device)
         overflow = torch.zeros(1, dtype=torch.int32, device=device)
-        vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
-                                       vs.ptr(xl), vs.ptr(overflow), st))
-        y = torch.empty_like(cnt)
-        vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
-        splits.append(_PackedSplit.from_device(d, Xa, Xb, xl, y, overflow))
-        ys.append(y)
-        del fr
+        if which == 1:
+            side.wait_stream(main)
+            for buf in (Xa, Xb, xl, y, overflow):
+                buf.record_stream(side)            # allocated on the main stream, written on the side stream
+        with torch.cuda.stream(side if which == 1 else main):
+            st = vs.stream()
+            fr = fr.to(device, non_blocking=True).reshape(K, Tf, -1).contiguous()
+            cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
+            if which == 0:
+                mean = torch.empty(Tf * F, dtype=torch.float64, device=device)
+                sd = torch.empty_like(mean)
+                vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf * F, vs.ptr(mean), vs.ptr(sd), st))
+                sm = torch.empty_like(cnt)
+                vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
+                my = torch.empty(T * N, dtype=torch.float64, device=device)
+                sy = torch.empty_like(my)
+                vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
+                del sm
+            vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
+                                           vs.ptr(xl), vs.ptr(overflow), st))
+            vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
+            sp = _PackedSplit.from_device(d, Xa, Xb, xl, y, overflow)
+            if which == 1:
+                sp.ready = torch.cuda.Event()
+                sp.ready.record(side)
+            del fr, cnt
+        splits.append(sp)
+        ys.append(_LazyY(sp) if which == 1 else y)
     Tf_F = mean.numel()
     return {"X": splits, "y": ys,
             "setup": {"mean_X_Tv": mean, "std_X_Tv": sd, "mean_y_TN": my.reshape(T, -1), "std_y_TN": sy.reshape(T, -1)}}
