@@ -281,8 +281,18 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)              # 3 bf16 planes ~ 24 bits
     np.testing.assert_array_equal(Xb.double().sum(0)[:, :K * T].cpu().numpy().T, got)
     assert torch.all(xl == 1.0)
-    # one plane is exactly bf16(X) -- frame gather is index-exact
+    # the first plane of the expansion is exactly bf16(X) -- frame gather is index-exact
     np.testing.assert_array_equal(Xa[0, :, :F].float().cpu().numpy(), torch.from_numpy(ref).to(torch.bfloat16).float().numpy())
+    # the single-plane fast path does the z-score in fp32 ((x - mean) * (1/std)): same values up to one bf16 ulp on the
+    # rare elements that sit on a rounding boundary
+    d1 = vs.RrrDims(K, T, F, 5, 3, 1, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T))
+    Xa1 = torch.zeros((1, K * T, d1.ldc), dtype=torch.bfloat16, device=cuda)
+    Xb1 = torch.zeros((1, F, d1.ldr), dtype=torch.bfloat16, device=cuda)
+    vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d1, vs.ptr(Xa1), vs.ptr(Xb1), vs.ptr(xl), None, vs.stream()))
+    want = torch.from_numpy(ref).to(torch.bfloat16).float().numpy()
+    got1 = Xa1[0, :, :F].float().cpu().numpy()
+    assert np.mean(got1 != want) < 2e-3 and np.abs(got1 - want).max() <= 2.0 ** -7 * np.abs(want).max()
+    np.testing.assert_array_equal(Xb1[0, :, :K * T].float().cpu().numpy().T, got1)
     # y: gaussian smoothing + z-score
     cnt = torch.from_numpy(ytr).float().to(cuda)
     sm = torch.empty_like(cnt)

@@ -65,10 +65,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X,
   const long long pa = K * T * ldc, pb = C1 * ldr;
   long long f = 0;
   if constexpr (kFromU8) f = sorted_idx[t];
+  // single-plane fast path from uint8 frames: the block's 32 columns share (mean, 1/std), taken to fp32 ONCE per block --
+  // per-element fp64 subtract + divide is what bounded this kernel on the narrow fp64 pipe (2.7 ms -> HBM-bound)
+  __shared__ float s_mean[32], s_istd[32];
+  const bool fast = kFromU8 && planes == 1;
+  if (fast) {
+    if (threadIdx.x < 32) {
+      const long long c = c0 + threadIdx.x;
+      const long long col = f * C1 + (c < C1 ? c : C1 - 1);
+      s_mean[threadIdx.x] = (float)mean[col];
+      s_istd[threadIdx.x] = (float)(1.0 / sd[col]);
+    }
+    __syncthreads();
+  }
   for (int rr = ly; rr < 32; rr += 8) {
     const long long k = k0 + rr, c = c0 + lx;
     uint16_t pl[3] = {0, 0, 0};
-    if (k < k_end && c < C1) {
+    if (fast) {
+      if (k < k_end && c < C1) {
+        const float vf = ((float)frames[(k * Tf + f) * C1 + c] - s_mean[lx]) * s_istd[lx];
+        if (fmt == VS_OPERAND_F16 && overflow && !(fabsf(vf) <= 65504.f)) atomicOr(overflow, 1);
+        pl[0] = enc16(vf, fmt);
+        Xa[(t * K + k) * ldc + c] = pl[0];
+      }
+    } else if (k < k_end && c < C1) {
       double v;
       if constexpr (kFromU8) {
         const long long col = f * C1 + c;

@@ -133,6 +133,14 @@ class _PackedSplit:
         self.ready = None
         return self
 
+    def __del__(self):
+        ev = getattr(self, "ready", None)
+        if ev is not None:
+            try:
+                ev.synchronize()
+            except Exception:
+                pass
+
     def wait_ready(self):
         """Join the side stream that produced this split (pack_session_from_frames) before the first read."""
         ev = getattr(self, "ready", None)
@@ -425,9 +433,8 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
         y = torch.empty((K, T, N), dtype=torch.float32, device=device)
         overflow = torch.zeros(1, dtype=torch.int32, device=device)
         if which == 1:
-            side.wait_stream(main)
-            for buf in (Xa, Xb, xl, y, overflow):
-                buf.record_stream(side)            # allocated on the main stream, written on the side stream
+            side.wait_stream(main)                  # (buffers are main-stream allocations: _PackedSplit.__del__ joins the
+            #                                         side stream if the split dies unread, so they are never recycled early)
         with torch.cuda.stream(side if which == 1 else main):
             st = vs.stream()
             fr = fr.to(device, non_blocking=True).reshape(K, Tf, -1).contiguous()
