@@ -222,7 +222,8 @@ def rrr_config(args, world):
     return {"workload": "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
             "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes,
-            "operand_format": (os.environ.get("VS_RRR_OPERAND") or "bf16") + " (16-bit tensor-core operands, fp32 accumulate in TMEM)", "lbfgs": "1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64",
+            "operand_format": (os.environ.get("VS_RRR_OPERAND") or "bf16") + " (16-bit tensor-core operands, fp32 accumulate in TMEM)", "lbfgs": ("1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64")
+                     + (", device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else ", host-driven"),
             "sessions": world, "parallelism": f"session-sharded x{world}" if world > 1 else "single GPU",
             "l2_cache": "operands (1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 4
+#define VS_ABI_VERSION 5
 
 enum {
   VS_OK = 0,
@@ -264,6 +264,45 @@ int vs_lbfgs_direction(int64_t n, const double* g, const void* hist, int64_t his
                        const int32_t* s_slots_host, const int32_t* y_slots_host, int m,
                        const double* coef_host, double t, double* x, void* s_out, double* dmax_out,
                        void* stream);
+
+/* ---- device-driven variant: the optimiser state lives on the GPU and a one-thread kernel takes every decision of
+ * torch.optim.LBFGS.step (memory update, two-loop recursion, step length, termination), so a whole step(closure) is
+ * enqueued without a single host<->device synchronisation: per iteration  closure kernels -> vs_lbfgs_dev_dots ->
+ * vs_lbfgs_dev_update -> vs_lbfgs_dev_direction.  Once the state says `done` the remaining launches are no-ops.
+ * The caller owns the state (a device buffer of sizeof(vs_lbfgs_dev), initialised on the host with
+ * vs_lbfgs_dev_init_host and copied over) and reads it back once at the end.                                   */
+typedef struct {
+  int32_t m;            /* curvature pairs in memory */
+  int32_t n_iter;       /* iterations of the current step() */
+  int32_t total_iter;   /* torch's state["n_iter"] (all step() calls) */
+  int32_t func_evals;   /* torch's state["func_evals"] */
+  int32_t cur_evals;    /* closure evaluations of the current step() */
+  int32_t done;         /* 0 running | 1 converged at the first evaluation | 2 directional derivative | 3 max_eval |
+                           4 gradient tolerance | 5 step tolerance | 6 loss tolerance */
+  int32_t have_prev, have_s;
+  int32_t s_cur, y_next;      /* slot of the latest step s = t*d; slot the next dots pass writes y into */
+  int32_t n_free, pad0;
+  int32_t free_slots[2 * VS_LBFGS_MAX_HIST + 8];
+  int32_t s_slots[VS_LBFGS_MAX_HIST], y_slots[VS_LBFGS_MAX_HIST];
+  double H_diag, prev_loss, loss, t, gtd, dmax;
+  double coef[2 * VS_LBFGS_MAX_HIST + 2];
+  double out[8 + 6 * VS_LBFGS_MAX_HIST];
+  double SY[VS_LBFGS_MAX_HIST * VS_LBFGS_MAX_HIST], YY[VS_LBFGS_MAX_HIST * VS_LBFGS_MAX_HIST];
+} vs_lbfgs_dev;
+
+/* fills *state_host for an empty memory over `n_slots` history slots (>= 2*min(history_size, iterations) + 4) */
+int vs_lbfgs_dev_init_host(vs_lbfgs_dev* state_host, int n_slots);
+size_t vs_lbfgs_dev_workspace(int64_t n);
+/* one pass over g (and g_prev, the latest step, the history): y, all inner products -> state->out */
+int vs_lbfgs_dev_dots(vs_lbfgs_dev* state, int64_t n, const double* g, const double* g_prev, void* hist,
+                      int64_t hist_stride, int hist_f32, void* workspace, size_t workspace_bytes, void* stream);
+/* decisions of one iteration.  loss: device scalar of the latest closure evaluation; first_eval != 0 for the evaluation
+ * that opens a step() call (resets the per-step counters and applies torch's "already converged" early return)      */
+int vs_lbfgs_dev_update(vs_lbfgs_dev* state, const double* loss, double lr, double tolerance_grad, double tolerance_change,
+                        int max_eval, int history_size, int first_eval, void* stream);
+/* d from the state's coefficients; hist[s_cur] = t*d; x += t*d */
+int vs_lbfgs_dev_direction(vs_lbfgs_dev* state, int64_t n, const double* g, void* hist, int64_t hist_stride, int hist_f32,
+                           double* x, void* stream);
 
 /* HOST: the two-loop recursion of torch.optim.LBFGS in coefficient space, between the two device passes.  Inputs are
  * the inner products vs_lbfgs_dots gathered (SY[i*ld+j] = s_i.y_j, YY[i*ld+j] = y_i.y_j, sg[i] = s_i.g,

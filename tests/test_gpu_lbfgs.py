@@ -152,3 +152,78 @@ def test_rrr_fit_float32_history(vs, cuda):
         _, res = train_model(m, td, m.make_optimizer(history_dtype=hd), "tmp", save=False)
         out[hd] = float(res["mse_val_mean"])
     assert out[torch.float32] == pytest.approx(out[torch.float64], rel=1e-5)
+
+
+# ----------------------------------------------------------------------------- device-driven mode (no host sync per iteration)
+@pytest.mark.parametrize("history,steps,max_iter,hd", [(100, 1, 20, torch.float64), (3, 1, 20, torch.float64), (5, 3, 7, torch.float64),
+                                                      (100, 2, 1, torch.float64), (100, 1, 20, torch.float32)])
+def test_device_driven_lbfgs_matches_host_driven(vs, cuda, history, steps, max_iter, hd):
+    """The one-thread update kernel takes the same decisions as the host logic: identical trajectories (to rounding),
+    identical logical counters, across memory windows, several step() calls and both history dtypes."""
+    from optim import FusedLBFGS
+    make = _problem(cuda, seed=5)
+    res = {}
+    for mode in (False, True):
+        ps, f = make()
+        opt = FusedLBFGS(ps, history_size=history, max_iter=max_iter, history_dtype=hd, device_driven=mode)
+        losses = []
+
+        def closure():
+            opt.zero_grad()
+            loss = f()
+            loss.backward()
+            losses.append(loss.detach().clone())
+            return loss
+        for _ in range(steps):
+            opt.step(closure)
+        st = opt.state[ps[0]]
+        res[mode] = ([float(l) for l in losses], torch.cat([p.detach().reshape(-1) for p in ps]).cpu().numpy(), st["func_evals"], st["n_iter"])
+    assert res[True][2:] == res[False][2:]
+    assert len(res[True][0]) == len(res[False][0])
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=1e-9 if hd == torch.float64 else 1e-6)
+    np.testing.assert_allclose(res[True][1], res[False][1], rtol=1e-7 if hd == torch.float64 else 1e-4, atol=1e-9)
+
+
+def test_device_driven_lbfgs_terminates_like_torch(vs, cuda):
+    """Early termination is decided on the device: the remaining launches are no-ops (parameters untouched) and the
+    logical counters equal torch's, although the closure itself is still called max_iter times."""
+    from optim import FusedLBFGS
+    # converged at the first evaluation
+    p = torch.nn.Parameter(torch.zeros(10, dtype=torch.float64, device=cuda))
+    opt = FusedLBFGS([p], device_driven=True)
+    calls = [0]
+
+    def closure():
+        opt.zero_grad(); loss = (p * p).sum(); loss.backward(); calls[0] += 1
+        return loss
+    opt.step(closure)
+    assert opt.state[p]["func_evals"] == 1 and opt.state[p]["n_iter"] == 0 and opt.state[p]["dev_done"] == 1 and calls[0] == 20
+    assert float(p.abs().max()) == 0.0
+    # a quadratic: solved in a few iterations, then the loss tolerance stops it -- same point, same counters as torch
+    out = {}
+    for name, make in (("torch", lambda q: torch.optim.LBFGS([q], max_iter=50)), ("dev", lambda q: FusedLBFGS([q], max_iter=50, device_driven=True))):
+        q = torch.nn.Parameter(torch.full((16,), 0.01, dtype=torch.float64, device=cuda))
+        o = make(q)
+
+        def cl():
+            o.zero_grad(); loss = ((q - 0.02) ** 2).sum(); loss.backward()
+            return loss
+        o.step(cl)
+        out[name] = (o.state[q]["func_evals"], o.state[q]["n_iter"], q.detach().cpu().numpy())
+    assert out["dev"][:2] == out["torch"][:2]
+    np.testing.assert_allclose(out["dev"][2], out["torch"][2], rtol=1e-9)
+
+
+def test_rrr_fit_device_driven(vs, cuda):
+    from model.rrr import RRRGD, train_model
+    from optim import FusedLBFGS
+    td = small_rrr_problem(seed=7, K=30, Kt=10, F=150, N=12)
+    out = {}
+    for mode in (False, True):
+        m = RRRGD(td, 3, l2=100.0, planes=3); m.to(cuda)
+        opt = FusedLBFGS(m.model.parameters(), device_driven=mode)
+        _, res = train_model(m, td, opt, "tmp", save=False)
+        out[mode] = (float(res["mse_val_mean"]), m.n_closure_evals, m.model["e1_U"].detach().cpu().numpy())
+    assert out[True][1] == out[False][1] == 20
+    assert out[True][0] == pytest.approx(out[False][0], rel=1e-8)
+    np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-6, atol=1e-9)

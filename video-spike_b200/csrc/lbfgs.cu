@@ -10,6 +10,7 @@
 //                       and every inner product the Gram update needs, plus |g|_inf and |g|_1
 //   vs_lbfgs_direction  one pass: d = cg*g + sum cs_i s_i + cy_i y_i;  s_out = t*d;  x += t*d;  max|t*d|
 // Both are HBM-bound (8 or 4 B/element/history vector: the history may be stored in float32).  Reductions are two-stage with a fixed order: bit-reproducible.
+#include <string.h>
 #include "common.cuh"
 
 namespace vs {
@@ -116,9 +117,20 @@ template <typename HT, bool kVec>
 __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __restrict__ g, const double* __restrict__ gp,
                                                    const HT* __restrict__ s_new, HT* __restrict__ y_out,
                                                    const HT* __restrict__ hist, long long stride, const Slots slots, int nh,
-                                                   int nout, double* __restrict__ part) {
+                                                   int nout, double* __restrict__ part, const vs_lbfgs_dev* __restrict__ dev) {
   extern __shared__ double red[];          // [nout][8 warps]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int m_dev = 0;
+  if (dev) {   // device-driven optimiser: everything that depends on its decisions comes from the state
+    if (dev->done) return;
+    m_dev = dev->m;
+    nh = 2 * m_dev;
+    if (!dev->have_prev) gp = nullptr;
+    s_new = dev->have_s ? hist + (long long)dev->s_cur * stride : nullptr;
+    y_out = (dev->have_prev && dev->have_s) ? const_cast<HT*>(hist) + (long long)dev->y_next * stride : nullptr;
+  }
+  auto slot_of = [&](int h) -> int { return dev ? (h < m_dev ? dev->s_slots[h] : dev->y_slots[h - m_dev]) : slots.s[h]; };
+  const int nvalid = kBase + 3 * nh;       // outputs this launch produces (nout is the stride of the partial rows)
   const long long i0 = (long long)blockIdx.x * kChunk + 4 * threadIdx.x;
   D4 gv[kGroups], yv[kGroups], sv[kGroups];
   double gg = 0.0, g1 = 0.0, gm = 0.0, yy = 0.0, ys = 0.0, sg = 0.0, yg = 0.0;
@@ -165,9 +177,9 @@ __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __
 #pragma unroll
     for (int q = 0; q < 4; ++q) { gf[j][q] = (AT)gv[j].v[q]; yf[j][q] = (AT)yv[j].v[q]; sf[j][q] = (AT)sv[j].v[q]; }
   for (int h = 0; h < nh; h += 2) {
-    const HT* h0 = hist + (long long)slots.s[h] * stride;
+    const HT* h0 = hist + (long long)slot_of(h) * stride;
     const bool two = h + 1 < nh;
-    const HT* h1 = two ? hist + (long long)slots.s[h + 1] * stride : h0;
+    const HT* h1 = two ? hist + (long long)slot_of(h + 1) * stride : h0;
     H4<HT> a[kGroups], b[kGroups];
 #pragma unroll
     for (int j = 0; j < kGroups; ++j) a[j] = load4h<kVec>(h0, i0 + 1024 * j, n);
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __
   }
   __syncthreads();
   double* out = part + (long long)blockIdx.x * nout;
-  for (int o = threadIdx.x; o < nout; o += 256) {
+  for (int o = threadIdx.x; o < nvalid; o += 256) {
     double s = 0.0;
     if (o == 2) {
       for (int w = 0; w < 8; ++w) s = fmax(s, red[o * 8 + w]);
@@ -212,9 +224,14 @@ __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __
 
 // out[o] = sum (max for o == 2) over the chunk partials: one block per output, thread t takes chunks t, t+128, ...
 // and the 128 lane sums are combined by a fixed tree, so the result does not depend on scheduling
-__global__ void __launch_bounds__(128) dots_reduce_kernel(const double* __restrict__ part, int chunks, int nout, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) dots_reduce_kernel(const double* __restrict__ part, int chunks, int nout, double* __restrict__ out,
+                                                          vs_lbfgs_dev* __restrict__ dev) {
   __shared__ double sh[128];
   const int o = blockIdx.x;
+  if (dev) {
+    if (dev->done || o >= kBase + 6 * dev->m) return;
+    out = dev->out;
+  }
   const bool is_max = (o == 2);
   double s = 0.0;
   for (int c = threadIdx.x; c < chunks; c += 128) {
@@ -235,27 +252,208 @@ __global__ void __launch_bounds__(128) dots_reduce_kernel(const double* __restri
 template <typename HT>
 struct CoefT { HT c[2 * VS_LBFGS_MAX_HIST + 1]; };
 
-template <typename HT>
+template <typename HT, bool kVec>
 __global__ void __launch_bounds__(256) direction_kernel(long long n, const double* __restrict__ g, const HT* __restrict__ hist,
                                                         long long stride, const Slots slots, int nh, const CoefT<HT> coef, double cg,
                                                         double t, double* __restrict__ x, HT* __restrict__ s_out,
-                                                        unsigned long long* __restrict__ dmax_bits) {
+                                                        unsigned long long* __restrict__ dmax_bits, vs_lbfgs_dev* __restrict__ dev) {
   __shared__ double sh[8];
+  __shared__ HT s_coef[2 * VS_LBFGS_MAX_HIST];
+  __shared__ const HT* s_ptr[2 * VS_LBFGS_MAX_HIST];
+  if (dev) {   // device-driven optimiser: coefficients, slots, step length and destination come from the state
+    if (dev->done) return;
+    const int md = dev->m;
+    nh = 2 * md;
+    for (int h = threadIdx.x; h < nh; h += 256) {
+      s_coef[h] = (HT)dev->coef[1 + h];
+      s_ptr[h] = hist + (long long)(h < md ? dev->s_slots[h] : dev->y_slots[h - md]) * stride;
+    }
+    cg = dev->coef[0];
+    t = dev->t;
+    s_out = const_cast<HT*>(hist) + (long long)dev->s_cur * stride;
+    dmax_bits = reinterpret_cast<unsigned long long*>(&dev->dmax);
+  } else {
+    for (int h = threadIdx.x; h < nh; h += 256) { s_coef[h] = coef.c[1 + h]; s_ptr[h] = hist + (long long)slots.s[h] * stride; }
+  }
+  __syncthreads();
   double m = 0.0;
-  const long long step = (long long)gridDim.x * 256;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
-    HT acc = 0;
-#pragma unroll 8
-    for (int h = 0; h < nh; ++h) acc = fma(coef.c[1 + h], hist[(long long)slots.s[h] * stride + i], acc);
-    const double d = fma(cg, g[i], (double)acc);
-    const double sd = t * d;
-    s_out[i] = (HT)sd;
-    if (x) x[i] += sd;
-    m = fmax(m, fabs(sd));
+  // 4 consecutive elements per thread and iteration: one coefficient / pointer fetch per 128-bit history load
+  const long long step = (long long)gridDim.x * 256 * 4;
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += step) {
+    HT acc[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int h = 0; h < nh; ++h) {
+      const H4<HT> v = load4h<kVec>(s_ptr[h], i, n);
+      const HT c = s_coef[h];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(c, v.v[q], acc[q]);
+    }
+    const D4 gv = load4<kVec>(g, i, n);
+    D4 sd;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sd.v[q] = t * fma(cg, gv.v[q], (double)acc[q]);
+      if (i + q < n) m = fmax(m, fabs(sd.v[q]));
+    }
+    store4<kVec>(s_out, i, n, sd);
+    if (x) {
+      if (kVec && i + 3 < n) {
+        double2* xp = reinterpret_cast<double2*>(x + i);
+        double2 a = xp[0], b2 = xp[1];
+        a.x += sd.v[0]; a.y += sd.v[1]; b2.x += sd.v[2]; b2.y += sd.v[3];
+        xp[0] = a; xp[1] = b2;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i + q < n) x[i + q] += sd.v[q];
+      }
+    }
   }
   m = block_max(m, sh);
   // non-negative doubles order like their bit patterns: an integer max is exact and order-independent
   if (threadIdx.x == 0) atomicMax(dmax_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// ------------------------------------------------------------------ device-driven optimiser: the decisions
+// Mirrors, statement for statement, the part of torch.optim.LBFGS.step between two closure evaluations (and
+// optim.py::FusedLBFGS.step, the host-driven version of the same logic): post-evaluation termination tests, memory update
+// with the ys > 1e-10 guard and the history_size window, two-loop recursion in coefficient space, step length,
+// directional-derivative test, slot bookkeeping for the next passes.
+__device__ __forceinline__ int pop_slot(vs_lbfgs_dev* d) { return d->free_slots[--d->n_free]; }
+__device__ __forceinline__ void push_slot(vs_lbfgs_dev* d, int s) { d->free_slots[d->n_free++] = s; }
+
+constexpr int kUpdSmemM = 32;   // memories up to this size run the recursion out of shared memory
+
+// thread 0: everything up to and including the memory update; returns false when the iteration must not proceed
+__device__ bool update_decide(vs_lbfgs_dev* __restrict__ d, const double* __restrict__ loss_ptr, double tol_g, double tol_c,
+                              int max_eval, int hsize, int first_eval, double* sg, double* yg) {
+  constexpr int H = VS_LBFGS_MAX_HIST;
+  if (first_eval) { d->n_iter = 0; d->cur_evals = 0; d->done = 0; }
+  if (d->done) return false;
+  const double loss = *loss_ptr;
+  const double* out = d->out;
+  d->loss = loss;
+  d->cur_evals += 1;
+  d->func_evals += 1;
+  if (first_eval) {
+    if (out[2] <= tol_g) { d->done = 1; return false; }        // optimal condition at the first evaluation
+  } else {
+    if (d->cur_evals >= max_eval) d->done = 3;
+    else if (out[2] <= tol_g) d->done = 4;
+    else if (d->dmax <= tol_c) d->done = 5;
+    else if (fabs(loss - d->prev_loss) < tol_c) d->done = 6;
+    if (d->done) return false;
+  }
+  d->n_iter += 1;
+  d->total_iter += 1;
+  int m = d->m;
+  for (int i = 0; i < m; ++i) { sg[i] = out[kBase + 3 * i]; yg[i] = out[kBase + 3 * (m + i)]; }
+  double Hd = d->H_diag;
+  if (d->total_iter == 1) {
+    Hd = 1.0;
+  } else if (d->have_prev && d->have_s) {
+    const double yy = out[3], ys = out[4];
+    if (ys > 1e-10) {
+      int lo = 0;
+      if (m == hsize) {                                          // limited memory: drop the oldest pair
+        push_slot(d, d->s_slots[0]); push_slot(d, d->y_slots[0]);
+        for (int i = 1; i < m; ++i) {
+          d->s_slots[i - 1] = d->s_slots[i]; d->y_slots[i - 1] = d->y_slots[i];
+          for (int j = 1; j < m; ++j) { d->SY[(i - 1) * H + (j - 1)] = d->SY[i * H + j]; d->YY[(i - 1) * H + (j - 1)] = d->YY[i * H + j]; }
+          sg[i - 1] = sg[i]; yg[i - 1] = yg[i];
+        }
+        lo = 1; m -= 1;
+      }
+      const int mo = m + lo;                                     // pairs the dots pass saw
+      for (int i = 0; i < m; ++i) {
+        const double sy_col = out[kBase + 3 * (i + lo) + 1];           // s_i . y_new
+        const double yy_col = out[kBase + 3 * (mo + i + lo) + 1];      // y_i . y_new
+        const double ys_row = out[kBase + 3 * (mo + i + lo) + 2];      // y_i . s_new
+        d->SY[i * H + m] = sy_col; d->SY[m * H + i] = ys_row;
+        d->YY[i * H + m] = yy_col; d->YY[m * H + i] = yy_col;
+      }
+      d->SY[m * H + m] = ys; d->YY[m * H + m] = yy;
+      d->s_slots[m] = d->s_cur; d->y_slots[m] = d->y_next;
+      sg[m] = out[5]; yg[m] = out[6];
+      m += 1;
+      Hd = ys / yy;
+    } else {
+      push_slot(d, d->s_cur); push_slot(d, d->y_next);
+    }
+    d->have_s = 0;
+  }
+  d->m = m;
+  d->H_diag = Hd;
+  return true;
+}
+
+// two-loop recursion in coefficient space (same statement order as csrc/host_lbfgs.cpp); SY / YY with row pitch ld
+__device__ void update_direction(vs_lbfgs_dev* __restrict__ d, const double* SY, const double* YY, int ld, const double* sg,
+                                 const double* yg, double loss, double lr, double tol_c) {
+  constexpr int H = VS_LBFGS_MAX_HIST;
+  const int m = d->m;
+  const double Hd = d->H_diag, gg = d->out[0], g1 = d->out[1];
+  double al[H], ro[H];
+  double* cs = d->coef + 1;
+  double* cy = d->coef + 1 + m;
+  for (int i = 0; i < m; ++i) ro[i] = 1.0 / SY[i * ld + i];
+  for (int i = m - 1; i >= 0; --i) {
+    double sq = -sg[i];
+    for (int j = i + 1; j < m; ++j) sq -= al[j] * SY[i * ld + j];
+    al[i] = sq * ro[i];
+  }
+  for (int i = 0; i < m; ++i) {
+    double yr = -yg[i];
+    for (int j = 0; j < m; ++j) yr -= al[j] * YY[i * ld + j];
+    yr *= Hd;
+    for (int j = 0; j < i; ++j) yr += cs[j] * SY[j * ld + i];
+    cs[i] = al[i] - yr * ro[i];
+  }
+  d->coef[0] = -Hd;
+  double dot_s = 0.0, dot_y = 0.0;
+  for (int i = 0; i < m; ++i) cy[i] = -Hd * al[i];
+  for (int i = 0; i < m; ++i) dot_s += cs[i] * sg[i];
+  for (int i = 0; i < m; ++i) dot_y += cy[i] * yg[i];
+  d->gtd = m ? -Hd * gg + dot_s + dot_y : -Hd * gg;
+  d->prev_loss = loss;
+  d->have_prev = 1;
+  d->t = d->total_iter == 1 ? fmin(1.0, 1.0 / g1) * lr : lr;
+  if (d->gtd > -tol_c) { d->done = 2; return; }                 // directional derivative below tolerance: no move
+  if (d->have_s) push_slot(d, d->s_cur);                        // an unconsumed step (no previous gradient yet)
+  d->s_cur = pop_slot(d);                                       // the direction pass writes s = t*d here
+  d->have_s = 1;
+  d->y_next = pop_slot(d);                                      // the next dots pass writes y here
+  d->dmax = 0.0;
+}
+
+// One block.  Thread 0 takes the decisions; the other threads only stage the m x m Gram blocks in shared memory so that
+// the O(m^2) recursion of thread 0 does not pay a global-memory round trip per element.
+__global__ void __launch_bounds__(128) update_kernel(vs_lbfgs_dev* __restrict__ d, const double* __restrict__ loss_ptr, double lr,
+                                                     double tol_g, double tol_c, int max_eval, int hsize, int first_eval) {
+  constexpr int H = VS_LBFGS_MAX_HIST;
+  __shared__ double s_SY[kUpdSmemM * kUpdSmemM], s_YY[kUpdSmemM * kUpdSmemM];
+  __shared__ double s_sg[H], s_yg[H];
+  __shared__ int s_go, s_m;
+  if (threadIdx.x == 0) {
+    s_go = update_decide(d, loss_ptr, tol_g, tol_c, max_eval, hsize, first_eval, s_sg, s_yg) ? 1 : 0;
+    s_m = d->m;
+    __threadfence_block();
+  }
+  __syncthreads();
+  if (!s_go) return;
+  const int m = s_m;
+  const bool in_smem = m <= kUpdSmemM;
+  if (in_smem)
+    for (int e = threadIdx.x; e < m * m; e += 128) {
+      const int i = e / m, j = e % m;
+      s_SY[i * kUpdSmemM + j] = d->SY[i * H + j];
+      s_YY[i * kUpdSmemM + j] = d->YY[i * H + j];
+    }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (in_smem) update_direction(d, s_SY, s_YY, kUpdSmemM, s_sg, s_yg, d->loss, lr, tol_c);
+    else update_direction(d, d->SY, d->YY, H, s_sg, s_yg, d->loss, lr, tol_c);
+  }
 }
 
 }  // namespace lbfgs
@@ -273,17 +471,18 @@ extern "C" size_t vs_lbfgs_workspace(int64_t n, int m) {
 
 template <typename HT>
 static int launch_dots(long long n, const double* g, const double* g_prev, const void* s_new, void* y_out, const void* hist,
-                       long long hist_stride, const Slots& sl, int nh, int nout, double* part, int chunks, void* stream) {
+                       long long hist_stride, const Slots& sl, int nh, int nout, double* part, int chunks, void* stream,
+                       const vs_lbfgs_dev* dev = nullptr) {
   const size_t smem = (size_t)nout * 8 * sizeof(double);
   // 128-bit loads need every vector base 16-byte aligned (hist slots: pitch a multiple of 4 elements)
   const bool vec = ((((uintptr_t)g | (uintptr_t)g_prev | (uintptr_t)s_new | (uintptr_t)y_out | (uintptr_t)hist) & 15) == 0) &&
-                   (hist_stride % 4 == 0 || nh == 0);
+                   (hist_stride % 4 == 0 || (nh == 0 && !dev));
   if (vec) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<HT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dots_kernel<HT, true>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part);
+    VS_LAUNCH((dots_kernel<HT, true>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part, dev);
   } else {
     VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<HT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dots_kernel<HT, false>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part);
+    VS_LAUNCH((dots_kernel<HT, false>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part, dev);
   }
   return VS_OK;
 }
@@ -305,7 +504,7 @@ extern "C" int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, c
   int rc = hist_f32 ? launch_dots<float>(n, g, g_prev, s_new, y_out, hist, hist_stride, sl, nh, nout, part, chunks, stream)
                     : launch_dots<double>(n, g, g_prev, s_new, y_out, hist, hist_stride, sl, nh, nout, part, chunks, stream);
   if (rc) return rc;
-  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, out);
+  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, out, (vs_lbfgs_dev*)nullptr);
   return VS_OK;
 }
 
@@ -320,16 +519,83 @@ extern "C" int vs_lbfgs_direction(int64_t n, const double* g, const void* hist, 
   VS_CHECK_CUDA(cudaMemsetAsync(dmax_out, 0, sizeof(double), (cudaStream_t)stream));
   long long blocks = ceil_div(n, 256 * 4);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  const bool vec = ((((uintptr_t)g | (uintptr_t)hist | (uintptr_t)x | (uintptr_t)s_out) & 15) == 0) && hist_stride % 4 == 0;
+  unsigned long long* dm = reinterpret_cast<unsigned long long*>(dmax_out);
   if (hist_f32) {
     CoefT<float> cf;
     for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = (float)coef_host[i];
-    VS_LAUNCH(direction_kernel<float>, (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf,
-              coef_host[0], t, x, (float*)s_out, reinterpret_cast<unsigned long long*>(dmax_out));
+    if (vec) { VS_LAUNCH((direction_kernel<float, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (float*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
+    else { VS_LAUNCH((direction_kernel<float, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (float*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
   } else {
     CoefT<double> cf;
     for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = coef_host[i];
-    VS_LAUNCH(direction_kernel<double>, (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf,
-              coef_host[0], t, x, (double*)s_out, reinterpret_cast<unsigned long long*>(dmax_out));
+    if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (double*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
+    else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (double*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
+  }
+  return VS_OK;
+}
+
+
+// ------------------------------------------------------------------ device-driven entry points
+extern "C" int vs_lbfgs_dev_init_host(vs_lbfgs_dev* st, int n_slots) {
+  if (!st || n_slots < 4 || n_slots > 2 * VS_LBFGS_MAX_HIST + 8) return VS_ERR_INVALID;
+  memset(st, 0, sizeof(*st));
+  st->H_diag = 1.0;
+  st->n_free = n_slots;
+  for (int i = 0; i < n_slots; ++i) st->free_slots[i] = n_slots - 1 - i;     // slot 0 is handed out first
+  return VS_OK;
+}
+
+extern "C" size_t vs_lbfgs_dev_workspace(int64_t n) {
+  if (n <= 0) return 0;
+  return (size_t)num_chunks(n) * (kBase + 6 * (size_t)VS_LBFGS_MAX_HIST) * sizeof(double) + 64;
+}
+
+extern "C" int vs_lbfgs_dev_dots(vs_lbfgs_dev* state, int64_t n, const double* g, const double* g_prev, void* hist,
+                                 int64_t hist_stride, int hist_f32, void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(state && n > 0 && g && g_prev && hist && hist_stride >= n, VS_ERR_INVALID, "vs_lbfgs_dev_dots: bad arguments");
+  VS_REQUIRE(workspace && workspace_bytes >= vs_lbfgs_dev_workspace(n) && ((uintptr_t)workspace & 7) == 0, VS_ERR_WORKSPACE,
+             "vs_lbfgs_dev_dots: workspace too small or misaligned");
+  VS_REQUIRE(n < (1ll << 40), VS_ERR_UNSUPPORTED, "vs_lbfgs_dev_dots: vector too long");
+  const int nout = kBase + 6 * VS_LBFGS_MAX_HIST;
+  const int chunks = num_chunks(n);
+  double* part = reinterpret_cast<double*>(workspace);
+  Slots sl;
+  sl.s[0] = 0;
+  int rc = hist_f32 ? launch_dots<float>(n, g, g_prev, nullptr, nullptr, hist, hist_stride, sl, 0, nout, part, chunks, stream, state)
+                    : launch_dots<double>(n, g, g_prev, nullptr, nullptr, hist, hist_stride, sl, 0, nout, part, chunks, stream, state);
+  if (rc) return rc;
+  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, (double*)nullptr, state);
+  return VS_OK;
+}
+
+extern "C" int vs_lbfgs_dev_update(vs_lbfgs_dev* state, const double* loss, double lr, double tolerance_grad, double tolerance_change,
+                                   int max_eval, int history_size, int first_eval, void* stream) {
+  VS_REQUIRE(state && loss, VS_ERR_INVALID, "vs_lbfgs_dev_update: null pointer");
+  VS_REQUIRE(history_size >= 1 && history_size <= VS_LBFGS_MAX_HIST, VS_ERR_UNSUPPORTED, "vs_lbfgs_dev_update: history_size outside 1..%d",
+             VS_LBFGS_MAX_HIST);
+  VS_LAUNCH(update_kernel, 1, 128, 0, stream, state, loss, lr, tolerance_grad, tolerance_change, max_eval, history_size, first_eval);
+  return VS_OK;
+}
+
+extern "C" int vs_lbfgs_dev_direction(vs_lbfgs_dev* state, int64_t n, const double* g, void* hist, int64_t hist_stride, int hist_f32,
+                                      double* x, void* stream) {
+  VS_REQUIRE(state && n > 0 && g && hist && x && hist_stride >= n, VS_ERR_INVALID, "vs_lbfgs_dev_direction: bad arguments");
+  long long blocks = ceil_div(n, 256 * 4);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  Slots sl;
+  sl.s[0] = 0;
+  const bool vec = ((((uintptr_t)g | (uintptr_t)hist | (uintptr_t)x) & 15) == 0) && hist_stride % 4 == 0;
+  if (hist_f32) {
+    CoefT<float> cf;
+    cf.c[0] = 0.f;
+    if (vec) { VS_LAUNCH((direction_kernel<float, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (float*)nullptr, (unsigned long long*)nullptr, state); }
+    else { VS_LAUNCH((direction_kernel<float, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (float*)nullptr, (unsigned long long*)nullptr, state); }
+  } else {
+    CoefT<double> cf;
+    cf.c[0] = 0.0;
+    if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, state); }
+    else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, state); }
   }
   return VS_OK;
 }

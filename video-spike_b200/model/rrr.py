@@ -64,6 +64,19 @@ def get_device():
 
 
 _SIDE_STREAMS = {}
+_PINNED_STAGES = {}
+
+
+def _pinned_stage(numel):
+    """A reusable pinned float64 staging buffer of `numel` elements (allocating pinned memory costs milliseconds, so it
+    is cached per size).  The event guards reuse: the previous upload out of the buffer must have finished."""
+    st = _PINNED_STAGES.get(numel)
+    if st is None:
+        st = _PINNED_STAGES[numel] = {"buf": torch.empty(numel, dtype=torch.float64).pin_memory(), "event": torch.cuda.Event()}
+    else:
+        st["event"].synchronize()
+    return st
+
 
 
 def _side_stream(device):
@@ -164,11 +177,13 @@ class _PackedSplit:
 
 
 class RRRGD():
-    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None, operand=None):
+    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None, operand=None, device=None):
         """`init_plan` (session-sharded joint model, parallel.py): [(eid, N, ncoef, T)] of ALL sessions of the joint
         model in the reference's iteration order.  The init stream is drawn for every session in that order so that
         this rank's U_s and the shared V are bit-identical to the single-process joint model; sessions that are not
-        in `train_data` are drawn and dropped."""
+        in `train_data` are drawn and dropped.
+        `device`: create the parameters directly on that CUDA device -- the init stream is generated into a pinned
+        staging buffer and uploaded asynchronously, instead of CPU parameters + a later blocking `.to(device)`."""
         self.l2 = l2
         self.eids = list(train_data.keys())
         self.withbias = True
@@ -190,7 +205,14 @@ class RRRGD():
         self.eids = [eid for eid, *_ in init_plan if eid in train_data]
         for eid, N, ncoef, T in init_plan:
             scale = float(np.sqrt(T * ncomp))
-            U = rng.normal((N, ncoef - 1, ncomp), scale)
+            if device is not None and eid in train_data:
+                stage = _pinned_stage(N * (ncoef - 1) * ncomp)
+                rng.normal((N, ncoef - 1, ncomp), scale, out=stage["buf"])
+                U = torch.empty((N, ncoef - 1, ncomp), dtype=torch.float64, device=device)
+                U.copy_(stage["buf"].view(N, ncoef - 1, ncomp), non_blocking=True)
+                stage["event"].record(torch.cuda.current_stream(device))
+            else:
+                U = rng.normal((N, ncoef - 1, ncomp), scale)
             V = rng.normal((ncomp, T), scale)                  # redrawn per eid, the last one is kept (rrr.py:43,49)
             if eid not in train_data:
                 continue
@@ -206,11 +228,13 @@ class RRRGD():
         params['V'] = np2param(V)
         self.n_comp, self.T = params['V'].shape
         self.model = nn.ParameterDict(params)
+        if device is not None:
+            self.model.to(device)                 # U is already there; V and b are a few KB
         self._packed = {}
         self._ws = None
         self.n_closure_evals = 0
 
-    def make_optimizer(self, history_dtype=None):
+    def make_optimizer(self, history_dtype=None, device_driven=None):
         """The optimiser `train_model_main` builds (rrr.py:199: `optim.LBFGS(params)` with torch's defaults).
         Curvature-pair storage follows the operand precision: float32 with plain-bf16 operands (planes == 1, where a
         closure evaluation carries ~1e-3 of rounding anyway), float64 with residual planes (parity mode).  Override
@@ -221,7 +245,9 @@ class RRRGD():
                 history_dtype = torch.float32 if env.lower() in ("f32", "float32", "fp32") else torch.float64
             else:
                 history_dtype = torch.float32 if self.planes == 1 else torch.float64
-        return FusedLBFGS(self.model.parameters(), history_dtype=history_dtype)
+        if device_driven is None:     # decisions on the device, no host sync per iteration (optim.FusedLBFGS); VS_LBFGS_DEVICE=0 disables
+            device_driven = os.environ.get("VS_LBFGS_DEVICE", "1") != "0"
+        return FusedLBFGS(self.model.parameters(), history_dtype=history_dtype, device_driven=device_driven)
 
     def train(self):
         self.model.train()
@@ -390,9 +416,9 @@ def train_model(model, train_data, optimizer, model_fname, save=True):
 
 
 def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None, engine=None, operand=None):
-    """rrr.py:192-202."""
-    area_model = RRRGD(train_data, n_comp, l2=l2, planes=planes, engine=engine, operand=operand)
+    """rrr.py:192-202 (the parameters are created on the device directly; `.to(device)` is then a no-op)."""
     device = get_device()
+    area_model = RRRGD(train_data, n_comp, l2=l2, planes=planes, engine=engine, operand=operand, device=device)
     area_model.to(device)
     print(f"training on device: {device}")
     optimizer = area_model.make_optimizer()                    # torch.optim.LBFGS semantics, device-side vector algebra

@@ -145,14 +145,23 @@ class FusedLBFGS(torch.optim.Optimizer):
     `history_dtype=torch.float32` stores the curvature pairs (s_i, y_i) in float32 (all arithmetic stays float64):
     half the HBM traffic of both passes; the default float64 reproduces torch.optim.LBFGS to rounding.
 
+    `device_driven=True` moves the decisions themselves (memory update, two-loop recursion, step length, termination
+    tests) into a one-thread kernel working on a device-resident state (vs_lbfgs_dev_*): a whole `step(closure)` is then
+    ENQUEUED without any host<->device synchronisation -- the host only runs ahead calling the closure -- and the state is
+    read back once at the end.  After the state says "done" the remaining launches are no-ops, so an early-terminated
+    step still calls the closure max_iter times (on unchanged parameters); `state["func_evals"]` / `["n_iter"]` report
+    the logical counts.  Same arithmetic, same order: trajectories agree with the host-driven mode to rounding.
+
     A closure that wants to avoid allocations writes gradients INTO the existing `p.grad` views
     (model.rrr.RRRGD.loss_and_grad does); autograd closures work too (`zero_grad()` zeroes the views)."""
 
     def __init__(self, params, lr=1, max_iter=20, max_eval=None, tolerance_grad=1e-7, tolerance_change=1e-9,
-                 history_size=100, line_search_fn=None, history_dtype=torch.float64):
+                 history_size=100, line_search_fn=None, history_dtype=torch.float64, device_driven=False):
         if history_dtype not in (torch.float64, torch.float32):
             raise ValueError("history_dtype must be torch.float64 or torch.float32")
         self._hdtype = history_dtype
+        self._device_driven = bool(device_driven)
+        self._dev = None
         if line_search_fn is not None:
             raise vs.VsError("FusedLBFGS implements the fixed-step variant only (the reference never sets line_search_fn)")
         if history_size > 100:
@@ -298,8 +307,88 @@ class FusedLBFGS(torch.optim.Optimizer):
         host = self._scal.cpu().numpy()
         return host[:k], float(host[-2]), float(host[-1])
 
+    # ---- device-driven step ----------------------------------------------------------------------------------
+    _DEV_HEADER = 1728        # leading bytes of vs_lbfgs_dev: counters, flags, slot tables, scalars (up to and including dmax)
+
+    def _dev_state(self, need_slots):
+        """Device buffer holding a vs_lbfgs_dev (+ float64 views of its `out` block and `dmax`), with a history buffer
+        of at least `need_slots` slots.  Grows between steps: new slot ids are appended to the state's free list."""
+        dev_t = self._flat["x"].device
+        n = self._flat["n"]
+        npad = (n + 3) // 4 * 4
+        need_slots = min(need_slots, 2 * vs.LBFGS_MAX_HIST + 8)
+        if self._dev is None:
+            host = vs.LbfgsDev()
+            vs.check(vs.lib.vs_lbfgs_dev_init_host(C.byref(host), need_slots))
+            raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(dev_t)
+            k = 8 + 6 * vs.LBFGS_MAX_HIST
+            self._dev = {"raw": raw, "n_slots": need_slots, "host": host,
+                         "out": raw[vs.LbfgsDev.out.offset:vs.LbfgsDev.out.offset + 8 * k].view(torch.float64),
+                         "dmax": raw[vs.LbfgsDev.dmax.offset:vs.LbfgsDev.dmax.offset + 8].view(torch.float64),
+                         "ws": torch.empty(int(vs.lib.vs_lbfgs_dev_workspace(n)), dtype=torch.uint8, device=dev_t)}
+            self._hist = torch.empty((need_slots, npad), dtype=self._hdtype, device=dev_t)
+        elif need_slots > self._dev["n_slots"]:
+            old_n, host = self._dev["n_slots"], self._dev["host"]
+            grown = torch.empty((need_slots, npad), dtype=self._hdtype, device=dev_t)
+            grown[:old_n].copy_(self._hist)
+            self._hist = grown
+            for s_id in range(old_n, need_slots):
+                host.free_slots[host.n_free] = s_id
+                host.n_free += 1
+            head = torch.frombuffer(bytearray(bytes(host)[:self._DEV_HEADER]), dtype=torch.uint8)
+            self._dev["raw"][:self._DEV_HEADER].copy_(head.to(dev_t))
+            self._dev["n_slots"] = need_slots
+        return self._dev
+
+    def _read_dev_state(self):
+        head = self._dev["raw"][:self._DEV_HEADER].cpu().numpy().tobytes()
+        host = vs.LbfgsDev.from_buffer_copy(head.ljust(C.sizeof(vs.LbfgsDev), b"\0"))
+        self._dev["host"] = host
+        return host
+
+    def _reduce_dev_scalars(self):
+        """Hook (parallel.ShardedLBFGS): combine the state's `out` block and `dmax` across ranks on the device."""
+
+    @torch.no_grad()
+    def _step_device_driven(self, closure):
+        closure = torch.enable_grad()(closure)
+        group = self.param_groups[0]
+        lr, max_iter, max_eval = float(group["lr"]), group["max_iter"], group["max_eval"]
+        tol_g, tol_c, hsize = float(group["tolerance_grad"]), float(group["tolerance_change"]), group["history_size"]
+        fl = self._bind()
+        n = fl["n"]
+        state = self.state[self._params[0]]
+        m_now = self._dev["host"].m if self._dev is not None else 0
+        dev = self._dev_state(2 * min(hsize, m_now + max_iter) + 6)
+        hist, f32 = self._hist, int(self._hdtype == torch.float32)
+        sp, st = vs.ptr(dev["raw"]), vs.stream
+        orig_loss = None
+        for it in range(max_iter):
+            # the closure writes the new gradient into the buffer that does not hold the previous one
+            prev = state.get("prev_buf")
+            if prev is not None and fl["cur"] == prev:
+                self._point_grads(1 - prev)
+            loss_t = closure()
+            if orig_loss is None:
+                orig_loss = loss_t
+            g = fl["g"][fl["cur"]]
+            g_prev = fl["g"][1 - fl["cur"]]
+            lt = torch.as_tensor(loss_t).detach().reshape(1).double()
+            vs.check(vs.lib.vs_lbfgs_dev_dots(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), hist.shape[1], f32, vs.ptr(dev["ws"]),
+                                              dev["ws"].numel(), st()))
+            self._reduce_dev_scalars()
+            vs.check(vs.lib.vs_lbfgs_dev_update(sp, vs.ptr(lt), lr, tol_g, tol_c, int(max_eval), int(hsize), int(it == 0), st()))
+            vs.check(vs.lib.vs_lbfgs_dev_direction(sp, n, vs.ptr(g), vs.ptr(hist), hist.shape[1], f32, vs.ptr(fl["x"]), st()))
+            state["prev_buf"] = fl["cur"]
+        host = self._read_dev_state()                        # the only synchronisation of the step
+        state["func_evals"], state["n_iter"] = int(host.func_evals), int(host.total_iter)
+        state["dev_done"] = int(host.done)
+        return orig_loss
+
     @torch.no_grad()
     def step(self, closure):
+        if self._device_driven:
+            return self._step_device_driven(closure)
         import numpy as np
         closure = torch.enable_grad()(closure)
         group = self.param_groups[0]

@@ -51,6 +51,8 @@ class ShardedLBFGS(FusedLBFGS):
 
     def __init__(self, shared, local, group=None, **kw):
         shared, local = list(shared), list(local)
+        if kw.get("device_driven"):
+            raise vs.VsError("ShardedLBFGS is host-driven (its inner products are all-reduced between the two passes)")
         super().__init__(shared + local, **kw)                 # shared block first in the flat vector
         self._n_shared = sum(p.numel() for p in shared)
         self._group = group

@@ -35,6 +35,23 @@ class Mlp(C.Structure):
                 ("W", "b", "mW", "vW", "mb", "vb", "act", "gact", "gW", "gb")]
 
 
+LBFGS_MAX_HIST = 100
+
+
+class LbfgsDev(C.Structure):
+    """vs_lbfgs_dev: the device-resident state of the device-driven L-BFGS (include/vs_b200.h)."""
+    _fields_ = [("m", C.c_int32), ("n_iter", C.c_int32), ("total_iter", C.c_int32), ("func_evals", C.c_int32),
+                ("cur_evals", C.c_int32), ("done", C.c_int32), ("have_prev", C.c_int32), ("have_s", C.c_int32),
+                ("s_cur", C.c_int32), ("y_next", C.c_int32), ("n_free", C.c_int32), ("pad0", C.c_int32),
+                ("free_slots", C.c_int32 * (2 * LBFGS_MAX_HIST + 8)),
+                ("s_slots", C.c_int32 * LBFGS_MAX_HIST), ("y_slots", C.c_int32 * LBFGS_MAX_HIST),
+                ("H_diag", C.c_double), ("prev_loss", C.c_double), ("loss", C.c_double), ("t", C.c_double),
+                ("gtd", C.c_double), ("dmax", C.c_double),
+                ("coef", C.c_double * (2 * LBFGS_MAX_HIST + 2)),
+                ("out", C.c_double * (8 + 6 * LBFGS_MAX_HIST)),
+                ("SY", C.c_double * (LBFGS_MAX_HIST * LBFGS_MAX_HIST)), ("YY", C.c_double * (LBFGS_MAX_HIST * LBFGS_MAX_HIST))]
+
+
 class RrrDims(C.Structure):
     _fields_ = [("K", C.c_int64), ("T", C.c_int64), ("C1", C.c_int64), ("N", C.c_int64), ("r", C.c_int64),
                 ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64), ("fmt", C.c_int32)]
@@ -80,6 +97,11 @@ def _load():
         "vs_lbfgs_workspace": (sz, [i64, i32]),
         "vs_lbfgs_dots": (C.c_int, [i64, vp, vp, vp, vp, vp, i64, i32, vp, vp, i32, vp, vp, sz, vp]),
         "vs_lbfgs_direction": (C.c_int, [i64, vp, vp, i64, i32, vp, vp, i32, vp, dbl, vp, vp, vp, vp]),
+        "vs_lbfgs_dev_init_host": (C.c_int, [C.POINTER(LbfgsDev), i32]),
+        "vs_lbfgs_dev_workspace": (sz, [i64]),
+        "vs_lbfgs_dev_dots": (C.c_int, [vp, i64, vp, vp, vp, i64, i32, vp, sz, vp]),
+        "vs_lbfgs_dev_update": (C.c_int, [vp, vp, dbl, dbl, dbl, i32, i32, i32, vp]),
+        "vs_lbfgs_dev_direction": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
         "vs_host_lbfgs_two_loop": (C.c_int, [i32, dbl, vp, vp, vp, vp, i32, dbl, vp, vp]),
         "vs_host_rng_seed": (C.c_int, [vp, C.c_uint32]),
         "vs_host_rng_normal": (C.c_int, [vp, i64, dbl, vp, i32]),
@@ -186,10 +208,17 @@ class LegacyNormalStream:
         self._state = C.create_string_buffer(self.STATE_BYTES)
         check(lib.vs_host_rng_seed(self._state, int(seed) & 0xFFFFFFFF))
 
-    def normal(self, size, divisor: float = 1.0, threads: int = 0):
+    def normal(self, size, divisor: float = 1.0, threads: int = 0, out=None):
+        """`out`: optional C-contiguous float64 array / CPU tensor of the right size to fill (e.g. pinned memory)."""
         import numpy as np
-        out = np.empty(size, dtype=np.float64)
-        check(lib.vs_host_rng_normal(self._state, out.size, float(divisor), out.ctypes.data_as(C.c_void_p), int(threads)))
+        if out is None:
+            out = np.empty(size, dtype=np.float64)
+            ptr, count = out.ctypes.data, out.size
+        else:
+            ptr, count = (out.data_ptr(), out.numel()) if isinstance(out, torch.Tensor) else (out.ctypes.data, out.size)
+            if count != int(np.prod(size)):
+                raise VsError("LegacyNormalStream.normal: `out` has the wrong number of elements")
+        check(lib.vs_host_rng_normal(self._state, count, float(divisor), C.c_void_p(ptr), int(threads)))
         return out
 
     def export_to_numpy(self):
