@@ -292,6 +292,7 @@ typedef struct {
 
 /* fills *state_host for an empty memory over `n_slots` history slots (>= 2*min(history_size, iterations) + 4) */
 int vs_lbfgs_dev_init_host(vs_lbfgs_dev* state_host, int n_slots);
+size_t vs_lbfgs_dev_state_bytes(void);   /* sizeof(vs_lbfgs_dev), for bindings that mirror the struct */
 size_t vs_lbfgs_dev_workspace(int64_t n);
 /* one pass over g (and g_prev, the latest step, the history): y, all inner products -> state->out */
 int vs_lbfgs_dev_dots(vs_lbfgs_dev* state, int64_t n, const double* g, const double* g_prev, void* hist,

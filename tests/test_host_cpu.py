@@ -34,6 +34,17 @@ def test_python_binding_covers_the_header():
     assert sorted(vsb200.EXPORTS) == _declared_symbols()
 
 
+def test_ctypes_structs_mirror_the_header():
+    """The device-resident L-BFGS state is parsed on the host: the ctypes mirror must have the C layout."""
+    import ctypes as C
+    import vsb200 as vs
+    assert C.sizeof(vs.LbfgsDev) == vs.lib.vs_lbfgs_dev_state_bytes()
+    host = vs.LbfgsDev()
+    assert vs.lib.vs_lbfgs_dev_init_host(C.byref(host), 46) == 0
+    assert (host.n_free, host.free_slots[45], host.free_slots[0], host.H_diag, host.m, host.done) == (46, 0, 45, 1.0, 0, 0)
+    assert vs.LbfgsDev.dmax.offset + 8 <= 1728 < vs.LbfgsDev.out.offset      # what FusedLBFGS reads back / re-uploads
+
+
 def test_no_cpu_fallback():
     """CPU tensors are refused by every wrapper: the product path cannot silently run without the GPU."""
     import vsb200 as vs

@@ -546,6 +546,8 @@ extern "C" int vs_lbfgs_dev_init_host(vs_lbfgs_dev* st, int n_slots) {
   return VS_OK;
 }
 
+extern "C" size_t vs_lbfgs_dev_state_bytes(void) { return sizeof(vs_lbfgs_dev); }
+
 extern "C" size_t vs_lbfgs_dev_workspace(int64_t n) {
   if (n <= 0) return 0;
   return (size_t)num_chunks(n) * (kBase + 6 * (size_t)VS_LBFGS_MAX_HIST) * sizeof(double) + 64;

@@ -98,6 +98,7 @@ def _load():
         "vs_lbfgs_dots": (C.c_int, [i64, vp, vp, vp, vp, vp, i64, i32, vp, vp, i32, vp, vp, sz, vp]),
         "vs_lbfgs_direction": (C.c_int, [i64, vp, vp, i64, i32, vp, vp, i32, vp, dbl, vp, vp, vp, vp]),
         "vs_lbfgs_dev_init_host": (C.c_int, [C.POINTER(LbfgsDev), i32]),
+        "vs_lbfgs_dev_state_bytes": (sz, []),
         "vs_lbfgs_dev_workspace": (sz, [i64]),
         "vs_lbfgs_dev_dots": (C.c_int, [vp, i64, vp, vp, vp, i64, i32, vp, sz, vp]),
         "vs_lbfgs_dev_update": (C.c_int, [vp, vp, dbl, dbl, dbl, i32, i32, i32, vp]),
