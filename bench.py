@@ -219,12 +219,14 @@ def reference_arm(args, rank, world):
 
 # ----------------------------------------------------------------------------- configs
 def rrr_config(args, world):
-    return {"workload": "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
+    return {"workload": "rrr_joint_fit, shared V across sessions (BASELINE configs[2])" if args.joint else "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
             "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes,
             "operand_format": (os.environ.get("VS_RRR_OPERAND") or "bf16") + " (16-bit tensor-core operands, fp32 accumulate in TMEM)", "lbfgs": ("1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64")
-                     + (", device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else ", host-driven"),
-            "sessions": world, "parallelism": f"session-sharded x{world}" if world > 1 else "single GPU",
+                     + (", host-driven with sharded inner products" if args.joint else ", device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else ", host-driven"),
+            "sessions": world,
+            "parallelism": (f"joint model over {world} sessions, one per GPU: shared V, [dV, loss] and L-BFGS inner products all-reduced (NCCL)"
+                            if args.joint else (f"independent sessions, one per GPU x{world} (no collective)" if world > 1 else "single GPU")),
             "l2_cache": "operands (1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
 
 
@@ -250,18 +252,28 @@ def run_rrr(args, rank, world, local):
 
     # ---- resident-input measurement: operands packed once, fit repeated
     entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=args.planes, device=dev)
-    td = {"s": entry}
-    model = RRRGD(td, 3, l2=100.0, planes=args.planes)
+    # --joint (BASELINE configs[2]): ONE model over all ranks' sessions with a shared V (src/model/rrr.py:37-49); rank r holds
+    # session r's U, b and operands, [dV, loss] and the L-BFGS inner products are all-reduced over NCCL (parallel.py)
+    joint = bool(args.joint)
+    eid = f"s{rank:02d}" if joint else "s"
+    plan = [(f"s{r:02d}", N, F + 1, 100) for r in range(world)] if joint else None
+    td = {eid: entry}
+    model = RRRGD(td, 3, l2=100.0, planes=args.planes, init_plan=plan)
     model.to(dev)
     model_fmt = model.fmt
     init = {k: v.detach().clone() for k, v in model.model.items()}
+    if joint:
+        from parallel import train_joint_model
 
     def one_fit():
         with torch.no_grad():
             for k, v in init.items():
                 model.model[k].copy_(v)
-        opt = model.make_optimizer()                       # what train_model_main builds (rrr.py:199 semantics)
-        _, res = train_model(model, td, opt, "tmp", save=False)
+        if joint:
+            _, res = train_joint_model(model, td)
+        else:
+            opt = model.make_optimizer()                   # what train_model_main builds (rrr.py:199 semantics)
+            _, res = train_model(model, td, opt, "tmp", save=False)
         return res["mse_val_mean"]
 
     for _ in range(args.warmup):
@@ -303,7 +315,7 @@ def run_rrr(args, rank, world, local):
     # ---- parity of the timed configuration (outside every timed region): the same fit with 3 operand planes and a float64
     # L-BFGS history -- the mode the tests pin against the float64 reference to ~1e-6 -- on the same session
     parity = None
-    if rank == 0 and not args.no_parity and args.planes == 1:
+    if rank == 0 and not args.no_parity and args.planes == 1 and not joint:
         entry3 = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=3, device=dev)
         m3 = RRRGD({"s": entry3}, 3, l2=100.0, planes=3)
         m3.to(dev)
@@ -332,7 +344,12 @@ def run_rrr(args, rank, world, local):
 
     # ---- end to end: pinned host uint8 frames -> R0 on device -> init -> fit -> validation loss on the host
     def e2e_fit():
-        m, res, _ = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3, planes=args.planes)
+        if joint:
+            ent = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=args.planes, device=dev)
+            m = RRRGD({eid: ent}, 3, l2=100.0, planes=args.planes, init_plan=plan, device=dev)
+            _, res = train_joint_model(m, {eid: ent})
+        else:
+            m, res, _ = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3, planes=args.planes)
         return float(res["mse_val_mean"])                    # device -> host read of the result
 
     del model, td, entry
@@ -358,7 +375,8 @@ def run_rrr(args, rank, world, local):
     e2e = {"value": world * K * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
            "ms_per_step": e2e_s * 1e3, "statistic": f"median of {n_e2e} fits", "mean_ms_per_step": mean_s * 1e3,
            "ms_each_rank0": [round(x, 2) for x in each],
-           "path": "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)"}
+           "path": ("pack_session_from_frames(pinned uint8 frames) -> RRRGD(init_plan) -> parallel.train_joint_model -> float(mse_val_mean)" if joint
+                    else "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)")}
 
     if rank != 0:
         return
@@ -514,6 +532,7 @@ def main():
     ap.add_argument("--cpu-trials", dest="cpu_trials", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--joint", action="store_true", help="rrr: one joint model with a shared V over all ranks' sessions (configs[2])")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 5 if args.workload == "rrr" else 50
