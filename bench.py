@@ -304,7 +304,7 @@ def run_rrr(args, rank, world, local):
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_kernel (tcgen05 kind::f16, 16-bit operands)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair, 16-bit operands)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak if peak else None,
             "traffic": ncu_traffic(f"rrr_K{K}_F{F}_N{N}_planes{args.planes}"), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} bf16_tflops_sustained",
             "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),

@@ -67,6 +67,17 @@ def test_gemm_tcgen05_bf16(vs, cuda, M, N, K):
     torch.testing.assert_close(Cm, Cs, rtol=1e-4, atol=2e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(19072, 432, 640), (129, 32, 64), (2500, 208, 4096), (640, 1000, 320)])
+def test_gemm_tcgen05_cta_pairs(vs, cuda, M, N, K):
+    """cta_group::2 route (two CTAs share each B tile): odd m-tile counts, one and two UMMA chunks per tile, several n-tiles,
+    more CTA pairs than the 74 TPCs; integer-valued operands make every product and partial sum exact in fp32."""
+    torch.manual_seed(21)
+    A = torch.randint(-4, 5, (M, K), device=cuda).to(torch.bfloat16)
+    B = torch.randint(-4, 5, (N, K), device=cuda).to(torch.bfloat16)
+    Cm = vs.gemm_tn(A, B, vs.ENGINE_TCGEN05)
+    assert torch.equal(Cm.double(), _gemm_ref(A, B))
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 16, 64), (300, 432, 1000), (130, 448, 520)])
 def test_gemm_tcgen05_f16(vs, cuda, M, N, K):
     """IEEE-half operands (kind::f16 with a/b format 0): products exact in fp32, same tolerance as bf16."""

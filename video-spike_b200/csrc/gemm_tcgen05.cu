@@ -283,6 +283,219 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// Same contract as gemm_tn_kernel for 16-bit operands, but two CTAs of one TPC share every B tile: CTA r of the
+// pair owns m-tile 2*pair + r (its own 128 rows of A) and HALF of each B chunk; the leader's tcgen05.mma.cta_group::2
+// (UMMA 256 x N) reads both halves, accumulators land in each CTA's own TMEM.  Per k-block a CTA now fetches
+// 16 KB + BN/2 * 128 B instead of 16 KB + BN * 128 B, so the ring holds 5 stages instead of 3 at BN = 432 and the
+// L2 -> shared-memory traffic drops by 39 %: the single-CTA kernel was latency-bound on its 3-stage ring
+// (tensor pipe 67-79 % active, profiles/r01_ncu_full_prof_rrr_gemm.csv).
+struct KParams2 {
+  int M, N, BN, n_tiles, m_tiles;
+  int nchunk;          // UMMA instructions per K-step (1 or 2)
+  int cn[2];           // UMMA N of each chunk (whole pair)
+  int coff[2];         // first tile column of each chunk
+  int num_kb, kb_per_split, n_pass;
+  int pa[kMaxPass], pb[kMaxPass];
+  int stages, tmem_cols, f16;
+  float* C;
+  long long ldc, split_stride;
+  int tail_unit0, tail_splits, tail_kb_per_split;   // pair units >= tail_unit0 are split along K (n_tiles == 1 only)
+  float* tail_ws;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_pair(bool f16, int n) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmB1, const KParams2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int h0 = p.cn[0] >> 1, h1 = p.nchunk > 1 ? (p.cn[1] >> 1) : 0;   // B rows this CTA holds per chunk
+  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)(h0 + h1) * KB_BYTES;
+  const uint32_t tiles0 = base + CTRL_BYTES;
+  const uint32_t bar_full0 = base;
+  const uint32_t bar_empty0 = base + 8u * 16;
+  const uint32_t bar_tmem = base + 8u * 32;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 33);
+
+  int unit = blockIdx.x >> 1, split = blockIdx.y, kbps = p.kb_per_split;
+  const bool is_tail = p.tail_splits > 1 && unit >= p.tail_unit0;
+  if (is_tail) {
+    const int u = unit - p.tail_unit0;
+    unit = p.tail_unit0 + u / p.tail_splits;
+    split = u % p.tail_splits;
+    kbps = p.tail_kb_per_split;
+  }
+  const int m_pair = unit / p.n_tiles, n_tile = unit % p.n_tiles;
+  const int m_tile = 2 * m_pair + rank;                              // may be one past the end (odd tile count)
+  const int m_load = m_tile < p.m_tiles ? m_tile : p.m_tiles - 1;    // keep the TMA box inside the tensor
+  const int kb0 = split * kbps;
+  const int kb1 = min(p.num_kb, kb0 + kbps);
+  const int iters = (kb1 > kb0 ? kb1 - kb0 : 0) * p.n_pass;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full0 + 8u * s, 1);
+      mbar_init(bar_empty0 + 8u * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 33), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs' barriers are initialised before either signals the other
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane per CTA): own A rows + own halves of the B chunks, counted on the leader's barrier =====
+    if (lane == 0) {
+      int it = 0;
+      for (int ps = 0; ps < p.n_pass; ++ps) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+          const uint32_t a_dst = tiles0 + s * stage_bytes;
+          const uint32_t b_dst = a_dst + A_TILE_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, 2u * stage_bytes);
+          const uint32_t full = mapa_cluster(bar_full0 + 8u * s, 0);
+          tma_load_3d_pair(a_dst, &tmA, full, kb * 64, m_load * BM, p.pa[ps]);
+          tma_load_3d_pair(b_dst, &tmB0, full, kb * 64, n_tile * p.BN + p.coff[0] + rank * h0, p.pb[ps]);
+          if (h1 > 0)
+            tma_load_3d_pair(b_dst + (uint32_t)h0 * KB_BYTES, &tmB1, full, kb * 64, n_tile * p.BN + p.coff[1] + rank * h1, p.pb[ps]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one lane of the leader CTA drives the tensor cores of both SMs =====
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc0 = make_idesc_pair(p.f16 != 0, p.cn[0]);
+      const uint32_t idesc1 = make_idesc_pair(p.f16 != 0, p.nchunk > 1 ? p.cn[1] : 16);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(bar_full0 + 8u * s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = tiles0 + s * stage_bytes;
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        const uint64_t da = make_smem_desc(a_addr);
+        const uint64_t db0 = make_smem_desc(b_addr);
+        const uint64_t db1 = make_smem_desc(b_addr + (uint32_t)h0 * KB_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          tc_mma_pair(tmem_base + (uint32_t)p.coff[0], da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc0, acc);
+          if (h1 > 0) tc_mma_pair(tmem_base + (uint32_t)p.coff[1], da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc1, acc);
+        }
+        tc_commit_pair(bar_empty0 + 8u * s);   // frees this slot in both CTAs
+      }
+      if (iters > 0) tc_commit_pair(bar_tmem); // accumulators complete in both CTAs
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global (each CTA drains its own 128 rows) =====
+    const int q = warp & 3;
+    const int row = m_tile * BM + q * 32 + lane;
+    if (iters > 0) {
+      mbar_wait(bar_tmem, 0);
+      tc_fence_after();
+    }
+    if (is_tail) {
+      float* trow = p.tail_ws + ((long long)(((unit - p.tail_unit0) * 2 + rank) * p.tail_splits + split) * BM + (q * 32 + lane)) * p.BN;
+      for (int c = 0; c < p.BN; c += 16) {
+        float v[16];
+        if (iters > 0) {
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(trow + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else {
+      float* crow = p.C + (long long)split * p.split_stride + (long long)row * p.ldc;
+      for (int c = 0; c < p.BN; c += 16) {
+        float v[16];
+        if (iters > 0) {
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        const int col = n_tile * p.BN + c;
+        if (row < p.M) {
+          if (col + 16 <= p.N && ((p.ldc & 3) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(crow + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col + i < p.N) crow[col + i] = v[i];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();            // the peer may still read this CTA's shared memory / signal its barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // C tile = ordered sum of the tail-wave partial tiles
 __global__ void __launch_bounds__(256) tail_reduce_kernel(const float* __restrict__ ws, int tail_cta0, int splits, int n_tiles, int BN,
                                                           int M, int N, float* __restrict__ C, long long ldc) {
@@ -365,10 +578,87 @@ int pick_bn(long long N) {
   return (int)round_up(ceil_div(n16, tiles), 16);
 }
 
+// CTA-pair route (16-bit operands, at least two m-tiles): see gemm_tn_pair_kernel
+static bool pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VS_GEMM_PAIR");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+static int gemm_tn_pair(const GemmDesc& g, int BN, cudaStream_t stream) {
+  KParams2 p;
+  p.M = (int)g.M; p.N = (int)g.N; p.BN = BN;
+  p.m_tiles = (int)ceil_div(g.M, BM); p.n_tiles = (int)ceil_div(g.N, BN);
+  if (BN <= 256) {
+    p.nchunk = 1; p.cn[0] = BN; p.cn[1] = 0; p.coff[0] = 0; p.coff[1] = 0;
+  } else {
+    p.nchunk = 2; p.cn[0] = (int)round_up(BN / 2, 16); p.cn[1] = BN - p.cn[0]; p.coff[0] = 0; p.coff[1] = p.cn[0];
+  }
+  const int h0 = p.cn[0] / 2, h1 = p.cn[1] / 2;
+  p.num_kb = (int)ceil_div(g.K, 64);
+  int splits = g.splits > 0 ? g.splits : 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (int)ceil_div(p.num_kb, splits);
+  splits = (int)ceil_div(p.num_kb, p.kb_per_split);
+  p.n_pass = g.n_pass;
+  for (int i = 0; i < kMaxPass; ++i) { p.pa[i] = i < g.n_pass ? g.pa[i] : 0; p.pb[i] = i < g.n_pass ? g.pb[i] : 0; }
+  const int stage_bytes = A_TILE_BYTES + (h0 + h1) * KB_BYTES;
+  int stages = (227 * 1024 - CTRL_BYTES - 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  VS_REQUIRE(stages >= 2, VS_ERR_UNSUPPORTED, "tcgen05 GEMM: tile too large for shared memory");
+  p.stages = stages;
+  int tcols = 32;
+  while (tcols < BN) tcols <<= 1;
+  p.tmem_cols = tcols;
+  p.f16 = g.f16 ? 1 : 0;
+  p.C = g.C; p.ldc = g.ldc; p.split_stride = g.split_stride;
+  VS_REQUIRE(splits == 1 || g.split_stride >= g.M * g.ldc, VS_ERR_INVALID, "split-K needs split_stride >= M*ldc");
+
+  CUtensorMap tmA, tmB0, tmB1;
+  int rc = make_map(&tmA, g.A, false, g.f16, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB0, g.B, false, g.f16, h0);
+  if (rc) return rc;
+  rc = make_map(&tmB1, g.B, false, g.f16, h1 > 0 ? h1 : h0);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)CTRL_BYTES + 1024 + (size_t)stages * stage_bytes;
+  const int pair_slots = kNumSMs / 2;
+  const int units = (int)ceil_div(p.m_tiles, 2) * p.n_tiles;
+  dim3 grid(2 * units, splits, 1);
+  p.tail_unit0 = 0; p.tail_splits = 1; p.tail_kb_per_split = p.num_kb; p.tail_ws = nullptr;
+  const int full = (units / pair_slots) * pair_slots, tail = units - full;
+  if (g.balance_ws && splits == 1 && p.n_tiles == 1 && full > 0 && tail > 0 && tail <= pair_slots / 2) {
+    int ts = pair_slots / tail;
+    if (ts > 16) ts = 16;
+    if (ts > p.num_kb / 8) ts = p.num_kb / 8;
+    if (ts >= 2) {
+      p.tail_kb_per_split = (int)ceil_div(p.num_kb, ts);
+      ts = (int)ceil_div(p.num_kb, p.tail_kb_per_split);
+      p.tail_unit0 = full; p.tail_splits = ts; p.tail_ws = reinterpret_cast<float*>(g.balance_ws);
+      grid.x = 2 * (full + tail * ts);
+    }
+  }
+  prof_begin(PROF_GEMM_TC, stream);
+  VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VS_LAUNCH(gemm_tn_pair_kernel, grid, NUM_THREADS, smem, stream, tmA, tmB0, tmB1, p);
+  if (p.tail_splits > 1) {
+    dim3 rg((unsigned)ceil_div((long long)BM * BN / 4, 256), (unsigned)(2 * tail));
+    VS_LAUNCH(tail_reduce_kernel, rg, 256, 0, stream, p.tail_ws, 2 * p.tail_unit0, p.tail_splits, 1, BN, p.M, p.N, p.C, p.ldc);
+  }
+  prof_end(PROF_GEMM_TC, stream);
+  if (g.splits_out) *g.splits_out = splits;
+  return VS_OK;
+}
+
 int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   VS_REQUIRE(gemm_supported(g), VS_ERR_UNSUPPORTED, "tcgen05 GEMM: unsupported operand layout/shape");
   const int BN = g.BN > 0 ? g.BN : pick_bn(g.N);
   VS_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= kMaxBN, VS_ERR_UNSUPPORTED, "tcgen05 GEMM: bad BN %d", BN);
+  if (!g.tf32 && pair_enabled() && g.M > BM && BN >= 32) return gemm_tn_pair(g, BN, stream);
   // TMA boxes are limited to 256 rows: split the B tile into equal boxes of a multiple of 8 rows
   int n_tb = 1;
   while (BN / n_tb > 256 || BN % n_tb != 0 || (BN / n_tb) % 8 != 0) {
