@@ -174,7 +174,9 @@ int vs_mlp_forward(const vs_mlp* net, const uint8_t* frames_u8, const float* x_f
  * Device layout built once per split by vs_rrr_pack (DESIGN.md "RRR data layout"); operand
  * rows are TIME-MAJOR, d = t*K + k, so the trials of one time bin are adjacent:
  *   Xa : planes x (K*T) x ldc   bf16, row d, c contiguous           (forward  A operand)
- *   Xb : planes x C1 x ldr      bf16, row c, d contiguous           (backward A operand)
+ *   Xb : planes x C1 x ldr      bf16, row c, column t*Kp + k        (backward A operand; every time bin is padded with
+ *                               zeros to Kp = K rounded up to 16 trials, so a bin starts 32-byte aligned and ends on a
+ *                               tensor-core K-step: the backward contracts one bin at a time)
  *   xl : (K*T) fp32, the last column of X, indexed by d
  * planes = 1 stores the 16-bit rounding of X; planes = 2 or 3 store the exact residual expansion
  * X ~= X0 + X1 (+ X2), each 16-bit, giving ~16 / ~24 significant bits with bf16 planes.  d.fmt selects bf16 or
@@ -188,7 +190,7 @@ typedef struct {
   int64_t K, T, C1, N, r; /* trials, time bins, features without the bias column, neurons, rank */
   int32_t planes;         /* 1, 2 or 3 */
   int64_t ldc;            /* row pitch of Xa in elements, multiple of 64, >= C1 */
-  int64_t ldr;            /* row pitch of Xb in elements, multiple of 64, >= K*T */
+  int64_t ldr;            /* row pitch of Xb in elements, multiple of 64, >= T * roundup(K, 16) */
   int32_t fmt;            /* VS_OPERAND_*: 16-bit format of every tensor-core operand plane (X, U, residuals) */
 } vs_rrr_dims;
 

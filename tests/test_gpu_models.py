@@ -183,6 +183,33 @@ def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, operand, rtol):
     assert np.abs(err).max() <= 3.0 * rtol * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("K,F,N", [(30, 200, 21), (37, 300, 144), (64, 129, 33), (16, 260, 160), (100, 520, 5), (130, 400, 150)])
+def test_rrr_dense_backward_matches_factorised_and_oracle(vs, cuda, monkeypatch, K, F, N):
+    """The per-time-bin dense backward (rrr_bwd_dense_kernel: D_t in TMEM, rank-one updates by the epilogue warps) against the
+    factorised GEMM-B route and float64: trial counts that are no multiple of 16 (zero-padded residual operand, boxes that start
+    at unaligned columns), odd numbers of 128-row feature tiles, every accumulator width up to 160 neurons."""
+    from model.rrr import RRRGD
+    td = small_rrr_problem(seed=K + N, K=K, Kt=5, F=F, N=N)
+    params = ro.rrr_init(td, 3)
+    rng = np.random.default_rng(0)
+    for k in params:
+        params[k] = params[k] + 0.05 * rng.standard_normal(params[k].shape)
+    loss_o, g_o, _ = ro.loss_and_grad_dense(params, td, 100.0, 0)
+    m = RRRGD(td, 3, l2=100.0, planes=1, engine=2); m.to(cuda)
+    _params_to_model(m, params, cuda)
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("VS_RRR_DENSE", mode)
+        loss = float(m.loss_and_grad(td, 0))
+        assert loss == pytest.approx(loss_o, rel=2e-4)
+        got[mode] = m.model["e1_U"].grad.cpu().numpy().copy()
+    scale = np.abs(g_o["e1_U"]).max()
+    assert np.abs(got["1"] - g_o["e1_U"]).max() <= 3e-3 * scale
+    assert np.abs(got["0"] - g_o["e1_U"]).max() <= 3e-3 * scale
+    assert np.abs(got["1"] - got["0"]).max() <= 5e-3 * scale        # two independent bf16 roundings (R vs R (x) V)
+    assert not np.array_equal(got["1"], got["0"])          # the two routes really are different kernels
+
+
 def test_rrr_closure_is_deterministic(vs, cuda):
     from model.rrr import RRRGD
     td = small_rrr_problem(seed=2, K=20, Kt=6, F=130, N=9)
@@ -271,7 +298,7 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     np.testing.assert_allclose(sd.cpu().numpy().reshape(Tf, F), data["setup"]["std_X_Tv"], rtol=1e-12)
     d = vs.RrrDims(K, T, F, 5, 3, 3, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T))
     Xa = torch.zeros((3, K * T, d.ldc), dtype=torch.bfloat16, device=cuda)
-    Xb = torch.zeros((3, F, d.ldr), dtype=torch.bfloat16, device=cuda)
+    Xb = torch.full((3, F, d.ldr), 7.0, dtype=torch.bfloat16, device=cuda)      # the pack call must zero the pad itself
     xl = torch.empty(K * T, dtype=torch.float32, device=cuda)
     idx = torch.from_numpy(sidx.astype(np.int32)).to(cuda)
     vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb), vs.ptr(xl), None, vs.stream()))
@@ -279,7 +306,11 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     ref = np.ascontiguousarray(data["X"][0][:, :, :-1].transpose(1, 0, 2)).reshape(T * K, F)
     got = Xa.double().sum(0)[:, :F].cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)              # 3 bf16 planes ~ 24 bits
-    np.testing.assert_array_equal(Xb.double().sum(0)[:, :K * T].cpu().numpy().T, got)
+    # Xb: row c, column t*Kp + k with every time bin zero-padded to Kp = K rounded up to 16 trials
+    Kp = (K + 15) // 16 * 16
+    xb = Xb.double().sum(0)[:, :T * Kp].reshape(F, T, Kp).cpu().numpy()
+    np.testing.assert_array_equal(xb[:, :, :K].reshape(F, T * K).T, got)
+    assert not xb[:, :, K:].any()
     assert torch.all(xl == 1.0)
     # the first plane of the expansion is exactly bf16(X) -- frame gather is index-exact
     np.testing.assert_array_equal(Xa[0, :, :F].float().cpu().numpy(), torch.from_numpy(ref).to(torch.bfloat16).float().numpy())
@@ -292,7 +323,7 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     want = torch.from_numpy(ref).to(torch.bfloat16).float().numpy()
     got1 = Xa1[0, :, :F].float().cpu().numpy()
     assert np.mean(got1 != want) < 2e-3 and np.abs(got1 - want).max() <= 2.0 ** -7 * np.abs(want).max()
-    np.testing.assert_array_equal(Xb1[0, :, :K * T].float().cpu().numpy().T, got1)
+    np.testing.assert_array_equal(Xb1[0, :, :T * Kp].float().reshape(F, T, Kp)[:, :, :K].reshape(F, T * K).cpu().numpy().T, got1)
     # y: gaussian smoothing + z-score
     cnt = torch.from_numpy(ytr).float().to(cuda)
     sm = torch.empty_like(cnt)

@@ -35,6 +35,19 @@ struct GemmDesc {
   // ordered reduction, instead of costing a whole wave.
   void* balance_ws = nullptr;
 };
+// Dense-per-time-bin RRR backward (rrr_bwd_dense_kernel): G[c, j*Npad + n] = sum_t V[j,t] sum_k Xb[c, t*Kp + k] R[n, t*Kp + k]
+struct DenseBwdDesc {
+  const void* Xb = nullptr;   // (C1, ldr) 16-bit, column t*Kp + k, zero for K <= k < Kp
+  const void* R = nullptr;    // (Npad, ldr) 16-bit, same columns
+  long long C1 = 0, K = 0, Kp = 0, T = 0, Npad = 0, ldr = 0;
+  int r = 0;
+  bool f16 = false;
+  const double* V = nullptr;  // (r, T) device
+  float* G = nullptr;         // (C1, ldg)
+  long long ldg = 0;
+};
+bool rrr_bwd_dense_supported(const DenseBwdDesc& g);
+int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream);
 size_t balance_ws_bytes();
 bool gemm_supported(const GemmDesc& g);
 int pick_bn(long long N);

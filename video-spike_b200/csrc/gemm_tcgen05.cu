@@ -50,22 +50,60 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  // no suspend-time hint: with one, ptxas emits NANOSLEEP.SYNCS after a failed check and the wake-up latency (~0.4 us)
+  // dominates pipelines whose stages hold only ~0.1 us of tensor-core work (profiles/r01_ncu_dense_bwd.txt)
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(1000000)  // suspend-time hint: 1 ms
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (int i = 0; i < 8000; ++i)
-    if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (global_timer_ns() - t0 > 8000000000ull) break;   // 8 s
+  }
+  printf("vs_b200 gemm_tn: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
+// Spinning wait for the single-thread roles (TMA producer, MMA issuer): try_wait parks the thread (NANOSLEEP.SYNCS) after a
+// failed check and its wake-up latency lands on the critical path of every stage hand-off; test_wait never sleeps.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  for (int outer = 0;; ++outer) {
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred P1;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, P1;\n\t"
+          "}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (ok) return;
+    }
+    if (outer == 0) t0 = global_timer_ns();
+    else if (global_timer_ns() - t0 > 8000000000ull) break;   // 8 s
+  }
   printf("vs_b200 gemm_tn: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
   __trap();
 }
@@ -77,6 +115,21 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -396,50 +449,60 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Both issuing roles run with the whole warp converged and elect one lane per instruction group: under `if (lane == 0)`
+  // ptxas wraps every uniform-datapath instruction (UTMALDG / UTCHMMA) in an ELECT / BRA.U.ANY retry loop, and `it % stages`
+  // with a run-time divisor costs ~40 dependent instructions per stage on the single issuing thread.
   if (warp == 0) {
-    // ===== TMA producer (one lane per CTA): own A rows + own halves of the B chunks, counted on the leader's barrier =====
-    if (lane == 0) {
-      int it = 0;
-      for (int ps = 0; ps < p.n_pass; ++ps) {
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+    // ===== TMA producer: own A rows + own halves of the B chunks, counted on the leader's barrier =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ps = 0; ps < p.n_pass; ++ps) {
+      const int pa = p.pa[ps], pb = p.pb[ps];
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+        if (elect_one()) {
           const uint32_t a_dst = tiles0 + s * stage_bytes;
           const uint32_t b_dst = a_dst + A_TILE_BYTES;
           if (rank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, 2u * stage_bytes);
           const uint32_t full = mapa_cluster(bar_full0 + 8u * s, 0);
-          tma_load_3d_pair(a_dst, &tmA, full, kb * 64, m_load * BM, p.pa[ps]);
-          tma_load_3d_pair(b_dst, &tmB0, full, kb * 64, n_tile * p.BN + p.coff[0] + rank * h0, p.pb[ps]);
+          tma_load_3d_pair(a_dst, &tmA, full, kb * 64, m_load * BM, pa);
+          tma_load_3d_pair(b_dst, &tmB0, full, kb * 64, n_tile * p.BN + p.coff[0] + rank * h0, pb);
           if (h1 > 0)
-            tma_load_3d_pair(b_dst + (uint32_t)h0 * KB_BYTES, &tmB1, full, kb * 64, n_tile * p.BN + p.coff[1] + rank * h1, p.pb[ps]);
+            tma_load_3d_pair(b_dst + (uint32_t)h0 * KB_BYTES, &tmB1, full, kb * 64, n_tile * p.BN + p.coff[1] + rank * h1, pb);
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one lane of the leader CTA drives the tensor cores of both SMs =====
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       const uint32_t idesc0 = make_idesc_pair(p.f16 != 0, p.cn[0]);
       const uint32_t idesc1 = make_idesc_pair(p.f16 != 0, p.nchunk > 1 ? p.cn[1] : 16);
+      const uint64_t desc0 = make_smem_desc(tiles0);
+      const uint32_t stage16 = stage_bytes >> 4, b16 = A_TILE_BYTES >> 4, b1_16 = ((uint32_t)h0 * KB_BYTES) >> 4;
+      const uint32_t tm0 = tmem_base + (uint32_t)p.coff[0], tm1 = tmem_base + (uint32_t)p.coff[1];
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(bar_full0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t a_addr = tiles0 + s * stage_bytes;
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
-        const uint64_t da = make_smem_desc(a_addr);
-        const uint64_t db0 = make_smem_desc(b_addr);
-        const uint64_t db1 = make_smem_desc(b_addr + (uint32_t)h0 * KB_BYTES);
+        if (elect_one()) {
+          const uint64_t da = desc0 + (uint64_t)(s * stage16);
+          const uint64_t db0 = da + (uint64_t)b16;
+          const uint64_t db1 = db0 + (uint64_t)b1_16;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-          tc_mma_pair(tmem_base + (uint32_t)p.coff[0], da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc0, acc);
-          if (h1 > 0) tc_mma_pair(tmem_base + (uint32_t)p.coff[1], da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc1, acc);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            tc_mma_pair(tm0, da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc0, acc);
+            if (h1 > 0) tc_mma_pair(tm1, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc1, acc);
+          }
+          tc_commit_pair(bar_empty0 + 8u * s);   // frees this slot in both CTAs
+          if (it == iters - 1) tc_commit_pair(bar_tmem);   // accumulators complete in both CTAs
         }
-        tc_commit_pair(bar_empty0 + 8u * s);   // frees this slot in both CTAs
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      if (iters > 0) tc_commit_pair(bar_tmem); // accumulators complete in both CTAs
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> global (each CTA drains its own 128 rows) =====
@@ -493,6 +556,215 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ RRR backward, dense per time bin
+// G[c, j*Npad + n] = sum_t V[j,t] * D_t[c,n],   D_t[c,n] = sum_k X[k,t,c] * R[k,t,n]         (src/model/rrr.py:113 autograd)
+// The factorised backward feeds the tensor cores the operand R (x) V (r*N columns: r x the flops of the reference's
+// einsum).  Here each time bin's D_t = X_t^T R_t (the reference's dbeta_t tile) is formed in TMEM with the contraction over
+// that bin's K trials only, and the r rank-one updates G_j += V[j,t] * D_t run on the CUDA cores, in REGISTERS, while the
+// tensor cores work on the next bin (D is double-buffered in TMEM).  TMEM reads run at 64 B/clk/SM, so the only per-bin
+// TMEM traffic is D_t itself; to make the r accumulators fit the register file a CTA owns 128 rows of c and HALF of the
+// neurons (the two CTAs of a c-tile are neighbours in the grid and share the A tile through L2).
+//   A = Xb (C1 rows) and B = R (Npad rows), both with column t*Kp + k, Kp = K rounded up to 16 and zeros in the pad:
+//       the bin's boxes start at t*Kp + 64 i (32-byte aligned, TMA needs 16), the last one is consumed only up to the
+//       UMMA K-steps that still hold trials of the bin
+// warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+constexpr int DENSE_THREADS = 320;
+constexpr int DENSE_R = 3;
+
+struct DenseParams {
+  int C1, Npad, T, K, Kp, nb;
+  int nc;            // neurons per CTA (Npad / 2)
+  int mma_n;         // nc rounded up to 16
+  int stages, f16, vbytes;
+  int flags;         // experiment switches (VS_DENSE_FLAGS): 1 = spinning waits in the issuing warps, 2 = L2 prefetch of A
+  int prefetch;      // prefetch distance in stages
+  const double* V;
+  float* G;
+  long long ldg;
+};
+
+__device__ __forceinline__ void mbar_wait_sel(uint32_t bar, uint32_t parity, bool spin) {
+  if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
+}
+
+__device__ __forceinline__ void tc_ld4_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int W4>   // 4-column chunks per epilogue thread (Npad / 16)
+__global__ void __launch_bounds__(DENSE_THREADS, 1)
+rrr_bwd_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DenseParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)p.mma_n * KB_BYTES;
+  const uint32_t bar_full0 = base, bar_empty0 = base + 8u * 16;
+  const uint32_t bar_dfull0 = base + 8u * 32, bar_dempty0 = base + 8u * 34;     // two D buffers
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 36);
+  float* vsm = reinterpret_cast<float*>(base_ptr + CTRL_BYTES);                 // V as float, (r, T)
+  const uint32_t tiles0 = base + CTRL_BYTES + (uint32_t)p.vbytes;
+  const int m_tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const bool spin = (p.flags & 1) != 0;
+  constexpr uint32_t kDStride = 128;                                             // TMEM columns between the two D buffers
+
+  for (int e = threadIdx.x; e < DENSE_R * p.T; e += DENSE_THREADS) vsm[e] = (float)p.V[e];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full0 + 8u * s, 1);
+      mbar_init(bar_empty0 + 8u * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_dfull0 + 8u * i, 1);
+      mbar_init(bar_dempty0 + 8u * i, 8);      // the 8 epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 36), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // The two issuing roles run with the WHOLE warp converged and elect one lane per instruction: a loop under `if (lane == 0)`
+  // makes ptxas wrap every uniform-datapath instruction (UTMALDG / UTCMMA operands live in uniform registers) in an
+  // ELECT / BRA.U.ANY retry loop, and with only ~160 clk of tensor work per stage that scalar overhead (plus the integer
+  // division of `it % stages`) was the bottleneck of the first version (tensor pipe 17 % active, profiles/r01_ncu_dense_bwd.txt).
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    // A comes from HBM (each box is used by the two CTAs of a c-tile, once): the even CTA asks for its boxes kPrefetch
+    // stages ahead of the ring with an L2 prefetch, so that the 8-stage ring only has to cover L2 latency
+    const int kPrefetch = p.prefetch;
+    int pt = 0, pi = 0;
+    const bool do_pf = (half == 0) && (p.flags & 2);
+    if (do_pf && elect_one()) {
+      for (int n = 0; n < kPrefetch && pt < p.T; ++n) {
+        tma_prefetch_3d(&tmA, pt * p.Kp + pi * 64, m_tile * BM, 0);
+        if (++pi == p.nb) { pi = 0; ++pt; }
+      }
+    }
+    {   // every lane tracks the prefetch cursor (the elected lane may change)
+      int n = kPrefetch; pt = 0; pi = 0;
+      while (n-- > 0 && pt < p.T) { if (++pi == p.nb) { pi = 0; ++pt; } }
+    }
+    __syncwarp();
+    for (int t = 0; t < p.T; ++t) {
+      int col = t * p.Kp;
+      for (int i = 0; i < p.nb; ++i, col += 64) {
+        mbar_wait_sel(bar_empty0 + 8u * s, ph ^ 1u, spin);
+        if (elect_one()) {
+          const uint32_t a_dst = tiles0 + s * stage_bytes;
+          const uint32_t full = bar_full0 + 8u * s;
+          mbar_arrive_expect_tx(full, stage_bytes);
+          tma_load_3d(a_dst, &tmA, full, col, m_tile * BM, 0);
+          tma_load_3d(a_dst + A_TILE_BYTES, &tmB, full, col, half * p.nc, 0);
+          if (do_pf && pt < p.T) tma_prefetch_3d(&tmA, pt * p.Kp + pi * 64, m_tile * BM, 0);
+        }
+        __syncwarp();
+        if (pt < p.T && ++pi == p.nb) { pi = 0; ++pt; }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(false, p.f16 != 0, p.mma_n);
+    const int last_ksteps = ((p.K - (p.nb - 1) * 64 + 15) >> 4) > 4 ? 4 : ((p.K - (p.nb - 1) * 64 + 15) >> 4);
+    const uint64_t desc0 = make_smem_desc(tiles0);
+    const uint32_t stage16 = stage_bytes >> 4, b16 = A_TILE_BYTES >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = 0; t < p.T; ++t) {
+      const int buf = t & 1;
+      if (t >= 2) {                   // the epilogue has drained bin t-2 from this buffer
+        mbar_wait_sel(bar_dempty0 + 8u * buf, (uint32_t)((t >> 1) - 1) & 1u, spin);
+        tc_fence_after();
+      }
+      const uint32_t dcol = tmem_base + (uint32_t)buf * kDStride;
+      for (int i = 0; i < p.nb; ++i) {
+        mbar_wait_sel(bar_full0 + 8u * s, ph, spin);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = desc0 + (uint64_t)(s * stage16);
+          const uint64_t db = da + (uint64_t)b16;
+          const int ksteps = (i == p.nb - 1) ? last_ksteps : 4;
+          tc_mma<false>(dcol, da, db, idesc, i > 0 ? 1u : 0u);
+          if (ksteps > 1) tc_mma<false>(dcol, da + 2, db + 2, idesc, 1u);
+          if (ksteps > 2) tc_mma<false>(dcol, da + 4, db + 4, idesc, 1u);
+          if (ksteps > 3) tc_mma<false>(dcol, da + 6, db + 6, idesc, 1u);
+          tc_commit(bar_empty0 + 8u * s);
+          if (i == p.nb - 1) tc_commit(bar_dfull0 + 8u * buf);     // D_t complete
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
+    constexpr int W = W4 * 4;                 // columns per thread
+    const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * W);
+    float g0[W], g1[W], g2[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) g0[i] = g1[i] = g2[i] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      const int buf = t & 1;
+      mbar_wait(bar_dfull0 + 8u * buf, (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const float v0 = vsm[t], v1 = vsm[p.T + t], v2 = vsm[2 * p.T + t];
+      const uint32_t td = t_d + (uint32_t)buf * kDStride;
+#pragma unroll
+      for (int c0 = 0; c0 < W4; c0 += 3) {    // 12 columns per TMEM round trip
+        uint32_t d[12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c0 + c < W4) tc_ld4_issue(td + (uint32_t)((c0 + c) * 4), d + c * 4);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          if (c0 * 4 + i < W) {
+            const float dv = __uint_as_float(d[i]);
+            g0[c0 * 4 + i] = fmaf(v0, dv, g0[c0 * 4 + i]);
+            g1[c0 * 4 + i] = fmaf(v1, dv, g1[c0 * 4 + i]);
+            g2[c0 * 4 + i] = fmaf(v2, dv, g2[c0 * 4 + i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dempty0 + 8u * buf);     // the tensor cores may overwrite this D buffer
+    }
+    // write the tile: G[c, j*Npad + n]
+    const int row = m_tile * BM + q * 32 + lane;
+    if (row < p.C1) {
+      float* grow = p.G + (long long)row * p.ldg + half * p.nc + hsel * W;
+#pragma unroll
+      for (int c = 0; c < W4; ++c) {
+        if (half * p.nc + hsel * W + c * 4 < p.Npad) {
+          *reinterpret_cast<float4*>(grow + c * 4) = make_float4(g0[c * 4], g0[c * 4 + 1], g0[c * 4 + 2], g0[c * 4 + 3]);
+          *reinterpret_cast<float4*>(grow + p.Npad + c * 4) = make_float4(g1[c * 4], g1[c * 4 + 1], g1[c * 4 + 2], g1[c * 4 + 3]);
+          *reinterpret_cast<float4*>(grow + 2 * p.Npad + c * 4) = make_float4(g2[c * 4], g2[c * 4 + 1], g2[c * 4 + 2], g2[c * 4 + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -652,6 +924,75 @@ static int gemm_tn_pair(const GemmDesc& g, int BN, cudaStream_t stream) {
   prof_end(PROF_GEMM_TC, stream);
   if (g.splits_out) *g.splits_out = splits;
   return VS_OK;
+}
+
+// ---- dense RRR backward (rrr_bwd_dense_kernel) ----
+bool rrr_bwd_dense_supported(const DenseBwdDesc& g) {
+  // Default route; VS_RRR_DENSE=0 selects the factorised GEMM-B (read per call: the tests compare both routes in one process).
+  // The kernel executes a third of the factorised flops, but its 8 x 26 KB ring cannot keep more bytes in flight than the
+  // CTA-pair GEMM does, so the kernel itself takes about the same 0.43 ms at the bench size; the fit still gains ~4 % because
+  // the residual operand is a third of the size (epi_f) and the tensor pipe draws less power (DESIGN.md "dense backward").
+  const char* e = getenv("VS_RRR_DENSE");
+  if (e && e[0] == '0') return false;
+  if (g.r != DENSE_R || g.Npad % 16 != 0 || g.Npad < 16 || g.Npad > 160) return false;
+  if (g.C1 <= BM || g.T <= 0 || g.K <= 0) return false;
+  if (((uintptr_t)g.Xb & 15) || ((uintptr_t)g.R & 15) || (g.ldr * 2) % 16 || g.Kp % 16 || g.Kp < g.K) return false;
+  if (g.T * g.Kp + 64 >= (1ll << 31)) return false;
+  return true;
+}
+
+template <int W4>
+static int launch_dense(const CUtensorMap& tmA, const CUtensorMap& tmB, const DenseParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+  VS_CHECK_CUDA(cudaFuncSetAttribute(rrr_bwd_dense_kernel<W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VS_LAUNCH(rrr_bwd_dense_kernel<W4>, grid, DENSE_THREADS, smem, stream, tmA, tmB, p);
+  return VS_OK;
+}
+
+int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream) {
+  VS_REQUIRE(rrr_bwd_dense_supported(g), VS_ERR_UNSUPPORTED, "dense RRR backward: unsupported shape");
+  DenseParams p;
+  p.C1 = (int)g.C1; p.Npad = (int)g.Npad; p.T = (int)g.T; p.K = (int)g.K; p.Kp = (int)g.Kp;
+  p.nb = (int)ceil_div(g.K, 64);
+  p.nc = p.Npad / 2;
+  p.mma_n = (int)round_up(p.nc, 16);
+  p.f16 = g.f16 ? 1 : 0;
+  p.V = g.V; p.G = g.G; p.ldg = g.ldg;
+  p.vbytes = (int)round_up((long long)DENSE_R * g.T * 4, 1024);
+  {
+    const char* e = getenv("VS_DENSE_FLAGS");
+    p.flags = e ? atoi(e) : 0;
+    const char* f = getenv("VS_DENSE_PREFETCH");
+    p.prefetch = f ? atoi(f) : 24;
+  }
+  const int stage_bytes = A_TILE_BYTES + p.mma_n * KB_BYTES;
+  int stages = (227 * 1024 - CTRL_BYTES - 1024 - p.vbytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  VS_REQUIRE(stages >= 2, VS_ERR_UNSUPPORTED, "dense RRR backward: too many time bins for shared memory");
+  p.stages = stages;
+  Operand a; a.ptr = g.Xb; a.rows = g.C1; a.k = g.T * g.Kp; a.ld = g.ldr;
+  Operand b; b.ptr = g.R; b.rows = g.Npad; b.k = g.T * g.Kp; b.ld = g.ldr;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a, false, g.f16, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, b, false, g.f16, p.mma_n);
+  if (rc) return rc;
+  const size_t smem = (size_t)CTRL_BYTES + 1024 + p.vbytes + (size_t)stages * stage_bytes;
+  dim3 grid(2 * (unsigned)ceil_div(g.C1, BM), 1, 1);
+  prof_begin(PROF_GEMM_TC, stream);
+  switch (p.Npad / 16) {
+    case 1: rc = launch_dense<1>(tmA, tmB, p, grid, smem, stream); break;
+    case 2: rc = launch_dense<2>(tmA, tmB, p, grid, smem, stream); break;
+    case 3: rc = launch_dense<3>(tmA, tmB, p, grid, smem, stream); break;
+    case 4: rc = launch_dense<4>(tmA, tmB, p, grid, smem, stream); break;
+    case 5: rc = launch_dense<5>(tmA, tmB, p, grid, smem, stream); break;
+    case 6: rc = launch_dense<6>(tmA, tmB, p, grid, smem, stream); break;
+    case 7: rc = launch_dense<7>(tmA, tmB, p, grid, smem, stream); break;
+    case 8: rc = launch_dense<8>(tmA, tmB, p, grid, smem, stream); break;
+    case 9: rc = launch_dense<9>(tmA, tmB, p, grid, smem, stream); break;
+    default: rc = launch_dense<10>(tmA, tmB, p, grid, smem, stream); break;
+  }
+  prof_end(PROF_GEMM_TC, stream);
+  return rc;
 }
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream) {

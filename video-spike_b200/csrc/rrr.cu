@@ -49,7 +49,9 @@ __device__ __forceinline__ void split_planes(double v, int planes, int fmt, uint
 // ------------------------------------------------------------------ pack X (R0 tail / RRRGD input)
 // One tile of 32 trials (of ONE time bin t) x 32 features per block.  Source: X[(k*T + t), c] (fp64 path) or
 // frames[k, sorted_idx[t], c] (uint8 path).  Destination rows are time-major d = t*K + k: Xa[d][c] is written
-// directly (coalesced in c) and Xb[c][d] through a shared-memory transpose (coalesced in d).
+// directly (coalesced in c) and Xb[c][t*Kp + k] through a shared-memory transpose (coalesced in k).  In Xb every
+// time bin is padded to Kp = K rounded up to 16 trials (zeros, pad_zero_kernel): a bin then starts on a 32-byte
+// boundary (TMA boxes must start 16-byte aligned) and ends on a UMMA K-step.
 template <bool kFromU8>
 __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X, const uint8_t* __restrict__ frames,
                                                    const int32_t* __restrict__ sorted_idx, const double* __restrict__ mean,
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X,
   const long long t = blockIdx.x / kblocks, k0 = k_begin + (blockIdx.x % kblocks) * 32;
   const long long c0 = (long long)blockIdx.y * 32;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const long long pa = K * T * ldc, pb = C1 * ldr;
+  const long long pa = K * T * ldc, pb = C1 * ldr, Kp = (K + 15) / 16 * 16;
   long long f = 0;
   if constexpr (kFromU8) f = sorted_idx[t];
   // single-plane fast path from uint8 frames: the block's 32 columns share (mean, 1/std), taken to fp32 ONCE per block --
@@ -107,12 +109,21 @@ __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X,
   for (int cc = ly; cc < 32; cc += 8) {
     const long long c = c0 + cc, k = k0 + lx;
     if (c < C1 && k < k_end)
-      for (int p = 0; p < planes; ++p) Xb[p * pb + c * ldr + t * K + k] = tile[p][lx][cc];
+      for (int p = 0; p < planes; ++p) Xb[p * pb + c * ldr + t * Kp + k] = tile[p][lx][cc];
   }
   if (blockIdx.y == 0 && threadIdx.x < 32) {
     const long long k = k0 + threadIdx.x;
     if (k < k_end) xl[t * K + k] = kFromU8 ? 1.0f : (float)X[((k - k_begin) * T + t) * (C1 + 1) + C1];
   }
+}
+
+// zeros in the pad trials K <= k < Kp of every time bin of Xb (one thread per (plane, c, t))
+__global__ void __launch_bounds__(256) pad_zero_kernel(uint16_t* __restrict__ Xb, long long rows, long long T, long long K, long long Kp,
+                                                       long long ldr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * T) return;
+  const long long row = i / T, t = i % T;
+  for (long long k = K; k < Kp; ++k) Xb[row * ldr + t * Kp + k] = 0;
 }
 
 // column mean / population std (clipped at 1e-8) over the K trials: src/utils/utils.py:107-112
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
                                                     long long T, long long N, long long Npad, int r, int planes, int fmt, long long ldr,
                                                     uint16_t* __restrict__ RV, float* __restrict__ sse_part,
                                                     float* __restrict__ db_part, float* __restrict__ pv_part,
-                                                    double* __restrict__ yhat) {
+                                                    double* __restrict__ yhat, long long Kp, int dense) {
   __shared__ float Rs[kEpiRows][33];
   __shared__ float red[8][32][2];
   __shared__ float xls[kEpiRows];
@@ -348,15 +359,27 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
       if (lane == 0) pvs[w][j] = s;
     }
     __syncthreads();
-    // phase 2: lane = trial pair (2*lane, 2*lane+1), warp w covers neurons w*4 .. w*4+3 of the tile
-    const long long prv = (long long)r * Npad * ldr;
-    const bool pair_ok = ((d0 & 1) == 0);
+    // phase 2: lane = trial pair (2*lane, 2*lane+1), warp w covers neurons w*4 .. w*4+3 of the tile.  Columns follow Xb:
+    // t*Kp + k with zeros in the pad K <= k < Kp (Rs is zero there); Kp and k0 are even, so pair stores are aligned.
     const long long ka = k0 + 2 * lane;
+    const long long dcol = t * Kp + ka;
+    if (dense) {
+      // dense backward (tc::rrr_bwd_dense): the plain residual R[n][t*Kp + k]
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nl = w * 4 + i;
+        const long long nn = n0 + nl;
+        if (nn >= N || ka >= Kp) continue;
+        const uint32_t lo = enc16(Rs[2 * lane][nl], fmt), hi = enc16(Rs[2 * lane + 1][nl], fmt);
+        *reinterpret_cast<uint32_t*>(RV + nn * ldr + dcol) = lo | (hi << 16);
+      }
+    } else {
+    const long long prv = (long long)r * Npad * ldr;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int nl = w * 4 + i;
       const long long nn = n0 + nl;
-      if (nn >= N) continue;
+      if (nn >= N || ka >= Kp) continue;
       const float r0v = Rs[2 * lane][nl], r1v = Rs[2 * lane + 1][nl];
 #pragma unroll
       for (int j = 0; j < RMAX; ++j) {
@@ -372,15 +395,10 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           if (p >= planes) continue;
-          uint16_t* dst = RV + p * prv + ((long long)j * Npad + nn) * ldr + d0 + 2 * lane;
-          if (pair_ok && ka + 1 < K) {
-            *reinterpret_cast<uint32_t*>(dst) = (uint32_t)pl0[p] | ((uint32_t)pl1[p] << 16);
-          } else {
-            if (ka < K) dst[0] = pl0[p];
-            if (ka + 1 < K) dst[1] = pl1[p];
-          }
+          *reinterpret_cast<uint32_t*>(RV + p * prv + ((long long)j * Npad + nn) * ldr + dcol) = (uint32_t)pl0[p] | ((uint32_t)pl1[p] << 16);
         }
       }
+    }
     }
     // phase 3: per-(t, kb, n) partials, the 8 warps' sums added in a fixed order
     if (w == 0 && n < N) {
@@ -538,6 +556,7 @@ struct Ws {
   double *Gp, *G, *W, *sse_tn;
   long long Npad, ldz, gp_blocks, KB;
   int splits_f, splits_b;  // split-K factors of the two GEMMs
+  long long Kp;            // trials per time bin in the backward operands (K rounded up to 16)
   size_t total;
 };
 
@@ -566,11 +585,12 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.gp_blocks = ceil_div(d.C1, 256 * kPrepC) * d.N;
   w.KB = ceil_div(d.K, kEpiRows);
   w.splits_f = hp_splits(d.C1, d.planes);
-  w.splits_b = hp_splits(KT, d.planes);
+  w.splits_b = hp_splits(d.T * round_up(d.K, 16), d.planes);
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += (size_t)round_up((long long)bytes, 1024); return q; };
   w.Ub = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldc * 2);
+  w.Kp = round_up(d.K, 16);
   w.RV = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldr * 2);
   w.Z = (float*)take((size_t)w.splits_f * KT * w.ldz * 4);
   w.Gacc = (float*)take((size_t)w.splits_b * d.C1 * w.ldz * 4);
@@ -591,7 +611,7 @@ static int check_dims(const vs_rrr_dims& d) {
   VS_REQUIRE(d.r <= kMaxR, VS_ERR_UNSUPPORTED, "rrr: rank %lld > %d", (long long)d.r, kMaxR);
   VS_REQUIRE(d.planes >= 1 && d.planes <= 3, VS_ERR_INVALID, "rrr: planes must be 1..3");
   VS_REQUIRE(d.fmt == VS_OPERAND_BF16 || d.fmt == VS_OPERAND_F16, VS_ERR_INVALID, "rrr: fmt must be VS_OPERAND_BF16 or VS_OPERAND_F16");
-  VS_REQUIRE(d.ldc >= d.C1 && d.ldc % 8 == 0 && d.ldr >= d.K * d.T && d.ldr % 8 == 0, VS_ERR_INVALID, "rrr: bad pitches");
+  VS_REQUIRE(d.ldc >= d.C1 && d.ldc % 8 == 0 && d.ldr >= d.T * round_up(d.K, 16) && d.ldr % 8 == 0, VS_ERR_INVALID, "rrr: bad pitches");
   VS_REQUIRE(d.K * d.T < (1ll << 31) && d.C1 < (1ll << 31), VS_ERR_UNSUPPORTED, "rrr: dimension exceeds 2^31");
   return VS_OK;
 }
@@ -632,7 +652,7 @@ static int gemm_f(const vs_rrr_dims& d, const uint16_t* Xa, const Ws& w, int eng
 // Gacc = Xb * RV^T  (M = C1, N = r*Npad, contraction K*T)
 static int gemm_b(const vs_rrr_dims& d, const uint16_t* Xb, const Ws& w, int engine, cudaStream_t st, int* splits_used) {
   *splits_used = 1;
-  const long long KT = d.K * d.T;
+  const long long KT = w.Kp * d.T;       // padded time bins
   if (engine == VS_ENGINE_SIMT) {
     simt::GemmDesc g;
     g.A.ptr = Xb; g.A.type = d.fmt == VS_OPERAND_F16 ? simt::F16 : simt::BF16; g.A.s_i = d.ldr; g.A.s_k = 1; g.A.planes = d.planes; g.A.plane_stride = d.C1 * d.ldr;
@@ -658,7 +678,7 @@ using namespace vs;
 using namespace vs::rrr;
 
 extern "C" int64_t vs_rrr_ldc(int64_t C1) { return round_up(C1, 64); }
-extern "C" int64_t vs_rrr_ldr(int64_t K, int64_t T) { return round_up(K * T, 64); }
+extern "C" int64_t vs_rrr_ldr(int64_t K, int64_t T) { return round_up(T * round_up(K, 16), 64); }
 
 extern "C" size_t vs_rrr_workspace(vs_rrr_dims d) {
   if (d.K <= 0 || d.T <= 0 || d.C1 <= 0 || d.N <= 0 || d.r <= 0 || d.planes < 1) return 0;
@@ -676,6 +696,9 @@ extern "C" int vs_rrr_pack(const double* X_trials, int64_t k0, int64_t nk, vs_rr
   VS_LAUNCH((pack_kernel<false>), grid, 256, 0, stream, X_trials, nullptr, nullptr, nullptr, nullptr, 0ll, (long long)k0,
             (long long)(k0 + nk), (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (int)d.fmt, (long long)d.ldc, (long long)d.ldr,
             Xa, Xb, xl, overflow_flag);
+  if (k0 + nk == d.K && round_up(d.K, 16) > d.K)
+    VS_LAUNCH(pad_zero_kernel, (unsigned)ceil_div((long long)d.planes * d.C1 * d.T, 256), 256, 0, stream, Xb, (long long)d.planes * d.C1,
+              (long long)d.T, (long long)d.K, (long long)round_up(d.K, 16), (long long)d.ldr);
   return VS_OK;
 }
 
@@ -696,6 +719,9 @@ extern "C" int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* 
   VS_LAUNCH((pack_kernel<true>), grid, 256, 0, stream, nullptr, frames, sorted_idx, mean, std_clipped, (long long)Tf, 0ll,
             (long long)d.K, (long long)d.K, (long long)d.T, (long long)d.C1, d.planes, (int)d.fmt, (long long)d.ldc, (long long)d.ldr, Xa, Xb,
             xl, overflow_flag);
+  if (round_up(d.K, 16) > d.K)
+    VS_LAUNCH(pad_zero_kernel, (unsigned)ceil_div((long long)d.planes * d.C1 * d.T, 256), 256, 0, stream, Xb, (long long)d.planes * d.C1,
+              (long long)d.T, (long long)d.K, (long long)round_up(d.K, 16), (long long)d.ldr);
   return VS_OK;
 }
 
@@ -726,14 +752,18 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   int sf = 1, sb = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);
   if (rc) return rc;
-  // stage 2: residuals -> RV operand, per-block partials of SSE / db / dV
+  // stage 2: residuals -> backward operand (R (x) V, or plain R for the dense backward), per-block partials of SSE / db / dV
+  tc::DenseBwdDesc dd;
+  dd.Xb = Xb; dd.R = w.RV; dd.C1 = d.C1; dd.K = d.K; dd.Kp = w.Kp; dd.T = d.T; dd.Npad = w.Npad; dd.ldr = d.ldr;
+  dd.r = r; dd.f16 = d.fmt == VS_OPERAND_F16; dd.V = V; dd.G = w.Gacc; dd.ldg = w.ldz;
+  const bool dense = dU && d.planes == 1 && engine != VS_ENGINE_SIMT && w.splits_b == 1 && tc::rrr_bwd_dense_supported(dd);
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (r <= 4) {
     VS_LAUNCH((epi_f_kernel<false, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
+              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr, w.Kp, dense ? 1 : 0);
   } else {
     VS_LAUNCH((epi_f_kernel<false, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr);
+              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr, w.Kp, dense ? 1 : 0);
   }
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
   VS_LAUNCH(reduce_part_kernel, g2, 128, 0, st, w.sse_part, w.db_part, b, w.KB, (long long)d.T, (long long)d.N, l2, db, w.sse_tn);
@@ -741,7 +771,7 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
             (long long)d.N, r, l2, sse_n, loss, dV);
   if (dU) {
     // stage 3/4: Gacc and dU
-    rc = gemm_b(d, Xb, w, engine, st, &sb);
+    rc = dense ? tc::rrr_bwd_dense(dd, st) : gemm_b(d, Xb, w, engine, st, &sb);
     if (rc) return rc;
     dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
     const bool fast = d.planes == 1 && sb == 1;
@@ -777,10 +807,10 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (d.r <= 4) {
     VS_LAUNCH((epi_f_kernel<true, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat, 0ll, 0);
   } else {
     VS_LAUNCH((epi_f_kernel<true, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat);
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat, 0ll, 0);
   }
   return VS_OK;
 }
