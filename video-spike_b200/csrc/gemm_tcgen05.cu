@@ -768,6 +768,216 @@ rrr_bwd_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ RRR backward, dense per time bin, CTA pairs
+// Same contraction as rrr_bwd_dense_kernel, other decomposition: the L2 -> SM path delivers ~45 B/clk/SM, and a CTA that
+// owns 128 rows of c and HALF of the neurons ingests 26 KB per 64-trial box for a 128 x 72 tile -- that kernel runs at the
+// ingest limit (5.3 GB per launch, profiles/r01_ncu_dense_bwd.txt).  Here a CTA PAIR (cta_group::2, UMMA 256 x Npad) owns
+// 256 rows of c and ALL neurons: each CTA ingests its 128 rows of A and half of R (25 KB per box for a 128 x 144 tile, half
+// the bytes per flop).  The price is accumulator space: 128 x 3*Npad fp32 per CTA does not fit the register file next to
+// the D_t staging, so G_0 and G_1 live in TMEM next to D_t and are updated with tcgen05.ld / fma / tcgen05.st, G_2 in
+// registers.  D_t is single-buffered (3*Npad <= 512 columns): the next bin's MMAs start when every epilogue warp of the
+// pair has read D_t.
+struct DensePairParams {
+  int C1, m_tiles, Npad, T, K, Kp, nb;
+  int stages, tmem_cols, f16, vbytes;
+  const double* V;
+  float* G;
+  long long ldg;
+};
+
+__device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+template <int HW8>   // 8-column chunks per epilogue thread (Npad / 16)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DENSE_THREADS, 1)
+rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DensePairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int h = p.Npad >> 1;                                   // B rows per CTA = columns per epilogue thread
+  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)h * KB_BYTES;
+  const uint32_t bar_full0 = base, bar_empty0 = base + 8u * 16;
+  const uint32_t bar_dfull = base + 8u * 32, bar_dempty = base + 8u * 33;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 34);
+  float* vsm = reinterpret_cast<float*>(base_ptr + CTRL_BYTES);
+  const uint32_t tiles0 = base + CTRL_BYTES + (uint32_t)p.vbytes;
+  const int m_tile = 2 * (int)(blockIdx.x >> 1) + rank;
+  const int m_load = m_tile < p.m_tiles ? m_tile : p.m_tiles - 1;
+
+  for (int e = threadIdx.x; e < DENSE_R * p.T; e += DENSE_THREADS) vsm[e] = (float)p.V[e];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full0 + 8u * s, 1);
+      mbar_init(bar_empty0 + 8u * s, 1);
+    }
+    mbar_init(bar_dfull, 1);
+    mbar_init(bar_dempty, 16);          // the 8 epilogue warps of both CTAs (only the leader's copy is waited on)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 34), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = 0; t < p.T; ++t) {
+      int col = t * p.Kp;
+      for (int i = 0; i < p.nb; ++i, col += 64) {
+        mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t a_dst = tiles0 + s * stage_bytes;
+          if (rank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, 2u * stage_bytes);
+          const uint32_t full = mapa_cluster(bar_full0 + 8u * s, 0);
+          tma_load_3d_pair(a_dst, &tmA, full, col, m_load * BM, 0);
+          tma_load_3d_pair(a_dst + A_TILE_BYTES, &tmB, full, col, rank * h, 0);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_pair(p.f16 != 0, p.Npad);
+      const int lk = (p.K - (p.nb - 1) * 64 + 15) >> 4;
+      const int last_ksteps = lk > 4 ? 4 : lk;
+      const uint64_t desc0 = make_smem_desc(tiles0);
+      const uint32_t stage16 = stage_bytes >> 4, b16 = A_TILE_BYTES >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < p.T; ++t) {
+        if (t > 0) {                    // D_{t-1} has been read by every epilogue warp of the pair
+          mbar_wait(bar_dempty, (uint32_t)(t - 1) & 1u);
+          tc_fence_after();
+        }
+        for (int i = 0; i < p.nb; ++i) {
+          mbar_wait(bar_full0 + 8u * s, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = desc0 + (uint64_t)(s * stage16);
+            const uint64_t db = da + (uint64_t)b16;
+            const int ksteps = (i == p.nb - 1) ? last_ksteps : 4;
+            tc_mma_pair(tmem_base, da, db, idesc, i > 0 ? 1u : 0u);
+            if (ksteps > 1) tc_mma_pair(tmem_base, da + 2, db + 2, idesc, 1u);
+            if (ksteps > 2) tc_mma_pair(tmem_base, da + 4, db + 4, idesc, 1u);
+            if (ksteps > 3) tc_mma_pair(tmem_base, da + 6, db + 6, idesc, 1u);
+            tc_commit_pair(bar_empty0 + 8u * s);
+            if (i == p.nb - 1) tc_commit_pair(bar_dfull);      // D_t complete in both CTAs
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
+    constexpr int W = HW8 * 8;              // columns per thread
+    const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * W);
+    const uint32_t t_g0 = t_d + (uint32_t)p.Npad, t_g1 = t_d + 2u * (uint32_t)p.Npad;
+    const uint32_t dempty_leader = mapa_cluster(bar_dempty, 0);
+    float g2[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) g2[i] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      mbar_wait(bar_dfull, (uint32_t)t & 1u);
+      tc_fence_after();
+      const float v0 = vsm[t], v1 = vsm[p.T + t], v2 = vsm[2 * p.T + t];
+#pragma unroll
+      for (int c = 0; c < HW8; c += 2) {      // 16 columns of D, G_0, G_1 per TMEM round trip
+        constexpr int kN = 16;
+        uint32_t d[kN], a0[kN], a1[kN];
+        const bool two = (c + 1 < HW8);
+        tc_ld8_issue(t_d + (uint32_t)(c * 8), d);
+        if (two) tc_ld8_issue(t_d + (uint32_t)(c * 8 + 8), d + 8);
+        if (t > 0) {
+          tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0);
+          tc_ld8_issue(t_g1 + (uint32_t)(c * 8), a1);
+          if (two) {
+            tc_ld8_issue(t_g0 + (uint32_t)(c * 8 + 8), a0 + 8);
+            tc_ld8_issue(t_g1 + (uint32_t)(c * 8 + 8), a1 + 8);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kN; ++i) a0[i] = a1[i] = 0u;
+        }
+        tc_wait_ld();
+        if (c + 2 >= HW8) {                   // last D columns are in registers: the tensor cores may overwrite D
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(dempty_leader);
+        }
+#pragma unroll
+        for (int i = 0; i < kN; ++i) {
+          if (i < 8 || two) {
+            const float dv = __uint_as_float(d[i]);
+            g2[(c * 8 + i) < W ? (c * 8 + i) : 0] = fmaf(v2, dv, g2[(c * 8 + i) < W ? (c * 8 + i) : 0]);
+            a0[i] = __float_as_uint(fmaf(v0, dv, __uint_as_float(a0[i])));
+            a1[i] = __float_as_uint(fmaf(v1, dv, __uint_as_float(a1[i])));
+          }
+        }
+        tc_st8(t_g0 + (uint32_t)(c * 8), a0);
+        tc_st8(t_g1 + (uint32_t)(c * 8), a1);
+        if (two) {
+          tc_st8(t_g0 + (uint32_t)(c * 8 + 8), a0 + 8);
+          tc_st8(t_g1 + (uint32_t)(c * 8 + 8), a1 + 8);
+        }
+      }
+      tc_wait_st();
+    }
+    // write the tile: G[c, j*Npad + n]
+    const int row = m_tile * BM + q * 32 + lane;
+    float* grow = p.G + (long long)row * p.ldg + hsel * W;
+#pragma unroll
+    for (int c = 0; c < HW8; ++c) {
+      uint32_t a0[8], a1[8];
+      tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0);
+      tc_ld8_issue(t_g1 + (uint32_t)(c * 8), a1);
+      tc_wait_ld();
+      if (row < p.C1) {
+        float4* o0 = reinterpret_cast<float4*>(grow + c * 8);
+        float4* o1 = reinterpret_cast<float4*>(grow + p.Npad + c * 8);
+        float4* o2 = reinterpret_cast<float4*>(grow + 2 * p.Npad + c * 8);
+        o0[0] = make_float4(__uint_as_float(a0[0]), __uint_as_float(a0[1]), __uint_as_float(a0[2]), __uint_as_float(a0[3]));
+        o0[1] = make_float4(__uint_as_float(a0[4]), __uint_as_float(a0[5]), __uint_as_float(a0[6]), __uint_as_float(a0[7]));
+        o1[0] = make_float4(__uint_as_float(a1[0]), __uint_as_float(a1[1]), __uint_as_float(a1[2]), __uint_as_float(a1[3]));
+        o1[1] = make_float4(__uint_as_float(a1[4]), __uint_as_float(a1[5]), __uint_as_float(a1[6]), __uint_as_float(a1[7]));
+        o2[0] = make_float4(g2[c * 8 + 0], g2[c * 8 + 1], g2[c * 8 + 2], g2[c * 8 + 3]);
+        o2[1] = make_float4(g2[c * 8 + 4], g2[c * 8 + 5], g2[c * 8 + 6], g2[c * 8 + 7]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // C tile = ordered sum of the tail-wave partial tiles
 __global__ void __launch_bounds__(256) tail_reduce_kernel(const float* __restrict__ ws, int tail_cta0, int splits, int n_tiles, int BN,
                                                           int M, int N, float* __restrict__ C, long long ldc) {
@@ -948,8 +1158,61 @@ static int launch_dense(const CUtensorMap& tmA, const CUtensorMap& tmB, const De
   return VS_OK;
 }
 
+template <int HW8>
+static int launch_dense_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const DensePairParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+  VS_CHECK_CUDA(cudaFuncSetAttribute(rrr_bwd_dense_pair_kernel<HW8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VS_LAUNCH(rrr_bwd_dense_pair_kernel<HW8>, grid, DENSE_THREADS, smem, stream, tmA, tmB, p);
+  return VS_OK;
+}
+
+static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
+  DensePairParams p;
+  p.C1 = (int)g.C1; p.m_tiles = (int)ceil_div(g.C1, BM); p.Npad = (int)g.Npad; p.T = (int)g.T; p.K = (int)g.K; p.Kp = (int)g.Kp;
+  p.nb = (int)ceil_div(g.K, 64);
+  p.f16 = g.f16 ? 1 : 0;
+  p.V = g.V; p.G = g.G; p.ldg = g.ldg;
+  p.vbytes = (int)round_up((long long)DENSE_R * g.T * 4, 1024);
+  const int h = p.Npad / 2;
+  const int stage_bytes = A_TILE_BYTES + h * KB_BYTES;
+  int stages = (227 * 1024 - CTRL_BYTES - 1024 - p.vbytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  VS_REQUIRE(stages >= 2, VS_ERR_UNSUPPORTED, "dense RRR backward: too many time bins for shared memory");
+  p.stages = stages;
+  int tcols = 32;
+  while (tcols < DENSE_R * p.Npad) tcols <<= 1;
+  p.tmem_cols = tcols;
+  Operand a; a.ptr = g.Xb; a.rows = g.C1; a.k = g.T * g.Kp; a.ld = g.ldr;
+  Operand b; b.ptr = g.R; b.rows = g.Npad; b.k = g.T * g.Kp; b.ld = g.ldr;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a, false, g.f16, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, b, false, g.f16, h);
+  if (rc) return rc;
+  const size_t smem = (size_t)CTRL_BYTES + 1024 + p.vbytes + (size_t)stages * stage_bytes;
+  dim3 grid(2 * (unsigned)ceil_div(p.m_tiles, 2), 1, 1);
+  prof_begin(PROF_GEMM_TC, stream);
+  switch (p.Npad / 16) {
+    case 1: rc = launch_dense_pair<1>(tmA, tmB, p, grid, smem, stream); break;
+    case 2: rc = launch_dense_pair<2>(tmA, tmB, p, grid, smem, stream); break;
+    case 3: rc = launch_dense_pair<3>(tmA, tmB, p, grid, smem, stream); break;
+    case 4: rc = launch_dense_pair<4>(tmA, tmB, p, grid, smem, stream); break;
+    case 5: rc = launch_dense_pair<5>(tmA, tmB, p, grid, smem, stream); break;
+    case 6: rc = launch_dense_pair<6>(tmA, tmB, p, grid, smem, stream); break;
+    case 7: rc = launch_dense_pair<7>(tmA, tmB, p, grid, smem, stream); break;
+    case 8: rc = launch_dense_pair<8>(tmA, tmB, p, grid, smem, stream); break;
+    case 9: rc = launch_dense_pair<9>(tmA, tmB, p, grid, smem, stream); break;
+    default: rc = launch_dense_pair<10>(tmA, tmB, p, grid, smem, stream); break;
+  }
+  prof_end(PROF_GEMM_TC, stream);
+  return rc;
+}
+
 int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream) {
   VS_REQUIRE(rrr_bwd_dense_supported(g), VS_ERR_UNSUPPORTED, "dense RRR backward: unsupported shape");
+  {
+    const char* e = getenv("VS_RRR_DENSE");   // 1 = half-split kernel (accumulators in registers), default = CTA-pair kernel
+    if (!(e && e[0] == '1')) return rrr_bwd_dense_pair(g, stream);
+  }
   DenseParams p;
   p.C1 = (int)g.C1; p.Npad = (int)g.Npad; p.T = (int)g.T; p.K = (int)g.K; p.Kp = (int)g.Kp;
   p.nb = (int)ceil_div(g.K, 64);
