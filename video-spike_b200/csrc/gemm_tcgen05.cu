@@ -773,10 +773,10 @@ rrr_bwd_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // owns 128 rows of c and HALF of the neurons ingests 26 KB per 64-trial box for a 128 x 72 tile -- that kernel runs at the
 // ingest limit (5.3 GB per launch, profiles/r01_ncu_dense_bwd.txt).  Here a CTA PAIR (cta_group::2, UMMA 256 x Npad) owns
 // 256 rows of c and ALL neurons: each CTA ingests its 128 rows of A and half of R (25 KB per box for a 128 x 144 tile, half
-// the bytes per flop).  The price is accumulator space: 128 x 3*Npad fp32 per CTA does not fit the register file next to
-// the D_t staging, so G_0 and G_1 live in TMEM next to D_t and are updated with tcgen05.ld / fma / tcgen05.st, G_2 in
-// registers.  D_t is single-buffered (3*Npad <= 512 columns): the next bin's MMAs start when every epilogue warp of the
-// pair has read D_t.
+// the bytes per flop).  The price is accumulator space: 128 x 3*Npad fp32 per CTA.  TMEM reads run at ~64 B/clk/SM, so as
+// much as possible lives in registers: the issuing warpgroup gives its registers away (setmaxnreg 40 / 232), the epilogue
+// threads keep G_1 and G_2 (2 x Npad/2 registers each); G_0 lives in TMEM next to the double-buffered D_t
+// (3*Npad <= 512 columns) and is updated with tcgen05.ld / fma / tcgen05.st.
 struct DensePairParams {
   int C1, m_tiles, Npad, T, K, Kp, nb;
   int stages, tmem_cols, f16, vbytes;
@@ -800,8 +800,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
+constexpr int DENSE_PAIR_THREADS = 384;   // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1-2: epilogue
+
 template <int HW8>   // 8-column chunks per epilogue thread (Npad / 16)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DENSE_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DENSE_PAIR_THREADS, 1)
 rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DensePairParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -811,14 +813,15 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int h = p.Npad >> 1;                                   // B rows per CTA = columns per epilogue thread
   const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)h * KB_BYTES;
   const uint32_t bar_full0 = base, bar_empty0 = base + 8u * 16;
-  const uint32_t bar_dfull = base + 8u * 32, bar_dempty = base + 8u * 33;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 34);
+  const uint32_t bar_dfull0 = base + 8u * 32, bar_dempty0 = base + 8u * 34;     // two D buffers
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 36);
   float* vsm = reinterpret_cast<float*>(base_ptr + CTRL_BYTES);
   const uint32_t tiles0 = base + CTRL_BYTES + (uint32_t)p.vbytes;
   const int m_tile = 2 * (int)(blockIdx.x >> 1) + rank;
   const int m_load = m_tile < p.m_tiles ? m_tile : p.m_tiles - 1;
+  const uint32_t Np = (uint32_t)p.Npad;                        // TMEM columns: D buffers at 0 and Npad, G_0 at 2*Npad
 
-  for (int e = threadIdx.x; e < DENSE_R * p.T; e += DENSE_THREADS) vsm[e] = (float)p.V[e];
+  for (int e = threadIdx.x; e < DENSE_R * p.T; e += DENSE_PAIR_THREADS) vsm[e] = (float)p.V[e];
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -826,12 +829,14 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(bar_full0 + 8u * s, 1);
       mbar_init(bar_empty0 + 8u * s, 1);
     }
-    mbar_init(bar_dfull, 1);
-    mbar_init(bar_dempty, 16);          // the 8 epilogue warps of both CTAs (only the leader's copy is waited on)
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_dfull0 + 8u * i, 1);
+      mbar_init(bar_dempty0 + 8u * i, 16);     // the 8 epilogue warps of both CTAs (only the leader's copies are waited on)
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 34), "r"((uint32_t)p.tmem_cols)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 36), "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -841,26 +846,28 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    int s = 0;
-    uint32_t ph = 0;
-    for (int t = 0; t < p.T; ++t) {
-      int col = t * p.Kp;
-      for (int i = 0; i < p.nb; ++i, col += 64) {
-        mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
-        if (elect_one()) {
-          const uint32_t a_dst = tiles0 + s * stage_bytes;
-          if (rank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, 2u * stage_bytes);
-          const uint32_t full = mapa_cluster(bar_full0 + 8u * s, 0);
-          tma_load_3d_pair(a_dst, &tmA, full, col, m_load * BM, 0);
-          tma_load_3d_pair(a_dst + A_TILE_BYTES, &tmB, full, col, rank * h, 0);
+  if (warp < 4) {
+    // ---- warpgroup 0 hands most of its registers to the epilogue warpgroups (two of the three accumulators live there)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < p.T; ++t) {
+        int col = t * p.Kp;
+        for (int i = 0; i < p.nb; ++i, col += 64) {
+          mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+          if (elect_one()) {
+            const uint32_t a_dst = tiles0 + s * stage_bytes;
+            if (rank == 0) mbar_arrive_expect_tx(bar_full0 + 8u * s, 2u * stage_bytes);
+            const uint32_t full = mapa_cluster(bar_full0 + 8u * s, 0);
+            tma_load_3d_pair(a_dst, &tmA, full, col, m_load * BM, 0);
+            tma_load_3d_pair(a_dst + A_TILE_BYTES, &tmB, full, col, rank * h, 0);
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-    }
-  } else if (warp == 1) {
-    if (rank == 0) {
+    } else if (warp == 1 && rank == 0) {
       const uint32_t idesc = make_idesc_pair(p.f16 != 0, p.Npad);
       const int lk = (p.K - (p.nb - 1) * 64 + 15) >> 4;
       const int last_ksteps = lk > 4 ? 4 : lk;
@@ -869,10 +876,12 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < p.T; ++t) {
-        if (t > 0) {                    // D_{t-1} has been read by every epilogue warp of the pair
-          mbar_wait(bar_dempty, (uint32_t)(t - 1) & 1u);
+        const int buf = t & 1;
+        if (t >= 2) {                   // every epilogue warp of the pair has drained bin t-2 from this D buffer
+          mbar_wait(bar_dempty0 + 8u * buf, (uint32_t)((t >> 1) - 1) & 1u);
           tc_fence_after();
         }
+        const uint32_t dcol = tmem_base + (uint32_t)buf * Np;
         for (int i = 0; i < p.nb; ++i) {
           mbar_wait(bar_full0 + 8u * s, ph);
           tc_fence_after();
@@ -880,12 +889,12 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const uint64_t da = desc0 + (uint64_t)(s * stage16);
             const uint64_t db = da + (uint64_t)b16;
             const int ksteps = (i == p.nb - 1) ? last_ksteps : 4;
-            tc_mma_pair(tmem_base, da, db, idesc, i > 0 ? 1u : 0u);
-            if (ksteps > 1) tc_mma_pair(tmem_base, da + 2, db + 2, idesc, 1u);
-            if (ksteps > 2) tc_mma_pair(tmem_base, da + 4, db + 4, idesc, 1u);
-            if (ksteps > 3) tc_mma_pair(tmem_base, da + 6, db + 6, idesc, 1u);
+            tc_mma_pair(dcol, da, db, idesc, i > 0 ? 1u : 0u);
+            if (ksteps > 1) tc_mma_pair(dcol, da + 2, db + 2, idesc, 1u);
+            if (ksteps > 2) tc_mma_pair(dcol, da + 4, db + 4, idesc, 1u);
+            if (ksteps > 3) tc_mma_pair(dcol, da + 6, db + 6, idesc, 1u);
             tc_commit_pair(bar_empty0 + 8u * s);
-            if (i == p.nb - 1) tc_commit_pair(bar_dfull);      // D_t complete in both CTAs
+            if (i == p.nb - 1) tc_commit_pair(bar_dfull0 + 8u * buf);      // D_t complete in both CTAs
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -893,56 +902,65 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
   } else {
-    const int q = warp & 3, hsel = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
     constexpr int W = HW8 * 8;              // columns per thread
     const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hsel * W);
-    const uint32_t t_g0 = t_d + (uint32_t)p.Npad, t_g1 = t_d + 2u * (uint32_t)p.Npad;
-    const uint32_t dempty_leader = mapa_cluster(bar_dempty, 0);
-    float g2[W];
+    const uint32_t t_g0 = t_d + 2u * Np;
+    const uint32_t dempty_leader0 = mapa_cluster(bar_dempty0, 0);
+    float g1[W], g2[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) g2[i] = 0.f;
+    for (int i = 0; i < W; ++i) g1[i] = g2[i] = 0.f;
     for (int t = 0; t < p.T; ++t) {
-      mbar_wait(bar_dfull, (uint32_t)t & 1u);
+      const int buf = t & 1;
+      mbar_wait(bar_dfull0 + 8u * buf, (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const float v0 = vsm[t], v1 = vsm[p.T + t], v2 = vsm[2 * p.T + t];
-#pragma unroll
-      for (int c = 0; c < HW8; c += 2) {      // 16 columns of D, G_0, G_1 per TMEM round trip
-        constexpr int kN = 16;
-        uint32_t d[kN], a0[kN], a1[kN];
-        const bool two = (c + 1 < HW8);
-        tc_ld8_issue(t_d + (uint32_t)(c * 8), d);
-        if (two) tc_ld8_issue(t_d + (uint32_t)(c * 8 + 8), d + 8);
+      const uint32_t td = t_d + (uint32_t)buf * Np;
+      // 16 columns of D and G_0 per TMEM round trip, software-pipelined: the loads of round r+1 are in flight while the
+      // FMAs and the G_0 store of round r run
+      constexpr int kN = 16, kRounds = (HW8 + 1) / 2;
+      uint32_t d[2][kN], a0[2][kN];
+      auto issue = [&](int r, int slot) {
+        const int c = 2 * r;
+        tc_ld8_issue(td + (uint32_t)(c * 8), d[slot]);
+        if (c + 1 < HW8) tc_ld8_issue(td + (uint32_t)(c * 8 + 8), d[slot] + 8);
         if (t > 0) {
-          tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0);
-          tc_ld8_issue(t_g1 + (uint32_t)(c * 8), a1);
-          if (two) {
-            tc_ld8_issue(t_g0 + (uint32_t)(c * 8 + 8), a0 + 8);
-            tc_ld8_issue(t_g1 + (uint32_t)(c * 8 + 8), a1 + 8);
-          }
+          tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0[slot]);
+          if (c + 1 < HW8) tc_ld8_issue(t_g0 + (uint32_t)(c * 8 + 8), a0[slot] + 8);
         } else {
 #pragma unroll
-          for (int i = 0; i < kN; ++i) a0[i] = a1[i] = 0u;
+          for (int i = 0; i < kN; ++i) a0[slot][i] = 0u;
         }
-        tc_wait_ld();
-        if (c + 2 >= HW8) {                   // last D columns are in registers: the tensor cores may overwrite D
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(dempty_leader);
-        }
+      };
+      auto release_d = [&]() {                 // every D column of this bin is in registers: the buffer may be overwritten
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(dempty_leader0 + 8u * (uint32_t)buf);
+      };
+      issue(0, 0);
+      tc_wait_ld();
+      if (kRounds == 1) release_d();
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int slot = r & 1, c = 2 * r;
+        const bool two = (c + 1 < HW8);
+        if (r + 1 < kRounds) issue(r + 1, slot ^ 1);
 #pragma unroll
         for (int i = 0; i < kN; ++i) {
           if (i < 8 || two) {
-            const float dv = __uint_as_float(d[i]);
-            g2[(c * 8 + i) < W ? (c * 8 + i) : 0] = fmaf(v2, dv, g2[(c * 8 + i) < W ? (c * 8 + i) : 0]);
-            a0[i] = __float_as_uint(fmaf(v0, dv, __uint_as_float(a0[i])));
-            a1[i] = __float_as_uint(fmaf(v1, dv, __uint_as_float(a1[i])));
+            const int col = (c * 8 + i) < W ? (c * 8 + i) : 0;
+            const float dv = __uint_as_float(d[slot][i]);
+            g1[col] = fmaf(v1, dv, g1[col]);
+            g2[col] = fmaf(v2, dv, g2[col]);
+            a0[slot][i] = __float_as_uint(fmaf(v0, dv, __uint_as_float(a0[slot][i])));
           }
         }
-        tc_st8(t_g0 + (uint32_t)(c * 8), a0);
-        tc_st8(t_g1 + (uint32_t)(c * 8), a1);
-        if (two) {
-          tc_st8(t_g0 + (uint32_t)(c * 8 + 8), a0 + 8);
-          tc_st8(t_g1 + (uint32_t)(c * 8 + 8), a1 + 8);
+        tc_st8(t_g0 + (uint32_t)(c * 8), a0[slot]);
+        if (two) tc_st8(t_g0 + (uint32_t)(c * 8 + 8), a0[slot] + 8);
+        if (r + 1 < kRounds) {
+          tc_wait_ld();
+          if (r + 2 == kRounds) release_d();
         }
       }
       tc_wait_st();
@@ -952,9 +970,8 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     float* grow = p.G + (long long)row * p.ldg + hsel * W;
 #pragma unroll
     for (int c = 0; c < HW8; ++c) {
-      uint32_t a0[8], a1[8];
+      uint32_t a0[8];
       tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0);
-      tc_ld8_issue(t_g1 + (uint32_t)(c * 8), a1);
       tc_wait_ld();
       if (row < p.C1) {
         float4* o0 = reinterpret_cast<float4*>(grow + c * 8);
@@ -962,8 +979,8 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         float4* o2 = reinterpret_cast<float4*>(grow + 2 * p.Npad + c * 8);
         o0[0] = make_float4(__uint_as_float(a0[0]), __uint_as_float(a0[1]), __uint_as_float(a0[2]), __uint_as_float(a0[3]));
         o0[1] = make_float4(__uint_as_float(a0[4]), __uint_as_float(a0[5]), __uint_as_float(a0[6]), __uint_as_float(a0[7]));
-        o1[0] = make_float4(__uint_as_float(a1[0]), __uint_as_float(a1[1]), __uint_as_float(a1[2]), __uint_as_float(a1[3]));
-        o1[1] = make_float4(__uint_as_float(a1[4]), __uint_as_float(a1[5]), __uint_as_float(a1[6]), __uint_as_float(a1[7]));
+        o1[0] = make_float4(g1[c * 8 + 0], g1[c * 8 + 1], g1[c * 8 + 2], g1[c * 8 + 3]);
+        o1[1] = make_float4(g1[c * 8 + 4], g1[c * 8 + 5], g1[c * 8 + 6], g1[c * 8 + 7]);
         o2[0] = make_float4(g2[c * 8 + 0], g2[c * 8 + 1], g2[c * 8 + 2], g2[c * 8 + 3]);
         o2[1] = make_float4(g2[c * 8 + 4], g2[c * 8 + 5], g2[c * 8 + 6], g2[c * 8 + 7]);
       }
@@ -1161,7 +1178,7 @@ static int launch_dense(const CUtensorMap& tmA, const CUtensorMap& tmB, const De
 template <int HW8>
 static int launch_dense_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const DensePairParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
   VS_CHECK_CUDA(cudaFuncSetAttribute(rrr_bwd_dense_pair_kernel<HW8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VS_LAUNCH(rrr_bwd_dense_pair_kernel<HW8>, grid, DENSE_THREADS, smem, stream, tmA, tmB, p);
+  VS_LAUNCH(rrr_bwd_dense_pair_kernel<HW8>, grid, DENSE_PAIR_THREADS, smem, stream, tmA, tmB, p);
   return VS_OK;
 }
 
