@@ -50,12 +50,12 @@ def peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
-def ncu_traffic(key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def ncu_traffic(key, field="bytes_per_launch_avg"):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
             ent = json.load(fh).get(key)
-        return int(ent["bytes_per_launch_avg"]) if ent else None            # bytes per launch
+        return int(ent[field]) if ent and field in ent else None            # bytes per launch
     except Exception:
         return None
 
@@ -290,27 +290,42 @@ def run_rrr(args, rank, world, local):
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
     clocks = sampler.stop()
     launches = int(vs.lib.vs_launch_count())
-    n_gemm, gemm_ms, gmin, gmax = vs.profile_read(0)
+    n_gemm, gemm_ms, gmin, gmax = vs.profile_read(0)          # forward GEMMs (train closures + the evaluation split)
+    n_bwd, bwd_ms, _, _ = vs.profile_read(2)                  # dense backward kernel (0 launches when VS_RRR_DENSE=0)
     vs.lib.vs_profile_enable(0)
     evals = (model.n_closure_evals - evals0) / args.steps
     value = world * K * FRAMES_PER_TRIAL / (ms * 1e-3)
 
-    # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs (2*K*T*C*N per contraction,
-    # i.e. the dense formulation) summed over the launches of the timed region / their summed duration
+    # roofline of the dominant kernel (the forward tcgen05 GEMM, Z = X U): algorithmic FLOPs (2*K*T*C*N per
+    # contraction, i.e. the dense formulation) summed over the launches of the timed region / their summed duration.
+    # With VS_RRR_DENSE=0 the factorised backward GEMM runs under the same tag and is counted the same way.
     C = F + 1
-    algo_flops = args.steps * (evals * 2 * (2.0 * K * 100 * C * N) + 2.0 * Kt * 100 * C * N)
-    exec_flops = args.steps * (evals * 2 * (2.0 * K * 100 * F * 3 * ((N + 15) // 16 * 16)) + 2.0 * Kt * 100 * F * 3 * ((N + 15) // 16 * 16)) * \
-        (1 if args.planes == 1 else (3 if args.planes == 2 else 6))
+    Np16 = (N + 15) // 16 * 16
+    plane_passes = 1 if args.planes == 1 else (3 if args.planes == 2 else 6)
+    n_contr = 1 if n_bwd > 0 else 2                             # contractions per closure evaluation under tag 0
+    algo_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * C * N) + 2.0 * Kt * 100 * C * N)
+    exec_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * F * 3 * Np16) + 2.0 * Kt * 100 * F * 3 * Np16) * plane_passes
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair, 16-bit operands)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak if peak else None,
-            "traffic": ncu_traffic(f"rrr_K{K}_F{F}_N{N}_planes{args.planes}"), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} bf16_tflops_sustained",
+    key = f"rrr_K{K}_F{F}_N{N}_planes{args.planes}"
+    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (forward Z = X U; tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+            "traffic": ncu_traffic(key), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)",
+            "peak_source": f"{pk_kind} bf16_tflops_sustained",
             "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
             "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
-            "note": "achieved counts ALGORITHMIC flops of the dense formulation; the factorised kernels execute r=3x that "
-                    "(executed_tflops)"}
+            "note": "achieved counts ALGORITHMIC flops of the dense formulation; the factorised forward executes r=3x that (executed_tflops)"}
+    if n_bwd > 0:
+        # second kernel of the closure: the per-time-bin dense backward streams Xb once (HBM-bound at a third of the flops)
+        Kp = (K + 15) // 16 * 16
+        bwd_bytes = 2.0 * F * 100 * Kp + 2.0 * Np16 * 100 * Kp + 4.0 * F * 3 * Np16      # Xb + R operand + G out
+        bw = bwd_bytes * n_bwd / (bwd_ms * 1e-3) / 1e9
+        roof["backward"] = {"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel (dU: D_t = X_t^T R_t per time bin in TMEM, rank-one updates in registers)",
+                            "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"],
+                            "traffic": ncu_traffic(key, "bwd_bytes_per_launch"), "launches": n_bwd, "avg_launch_ms": bwd_ms / n_bwd,
+                            "share_of_step": bwd_ms / (ms * args.steps),
+                            "algorithmic_tflops": 2.0 * K * 100 * C * N * n_bwd / (bwd_ms * 1e-3) / 1e12}
 
     # ---- parity of the timed configuration (outside every timed region): the same fit with 3 operand planes and a float64
     # L-BFGS history -- the mode the tests pin against the float64 reference to ~1e-6 -- on the same session

@@ -1207,7 +1207,7 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
   if (rc) return rc;
   const size_t smem = (size_t)CTRL_BYTES + 1024 + p.vbytes + (size_t)stages * stage_bytes;
   dim3 grid(2 * (unsigned)ceil_div(p.m_tiles, 2), 1, 1);
-  prof_begin(PROF_GEMM_TC, stream);
+  prof_begin(PROF_RRR_BWD, stream);
   switch (p.Npad / 16) {
     case 1: rc = launch_dense_pair<1>(tmA, tmB, p, grid, smem, stream); break;
     case 2: rc = launch_dense_pair<2>(tmA, tmB, p, grid, smem, stream); break;
@@ -1220,7 +1220,7 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
     case 9: rc = launch_dense_pair<9>(tmA, tmB, p, grid, smem, stream); break;
     default: rc = launch_dense_pair<10>(tmA, tmB, p, grid, smem, stream); break;
   }
-  prof_end(PROF_GEMM_TC, stream);
+  prof_end(PROF_RRR_BWD, stream);
   return rc;
 }
 
@@ -1258,7 +1258,7 @@ int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream) {
   if (rc) return rc;
   const size_t smem = (size_t)CTRL_BYTES + 1024 + p.vbytes + (size_t)stages * stage_bytes;
   dim3 grid(2 * (unsigned)ceil_div(g.C1, BM), 1, 1);
-  prof_begin(PROF_GEMM_TC, stream);
+  prof_begin(PROF_RRR_BWD, stream);
   switch (p.Npad / 16) {
     case 1: rc = launch_dense<1>(tmA, tmB, p, grid, smem, stream); break;
     case 2: rc = launch_dense<2>(tmA, tmB, p, grid, smem, stream); break;
@@ -1271,7 +1271,7 @@ int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream) {
     case 9: rc = launch_dense<9>(tmA, tmB, p, grid, smem, stream); break;
     default: rc = launch_dense<10>(tmA, tmB, p, grid, smem, stream); break;
   }
-  prof_end(PROF_GEMM_TC, stream);
+  prof_end(PROF_RRR_BWD, stream);
   return rc;
 }
 
