@@ -67,21 +67,33 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.t0 = [], None, gpu_index, None
 
     def start(self):
+        """Launch the sampling process (before the warm-up: nvidia-smi needs ~0.1 s to deliver its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def wait_first(self, timeout=1.5):
+        """Block until the sampling process has delivered its first line (so that it is running when the timed region starts)."""
+        t = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
+
+    def begin(self):
+        """Start of the timed region: only samples taken from here on are reported."""
+        self.t0 = time.perf_counter()
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
+        t1 = time.perf_counter()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,12 +101,17 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        smax = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.02]
+        in_region = len(rows)
+        if not rows:     # timed region shorter than one sampling period: the samples of the warm-up steps just before it (same load)
+            rows = [r for (ts, r) in self.rows if ts >= t0 - 0.5]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        smax = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_in_timed_region": in_region}
 
 
 # ----------------------------------------------------------------------------- distributed plumbing
@@ -276,13 +293,14 @@ def run_rrr(args, rank, world, local):
             _, res = train_model(model, td, opt, "tmp", save=False)
         return res["mse_val_mean"]
 
+    sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
     for _ in range(args.warmup):
         one_fit()
     torch.cuda.synchronize(); barrier(world)
-    sampler = ClockSampler(local); sampler.start()
     vs.lib.vs_launch_count_reset(); vs.lib.vs_profile_enable(1)
     evals0 = model.n_closure_evals
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         mse = one_fit()
@@ -449,12 +467,13 @@ def run_linear(args, rank, world, local):
 
     import warnings
     warnings.filterwarnings("ignore", message="Detected call of `lr_scheduler.step")
+    sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
     for i in range(args.warmup):
         step(i, frames_d, ap_d)
     torch.cuda.synchronize(); barrier(world)
-    sampler = ClockSampler(local); sampler.start()
     vs.lib.vs_launch_count_reset(); vs.lib.vs_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     e0.record()
     for i in range(args.steps):
         loss = step(i, frames_d, ap_d)
