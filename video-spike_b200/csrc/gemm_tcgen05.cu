@@ -33,6 +33,7 @@ struct KParams {
   int n_pass;
   int pa[kMaxPass], pb[kMaxPass];
   int stages;
+  int kb_group;     // consecutive k-blocks per pipeline stage (1, or 4 for skinny tiles: longer contiguous reads per operand row)
   int tmem_cols;
   int f16;          // 16-bit operand format: 0 = bf16, 1 = IEEE half
   float* C;
@@ -190,7 +191,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)p.BN * KB_BYTES;
+  const uint32_t kb_bytes = A_TILE_BYTES + (uint32_t)p.BN * KB_BYTES;   // one k-block: A tile + B tile
+  const uint32_t stage_bytes = kb_bytes * (uint32_t)p.kb_group;         // a stage holds kb_group consecutive k-blocks
   const uint32_t tiles0 = base + CTRL_BYTES;
   const uint32_t bar_full0 = base;                 // stages x 8 B
   const uint32_t bar_empty0 = base + 8u * 16;      // stages x 8 B (stages <= 16)
@@ -209,7 +211,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tile = tile / n_tiles, n_tile = tile % n_tiles;
   const int kb0 = split * kbps;
   const int kb1 = min(p.num_kb, kb0 + kbps);
-  const int iters = (kb1 > kb0 ? kb1 - kb0 : 0) * p.n_pass;
+  const int groups = kb1 > kb0 ? (kb1 - kb0 + p.kb_group - 1) / p.kb_group : 0;
+  const int iters = groups * p.n_pass;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -231,53 +234,69 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Both issuing roles run with the whole warp converged and elect one lane per instruction group (see gemm_tn_pair_kernel):
+  // no ELECT / BRA.U.ANY retry loops around the uniform-datapath instructions, no integer division per stage.  This matters
+  // most for the first Linear layer (N = 16: ~30 clk of tensor work per stage).
   if (warp == 0) {
-    // ===== TMA producer (one elected lane) =====
-    if (lane == 0) {
-      const int elems_per_kb = kTF32 ? 32 : 64;
-      int it = 0;
-      for (int ps = 0; ps < p.n_pass; ++ps) {
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
-          const uint32_t a_dst = tiles0 + s * stage_bytes;
-          const uint32_t b_dst = a_dst + A_TILE_BYTES;
+    // ===== TMA producer =====
+    const int elems_per_kb = kTF32 ? 32 : 64;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ps = 0; ps < p.n_pass; ++ps) {
+      const int pa = p.pa[ps], pb = p.pb[ps];
+      for (int kb = kb0; kb < kb1; kb += p.kb_group) {
+        mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+        if (elect_one()) {
           const uint32_t full = bar_full0 + 8u * s;
           mbar_arrive_expect_tx(full, stage_bytes);
-          tma_load_3d(a_dst, &tmA, full, kb * elems_per_kb, m_tile * BM, p.pa[ps]);
-          for (int t = 0; t < p.n_tb; ++t)
-            tma_load_3d(b_dst + (uint32_t)(t * p.tb_rows) * KB_BYTES, &tmB, full, kb * elems_per_kb,
-                        n_tile * p.BN + t * p.tb_rows, p.pb[ps]);
+          // consecutive k-blocks of the same rows back to back: each operand row is read in kb_group * 128 contiguous bytes
+          // (k-blocks past the end of the split are zero-filled by TMA and add nothing)
+          for (int g = 0; g < p.kb_group; ++g) {
+            const uint32_t a_dst = tiles0 + s * stage_bytes + (uint32_t)g * kb_bytes;
+            const int kcol = (kb + g < kb1 ? kb + g : p.num_kb) * elems_per_kb;
+            tma_load_3d(a_dst, &tmA, full, kcol, m_tile * BM, pa);
+          }
+          for (int g = 0; g < p.kb_group; ++g) {
+            const uint32_t b_dst = tiles0 + s * stage_bytes + (uint32_t)g * kb_bytes + A_TILE_BYTES;
+            const int kcol = (kb + g < kb1 ? kb + g : p.num_kb) * elems_per_kb;
+            for (int t = 0; t < p.n_tb; ++t)
+              tma_load_3d(b_dst + (uint32_t)(t * p.tb_rows) * KB_BYTES, &tmB, full, kcol, n_tile * p.BN + t * p.tb_rows, pb);
+          }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one lane) =====
-    if (lane == 0) {
-      const int n0 = p.BN > 256 ? 256 : p.BN;      // first UMMA N chunk
-      const int n1 = p.BN - n0;                    // second chunk (0 or a multiple of 16)
-      const uint32_t idesc0 = make_idesc(kTF32, p.f16 != 0, n0);
-      const uint32_t idesc1 = make_idesc(kTF32, p.f16 != 0, n1 > 0 ? n1 : 16);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(bar_full0 + 8u * s, ph);
-        tc_fence_after();
-        const uint32_t a_addr = tiles0 + s * stage_bytes;
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
-        const uint64_t da = make_smem_desc(a_addr);
-        const uint64_t db0 = make_smem_desc(b_addr);
-        const uint64_t db1 = make_smem_desc(b_addr + 256u * KB_BYTES);
+    // ===== MMA issuer =====
+    const int n0 = p.BN > 256 ? 256 : p.BN;      // first UMMA N chunk
+    const int n1 = p.BN - n0;                    // second chunk (0 or a multiple of 16)
+    const uint32_t idesc0 = make_idesc(kTF32, p.f16 != 0, n0);
+    const uint32_t idesc1 = make_idesc(kTF32, p.f16 != 0, n1 > 0 ? n1 : 16);
+    const uint64_t desc0 = make_smem_desc(tiles0);
+    const uint32_t stage16 = stage_bytes >> 4, kb16 = kb_bytes >> 4, b16 = A_TILE_BYTES >> 4, b1_16 = (256u * KB_BYTES) >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(bar_full0 + 8u * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int g = 0; g < p.kb_group; ++g) {
+          const uint64_t da = desc0 + (uint64_t)(s * stage16 + g * kb16);
+          const uint64_t db0 = da + (uint64_t)b16;
+          const uint64_t db1 = db0 + (uint64_t)b1_16;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 UMMA K-steps of 32 B inside the 128 B atom
-          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-          tc_mma<kTF32>(tmem_base, da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc0, acc);
-          if (n1 > 0) tc_mma<kTF32>(tmem_base + 256u, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc1, acc);
+          for (int k = 0; k < 4; ++k) {  // 4 UMMA K-steps of 32 B inside the 128 B atom
+            const uint32_t acc = (it > 0 || g > 0 || k > 0) ? 1u : 0u;
+            tc_mma<kTF32>(tmem_base, da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc0, acc);
+            if (n1 > 0) tc_mma<kTF32>(tmem_base + 256u, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc1, acc);
+          }
         }
         tc_commit(bar_empty0 + 8u * s);  // frees the smem slot when these MMAs retire
+        if (it == iters - 1) tc_commit(bar_tmem);   // accumulator complete
       }
-      tc_commit(bar_tmem);               // accumulator complete
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> global =====
@@ -1296,7 +1315,13 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   splits = (int)ceil_div(p.num_kb, p.kb_per_split);
   p.n_pass = g.n_pass;
   for (int i = 0; i < kMaxPass; ++i) { p.pa[i] = i < g.n_pass ? g.pa[i] : 0; p.pb[i] = i < g.n_pass ? g.pb[i] : 0; }
-  const int stage_bytes = A_TILE_BYTES + BN * KB_BYTES;
+  // skinny tiles (first Linear layer: N = 16, pitch 7.8 MB): group 4 k-blocks per stage so that every operand row is read in
+  // 512 contiguous bytes instead of 128 (DRAM page locality); VS_GEMM_KBGROUP overrides
+  int kb_group = (BN <= 64 && p.kb_per_split >= 64) ? 4 : 1;
+  { const char* e = getenv("VS_GEMM_KBGROUP"); if (e && atoi(e) >= 1 && atoi(e) <= 8) kb_group = atoi(e); }
+  if (kb_group > 1 && (A_TILE_BYTES + BN * KB_BYTES) * kb_group * 2 > 220 * 1024) kb_group = 1;
+  p.kb_group = kb_group;
+  const int stage_bytes = (A_TILE_BYTES + BN * KB_BYTES) * kb_group;
   const int max_smem = 227 * 1024;
   int stages = (max_smem - CTRL_BYTES - 1024) / stage_bytes;
   if (stages > 8) stages = 8;
