@@ -183,7 +183,8 @@ def test_rrr_closure_matches_oracle(vs, cuda, engine, planes, operand, rtol):
     assert np.abs(err).max() <= 3.0 * rtol * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("K,F,N", [(30, 200, 21), (37, 300, 144), (64, 129, 33), (16, 260, 160), (100, 520, 5), (130, 400, 150)])
+@pytest.mark.parametrize("K,F,N", [(30, 200, 21), (37, 300, 144), (64, 129, 33), (16, 260, 160), (100, 520, 5), (130, 400, 150), (5, 300, 7),
+                                   (70, 140, 64)])
 def test_rrr_dense_backward_matches_factorised_and_oracle(vs, cuda, monkeypatch, K, F, N):
     """The per-time-bin dense backward (rrr_bwd_dense_kernel: D_t in TMEM, rank-one updates by the epilogue warps) against the
     factorised GEMM-B route and float64: trial counts that are no multiple of 16 (zero-padded residual operand, boxes that start

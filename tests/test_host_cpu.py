@@ -232,3 +232,15 @@ def test_select_frames_is_the_reference_draw(golden_dir):
     g = np.load(os.path.join(golden_dir, "metrics_kat.npz"))
     set_seed(42)
     np.testing.assert_array_equal(select_frames(), g["sorted_idx"])
+
+
+def test_rrr_pitch_helpers():
+    """vs_rrr_ldc / vs_rrr_ldr are host-only: Xa rows are padded to 64 features, the backward operand pads every time bin to
+    16 trials (a bin starts 32-byte aligned and ends on a tensor-core K-step) and its rows to 64 columns."""
+    import vsb200 as vs
+    for C1 in (1, 64, 65, 18260):
+        assert vs.lib.vs_rrr_ldc(C1) == (C1 + 63) // 64 * 64
+    for K, T in ((1, 1), (5, 100), (16, 100), (37, 100), (400, 100), (401, 7)):
+        Kp = (K + 15) // 16 * 16
+        assert vs.lib.vs_rrr_ldr(K, T) == (T * Kp + 63) // 64 * 64
+        assert vs.lib.vs_rrr_ldr(K, T) >= T * K

@@ -433,28 +433,48 @@ __global__ void __launch_bounds__(128) reduce_part_kernel(const float* __restric
 }
 
 // final scalars: sse_n, loss, dV
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv_part,
+__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv_part,
                                                        const double* __restrict__ G, const double* __restrict__ W,
                                                        const double* __restrict__ V, const double* __restrict__ b, long long KB,
                                                        long long NT, long long T, long long N, int r, double l2, double* __restrict__ sse_n,
                                                        double* __restrict__ loss, double* __restrict__ dV) {
-  __shared__ double red[256];
+  __shared__ double red[1024];      // one block of 1024 threads: every loop below is a latency chain, so more lanes = shorter chains
   // per-neuron SSE (src/model/rrr.py:151) and its total
   double tot = 0.0;
-  for (long long n = threadIdx.x; n < N; n += 256) {
-    double s = 0.0;
+  if (N <= 512) {
+    // P threads per neuron, each over every P-th time bin; the P partial sums are then added in a fixed order
+    __shared__ double sp[1024];
+    const int P = 1024 / (int)N;
+    const int part = threadIdx.x / (int)N, n = threadIdx.x % (int)N;
+    if (part < P) {
+      double s = 0.0;
+#pragma unroll 4
+      for (long long t = part; t < T; t += P) s += sse_tn[t * N + n];
+      sp[part * N + n] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+      double s = 0.0;
+      for (int q = 0; q < P; ++q) s += sp[q * N + threadIdx.x];
+      if (sse_n) sse_n[threadIdx.x] = s;
+      tot += s;
+    }
+  } else {
+    for (long long n = threadIdx.x; n < N; n += 1024) {
+      double s = 0.0;
 #pragma unroll 10
-    for (long long t = 0; t < T; ++t) s += sse_tn[t * N + n];      // independent loads: unrolled so they overlap
-    if (sse_n) sse_n[n] = s;
-    tot += s;
+      for (long long t = 0; t < T; ++t) s += sse_tn[t * N + n];      // independent loads: unrolled so they overlap
+      if (sse_n) sse_n[n] = s;
+      tot += s;
+    }
   }
   // sum b^2 (the intercept is part of beta: SURVEY A14)
   double bsq = 0.0;
 #pragma unroll 8
-  for (long long i = threadIdx.x; i < N * T; i += 256) bsq += b[i] * b[i];
+  for (long long i = threadIdx.x; i < N * T; i += 1024) bsq += b[i] * b[i];
   red[threadIdx.x] = tot + l2 * bsq;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = 512; s > 0; s >>= 1) {
     if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
     __syncthreads();
   }
@@ -464,7 +484,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
     *loss = red[0] + l2 * gw;
   }
   if (dV) {
-    for (long long e = threadIdx.x; e < (long long)r * T; e += 256) {
+    for (long long e = threadIdx.x; e < (long long)r * T; e += 1024) {
       const long long j = e / T, t = e % T;
       double s = 0.0;
 #pragma unroll 7
@@ -767,7 +787,7 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   }
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
   VS_LAUNCH(reduce_part_kernel, g2, 128, 0, st, w.sse_part, w.db_part, b, w.KB, (long long)d.T, (long long)d.N, l2, db, w.sse_tn);
-  VS_LAUNCH(finalize_kernel, 1, 256, 0, st, w.sse_tn, w.pv_part, w.G, w.W, V, b, w.KB, (long long)ceil_div(d.N, 32), (long long)d.T,
+  VS_LAUNCH(finalize_kernel, 1, 1024, 0, st, w.sse_tn, w.pv_part, w.G, w.W, V, b, w.KB, (long long)ceil_div(d.N, 32), (long long)d.T,
             (long long)d.N, r, l2, sse_n, loss, dV);
   if (dU) {
     // stage 3/4: Gacc and dU
