@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 5
+#define VS_ABI_VERSION 6
 
 enum {
   VS_OK = 0,
