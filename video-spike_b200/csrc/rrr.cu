@@ -117,6 +117,81 @@ __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ X,
   }
 }
 
+// Single-plane pack from uint8 frames, wide tile: 32 trials (of ONE time bin) x 128 features per block.  Every thread
+// reads 4 consecutive pixels as ONE 32-bit load (128 B per trial row), writes them as 4 packed 16-bit values of Xa
+// (256 B per row) and, after a shared-memory transpose, 2 trials of one feature row of Xb per thread (64 B per feature).
+// Same arithmetic as the fast path of pack_kernel ((x - mean) * (1/std) in fp32); that kernel moved 32-byte row segments
+// with byte loads and ran at 1.5 TB/s.
+__global__ void __launch_bounds__(256) pack_u8_wide_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ sorted_idx,
+                                                           const double* __restrict__ mean, const double* __restrict__ sd, long long Tf,
+                                                           long long K, long long T, long long C1, int fmt, long long ldc, long long ldr,
+                                                           uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xb, float* __restrict__ xl,
+                                                           int* __restrict__ overflow) {
+  __shared__ uint16_t tile[128][34];          // [feature][trial], 2 trials per 32-bit word, odd word pitch
+  __shared__ float s_mean[128], s_istd[128];
+  const long long kblocks = (K + 31) / 32;
+  const long long t = blockIdx.x / kblocks, k0 = (blockIdx.x % kblocks) * 32;
+  const long long c0 = (long long)blockIdx.y * 128, Kp = (K + 15) / 16 * 16;
+  const long long f = sorted_idx[t];
+  if (threadIdx.x < 128) {
+    const long long c = c0 + threadIdx.x;
+    const long long col = f * C1 + (c < C1 ? c : C1 - 1);
+    s_mean[threadIdx.x] = (float)mean[col];
+    s_istd[threadIdx.x] = (float)(1.0 / sd[col]);
+  }
+  __syncthreads();
+  const int cx = (threadIdx.x & 31) * 4, ry = threadIdx.x >> 5;      // 4 features per thread, 8 trial rows per pass
+  bool ovf = false;
+#pragma unroll
+  for (int rr = ry; rr < 32; rr += 8) {
+    const long long k = k0 + rr, c = c0 + cx;
+    uint16_t v[4] = {0, 0, 0, 0};
+    if (k < K && c < C1) {
+      const uint8_t* src = frames + (k * Tf + f) * C1 + c;
+      uint32_t w;
+      if (c + 4 <= C1 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+        w = __ldg(reinterpret_cast<const uint32_t*>(src));
+      } else {
+        w = 0;
+        for (int i = 0; i < 4; ++i)
+          if (c + i < C1) w |= (uint32_t)src[i] << (8 * i);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float vf = ((float)((w >> (8 * i)) & 0xff) - s_mean[cx + i]) * s_istd[cx + i];
+        if (fmt == VS_OPERAND_F16 && !(fabsf(vf) <= 65504.f)) ovf = true;
+        v[i] = (c + i < C1) ? enc16(vf, fmt) : (uint16_t)0;
+      }
+      uint16_t* dst = Xa + (t * K + k) * ldc + c;
+      if (c + 4 <= C1) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));   // ldc % 8 == 0, c % 4 == 0
+      } else {
+        for (int i = 0; i < 4; ++i)
+          if (c + i < C1) dst[i] = v[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tile[cx + i][rr] = v[i];
+  }
+  if (ovf && overflow) atomicOr(overflow, 1);
+  __syncthreads();
+  // Xb[c][t*Kp + k]: 16 threads per feature row, 2 trials (one 32-bit store) each; 16 feature rows per pass
+  const int kp = (threadIdx.x & 15) * 2, cr = threadIdx.x >> 4;
+#pragma unroll
+  for (int cc = cr; cc < 128; cc += 16) {
+    const long long c = c0 + cc, k = k0 + kp;
+    if (c < C1 && k < K) {
+      uint16_t* dst = Xb + c * ldr + t * Kp + k;
+      if (k + 1 < K) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)tile[cc][kp] | ((uint32_t)tile[cc][kp + 1] << 16);   // Kp, k0, kp even
+      else dst[0] = tile[cc][kp];
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.x < 32) {
+    const long long k = k0 + threadIdx.x;
+    if (k < K) xl[t * K + k] = 1.0f;
+  }
+}
+
 // zeros in the pad trials K <= k < Kp of every time bin of Xb (one thread per (plane, c, t))
 __global__ void __launch_bounds__(256) pad_zero_kernel(uint16_t* __restrict__ Xb, long long rows, long long T, long long K, long long Kp,
                                                        long long ldr) {
@@ -734,6 +809,16 @@ extern "C" int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* 
   int rc = check_dims(d);
   if (rc) return rc;
   VS_REQUIRE(frames && sorted_idx && mean && std_clipped && Xa && Xb && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8: bad arguments");
+  if (d.planes == 1 && d.ldr % 2 == 0) {
+    dim3 gw((unsigned)(ceil_div(d.K, 32) * d.T), (unsigned)ceil_div(d.C1, 128));
+    VS_REQUIRE(gw.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8: too many columns");
+    VS_LAUNCH(pack_u8_wide_kernel, gw, 256, 0, stream, frames, sorted_idx, mean, std_clipped, (long long)Tf, (long long)d.K, (long long)d.T,
+              (long long)d.C1, (int)d.fmt, (long long)d.ldc, (long long)d.ldr, Xa, Xb, xl, overflow_flag);
+    if (round_up(d.K, 16) > d.K)
+      VS_LAUNCH(pad_zero_kernel, (unsigned)ceil_div((long long)d.planes * d.C1 * d.T, 256), 256, 0, stream, Xb, (long long)d.planes * d.C1,
+                (long long)d.T, (long long)d.K, (long long)round_up(d.K, 16), (long long)d.ldr);
+    return VS_OK;
+  }
   dim3 grid((unsigned)(ceil_div(d.K, 32) * d.T), (unsigned)ceil_div(d.C1, 32));
   VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8: too many columns");
   VS_LAUNCH((pack_kernel<true>), grid, 256, 0, stream, nullptr, frames, sorted_idx, mean, std_clipped, (long long)Tf, 0ll,
