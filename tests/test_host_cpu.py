@@ -244,3 +244,25 @@ def test_rrr_pitch_helpers():
         Kp = (K + 15) // 16 * 16
         assert vs.lib.vs_rrr_ldr(K, T) == (T * Kp + 63) // 64 * 64
         assert vs.lib.vs_rrr_ldr(K, T) >= T * K
+
+
+def test_argument_validation_needs_no_gpu():
+    """The C-ABI validates its arguments before it touches CUDA: empty / inconsistent shapes and null buffers come back as
+    error codes with a message (never an exception, never a launch), which is also what a CPU-only box observes."""
+    import vsb200 as vs
+    C1, K, T, N = 200, 30, 100, 21
+    good = vs.RrrDims(K, T, C1, N, 3, 1, vs.lib.vs_rrr_ldc(C1), vs.lib.vs_rrr_ldr(K, T), 0)
+    assert vs.lib.vs_rrr_workspace(good) > 0
+    for bad in (vs.RrrDims(0, T, C1, N, 3, 1, good.ldc, good.ldr, 0),          # no trials
+                vs.RrrDims(K, T, C1, 0, 3, 1, good.ldc, good.ldr, 0)):         # no neurons
+        assert vs.lib.vs_rrr_workspace(bad) == 0
+    def closure_rc(d):
+        return vs.lib.vs_rrr_closure(d, None, None, None, None, None, None, None, 100.0, None, None, None, None, None, 0, None, 0, None)
+    assert closure_rc(vs.RrrDims(0, T, C1, N, 3, 1, good.ldc, good.ldr, 0)) != 0
+    assert b"empty" in vs.lib.vs_last_error()
+    assert closure_rc(vs.RrrDims(K, T, C1, N, 3, 4, good.ldc, good.ldr, 0)) != 0            # planes out of range
+    assert closure_rc(vs.RrrDims(K, T, C1, N, 3, 1, good.ldc, K * T, 0)) != 0               # pitch ignores the padded time bins
+    assert b"pitch" in vs.lib.vs_last_error()
+    assert closure_rc(vs.RrrDims(K, T, C1, N, 3, 1, good.ldc, good.ldr, 7)) != 0            # unknown operand format
+    assert closure_rc(good) != 0 and b"null" in vs.lib.vs_last_error()                      # valid shape, null buffers
+    assert vs.lib.vs_u8_to_f32(None, None, 16, None) != 0
