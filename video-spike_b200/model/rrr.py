@@ -247,7 +247,9 @@ class RRRGD():
                 history_dtype = torch.float32 if self.planes == 1 else torch.float64
         if device_driven is None:     # decisions on the device, no host sync per iteration (optim.FusedLBFGS); VS_LBFGS_DEVICE=0 disables
             device_driven = os.environ.get("VS_LBFGS_DEVICE", "1") != "0"
-        return FusedLBFGS(self.model.parameters(), history_dtype=history_dtype, device_driven=device_driven)
+        opt = FusedLBFGS(self.model.parameters(), history_dtype=history_dtype, device_driven=device_driven)
+        opt.closure_overwrites_grads = True     # loss_and_grad writes every gradient element (see there): zero_grad() need not memset
+        return opt
 
     def train(self):
         self.model.train()
@@ -350,6 +352,10 @@ class RRRGD():
         for eid in data:
             loss, _, dU, db = self._closure_eval(data, eid, k, True, dV)
             total = loss if total is None else total + loss
+        for eid in self.eids:                       # sessions the caller left out contribute nothing: their gradients are zero,
+            if eid not in data:                     # never stale (make_optimizer() promises that every element is written)
+                for name in (f"{eid}_U", f"{eid}_b"):
+                    self._grad_buffer(self.model[name]).zero_()
         self.n_closure_evals += 1
         return total
 
