@@ -265,7 +265,8 @@ def run_rrr(args, rank, world, local):
     K, Kt, F, N = args.trials, args.trials_test, args.features, args.neurons
     sidx = sorted_idx_42()
     ftr, ctr, fte, cte = rrr_inputs(K, Kt, F, N, seed=rank, pinned=True)
-    h2d = ftr.numel() + fte.numel() + 4 * (ctr.numel() + cte.numel())
+    # bytes that cross PCIe per fit: the 100 selected frames of every trial (vs_h2d_select_frames) + the spike counts
+    h2d = (ftr.numel() + fte.numel()) // ftr.shape[1] * len(sidx) + 4 * (ctr.numel() + cte.numel())
 
     # ---- resident-input measurement: operands packed once, fit repeated
     entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=args.planes, device=dev)

@@ -63,6 +63,14 @@ int vs_u8_to_bf16(const uint8_t* frames, uint16_t* out_bf16, int64_t n, void* st
 int vs_gather_windows(const uint8_t* frames, int64_t n_frames, int64_t row_bytes, const int64_t* start_idx,
                       int64_t n_trials, int64_t frames_per_trial, uint8_t* out, void* stream);
 
+/* Upload of the frames a model actually reads.  src/train_rrr.py:48-49,171 keeps T = 100 of the 120 frames of every trial
+ * (`X[:, sorted_idx]`, selected AFTER the per-frame z-score, so unselected frames never influence the fit): this copies
+ * host_frames[k, idx_host[t], :] -> dev_out[k, t, :] for all K trials, one strided DMA (cudaMemcpy2DAsync) per run of
+ * consecutive indices, on `stream`.  host_frames (K, Tf, row_bytes) uint8 in HOST memory (pinned for an asynchronous copy),
+ * idx_host (T) strictly increasing int32 in HOST memory, dev_out (K, T, row_bytes) on the device.  Byte copy, bit-exact.   */
+int vs_h2d_select_frames(const uint8_t* host_frames, int64_t K, int64_t Tf, int64_t row_bytes, const int32_t* idx_host,
+                         int64_t T, uint8_t* dev_out, void* stream);
+
 /* ------------------------------------------------------------------ Linear layers (M1-M3, G1)
  * torch.nn.Linear / ReLU as used by src/model/linear.py:24-32,45-53.
  *   y[b,o] = act( sum_i x[b,i] * W[o,i] + bias[o] ),  W is (out,in) row-major like nn.Linear.

@@ -339,6 +339,39 @@ def test_rrr_device_preprocessing_matches_oracle(vs, cuda):
     np.testing.assert_allclose(yz.cpu().numpy(), data["y"][0], rtol=2e-4, atol=2e-5)
 
 
+def test_selective_frame_upload_is_byte_exact_and_changes_nothing(vs, cuda):
+    """vs_h2d_select_frames (only the T selected frames of a trial cross PCIe) vs uploading everything: the same bytes on the
+    device, and pack_session_from_frames builds bit-identical operands either way (the statistics of a frame depend on that
+    frame alone, src/train_rrr.py:108-171)."""
+    from model.rrr import pack_session_from_frames
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=9, K=21, Kt=6, F=131, N=7, raw=True)
+    ftr, fte = torch.from_numpy(Xtr).pin_memory(), torch.from_numpy(Xte).pin_memory()
+    idx = np.ascontiguousarray(sidx, dtype=np.int32)
+    out = torch.zeros((ftr.shape[0], len(idx), ftr.shape[2]), dtype=torch.uint8, device=cuda)
+    vs.check(vs.lib.vs_h2d_select_frames(ftr.data_ptr(), ftr.shape[0], ftr.shape[1], ftr.shape[2], idx.ctypes.data, len(idx), vs.ptr(out), vs.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ftr[:, torch.from_numpy(sidx.astype(np.int64))])
+    bad = idx[::-1].copy()
+    assert vs.lib.vs_h2d_select_frames(ftr.data_ptr(), ftr.shape[0], ftr.shape[1], ftr.shape[2], bad.ctypes.data, len(bad), vs.ptr(out), vs.stream()) != 0
+    ctr, cte = torch.from_numpy(ytr).float(), torch.from_numpy(yte).float()
+    a = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=1)                       # host frames: selective upload
+    b = pack_session_from_frames(ftr.to(cuda), ctr, fte.to(cuda), cte, sidx, 3, planes=1)     # device frames: everything is there
+    c = pack_session_from_frames(ftr, ctr, fte.to(cuda), cte, sidx, 3, planes=1)              # mixed
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        for other in (b, c):
+            a["X"][k].wait_ready(); other["X"][k].wait_ready()
+            K, T = a["X"][k].K, a["X"][k].T
+            Kp = (K + 15) // 16 * 16
+            F = ftr.shape[2]
+            assert torch.equal(a["X"][k].Xa[:, :, :F], other["X"][k].Xa[:, :, :F])          # (columns F..ldc are padding, never read)
+            assert torch.equal(a["X"][k].Xb[:, :, :T * Kp], other["X"][k].Xb[:, :, :T * Kp])
+            assert torch.equal(a["X"][k].y, other["X"][k].y) and torch.equal(a["X"][k].xl, other["X"][k].xl)
+    sel = torch.from_numpy(sidx.astype(np.int64)).to(cuda)
+    ma = a["setup"]["mean_X_Tv"].view(ftr.shape[1], -1); mb = b["setup"]["mean_X_Tv"].view(ftr.shape[1], -1)
+    assert torch.equal(ma[sel], mb[sel]) and torch.isnan(ma).sum() == (ftr.shape[1] - len(idx)) * ftr.shape[2]
+
+
 def test_joint_model_through_sharded_optimizer_world1(vs, cuda):
     """parallel.train_joint_model on one rank == train_model with FusedLBFGS on the same joint two-session model
     (the world_size-2 equivalence of ShardedLBFGS is covered on CPU/gloo in tests/test_distributed_cpu.py and on two

@@ -495,6 +495,25 @@ extern "C" int vs_u8_to_bf16(const uint8_t* frames, uint16_t* out, int64_t n, vo
   return VS_OK;
 }
 
+extern "C" int vs_h2d_select_frames(const uint8_t* host_frames, int64_t K, int64_t Tf, int64_t row_bytes, const int32_t* idx_host,
+                                    int64_t T, uint8_t* dev_out, void* stream) {
+  VS_REQUIRE(host_frames && idx_host && dev_out && K > 0 && Tf > 0 && row_bytes > 0 && T > 0 && T <= Tf, VS_ERR_INVALID,
+             "vs_h2d_select_frames: bad arguments");
+  for (int64_t t = 0; t < T; ++t)
+    VS_REQUIRE(idx_host[t] >= 0 && idx_host[t] < Tf && (t == 0 || idx_host[t] > idx_host[t - 1]), VS_ERR_INVALID,
+               "vs_h2d_select_frames: indices must be strictly increasing and inside [0, %lld)", (long long)Tf);
+  int64_t t = 0;
+  while (t < T) {                       // one 2-D copy per run of consecutive frame indices: K rows of (run * row_bytes) bytes
+    int64_t e = t + 1;
+    while (e < T && idx_host[e] == idx_host[e - 1] + 1) ++e;
+    VS_CHECK_CUDA(cudaMemcpy2DAsync(dev_out + t * row_bytes, (size_t)(T * row_bytes), host_frames + (int64_t)idx_host[t] * row_bytes,
+                                    (size_t)(Tf * row_bytes), (size_t)((e - t) * row_bytes), (size_t)K, cudaMemcpyHostToDevice,
+                                    (cudaStream_t)stream));
+    t = e;
+  }
+  return VS_OK;
+}
+
 extern "C" int vs_gather_windows(const uint8_t* frames, int64_t n_frames, int64_t row_bytes, const int64_t* start_idx,
                                  int64_t n_trials, int64_t frames_per_trial, uint8_t* out, void* stream) {
   VS_REQUIRE(frames && start_idx && out && n_frames > 0 && row_bytes > 0 && frames_per_trial > 0 && n_trials >= 0, VS_ERR_INVALID,

@@ -444,8 +444,12 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
     vs.require_b200()
     device = device or torch.device("cuda")
     st = vs.stream()
-    idx = torch.as_tensor(np.asarray(sorted_idx), dtype=torch.int32).to(device)
+    idx_np = np.ascontiguousarray(np.asarray(sorted_idx), dtype=np.int32)
+    idx = torch.as_tensor(idx_np).to(device)
     T = int(idx.numel())
+    idx_compact = torch.arange(T, dtype=torch.int32, device=device)
+    host_select = T > 0 and bool(np.all(np.diff(idx_np) > 0))       # vs_h2d_select_frames wants strictly increasing indices
+    compact_stats = False
     fmt = operand_format(planes, operand)
     splits, ys = [], []
     mean = sd = my = sy = None
@@ -469,19 +473,32 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
             #                                         side stream if the split dies unread, so they are never recycled early)
         with torch.cuda.stream(side if which == 1 else main):
             st = vs.stream()
-            fr = fr.to(device, non_blocking=True).reshape(K, Tf, -1).contiguous()
+            if host_select and not fr.is_cuda and fr.dtype == torch.uint8 and fr.is_contiguous() and T < Tf \
+                    and (which == 0 or compact_stats):
+                # only the T selected frames of each trial cross PCIe (one strided DMA per run of consecutive indices); the
+                # z-score statistics of a frame depend on that frame alone, so the unselected ones are never needed
+                frd = torch.empty((K, T, F), dtype=torch.uint8, device=device)
+                vs.check(vs.lib.vs_h2d_select_frames(fr.data_ptr(), K, Tf, F, idx_np.ctypes.data, T, vs.ptr(frd), st))
+                fr, Tf_dev, idx_dev = frd, T, idx_compact
+            else:
+                fr = fr.to(device, non_blocking=True).reshape(K, Tf, -1).contiguous()
+                Tf_dev, idx_dev = Tf, idx
+                if which == 1 and compact_stats:              # train statistics are compact: bring the test frames to the same order
+                    fr = fr[:, idx.long()].contiguous()
+                    Tf_dev, idx_dev = T, idx_compact
             cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
             if which == 0:
-                mean = torch.empty(Tf * F, dtype=torch.float64, device=device)
+                compact_stats = Tf_dev == T and Tf != T
+                mean = torch.empty(Tf_dev * F, dtype=torch.float64, device=device)
                 sd = torch.empty_like(mean)
-                vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf * F, vs.ptr(mean), vs.ptr(sd), st))
+                vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf_dev * F, vs.ptr(mean), vs.ptr(sd), st))
                 sm = torch.empty_like(cnt)
                 vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
                 my = torch.empty(T * N, dtype=torch.float64, device=device)
                 sy = torch.empty_like(my)
                 vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
                 del sm
-            vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf, vs.ptr(idx), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
+            vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
                                            vs.ptr(xl), vs.ptr(overflow), st))
             vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
             sp = _PackedSplit.from_device(d, Xa, Xb, xl, y, overflow)
@@ -491,7 +508,14 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
             del fr, cnt
         splits.append(sp)
         ys.append(_LazyY(sp) if which == 1 else y)
-    Tf_F = mean.numel()
+    if compact_stats:
+        # API shape of the reference's `setup` (per frame of the trial window): statistics exist for the selected frames only
+        Tf_all, F_all = int(frames_train.shape[1]), int(frames_train[0, 0].numel())
+        mean_full = torch.full((Tf_all, F_all), float("nan"), dtype=torch.float64, device=device)
+        sd_full = torch.full((Tf_all, F_all), float("nan"), dtype=torch.float64, device=device)
+        mean_full[idx.long()] = mean.view(T, F_all)
+        sd_full[idx.long()] = sd.view(T, F_all)
+        mean, sd = mean_full.reshape(-1), sd_full.reshape(-1)
     return {"X": splits, "y": ys,
             "setup": {"mean_X_Tv": mean, "std_X_Tv": sd, "mean_y_TN": my.reshape(T, -1), "std_y_TN": sy.reshape(T, -1)}}
 

@@ -69,6 +69,7 @@ def _load():
         "vs_last_error": (C.c_char_p, []),
         "vs_device_ok": (C.c_int, []),
         "vs_u8_to_f32": (C.c_int, [vp, vp, i64, vp]),
+        "vs_h2d_select_frames": (C.c_int, [vp, i64, i64, i64, vp, i64, vp, vp]),
         "vs_u8_to_bf16": (C.c_int, [vp, vp, i64, vp]),
         "vs_gather_windows": (C.c_int, [vp, i64, i64, vp, i64, i64, vp, vp]),
         "vs_linear_fwd_workspace": (sz, [i64, i64, i64]),
