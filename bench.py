@@ -8,9 +8,12 @@ Workloads (config.workload):
           120 frames x (110 x 166) whisker ROI, N=144 neurons, l2=100.  A "step" is one full fit
           (src/model/rrr.py:164-202: one LBFGS.step = 20 closure evaluations + the validation pass).
           frames/s = K*120 / fit time.  N>1 GPUs: one independent session per rank (train_rrr.py:179-187
-          fits sessions independently: no data-path collective), weak scaling.
+          fits sessions independently: no data-path collective), weak scaling.  --joint (configs[2]): the N
+          sessions form ONE model with a shared V (rrr.py:37-49); [dV, loss] and the L-BFGS inner products
+          are all-reduced over NCCL.
   linear  BASELINE configs[0]/[3]: `Linear` MLP train step (src/trainer/base.py:147-154), B=16,
-          D=120*128*128, N=144: frames/s = B*120 / step time.  N>1: independent replicas.
+          D=120*128*128, N=144: frames/s = B*120 / step time.  N>1: row-parallel first layer (each rank owns
+          1/N of the pixels of W0 and of every frame; one 16 KB all-reduce per step), strong scaling.
 
 `value`  : device-timed (CUDA events), inputs resident in HBM.
 `e2e`    : same metric through the public Python API from PINNED HOST buffers, H2D/D2H inside the timed region.
