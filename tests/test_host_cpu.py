@@ -266,3 +266,37 @@ def test_argument_validation_needs_no_gpu():
     assert closure_rc(vs.RrrDims(K, T, C1, N, 3, 1, good.ldc, good.ldr, 7)) != 0            # unknown operand format
     assert closure_rc(good) != 0 and b"null" in vs.lib.vs_last_error()                      # valid shape, null buffers
     assert vs.lib.vs_u8_to_f32(None, None, 16, None) != 0
+
+
+def test_bench_clock_sampler_filters_the_timed_region(monkeypatch):
+    """bench.py's clocks object: only nvidia-smi samples taken inside the timed region count; a region shorter than one sampling
+    period falls back to the samples of the warm-up just before it; throttle reasons are collected from the kept rows."""
+    import time
+    import bench
+
+    class FakeProc:
+        stdout = ()
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+
+    def row(sm, power_cap="Not Active", hw="Not Active"):
+        return ["0", str(sm), "1965", "700.0", "0x4", hw, "Not Active", "Not Active", power_cap]
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    now = time.perf_counter()
+    s.rows = [(now - 3.0, row(300)), (now - 0.2, row(1700, power_cap="Active")), (now + 0.01, row(1800)), (now + 0.02, row(1900, power_cap="Active"))]
+    s.t0 = now
+    time.sleep(0.05)
+    out = s.stop()
+    assert out["samples_in_timed_region"] == 2 and out["sm_mhz"] == 1850.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    s2.proc = FakeProc()
+    now = time.perf_counter()
+    s2.rows = [(now - 3.0, row(300, hw="Active")), (now - 0.2, row(1700))]
+    s2.t0 = now
+    out = s2.stop()
+    assert out["samples_in_timed_region"] == 0 and out["samples"] == 1 and out["sm_mhz"] == 1700.0 and out["reasons"] == []
+    s3 = bench.ClockSampler(0)                  # nvidia-smi missing: reported, not fatal
+    assert s3.stop()["reasons"] == ["nvidia-smi unavailable"]
