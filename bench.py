@@ -1,25 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- training video frames/s of the video->spike hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload rrr|linear] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload both|rrr|linear] [--impl reference]
 
-Workloads (config.workload):
-  rrr     BASELINE configs[1] (default): RRR rank-3, ONE session, bf16 operands, K=400 train trials of
-          120 frames x (110 x 166) whisker ROI, N=144 neurons, l2=100.  A "step" is one full fit
-          (src/model/rrr.py:164-202: one LBFGS.step = 20 closure evaluations + the validation pass).
-          frames/s = K*120 / fit time.  N>1 GPUs: one independent session per rank (train_rrr.py:179-187
-          fits sessions independently: no data-path collective), weak scaling.  --joint (configs[2]): the N
-          sessions form ONE model with a shared V (rrr.py:37-49); [dV, loss] and the L-BFGS inner products
-          are all-reduced over NCCL.
-  linear  BASELINE configs[0]/[3]: `Linear` MLP train step (src/trainer/base.py:147-154), B=16,
-          D=120*128*128, N=144: frames/s = B*120 / step time.  N>1: row-parallel first layer (each rank owns
-          1/N of the pixels of W0 and of every frame; one 16 KB all-reduce per step), strong scaling.
+ONE JSON line.  The top level is the RRR workload (config.workload); the Linear workload is nested under "linear".
+  rrr     BASELINE configs[1] at N = 1: RRR rank-3, ONE session, K=400 train trials of 120 frames x (110 x 166) whisker
+          ROI, N=144 neurons, l2=100.  A "step" is one full fit (src/model/rrr.py:164-202: one LBFGS.step = 20 closure
+          evaluations + the validation pass).  frames/s = K*120 / fit time.  Default operand mode "exact" (the mode whose
+          whole fit is within 1e-3 of the float64 reference; --mode classic --planes 1 is the faster non-parity mode).
+          N > 1 GPUs (BASELINE configs[2]): ONE joint model over N sessions, one per GPU, with a shared V
+          (rrr.py:37-49): [dV, loss] are all-reduced per closure evaluation and the L-BFGS scalars all-gathered per
+          iteration (NCCL, stream-ordered: the optimiser stays device-driven).  --independent: N separate fits instead
+          (what train_rrr.py:179-187 runs; no data-path collective).
+  linear  BASELINE configs[0]/[3]: `Linear` MLP train step (src/trainer/base.py:147-154), B=16, D=120*128*128, N=144:
+          frames/s = B*120 / step time.  N > 1: row-parallel first layer (each rank owns 1/N of the pixels of W0 and of
+          every frame; one 16 KB all-reduce per step), strong scaling.
 
 `value`  : device-timed (CUDA events), inputs resident in HBM.
-`e2e`    : same metric through the public Python API from PINNED HOST buffers, H2D/D2H inside the timed region.
+`e2e`    : same metric through the public Python API from PINNED HOST buffers, H2D/D2H inside the timed region: the MEAN
+           of a fixed number of calls (median and every sample listed beside it).
 `roofline`: dominant kernel, event-bracketed inside the timed region (vs_profile_*), vs MEASURED_PEAKS.json.
+`parity` : the timed mode against an independent float64 dense fit (torch einsum + autograd + torch.optim.LBFGS on the GPU).
 `cpu_baseline`: the oracle (CPU port of the reference) timed on the host cores on a bounded sample.
---impl reference: only that CPU arm, printed in the same JSON shape.
+--impl reference: only that CPU arm (whole fits on a bounded sample of trials), printed in the same JSON shape.
 """
 from __future__ import annotations
 
@@ -182,23 +185,61 @@ def sorted_idx_42():
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle)
-def cpu_rrr_sample(K_s, Kt_s, F, N, evals=2, seed=0):
-    """Host-core baseline: the oracle's autograd transcription of the reference closure, `evals` of the
-    fit's 20 closure evaluations at full C and N on K_s trials.  frames/s = K_s*120 / (20 * mean eval time)."""
+def _cpu_rrr_problem(K_s, Kt_s, F, N, seed=0):
     from oracle import rrr_oracle as ro
-    torch.set_num_threads(os.cpu_count() or 1)
     ftr, ctr, fte, cte = rrr_inputs(K_s, Kt_s, F, N, seed, pinned=False)
     data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)],
                                     sorted_idx_42())
-    td = {"s": data}
+    return {"s": data}
+
+
+def _cpu_rrr_fit(td):
+    """One whole fit of the reference on the host cores (src/model/rrr.py:164-202): the oracle's autograd transcription of
+    the closure (beta built twice, X/y converted on every call, einsum + backward) driven by the oracle's restatement of
+    torch.optim.LBFGS.step, then the validation pass on split 1.  Returns (seconds, closure evaluations, val SSE)."""
+    from oracle import rrr_oracle as ro
     params = ro.rrr_init(td, 3)
-    ro.loss_and_grad_autograd(params, td, 100.0)             # warm-up (allocator, threads)
+    order = list(params.keys())
     t0 = time.perf_counter()
-    for _ in range(evals):
-        ro.loss_and_grad_autograd(params, td, 100.0)
-    dt = (time.perf_counter() - t0) / evals
-    fit_s = 20.0 * dt
-    return K_s * FRAMES_PER_TRIAL / fit_s, fit_s, dt
+    n_eval = [0]
+
+    def closure(x):
+        n_eval[0] += 1
+        loss, grads = ro.loss_and_grad_autograd(ro._unflatten(x, params, order), td, 100.0)
+        return loss, ro._flatten(grads, order)
+
+    x, _ = ro.lbfgs_step(closure, ro._flatten(params, order))
+    p = ro._unflatten(x, params, order)
+    beta = ro.compute_beta(p["s_U"], p["V"], p["s_b"])
+    val = float(np.sum((ro.predict(beta, td["s"]["X"][1]) - td["s"]["y"][1]) ** 2))
+    return time.perf_counter() - t0, n_eval[0], val
+
+
+def cpu_rrr_sample(F, N, n_fits, n_warm, budget_s, K_full):
+    """Host-core baseline on a BOUNDED sample: K_s trials at full C and N, chosen from one calibration evaluation so that
+    (n_warm + n_fits) whole fits take about budget_s seconds (the cost of a fit is linear in the number of trials, so
+    frames/s measured on K_s trials is the frames/s of the full-size fit).  Returns a dict."""
+    from oracle import rrr_oracle as ro
+    torch.set_num_threads(os.cpu_count() or 1)
+    K0 = 8
+    td0 = _cpu_rrr_problem(K0, 2, F, N)
+    p0 = ro.rrr_init(td0, 3)
+    ro.loss_and_grad_autograd(p0, td0, 100.0)                    # warm-up (allocator, threads)
+    t0 = time.perf_counter()
+    ro.loss_and_grad_autograd(p0, td0, 100.0)
+    per_trial_eval = (time.perf_counter() - t0) / K0
+    K_s = int(budget_s / ((n_warm + n_fits) * 21.5 * per_trial_eval))
+    K_s = max(4, min(K_full, K_s))
+    td = _cpu_rrr_problem(K_s, max(2, K_s // 5), F, N)
+    for _ in range(n_warm):
+        _cpu_rrr_fit(td)
+    secs, evals = [], 0
+    for _ in range(n_fits):
+        dt, evals, _ = _cpu_rrr_fit(td)
+        secs.append(dt)
+    fit_s = float(np.mean(secs))
+    return {"value": K_s * FRAMES_PER_TRIAL / fit_s, "fit_s": fit_s, "trials": K_s, "trials_val": max(2, K_s // 5), "evals": evals,
+            "fits_timed": n_fits, "fits_warmup": n_warm, "calibration_s_per_trial_eval": per_trial_eval}
 
 
 def cpu_linear_sample(B, D, N, steps=2):
@@ -215,15 +256,22 @@ def cpu_linear_sample(B, D, N, steps=2):
 
 
 def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores (the oracle port: the reference is Python and needs
+    packages this image lacks).  Every step is a WHOLE fit / train step, on a bounded sample."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    if args.workload == "rrr":
-        v, fit_s, ev_s = cpu_rrr_sample(args.cpu_trials, 8, args.features, args.neurons, evals=max(1, args.steps))
-        sample = (f"oracle autograd closure (CPU port of src/model/rrr.py:165-175, torch fp64), {args.cpu_trials} trials x 120 frames, "
-                  f"C={args.features + 1}, N={args.neurons}: {max(1, args.steps)} timed closure evals, fit = 20 evals ({ev_s:.2f} s/eval)")
+    if args.workload != "linear":
+        r = cpu_rrr_sample(args.features, args.neurons, max(1, args.steps), max(0, args.warmup), args.ref_budget, args.trials)
+        sample = (f"oracle whole fits (CPU port of src/model/rrr.py:164-202: autograd closure, torch fp64, + L-BFGS vector work + validation "
+                  f"pass) on {r['trials']} train / {r['trials_val']} val trials x 120 frames at full C={args.features + 1}, N={args.neurons}: "
+                  f"{r['fits_warmup']} warm-up + {r['fits_timed']} timed fits of {r['evals']} closure evaluations, {r['fit_s']:.2f} s per fit; "
+                  f"the cost of a fit is linear in the trial count, so frames/s on the sample is the full-size figure")
         cfg = rrr_config(args, world)
-        ms = fit_s * 1e3
+        cfg.update({"trials_train": r["trials"], "trials_test": r["trials_val"], "sessions": 1, "parallelism": f"host cores x{cores}",
+                    "operand_mode": "float64 (reference)", "lbfgs": "1 step, max_iter 20 (oracle restatement of torch.optim.LBFGS)",
+                    "sample_of_trials_train": args.trials, "extrapolated": False})
+        v, ms = r["value"], r["fit_s"] * 1e3
     else:
         v, dt = cpu_linear_sample(args.batch, args.input_dim, args.neurons, steps=max(1, min(args.steps, 3)))
         sample = f"oracle Trainer.step (CPU port of src/trainer/base.py:147-154, torch fp32), B={args.batch}, D={args.input_dim}, N={args.neurons}"
@@ -231,23 +279,40 @@ def reference_arm(args, rank, world):
         ms = dt * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if args.workload == "rrr" else "f32", "data": "synthetic", "config": cfg,
+            "dtype": "f32" if args.workload == "linear" else "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- configs
+def rrr_mode_of(args):
+    return "classic" if (args.mode == "classic" or (args.mode is None and args.planes is not None)) else "exact"
+
+
 def rrr_config(args, world):
-    return {"workload": "rrr_joint_fit, shared V across sessions (BASELINE configs[2])" if args.joint else "rrr_single_session_fit (BASELINE configs[1])", "trials_train": args.trials, "trials_test": args.trials_test,
+    exact = rrr_mode_of(args) == "exact"
+    joint = world > 1 and not args.independent
+    planes = 2 if exact else (args.planes or 1)
+    if exact:
+        fmt = ("exact: forward operand = z-score as hi+lo IEEE-half planes (3 plane products), backward operand = exact integer frames "
+               "(half) x hi+lo residual planes, fp32 accumulate in TMEM, float64 epilogues")
+    else:
+        fmt = (os.environ.get("VS_RRR_OPERAND") or "bf16") + f" x {planes} plane(s) (16-bit tensor-core operands, fp32 accumulate in TMEM)"
+    hist = "float64" if planes > 1 else "float32"
+    return {"workload": "rrr_joint_fit, shared V across sessions (BASELINE configs[2])" if joint else "rrr_single_session_fit (BASELINE configs[1])",
+            "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
-            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_planes": args.planes,
-            "operand_format": (os.environ.get("VS_RRR_OPERAND") or "bf16") + " (16-bit tensor-core operands, fp32 accumulate in TMEM)", "lbfgs": ("1 step, max_iter 20 (20 closure evals), history float32" if args.planes == 1 else "1 step, max_iter 20 (20 closure evals), history float64")
-                     + (", host-driven with sharded inner products" if args.joint else ", device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else ", host-driven"),
+            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_mode": "exact" if exact else "classic", "operand_planes": planes,
+            "operand_format": fmt,
+            "lbfgs": f"1 step, max_iter 20 (20 closure evals), history {hist}, "
+                     + ("device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else "host-driven")
+                     + (", inner products sharded over the ranks" if joint else ""),
             "sessions": world,
-            "parallelism": (f"joint model over {world} sessions, one per GPU: shared V, [dV, loss] and L-BFGS inner products all-reduced (NCCL)"
-                            if args.joint else (f"independent sessions, one per GPU x{world} (no collective)" if world > 1 else "single GPU")),
-            "l2_cache": "operands (1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
+            "parallelism": (f"joint model over {world} sessions, one per GPU: shared V; per closure evaluation ONE NCCL all-reduce of [dV, loss], "
+                            f"per L-BFGS iteration ONE NCCL all-gather of the {8 + 6 * 100 + 1} optimiser scalars (stream-ordered, no host sync)"
+                            if joint else (f"independent sessions, one per GPU x{world} (no collective)" if world > 1 else "single GPU")),
+            "l2_cache": "operands (>= 1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
 
 
 def linear_config(args, world):
@@ -257,31 +322,97 @@ def linear_config(args, world):
             "l2_cache": "weights+Adam state (6 GB) exceed the 126 MB L2; no flush needed"}
 
 
+# ----------------------------------------------------------------------------- float64 dense reference on the GPU
+def fp64_dense_reference(ftr, ctr, fte, cte, sidx, dev, perturb_seed=1):
+    """The reference's own formulation (src/model/rrr.py:79-155,164-202; preprocessing of src/train_rrr.py:108-171) in
+    float64 torch on the GPU: einsum + autograd + torch.optim.LBFGS.  Independent of every kernel of this repo.
+    Returns {"val_sse", "evals", "probe": (loss, {name: grad}) at a perturbed start, "start": {name: tensor}}."""
+    from scipy.ndimage import gaussian_filter1d
+    sid = torch.as_tensor(np.asarray(sidx), device=dev)
+
+    def prep(fr, mean=None, std=None):
+        X = fr.to(dev).reshape(fr.shape[0], fr.shape[1], -1).double()
+        if mean is None:
+            mean = X.mean(0); std = X.std(0, unbiased=False).clamp_min(1e-8)
+        X = (X - mean) / std
+        X = torch.cat([X, torch.ones(X.shape[0], X.shape[1], 1, dtype=torch.float64, device=dev)], 2)
+        return X[:, sid], mean, std
+
+    Xtr, mX, sX = prep(ftr)
+    Xte, _, _ = prep(fte, mX, sX)
+    ytr = gaussian_filter1d(ctr.numpy().astype(np.float64), 2, axis=1)
+    yte = gaussian_filter1d(cte.numpy().astype(np.float64), 2, axis=1)
+    my, sy = ytr.mean(0), np.clip(ytr.std(0), 1e-8, None)
+    ytr = torch.from_numpy((ytr - my) / sy).to(dev); yte = torch.from_numpy((yte - my) / sy).to(dev)
+    N, F = ytr.shape[2], Xtr.shape[2] - 1
+    st = np.random.get_state()
+    np.random.seed(0)
+    U0 = np.random.normal(size=(N, F, 3)) / np.sqrt(300); V0 = np.random.normal(size=(3, 100)) / np.sqrt(300)
+    np.random.set_state(st)
+    U = torch.nn.Parameter(torch.from_numpy(U0).to(dev)); V = torch.nn.Parameter(torch.from_numpy(V0).to(dev))
+    b = torch.nn.Parameter(ytr.mean(0).T.unsqueeze(1).contiguous())
+
+    def loss_fn():
+        beta = torch.cat([U @ V, b], 1)                                   # (N, C, T)
+        pred = torch.einsum("ktc,nct->ktn", Xtr, beta)
+        return ((pred - ytr) ** 2).sum() + 100.0 * (beta ** 2).sum()
+
+    # (1) one evaluation at a perturbed start (at the exact init the gradient of b is ~0 by construction)
+    init = {"U": U.detach().clone(), "b": b.detach().clone(), "V": V.detach().clone()}
+    gp = torch.Generator().manual_seed(perturb_seed)
+    start = {k: v + (0.02 * torch.randn(v.shape, generator=gp, dtype=torch.float64)).to(dev) for k, v in init.items()}
+    with torch.no_grad():
+        U.copy_(start["U"]); b.copy_(start["b"]); V.copy_(start["V"])
+    l = loss_fn(); l.backward()
+    probe = (float(l), {"U": U.grad.clone(), "b": b.grad.clone(), "V": V.grad.clone()})
+    with torch.no_grad():
+        U.copy_(init["U"]); b.copy_(init["b"]); V.copy_(init["V"])
+    # (2) the whole fit
+    opt = torch.optim.LBFGS([U, b, V])
+    trace = []
+
+    def closure():
+        opt.zero_grad()
+        l = loss_fn(); l.backward(); trace.append(float(l.detach())); return l
+
+    opt.step(closure)
+    with torch.no_grad():
+        beta = torch.cat([U @ V, b], 1)
+        pred = torch.einsum("ktc,nct->ktn", Xte, beta)
+        val = float(((pred - yte) ** 2).sum())
+        pred_fr = (pred.cpu().numpy() * sy + my)              # src/model/rrr.py:136-142 (predict_y_fr)
+    del Xtr, Xte, beta, pred
+    torch.cuda.empty_cache()
+    return {"val_sse": val, "evals": len(trace), "probe": probe, "start": start, "first_loss": trace[0], "last_loss": trace[-1],
+            "pred_test_fr": pred_fr}
+
+
 # ----------------------------------------------------------------------------- RRR workload
 def run_rrr(args, rank, world, local):
     import vsb200 as vs
     from model.rrr import RRRGD, pack_session_from_frames, train_model, train_model_from_frames
-    from optim import FusedLBFGS
     vs.require_b200()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     K, Kt, F, N = args.trials, args.trials_test, args.features, args.neurons
+    mode = rrr_mode_of(args)
+    planes = None if mode == "exact" else (args.planes or 1)
     sidx = sorted_idx_42()
     ftr, ctr, fte, cte = rrr_inputs(K, Kt, F, N, seed=rank, pinned=True)
     # bytes that cross PCIe per fit: the 100 selected frames of every trial (vs_h2d_select_frames) + the spike counts
     h2d = (ftr.numel() + fte.numel()) // ftr.shape[1] * len(sidx) + 4 * (ctr.numel() + cte.numel())
 
     # ---- resident-input measurement: operands packed once, fit repeated
-    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=args.planes, device=dev)
-    # --joint (BASELINE configs[2]): ONE model over all ranks' sessions with a shared V (src/model/rrr.py:37-49); rank r holds
-    # session r's U, b and operands, [dV, loss] and the L-BFGS inner products are all-reduced over NCCL (parallel.py)
-    joint = bool(args.joint)
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, mode=mode)
+    # N > 1 (BASELINE configs[2]): ONE model over all ranks' sessions with a shared V (src/model/rrr.py:37-49); rank r holds
+    # session r's U, b and operands; [dV, loss] all-reduced per evaluation, the L-BFGS scalars all-gathered per iteration
+    joint = world > 1 and not args.independent
     eid = f"s{rank:02d}" if joint else "s"
     plan = [(f"s{r:02d}", N, F + 1, 100) for r in range(world)] if joint else None
     td = {eid: entry}
-    model = RRRGD(td, 3, l2=100.0, planes=args.planes, init_plan=plan)
+    model = RRRGD(td, 3, l2=100.0, planes=planes, init_plan=plan)
     model.to(dev)
-    model_fmt = model.fmt
+    model_fmt, model_planes = model.fmt, model.planes
     init = {k: v.detach().clone() for k, v in model.model.items()}
     if joint:
         from parallel import train_joint_model
@@ -323,70 +454,65 @@ def run_rrr(args, rank, world, local):
     # With VS_RRR_DENSE=0 the factorised backward GEMM runs under the same tag and is counted the same way.
     C = F + 1
     Np16 = (N + 15) // 16 * 16
-    plane_passes = 1 if args.planes == 1 else (3 if args.planes == 2 else 6)
+    plane_passes = 1 if model_planes == 1 else (3 if model_planes == 2 else 6)
     n_contr = 1 if n_bwd > 0 else 2                             # contractions per closure evaluation under tag 0
     algo_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * C * N) + 2.0 * Kt * 100 * C * N)
     exec_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * F * 3 * Np16) + 2.0 * Kt * 100 * F * 3 * Np16) * plane_passes
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    key = f"rrr_K{K}_F{F}_N{N}_planes{args.planes}"
-    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (forward Z = X U; tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair)",
+    key = f"rrr_K{K}_F{F}_N{N}_planes{model_planes}" + ("_exact" if mode == "exact" else "")
+    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (forward Z = X U; tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair"
+                                         + (f"; {plane_passes} plane products per launch)" if plane_passes > 1 else ")"),
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-            "traffic": ncu_traffic(key), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)",
+            "traffic": ncu_traffic(key), "traffic_unit": "bytes/launch (ncu dram read+write of an EARLIER run of this command, profiles/; not measured in this run)",
             "peak_source": f"{pk_kind} bf16_tflops_sustained",
             "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
             "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
-            "note": "achieved counts ALGORITHMIC flops of the dense formulation; the factorised forward executes r=3x that (executed_tflops)"}
+            "note": "achieved counts ALGORITHMIC flops of the dense formulation (2*K*T*C*N per contraction); the factorised forward executes "
+                    f"r=3x that per plane product and {plane_passes} plane product(s) (executed_tflops)"}
     if n_bwd > 0:
-        # second kernel of the closure: the per-time-bin dense backward streams Xb once (HBM-bound at a third of the flops)
+        # second kernel of the closure: the per-time-bin dense backward streams the backward operand once
         Kp = (K + 15) // 16 * 16
-        bwd_bytes = 2.0 * F * 100 * Kp + 2.0 * Np16 * 100 * Kp + 4.0 * F * 3 * Np16      # Xb + R operand + G out
+        r_planes = 2 if mode == "exact" else 1
+        bwd_bytes = 2.0 * F * 100 * Kp + 2.0 * r_planes * Np16 * 100 * Kp + 4.0 * F * 3 * Np16      # operand + R planes + G out
         bw = bwd_bytes * n_bwd / (bwd_ms * 1e-3) / 1e9
-        roof["backward"] = {"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel (dU: D_t = X_t^T R_t per time bin in TMEM, rank-one updates in registers)",
+        roof["backward"] = {"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel (dU: D_t = X_t^T R_t per time bin in TMEM, rank-one updates in registers"
+                                                      + ("; exact integer operand x hi+lo residual planes)" if mode == "exact" else ")"),
                             "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"],
                             "traffic": ncu_traffic(key, "bwd_bytes_per_launch"), "launches": n_bwd, "avg_launch_ms": bwd_ms / n_bwd,
                             "share_of_step": bwd_ms / (ms * args.steps),
                             "algorithmic_tflops": 2.0 * K * 100 * C * N * n_bwd / (bwd_ms * 1e-3) / 1e12}
 
-    # ---- parity of the timed configuration (outside every timed region): the same fit with 3 operand planes and a float64
-    # L-BFGS history -- the mode the tests pin against the float64 reference to ~1e-6 -- on the same session
+    # ---- parity of the timed configuration (outside every timed region) against an INDEPENDENT float64 dense fit on the
+    # GPU (the reference's formulation in torch: einsum + autograd + torch.optim.LBFGS), same session
     parity = None
-    if rank == 0 and not args.no_parity and args.planes == 1 and not joint:
-        entry3 = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=3, device=dev)
-        m3 = RRRGD({"s": entry3}, 3, l2=100.0, planes=3)
-        m3.to(dev)
-        # (1) one closure evaluation at identical (initial) parameters: loss and gradient, timed mode vs 3 planes
-        gp = torch.Generator().manual_seed(1)
-        with torch.no_grad():                      # perturbed start (at the exact init the gradient of b is ~0 by construction)
-            for k, v in init.items():
-                x = v + (0.02 * torch.randn(v.shape, generator=gp, dtype=torch.float64)).to(dev)
-                model.model[k].copy_(x)
-                m3.model[k].copy_(x)
-        l1, l3 = float(model.loss_and_grad(td, 0)), float(m3.loss_and_grad({"s": entry3}, 0))
-        gerr = {k.split("_")[-1]: float((model.model[k].grad - m3.model[k].grad).abs().max() / m3.model[k].grad.abs().max()) for k in init}
+    if rank == 0 and not args.no_parity and not joint:
+        ref = fp64_dense_reference(ftr, ctr, fte, cte, sidx, dev)
         with torch.no_grad():
-            for k, v in init.items():
-                m3.model[k].copy_(v)
-        # (2) the whole fit (20 closure evaluations of an un-line-searched L-BFGS amplify any perturbation)
-        _, r3 = train_model(m3, {"s": entry3}, m3.make_optimizer(), "tmp", save=False)
-        ref_sse = float(r3["mse_val_mean"])
-        parity = {"per_eval_loss_rel_diff": abs(l1 - l3) / abs(l3), "per_eval_grad_max_abs_diff_over_max_abs": gerr,
-                  "fit_val_sse": float(mse), "fit_val_sse_3plane_f64hist": ref_sse, "fit_rel_diff": abs(float(mse) - ref_sse) / ref_sse,
-                  "tolerance": 1e-3,
-                  "note": "reference = 3 bf16 residual planes + float64 L-BFGS history (pinned to the float64 reference by the tests; "
-                          "1.0e-4 from a float64 dense torch fit at this size, profiles/r01_parity_probe_noise_data.txt)"}
-        del entry3, m3, r3
+            model.model["s_U"].copy_(ref["start"]["U"]); model.model["s_b"].copy_(ref["start"]["b"]); model.model["V"].copy_(ref["start"]["V"])
+        l1 = float(model.loss_and_grad(td, 0))
+        lref, gref = ref["probe"]
+        names = {"U": "s_U", "b": "s_b", "V": "V"}
+        gerr = {k: float((model.model[nm].grad - gref[k]).abs().max() / gref[k].abs().max()) for k, nm in names.items()}
+        gerr2 = {k: float((model.model[nm].grad - gref[k]).norm() / gref[k].norm()) for k, nm in names.items()}
+        parity = {"reference": "float64 dense fit on the GPU (torch einsum + autograd + torch.optim.LBFGS; src/model/rrr.py:79-155,164-202)",
+                  "per_eval_loss_rel_diff": abs(l1 - lref) / abs(lref), "per_eval_grad_max_abs_diff_over_max_abs": gerr,
+                  "per_eval_grad_rel_l2": gerr2,
+                  "fit_val_sse": float(mse), "fit_val_sse_fp64": ref["val_sse"], "fit_rel_diff": abs(float(mse) - ref["val_sse"]) / ref["val_sse"],
+                  "tolerance": 1e-3, "within_tolerance": bool(abs(float(mse) - ref["val_sse"]) / ref["val_sse"] <= 1e-3),
+                  "fp64_evals": ref["evals"]}
+        del ref, gref
         torch.cuda.empty_cache()
 
     # ---- end to end: pinned host uint8 frames -> R0 on device -> init -> fit -> validation loss on the host
     def e2e_fit():
         if joint:
-            ent = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=args.planes, device=dev)
-            m = RRRGD({eid: ent}, 3, l2=100.0, planes=args.planes, init_plan=plan, device=dev)
+            ent = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, mode=mode)
+            m = RRRGD({eid: ent}, 3, l2=100.0, planes=planes, init_plan=plan, device=dev)
             _, res = train_joint_model(m, {eid: ent})
         else:
-            m, res, _ = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3, planes=args.planes)
+            m, res, _ = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3, planes=planes, mode=mode)
         return float(res["mse_val_mean"])                    # device -> host read of the result
 
     del model, td, entry
@@ -395,51 +521,103 @@ def run_rrr(args, rank, world, local):
     e2e_fit(); e2e_fit()
     gc.collect(); gc.disable()                      # no collector pauses inside the timed region (re-enabled below)
     torch.cuda.synchronize(); barrier(world)
-    n_e2e = max(5, args.steps)
+    n_e2e = max(5, args.steps)                      # FIXED number of calls: no adaptive stopping
     each = []
-    for i in range(3 * n_e2e):
+    for i in range(n_e2e):
         t1 = time.perf_counter()
         val = e2e_fit()
         each.append((time.perf_counter() - t1) * 1e3)
         gc.collect()                                # between fits, outside the per-fit timing: frees the previous fit's operands
-        # a shared host can stall single fits by 100+ ms: keep sampling (up to 3x) until the fastest and the median agree to 25 %
-        # (ranks decide together: the joint model's fits contain collectives)
-        if i + 1 >= n_e2e and max_over_ranks(1.0 if float(np.median(each)) > 1.25 * min(each) else 0.0, world, dev) == 0.0:
-            break
-    n_e2e = len(each)
     torch.cuda.synchronize(); barrier(world)
-    mean_s = max_over_ranks(float(np.mean(each)) * 1e-3, world, dev)
-    # this path crosses the host 20+ times per fit (init stream threads, one sync per L-BFGS iteration, PCIe): on a shared
-    # box single iterations are hit by 100+ ms of host jitter, so the headline uses the MEDIAN iteration (max over ranks);
-    # the mean and every sample are reported next to it
-    e2e_s = max_over_ranks(float(np.median(each)) * 1e-3, world, dev)
     gc.enable()
-    e2e = {"value": world * K * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-           "ms_per_step": e2e_s * 1e3, "statistic": f"median of {n_e2e} fits", "mean_ms_per_step": mean_s * 1e3,
+    mean_s = max_over_ranks(float(np.mean(each)) * 1e-3, world, dev)
+    med_s = max_over_ranks(float(np.median(each)) * 1e-3, world, dev)
+    e2e = {"value": world * K * FRAMES_PER_TRIAL / mean_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+           "ms_per_step": mean_s * 1e3, "statistic": f"mean of {n_e2e} consecutive calls (max over ranks)",
+           "median_ms_per_step": med_s * 1e3, "value_at_median": world * K * FRAMES_PER_TRIAL / med_s,
            "ms_each_rank0": [round(x, 2) for x in each],
            "path": ("pack_session_from_frames(pinned uint8 frames) -> RRRGD(init_plan) -> parallel.train_joint_model -> float(mse_val_mean)" if joint
                     else "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)")}
 
+    # ---- the reference's own entry point: train_model_main(train_data) with the float64 numpy arrays train_rrr.py builds
+    # (5.8 GB + 1.2 GB of float64 over PCIe, packed into 3 residual planes on the device): the drop-in call, few samples
+    if rank == 0 and world == 1 and args.dropin_e2e > 0:
+        try:
+            e2e["dropin_fp64"] = dropin_fp64_e2e(ftr, ctr, fte, cte, sidx, args.dropin_e2e, K)
+        except Exception as exc:                     # never lose the line over the optional measurement
+            e2e["dropin_fp64"] = {"error": repr(exc)[:200]}
+
     if rank != 0:
-        return
+        return None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, fit_s, ev_s = cpu_rrr_sample(args.cpu_trials, 8, F, N, evals=2)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle autograd closure (torch fp64 CPU), {args.cpu_trials} trials x 120 frames at full C={C}, N={N}: "
-                         f"2 timed closure evals ({ev_s:.2f} s each), fit = 20 evals"}
+        r = cpu_rrr_sample(F, N, 1, 0, args.cpu_budget, K)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle whole fit (CPU port of src/model/rrr.py:164-202, torch fp64 autograd closure + L-BFGS + validation pass) on "
+                         f"{r['trials']} train / {r['trials_val']} val trials x 120 frames at full C={C}, N={N}: 1 fit of {r['evals']} closure "
+                         f"evaluations, {r['fit_s']:.1f} s; cost is linear in the trial count"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if model_fmt == 1 else "bf16",
             "data": "synthetic", "config": rrr_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "closure_evals_per_step": evals, "val_sse": float(mse), "val_sse_e2e": val, "parity": parity}
-    print(json.dumps(line))
+    return line
+
+
+def dropin_fp64_e2e(ftr, ctr, fte, cte, sidx, n, K):
+    """`model.rrr.train_model_main(train_data, l2, n_comp, fname, save=False)` with the reference's own inputs: float64
+    numpy X (K, 100, C) / y (K, 100, N) as src/train_rrr.py:143-171 builds them (host preprocessing NOT timed)."""
+    from scipy.ndimage import gaussian_filter1d
+    from model.rrr import train_model_main
+    Xs = [f.numpy().reshape(f.shape[0], f.shape[1], -1) for f in (ftr, fte)]
+    mean = Xs[0].mean(0, dtype=np.float64); std = np.clip(Xs[0].std(0, dtype=np.float64), 1e-8, None)
+    ys = [gaussian_filter1d(c.numpy().astype(np.float64), 2, axis=1) for c in (ctr, cte)]
+    my, sy = ys[0].mean(0), np.clip(ys[0].std(0), 1e-8, None)
+    Xo = []
+    for x in Xs:
+        z = np.empty((x.shape[0], len(sidx), x.shape[2] + 1), dtype=np.float64)
+        z[:, :, :-1] = (x[:, sidx] - mean[sidx]) / std[sidx]
+        z[:, :, -1] = 1.0
+        Xo.append(z)
+    td = {"s": {"X": Xo, "y": [(y - my) / sy for y in ys], "setup": {"mean_X_Tv": mean, "std_X_Tv": std, "mean_y_TN": my, "std_y_TN": sy}}}
+    nbytes = sum(a.nbytes for a in Xo) + sum(a.nbytes for a in td["s"]["y"])
+    import contextlib, io
+    each, val = [], None
+    for i in range(n + 1):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, res = train_model_main(td, 100.0, 3, "tmp", save=False)
+        val = float(res["mse_val_mean"])
+        if i:
+            each.append((time.perf_counter() - t0) * 1e3)
+    mean_ms = float(np.mean(each))
+    return {"value": K * FRAMES_PER_TRIAL / (mean_ms * 1e-3), "unit": UNIT, "ms_per_step": mean_ms, "ms_each": [round(x, 1) for x in each],
+            "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": 8, "val_sse": val,
+            "path": "model.rrr.train_model_main(float64 numpy train_data) -> float(mse_val_mean)  [default operand planes for host arrays: "
+                    + os.environ.get("VS_RRR_PLANES", "3") + "]"}
 
 
 # ----------------------------------------------------------------------------- Linear workload
-def run_linear(args, rank, world, local):
+def make_linear_model(input_dim, n_neurons, device, total_steps=5000, seed=42):
+    """Model + optimizer + OneCycleLR built the way src/train.py:36-57 builds them from the YAML configs."""
+    from model.linear import Linear
+    from optim import FusedAdamW
+    from utils.config_utils import config_from_kwargs, update_config
+    cfg = config_from_kwargs({"model": "include:" + os.path.join(PKG, "config", "model", "linear_video.yaml")})
+    cfg = update_config(os.path.join(PKG, "config", "train", "linear_video.yaml"), cfg)
+    cfg["model"]["encoder"]["input_dim"] = input_dim
+    cfg["model"]["decoder"]["output_dim"] = 100 * n_neurons
+    torch.manual_seed(seed)
+    model = Linear(cfg.model).to(device)
+    o = cfg.optimizer
+    opt = FusedAdamW(model.parameters(), lr=o.lr, weight_decay=o.wd, eps=o.eps)
+    sched = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, total_steps=total_steps, max_lr=o.lr, pct_start=o.warmup_pct,
+                                                div_factor=o.div_factor)
+    return model, opt, sched
+
+
+def run_linear(args, rank, world, local, steps):
     import vsb200 as vs
-    from tests.helpers import make_linear_model
     vs.require_b200()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -477,17 +655,17 @@ def run_linear(args, rank, world, local):
     import warnings
     warnings.filterwarnings("ignore", message="Detected call of `lr_scheduler.step")
     sampler = ClockSampler(local); sampler.start(); sampler.wait_first()
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         step(i, frames_d, ap_d)
     torch.cuda.synchronize(); barrier(world)
     vs.lib.vs_launch_count_reset(); vs.lib.vs_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.begin()
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         loss = step(i, frames_d, ap_d)
     e1.record(); torch.cuda.synchronize(); barrier(world)
-    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
     clocks = sampler.stop()
     launches = int(vs.lib.vs_launch_count())
     n_k, k_ms, _, _ = vs.profile_read(1)
@@ -498,8 +676,13 @@ def run_linear(args, rank, world, local):
     pk, pk_kind = peaks()
     ach = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roof = {"bound": "hbm", "kernel": "vs::dw_adamw_kernel (fused first-layer dW + AdamW)", "achieved": ach, "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(f"linear_B{B}_D{D}_N{N}") if world == 1 else None, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_traffic.json)", "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
-            "avg_launch_ms": k_ms / max(n_k, 1), "share_of_step": k_ms / (ms * args.steps)}
+            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(f"linear_B{B}_D{D}_N{N}") if world == 1 else None,
+            "traffic_unit": "bytes/launch (ncu dram read+write of an EARLIER run, profiles/r01_ncu_traffic.json; not measured in this run)",
+            "peak_source": f"{pk_kind} hbm_gbs", "launches": n_k,
+            "avg_launch_ms": k_ms / max(n_k, 1), "share_of_step": k_ms / (ms * steps),
+            "step_roofline": {"algorithmic_bytes": 28.0 * (P0 + 81920 + 256 * 100 * N) + B * Dl, "note": "SURVEY 8d: 28 B/param + frames",
+                              "floor_ms": (28.0 * (P0 + 81920 + 256 * 100 * N) + B * Dl) / (pk["hbm_gbs"] * 1e9) * 1e3,
+                              "frac": (28.0 * (P0 + 81920 + 256 * 100 * N) + B * Dl) / (pk["hbm_gbs"] * 1e9) * 1e3 / ms}}
 
     # e2e: per step pinned host uint8 frames + targets -> device on a copy stream (double buffered so the copy of
     # batch i+1 overlaps the compute of batch i), loss -> host every step like src/trainer/base.py:154
@@ -537,25 +720,26 @@ def run_linear(args, rank, world, local):
     e2e_loop(2)
     torch.cuda.synchronize(); barrier(world)
     t0 = time.perf_counter()
-    e2e_loop(args.steps)
+    e2e_loop(steps)
     torch.cuda.synchronize(); barrier(world)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / args.steps
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev) / steps
     e2e = {"value": B * FRAMES_PER_TRIAL / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * Dl + 4 * B * 100 * N),
-           "d2h_bytes_per_step": 8, "ms_per_step": e2e_s * 1e3,
+           "d2h_bytes_per_step": 8, "ms_per_step": e2e_s * 1e3, "statistic": f"mean of {steps} consecutive steps (max over ranks)",
            "path": "Linear.fused_train_step(pinned uint8 frames -> device copy stream) + float(loss) every step"}
+    del model, opt, frames_d, ap_d, slots
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, dt = cpu_linear_sample(B, D, N, steps=2)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"oracle Trainer.step (torch fp32 CPU port of the reference step), B={B}, D={D}, N={N}, 2 timed steps ({dt:.2f} s each)"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": "tf32 fwd / f32 update",
             "data": "synthetic", "config": linear_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "loss": float(loss)}
-    print(json.dumps(line))
 
 
 def main():
@@ -564,30 +748,43 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rrr", choices=["rrr", "linear"])
+    ap.add_argument("--workload", default="both", choices=["both", "rrr", "linear"])
     ap.add_argument("--trials", type=int, default=400)
     ap.add_argument("--trials-test", dest="trials_test", type=int, default=80)
     ap.add_argument("--features", type=int, default=110 * 166)
     ap.add_argument("--neurons", type=int, default=144)
-    ap.add_argument("--planes", type=int, default=1)
+    ap.add_argument("--mode", default=None, choices=["exact", "classic"], help="rrr operand mode (default exact; --planes implies classic)")
+    ap.add_argument("--planes", type=int, default=None, help="rrr classic mode: residual planes of the 16-bit operands")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--input-dim", dest="input_dim", type=int, default=120 * 128 * 128)
-    ap.add_argument("--cpu-trials", dest="cpu_trials", type=int, default=40)
+    ap.add_argument("--linear-steps", dest="linear_steps", type=int, default=50)
+    ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=20.0, help="seconds of CPU work of the cpu_baseline sample")
+    ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=150.0, help="--impl reference: seconds for all warm-up + timed fits")
+    ap.add_argument("--dropin-e2e", dest="dropin_e2e", type=int, default=2, help="samples of the float64-numpy drop-in e2e (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--joint", action="store_true", help="rrr: one joint model with a shared V over all ranks' sessions (configs[2])")
+    ap.add_argument("--independent", action="store_true", help="rrr, N > 1: independent per-session fits instead of the joint shared-V model")
+    ap.add_argument("--joint", action="store_true", help="(default for N > 1; kept for compatibility)")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 5 if args.workload == "rrr" else 50
+        args.steps = 5
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":                               # CPU arm: rank 0 alone works, no process group
         reference_arm(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
     rank, world, local = dist_setup(args.gpus)
-    if args.workload == "rrr":
-        run_rrr(args, rank, world, local)
-    else:
-        run_linear(args, rank, world, local)
+    line = None
+    if args.workload in ("both", "rrr"):
+        line = run_rrr(args, rank, world, local)
+    if args.workload in ("both", "linear"):
+        lin_steps = args.linear_steps if args.workload == "both" else max(args.steps, 10)
+        lin = run_linear(args, rank, world, local, lin_steps)
+        if args.workload == "linear":
+            line = lin
+        elif line is not None:
+            line["linear"] = lin
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VS_ABI_VERSION 6
+#define VS_ABI_VERSION 7
 
 enum {
   VS_OK = 0,
@@ -194,12 +194,18 @@ enum {
   VS_OPERAND_BF16 = 0, /* 8 significant bits, fp32 range */
   VS_OPERAND_F16 = 1   /* 11 significant bits at the same tensor-core rate; |x| <= 65504 (the pack calls report overflow) */
 };
+enum {
+  VS_RRR_MODE_CLASSIC = 0, /* Xa and Xb both hold the z-scored matrix in `planes` residual planes */
+  VS_RRR_MODE_EXACT = 1    /* uint8 frames only: Xa = z-score as hi + lo half planes, the backward operand holds the EXACT
+                              integers frame - round(mean); see vs_rrr_pack_u8_exact / vs_rrr_closure_exact */
+};
 typedef struct {
   int64_t K, T, C1, N, r; /* trials, time bins, features without the bias column, neurons, rank */
   int32_t planes;         /* 1, 2 or 3 */
   int64_t ldc;            /* row pitch of Xa in elements, multiple of 64, >= C1 */
   int64_t ldr;            /* row pitch of Xb in elements, multiple of 64, >= T * roundup(K, 16) */
   int32_t fmt;            /* VS_OPERAND_*: 16-bit format of every tensor-core operand plane (X, U, residuals) */
+  int32_t mode;           /* VS_RRR_MODE_* */
 } vs_rrr_dims;
 
 /* pitches the library wants for given sizes */
@@ -225,6 +231,9 @@ int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx,
  * may be NULL to get the smoothed counts only (used to derive the train statistics).      */
 int vs_rrr_smooth_y(const float* counts, int64_t K, int64_t T, int64_t N, double sigma, const double* mean,
                     const double* std_clipped, float* y_out, void* stream);
+/* same, with the float32 rounding residual as a second output (may be NULL): y_out + y_lo_out is the float64 value */
+int vs_rrr_smooth_y2(const float* counts, int64_t K, int64_t T, int64_t N, double sigma, const double* mean,
+                     const double* std_clipped, float* y_out, float* y_lo_out, void* stream);
 /* mean / clipped population std over the K trials of a (K, cols) fp32 matrix (src/utils/utils.py:107-112) */
 int vs_colstats_f32(const float* x, int64_t K, int64_t cols, double* mean, double* std_clipped, void* stream);
 
@@ -241,6 +250,27 @@ int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const 
                    const float* y, const double* U, const double* V, const double* b, double l2,
                    double* loss, double* sse_n, double* dU, double* dV, double* db, int engine,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- exact-operand mode (VS_RRR_MODE_EXACT; d.planes = 2, d.fmt = VS_OPERAND_F16): the mode whose WHOLE FIT lands within
+ * 1e-3 of the float64 reference (the reference trains with one un-line-searched LBFGS.step, src/model/rrr.py:177,199,
+ * which amplifies operand rounding by 3-4 orders of magnitude: DESIGN.md "RRR precision").  For uint8 frames
+ * (src/train_rrr.py:143-165):
+ *   Xa   : 2 x (K*T) x ldc half -- z = (frame - mean)/std as hi + lo planes (22 significant bits)   forward A operand
+ *   Xi   : C1 x ldr half        -- the EXACT integers frame - round(mean), |.| <= 255, layout of Xb  backward A operand
+ *                                  (NULL for splits that are only evaluated, e.g. the validation split)
+ *   isdT : C1 x ldt fp32        -- 1/std[t,c]; the dense backward applies it to its rank-one weights
+ *   qT   : C1 x ldt fp32        -- (mean - round(mean))[t,c]/std[t,c]; rank-T correction of the backward's result
+ * with ldt = vs_rrr_ldt(T).  The residual goes to the backward as hi + lo half planes as well, so every tensor-core
+ * product has one exact or two-plane operand on each side.  y_lo (may be NULL): y + y_lo is the target at float64
+ * precision.  All epilogue sums are float64.                                                             */
+int64_t vs_rrr_ldt(int64_t T);
+int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
+                         const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xi, float* xl, float* isdT,
+                         float* qT, int32_t* overflow_flag, void* stream);
+int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xi, const float* isdT, const float* qT,
+                         int64_t ldt, const float* xl, const float* y, const float* y_lo, const double* U,
+                         const double* V, const double* b, double l2, double* loss, double* sse_n, double* dU,
+                         double* dV, double* db, void* workspace, size_t workspace_bytes, void* stream);
 
 /* src/model/rrr.py:105-130 (predict_y): yhat (K,T,N) fp64 for one split. */
 int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl, const double* U, const double* V,

@@ -575,3 +575,105 @@ def test_linear_large_batch_step_vs_oracle(vs, cuda):
         got = float(model.fused_train_step(frames.to(cuda), ap.to(cuda), opt)); sched.step()
         assert got == pytest.approx(ref, rel=1e-4)
     _assert_weights_close(tr.params, model)
+
+
+# ----------------------------------------------------------------------------- exact-operand mode (the default for uint8 frames)
+def test_rrr_exact_mode_closure_vs_oracle(vs, cuda):
+    """vs_rrr_pack_u8_exact + vs_rrr_closure_exact: z-score as hi+lo half planes forward, exact integer frames x hi+lo
+    residual planes backward, float64 epilogues.  One closure evaluation at full feature width against the float64
+    oracle: loss to 1e-6, every gradient to 2e-5 of its largest entry (one bf16 plane reaches 1e-2 on this problem)."""
+    from model.rrr import RRRGD, pack_session_from_frames
+    ftr, ctr, fte, cte, sidx = _full_size_session(24, 8)
+    data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)], sidx)
+    td_o = {"s": data}
+    params = ro.rrr_init(td_o, 3)
+    rng = np.random.default_rng(1)
+    for k in params:
+        params[k] = params[k] + 0.02 * rng.standard_normal(params[k].shape)
+    loss_o, g_o, sse_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, device=cuda, mode="exact")
+    assert entry["X"][0].dims.mode == vs.RRR_MODE_EXACT and entry["X"][1].Xb is None
+    td = {"s": entry}
+    m = RRRGD(td, 3, l2=100.0); m.to(cuda)
+    assert m.exact and m.planes == 2
+    _params_to_model(m, params, cuda)
+    loss = float(m.loss_and_grad(td, 0))
+    assert loss == pytest.approx(loss_o, rel=1e-6)
+    for k in g_o:
+        got = m.model[k].grad.cpu().numpy()
+        assert np.abs(got - g_o[k]).max() <= 2e-5 * np.abs(g_o[k]).max(), k
+    sse = m.compute_MSE_RRRGD(td, 0)["s"].cpu().numpy()
+    np.testing.assert_allclose(sse, sse_o["s"], rtol=1e-6)
+    # the validation split has no backward operand: evaluation works, a gradient request is refused loudly
+    val = m.compute_MSE_RRRGD(td, 1)["s"]
+    _, _, sse_val_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 1)
+    np.testing.assert_allclose(val.cpu().numpy(), sse_val_o["s"], rtol=1e-6)
+    with pytest.raises(vs.VsError):
+        m.loss_and_grad(td, 1)
+
+
+@pytest.mark.parametrize("K,F,N", [(40, 96, 10), (37, 200, 33), (70, 130, 144)])
+def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N):
+    """Exact-operand mode on shapes that do not fill tiles (K not a multiple of 16, F not of 128, N not of 16)."""
+    from model.rrr import RRRGD, pack_session_from_frames
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=3, K=K, Kt=9, F=F, N=N, raw=True)
+    data, _ = ro.preprocess_session([Xtr, Xte], [ytr, yte], sidx)
+    td_o = {"s": data}
+    params = ro.rrr_init(td_o, 3)
+    rng = np.random.default_rng(2)
+    for k in params:
+        params[k] = params[k] + 0.05 * rng.standard_normal(params[k].shape)
+    loss_o, g_o, _ = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
+    entry = pack_session_from_frames(torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(Xte), torch.from_numpy(yte), sidx, 3,
+                                     device=cuda, mode="exact")
+    td = {"s": entry}
+    m = RRRGD(td, 3, l2=100.0); m.to(cuda)
+    _params_to_model(m, params, cuda)
+    assert float(m.loss_and_grad(td, 0)) == pytest.approx(loss_o, rel=1e-6)
+    for k in g_o:
+        got = m.model[k].grad.cpu().numpy()
+        assert np.abs(got - g_o[k]).max() <= 2e-5 * np.abs(g_o[k]).max(), k
+
+
+def test_rrr_exact_mode_whole_fit_small_vs_oracle(vs, cuda):
+    """train_model_from_frames in its default (exact) mode against the oracle's float64 fit of the same raw arrays:
+    validation SSE, de-z-scored predictions, co-bps and R2 (src/train_rrr.py:193-236)."""
+    from model.rrr import train_model_from_frames
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=0, K=40, Kt=12, F=96, N=10, raw=True)
+    data, gt = ro.preprocess_session([Xtr, Xte], [ytr, yte], sidx)
+    td_o = {"session": data}
+    p_o, mse_o, _ = ro.train_model_main(td_o, 100.0, 3)
+    model, mse, td = train_model_from_frames(torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(Xte), torch.from_numpy(yte), sidx,
+                                             l2=100.0, n_comp=3)
+    assert model.exact
+    assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=1e-5)
+    _, _, pred = model.predict_y_fr(td, "session", 1)
+    _, _, pred_o = ro.predict_y_fr(p_o, td_o, "session", 1)
+    np.testing.assert_allclose(pred.cpu().numpy(), pred_o, rtol=1e-4, atol=1e-6)
+    ev, ev_o = ro.eval_session(pred.cpu().numpy(), gt), ro.eval_session(pred_o, gt)
+    assert ev["co_bps"] == pytest.approx(ev_o["co_bps"], rel=1e-3, abs=1e-6)
+    assert ev["r2"] == pytest.approx(ev_o["r2"], rel=1e-3, abs=1e-6)
+
+
+def test_rrr_default_mode_full_size_fit_within_tolerance(vs, cuda):
+    """BASELINE configs[1] at FULL size (K = 400, C = 18,261, N = 144): the default mode of train_model_from_frames -- the
+    one bench.py times -- against an independent float64 dense fit (torch einsum + autograd + torch.optim.LBFGS on the
+    GPU, bench.fp64_dense_reference).  The reference trains with ONE un-line-searched LBFGS.step whose trajectory
+    amplifies a 1e-6 perturbation of a closure evaluation to ~3e-5 of the result (profiles/r02_precision_sim_full.txt);
+    tolerance rel 1e-3 on validation SSE, co-bps and R2 as BASELINE.json states."""
+    import bench
+    from model.rrr import train_model_from_frames
+    ftr, ctr, fte, cte, sidx = _full_size_session(400, 80)
+    ref = bench.fp64_dense_reference(ftr, ctr, fte, cte, sidx, cuda)
+    model, mse, td = train_model_from_frames(ftr, ctr, fte, cte, sidx, l2=100.0, n_comp=3)
+    assert model.exact
+    got = float(mse["mse_val_mean"])
+    assert abs(got - ref["val_sse"]) <= 1e-3 * ref["val_sse"], (got, ref["val_sse"])
+    assert model.n_closure_evals >= 20
+    # co-bps and per-trial R2 of the de-z-scored, clipped predictions against the unsmoothed test counts
+    # (src/train_rrr.py:193-236); both sit near zero on this signal-free session, hence the absolute floors
+    _, _, pred = model.predict_y_fr(td, "session", 1)
+    gt = cte.numpy().astype(np.float64)
+    ev, ev_o = ro.eval_session(pred.cpu().numpy(), gt), ro.eval_session(ref["pred_test_fr"], gt)
+    assert ev["co_bps"] == pytest.approx(ev_o["co_bps"], rel=1e-3, abs=2e-5), (ev["co_bps"], ev_o["co_bps"])
+    assert ev["r2"] == pytest.approx(ev_o["r2"], rel=1e-3, abs=2e-5), (ev["r2"], ev_o["r2"])

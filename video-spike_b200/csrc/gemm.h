@@ -45,6 +45,13 @@ struct DenseBwdDesc {
   const double* V = nullptr;  // (r, T) device
   float* G = nullptr;         // (C1, ldg)
   long long ldg = 0;
+  // exact-operand mode (vs_rrr_closure_exact): Xb holds the EXACT integers frame - round(mean) and R is split into
+  // r_planes = 2 residual planes (hi, lo) at r_plane_stride elements; the z-score scale 1/std[t,c] is applied per
+  // (feature row, time bin) to the rank-one weights: G_j += V[j,t] * scaleT[c*ldt + t] * D_t
+  int r_planes = 1;
+  long long r_plane_stride = 0;
+  const float* scaleT = nullptr;
+  long long ldt = 0;
 };
 bool rrr_bwd_dense_supported(const DenseBwdDesc& g);
 int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream);

@@ -799,9 +799,12 @@ rrr_bwd_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 struct DensePairParams {
   int C1, m_tiles, Npad, T, K, Kp, nb;
   int stages, tmem_cols, f16, vbytes;
+  int r_planes;              // 1, or 2: R = hi + lo (each plane is a separate B tile, both accumulate into the same D_t)
   const double* V;
   float* G;
   long long ldg;
+  const float* scaleT;       // per (feature row, time bin) weight of the rank-one updates (1/std of the z-score), or NULL
+  long long ldt;
 };
 
 __device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t* r) {
@@ -830,7 +833,8 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int h = p.Npad >> 1;                                   // B rows per CTA = columns per epilogue thread
-  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)h * KB_BYTES;
+  const uint32_t b_bytes = (uint32_t)h * KB_BYTES;             // one residual plane of the B tile
+  const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)p.r_planes * b_bytes;
   const uint32_t bar_full0 = base, bar_empty0 = base + 8u * 16;
   const uint32_t bar_dfull0 = base + 8u * 32, bar_dempty0 = base + 8u * 34;     // two D buffers
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 36);
@@ -881,6 +885,7 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const uint32_t full = mapa_cluster(bar_full0 + 8u * s, 0);
             tma_load_3d_pair(a_dst, &tmA, full, col, m_load * BM, 0);
             tma_load_3d_pair(a_dst + A_TILE_BYTES, &tmB, full, col, rank * h, 0);
+            if (p.r_planes > 1) tma_load_3d_pair(a_dst + A_TILE_BYTES + b_bytes, &tmB, full, col, rank * h, 1);
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -891,7 +896,8 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int lk = (p.K - (p.nb - 1) * 64 + 15) >> 4;
       const int last_ksteps = lk > 4 ? 4 : lk;
       const uint64_t desc0 = make_smem_desc(tiles0);
-      const uint32_t stage16 = stage_bytes >> 4, b16 = A_TILE_BYTES >> 4;
+      const uint32_t stage16 = stage_bytes >> 4, b16 = A_TILE_BYTES >> 4, lo16 = b_bytes >> 4;
+      const bool two = p.r_planes > 1;
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < p.T; ++t) {
@@ -908,10 +914,20 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const uint64_t da = desc0 + (uint64_t)(s * stage16);
             const uint64_t db = da + (uint64_t)b16;
             const int ksteps = (i == p.nb - 1) ? last_ksteps : 4;
+            if (two) {
+              // residual planes of R: the small lo product first, then hi, both into the same D_t
+              const uint64_t dl = db + (uint64_t)lo16;
+              tc_mma_pair(dcol, da, dl, idesc, i > 0 ? 1u : 0u);
+              tc_mma_pair(dcol, da, db, idesc, 1u);
+              if (ksteps > 1) { tc_mma_pair(dcol, da + 2, dl + 2, idesc, 1u); tc_mma_pair(dcol, da + 2, db + 2, idesc, 1u); }
+              if (ksteps > 2) { tc_mma_pair(dcol, da + 4, dl + 4, idesc, 1u); tc_mma_pair(dcol, da + 4, db + 4, idesc, 1u); }
+              if (ksteps > 3) { tc_mma_pair(dcol, da + 6, dl + 6, idesc, 1u); tc_mma_pair(dcol, da + 6, db + 6, idesc, 1u); }
+            } else {
             tc_mma_pair(dcol, da, db, idesc, i > 0 ? 1u : 0u);
             if (ksteps > 1) tc_mma_pair(dcol, da + 2, db + 2, idesc, 1u);
             if (ksteps > 2) tc_mma_pair(dcol, da + 4, db + 4, idesc, 1u);
             if (ksteps > 3) tc_mma_pair(dcol, da + 6, db + 6, idesc, 1u);
+            }
             tc_commit_pair(bar_empty0 + 8u * s);
             if (i == p.nb - 1) tc_commit_pair(bar_dfull0 + 8u * buf);      // D_t complete in both CTAs
           }
@@ -930,11 +946,18 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     float g1[W], g2[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) g1[i] = g2[i] = 0.f;
+    // exact-operand mode: this thread's feature row carries its own z-score scale per time bin (rows past C1 are zero
+    // tiles: any in-range scale will do); four bins per 128-bit load
+    const int srow = (m_tile * BM + q * 32 + lane) < p.C1 ? (m_tile * BM + q * 32 + lane) : p.C1 - 1;
+    const float* sct = p.scaleT ? p.scaleT + (long long)srow * p.ldt : nullptr;
+    float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f);
     for (int t = 0; t < p.T; ++t) {
       const int buf = t & 1;
+      if (sct && (t & 3) == 0) sc4 = __ldg(reinterpret_cast<const float4*>(sct + t));      // ldt % 4 == 0, rows padded to ldt
+      const float sc = (t & 3) == 0 ? sc4.x : ((t & 3) == 1 ? sc4.y : ((t & 3) == 2 ? sc4.z : sc4.w));
       mbar_wait(bar_dfull0 + 8u * buf, (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
-      const float v0 = vsm[t], v1 = vsm[p.T + t], v2 = vsm[2 * p.T + t];
+      const float v0 = vsm[t] * sc, v1 = vsm[p.T + t] * sc, v2 = vsm[2 * p.T + t] * sc;
       const uint32_t td = t_d + (uint32_t)buf * Np;
       // 16 columns of D and G_0 per TMEM round trip, software-pipelined: the loads of round r+1 are in flight while the
       // FMAs and the G_0 store of round r run
@@ -1207,9 +1230,13 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
   p.nb = (int)ceil_div(g.K, 64);
   p.f16 = g.f16 ? 1 : 0;
   p.V = g.V; p.G = g.G; p.ldg = g.ldg;
+  p.r_planes = g.r_planes > 1 ? 2 : 1;
+  p.scaleT = g.scaleT; p.ldt = g.ldt;
+  VS_REQUIRE(!g.scaleT || (g.ldt % 4 == 0 && g.ldt >= g.T && ((uintptr_t)g.scaleT & 15) == 0), VS_ERR_INVALID,
+             "dense RRR backward: the scale table needs a 16-byte aligned base and a pitch that is a multiple of 4 >= T");
   p.vbytes = (int)round_up((long long)DENSE_R * g.T * 4, 1024);
   const int h = p.Npad / 2;
-  const int stage_bytes = A_TILE_BYTES + h * KB_BYTES;
+  const int stage_bytes = A_TILE_BYTES + p.r_planes * h * KB_BYTES;
   int stages = (227 * 1024 - CTRL_BYTES - 1024 - p.vbytes) / stage_bytes;
   if (stages > 8) stages = 8;
   VS_REQUIRE(stages >= 2, VS_ERR_UNSUPPORTED, "dense RRR backward: too many time bins for shared memory");
@@ -1219,6 +1246,7 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
   p.tmem_cols = tcols;
   Operand a; a.ptr = g.Xb; a.rows = g.C1; a.k = g.T * g.Kp; a.ld = g.ldr;
   Operand b; b.ptr = g.R; b.rows = g.Npad; b.k = g.T * g.Kp; b.ld = g.ldr;
+  if (p.r_planes > 1) { b.planes = 2; b.plane_stride = g.r_plane_stride; }
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a, false, g.f16, BM);
   if (rc) return rc;

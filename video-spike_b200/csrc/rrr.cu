@@ -192,6 +192,116 @@ __global__ void __launch_bounds__(256) pack_u8_wide_kernel(const uint8_t* __rest
   }
 }
 
+
+// ------------------------------------------------------------------ exact-operand pack (vs_rrr_pack_u8_exact)
+// The whole-fit parity of the reference's un-line-searched L-BFGS needs ~22 significant bits on every tensor-core
+// operand (profiles/r02_precision_sim_full.txt).  Two facts make that affordable for uint8 frames:
+//   * frame - round(mean) is an INTEGER of magnitude <= 255: exact in IEEE half.  The backward operand Xi holds those
+//     integers (layout of Xb); the z-score 1/std[t,c] moves into the rank-one weights of the dense backward and the
+//     fractional part of the mean into a rank-T correction of its result (epi_b_kernel), so dbeta_t = X_t^T R_t is formed
+//     from an exact A operand and only the small operand R needs two planes;
+//   * the forward operand Xa stores z = (frame - mean)/std as hi + lo half planes (the second plane is the rounding
+//     residual of the first), which the factorised GEMM consumes as three plane products.
+// isdT[c*ldt + t] = 1/std[t,c];  qT[c*ldt + t] = (mean - round(mean))[t,c] / std[t,c]   (zeros for T <= t < ldt)
+__global__ void __launch_bounds__(256) exact_stats_kernel(const int32_t* __restrict__ sorted_idx, const double* __restrict__ mean,
+                                                          const double* __restrict__ sd, long long T, long long C1, long long ldt,
+                                                          float* __restrict__ isdT, float* __restrict__ qT) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C1 * ldt) return;
+  const long long c = i / ldt, t = i % ldt;
+  float a = 0.f, q = 0.f;
+  if (t < T) {
+    const long long col = (long long)sorted_idx[t] * C1 + c;
+    const double m = mean[col], is = 1.0 / sd[col];
+    a = (float)is;
+    q = (float)((m - rint(m)) * is);
+  }
+  isdT[i] = a;
+  qT[i] = q;
+}
+
+// 32 trials (of ONE time bin) x 128 features per block, like pack_u8_wide_kernel.  Xa: two half planes of z (row
+// d = t*K + k); Xi (may be NULL: forward-only splits): the exact integers, transposed through shared memory.
+__global__ void __launch_bounds__(256) pack_u8_exact_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ sorted_idx,
+                                                            const double* __restrict__ mean, const double* __restrict__ sd, long long Tf,
+                                                            long long K, long long T, long long C1, long long ldc, long long ldr,
+                                                            uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xi, float* __restrict__ xl,
+                                                            int* __restrict__ overflow) {
+  __shared__ uint16_t tile[128][34];          // [feature][trial]
+  __shared__ float s_m[128], s_dl[128], s_istd[128];
+  const long long kblocks = (K + 31) / 32;
+  const long long t = blockIdx.x / kblocks, k0 = (blockIdx.x % kblocks) * 32;
+  const long long c0 = (long long)blockIdx.y * 128, Kp = (K + 15) / 16 * 16;
+  const long long f = sorted_idx[t];
+  const long long pa = K * T * ldc;
+  if (threadIdx.x < 128) {
+    const long long c = c0 + threadIdx.x;
+    const long long col = f * C1 + (c < C1 ? c : C1 - 1);
+    const double m = mean[col], mi = rint(m);
+    s_m[threadIdx.x] = (float)mi;
+    s_dl[threadIdx.x] = (float)(m - mi);
+    s_istd[threadIdx.x] = (float)(1.0 / sd[col]);
+  }
+  __syncthreads();
+  const int cx = (threadIdx.x & 31) * 4, ry = threadIdx.x >> 5;
+  bool ovf = false;
+#pragma unroll
+  for (int rr = ry; rr < 32; rr += 8) {
+    const long long k = k0 + rr, c = c0 + cx;
+    uint16_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0}, xi[4] = {0, 0, 0, 0};
+    if (k < K && c < C1) {
+      const uint8_t* src = frames + (k * Tf + f) * C1 + c;
+      uint32_t w;
+      if (c + 4 <= C1 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+        w = __ldg(reinterpret_cast<const uint32_t*>(src));
+      } else {
+        w = 0;
+        for (int i = 0; i < 4; ++i)
+          if (c + i < C1) w |= (uint32_t)src[i] << (8 * i);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (c + i >= C1) continue;
+        const float xc = (float)((w >> (8 * i)) & 0xff) - s_m[cx + i];          // exact integer, |xc| <= 255
+        const float zf = (xc - s_dl[cx + i]) * s_istd[cx + i];
+        if (!(fabsf(zf) <= 65504.f)) ovf = true;
+        const __half h = __float2half_rn(zf);
+        hi[i] = __half_as_ushort(h);
+        lo[i] = __half_as_ushort(__float2half_rn(zf - __half2float(h)));
+        xi[i] = __half_as_ushort(__float2half_rn(xc));
+      }
+      uint16_t* dst = Xa + (t * K + k) * ldc + c;
+      if (c + 4 <= C1) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+        *reinterpret_cast<uint2*>(dst + pa) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+      } else {
+        for (int i = 0; i < 4; ++i)
+          if (c + i < C1) { dst[i] = hi[i]; dst[pa + i] = lo[i]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tile[cx + i][rr] = xi[i];
+  }
+  if (ovf && overflow) atomicOr(overflow, 1);
+  __syncthreads();
+  if (Xi) {
+    const int kp = (threadIdx.x & 15) * 2, cr = threadIdx.x >> 4;
+#pragma unroll
+    for (int cc = cr; cc < 128; cc += 16) {
+      const long long c = c0 + cc, k = k0 + kp;
+      if (c < C1 && k < K) {
+        uint16_t* dst = Xi + c * ldr + t * Kp + k;
+        if (k + 1 < K) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)tile[cc][kp] | ((uint32_t)tile[cc][kp + 1] << 16);
+        else dst[0] = tile[cc][kp];
+      }
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.x < 32) {
+    const long long k = k0 + threadIdx.x;
+    if (k < K) xl[t * K + k] = 1.0f;
+  }
+}
+
 // zeros in the pad trials K <= k < Kp of every time bin of Xb (one thread per (plane, c, t))
 __global__ void __launch_bounds__(256) pad_zero_kernel(uint16_t* __restrict__ Xb, long long rows, long long T, long long K, long long Kp,
                                                        long long ldr) {
@@ -226,7 +336,8 @@ __global__ void colstats_kernel(const uint8_t* __restrict__ frames, long long K,
 // scipy.ndimage.gaussian_filter1d(sigma, axis=1, mode="reflect", truncate=4.0): radius = int(4 sigma + .5),
 // weights exp(-x^2 / (2 sigma^2)) normalised to sum 1, "reflect" = (d c b a | a b c d | d c b a).
 __global__ void smooth_y_kernel(const float* __restrict__ counts, long long K, long long T, long long N, double sigma,
-                                const double* __restrict__ mean, const double* __restrict__ sd, float* __restrict__ out) {
+                                const double* __restrict__ mean, const double* __restrict__ sd, float* __restrict__ out,
+                                float* __restrict__ out_lo) {
   __shared__ double wts[65];
   const int radius = (int)(4.0 * sigma + 0.5);
   if (threadIdx.x == 0) {
@@ -246,7 +357,9 @@ __global__ void smooth_y_kernel(const float* __restrict__ counts, long long K, l
     acc += wts[i + radius] * (double)counts[(k * T + tt) * N + n];
   }
   if (mean) acc = (acc - mean[t * N + n]) / sd[t * N + n];
-  out[idx] = (float)acc;
+  const float hi = (float)acc;
+  out[idx] = hi;
+  if (out_lo) out_lo[idx] = (float)(acc - (double)hi);     // out + out_lo = the float64 value to ~2^-48
 }
 
 __global__ void colstats_f32_kernel(const float* __restrict__ x, long long K, long long cols, double* __restrict__ mean,
@@ -349,37 +462,42 @@ __global__ void __launch_bounds__(256) small_mats_kernel(const double* __restric
 constexpr int kEpiRows = 64;
 
 // block (kb, t, nt) = 64 trials of time bin t x 32 neurons.  Phase 1 (lanes over n): yhat, residual, per-block
-// partials of SSE, db and dV.  Phase 2 (lanes over trial pairs): RV[p][(j,n)][d] = planes of V[j,t] * R, the B
-// operand of GEMM-B, written as bf16x2.  The residual itself never goes to HBM.
-template <bool kPredict, int RMAX>
+// partials of SSE, db and dV.  Phase 2 (lanes over trial pairs): the B operand of the backward GEMM -- R (x) V planes
+// for the factorised route, the plain residual R for the dense per-time-bin route (one plane, or hi + lo half planes in
+// the exact-operand mode) -- written as 16-bit pairs.  The residual itself never goes to HBM.
+// AT = arithmetic of the epilogue: float on the plain 16-bit path (the operands carry ~1e-3 of rounding anyway), double in
+// the exact-operand mode (Z comes out of TMEM as fp32; V, b and the targets y = y + y_lo enter at full precision, and
+// the SSE / db / dV partial sums are wide: dV is a small difference of large sums, DESIGN.md "RRR precision").
+template <bool kPredict, int RMAX, typename AT>
 __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z, long long ldz, int splits, long long split_stride,
-                                                    const float* __restrict__ y, const float* __restrict__ xl,
+                                                    const float* __restrict__ y, const float* __restrict__ y_lo, const float* __restrict__ xl,
                                                     const double* __restrict__ V, const double* __restrict__ b, long long K,
                                                     long long T, long long N, long long Npad, int r, int planes, int fmt, long long ldr,
-                                                    uint16_t* __restrict__ RV, float* __restrict__ sse_part,
-                                                    float* __restrict__ db_part, float* __restrict__ pv_part,
+                                                    uint16_t* __restrict__ RV, AT* __restrict__ sse_part,
+                                                    AT* __restrict__ db_part, AT* __restrict__ pv_part,
                                                     double* __restrict__ yhat, long long Kp, int dense) {
-  __shared__ float Rs[kEpiRows][33];
-  __shared__ float red[8][32][2];
+  __shared__ AT Rs[kEpiRows][33];
+  __shared__ AT red[8][32][2];
   __shared__ float xls[kEpiRows];
-  __shared__ float pvs[8][RMAX];
+  __shared__ AT pvs[8][RMAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long kb = blockIdx.x, t = blockIdx.y, nt = blockIdx.z, KB = gridDim.x, NT = gridDim.z;
   const long long k0 = kb * kEpiRows, d0 = t * K + k0, n0 = nt * 32;
-  float vt[RMAX];
+  AT vt[RMAX];
 #pragma unroll
-  for (int j = 0; j < RMAX; ++j) vt[j] = j < r ? (float)V[(long long)j * T + t] : 0.f;
+  for (int j = 0; j < RMAX; ++j) vt[j] = j < r ? (AT)V[(long long)j * T + t] : (AT)0;
   if (threadIdx.x < kEpiRows) xls[threadIdx.x] = (k0 + threadIdx.x < K) ? xl[d0 + threadIdx.x] : 0.f;
   __syncthreads();
-  float pvacc[RMAX];
+  AT pvacc[RMAX];
 #pragma unroll
-  for (int j = 0; j < RMAX; ++j) pvacc[j] = 0.f;
+  for (int j = 0; j < RMAX; ++j) pvacc[j] = (AT)0;
   const long long n = n0 + lane;
-  const float bn = n < N ? (float)b[n * T + t] : 0.f;
-  float sse = 0.f, sdb = 0.f;
+  const AT bn = n < N ? (AT)b[n * T + t] : (AT)0;
+  AT sse = (AT)0, sdb = (AT)0;
   constexpr int RPW = kEpiRows / 8;   // rows per warp
   // all loads of the block's tile are issued before the first use
-  float z[RPW][RMAX], yv[RPW];
+  float z[RPW][RMAX];
+  AT yv[RPW];
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
     const int rl = w * RPW + i;
@@ -400,27 +518,33 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
         }
       }
     }
-    if constexpr (!kPredict) yv[i] = ok ? __ldg(y + (k * T + t) * N + n) : 0.f;
+    if constexpr (!kPredict) {
+      yv[i] = (AT)0;
+      if (ok) {
+        yv[i] = (AT)__ldg(y + (k * T + t) * N + n);
+        if (y_lo) yv[i] += (AT)__ldg(y_lo + (k * T + t) * N + n);
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
     const int rl = w * RPW + i;
     const long long k = k0 + rl;
-    float res = 0.f;
+    AT res = (AT)0;
     if (k < K && n < N) {
-      float acc = xls[rl] * bn;
+      AT acc = (AT)xls[rl] * bn;
 #pragma unroll
       for (int j = 0; j < RMAX; ++j)
-        if (j < r) acc = fmaf(vt[j], z[i][j], acc);
+        if (j < r) acc = fma(vt[j], (AT)z[i][j], acc);
       if constexpr (kPredict) {
         yhat[(k * T + t) * N + n] = (double)acc;
       } else {
         res = acc - yv[i];
-        sse = fmaf(res, res, sse);
-        sdb = fmaf(xls[rl], res, sdb);
+        sse = fma(res, res, sse);
+        sdb = fma((AT)xls[rl], res, sdb);
 #pragma unroll
         for (int j = 0; j < RMAX; ++j)
-          if (j < r) pvacc[j] = fmaf(res, z[i][j], pvacc[j]);
+          if (j < r) pvacc[j] = fma(res, (AT)z[i][j], pvacc[j]);
       }
     }
     if constexpr (!kPredict) Rs[rl][lane] = res;
@@ -430,8 +554,8 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
     red[w][lane][1] = sdb;
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
-      const float s = warp_sum(pvacc[j]);
-      if (lane == 0) pvs[w][j] = s;
+      const AT sj = warp_sum(pvacc[j]);
+      if (lane == 0) pvs[w][j] = sj;
     }
     __syncthreads();
     // phase 2: lane = trial pair (2*lane, 2*lane+1), warp w covers neurons w*4 .. w*4+3 of the tile.  Columns follow Xb:
@@ -439,14 +563,19 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
     const long long ka = k0 + 2 * lane;
     const long long dcol = t * Kp + ka;
     if (dense) {
-      // dense backward (tc::rrr_bwd_dense): the plain residual R[n][t*Kp + k]
+      // dense backward (tc::rrr_bwd_dense): the plain residual R[n][t*Kp + k], `planes` residual planes of Npad rows
+      const long long prd = Npad * ldr;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int nl = w * 4 + i;
         const long long nn = n0 + nl;
         if (nn >= N || ka >= Kp) continue;
-        const uint32_t lo = enc16(Rs[2 * lane][nl], fmt), hi = enc16(Rs[2 * lane + 1][nl], fmt);
-        *reinterpret_cast<uint32_t*>(RV + nn * ldr + dcol) = lo | (hi << 16);
+        float ra = (float)Rs[2 * lane][nl], rb = (float)Rs[2 * lane + 1][nl];
+        for (int pl = 0; pl < planes && pl < 2; ++pl) {
+          const uint32_t lo = enc16(ra, fmt), hi = enc16(rb, fmt);
+          *reinterpret_cast<uint32_t*>(RV + pl * prd + nn * ldr + dcol) = lo | (hi << 16);
+          ra -= dec16((uint16_t)lo, fmt); rb -= dec16((uint16_t)hi, fmt);
+        }
       }
     } else {
     const long long prv = (long long)r * Npad * ldr;
@@ -455,46 +584,49 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
       const int nl = w * 4 + i;
       const long long nn = n0 + nl;
       if (nn >= N || ka >= Kp) continue;
-      const float r0v = Rs[2 * lane][nl], r1v = Rs[2 * lane + 1][nl];
+      const float r0v = (float)Rs[2 * lane][nl], r1v = (float)Rs[2 * lane + 1][nl];
 #pragma unroll
       for (int j = 0; j < RMAX; ++j) {
         if (j >= r) continue;
         uint16_t pl0[3], pl1[3];
         if (planes == 1) {   // plain bf16 operand: no fp64 on this path (the vector fp64 pipe is narrow)
-          pl0[0] = enc16(vt[j] * r0v, fmt); pl1[0] = enc16(vt[j] * r1v, fmt);
+          pl0[0] = enc16((float)vt[j] * r0v, fmt); pl1[0] = enc16((float)vt[j] * r1v, fmt);
           pl0[1] = pl0[2] = pl1[1] = pl1[2] = 0;
         } else {
-          split_planes((double)(vt[j] * r0v), planes, fmt, pl0);
-          split_planes((double)(vt[j] * r1v), planes, fmt, pl1);
+          split_planes((double)((float)vt[j] * r0v), planes, fmt, pl0);
+          split_planes((double)((float)vt[j] * r1v), planes, fmt, pl1);
         }
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          if (p >= planes) continue;
-          *reinterpret_cast<uint32_t*>(RV + p * prv + ((long long)j * Npad + nn) * ldr + dcol) = (uint32_t)pl0[p] | ((uint32_t)pl1[p] << 16);
+        for (int pq = 0; pq < 3; ++pq) {
+          if (pq >= planes) continue;
+          *reinterpret_cast<uint32_t*>(RV + pq * prv + ((long long)j * Npad + nn) * ldr + dcol) = (uint32_t)pl0[pq] | ((uint32_t)pl1[pq] << 16);
         }
       }
     }
     }
     // phase 3: per-(t, kb, n) partials, the 8 warps' sums added in a fixed order
     if (w == 0 && n < N) {
-      float s0 = 0.f, s1 = 0.f;
+      AT s0 = (AT)0, s1 = (AT)0;
 #pragma unroll
       for (int w2 = 0; w2 < 8; ++w2) { s0 += red[w2][lane][0]; s1 += red[w2][lane][1]; }
       sse_part[(t * KB + kb) * N + n] = s0;
       db_part[(t * KB + kb) * N + n] = s1;
     }
     if (threadIdx.x < r) {
-      float s = 0.f;
-      for (int w2 = 0; w2 < 8; ++w2) s += pvs[w2][threadIdx.x];
-      pv_part[((t * KB + kb) * NT + nt) * r + threadIdx.x] = s;
+      AT sj = (AT)0;
+      for (int w2 = 0; w2 < 8; ++w2) sj += pvs[w2][threadIdx.x];
+      pv_part[((t * KB + kb) * NT + nt) * r + threadIdx.x] = sj;
     }
   }
 }
 
-// per (t, n): db and SSE from the per-block partials (ordered sum over the trial blocks)
-__global__ void __launch_bounds__(128) reduce_part_kernel(const float* __restrict__ sse_part, const float* __restrict__ db_part,
+// per (t, n): db and SSE from the per-block partials (ordered sum over the trial blocks); sr (may be NULL) receives
+// sum_k xl*R = the column sums of the residual the exact-operand backward's mean correction needs
+template <typename AT>
+__global__ void __launch_bounds__(128) reduce_part_kernel(const AT* __restrict__ sse_part, const AT* __restrict__ db_part,
                                                           const double* __restrict__ b, long long KB, long long T, long long N,
-                                                          double l2, double* __restrict__ db, double* __restrict__ sse_tn) {
+                                                          double l2, double* __restrict__ db, double* __restrict__ sse_tn,
+                                                          float* __restrict__ sr, long long Npad) {
   const long long t = blockIdx.y;
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -504,11 +636,13 @@ __global__ void __launch_bounds__(128) reduce_part_kernel(const float* __restric
     sdb += (double)db_part[(t * KB + kb) * N + n];
   }
   if (db) db[n * T + t] = 2.0 * sdb + 2.0 * l2 * b[n * T + t];
+  if (sr) sr[t * Npad + n] = (float)sdb;
   sse_tn[t * N + n] = sse;
 }
 
 // final scalars: sse_n, loss, dV
-__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ sse_tn, const float* __restrict__ pv_part,
+template <typename AT>
+__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ sse_tn, const AT* __restrict__ pv_part,
                                                        const double* __restrict__ G, const double* __restrict__ W,
                                                        const double* __restrict__ V, const double* __restrict__ b, long long KB,
                                                        long long NT, long long T, long long N, int r, double l2, double* __restrict__ sse_n,
@@ -576,16 +710,54 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
 // kFast (plain bf16 operands, one split): the whole combination runs in fp32 and is widened once per output -- the
 // vector fp64 pipe of the B200 is narrow and the gradient carries the ~1e-3 operand rounding anyway.  Otherwise
 // (residual planes / split-K partials) everything is summed in fp64.
-template <bool kFast, int RMAX>
+// kCorr (exact-operand mode): the backward contracted the integers frame - round(mean) instead of frame - mean; the
+// missing part is rank T:  Gacc[c,(j,n)] -= sum_t V[j,t] * qT[c,t] * SR[t,n]   with qT = (mean - round(mean))/std and
+// SR[t,n] = sum_k R[k,t,n].  |mean - round(mean)| <= 1/2, so the correction is < 1 % of Gacc; it is formed in fp32.
+template <bool kFast, int RMAX, bool kCorr>
 __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Gacc, long long ldg, int splits,
                                                     long long split_stride, const double* __restrict__ U,
                                                     const double* __restrict__ W, long long C1, long long N, long long Npad, int r,
-                                                    double l2, double* __restrict__ dU) {
+                                                    double l2, double* __restrict__ dU, const float* __restrict__ qT, long long ldt,
+                                                    const float* __restrict__ SR, const double* __restrict__ V, long long T) {
   __shared__ float Gs[RMAX][32][33];
   __shared__ double Ws[RMAX * RMAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long c0 = (long long)blockIdx.x * 32, n0 = (long long)blockIdx.y * 32;
   if (threadIdx.x < r * r) Ws[threadIdx.x] = W[threadIdx.x];
+  float corr[4][RMAX];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) corr[i][j] = 0.f;
+  if constexpr (kCorr) {
+    __shared__ float qs[32][33], srs[32][33], vsj[RMAX][32];
+    for (long long t0 = 0; t0 < T; t0 += 32) {
+      __syncthreads();
+      // qs[c][t], srs[t][n], vsj[j][t] for 32 time bins (zero past T)
+      for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+        const int a = e >> 5, bq = e & 31;
+        const long long c = c0 + a, tt = t0 + bq;
+        qs[a][bq] = (c < C1 && tt < T) ? __ldg(qT + c * ldt + tt) : 0.f;
+        const long long t2 = t0 + a, nn = n0 + bq;
+        srs[a][bq] = (t2 < T && nn < N) ? __ldg(SR + t2 * Npad + nn) : 0.f;
+      }
+      for (int e = threadIdx.x; e < RMAX * 32; e += 256) {
+        const int j = e >> 5, tq = e & 31;
+        vsj[j][tq] = (j < r && t0 + tq < T) ? (float)V[(long long)j * T + t0 + tq] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int tq = 0; tq < 32; ++tq) {
+        const float sv = srs[tq][lane];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float qv = qs[w + 8 * i][tq] * sv;
+#pragma unroll
+          for (int j = 0; j < RMAX; ++j) corr[i][j] = fmaf(vsj[j][tq], qv, corr[i][j]);
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = w + 8 * i;
@@ -601,7 +773,7 @@ __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Ga
         } else {
           double gsum = 0.0;
           for (int sp = 0; sp < splits; ++sp) gsum += (double)gp[(long long)sp * split_stride];
-          gv = (float)gsum;
+          gv = (float)(gsum - (double)corr[i][j]);
         }
       }
       Gs[j][cl][lane] = gv;
@@ -646,7 +818,8 @@ __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Ga
 // ------------------------------------------------------------------ host orchestration
 struct Ws {
   uint16_t *Ub, *RV;
-  float *Z, *Gacc, *sse_part, *db_part, *pv_part;
+  float *Z, *Gacc, *SR;
+  void *sse_part, *db_part, *pv_part;   // float, or double in the exact-operand mode
   void* bal;                 // tail-wave split-K scratch of the GEMMs
   double *Gp, *G, *W, *sse_tn;
   long long Npad, ldz, gp_blocks, KB;
@@ -659,11 +832,15 @@ struct Ws {
 // (#MMA steps) * 2^-24.  That is far below bf16 operand noise (planes == 1) but not below the
 // ~2^-24 the 3-plane mode is after: there each TMEM accumulation run is limited to 16 k-blocks and
 // the partial tiles are summed in fp64 by the epilogue kernels.
-static int hp_splits(long long k_elems, int planes) {
+static int hp_splits(long long k_elems, int planes, int mode) {
   // experiment hook: VS_RRR_RUN=<k-blocks per TMEM accumulation run> forces split-K in the single-plane mode too
   static int run1 = -1;
   if (run1 < 0) { const char* e = getenv("VS_RRR_RUN"); run1 = e ? atoi(e) : 0; }
-  if (planes < 2) {
+  // exact-operand mode: one TMEM run.  The truncation of the fp32 accumulator acts as a smooth relative shrink of the
+  // prediction (~1e-4 over 3400 MMA steps), to which the fit is insensitive, unlike to operand rounding noise
+  // (profiles/r02_precision_sim_full.txt: shrink 6e-5 -> 1e-5 on the final validation SSE); split-K partial tiles would
+  // cost more HBM traffic than the GEMM itself.
+  if (planes < 2 || mode == VS_RRR_MODE_EXACT) {
     if (run1 <= 0) return 1;
     long long s1 = ceil_div(ceil_div(k_elems, 64), run1);
     return (int)(s1 < 1 ? 1 : (s1 > 256 ? 256 : s1));
@@ -679,8 +856,9 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.ldz = d.r * w.Npad;
   w.gp_blocks = ceil_div(d.C1, 256 * kPrepC) * d.N;
   w.KB = ceil_div(d.K, kEpiRows);
-  w.splits_f = hp_splits(d.C1, d.planes);
-  w.splits_b = hp_splits(d.T * round_up(d.K, 16), d.planes);
+  w.splits_f = hp_splits(d.C1, d.planes, d.mode);
+  w.splits_b = hp_splits(d.T * round_up(d.K, 16), d.planes, d.mode);
+  const size_t pe = d.mode == VS_RRR_MODE_EXACT ? 8 : 4;     // element size of the epilogue partials
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += (size_t)round_up((long long)bytes, 1024); return q; };
@@ -689,9 +867,10 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.RV = (uint16_t*)take((size_t)d.planes * w.ldz * d.ldr * 2);
   w.Z = (float*)take((size_t)w.splits_f * KT * w.ldz * 4);
   w.Gacc = (float*)take((size_t)w.splits_b * d.C1 * w.ldz * 4);
-  w.sse_part = (float*)take((size_t)d.T * w.KB * d.N * 4);
-  w.db_part = (float*)take((size_t)d.T * w.KB * d.N * 4);
-  w.pv_part = (float*)take((size_t)d.T * w.KB * ceil_div(d.N, 32) * d.r * 4);
+  w.sse_part = take((size_t)d.T * w.KB * d.N * pe);
+  w.db_part = take((size_t)d.T * w.KB * d.N * pe);
+  w.pv_part = take((size_t)d.T * w.KB * ceil_div(d.N, 32) * d.r * pe);
+  w.SR = (float*)take((size_t)d.T * w.Npad * 4);
   w.bal = take(tc::balance_ws_bytes());
   w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
   w.G = (double*)take(kMaxR * kMaxR * 8);
@@ -708,6 +887,9 @@ static int check_dims(const vs_rrr_dims& d) {
   VS_REQUIRE(d.fmt == VS_OPERAND_BF16 || d.fmt == VS_OPERAND_F16, VS_ERR_INVALID, "rrr: fmt must be VS_OPERAND_BF16 or VS_OPERAND_F16");
   VS_REQUIRE(d.ldc >= d.C1 && d.ldc % 8 == 0 && d.ldr >= d.T * round_up(d.K, 16) && d.ldr % 8 == 0, VS_ERR_INVALID, "rrr: bad pitches");
   VS_REQUIRE(d.K * d.T < (1ll << 31) && d.C1 < (1ll << 31), VS_ERR_UNSUPPORTED, "rrr: dimension exceeds 2^31");
+  VS_REQUIRE(d.mode == VS_RRR_MODE_CLASSIC || d.mode == VS_RRR_MODE_EXACT, VS_ERR_INVALID, "rrr: mode must be VS_RRR_MODE_*");
+  VS_REQUIRE(d.mode != VS_RRR_MODE_EXACT || (d.planes == 2 && d.fmt == VS_OPERAND_F16), VS_ERR_INVALID,
+             "rrr: the exact-operand mode uses two IEEE-half planes (planes = 2, fmt = VS_OPERAND_F16)");
   return VS_OK;
 }
 
@@ -830,12 +1012,20 @@ extern "C" int vs_rrr_pack_u8(const uint8_t* frames, int64_t Tf, const int32_t* 
   return VS_OK;
 }
 
-extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const float* xl, const float* y,
-                              const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,
-                              double* dU, double* dV, double* db, int engine, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+// exact-operand extras of one split (vs_rrr_closure_exact); all NULL in the classic mode
+struct ExactArgs {
+  const float* isdT = nullptr;   // (C1, ldt): 1/std[t,c]
+  const float* qT = nullptr;     // (C1, ldt): (mean - round(mean))[t,c] / std[t,c]
+  long long ldt = 0;
+  const float* y_lo = nullptr;   // (K,T,N): y = y + y_lo at float64 precision (may be NULL)
+};
+
+static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const ExactArgs& ex, const float* xl, const float* y,
+                        const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,
+                        double* dU, double* dV, double* db, int engine, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
+  const bool exact = d.mode == VS_RRR_MODE_EXACT;
   VS_REQUIRE(Xa && xl && y && U && V && b, VS_ERR_INVALID, "vs_rrr_closure: null pointer");
   VS_REQUIRE(!dU || Xb, VS_ERR_INVALID, "vs_rrr_closure: dU needs Xb");
   VS_REQUIRE(workspace && workspace_bytes >= vs_rrr_workspace(d), VS_ERR_WORKSPACE, "vs_rrr_closure: workspace too small (%zu < %zu)",
@@ -861,29 +1051,88 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   tc::DenseBwdDesc dd;
   dd.Xb = Xb; dd.R = w.RV; dd.C1 = d.C1; dd.K = d.K; dd.Kp = w.Kp; dd.T = d.T; dd.Npad = w.Npad; dd.ldr = d.ldr;
   dd.r = r; dd.f16 = d.fmt == VS_OPERAND_F16; dd.V = V; dd.G = w.Gacc; dd.ldg = w.ldz;
-  const bool dense = dU && d.planes == 1 && engine != VS_ENGINE_SIMT && w.splits_b == 1 && tc::rrr_bwd_dense_supported(dd);
+  if (exact) { dd.r_planes = 2; dd.r_plane_stride = w.Npad * d.ldr; dd.scaleT = ex.isdT; dd.ldt = ex.ldt; }
+  const bool dense_ok = engine != VS_ENGINE_SIMT && w.splits_b == 1 && tc::rrr_bwd_dense_supported(dd);
+  if (exact && dU)
+    VS_REQUIRE(dense_ok && ex.isdT && ex.qT, VS_ERR_UNSUPPORTED,
+               "vs_rrr_closure_exact: the exact-operand backward needs the tcgen05 dense kernel (r = 3, N <= 160) and the scale tables");
+  const bool dense = dU && (exact || d.planes == 1) && dense_ok;
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
-  if (r <= 4) {
-    VS_LAUNCH((epi_f_kernel<false, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr, w.Kp, dense ? 1 : 0);
-  } else {
-    VS_LAUNCH((epi_f_kernel<false, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV, w.sse_part, w.db_part, w.pv_part, nullptr, w.Kp, dense ? 1 : 0);
-  }
+#define VS_EPI_F(RM, AT) VS_LAUNCH((epi_f_kernel<false, RM, AT>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, ex.y_lo, xl, V, b,       \
+                                   (long long)d.K, (long long)d.T, (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV,   \
+                                   (AT*)w.sse_part, (AT*)w.db_part, (AT*)w.pv_part, nullptr, w.Kp, dense ? 1 : 0)
+  if (exact) { if (r <= 4) { VS_EPI_F(4, double); } else { VS_EPI_F(kMaxR, double); } }
+  else { if (r <= 4) { VS_EPI_F(4, float); } else { VS_EPI_F(kMaxR, float); } }
+#undef VS_EPI_F
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
-  VS_LAUNCH(reduce_part_kernel, g2, 128, 0, st, w.sse_part, w.db_part, b, w.KB, (long long)d.T, (long long)d.N, l2, db, w.sse_tn);
-  VS_LAUNCH(finalize_kernel, 1, 1024, 0, st, w.sse_tn, w.pv_part, w.G, w.W, V, b, w.KB, (long long)ceil_div(d.N, 32), (long long)d.T,
-            (long long)d.N, r, l2, sse_n, loss, dV);
+  const long long NT = ceil_div(d.N, 32);
+  if (exact) {
+    VS_LAUNCH(reduce_part_kernel<double>, g2, 128, 0, st, (const double*)w.sse_part, (const double*)w.db_part, b, w.KB, (long long)d.T,
+              (long long)d.N, l2, db, w.sse_tn, w.SR, w.Npad);
+    VS_LAUNCH(finalize_kernel<double>, 1, 1024, 0, st, w.sse_tn, (const double*)w.pv_part, w.G, w.W, V, b, w.KB, NT, (long long)d.T,
+              (long long)d.N, r, l2, sse_n, loss, dV);
+  } else {
+    VS_LAUNCH(reduce_part_kernel<float>, g2, 128, 0, st, (const float*)w.sse_part, (const float*)w.db_part, b, w.KB, (long long)d.T,
+              (long long)d.N, l2, db, w.sse_tn, (float*)nullptr, w.Npad);
+    VS_LAUNCH(finalize_kernel<float>, 1, 1024, 0, st, w.sse_tn, (const float*)w.pv_part, w.G, w.W, V, b, w.KB, NT, (long long)d.T,
+              (long long)d.N, r, l2, sse_n, loss, dV);
+  }
   if (dU) {
     // stage 3/4: Gacc and dU
     rc = dense ? tc::rrr_bwd_dense(dd, st) : gemm_b(d, Xb, w, engine, st, &sb);
     if (rc) return rc;
     dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
     const bool fast = d.planes == 1 && sb == 1;
-#define VS_EPI_B(FAST, RM) VS_LAUNCH((epi_b_kernel<FAST, RM>), g4, 256, 0, st, w.Gacc, w.ldz, sb, (long long)d.C1 * w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU)
-    if (r <= 4) { if (fast) { VS_EPI_B(true, 4); } else { VS_EPI_B(false, 4); } }
-    else { if (fast) { VS_EPI_B(true, kMaxR); } else { VS_EPI_B(false, kMaxR); } }
+#define VS_EPI_B(FAST, RM, CORR) VS_LAUNCH((epi_b_kernel<FAST, RM, CORR>), g4, 256, 0, st, w.Gacc, w.ldz, sb, (long long)d.C1 * w.ldz, U, w.W, \
+                                           (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU, ex.qT, ex.ldt, w.SR, V, (long long)d.T)
+    if (exact) { if (r <= 4) { VS_EPI_B(false, 4, true); } else { VS_EPI_B(false, kMaxR, true); } }
+    else if (r <= 4) { if (fast) { VS_EPI_B(true, 4, false); } else { VS_EPI_B(false, 4, false); } }
+    else { if (fast) { VS_EPI_B(true, kMaxR, false); } else { VS_EPI_B(false, kMaxR, false); } }
 #undef VS_EPI_B
+  }
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const float* xl, const float* y,
+                              const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,
+                              double* dU, double* dV, double* db, int engine, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  VS_REQUIRE(d.mode == VS_RRR_MODE_CLASSIC, VS_ERR_INVALID, "vs_rrr_closure: exact-operand splits go through vs_rrr_closure_exact");
+  return closure_impl(d, Xa, Xb, ExactArgs(), xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, engine, workspace, workspace_bytes, stream);
+}
+
+extern "C" int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xi, const float* isdT, const float* qT,
+                                    int64_t ldt, const float* xl, const float* y, const float* y_lo, const double* U, const double* V,
+                                    const double* b, double l2, double* loss, double* sse_n, double* dU, double* dV, double* db,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT, VS_ERR_INVALID, "vs_rrr_closure_exact: dims.mode must be VS_RRR_MODE_EXACT");
+  ExactArgs ex;
+  ex.isdT = isdT; ex.qT = qT; ex.ldt = ldt; ex.y_lo = y_lo;
+  return closure_impl(d, Xa, Xi, ex, xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, VS_ENGINE_AUTO, workspace, workspace_bytes, stream);
+}
+
+extern "C" int64_t vs_rrr_ldt(int64_t T) { return round_up(T, 4); }
+
+extern "C" int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
+                                    const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xi, float* xl, float* isdT,
+                                    float* qT, int32_t* overflow_flag, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: dims.mode must be VS_RRR_MODE_EXACT");
+  VS_REQUIRE(frames && sorted_idx && mean && std_clipped && Xa && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: bad arguments");
+  VS_REQUIRE((isdT == nullptr) == (qT == nullptr), VS_ERR_INVALID, "vs_rrr_pack_u8_exact: the two scale tables go together");
+  VS_REQUIRE(d.ldr % 2 == 0, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: ldr must be even");
+  dim3 gw((unsigned)(ceil_div(d.K, 32) * d.T), (unsigned)ceil_div(d.C1, 128));
+  VS_REQUIRE(gw.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8_exact: too many columns");
+  VS_LAUNCH(pack_u8_exact_kernel, gw, 256, 0, stream, frames, sorted_idx, mean, std_clipped, (long long)Tf, (long long)d.K, (long long)d.T,
+            (long long)d.C1, (long long)d.ldc, (long long)d.ldr, Xa, Xi, xl, overflow_flag);
+  if (Xi && round_up(d.K, 16) > d.K)
+    VS_LAUNCH(pad_zero_kernel, (unsigned)ceil_div((long long)d.C1 * d.T, 256), 256, 0, stream, Xi, (long long)d.C1, (long long)d.T,
+              (long long)d.K, (long long)round_up(d.K, 16), (long long)d.ldr);
+  if (isdT) {
+    const long long ldt = round_up(d.T, 4);
+    VS_LAUNCH(exact_stats_kernel, (unsigned)ceil_div(d.C1 * ldt, 256), 256, 0, stream, sorted_idx, mean, std_clipped, (long long)d.T,
+              (long long)d.C1, ldt, isdT, qT);
   }
   return VS_OK;
 }
@@ -911,11 +1160,11 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   if (rc) return rc;
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (d.r <= 4) {
-    VS_LAUNCH((epi_f_kernel<true, 4>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat, 0ll, 0);
+    VS_LAUNCH((epi_f_kernel<true, 4, float>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, yhat, 0ll, 0);
   } else {
-    VS_LAUNCH((epi_f_kernel<true, kMaxR>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, nullptr, nullptr, nullptr, yhat, 0ll, 0);
+    VS_LAUNCH((epi_f_kernel<true, kMaxR, float>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, yhat, 0ll, 0);
   }
   return VS_OK;
 }
@@ -927,7 +1176,18 @@ extern "C" int vs_rrr_smooth_y(const float* counts, int64_t K, int64_t T, int64_
   VS_REQUIRE((mean == nullptr) == (std_clipped == nullptr), VS_ERR_INVALID, "vs_rrr_smooth_y: mean and std go together");
   const long long n = K * T * N;
   VS_LAUNCH(smooth_y_kernel, (unsigned)ceil_div(n, 256), 256, 0, stream, counts, (long long)K, (long long)T, (long long)N, sigma, mean,
-            std_clipped, y_out);
+            std_clipped, y_out, (float*)nullptr);
+  return VS_OK;
+}
+
+extern "C" int vs_rrr_smooth_y2(const float* counts, int64_t K, int64_t T, int64_t N, double sigma, const double* mean,
+                                const double* std_clipped, float* y_out, float* y_lo_out, void* stream) {
+  VS_REQUIRE(counts && y_out && K > 0 && T > 0 && N > 0, VS_ERR_INVALID, "vs_rrr_smooth_y2: bad arguments");
+  VS_REQUIRE(sigma > 0.0 && (int)(4.0 * sigma + 0.5) <= 32, VS_ERR_UNSUPPORTED, "vs_rrr_smooth_y2: sigma out of range");
+  VS_REQUIRE((mean == nullptr) == (std_clipped == nullptr), VS_ERR_INVALID, "vs_rrr_smooth_y2: mean and std go together");
+  const long long n = K * T * N;
+  VS_LAUNCH(smooth_y_kernel, (unsigned)ceil_div(n, 256), 256, 0, stream, counts, (long long)K, (long long)T, (long long)N, sigma, mean,
+            std_clipped, y_out, y_lo_out);
   return VS_OK;
 }
 

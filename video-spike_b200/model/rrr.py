@@ -12,9 +12,11 @@ of each session is packed ONCE into device-resident bf16 operand planes (vs_rrr_
 closure evaluation is one vs_rrr_closure call: two tcgen05 GEMMs plus ordered reductions that
 return the loss and write dU, dV, db straight into `param.grad`.  No CPU path exists.
 
-Precision: `planes` (env VS_RRR_PLANES, default 1) selects how many bf16 residual planes represent
-each tensor-core operand: 1 = plain bf16 (fast path, BASELINE config "bf16"), 3 = ~fp32 operand
-accuracy.  Accumulation is fp32 in TMEM, reductions fp64.  See DESIGN.md "RRR precision".
+Precision (DESIGN.md "RRR precision"): the reference's un-line-searched L-BFGS amplifies operand rounding by 3-4
+orders of magnitude, so the defaults are the modes whose WHOLE FIT stays within 1e-3 of the float64 reference:
+splits packed from uint8 frames use the exact-operand mode (`rrr_mode`), float64 numpy splits 3 bf16 residual
+planes (`planes`, env VS_RRR_PLANES).  planes = 1 is the fastest, non-parity setting.  Accumulation is fp32 in
+TMEM, reductions fp64.
 """
 from __future__ import annotations
 
@@ -44,6 +46,18 @@ def _op_dtype(fmt):
     return torch.float16 if fmt == vs.OPERAND_F16 else torch.bfloat16
 
 
+def rrr_mode(mode=None):
+    """"exact" (default) or "classic" -- how splits packed from uint8 frames represent X (include/vs_b200.h,
+    VS_RRR_MODE_*).  exact: the mode whose whole fit lands within 1e-3 of the float64 reference (z-score as hi + lo half
+    planes for the forward, exact integer frames for the backward, float64 epilogues, float64 L-BFGS history).
+    classic: `planes` residual planes of the z-scored matrix for both contractions (planes = 1 is the fastest setting;
+    its fit is ~2e-3 away from the reference's, DESIGN.md "RRR precision").  Select with `mode=` or VS_RRR_MODE."""
+    mode = mode or os.environ.get("VS_RRR_MODE") or "exact"
+    if mode not in ("exact", "classic"):
+        raise ValueError("mode must be 'exact' or 'classic'")
+    return mode
+
+
 def np2tensor(v):
     return v if isinstance(v, torch.Tensor) else torch.from_numpy(v)
 
@@ -68,13 +82,15 @@ _PINNED_STAGES = {}
 
 
 def _pinned_stage(numel):
-    """A reusable pinned float64 staging buffer of `numel` elements (allocating pinned memory costs milliseconds, so it
-    is cached per size).  The event guards reuse: the previous upload out of the buffer must have finished."""
-    st = _PINNED_STAGES.get(numel)
-    if st is None:
-        st = _PINNED_STAGES[numel] = {"buf": torch.empty(numel, dtype=torch.float64).pin_memory(), "event": torch.cuda.Event()}
-    else:
+    """A reusable pinned float64 staging buffer of `numel` elements (allocating pinned memory costs milliseconds).  ONE
+    grow-only buffer per process, sliced to the size asked for: a sweep over sessions of different sizes pins the largest
+    one, not one buffer per size.  The event guards reuse: the previous upload out of the buffer must have finished."""
+    st = _PINNED_STAGES.get("stage")
+    if st is not None:
         st["event"].synchronize()
+    if st is None or st["full"].numel() < numel:
+        st = _PINNED_STAGES["stage"] = {"full": torch.empty(numel, dtype=torch.float64).pin_memory(), "event": torch.cuda.Event()}
+    st["buf"] = st["full"][:numel]
     return st
 
 
@@ -123,6 +139,7 @@ class _PackedSplit:
         d = vs.RrrDims(K, T, C - 1, N, r, planes, vs.lib.vs_rrr_ldc(C - 1), vs.lib.vs_rrr_ldr(K, T), fmt)
         self.dims = d
         KT = K * T
+        self.exact = None
         self.Xa = torch.empty((planes, KT, d.ldc), dtype=_op_dtype(fmt), device=device)
         self.Xb = torch.empty((planes, C - 1, d.ldr), dtype=_op_dtype(fmt), device=device)
         self.xl = torch.empty(KT, dtype=torch.float32, device=device)
@@ -138,12 +155,15 @@ class _PackedSplit:
         self.y = torch.from_numpy(np.ascontiguousarray(y)).to(device=device, dtype=torch.float32).contiguous()
 
     @classmethod
-    def from_device(cls, dims, Xa, Xb, xl, y, overflow=None):
-        """Wrap operands that were produced on the device (vs_rrr_pack_u8 path)."""
+    def from_device(cls, dims, Xa, Xb, xl, y, overflow=None, exact=None):
+        """Wrap operands that were produced on the device (vs_rrr_pack_u8 / vs_rrr_pack_u8_exact path).
+        `exact`: {"isdT", "qT", "ldt", "y_lo"} of an exact-operand split (Xb then holds the integer operand, or None)."""
         self = cls.__new__(cls)
         self.K, self.T, self.C1, self.N = dims.K, dims.T, dims.C1, dims.N
         self.dims, self.Xa, self.Xb, self.xl, self.y, self.overflow = dims, Xa, Xb, xl, y, overflow
+        self.exact = exact
         self.ready = None
+        self._keep = None
         return self
 
     def __del__(self):
@@ -153,6 +173,7 @@ class _PackedSplit:
                 ev.synchronize()
             except Exception:
                 pass
+        self._keep = None
 
     def wait_ready(self):
         """Join the side stream that produced this split (pack_session_from_frames) before the first read."""
@@ -160,6 +181,10 @@ class _PackedSplit:
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
             self.ready = None
+            # main-stream tensors the side-stream kernels read (frame indices, z-score statistics): the caching allocator
+            # may hand their blocks to the next main-stream allocation the moment they die, so they live exactly until
+            # the main stream is ordered behind the side stream
+            self._keep = None
 
     def check_range(self):
         """Half-precision operands: fail loudly if a value left the half range while packing (checked once, lazily,
@@ -187,9 +212,16 @@ class RRRGD():
         self.l2 = l2
         self.eids = list(train_data.keys())
         self.withbias = True
-        self.planes = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
+        # host (float64 numpy) splits are packed into this many residual planes; the default 3 keeps the whole fit within
+        # 1e-3 of the float64 reference (1 = fastest, ~2e-3 away; device-packed splits carry their own layout)
+        self.planes = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "3"))
         self.engine = int(engine if engine is not None else os.environ.get("VS_ENGINE", str(vs.ENGINE_AUTO)))
         self.fmt = operand_format(self.planes, operand)
+        # splits packed in the exact-operand mode (pack_session_from_frames) carry their own layout: two half planes
+        self.exact = any(isinstance(x, _PackedSplit) and x.dims.mode == vs.RRR_MODE_EXACT
+                         for e in train_data.values() for x in e["X"])
+        if self.exact:
+            self.planes, self.fmt = 2, vs.OPERAND_F16
 
         # rrr.py:35 seeds numpy's GLOBAL legacy stream with 0 regardless of the user's seed and draws
         # U then V per session from it.  The same stream -- bit for bit -- comes from the multi-threaded host
@@ -328,6 +360,13 @@ class RRRGD():
         if want_grad:
             dU, db = self._grad_buffer(U), self._grad_buffer(b)
         ws = self._workspace(sp.dims)
+        if sp.dims.mode == vs.RRR_MODE_EXACT:
+            ex = sp.exact
+            vs.check(vs.lib.vs_rrr_closure_exact(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(ex["isdT"]), vs.ptr(ex["qT"]), ex["ldt"],
+                                                 vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(ex.get("y_lo")), vs.ptr(U.data), vs.ptr(V.data),
+                                                 vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU), vs.ptr(dV),
+                                                 vs.ptr(db), vs.ptr(ws), ws.numel(), vs.stream()))
+            return loss[0], sse, dU, db
         vs.check(vs.lib.vs_rrr_closure(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
                                        vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
                                        vs.ptr(dV), vs.ptr(db), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
@@ -435,13 +474,21 @@ def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None
 # ------------------------------------------------------------------------------------------------
 # R0 on the device: the preprocessing of src/train_rrr.py:108-171 for the video modalities, from raw
 # uint8 frames, without ever forming the float64 (K, T, C) matrix on the host.
-def pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=1,
-                             smooth_w=2.0, device=None, operand=None):
+def pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=None,
+                             smooth_w=2.0, device=None, operand=None, mode=None):
     """frames_*: uint8 (K, Tf, ...) torch tensors (pinned host or CUDA); counts_*: (K, T, N) spike counts.
     Mirrors train_rrr.py: y smoothed with gaussian_filter1d(sigma=smooth_w, axis=1); X and y z-scored with
     the TRAIN statistics (std clipped at 1e-8); ones column; frames `sorted_idx` selected AFTER the z-score.
-    Returns the per-session entry of the `train_data` dict RRRGD consumes, with device-resident splits."""
+    Returns the per-session entry of the `train_data` dict RRRGD consumes, with device-resident splits.
+    `mode` (see rrr_mode): "exact" unless `planes` is given (then "classic" with that many planes)."""
     vs.require_b200()
+    if mode is None:
+        mode = "classic" if planes is not None else rrr_mode(None)
+    exact = rrr_mode(mode) == "exact"
+    if exact:
+        planes, operand = 2, "f16"
+    elif planes is None:
+        planes = int(os.environ.get("VS_RRR_PLANES", "1"))
     device = device or torch.device("cuda")
     st = vs.stream()
     idx_np = np.ascontiguousarray(np.asarray(sorted_idx), dtype=np.int32)
@@ -462,9 +509,21 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
         K, Tf = int(fr.shape[0]), int(fr.shape[1])
         F = int(fr[0, 0].numel())
         N = int(cnt.shape[2])
-        d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T), fmt)
+        d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T), fmt,
+                       vs.RRR_MODE_EXACT if exact else vs.RRR_MODE_CLASSIC)
         Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)          # allocated on the main stream
-        Xb = torch.empty((planes, F, d.ldr), dtype=_op_dtype(fmt), device=device)
+        ex = None
+        if exact:
+            # backward operand: ONE plane of exact integers, train split only (the other splits are only evaluated);
+            # the scale tables come from the train statistics and are shared by every split of the session
+            Xb = torch.empty((F, d.ldr), dtype=_op_dtype(fmt), device=device) if which == 0 else None
+            ldt = int(vs.lib.vs_rrr_ldt(T))
+            if which == 0:
+                isdT = torch.empty((F, ldt), dtype=torch.float32, device=device)
+                qT = torch.empty((F, ldt), dtype=torch.float32, device=device)
+            ex = {"isdT": isdT, "qT": qT, "ldt": ldt, "y_lo": torch.empty((K, T, N), dtype=torch.float32, device=device)}
+        else:
+            Xb = torch.empty((planes, F, d.ldr), dtype=_op_dtype(fmt), device=device)
         xl = torch.empty(K * T, dtype=torch.float32, device=device)
         y = torch.empty((K, T, N), dtype=torch.float32, device=device)
         overflow = torch.zeros(1, dtype=torch.int32, device=device)
@@ -498,16 +557,24 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                 sy = torch.empty_like(my)
                 vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
                 del sm
-            vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
-                                           vs.ptr(xl), vs.ptr(overflow), st))
-            vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
-            sp = _PackedSplit.from_device(d, Xa, Xb, xl, y, overflow)
+            if exact:
+                vs.check(vs.lib.vs_rrr_pack_u8_exact(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa),
+                                                     vs.ptr(Xb), vs.ptr(xl), vs.ptr(isdT) if which == 0 else None,
+                                                     vs.ptr(qT) if which == 0 else None, vs.ptr(overflow), st))
+                vs.check(vs.lib.vs_rrr_smooth_y2(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y),
+                                                 vs.ptr(ex["y_lo"]), st))
+            else:
+                vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
+                                               vs.ptr(xl), vs.ptr(overflow), st))
+                vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
+            sp = _PackedSplit.from_device(d, Xa, Xb, xl, y, overflow, exact=ex)
             if which == 1:
+                sp._keep = (idx, idx_compact, idx_dev, mean, sd, my, sy)
                 sp.ready = torch.cuda.Event()
                 sp.ready.record(side)
             del fr, cnt
         splits.append(sp)
-        ys.append(_LazyY(sp) if which == 1 else y)
+        ys.append(_LazyY(sp) if which == 1 else (y.double() + ex["y_lo"].double() if exact else y))
     if compact_stats:
         # API shape of the reference's `setup` (per frame of the trial window): statistics exist for the selected frames only
         Tf_all, F_all = int(frames_train.shape[1]), int(frames_train[0, 0].numel())
@@ -521,11 +588,10 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
 
 
 def train_model_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, l2=100.0, n_comp=3,
-                            eid="session", planes=None, engine=None, model_fname="tmp", save=False, operand=None):
-    """R0 + train_model_main (rrr.py:192-202) in one call, from raw uint8 frames."""
-    pl = int(planes if planes is not None else os.environ.get("VS_RRR_PLANES", "1"))
-    entry = pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=pl,
-                                     operand=operand)
+                            eid="session", planes=None, engine=None, model_fname="tmp", save=False, operand=None, mode=None):
+    """R0 + train_model_main (rrr.py:192-202) in one call, from raw uint8 frames (`mode`, `planes`: pack_session_from_frames)."""
+    entry = pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=planes,
+                                     operand=operand, mode=mode)
     train_data = {eid: entry}
-    model, mse_val = train_model_main(train_data, l2, n_comp, model_fname, save=save, planes=pl, engine=engine, operand=operand)
+    model, mse_val = train_model_main(train_data, l2, n_comp, model_fname, save=save, planes=planes, engine=engine, operand=operand)
     return model, mse_val, train_data

@@ -225,6 +225,7 @@ class FusedLBFGS(torch.optim.Optimizer):
         self._scal = torch.zeros(8 + 6 * m + 8, dtype=torch.float64, device=dev)      # dots out | dmax | loss
         self._alloc_workspace(n, m, dev)
         self._pairs, self._hist, self._free = [], None, []
+        self._dev = None               # the device-resident state (slot tables, history window) belonged to the old storage
         self._new_gram()
         self.state[ps[0]].clear()
         return fl
@@ -353,6 +354,12 @@ class FusedLBFGS(torch.optim.Optimizer):
     def _reduce_dev_scalars(self):
         """Hook (parallel.ShardedLBFGS): combine the state's `out` block and `dmax` across ranks on the device."""
 
+    def _dev_dots(self, sp, n, g, g_prev, hist, f32, dev):
+        """vs_lbfgs_dev_dots over the whole flat vector (parallel.ShardedLBFGS restricts the inner products of the
+        replicated prefix to rank 0)."""
+        vs.check(vs.lib.vs_lbfgs_dev_dots(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), hist.shape[1], f32, vs.ptr(dev["ws"]),
+                                          dev["ws"].numel(), vs.stream()))
+
     @torch.no_grad()
     def _step_device_driven(self, closure):
         closure = torch.enable_grad()(closure)
@@ -378,8 +385,7 @@ class FusedLBFGS(torch.optim.Optimizer):
             g = fl["g"][fl["cur"]]
             g_prev = fl["g"][1 - fl["cur"]]
             lt = torch.as_tensor(loss_t).detach().reshape(1).double()
-            vs.check(vs.lib.vs_lbfgs_dev_dots(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), hist.shape[1], f32, vs.ptr(dev["ws"]),
-                                              dev["ws"].numel(), st()))
+            self._dev_dots(sp, n, g, g_prev, hist, f32, dev)
             self._reduce_dev_scalars()
             vs.check(vs.lib.vs_lbfgs_dev_update(sp, vs.ptr(lt), lr, tol_g, tol_c, int(max_eval), int(hsize), int(it == 0), st()))
             vs.check(vs.lib.vs_lbfgs_dev_direction(sp, n, vs.ptr(g), vs.ptr(hist), hist.shape[1], f32, vs.ptr(fl["x"]), st()))

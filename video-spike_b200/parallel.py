@@ -51,12 +51,48 @@ class ShardedLBFGS(FusedLBFGS):
 
     def __init__(self, shared, local, group=None, **kw):
         shared, local = list(shared), list(local)
-        if kw.get("device_driven"):
-            raise vs.VsError("ShardedLBFGS is host-driven (its inner products are all-reduced between the two passes)")
         super().__init__(shared + local, **kw)                 # shared block first in the flat vector
         self._n_shared = sum(p.numel() for p in shared)
         self._group = group
         self._rank, self._world = world()
+        self._gather = None
+
+    # ---- device-driven mode: the collectives are stream-ordered (NCCL), so the whole step is still enqueued without a
+    #      host read: dots (local shard) -> ONE all-gather of every rank's scalar block -> ordered combine -> update -> direction
+    def _dev_dots(self, sp, n, g, g_prev, hist, f32, dev):
+        ns = self._n_shared
+        lib, st = vs.lib, vs.stream()
+        wsp, wsn, stride = vs.ptr(dev["ws"]), dev["ws"].numel(), hist.shape[1]
+        if self._rank == 0 or self._world == 1 or ns == 0:
+            vs.check(lib.vs_lbfgs_dev_dots(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), stride, f32, wsp, wsn, st))
+            return
+        # rank != 0: the replicated prefix still gets its y = g - g_prev written (the history must be complete on every
+        # rank), but its inner products are rank 0's to count: that pass's scalars are overwritten by the local pass
+        esz = 4 if f32 else 8
+        vs.check(lib.vs_lbfgs_dev_dots(sp, ns, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), stride, f32, wsp, wsn, st))
+        if n > ns:
+            vs.check(lib.vs_lbfgs_dev_dots(sp, n - ns, g.data_ptr() + 8 * ns, g_prev.data_ptr() + 8 * ns, hist.data_ptr() + esz * ns,
+                                           stride, f32, wsp, wsn, st))
+        else:
+            dev["out"].zero_()
+
+    def _reduce_dev_scalars(self):
+        if self._world == 1:
+            return
+        dev = self._dev
+        out, dmax = dev["out"], dev["dmax"]
+        k = out.numel()
+        if self._gather is None or self._gather.device != out.device:
+            self._gather = torch.empty((self._world, k + 1), dtype=torch.float64, device=out.device)
+            self._mine = torch.empty(k + 1, dtype=torch.float64, device=out.device)
+        self._mine[:k].copy_(out)
+        self._mine[k:].copy_(dmax)
+        dist.all_gather_into_tensor(self._gather.view(-1), self._mine, group=self._group)
+        # sums in rank order (bit-identical on every rank whatever the collective's internal order); |g|_inf and max|t*d| by max.
+        # entries past 8 + 6m hold stale values on every rank: they are never read
+        torch.sum(self._gather[:, :k], dim=0, out=out)
+        out[2:3].copy_(self._gather[:, 2].max().reshape(1))
+        dmax.copy_(self._gather[:, k].max().reshape(1))
 
     def _dots(self, g, g_prev, s_slot, y_slot, loss_t):
         k = 8 + 6 * len(self._pairs)
@@ -102,14 +138,17 @@ def joint_loss_and_grad(model, data, k=0, group=None):
     return loss
 
 
-def train_joint_model(model, train_data_local, model_fname="tmp", save=False, group=None, history_dtype=None):
+def train_joint_model(model, train_data_local, model_fname="tmp", save=False, group=None, history_dtype=None, device_driven=None):
     """`train_model` (rrr.py:164-190) for the sharded joint model: one ShardedLBFGS.step over all ranks' sessions,
     validation SSE summed over ranks.  Returns (model, {"mses_val": local dict, "mse_val_mean": global})."""
     shared = [model.model["V"]]
     local = [p for k_, p in model.model.items() if k_ != "V"]
     if history_dtype is None:
         history_dtype = torch.float32 if model.planes == 1 else torch.float64
-    optimizer = ShardedLBFGS(shared, local, group=group, history_dtype=history_dtype)
+    if device_driven is None:
+        device_driven = os.environ.get("VS_LBFGS_DEVICE", "1") != "0" and model.model["V"].is_cuda
+    optimizer = ShardedLBFGS(shared, local, group=group, history_dtype=history_dtype, device_driven=device_driven)
+    optimizer.closure_overwrites_grads = True
 
     def closure():
         optimizer.zero_grad()

@@ -121,7 +121,9 @@ def main(argv=None):
     if not device_r0:
         train_data = preprocess_host(train_data, my_eids, args.input_mod, sorted_idx)
     l2, n_comp = 100, 3
-    planes = int(os.environ.get("VS_RRR_PLANES", "1"))            # 1 = plain bf16 operands (BASELINE config), 3 = parity mode
+    # operand precision: None = the parity defaults (exact-operand mode for uint8 frames, 3 planes for float64 arrays);
+    # VS_RRR_PLANES=1 selects the fastest, non-parity setting (DESIGN.md "RRR precision")
+    planes = int(os.environ["VS_RRR_PLANES"]) if os.environ.get("VS_RRR_PLANES") else None
     print('start training')
     result, test_bps = {}, []
     for eid in my_eids:
@@ -130,8 +132,8 @@ def main(argv=None):
             entry = pack_session_from_frames(torch.from_numpy(d["X"][0]), d["y"][0], torch.from_numpy(d["X"][1]), d["y"][1],
                                              sorted_idx, n_comp, planes=planes, smooth_w=2.0)
             train_data[eid] = entry
-        model, mse_val = train_model_main(train_data={eid: train_data[eid]}, l2=l2, n_comp=n_comp, model_fname='tmp', save=True,
-                                          planes=planes)
+        model, mse_val = train_model_main(train_data={eid: train_data[eid]}, l2=l2, n_comp=n_comp, save=True, planes=planes,
+                                          model_fname='tmp' if world == 1 else f'tmp.rank{rank}')   # one writer per file
         print('finished training')
         print('eid:', eid)
         _, _, pred_orig = model.predict_y_fr(train_data, eid, 1)

@@ -67,11 +67,30 @@ class BaseTrainer():
         if self._use_wandb():
             wandb.init(project=self.config.wandb.project, name="{}_{}_{}".format(self.eid[:5], mods, name), config=self.config)
 
+    def _unwrapped(self):
+        """(model, optimizer) without the wrappers `accelerator.prepare` may add (DDP / AcceleratedOptimizer)."""
+        model = self.model
+        unwrap = getattr(self.accelerator, "unwrap_model", None)
+        if unwrap is not None:
+            model = unwrap(model)
+        model = getattr(model, "module", model)
+        return model, getattr(self.optimizer, "optimizer", self.optimizer)
+
+    def _is_main(self):
+        return bool(getattr(self.accelerator, "is_main_process", True))
+
     def _fused_route(self):
         from model.linear import Linear
         from optim import FusedAdamW
         c = self.criterion
-        return (isinstance(self.model, Linear) and isinstance(self.optimizer, FusedAdamW)
+        model, optimizer = self._unwrapped()
+        if model is not self.model:
+            # a wrapped (DDP) model synchronises gradients through autograd hooks: the fused step and the factored
+            # first-layer gradient bypass them, so a wrapped model always takes the generic route with plain gradients
+            for p in model.parameters():
+                p._vs_defer_ok = False
+            return False
+        return (isinstance(model, Linear) and isinstance(optimizer, FusedAdamW)
                 and isinstance(c, torch.nn.PoissonNLLLoss) and c.log_input and c.reduction == "none" and not c.full)
 
     # ------------------------------------------------------------------ forward / loss
@@ -98,7 +117,7 @@ class BaseTrainer():
         for batch in tqdm(self.train_dataloader):
             if fused:
                 inputs = self._gather_inputs(batch)
-                loss = self.model.fused_train_step(inputs, batch['ap'], self.optimizer)
+                loss = self.model.fused_train_step(inputs, batch['ap'], self._unwrapped()[1])
                 self.lr_scheduler.step()
                 losses.append(loss)               # device scalar: no host sync inside the loop
             else:
@@ -172,11 +191,16 @@ class BaseTrainer():
 
     @torch.no_grad()
     def test_model(self):
-        # the best checkpoint is a pickled module (base.py:212)
+        # the best checkpoint is a pickled module (base.py:212); rank 0 wrote it
+        wait = getattr(self.accelerator, "wait_for_everyone", None)
+        if wait is not None:
+            wait()
         self.model = torch.load(os.path.join(self.log_dir, "model_best.pt"), weights_only=False)['model']
         self.model.eval()
         return self._run_split(self.test_dataloader, self.dataset_split_dict['eid']['test'], "test")
 
     def save_model(self, name="last", epoch=0):
+        if not self._is_main():        # every rank trains the same replica (the reference never shards its loaders): one writer
+            return
         print(f"saving model: {name} to {self.log_dir}")
-        torch.save({"model": self.model, "epoch": epoch}, os.path.join(self.log_dir, f"model_{name}.pt"))
+        torch.save({"model": self._unwrapped()[0], "epoch": epoch}, os.path.join(self.log_dir, f"model_{name}.pt"))

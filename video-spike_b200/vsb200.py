@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvs_b200.so")
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 OPERAND_BF16, OPERAND_F16 = 0, 1
+RRR_MODE_CLASSIC, RRR_MODE_EXACT = 0, 1
 MAX_LAYERS = 16
 
 
@@ -54,7 +55,7 @@ class LbfgsDev(C.Structure):
 
 class RrrDims(C.Structure):
     _fields_ = [("K", C.c_int64), ("T", C.c_int64), ("C1", C.c_int64), ("N", C.c_int64), ("r", C.c_int64),
-                ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64), ("fmt", C.c_int32)]
+                ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64), ("fmt", C.c_int32), ("mode", C.c_int32)]
 
 
 def _load():
@@ -91,6 +92,10 @@ def _load():
         "vs_rrr_colstats": (C.c_int, [vp, i64, i64, vp, vp, vp]),
         "vs_rrr_pack_u8": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, vp, vp, vp, vp]),
         "vs_rrr_smooth_y": (C.c_int, [vp, i64, i64, i64, dbl, vp, vp, vp, vp]),
+        "vs_rrr_smooth_y2": (C.c_int, [vp, i64, i64, i64, dbl, vp, vp, vp, vp, vp]),
+        "vs_rrr_ldt": (i64, [i64]),
+        "vs_rrr_pack_u8_exact": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, vp, vp, vp, vp, vp, vp]),
+        "vs_rrr_closure_exact": (C.c_int, [RrrDims, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, sz, vp]),
         "vs_colstats_f32": (C.c_int, [vp, i64, i64, vp, vp, vp]),
         "vs_rrr_workspace": (sz, [RrrDims]),
         "vs_rrr_closure": (C.c_int, [RrrDims, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
