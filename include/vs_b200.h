@@ -264,6 +264,8 @@ int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const 
  * product has one exact or two-plane operand on each side.  y_lo (may be NULL): y + y_lo is the target at float64
  * precision.  All epilogue sums are float64.                                                             */
 int64_t vs_rrr_ldt(int64_t T);
+/* 1 if the exact-operand closure covers the shape (rank 3, N <= 160 after padding to 16, more than 128 features) */
+int vs_rrr_exact_supported(int64_t K, int64_t T, int64_t C1, int64_t N, int64_t r);
 int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
                          const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xi, float* xl, float* isdT,
                          float* qT, int32_t* overflow_flag, void* stream);

@@ -612,7 +612,7 @@ def test_rrr_exact_mode_closure_vs_oracle(vs, cuda):
         m.loss_and_grad(td, 1)
 
 
-@pytest.mark.parametrize("K,F,N", [(40, 96, 10), (37, 200, 33), (70, 130, 144)])
+@pytest.mark.parametrize("K,F,N", [(40, 160, 10), (37, 200, 33), (70, 130, 144)])
 def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N):
     """Exact-operand mode on shapes that do not fill tiles (K not a multiple of 16, F not of 128, N not of 16)."""
     from model.rrr import RRRGD, pack_session_from_frames
@@ -639,7 +639,7 @@ def test_rrr_exact_mode_whole_fit_small_vs_oracle(vs, cuda):
     """train_model_from_frames in its default (exact) mode against the oracle's float64 fit of the same raw arrays:
     validation SSE, de-z-scored predictions, co-bps and R2 (src/train_rrr.py:193-236)."""
     from model.rrr import train_model_from_frames
-    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=0, K=40, Kt=12, F=96, N=10, raw=True)
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=0, K=40, Kt=12, F=160, N=10, raw=True)
     data, gt = ro.preprocess_session([Xtr, Xte], [ytr, yte], sidx)
     td_o = {"session": data}
     p_o, mse_o, _ = ro.train_model_main(td_o, 100.0, 3)

@@ -1,67 +1,48 @@
 """Full-size RRR fit (BASELINE configs[1]) in every operand mode against an independent float64 dense implementation
-(torch einsum + autograd + torch.optim.LBFGS on the GPU in fp64, i.e. the reference's own formulation)."""
+(bench.fp64_dense_reference: torch einsum + autograd + torch.optim.LBFGS on the GPU in fp64, the reference's own formulation).
+MODES=exact,exact32,p3,p2,p1f16,p1  selects what runs (default: all)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "video-spike_b200"), ROOT]
 import numpy as np, torch
-from scipy.ndimage import gaussian_filter1d
 import bench
-from model.rrr import RRRGD, pack_session_from_frames, train_model
-from optim import FusedLBFGS
+from model.rrr import RRRGD, pack_session_from_frames
 
 dev = torch.device("cuda")
 K, Kt, F, N = int(os.environ.get("K", 400)), 80, 110 * 166, 144
-ftr, ctr, fte, cte = bench.rrr_inputs(K, Kt, F, N, 0, pinned=False, signal=os.environ.get("SIGNAL", "1") == "1")
+seed = int(os.environ.get("SEED", 0))
+ftr, ctr, fte, cte = bench.rrr_inputs(K, Kt, F, N, seed, pinned=False, signal=os.environ.get("SIGNAL", "0") == "1")
 sidx = bench.sorted_idx_42()
-
-# ---- float64 dense reference on the GPU (formulation of src/model/rrr.py:79-155, preprocessing of train_rrr.py:108-171)
-def prep(fr, mean=None, std=None):
-    X = fr.to(dev).double()
-    if mean is None:
-        mean = X.mean(0); std = X.std(0, unbiased=False).clamp_min(1e-8)
-    X = (X - mean) / std
-    X = torch.cat([X, torch.ones(X.shape[0], X.shape[1], 1, dtype=torch.float64, device=dev)], 2)
-    return X[:, torch.as_tensor(sidx, device=dev)], mean, std
-Xtr, mX, sX = prep(ftr); Xte, _, _ = prep(fte, mX, sX)
-ytr = gaussian_filter1d(ctr.numpy().astype(np.float64), 2, axis=1); yte = gaussian_filter1d(cte.numpy().astype(np.float64), 2, axis=1)
-my, sy = ytr.mean(0), np.clip(ytr.std(0), 1e-8, None)
-ytr = torch.from_numpy((ytr - my) / sy).to(dev); yte = torch.from_numpy((yte - my) / sy).to(dev)
-np.random.seed(0)
-U0 = np.random.normal(size=(N, F, 3)) / np.sqrt(300); V0 = np.random.normal(size=(3, 100)) / np.sqrt(300)
-U = torch.nn.Parameter(torch.from_numpy(U0).to(dev)); V = torch.nn.Parameter(torch.from_numpy(V0).to(dev))
-b = torch.nn.Parameter(ytr.mean(0).T.unsqueeze(1).contiguous())
-opt = torch.optim.LBFGS([U, b, V])
-trace = []
-def closure():
-    opt.zero_grad()
-    beta = torch.cat([U @ V, b], 1)                                   # (N, C, T)
-    pred = torch.einsum("ktc,nct->ktn", Xtr, beta)
-    loss = ((pred - ytr) ** 2).sum() + 100.0 * (beta ** 2).sum()
-    loss.backward(); trace.append(float(loss.detach())); return loss
-t0 = time.time(); opt.step(closure); torch.cuda.synchronize()
-with torch.no_grad():
-    beta = torch.cat([U @ V, b], 1)
-    ref_val = float(((torch.einsum("ktc,nct->ktn", Xte, beta) - yte) ** 2).sum())
-print(f"fp64 dense reference: val SSE {ref_val:.6f}  evals {len(trace)}  ({time.time()-t0:.1f} s)  first/last train loss {trace[0]:.6e} {trace[-1]:.6e}")
-del Xtr, Xte, beta
-torch.cuda.empty_cache()
-MODES = ((3, "bf16", torch.float64), (2, "bf16", torch.float64), (1, "f16", torch.float64), (1, "f16", torch.float32),
-         (1, "bf16", torch.float64), (1, "bf16", torch.float32))
-if os.environ.get("FAST_ONLY"):
-    MODES = ((1, "f16", torch.float32), (1, "bf16", torch.float32))
-for planes, operand, hd in MODES:
-    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, operand=operand)
+t0 = time.time()
+ref = bench.fp64_dense_reference(ftr, ctr, fte, cte, sidx, dev)
+ref_val = ref["val_sse"]
+print(f"fp64 dense reference (seed {seed}): val SSE {ref_val:.6f}  evals {ref['evals']}  ({time.time()-t0:.1f} s)  first/last train loss "
+      f"{ref['first_loss']:.6e} {ref['last_loss']:.6e}", flush=True)
+ALL = {"exact": ("exact", None, None, torch.float64), "exact32": ("exact", None, None, torch.float32),
+       "p3": ("classic", 3, "bf16", torch.float64), "p2": ("classic", 2, "bf16", torch.float64),
+       "p2f16": ("classic", 2, "f16", torch.float64),
+       "p1f16": ("classic", 1, "f16", torch.float32), "p1": ("classic", 1, "bf16", torch.float32)}
+names = (os.environ.get("MODES") or ",".join(ALL)).split(",")
+for nm in names:
+    mode, planes, operand, hd = ALL[nm]
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, operand=operand, mode=mode)
     td = {"s": entry}
     m = RRRGD(td, 3, l2=100.0, planes=planes, operand=operand); m.to(dev)
+    # per-evaluation error at the perturbed start of the reference
+    with torch.no_grad():
+        m.model["s_U"].copy_(ref["start"]["U"]); m.model["s_b"].copy_(ref["start"]["b"]); m.model["V"].copy_(ref["start"]["V"])
+    l1 = float(m.loss_and_grad(td, 0)); lref, gref = ref["probe"]
+    ge = {k: float((m.model[n_].grad - gref[k]).norm() / gref[k].norm()) for k, n_ in (("U", "s_U"), ("b", "s_b"), ("V", "V"))}
+    m2 = RRRGD(td, 3, l2=100.0, planes=planes, operand=operand); m2.to(dev)
     losses = []
-    o = m.make_optimizer(history_dtype=hd)
+    o = m2.make_optimizer(history_dtype=hd)
     def cl():
-        o.zero_grad(); l = m.loss_and_grad(td, 0); losses.append(float(l)); return l
+        o.zero_grad(); l = m2.loss_and_grad(td, 0); losses.append(l); return l
     torch.cuda.synchronize(); t1 = time.perf_counter()
     o.step(cl)
-    val = float(torch.sum(m.compute_MSE_RRRGD(td, 1)["s"]))
+    val = float(torch.sum(m2.compute_MSE_RRRGD(td, 1)["s"]))
     fit_ms = (time.perf_counter() - t1) * 1e3
-    dev_tr = max(abs(a - r) / abs(r) for a, r in zip(losses, trace))
-    print(f"planes={planes} {operand:4s} hist={str(hd)[6:]:8s} val SSE {val:.4f} rel diff {abs(val-ref_val)/ref_val:.3e} | first-eval loss rel diff {abs(losses[0]-trace[0])/trace[0]:.3e} max over evals {dev_tr:.3e} | fit {fit_ms:.1f} ms  VS_RRR_RUN={os.environ.get('VS_RRR_RUN')}")
-    del m, td, entry, o
+    print(f"{nm:8s} hist={str(hd)[6:]:8s} val SSE {val:.4f} rel diff {abs(val-ref_val)/ref_val:.3e} | per-eval loss rel {abs(l1-lref)/abs(lref):.2e} "
+          f"grad rel-L2 U {ge['U']:.2e} b {ge['b']:.2e} V {ge['V']:.2e} | fit {fit_ms:.1f} ms", flush=True)
+    del m, m2, td, entry, o
     torch.cuda.empty_cache()

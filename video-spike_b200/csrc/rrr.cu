@@ -18,6 +18,7 @@ namespace vs {
 namespace rrr {
 
 constexpr int kMaxR = 8;
+constexpr double kExactUScale = 256.0;   // exact-operand mode: U planes are stored as 256 * U (see closure_impl)
 
 // 16-bit operand encodings (vs_rrr_dims.fmt): bf16 or IEEE half, round to nearest even
 __device__ __forceinline__ uint16_t enc16(float v, int fmt) {
@@ -383,7 +384,7 @@ constexpr int kPrepC = 4;
 template <int RMAX>
 __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ U, long long N, long long Npad, long long C1,
                                                      int r, int planes, int fmt, long long ldc, uint16_t* __restrict__ Ub,
-                                                     double* __restrict__ Gp) {
+                                                     double* __restrict__ Gp, double uscale) {
   __shared__ double red[8][RMAX * RMAX];
   const long long n = blockIdx.y;
   const long long c0 = ((long long)blockIdx.x * 256 + threadIdx.x) * kPrepC;
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
     for (int j = 0; j < RMAX; ++j) {
       if (j >= r) break;
       uint16_t pl[3];
-      split_planes(u[j], planes, fmt, pl);
+      split_planes(u[j] * uscale, planes, fmt, pl);        // uscale: a power of two (exact), undone by the epilogue of GEMM-F
       for (int p = 0; p < planes; ++p) Ub[p * pu + ((long long)j * Npad + n) * ldc + c] = pl[p];
     }
     if (Gp) {
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
                                                     long long T, long long N, long long Npad, int r, int planes, int fmt, long long ldr,
                                                     uint16_t* __restrict__ RV, AT* __restrict__ sse_part,
                                                     AT* __restrict__ db_part, AT* __restrict__ pv_part,
-                                                    double* __restrict__ yhat, long long Kp, int dense) {
+                                                    double* __restrict__ yhat, long long Kp, int dense, double zscale) {
   __shared__ AT Rs[kEpiRows][33];
   __shared__ AT red[8][32][2];
   __shared__ float xls[kEpiRows];
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
   const long long k0 = kb * kEpiRows, d0 = t * K + k0, n0 = nt * 32;
   AT vt[RMAX];
 #pragma unroll
-  for (int j = 0; j < RMAX; ++j) vt[j] = j < r ? (AT)V[(long long)j * T + t] : (AT)0;
+  for (int j = 0; j < RMAX; ++j) vt[j] = j < r ? (AT)(V[(long long)j * T + t] * zscale) : (AT)0;     // Z = zscale^-1 * X U (see prep_u_kernel)
   if (threadIdx.x < kEpiRows) xls[threadIdx.x] = (k0 + threadIdx.x < K) ? xl[d0 + threadIdx.x] : 0.f;
   __syncthreads();
   AT pvacc[RMAX];
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
     if (threadIdx.x < r) {
       AT sj = (AT)0;
       for (int w2 = 0; w2 < 8; ++w2) sj += pvs[w2][threadIdx.x];
-      pv_part[((t * KB + kb) * NT + nt) * r + threadIdx.x] = sj;
+      pv_part[((t * KB + kb) * NT + nt) * r + threadIdx.x] = sj * (AT)zscale;
     }
   }
 }
@@ -1035,12 +1036,15 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
   const Ws w = carve(d, workspace);
   const long long KT = d.K * d.T;
   const int r = (int)d.r;
+  // half planes: U ~ 1/sqrt(T r) would put its lo plane (2^-11 of the value) into the half subnormals; a power-of-two
+  // scale keeps both planes normal and is undone exactly in the epilogue
+  const double uscale = exact ? kExactUScale : 1.0;
   // stage 0: U planes + Gram partials, then G and W = V V^T
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
   if (r <= 4) {
-    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp);
+    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale);
   } else {
-    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp);
+    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale);
   }
   VS_LAUNCH(small_mats_kernel, r * r + 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   // stage 1: Z
@@ -1060,7 +1064,7 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
 #define VS_EPI_F(RM, AT) VS_LAUNCH((epi_f_kernel<false, RM, AT>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, ex.y_lo, xl, V, b,       \
                                    (long long)d.K, (long long)d.T, (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV,   \
-                                   (AT*)w.sse_part, (AT*)w.db_part, (AT*)w.pv_part, nullptr, w.Kp, dense ? 1 : 0)
+                                   (AT*)w.sse_part, (AT*)w.db_part, (AT*)w.pv_part, nullptr, w.Kp, dense ? 1 : 0, 1.0 / uscale)
   if (exact) { if (r <= 4) { VS_EPI_F(4, double); } else { VS_EPI_F(kMaxR, double); } }
   else { if (r <= 4) { VS_EPI_F(4, float); } else { VS_EPI_F(kMaxR, float); } }
 #undef VS_EPI_F
@@ -1113,6 +1117,13 @@ extern "C" int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const uin
 
 extern "C" int64_t vs_rrr_ldt(int64_t T) { return round_up(T, 4); }
 
+// shapes the exact-operand closure covers (its backward is the tcgen05 dense per-time-bin kernel); callers fall back to
+// the classic mode with 3 residual planes elsewhere
+extern "C" int vs_rrr_exact_supported(int64_t K, int64_t T, int64_t C1, int64_t N, int64_t r) {
+  const long long Npad = round_up(N, 16);
+  return (r == 3 && Npad <= 160 && C1 > 128 && K > 0 && T > 0 && T * round_up(K, 16) + 64 < (1ll << 31)) ? 1 : 0;
+}
+
 extern "C" int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
                                     const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xi, float* xl, float* isdT,
                                     float* qT, int32_t* overflow_flag, void* stream) {
@@ -1148,12 +1159,13 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   const Ws w = carve(d, workspace);
   const long long KT = d.K * d.T;
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
+  const double uscale = d.mode == VS_RRR_MODE_EXACT ? kExactUScale : 1.0;
   if (d.r <= 4) {
     VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
-              (double*)nullptr);
+              (double*)nullptr, uscale);
   } else {
     VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
-              (double*)nullptr);
+              (double*)nullptr, uscale);
   }
   int sf = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);
@@ -1161,10 +1173,10 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   if (d.r <= 4) {
     VS_LAUNCH((epi_f_kernel<true, 4, float>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, yhat, 0ll, 0);
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, yhat, 0ll, 0, 1.0 / uscale);
   } else {
     VS_LAUNCH((epi_f_kernel<true, kMaxR, float>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, nullptr, nullptr, xl, V, b, (long long)d.K, (long long)d.T,
-              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, yhat, 0ll, 0);
+              (long long)d.N, w.Npad, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldr, nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, yhat, 0ll, 0, 1.0 / uscale);
   }
   return VS_OK;
 }

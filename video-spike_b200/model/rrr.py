@@ -486,6 +486,12 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
         mode = "classic" if planes is not None else rrr_mode(None)
     exact = rrr_mode(mode) == "exact"
     if exact:
+        # shapes outside the exact-operand kernels (rank != 3, more than 160 neurons, <= 128 features): the parity mode is
+        # then the classic layout with 3 residual planes
+        Kq, Fq, Nq = int(frames_train.shape[0]), int(frames_train[0, 0].numel()), int(counts_train.shape[2])
+        if not vs.lib.vs_rrr_exact_supported(Kq, len(np.asarray(sorted_idx)), Fq, Nq, n_comp):
+            exact, planes = False, 3
+    if exact:
         planes, operand = 2, "f16"
     elif planes is None:
         planes = int(os.environ.get("VS_RRR_PLANES", "1"))
