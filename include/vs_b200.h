@@ -196,8 +196,10 @@ enum {
 };
 enum {
   VS_RRR_MODE_CLASSIC = 0, /* Xa and Xb both hold the z-scored matrix in `planes` residual planes */
-  VS_RRR_MODE_EXACT = 1    /* uint8 frames only: Xa = z-score as hi + lo half planes, the backward operand holds the EXACT
-                              integers frame - round(mean); see vs_rrr_pack_u8_exact / vs_rrr_closure_exact */
+  VS_RRR_MODE_EXACT = 1,   /* uint8 frames only: Xa = z-score as hi + lo half planes (factorised forward), the backward operand
+                              holds the EXACT integers frame - round(mean); see vs_rrr_pack_u8_exact / vs_rrr_closure_exact */
+  VS_RRR_MODE_DENSE = 2    /* uint8 frames only: BOTH contractions use the exact integers, one time bin at a time, like the
+                              reference's einsum (no factorised product Z = X U): forward coefficient tiles generated on chip */
 };
 typedef struct {
   int64_t K, T, C1, N, r; /* trials, time bins, features without the bias column, neurons, rank */
@@ -251,28 +253,42 @@ int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const 
                    double* loss, double* sse_n, double* dU, double* dV, double* db, int engine,
                    void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- exact-operand mode (VS_RRR_MODE_EXACT; d.planes = 2, d.fmt = VS_OPERAND_F16): the mode whose WHOLE FIT lands within
- * 1e-3 of the float64 reference (the reference trains with one un-line-searched LBFGS.step, src/model/rrr.py:177,199,
- * which amplifies operand rounding by 3-4 orders of magnitude: DESIGN.md "RRR precision").  For uint8 frames
- * (src/train_rrr.py:143-165):
- *   Xa   : 2 x (K*T) x ldc half -- z = (frame - mean)/std as hi + lo planes (22 significant bits)   forward A operand
- *   Xi   : C1 x ldr half        -- the EXACT integers frame - round(mean), |.| <= 255, layout of Xb  backward A operand
- *                                  (NULL for splits that are only evaluated, e.g. the validation split)
- *   isdT : C1 x ldt fp32        -- 1/std[t,c]; the dense backward applies it to its rank-one weights
- *   qT   : C1 x ldt fp32        -- (mean - round(mean))[t,c]/std[t,c]; rank-T correction of the backward's result
- * with ldt = vs_rrr_ldt(T).  The residual goes to the backward as hi + lo half planes as well, so every tensor-core
- * product has one exact or two-plane operand on each side.  y_lo (may be NULL): y + y_lo is the target at float64
- * precision.  All epilogue sums are float64.                                                             */
+/* ---- exact-operand modes (VS_RRR_MODE_EXACT / VS_RRR_MODE_DENSE; d.planes = 2, d.fmt = VS_OPERAND_F16): the modes whose WHOLE
+ * FIT lands within 1e-3 of the float64 reference (the reference trains with one un-line-searched LBFGS.step,
+ * src/model/rrr.py:177,199, which amplifies operand rounding by 3-4 orders of magnitude: DESIGN.md "RRR precision").  For
+ * uint8 frames (src/train_rrr.py:143-165) frame - round(mean) is an INTEGER of magnitude <= 255, exact in IEEE half; the
+ * z-score scale 1/std[t,c] and the fractional part of the mean are applied around the tensor-core products, and the small
+ * operand of each product (coefficients, residuals) is split into hi + lo half planes.
+ *   EXACT: forward = factorised GEMM on Xa = z as hi + lo planes (3 plane products); backward on the integers Xi.
+ *   DENSE: forward AND backward on the integers, per time bin (the reference's own contraction: a third of the flops per
+ *          plane product); Xa is unused (NULL); dV comes from a second pass of the backward kernel over the same tiles.
+ * Operand table of one split (device pointers; `const` because the closure only reads them, vs_rrr_pack_u8_exact writes):  */
+typedef struct {
+  const uint16_t* Xi;   /* (C1, ldr) half: exact integers, layout of Xb (backward A operand); NULL for evaluation-only splits */
+  const float* isdT;    /* (C1, ldt) fp32: 1/std[t,c]                      (weights of the dense backward), ldt = vs_rrr_ldt(T) */
+  const float* qT;      /* (C1, ldt) fp32: (mean - round(mean))[t,c]/std   (rank-T correction of the backward's result)       */
+  int64_t ldt;
+  const float* y_lo;    /* (K,T,N) fp32 or NULL: y + y_lo is the target at float64 precision */
+  /* VS_RRR_MODE_DENSE only */
+  const uint16_t* Xc;   /* (K*T, ldc) half: exact integers, layout of Xa, row t*K + k (forward A operand) */
+  const float* isd;     /* (T, ldc) fp32: 1/std[t,c], 0 for features that are constant in the train split */
+  const uint16_t* qh;   /* (2, roundup(T,16), ldc) half: hi + lo planes of q[t,c] = (mean - round(mean))/std */
+  const float* isdmax;  /* (T) fp32: max_c isd[t,c] */
+} vs_rrr_exact_ops;
 int64_t vs_rrr_ldt(int64_t T);
-/* 1 if the exact-operand closure covers the shape (rank 3, N <= 160 after padding to 16, more than 128 features) */
+/* 1 if the exact-operand closures cover the shape (rank 3, N <= 160 after padding to 16, more than 128 features) */
 int vs_rrr_exact_supported(int64_t K, int64_t T, int64_t C1, int64_t N, int64_t r);
+/* fills Xa (EXACT) / out->Xc (DENSE), out->Xi and whichever tables of `out` are non-NULL */
 int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
-                         const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xi, float* xl, float* isdT,
-                         float* qT, int32_t* overflow_flag, void* stream);
-int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xi, const float* isdT, const float* qT,
-                         int64_t ldt, const float* xl, const float* y, const float* y_lo, const double* U,
-                         const double* V, const double* b, double l2, double* loss, double* sse_n, double* dU,
-                         double* dV, double* db, void* workspace, size_t workspace_bytes, void* stream);
+                         const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, const vs_rrr_exact_ops* out, float* xl,
+                         int32_t* overflow_flag, void* stream);
+/* vs_rrr_closure for an exact-operand split; all epilogue sums are float64 */
+int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const vs_rrr_exact_ops* ops, const float* xl, const float* y,
+                         const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,
+                         double* dU, double* dV, double* db, void* workspace, size_t workspace_bytes, void* stream);
+/* vs_rrr_predict for a VS_RRR_MODE_DENSE split (EXACT splits use vs_rrr_predict with their Xa) */
+int vs_rrr_predict_exact(vs_rrr_dims d, const vs_rrr_exact_ops* ops, const float* xl, const double* U, const double* V,
+                         const double* b, double* yhat, void* workspace, size_t workspace_bytes, void* stream);
 
 /* src/model/rrr.py:105-130 (predict_y): yhat (K,T,N) fp64 for one split. */
 int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl, const double* U, const double* V,

@@ -578,10 +578,13 @@ def test_linear_large_batch_step_vs_oracle(vs, cuda):
 
 
 # ----------------------------------------------------------------------------- exact-operand mode (the default for uint8 frames)
-def test_rrr_exact_mode_closure_vs_oracle(vs, cuda):
-    """vs_rrr_pack_u8_exact + vs_rrr_closure_exact: z-score as hi+lo half planes forward, exact integer frames x hi+lo
-    residual planes backward, float64 epilogues.  One closure evaluation at full feature width against the float64
-    oracle: loss to 1e-6, every gradient to 2e-5 of its largest entry (one bf16 plane reaches 1e-2 on this problem)."""
+@pytest.mark.parametrize("mode", ["exact", "dense"])
+def test_rrr_exact_mode_closure_vs_oracle(vs, cuda, mode):
+    """vs_rrr_pack_u8_exact + vs_rrr_closure_exact.  exact: z-score as hi+lo half planes forward (factorised GEMM), exact
+    integer frames x hi+lo residual planes backward.  dense: both contractions on the exact integers, one time bin at a
+    time (coefficient tiles generated on chip; dV from the second pass of the backward kernel).  float64 epilogues.
+    One closure evaluation at full feature width against the float64 oracle: loss to 1e-6, every gradient to 2e-5 of
+    its largest entry (one bf16 plane reaches 1e-2 on this problem)."""
     from model.rrr import RRRGD, pack_session_from_frames
     ftr, ctr, fte, cte, sidx = _full_size_session(24, 8)
     data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)], sidx)
@@ -591,8 +594,8 @@ def test_rrr_exact_mode_closure_vs_oracle(vs, cuda):
     for k in params:
         params[k] = params[k] + 0.02 * rng.standard_normal(params[k].shape)
     loss_o, g_o, sse_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
-    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, device=cuda, mode="exact")
-    assert entry["X"][0].dims.mode == vs.RRR_MODE_EXACT and entry["X"][1].Xb is None
+    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, device=cuda, mode=mode)
+    assert entry["X"][0].dims.mode == (vs.RRR_MODE_EXACT if mode == "exact" else vs.RRR_MODE_DENSE) and entry["X"][1].Xb is None
     td = {"s": entry}
     m = RRRGD(td, 3, l2=100.0); m.to(cuda)
     assert m.exact and m.planes == 2
@@ -610,10 +613,14 @@ def test_rrr_exact_mode_closure_vs_oracle(vs, cuda):
     np.testing.assert_allclose(val.cpu().numpy(), sse_val_o["s"], rtol=1e-6)
     with pytest.raises(vs.VsError):
         m.loss_and_grad(td, 1)
+    # predict_y reproduces the closure's residuals
+    _, yv, yhat = m.predict_y(td, "s", 0)
+    assert float(((yhat - yv) ** 2).sum()) == pytest.approx(float(sse.sum()), rel=1e-6)
 
 
-@pytest.mark.parametrize("K,F,N", [(40, 160, 10), (37, 200, 33), (70, 130, 144)])
-def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N):
+@pytest.mark.parametrize("mode", ["exact", "dense"])
+@pytest.mark.parametrize("K,F,N", [(40, 160, 10), (37, 200, 33), (70, 130, 144), (300, 257, 16)])
+def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N, mode):
     """Exact-operand mode on shapes that do not fill tiles (K not a multiple of 16, F not of 128, N not of 16)."""
     from model.rrr import RRRGD, pack_session_from_frames
     Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=3, K=K, Kt=9, F=F, N=N, raw=True)
@@ -625,7 +632,7 @@ def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N):
         params[k] = params[k] + 0.05 * rng.standard_normal(params[k].shape)
     loss_o, g_o, _ = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
     entry = pack_session_from_frames(torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(Xte), torch.from_numpy(yte), sidx, 3,
-                                     device=cuda, mode="exact")
+                                     device=cuda, mode=mode)
     td = {"s": entry}
     m = RRRGD(td, 3, l2=100.0); m.to(cuda)
     _params_to_model(m, params, cuda)
@@ -635,16 +642,17 @@ def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N):
         assert np.abs(got - g_o[k]).max() <= 2e-5 * np.abs(g_o[k]).max(), k
 
 
-def test_rrr_exact_mode_whole_fit_small_vs_oracle(vs, cuda):
-    """train_model_from_frames in its default (exact) mode against the oracle's float64 fit of the same raw arrays:
-    validation SSE, de-z-scored predictions, co-bps and R2 (src/train_rrr.py:193-236)."""
+@pytest.mark.parametrize("mode", [None, "exact", "dense"])
+def test_rrr_exact_mode_whole_fit_small_vs_oracle(vs, cuda, mode):
+    """train_model_from_frames in its default mode and in both exact-operand modes against the oracle's float64 fit of the
+    same raw arrays: validation SSE, de-z-scored predictions, co-bps and R2 (src/train_rrr.py:193-236)."""
     from model.rrr import train_model_from_frames
     Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=0, K=40, Kt=12, F=160, N=10, raw=True)
     data, gt = ro.preprocess_session([Xtr, Xte], [ytr, yte], sidx)
     td_o = {"session": data}
     p_o, mse_o, _ = ro.train_model_main(td_o, 100.0, 3)
     model, mse, td = train_model_from_frames(torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(Xte), torch.from_numpy(yte), sidx,
-                                             l2=100.0, n_comp=3)
+                                             l2=100.0, n_comp=3, mode=mode)
     assert model.exact
     assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=1e-5)
     _, _, pred = model.predict_y_fr(td, "session", 1)

@@ -40,7 +40,7 @@ extern std::atomic<long long> g_launches;
   } while (0)
 
 // ---- optional per-kernel timing (bench.py roofline): event pairs on the launching stream -------
-enum { PROF_GEMM_TC = 0, PROF_DW_ADAMW = 1, PROF_RRR_BWD = 2, PROF_NUM_TAGS = 3 };
+enum { PROF_GEMM_TC = 0, PROF_DW_ADAMW = 1, PROF_RRR_BWD = 2, PROF_RRR_FWD = 3, PROF_RRR_DV = 4, PROF_NUM_TAGS = 5 };
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
 

@@ -52,7 +52,28 @@ struct DenseBwdDesc {
   long long r_plane_stride = 0;
   const float* scaleT = nullptr;
   long long ldt = 0;
+  // dV pass (dense-forward mode, where no Z exists): the same D_t tiles contracted with U instead of accumulated with V:
+  //   dvpart[((cta * 8 + w) * T + t) * 3 + j], cta < rrr_bwd_dense_ctas(C1), w < 8  (G is not written)
+  const float* dv_U32 = nullptr;  // [N][dv_ldu][3] fp32
+  long long dv_ldu = 0, dv_N = 0;
+  float* dvpart = nullptr;
 };
+inline long long rrr_bwd_dense_ctas(long long C1) { return 2 * ((C1 + 255) / 256); }
+// Dense-per-time-bin RRR forward (rrr_fwd_dense_pair_kernel): Y[(t,k), n] = sum_c Xc[(t,k), c] * (U[n,c,:] . V[:,t]) * isd[t,c],
+// the coefficient tiles generated on chip from U (hi + lo half planes), three time bins per CTA pair
+struct DenseFwdDesc {
+  const void* Xc = nullptr;     // (K*T, ldc) IEEE half, EXACT integers frame - round(mean), row t*K + k
+  long long K = 0, T = 0, C1 = 0, N = 0, Npad = 0, ldc = 0;
+  const float* U32 = nullptr;   // [N][ldu][3] fp32, zero for C1 <= c < ldu
+  const float* isd = nullptr;   // [T][ldu] fp32, zero for C1 <= c < ldu
+  long long ldu = 0;            // multiple of 64, >= C1
+  const double* V = nullptr;    // (3, T)
+  const float* bscale = nullptr;  // [T] power-of-two scales of the generated tiles
+  float* Y = nullptr;           // (K*T, ldy) fp32
+  long long ldy = 0;
+};
+bool rrr_fwd_dense_supported(const DenseFwdDesc& g);
+int rrr_fwd_dense(const DenseFwdDesc& g, cudaStream_t stream);
 bool rrr_bwd_dense_supported(const DenseBwdDesc& g);
 int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream);
 size_t balance_ws_bytes();

@@ -805,6 +805,12 @@ struct DensePairParams {
   long long ldg;
   const float* scaleT;       // per (feature row, time bin) weight of the rank-one updates (1/std of the z-score), or NULL
   long long ldt;
+  // kDV variant: instead of accumulating G_j += V[j,t] D_t, contract D_t with the U slab of the CTA's rows:
+  //   dvpart[((cta * 8 + epilogue warp) * T + t) * 3 + j] = sum over the warp's 32 rows c and its columns n of U[n,c,j] * scaleT[c,t] * D_t[c,n]
+  const float* U32;          // [N][ldu][3] fp32
+  long long ldu;
+  int N;
+  float* dvpart;
 };
 
 __device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t* r) {
@@ -824,7 +830,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
 
 constexpr int DENSE_PAIR_THREADS = 384;   // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1-2: epilogue
 
-template <int HW8>   // 8-column chunks per epilogue thread (Npad / 16)
+template <int HW8, bool kDV>   // 8-column chunks per epilogue thread (Npad / 16); kDV: the dV contraction instead of the dU accumulation
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DENSE_PAIR_THREADS, 1)
 rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DensePairParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -949,6 +955,25 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // exact-operand mode: this thread's feature row carries its own z-score scale per time bin (rows past C1 are zero
     // tiles: any in-range scale will do); four bins per 128-bit load
     const int srow = (m_tile * BM + q * 32 + lane) < p.C1 ? (m_tile * BM + q * 32 + lane) : p.C1 - 1;
+    if constexpr (kDV) {
+      // the U slab of this thread's feature row: U_1, U_2 in registers, U_0 parked in the TMEM columns the dU variant uses for G_0
+#pragma unroll
+      for (int c8 = 0; c8 < HW8; ++c8) {
+        uint32_t u0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = hsel * W + c8 * 8 + i;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+          if (n < p.N) {
+            const float* up = p.U32 + ((long long)n * p.ldu + srow) * 3;
+            a0 = __ldg(up); a1 = __ldg(up + 1); a2 = __ldg(up + 2);
+          }
+          u0[i] = __float_as_uint(a0); g1[c8 * 8 + i] = a1; g2[c8 * 8 + i] = a2;
+        }
+        tc_st8(t_g0 + (uint32_t)(c8 * 8), u0);
+      }
+      tc_wait_st();
+    }
     const float* sct = p.scaleT ? p.scaleT + (long long)srow * p.ldt : nullptr;
     float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f);
     for (int t = 0; t < p.T; ++t) {
@@ -980,6 +1005,51 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(dempty_leader0 + 8u * (uint32_t)buf);
       };
+      if constexpr (kDV) {
+        auto issue_dv = [&](int r, int slot) {
+          const int c = 2 * r;
+          tc_ld8_issue(td + (uint32_t)(c * 8), d[slot]);
+          tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0[slot]);
+          if (c + 1 < HW8) { tc_ld8_issue(td + (uint32_t)(c * 8 + 8), d[slot] + 8); tc_ld8_issue(t_g0 + (uint32_t)(c * 8 + 8), a0[slot] + 8); }
+        };
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+        issue_dv(0, 0);
+        tc_wait_ld();
+        if (kRounds == 1) release_d();
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+          const int slot = r & 1, c = 2 * r;
+          const bool two = (c + 1 < HW8);
+          if (r + 1 < kRounds) issue_dv(r + 1, slot ^ 1);
+#pragma unroll
+          for (int i = 0; i < kN; ++i) {
+            if (i < 8 || two) {
+              const int col = (c * 8 + i) < W ? (c * 8 + i) : 0;
+              const float dv = __uint_as_float(d[slot][i]);
+              p0 = fmaf(__uint_as_float(a0[slot][i]), dv, p0);
+              p1 = fmaf(g1[col], dv, p1);
+              p2 = fmaf(g2[col], dv, p2);
+            }
+          }
+          if (r + 1 < kRounds) {
+            tc_wait_ld();
+            if (r + 2 == kRounds) release_d();
+          }
+        }
+        // the 1/std of this row and bin (sc), then the sum over the warp's 32 feature rows
+        p0 *= sc; p1 *= sc; p2 *= sc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+          p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+        }
+        if (lane == 0) {
+          float* o3 = p.dvpart + (((long long)blockIdx.x * 8 + (warp - 4)) * p.T + t) * 3;
+          o3[0] = p0; o3[1] = p1; o3[2] = p2;
+        }
+        continue;
+      }
       issue(0, 0);
       tc_wait_ld();
       if (kRounds == 1) release_d();
@@ -1012,6 +1082,7 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     float* grow = p.G + (long long)row * p.ldg + hsel * W;
 #pragma unroll
     for (int c = 0; c < HW8; ++c) {
+      if constexpr (kDV) break;
       uint32_t a0[8];
       tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0);
       tc_wait_ld();
@@ -1034,6 +1105,233 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ RRR forward, dense per time bin, CTA pairs
+// yraw[(t,k), n] = sum_c Xc[(t,k), c] * beta'_t[n, c],   beta'_t[n,c] = (U[n,c,:] . V[:,t]) / std[t,c]      (src/model/rrr.py:105-116)
+// The factorised forward (Z = X U, 3 N columns) executes r = 3x the flops of the reference's einsum and cannot use the
+// exact integer operand (the z-score scale depends on (t, c)).  Here the coefficient tile of a time bin is GENERATED ON
+// CHIP: nine warps per CTA read U (fp32, L2 resident), form beta'_t for THREE time bins at once -- so a U chunk is fetched
+// once per three bins -- split it into hi + lo half planes and write the K-major, 128B-swizzled B tiles the tensor cores
+// read; A = Xc (exact integers frame - round(mean), half) comes by TMA.  A CTA pair (cta_group::2, UMMA 256 x Npad) owns
+// 256 trials of three bins: 3 accumulators of Npad columns in TMEM (3 * 144 = 432 of 512).  Each CTA generates the B rows
+// of HALF of the neurons.  beta and Z never exist in HBM.
+// warp 0 TMA (A tiles), warp 1 MMA issue, warps 3..11 B generators, warps 4..11 drain the accumulators at the end.
+constexpr int FWD_THREADS = 384;
+constexpr int FWD_BINS = 3;
+constexpr int FWD_GEN_WARPS = 9;
+constexpr int FWD_GEN_THREADS = FWD_GEN_WARPS * 32;     // 288: 8 sixteen-byte chunks x 36 neuron slots
+
+struct DenseFwdParams {
+  int K, T, C1, N, Npad;
+  int n_rt;                  // 256-trial row tiles per time bin
+  int num_kb;                // 64-feature k-blocks
+  const float* U32;          // [N][ldu][3] fp32, zero past C1
+  const float* isd;          // [T][ldu] fp32: 1/std[t,c], zero past C1
+  long long ldu;
+  const double* V;           // (3, T)
+  const float* bscale;       // [T]: power-of-two scale of bin t's B tiles (keeps both half planes in the normal range)
+  float* Y;                  // [T*K][ldy] fp32: sum_c Xc beta' (unscaled)
+  long long ldy;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
+rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int h = p.Npad >> 1;                                   // B rows (neurons) this CTA generates
+  const uint32_t b_bytes = (uint32_t)h * KB_BYTES;             // one (bin, plane) B tile
+  const uint32_t stage_bytes = FWD_BINS * (A_TILE_BYTES + 2u * b_bytes);
+  constexpr int kStages = 2;
+  const uint32_t bar_fullA0 = base, bar_fullB0 = base + 8u * 4, bar_empty0 = base + 8u * 8, bar_done = base + 8u * 12;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 8 * 13);
+  const uint32_t tiles0 = base + CTRL_BYTES;
+
+  const int item = (int)(blockIdx.x >> 1);
+  const int grp = item / p.n_rt, rt = item % p.n_rt;
+  const int t0 = grp * FWD_BINS;
+  const int nbins = (p.T - t0) < FWD_BINS ? (p.T - t0) : FWD_BINS;
+  const int row0 = rt * 256 + rank * BM;                       // first trial of this CTA's 128 rows
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_fullA0 + 8u * s, 1);
+      mbar_init(bar_fullB0 + 8u * s, 2 * FWD_GEN_WARPS);       // the generator warps of both CTAs (only the leader's copy is waited on)
+      mbar_init(bar_empty0 + 8u * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 8u * 13), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's 128 trials of each of the bins, one 64-feature box per bin and k-block =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(bar_fullA0 + 8u * s, 2u * (uint32_t)nbins * A_TILE_BYTES);
+        const uint32_t full = mapa_cluster(bar_fullA0 + 8u * s, 0);
+        for (int b = 0; b < nbins; ++b)
+          tma_load_3d_pair(tiles0 + s * stage_bytes + (uint32_t)b * A_TILE_BYTES, &tmA, full, kb * 64, (t0 + b) * p.K + row0, 0);
+      }
+      __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA): per k-block and bin, 4 K-steps x (lo plane, hi plane) into the bin's accumulator =====
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_pair(true, p.Npad);
+      const uint64_t desc0 = make_smem_desc(tiles0);
+      const uint32_t stage16 = stage_bytes >> 4, a16 = A_TILE_BYTES >> 4, b16 = b_bytes >> 4, boff16 = (FWD_BINS * A_TILE_BYTES) >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(bar_fullA0 + 8u * s, ph);
+        mbar_wait(bar_fullB0 + 8u * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int b = 0; b < nbins; ++b) {
+            const uint64_t da = desc0 + (uint64_t)(s * stage16 + b * a16);
+            const uint64_t dh = desc0 + (uint64_t)(s * stage16 + boff16 + (2 * b) * b16);
+            const uint64_t dl = dh + (uint64_t)b16;
+            const uint32_t dcol = tmem_base + (uint32_t)(b * p.Npad);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_pair(dcol, da + (uint64_t)(k * 2), dl + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              tc_mma_pair(dcol, da + (uint64_t)(k * 2), dh + (uint64_t)(k * 2), idesc, 1u);
+            }
+          }
+          tc_commit_pair(bar_empty0 + 8u * s);
+          if (kb == p.num_kb - 1) tc_commit_pair(bar_done);
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  }
+  if (warp >= 3) {
+    // ===== B generators: thread = (16-byte chunk q of the 128-byte row, neuron slot ns); neurons ns, ns + 36, ... of this half =====
+    const int g = threadIdx.x - 96;
+    const int q = g & 7, ns = g >> 3;
+    float v[FWD_BINS][3], bs[FWD_BINS];
+#pragma unroll
+    for (int b = 0; b < FWD_BINS; ++b) {
+      const int t = (t0 + b) < p.T ? (t0 + b) : (p.T - 1);
+      bs[b] = __ldg(p.bscale + t);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[b][j] = (float)p.V[(long long)j * p.T + t] * bs[b];     // scale folded into V (power of two: exact)
+    }
+    const uint32_t fullB_leader0 = mapa_cluster(bar_fullB0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const long long c0 = (long long)kb * 64 + q * 8;
+      // 1/std of the 8 features of this chunk, per bin
+      float4 sa[FWD_BINS][2];
+#pragma unroll
+      for (int b = 0; b < FWD_BINS; ++b) {
+        const int t = (t0 + b) < p.T ? (t0 + b) : (p.T - 1);
+        const float4* ip = reinterpret_cast<const float4*>(p.isd + (long long)t * p.ldu + c0);
+        sa[b][0] = __ldg(ip); sa[b][1] = __ldg(ip + 1);
+      }
+      mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+      const uint32_t bt0 = tiles0 + s * stage_bytes + FWD_BINS * A_TILE_BYTES;
+      for (int nl = ns; nl < h; nl += FWD_GEN_THREADS / 8) {
+        const int n = rank * h + nl;
+        float u[24];
+        if (n < p.N) {
+          const float4* up = reinterpret_cast<const float4*>(p.U32 + ((long long)n * p.ldu + c0) * 3);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float4 w = __ldg(up + i);
+            u[4 * i] = w.x; u[4 * i + 1] = w.y; u[4 * i + 2] = w.z; u[4 * i + 3] = w.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 24; ++i) u[i] = 0.f;
+        }
+        const uint32_t roff = (uint32_t)(nl >> 3) * 1024u + (uint32_t)(nl & 7) * 128u + ((uint32_t)(q ^ (nl & 7)) << 4);   // SWIZZLE_128B
+#pragma unroll
+        for (int b = 0; b < FWD_BINS; ++b) {
+          if (b < nbins) {
+            const float sc[8] = {sa[b][0].x, sa[b][0].y, sa[b][0].z, sa[b][0].w, sa[b][1].x, sa[b][1].y, sa[b][1].z, sa[b][1].w};
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = fmaf(u[3 * i + 2], v[b][2], fmaf(u[3 * i + 1], v[b][1], u[3 * i] * v[b][0])) * sc[i];
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              hi[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+              const float2 hf = unpack_h2(hi[i]);
+              lo[i] = pack_h2(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+            }
+            const uint32_t dst = bt0 + (uint32_t)(2 * b) * b_bytes + roff;
+            sts128(dst, hi[0], hi[1], hi[2], hi[3]);
+            sts128(dst + b_bytes, lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor cores' async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(fullB_leader0 + 8u * (uint32_t)s);
+      if (++s == kStages) { s = 0; ph ^= 1u; }
+    }
+  }
+  if (warp >= 4) {
+    // ===== drain: Y[(t, k), n] = accumulator / scale; TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 =====
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int qd = warp & 3, hsel = (warp - 4) >> 2;
+    const int W = h;                                           // columns per thread (Npad / 2, a multiple of 8)
+    const int k = row0 + qd * 32 + lane;
+    for (int b = 0; b < nbins; ++b) {
+      const float inv = 1.0f / __ldg(p.bscale + t0 + b);
+      const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * p.Npad + hsel * W);
+      float* yrow = p.Y + ((long long)(t0 + b) * p.K + k) * p.ldy + hsel * W;
+      for (int c = 0; c < W; c += 8) {
+        uint32_t d[8];
+        tc_ld8_issue(ta + (uint32_t)c, d);
+        tc_wait_ld();
+        if (k < p.K) {
+          float4* o = reinterpret_cast<float4*>(yrow + c);
+          o[0] = make_float4(__uint_as_float(d[0]) * inv, __uint_as_float(d[1]) * inv, __uint_as_float(d[2]) * inv, __uint_as_float(d[3]) * inv);
+          o[1] = make_float4(__uint_as_float(d[4]) * inv, __uint_as_float(d[5]) * inv, __uint_as_float(d[6]) * inv, __uint_as_float(d[7]) * inv);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1195,6 +1493,41 @@ static int gemm_tn_pair(const GemmDesc& g, int BN, cudaStream_t stream) {
   return VS_OK;
 }
 
+// ---- dense RRR forward (rrr_fwd_dense_pair_kernel) ----
+bool rrr_fwd_dense_supported(const DenseFwdDesc& g) {
+  if (g.Npad % 16 != 0 || g.Npad < 16 || g.Npad > 160 || g.N > g.Npad || g.N <= 0) return false;
+  if (g.K <= 0 || g.T <= 0 || g.C1 <= 0 || g.K * g.T >= (1ll << 31)) return false;
+  if (((uintptr_t)g.Xc & 15) || (g.ldc * 2) % 16 || g.ldc < g.C1) return false;
+  if (g.ldu % 64 != 0 || g.ldu < round_up(g.C1, 64) || ((uintptr_t)g.U32 & 15) || ((uintptr_t)g.isd & 15)) return false;
+  if (g.ldy % 4 != 0 || g.ldy < g.Npad || ((uintptr_t)g.Y & 15)) return false;
+  return true;
+}
+
+int rrr_fwd_dense(const DenseFwdDesc& g, cudaStream_t stream) {
+  VS_REQUIRE(rrr_fwd_dense_supported(g), VS_ERR_UNSUPPORTED, "dense RRR forward: unsupported shape or operand layout");
+  VS_REQUIRE(g.U32 && g.isd && g.V && g.bscale && g.Y && g.Xc, VS_ERR_INVALID, "dense RRR forward: null pointer");
+  DenseFwdParams p;
+  p.K = (int)g.K; p.T = (int)g.T; p.C1 = (int)g.C1; p.N = (int)g.N; p.Npad = (int)g.Npad;
+  p.n_rt = (int)ceil_div(g.K, 256);
+  p.num_kb = (int)ceil_div(g.C1, 64);
+  p.U32 = g.U32; p.isd = g.isd; p.ldu = g.ldu; p.V = g.V; p.bscale = g.bscale; p.Y = g.Y; p.ldy = g.ldy;
+  Operand a; a.ptr = g.Xc; a.rows = g.K * g.T; a.k = g.C1; a.ld = g.ldc;
+  CUtensorMap tmA;
+  int rc = make_map(&tmA, a, false, true, BM);
+  if (rc) return rc;
+  const int h = p.Npad / 2;
+  const size_t stage_bytes = (size_t)FWD_BINS * (A_TILE_BYTES + 2 * (size_t)h * KB_BYTES);
+  const size_t smem = (size_t)CTRL_BYTES + 1024 + 2 * stage_bytes;
+  VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "dense RRR forward: tile too large for shared memory");
+  const int items = (int)ceil_div(g.T, FWD_BINS) * p.n_rt;
+  dim3 grid(2 * (unsigned)items, 1, 1);
+  prof_begin(PROF_RRR_FWD, stream);
+  VS_CHECK_CUDA(cudaFuncSetAttribute(rrr_fwd_dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VS_LAUNCH(rrr_fwd_dense_pair_kernel, grid, FWD_THREADS, smem, stream, tmA, p);
+  prof_end(PROF_RRR_FWD, stream);
+  return VS_OK;
+}
+
 // ---- dense RRR backward (rrr_bwd_dense_kernel) ----
 bool rrr_bwd_dense_supported(const DenseBwdDesc& g) {
   // Default route; VS_RRR_DENSE=0 selects the factorised GEMM-B (read per call: the tests compare both routes in one process).
@@ -1219,8 +1552,13 @@ static int launch_dense(const CUtensorMap& tmA, const CUtensorMap& tmB, const De
 
 template <int HW8>
 static int launch_dense_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const DensePairParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
-  VS_CHECK_CUDA(cudaFuncSetAttribute(rrr_bwd_dense_pair_kernel<HW8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VS_LAUNCH(rrr_bwd_dense_pair_kernel<HW8>, grid, DENSE_PAIR_THREADS, smem, stream, tmA, tmB, p);
+  if (p.dvpart) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute((rrr_bwd_dense_pair_kernel<HW8, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH((rrr_bwd_dense_pair_kernel<HW8, true>), grid, DENSE_PAIR_THREADS, smem, stream, tmA, tmB, p);
+    return VS_OK;
+  }
+  VS_CHECK_CUDA(cudaFuncSetAttribute((rrr_bwd_dense_pair_kernel<HW8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VS_LAUNCH((rrr_bwd_dense_pair_kernel<HW8, false>), grid, DENSE_PAIR_THREADS, smem, stream, tmA, tmB, p);
   return VS_OK;
 }
 
@@ -1232,6 +1570,8 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
   p.V = g.V; p.G = g.G; p.ldg = g.ldg;
   p.r_planes = g.r_planes > 1 ? 2 : 1;
   p.scaleT = g.scaleT; p.ldt = g.ldt;
+  p.U32 = g.dv_U32; p.ldu = g.dv_ldu; p.N = (int)g.dv_N; p.dvpart = g.dvpart;
+  VS_REQUIRE(!g.dvpart || (g.dv_U32 && g.dv_ldu >= g.C1 && g.dv_N > 0 && g.dv_N <= g.Npad), VS_ERR_INVALID, "dense RRR dV pass: bad U operand");
   VS_REQUIRE(!g.scaleT || (g.ldt % 4 == 0 && g.ldt >= g.T && ((uintptr_t)g.scaleT & 15) == 0), VS_ERR_INVALID,
              "dense RRR backward: the scale table needs a 16-byte aligned base and a pitch that is a multiple of 4 >= T");
   p.vbytes = (int)round_up((long long)DENSE_R * g.T * 4, 1024);
@@ -1254,7 +1594,7 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
   if (rc) return rc;
   const size_t smem = (size_t)CTRL_BYTES + 1024 + p.vbytes + (size_t)stages * stage_bytes;
   dim3 grid(2 * (unsigned)ceil_div(p.m_tiles, 2), 1, 1);
-  prof_begin(PROF_RRR_BWD, stream);
+  prof_begin(p.dvpart ? PROF_RRR_DV : PROF_RRR_BWD, stream);
   switch (p.Npad / 16) {
     case 1: rc = launch_dense_pair<1>(tmA, tmB, p, grid, smem, stream); break;
     case 2: rc = launch_dense_pair<2>(tmA, tmB, p, grid, smem, stream); break;
@@ -1267,7 +1607,7 @@ static int rrr_bwd_dense_pair(const DenseBwdDesc& g, cudaStream_t stream) {
     case 9: rc = launch_dense_pair<9>(tmA, tmB, p, grid, smem, stream); break;
     default: rc = launch_dense_pair<10>(tmA, tmB, p, grid, smem, stream); break;
   }
-  prof_end(PROF_RRR_BWD, stream);
+  prof_end(p.dvpart ? PROF_RRR_DV : PROF_RRR_BWD, stream);
   return rc;
 }
 
@@ -1275,7 +1615,7 @@ int rrr_bwd_dense(const DenseBwdDesc& g, cudaStream_t stream) {
   VS_REQUIRE(rrr_bwd_dense_supported(g), VS_ERR_UNSUPPORTED, "dense RRR backward: unsupported shape");
   {
     const char* e = getenv("VS_RRR_DENSE");   // 1 = half-split kernel (accumulators in registers), default = CTA-pair kernel
-    if (!(e && e[0] == '1')) return rrr_bwd_dense_pair(g, stream);
+    if (!(e && e[0] == '1') || g.dvpart || g.r_planes > 1) return rrr_bwd_dense_pair(g, stream);
   }
   DenseParams p;
   p.C1 = (int)g.C1; p.Npad = (int)g.Npad; p.T = (int)g.T; p.K = (int)g.K; p.Kp = (int)g.Kp;

@@ -221,15 +221,45 @@ __global__ void __launch_bounds__(256) exact_stats_kernel(const int32_t* __restr
   qT[i] = q;
 }
 
-// 32 trials (of ONE time bin) x 128 features per block, like pack_u8_wide_kernel.  Xa: two half planes of z (row
-// d = t*K + k); Xi (may be NULL: forward-only splits): the exact integers, transposed through shared memory.
+// Tables of the dense forward (VS_RRR_MODE_DENSE), one thread per (t, c), rows padded to Tq = T rounded up to 16:
+//   isd[t*ldc + c] = 1/std[t,c] (0 past C1 and past T);  qh: hi + lo half planes of q[t,c] = (mean - round(mean))/std (the A
+//   operand of the small GEMM that forms the constant term);  isdmax[t] = max_c isd[t,c] (caller zeroes it).
+// Features that are constant in the train split (std clipped at 1e-8) get scale 0 in every table: their exact
+// operand is identically zero on the train split, and the pack kernel flags any other split on which it is not.
+__global__ void __launch_bounds__(256) exact_stats2_kernel(const int32_t* __restrict__ sorted_idx, const double* __restrict__ mean,
+                                                           const double* __restrict__ sd, long long T, long long Tq, long long C1,
+                                                           long long ldc, float* __restrict__ isd, uint16_t* __restrict__ qh,
+                                                           unsigned* __restrict__ isdmax_bits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Tq * ldc) return;
+  const long long t = i / ldc, c = i % ldc;
+  float a = 0.f, q = 0.f;
+  if (t < T && c < C1) {
+    const long long col = (long long)sorted_idx[t] * C1 + c;
+    const double m = mean[col], sdv = sd[col];
+    if (sdv > 1e-8) {
+      a = (float)(1.0 / sdv);
+      q = (float)((m - rint(m)) / sdv);
+    }
+  }
+  if (t < T) isd[i] = a;
+  const __half h = __float2half_rn(q);
+  qh[i] = __half_as_ushort(h);
+  qh[Tq * ldc + i] = __half_as_ushort(__float2half_rn(q - __half2float(h)));
+  if (a > 0.f) atomicMax(isdmax_bits + t, __float_as_uint(a));       // non-negative floats order like their bit patterns
+}
+
+// 32 trials (of ONE time bin) x 128 features per block, like pack_u8_wide_kernel.  Xa (may be NULL): two half planes of z
+// (row d = t*K + k); Xc (may be NULL): the exact integers in the same row layout (dense forward operand); Xi (may be NULL:
+// forward-only splits): the exact integers, transposed through shared memory (backward operand).
 __global__ void __launch_bounds__(256) pack_u8_exact_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ sorted_idx,
                                                             const double* __restrict__ mean, const double* __restrict__ sd, long long Tf,
                                                             long long K, long long T, long long C1, long long ldc, long long ldr,
-                                                            uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xi, float* __restrict__ xl,
-                                                            int* __restrict__ overflow) {
+                                                            uint16_t* __restrict__ Xa, uint16_t* __restrict__ Xc, uint16_t* __restrict__ Xi,
+                                                            float* __restrict__ xl, int* __restrict__ overflow) {
   __shared__ uint16_t tile[128][34];          // [feature][trial]
   __shared__ float s_m[128], s_dl[128], s_istd[128];
+  __shared__ bool s_const[128];
   const long long kblocks = (K + 31) / 32;
   const long long t = blockIdx.x / kblocks, k0 = (blockIdx.x % kblocks) * 32;
   const long long c0 = (long long)blockIdx.y * 128, Kp = (K + 15) / 16 * 16;
@@ -242,6 +272,7 @@ __global__ void __launch_bounds__(256) pack_u8_exact_kernel(const uint8_t* __res
     s_m[threadIdx.x] = (float)mi;
     s_dl[threadIdx.x] = (float)(m - mi);
     s_istd[threadIdx.x] = (float)(1.0 / sd[col]);
+    s_const[threadIdx.x] = !(sd[col] > 1e-8);
   }
   __syncthreads();
   const int cx = (threadIdx.x & 31) * 4, ry = threadIdx.x >> 5;
@@ -265,19 +296,32 @@ __global__ void __launch_bounds__(256) pack_u8_exact_kernel(const uint8_t* __res
         if (c + i >= C1) continue;
         const float xc = (float)((w >> (8 * i)) & 0xff) - s_m[cx + i];          // exact integer, |xc| <= 255
         const float zf = (xc - s_dl[cx + i]) * s_istd[cx + i];
-        if (!(fabsf(zf) <= 65504.f)) ovf = true;
+        // a value outside the half range -- or, for the integer operands, a feature that is constant in the train split but
+        // not here (the reference then multiplies by 1e8) -- is reported, never silently mangled
+        if (Xa ? !(fabsf(zf) <= 65504.f) : (s_const[cx + i] && xc != 0.f)) ovf = true;
         const __half h = __float2half_rn(zf);
         hi[i] = __half_as_ushort(h);
         lo[i] = __half_as_ushort(__float2half_rn(zf - __half2float(h)));
         xi[i] = __half_as_ushort(__float2half_rn(xc));
       }
-      uint16_t* dst = Xa + (t * K + k) * ldc + c;
-      if (c + 4 <= C1) {
-        *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
-        *reinterpret_cast<uint2*>(dst + pa) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
-      } else {
-        for (int i = 0; i < 4; ++i)
-          if (c + i < C1) { dst[i] = hi[i]; dst[pa + i] = lo[i]; }
+      if (Xa) {
+        uint16_t* dst = Xa + (t * K + k) * ldc + c;
+        if (c + 4 <= C1) {
+          *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+          *reinterpret_cast<uint2*>(dst + pa) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+        } else {
+          for (int i = 0; i < 4; ++i)
+            if (c + i < C1) { dst[i] = hi[i]; dst[pa + i] = lo[i]; }
+        }
+      }
+      if (Xc) {
+        uint16_t* dst = Xc + (t * K + k) * ldc + c;
+        if (c + 4 <= C1) {
+          *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)xi[0] | ((uint32_t)xi[1] << 16), (uint32_t)xi[2] | ((uint32_t)xi[3] << 16));
+        } else {
+          for (int i = 0; i < 4; ++i)
+            if (c + i < C1) dst[i] = xi[i];
+        }
       }
     }
 #pragma unroll
@@ -384,7 +428,8 @@ constexpr int kPrepC = 4;
 template <int RMAX>
 __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ U, long long N, long long Npad, long long C1,
                                                      int r, int planes, int fmt, long long ldc, uint16_t* __restrict__ Ub,
-                                                     double* __restrict__ Gp, double uscale) {
+                                                     double* __restrict__ Gp, double uscale, float* __restrict__ U32, long long ldu,
+                                                     unsigned* __restrict__ umax_bits) {
   __shared__ double red[8][RMAX * RMAX];
   const long long n = blockIdx.y;
   const long long c0 = ((long long)blockIdx.x * 256 + threadIdx.x) * kPrepC;
@@ -392,13 +437,24 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
   double g[RMAX * RMAX];
 #pragma unroll
   for (int e = 0; e < RMAX * RMAX; ++e) g[e] = 0.0;
+  float um = 0.f;
 #pragma unroll
   for (int q = 0; q < kPrepC; ++q) {
     const long long c = c0 + q;
-    if (c >= C1) break;
+    if (c >= C1) {
+      // dense forward operand: [n][ldu][r] fp32 with zeros in the pad columns (its generator reads whole 64-feature blocks)
+      if (U32 && c < ldu)
+        for (int j = 0; j < r; ++j) U32[(n * ldu + c) * r + j] = 0.f;
+      continue;
+    }
     double u[RMAX];
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) u[j] = j < r ? U[(n * C1 + c) * r + j] : 0.0;
+    if (U32) {
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j)
+        if (j < r) { const float uf = (float)u[j]; U32[(n * ldu + c) * r + j] = uf; um = fmaxf(um, fabsf(uf)); }
+    }
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
       if (j >= r) break;
@@ -413,6 +469,12 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
         for (int j = i; j < RMAX; ++j)
           if (j < r) g[i * RMAX + j] = fma(u[i], u[j], g[i * RMAX + j]);
     }
+  }
+  if (umax_bits) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) um = fmaxf(um, __shfl_xor_sync(0xffffffffu, um, o));
+    // non-negative floats order like their bit patterns: an integer max is exact and order-independent
+    if ((threadIdx.x & 31) == 0 && um > 0.f) atomicMax(umax_bits, __float_as_uint(um));
   }
   if (Gp) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -816,10 +878,154 @@ __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Ga
   }
 }
 
+// ------------------------------------------------------------------ dense-forward mode (VS_RRR_MODE_DENSE): small kernels
+// power-of-two scale of time bin t's generated coefficient tiles: |beta'_t| <= isdmax[t] * umax * sum_j |V[j,t]| =: bound;
+// scale = 2^floor(log2(16384 / bound)) keeps the hi plane below the half maximum and the lo plane (2^-11 of the value)
+// in the normal range for every coefficient within ~2^-9 of the largest one
+__global__ void __launch_bounds__(128) bscale_kernel(const unsigned* __restrict__ umax_bits, const float* __restrict__ isdmax,
+                                                     const double* __restrict__ V, int r, long long T, float* __restrict__ bscale) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float umax = __uint_as_float(*umax_bits);
+  float vs1 = 0.f;
+  for (int j = 0; j < r; ++j) vs1 += fabsf((float)V[(long long)j * T + t]);
+  const float bound = isdmax[t] * umax * vs1;
+  float sc = 1.f;
+  if (bound > 0.f && isfinite(bound)) {
+    int e = (int)floorf(log2f(16384.f / bound));
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    sc = exp2f((float)e);
+  }
+  bscale[t] = sc;
+}
+
+// M1[t][(j,n)] = (1/uscale) * ordered sum of the split-K partials of the small GEMM  q (T x C1) * Ub^T (3 Npad x C1):
+// M1[t][j][n] = sum_c q[t,c] U[n,c,j] with q = (mean - round(mean))/std -- the fractional part of the mean that the exact
+// integer operands leave out (constant term of the forward, correction of dV)
+__global__ void __launch_bounds__(256) m1_reduce_kernel(const float* __restrict__ part, int splits, long long split_stride, long long n,
+                                                        double inv_uscale, double* __restrict__ M1) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int sp = 0; sp < splits; ++sp) s += (double)part[(long long)sp * split_stride + i];
+  M1[i] = s * inv_uscale;
+}
+
+// Epilogue of the dense forward: block (kb, t, nt) = 64 trials of time bin t x 32 neurons (the tiling of epi_f_kernel).
+//   yhat = Y - c0[t,n] + xl * b[n,t],  c0[t,n] = sum_j V[j,t] M1[t][j][n];  R = yhat - y  (float64 throughout)
+// outputs: per-block SSE / db partials, the residual as hi + lo half planes R[p][n][t*Kp + k] (B operand of the backward and
+// of the dV pass), or the prediction itself (kPredict).
+template <bool kPredict>
+__global__ void __launch_bounds__(256) epi_d_kernel(const float* __restrict__ Y, long long ldy, const double* __restrict__ M1, long long ldm,
+                                                    const float* __restrict__ y, const float* __restrict__ y_lo, const float* __restrict__ xl,
+                                                    const double* __restrict__ V, const double* __restrict__ b, long long K, long long T,
+                                                    long long N, long long Npad, int r, long long ldr, uint16_t* __restrict__ RV,
+                                                    double* __restrict__ sse_part, double* __restrict__ db_part, double* __restrict__ yhat,
+                                                    long long Kp) {
+  __shared__ double Rs[kEpiRows][33];
+  __shared__ double red[8][32][2];
+  __shared__ float xls[kEpiRows];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long kb = blockIdx.x, t = blockIdx.y, nt = blockIdx.z, KB = gridDim.x;
+  const long long k0 = kb * kEpiRows, d0 = t * K + k0, n0 = nt * 32;
+  if (threadIdx.x < kEpiRows) xls[threadIdx.x] = (k0 + threadIdx.x < K) ? xl[d0 + threadIdx.x] : 0.f;
+  __syncthreads();
+  const long long n = n0 + lane;
+  double c0 = 0.0, bn = 0.0;
+  if (n < N) {
+    for (int j = 0; j < r; ++j) c0 = fma(V[(long long)j * T + t], M1[t * ldm + (long long)j * Npad + n], c0);
+    bn = b[n * T + t];
+  }
+  double sse = 0.0, sdb = 0.0;
+  constexpr int RPW = kEpiRows / 8;
+  float yr[RPW];
+  double yv[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int rl = w * RPW + i;
+    const long long k = k0 + rl;
+    const bool ok = k < K && n < N;
+    yr[i] = ok ? __ldg(Y + (d0 + rl) * ldy + n) : 0.f;
+    if constexpr (!kPredict) {
+      yv[i] = 0.0;
+      if (ok) {
+        yv[i] = (double)__ldg(y + (k * T + t) * N + n);
+        if (y_lo) yv[i] += (double)__ldg(y_lo + (k * T + t) * N + n);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int rl = w * RPW + i;
+    const long long k = k0 + rl;
+    double res = 0.0;
+    if (k < K && n < N) {
+      const double acc = fma((double)xls[rl], bn, (double)yr[i] - c0);
+      if constexpr (kPredict) {
+        yhat[(k * T + t) * N + n] = acc;
+      } else {
+        res = acc - yv[i];
+        sse = fma(res, res, sse);
+        sdb = fma((double)xls[rl], res, sdb);
+      }
+    }
+    if constexpr (!kPredict) Rs[rl][lane] = res;
+  }
+  if constexpr (!kPredict) {
+    red[w][lane][0] = sse;
+    red[w][lane][1] = sdb;
+    __syncthreads();
+    const long long ka = k0 + 2 * lane;
+    const long long dcol = t * Kp + ka;
+    const long long prd = Npad * ldr;
+    if (RV) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nl = w * 4 + i;
+        const long long nn = n0 + nl;
+        if (nn >= N || ka >= Kp) continue;
+        float ra = (float)Rs[2 * lane][nl], rb = (float)Rs[2 * lane + 1][nl];
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          const uint32_t lo = enc16(ra, VS_OPERAND_F16), hi = enc16(rb, VS_OPERAND_F16);
+          *reinterpret_cast<uint32_t*>(RV + pl * prd + nn * ldr + dcol) = lo | (hi << 16);
+          ra -= dec16((uint16_t)lo, VS_OPERAND_F16); rb -= dec16((uint16_t)hi, VS_OPERAND_F16);
+        }
+      }
+    }
+    if (w == 0 && n < N) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int w2 = 0; w2 < 8; ++w2) { s0 += red[w2][lane][0]; s1 += red[w2][lane][1]; }
+      sse_part[(t * KB + kb) * N + n] = s0;
+      db_part[(t * KB + kb) * N + n] = s1;
+    }
+  }
+}
+
+// dV[j,t] += 2 * ( sum over the dV pass's partials  -  sum_n SR[t,n] M1[t][j][n] )       (one thread per (j, t), ordered sums)
+__global__ void __launch_bounds__(128) dv_reduce_kernel(const float* __restrict__ dvpart, long long nparts, const float* __restrict__ SR,
+                                                        const double* __restrict__ M1, long long ldm, long long T, long long N,
+                                                        long long Npad, int r, double* __restrict__ dV) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)r * T) return;
+  const long long j = e / T, t = e % T;
+  double s = 0.0;
+#pragma unroll 8
+  for (long long q = 0; q < nparts; ++q) s += (double)dvpart[(q * T + t) * 3 + j];
+  double corr = 0.0;
+  for (long long n = 0; n < N; ++n) corr = fma((double)SR[t * Npad + n], M1[t * ldm + j * Npad + n], corr);
+  dV[e] += 2.0 * (s - corr);
+}
+
 // ------------------------------------------------------------------ host orchestration
 struct Ws {
   uint16_t *Ub, *RV;
   float *Z, *Gacc, *SR;
+  float *U32, *bscale, *dvpart;   // dense-forward mode
+  unsigned* umax;
+  double* M1;
+  long long ldm, dv_parts;
   void *sse_part, *db_part, *pv_part;   // float, or double in the exact-operand mode
   void* bal;                 // tail-wave split-K scratch of the GEMMs
   double *Gp, *G, *W, *sse_tn;
@@ -841,7 +1047,7 @@ static int hp_splits(long long k_elems, int planes, int mode) {
   // prediction (~1e-4 over 3400 MMA steps), to which the fit is insensitive, unlike to operand rounding noise
   // (profiles/r02_precision_sim_full.txt: shrink 6e-5 -> 1e-5 on the final validation SSE); split-K partial tiles would
   // cost more HBM traffic than the GEMM itself.
-  if (planes < 2 || mode == VS_RRR_MODE_EXACT) {
+  if (planes < 2 || mode == VS_RRR_MODE_EXACT || mode == VS_RRR_MODE_DENSE) {
     if (run1 <= 0) return 1;
     long long s1 = ceil_div(ceil_div(k_elems, 64), run1);
     return (int)(s1 < 1 ? 1 : (s1 > 256 ? 256 : s1));
@@ -859,7 +1065,7 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.KB = ceil_div(d.K, kEpiRows);
   w.splits_f = hp_splits(d.C1, d.planes, d.mode);
   w.splits_b = hp_splits(d.T * round_up(d.K, 16), d.planes, d.mode);
-  const size_t pe = d.mode == VS_RRR_MODE_EXACT ? 8 : 4;     // element size of the epilogue partials
+  const size_t pe = d.mode != VS_RRR_MODE_CLASSIC ? 8 : 4;     // element size of the epilogue partials
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += (size_t)round_up((long long)bytes, 1024); return q; };
@@ -872,6 +1078,15 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
   w.db_part = take((size_t)d.T * w.KB * d.N * pe);
   w.pv_part = take((size_t)d.T * w.KB * ceil_div(d.N, 32) * d.r * pe);
   w.SR = (float*)take((size_t)d.T * w.Npad * 4);
+  w.U32 = nullptr; w.bscale = nullptr; w.dvpart = nullptr; w.umax = nullptr; w.M1 = nullptr;
+  w.ldm = w.ldz; w.dv_parts = 8 * tc::rrr_bwd_dense_ctas(d.C1);
+  if (d.mode == VS_RRR_MODE_DENSE) {
+    w.U32 = (float*)take((size_t)d.N * d.ldc * d.r * 4);
+    w.bscale = (float*)take((size_t)d.T * 4);
+    w.umax = (unsigned*)take(64);
+    w.M1 = (double*)take((size_t)d.T * w.ldm * 8);
+    w.dvpart = (float*)take((size_t)w.dv_parts * d.T * 3 * 4);
+  }
   w.bal = take(tc::balance_ws_bytes());
   w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
   w.G = (double*)take(kMaxR * kMaxR * 8);
@@ -888,9 +1103,11 @@ static int check_dims(const vs_rrr_dims& d) {
   VS_REQUIRE(d.fmt == VS_OPERAND_BF16 || d.fmt == VS_OPERAND_F16, VS_ERR_INVALID, "rrr: fmt must be VS_OPERAND_BF16 or VS_OPERAND_F16");
   VS_REQUIRE(d.ldc >= d.C1 && d.ldc % 8 == 0 && d.ldr >= d.T * round_up(d.K, 16) && d.ldr % 8 == 0, VS_ERR_INVALID, "rrr: bad pitches");
   VS_REQUIRE(d.K * d.T < (1ll << 31) && d.C1 < (1ll << 31), VS_ERR_UNSUPPORTED, "rrr: dimension exceeds 2^31");
-  VS_REQUIRE(d.mode == VS_RRR_MODE_CLASSIC || d.mode == VS_RRR_MODE_EXACT, VS_ERR_INVALID, "rrr: mode must be VS_RRR_MODE_*");
-  VS_REQUIRE(d.mode != VS_RRR_MODE_EXACT || (d.planes == 2 && d.fmt == VS_OPERAND_F16), VS_ERR_INVALID,
-             "rrr: the exact-operand mode uses two IEEE-half planes (planes = 2, fmt = VS_OPERAND_F16)");
+  VS_REQUIRE(d.mode == VS_RRR_MODE_CLASSIC || d.mode == VS_RRR_MODE_EXACT || d.mode == VS_RRR_MODE_DENSE, VS_ERR_INVALID,
+             "rrr: mode must be VS_RRR_MODE_*");
+  VS_REQUIRE(d.mode == VS_RRR_MODE_CLASSIC || (d.planes == 2 && d.fmt == VS_OPERAND_F16), VS_ERR_INVALID,
+             "rrr: the exact-operand modes use two IEEE-half planes (planes = 2, fmt = VS_OPERAND_F16)");
+  VS_REQUIRE(d.mode != VS_RRR_MODE_DENSE || d.r == 3, VS_ERR_UNSUPPORTED, "rrr: the dense-forward mode is built for rank 3");
   return VS_OK;
 }
 
@@ -1019,15 +1236,102 @@ struct ExactArgs {
   const float* qT = nullptr;     // (C1, ldt): (mean - round(mean))[t,c] / std[t,c]
   long long ldt = 0;
   const float* y_lo = nullptr;   // (K,T,N): y = y + y_lo at float64 precision (may be NULL)
+  // dense-forward mode
+  const uint16_t* Xc = nullptr;  // (K*T, ldc) half exact integers (forward A operand)
+  const float* isd = nullptr;    // (T, ldc)
+  const uint16_t* qh = nullptr;  // (2, Tq, ldc) half planes of q
+  const float* isdmax = nullptr; // (T)
 };
+
+// Forward of the dense mode up to the raw accumulators: U planes + U32 + Gram partials, scales, the small GEMM M1 = q U,
+// then Y = Xc beta' (tc::rrr_fwd_dense).  Y lands in w.Z (pitch Npad), M1 in w.M1.
+static int dense_forward(const vs_rrr_dims& d, const ExactArgs& ex, const Ws& w, const double* U, const double* V, bool want_gram,
+                         cudaStream_t st) {
+  const int r = (int)d.r;
+  VS_REQUIRE(ex.Xc && ex.isd && ex.qh && ex.isdmax, VS_ERR_INVALID, "vs_rrr_closure_exact: the dense-forward mode needs Xc, isd, qh and isdmax");
+  VS_CHECK_CUDA(cudaMemsetAsync(w.umax, 0, 4, st));
+  dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
+  VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
+            want_gram ? w.Gp : (double*)nullptr, kExactUScale, w.U32, (long long)d.ldc, w.umax);
+  VS_LAUNCH(bscale_kernel, (unsigned)ceil_div(d.T, 128), 128, 0, st, w.umax, ex.isdmax, V, r, (long long)d.T, w.bscale);
+  // M1 partials (split-K of the (T x C1) x (C1 x 3 Npad) product over ~all SMs) live in the Gacc buffer until reduced
+  const long long Tq = round_up(d.T, 16);
+  tc::GemmDesc g;
+  g.A.ptr = ex.qh; g.A.rows = d.T; g.A.k = d.C1; g.A.ld = d.ldc; g.A.planes = 2; g.A.plane_stride = Tq * d.ldc;
+  g.B.ptr = w.Ub; g.B.rows = w.ldz; g.B.k = d.C1; g.B.ld = d.ldc; g.B.planes = 2; g.B.plane_stride = w.ldz * d.ldc;
+  g.M = d.T; g.N = w.ldz; g.K = d.C1; g.C = w.Gacc; g.ldc = w.ldz;
+  long long want = kNumSMs;
+  if (want * d.T > d.C1) want = d.C1 / d.T;             // the partials must fit the Gacc buffer (C1 x ldz floats)
+  if (want < 1) want = 1;
+  int splits = 1;
+  g.splits = (int)want; g.split_stride = d.T * w.ldz; g.splits_out = &splits;
+  g.f16 = true;
+  set_passes(g, 2);
+  int rc = tc::gemm_tn(g, st);
+  if (rc) return rc;
+  VS_LAUNCH(m1_reduce_kernel, (unsigned)ceil_div(d.T * w.ldz, 256), 256, 0, st, w.Gacc, splits, (long long)(d.T * w.ldz), (long long)(d.T * w.ldz),
+            1.0 / kExactUScale, w.M1);
+  tc::DenseFwdDesc f;
+  f.Xc = ex.Xc; f.K = d.K; f.T = d.T; f.C1 = d.C1; f.N = d.N; f.Npad = w.Npad; f.ldc = d.ldc;
+  f.U32 = w.U32; f.isd = ex.isd; f.ldu = d.ldc; f.V = V; f.bscale = w.bscale; f.Y = w.Z; f.ldy = w.Npad;
+  return tc::rrr_fwd_dense(f, st);
+}
+
+// One closure evaluation in the dense-forward mode: every contraction is the reference's own (src/model/rrr.py:105-116 and
+// its autograd), one time bin at a time, with the exact integer frames as the large operand:
+//   forward  Y_t = Xc_t beta'_t^T            tc::rrr_fwd_dense   (coefficient tiles generated on chip, hi + lo)
+//   dU       G_j = sum_t V[j,t]/std D_t      tc::rrr_bwd_dense   (D_t = Xc_t^T R_t, R as hi + lo planes)
+//   dV       sum_c,n U/std D_t               tc::rrr_bwd_dense with dvpart (the same D_t tiles contracted with U)
+// plus the rank-T terms the fractional part of the mean contributes (M1 = q U).
+static int closure_dense(const vs_rrr_dims& d, const uint16_t* Xi, const ExactArgs& ex, const float* xl, const float* y, const double* U,
+                         const double* V, const double* b, double l2, double* loss, double* sse_n, double* dU, double* dV, double* db,
+                         const Ws& w, cudaStream_t st) {
+  const int r = (int)d.r;
+  int rc = dense_forward(d, ex, w, U, V, true, st);
+  if (rc) return rc;
+  VS_LAUNCH(small_mats_kernel, r * r + 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
+  dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
+  VS_LAUNCH((epi_d_kernel<false>), ge, 256, 0, st, w.Z, w.Npad, w.M1, w.ldm, y, ex.y_lo, xl, V, b, (long long)d.K, (long long)d.T, (long long)d.N,
+            w.Npad, r, (long long)d.ldr, dU ? w.RV : (uint16_t*)nullptr, (double*)w.sse_part, (double*)w.db_part, (double*)nullptr, w.Kp);
+  dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
+  VS_LAUNCH(reduce_part_kernel<double>, g2, 128, 0, st, (const double*)w.sse_part, (const double*)w.db_part, b, w.KB, (long long)d.T,
+            (long long)d.N, l2, db, w.sse_tn, w.SR, w.Npad);
+  // loss, per-neuron SSE, and the penalty part of dV (the data part comes from the dV pass below: no Z exists here)
+  VS_LAUNCH(finalize_kernel<double>, 1, 1024, 0, st, w.sse_tn, (const double*)nullptr, w.G, w.W, V, b, 0ll, 0ll, (long long)d.T,
+            (long long)d.N, r, l2, sse_n, loss, dV);
+  if (!dU && !dV) return VS_OK;
+  VS_REQUIRE(Xi && ex.isdT && ex.qT, VS_ERR_INVALID, "vs_rrr_closure_exact: gradients need the backward operand Xi and the scale tables");
+  tc::DenseBwdDesc dd;
+  dd.Xb = Xi; dd.R = w.RV; dd.C1 = d.C1; dd.K = d.K; dd.Kp = w.Kp; dd.T = d.T; dd.Npad = w.Npad; dd.ldr = d.ldr;
+  dd.r = r; dd.f16 = true; dd.V = V; dd.G = w.Gacc; dd.ldg = w.ldz;
+  dd.r_planes = 2; dd.r_plane_stride = w.Npad * d.ldr; dd.scaleT = ex.isdT; dd.ldt = ex.ldt;
+  VS_REQUIRE(tc::rrr_bwd_dense_supported(dd), VS_ERR_UNSUPPORTED, "vs_rrr_closure_exact: shape outside the dense backward kernel");
+  if (dV) {
+    tc::DenseBwdDesc dv = dd;
+    dv.dv_U32 = w.U32; dv.dv_ldu = d.ldc; dv.dv_N = d.N; dv.dvpart = w.dvpart;
+    rc = tc::rrr_bwd_dense(dv, st);
+    if (rc) return rc;
+    VS_LAUNCH(dv_reduce_kernel, (unsigned)ceil_div((long long)r * d.T, 128), 128, 0, st, w.dvpart, w.dv_parts, w.SR, w.M1, w.ldm, (long long)d.T,
+              (long long)d.N, w.Npad, r, dV);
+  }
+  if (dU) {
+    rc = tc::rrr_bwd_dense(dd, st);
+    if (rc) return rc;
+    dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
+    VS_LAUNCH((epi_b_kernel<false, 4, true>), g4, 256, 0, st, w.Gacc, w.ldz, 1, (long long)d.C1 * w.ldz, U, w.W, (long long)d.C1, (long long)d.N,
+              w.Npad, r, l2, dU, ex.qT, ex.ldt, w.SR, V, (long long)d.T);
+  }
+  return VS_OK;
+}
 
 static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, const ExactArgs& ex, const float* xl, const float* y,
                         const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,
                         double* dU, double* dV, double* db, int engine, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
-  const bool exact = d.mode == VS_RRR_MODE_EXACT;
-  VS_REQUIRE(Xa && xl && y && U && V && b, VS_ERR_INVALID, "vs_rrr_closure: null pointer");
+  const bool dense_fwd = d.mode == VS_RRR_MODE_DENSE;
+  const bool exact = d.mode == VS_RRR_MODE_EXACT || dense_fwd;
+  VS_REQUIRE((Xa || dense_fwd) && xl && y && U && V && b, VS_ERR_INVALID, "vs_rrr_closure: null pointer");
   VS_REQUIRE(!dU || Xb, VS_ERR_INVALID, "vs_rrr_closure: dU needs Xb");
   VS_REQUIRE(workspace && workspace_bytes >= vs_rrr_workspace(d), VS_ERR_WORKSPACE, "vs_rrr_closure: workspace too small (%zu < %zu)",
              workspace_bytes, vs_rrr_workspace(d));
@@ -1039,12 +1343,14 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
   // half planes: U ~ 1/sqrt(T r) would put its lo plane (2^-11 of the value) into the half subnormals; a power-of-two
   // scale keeps both planes normal and is undone exactly in the epilogue
   const double uscale = exact ? kExactUScale : 1.0;
+  float* u32 = nullptr; long long ldu = 0; unsigned* umax = nullptr;
+  if (dense_fwd) return closure_dense(d, Xb, ex, xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, w, st);
   // stage 0: U planes + Gram partials, then G and W = V V^T
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
   if (r <= 4) {
-    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale);
+    VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale, u32, ldu, umax);
   } else {
-    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale);
+    VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale, u32, ldu, umax);
   }
   VS_LAUNCH(small_mats_kernel, r * r + 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   // stage 1: Z
@@ -1105,19 +1411,28 @@ extern "C" int vs_rrr_closure(vs_rrr_dims d, const uint16_t* Xa, const uint16_t*
   return closure_impl(d, Xa, Xb, ExactArgs(), xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, engine, workspace, workspace_bytes, stream);
 }
 
-extern "C" int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xi, const float* isdT, const float* qT,
-                                    int64_t ldt, const float* xl, const float* y, const float* y_lo, const double* U, const double* V,
-                                    const double* b, double l2, double* loss, double* sse_n, double* dU, double* dV, double* db,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
-  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT, VS_ERR_INVALID, "vs_rrr_closure_exact: dims.mode must be VS_RRR_MODE_EXACT");
+static ExactArgs exact_args(const vs_rrr_exact_ops* o) {
   ExactArgs ex;
-  ex.isdT = isdT; ex.qT = qT; ex.ldt = ldt; ex.y_lo = y_lo;
-  return closure_impl(d, Xa, Xi, ex, xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, VS_ENGINE_AUTO, workspace, workspace_bytes, stream);
+  if (o) {
+    ex.isdT = o->isdT; ex.qT = o->qT; ex.ldt = o->ldt; ex.y_lo = o->y_lo;
+    ex.Xc = o->Xc; ex.isd = o->isd; ex.qh = o->qh; ex.isdmax = o->isdmax;
+  }
+  return ex;
+}
+
+extern "C" int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const vs_rrr_exact_ops* ops, const float* xl, const float* y,
+                                    const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n, double* dU,
+                                    double* dV, double* db, void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT || d.mode == VS_RRR_MODE_DENSE, VS_ERR_INVALID,
+             "vs_rrr_closure_exact: dims.mode must be VS_RRR_MODE_EXACT or VS_RRR_MODE_DENSE");
+  VS_REQUIRE(ops, VS_ERR_INVALID, "vs_rrr_closure_exact: null operand table");
+  return closure_impl(d, Xa, ops->Xi, exact_args(ops), xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, VS_ENGINE_AUTO, workspace, workspace_bytes,
+                      stream);
 }
 
 extern "C" int64_t vs_rrr_ldt(int64_t T) { return round_up(T, 4); }
 
-// shapes the exact-operand closure covers (its backward is the tcgen05 dense per-time-bin kernel); callers fall back to
+// shapes the exact-operand closures cover (their backward is the tcgen05 dense per-time-bin kernel); callers fall back to
 // the classic mode with 3 residual planes elsewhere
 extern "C" int vs_rrr_exact_supported(int64_t K, int64_t T, int64_t C1, int64_t N, int64_t r) {
   const long long Npad = round_up(N, 16);
@@ -1125,26 +1440,58 @@ extern "C" int vs_rrr_exact_supported(int64_t K, int64_t T, int64_t C1, int64_t 
 }
 
 extern "C" int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
-                                    const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, uint16_t* Xi, float* xl, float* isdT,
-                                    float* qT, int32_t* overflow_flag, void* stream) {
+                                    const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, const vs_rrr_exact_ops* out, float* xl,
+                                    int32_t* overflow_flag, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
-  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: dims.mode must be VS_RRR_MODE_EXACT");
-  VS_REQUIRE(frames && sorted_idx && mean && std_clipped && Xa && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: bad arguments");
-  VS_REQUIRE((isdT == nullptr) == (qT == nullptr), VS_ERR_INVALID, "vs_rrr_pack_u8_exact: the two scale tables go together");
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT || d.mode == VS_RRR_MODE_DENSE, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: dims.mode must be an exact-operand mode");
+  VS_REQUIRE(frames && sorted_idx && mean && std_clipped && out && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: bad arguments");
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT ? Xa != nullptr : out->Xc != nullptr, VS_ERR_INVALID,
+             "vs_rrr_pack_u8_exact: the forward operand of the mode is missing (Xa for EXACT, ops.Xc for DENSE)");
+  VS_REQUIRE((out->isdT == nullptr) == (out->qT == nullptr), VS_ERR_INVALID, "vs_rrr_pack_u8_exact: isdT and qT go together");
   VS_REQUIRE(d.ldr % 2 == 0, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: ldr must be even");
+  uint16_t* Xi = const_cast<uint16_t*>(out->Xi);
+  uint16_t* Xc = d.mode == VS_RRR_MODE_DENSE ? const_cast<uint16_t*>(out->Xc) : nullptr;
   dim3 gw((unsigned)(ceil_div(d.K, 32) * d.T), (unsigned)ceil_div(d.C1, 128));
   VS_REQUIRE(gw.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8_exact: too many columns");
   VS_LAUNCH(pack_u8_exact_kernel, gw, 256, 0, stream, frames, sorted_idx, mean, std_clipped, (long long)Tf, (long long)d.K, (long long)d.T,
-            (long long)d.C1, (long long)d.ldc, (long long)d.ldr, Xa, Xi, xl, overflow_flag);
+            (long long)d.C1, (long long)d.ldc, (long long)d.ldr, d.mode == VS_RRR_MODE_EXACT ? Xa : (uint16_t*)nullptr, Xc, Xi, xl, overflow_flag);
   if (Xi && round_up(d.K, 16) > d.K)
     VS_LAUNCH(pad_zero_kernel, (unsigned)ceil_div((long long)d.C1 * d.T, 256), 256, 0, stream, Xi, (long long)d.C1, (long long)d.T,
               (long long)d.K, (long long)round_up(d.K, 16), (long long)d.ldr);
-  if (isdT) {
+  if (out->isdT) {
     const long long ldt = round_up(d.T, 4);
+    VS_REQUIRE(out->ldt == ldt, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: ops.ldt must be vs_rrr_ldt(T)");
     VS_LAUNCH(exact_stats_kernel, (unsigned)ceil_div(d.C1 * ldt, 256), 256, 0, stream, sorted_idx, mean, std_clipped, (long long)d.T,
-              (long long)d.C1, ldt, isdT, qT);
+              (long long)d.C1, ldt, const_cast<float*>(out->isdT), const_cast<float*>(out->qT));
   }
+  if (out->isd) {
+    VS_REQUIRE(out->qh && out->isdmax, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: isd, qh and isdmax go together");
+    const long long Tq = round_up(d.T, 16);
+    VS_CHECK_CUDA(cudaMemsetAsync(const_cast<float*>(out->isdmax), 0, (size_t)d.T * 4, (cudaStream_t)stream));
+    VS_LAUNCH(exact_stats2_kernel, (unsigned)ceil_div(Tq * d.ldc, 256), 256, 0, stream, sorted_idx, mean, std_clipped, (long long)d.T, Tq,
+              (long long)d.C1, (long long)d.ldc, const_cast<float*>(out->isd), const_cast<uint16_t*>(out->qh),
+              reinterpret_cast<unsigned*>(const_cast<float*>(out->isdmax)));
+  }
+  return VS_OK;
+}
+
+// src/model/rrr.py:105-130 for a split packed in the dense-forward mode (vs_rrr_predict serves the other modes)
+extern "C" int vs_rrr_predict_exact(vs_rrr_dims d, const vs_rrr_exact_ops* ops, const float* xl, const double* U, const double* V,
+                                    const double* b, double* yhat, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(d.mode == VS_RRR_MODE_DENSE, VS_ERR_INVALID, "vs_rrr_predict_exact: dims.mode must be VS_RRR_MODE_DENSE");
+  VS_REQUIRE(ops && xl && U && V && b && yhat, VS_ERR_INVALID, "vs_rrr_predict_exact: null pointer");
+  VS_REQUIRE(workspace && workspace_bytes >= vs_rrr_workspace(d), VS_ERR_WORKSPACE, "vs_rrr_predict_exact: workspace too small");
+  VS_REQUIRE(((uintptr_t)workspace & 1023) == 0, VS_ERR_INVALID, "vs_rrr_predict_exact: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = carve(d, workspace);
+  rc = dense_forward(d, exact_args(ops), w, U, V, false, st);
+  if (rc) return rc;
+  dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
+  VS_LAUNCH((epi_d_kernel<true>), ge, 256, 0, st, w.Z, w.Npad, w.M1, w.ldm, (const float*)nullptr, (const float*)nullptr, xl, V, b, (long long)d.K,
+            (long long)d.T, (long long)d.N, w.Npad, (int)d.r, (long long)d.ldr, (uint16_t*)nullptr, (double*)nullptr, (double*)nullptr, yhat, 0ll);
   return VS_OK;
 }
 
@@ -1159,13 +1506,15 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   const Ws w = carve(d, workspace);
   const long long KT = d.K * d.T;
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
+  VS_REQUIRE(d.mode != VS_RRR_MODE_DENSE, VS_ERR_INVALID, "vs_rrr_predict: dense-forward splits go through vs_rrr_predict_exact");
   const double uscale = d.mode == VS_RRR_MODE_EXACT ? kExactUScale : 1.0;
+  float* u32 = nullptr; long long ldu = 0; unsigned* umax = nullptr;
   if (d.r <= 4) {
     VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
-              (double*)nullptr, uscale);
+              (double*)nullptr, uscale, u32, ldu, umax);
   } else {
     VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
-              (double*)nullptr, uscale);
+              (double*)nullptr, uscale, u32, ldu, umax);
   }
   int sf = 1;
   rc = gemm_f(d, Xa, w, engine, st, &sf);

@@ -53,8 +53,8 @@ def rrr_mode(mode=None):
     classic: `planes` residual planes of the z-scored matrix for both contractions (planes = 1 is the fastest setting;
     its fit is ~2e-3 away from the reference's, DESIGN.md "RRR precision").  Select with `mode=` or VS_RRR_MODE."""
     mode = mode or os.environ.get("VS_RRR_MODE") or "exact"
-    if mode not in ("exact", "classic"):
-        raise ValueError("mode must be 'exact' or 'classic'")
+    if mode not in ("exact", "dense", "classic"):
+        raise ValueError("mode must be 'exact', 'dense' or 'classic'")
     return mode
 
 
@@ -166,6 +166,13 @@ class _PackedSplit:
         self._keep = None
         return self
 
+    def exact_ops(self):
+        """ctypes vs_rrr_exact_ops of this split (the tensors stay referenced by self.exact)."""
+        ex = self.exact
+        g = lambda k: vs.ptr(ex.get(k)) if ex.get(k) is not None else None      # noqa: E731
+        return vs.RrrExactOps(vs.ptr(self.Xb) if self.Xb is not None else None, g("isdT"), g("qT"), int(ex["ldt"]), g("y_lo"),
+                              g("Xc"), g("isd"), g("qh"), g("isdmax"))
+
     def __del__(self):
         ev = getattr(self, "ready", None)
         if ev is not None:
@@ -218,7 +225,7 @@ class RRRGD():
         self.engine = int(engine if engine is not None else os.environ.get("VS_ENGINE", str(vs.ENGINE_AUTO)))
         self.fmt = operand_format(self.planes, operand)
         # splits packed in the exact-operand mode (pack_session_from_frames) carry their own layout: two half planes
-        self.exact = any(isinstance(x, _PackedSplit) and x.dims.mode == vs.RRR_MODE_EXACT
+        self.exact = any(isinstance(x, _PackedSplit) and x.dims.mode != vs.RRR_MODE_CLASSIC
                          for e in train_data.values() for x in e["X"])
         if self.exact:
             self.planes, self.fmt = 2, vs.OPERAND_F16
@@ -360,12 +367,12 @@ class RRRGD():
         if want_grad:
             dU, db = self._grad_buffer(U), self._grad_buffer(b)
         ws = self._workspace(sp.dims)
-        if sp.dims.mode == vs.RRR_MODE_EXACT:
-            ex = sp.exact
-            vs.check(vs.lib.vs_rrr_closure_exact(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(ex["isdT"]), vs.ptr(ex["qT"]), ex["ldt"],
-                                                 vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(ex.get("y_lo")), vs.ptr(U.data), vs.ptr(V.data),
-                                                 vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU), vs.ptr(dV),
-                                                 vs.ptr(db), vs.ptr(ws), ws.numel(), vs.stream()))
+        if sp.dims.mode != vs.RRR_MODE_CLASSIC:
+            import ctypes
+            ops = sp.exact_ops()
+            vs.check(vs.lib.vs_rrr_closure_exact(sp.dims, vs.ptr(sp.Xa), ctypes.byref(ops), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
+                                                 vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
+                                                 vs.ptr(dV), vs.ptr(db), vs.ptr(ws), ws.numel(), vs.stream()))
             return loss[0], sse, dU, db
         vs.check(vs.lib.vs_rrr_closure(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
                                        vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
@@ -408,8 +415,14 @@ class RRRGD():
         U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
         yhat = torch.empty((sp.K, sp.T, sp.N), dtype=torch.float64, device=V.device)
         ws = self._workspace(sp.dims)
-        vs.check(vs.lib.vs_rrr_predict(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.xl), vs.ptr(U.data), vs.ptr(V.data), vs.ptr(b.data),
-                                       vs.ptr(yhat), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
+        if sp.dims.mode == vs.RRR_MODE_DENSE:
+            import ctypes
+            ops = sp.exact_ops()
+            vs.check(vs.lib.vs_rrr_predict_exact(sp.dims, ctypes.byref(ops), vs.ptr(sp.xl), vs.ptr(U.data), vs.ptr(V.data), vs.ptr(b.data),
+                                                 vs.ptr(yhat), vs.ptr(ws), ws.numel(), vs.stream()))
+        else:
+            vs.check(vs.lib.vs_rrr_predict(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.xl), vs.ptr(U.data), vs.ptr(V.data), vs.ptr(b.data),
+                                           vs.ptr(yhat), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
         Xraw = data[eid]['X'][k]
         X = np2tensor(Xraw) if isinstance(Xraw, np.ndarray) else None
         y = np2tensor(np.ascontiguousarray(data[eid]['y'][k])).to(V.device) if isinstance(data[eid]['y'][k], np.ndarray) \
@@ -484,7 +497,9 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
     vs.require_b200()
     if mode is None:
         mode = "classic" if planes is not None else rrr_mode(None)
-    exact = rrr_mode(mode) == "exact"
+    mode = rrr_mode(mode)
+    exact = mode in ("exact", "dense")
+    dense = mode == "dense"
     if exact:
         # shapes outside the exact-operand kernels (rank != 3, more than 160 neurons, <= 128 features): the parity mode is
         # then the classic layout with 3 residual planes
@@ -516,19 +531,29 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
         F = int(fr[0, 0].numel())
         N = int(cnt.shape[2])
         d = vs.RrrDims(K, T, F, N, n_comp, planes, vs.lib.vs_rrr_ldc(F), vs.lib.vs_rrr_ldr(K, T), fmt,
-                       vs.RRR_MODE_EXACT if exact else vs.RRR_MODE_CLASSIC)
-        Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)          # allocated on the main stream
+                       (vs.RRR_MODE_DENSE if dense else vs.RRR_MODE_EXACT) if exact else vs.RRR_MODE_CLASSIC)
         ex = None
         if exact:
+            # forward operand: z as hi + lo half planes (exact) or the exact integers in the same row layout (dense);
             # backward operand: ONE plane of exact integers, train split only (the other splits are only evaluated);
             # the scale tables come from the train statistics and are shared by every split of the session
+            Xa = None if dense else torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)
             Xb = torch.empty((F, d.ldr), dtype=_op_dtype(fmt), device=device) if which == 0 else None
             ldt = int(vs.lib.vs_rrr_ldt(T))
             if which == 0:
-                isdT = torch.empty((F, ldt), dtype=torch.float32, device=device)
-                qT = torch.empty((F, ldt), dtype=torch.float32, device=device)
-            ex = {"isdT": isdT, "qT": qT, "ldt": ldt, "y_lo": torch.empty((K, T, N), dtype=torch.float32, device=device)}
+                tables = {"isdT": torch.empty((F, ldt), dtype=torch.float32, device=device),
+                          "qT": torch.empty((F, ldt), dtype=torch.float32, device=device)}
+                if dense:
+                    Tq = (T + 15) // 16 * 16
+                    tables.update({"isd": torch.empty((T, d.ldc), dtype=torch.float32, device=device),
+                                   "qh": torch.empty((2, Tq, d.ldc), dtype=torch.float16, device=device),
+                                   "isdmax": torch.empty(T, dtype=torch.float32, device=device)})
+            ex = dict(tables)
+            ex.update({"ldt": ldt, "y_lo": torch.empty((K, T, N), dtype=torch.float32, device=device)})
+            if dense:
+                ex["Xc"] = torch.empty((K * T, d.ldc), dtype=_op_dtype(fmt), device=device)
         else:
+            Xa = torch.empty((planes, K * T, d.ldc), dtype=_op_dtype(fmt), device=device)          # allocated on the main stream
             Xb = torch.empty((planes, F, d.ldr), dtype=_op_dtype(fmt), device=device)
         xl = torch.empty(K * T, dtype=torch.float32, device=device)
         y = torch.empty((K, T, N), dtype=torch.float32, device=device)
@@ -564,9 +589,13 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                 vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
                 del sm
             if exact:
-                vs.check(vs.lib.vs_rrr_pack_u8_exact(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa),
-                                                     vs.ptr(Xb), vs.ptr(xl), vs.ptr(isdT) if which == 0 else None,
-                                                     vs.ptr(qT) if which == 0 else None, vs.ptr(overflow), st))
+                import ctypes
+                tw = (lambda k: vs.ptr(ex[k]) if (which == 0 and k in ex) else None)      # tables are written with the train split only
+                out = vs.RrrExactOps(vs.ptr(Xb) if Xb is not None else None, tw("isdT"), tw("qT"), ldt, None,
+                                     vs.ptr(ex["Xc"]) if dense else None, tw("isd"), tw("qh"), tw("isdmax"))
+                vs.check(vs.lib.vs_rrr_pack_u8_exact(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d,
+                                                     vs.ptr(Xa) if Xa is not None else None, ctypes.byref(out), vs.ptr(xl),
+                                                     vs.ptr(overflow), st))
                 vs.check(vs.lib.vs_rrr_smooth_y2(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y),
                                                  vs.ptr(ex["y_lo"]), st))
             else:

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvs_b200.so")
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 OPERAND_BF16, OPERAND_F16 = 0, 1
-RRR_MODE_CLASSIC, RRR_MODE_EXACT = 0, 1
+RRR_MODE_CLASSIC, RRR_MODE_EXACT, RRR_MODE_DENSE = 0, 1, 2
 MAX_LAYERS = 16
 
 
@@ -58,6 +58,12 @@ class RrrDims(C.Structure):
                 ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64), ("fmt", C.c_int32), ("mode", C.c_int32)]
 
 
+class RrrExactOps(C.Structure):
+    """vs_rrr_exact_ops: device pointers of the exact-operand tables of one split (include/vs_b200.h)."""
+    _fields_ = [("Xi", C.c_void_p), ("isdT", C.c_void_p), ("qT", C.c_void_p), ("ldt", C.c_int64), ("y_lo", C.c_void_p),
+                ("Xc", C.c_void_p), ("isd", C.c_void_p), ("qh", C.c_void_p), ("isdmax", C.c_void_p)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -95,8 +101,9 @@ def _load():
         "vs_rrr_smooth_y2": (C.c_int, [vp, i64, i64, i64, dbl, vp, vp, vp, vp, vp]),
         "vs_rrr_ldt": (i64, [i64]),
         "vs_rrr_exact_supported": (C.c_int, [i64, i64, i64, i64, i64]),
-        "vs_rrr_pack_u8_exact": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, vp, vp, vp, vp, vp, vp]),
-        "vs_rrr_closure_exact": (C.c_int, [RrrDims, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "vs_rrr_pack_u8_exact": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, C.POINTER(RrrExactOps), vp, vp, vp]),
+        "vs_rrr_closure_exact": (C.c_int, [RrrDims, vp, C.POINTER(RrrExactOps), vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "vs_rrr_predict_exact": (C.c_int, [RrrDims, C.POINTER(RrrExactOps), vp, vp, vp, vp, vp, vp, sz, vp]),
         "vs_colstats_f32": (C.c_int, [vp, i64, i64, vp, vp, vp]),
         "vs_rrr_workspace": (sz, [RrrDims]),
         "vs_rrr_closure": (C.c_int, [RrrDims, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
