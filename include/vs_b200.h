@@ -282,6 +282,13 @@ int vs_rrr_exact_supported(int64_t K, int64_t T, int64_t C1, int64_t N, int64_t 
 int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, const double* mean,
                          const double* std_clipped, vs_rrr_dims d, uint16_t* Xa, const vs_rrr_exact_ops* out, float* xl,
                          int32_t* overflow_flag, void* stream);
+/* The same operands from ONE read of the frames (statistics and pack fused per time bin: the K trials of a 128-feature
+ * chunk of one frame are staged in shared memory).  compute_stats != 0 (train split): mean / std_clipped of the selected
+ * frames sorted_idx[t] are computed (src/utils/utils.py:107-112) and written into the (Tf, C1) tables; == 0: read.
+ * Needs C1 % 4 == 0 and K <= 1600; otherwise VS_ERR_UNSUPPORTED (use vs_rrr_colstats + vs_rrr_pack_u8_exact).          */
+int vs_rrr_pack_u8_fused(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, double* mean, double* std_clipped,
+                         int compute_stats, vs_rrr_dims d, uint16_t* Xa, const vs_rrr_exact_ops* out, float* xl,
+                         int32_t* overflow_flag, void* stream);
 /* vs_rrr_closure for an exact-operand split; all epilogue sums are float64 */
 int vs_rrr_closure_exact(vs_rrr_dims d, const uint16_t* Xa, const vs_rrr_exact_ops* ops, const float* xl, const float* y,
                          const double* U, const double* V, const double* b, double l2, double* loss, double* sse_n,

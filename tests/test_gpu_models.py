@@ -685,3 +685,35 @@ def test_rrr_default_mode_full_size_fit_within_tolerance(vs, cuda):
     ev, ev_o = ro.eval_session(pred.cpu().numpy(), gt), ro.eval_session(ref["pred_test_fr"], gt)
     assert ev["co_bps"] == pytest.approx(ev_o["co_bps"], rel=1e-3, abs=2e-5), (ev["co_bps"], ev_o["co_bps"])
     assert ev["r2"] == pytest.approx(ev_o["r2"], rel=1e-3, abs=2e-5), (ev["r2"], ev_o["r2"])
+
+
+@pytest.mark.parametrize("mode", ["exact", "dense"])
+@pytest.mark.parametrize("K,F", [(37, 200), (400, 18260 // 4)])
+def test_fused_loader_matches_two_kernel_path(vs, cuda, monkeypatch, mode, K, F):
+    """vs_rrr_pack_u8_fused (one read of the frames: statistics + pack per time bin, 128-bit loads and stores) against
+    vs_rrr_colstats + vs_rrr_pack_u8_exact: statistics and every operand bit for bit."""
+    from model.rrr import pack_session_from_frames
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=7, K=K, Kt=11, F=F, N=16, raw=True)
+    args = (torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(Xte), torch.from_numpy(yte), sidx, 3)
+    monkeypatch.setenv("VS_RRR_FUSED_PACK", "1")
+    a = pack_session_from_frames(*args, device=cuda, mode=mode)
+    monkeypatch.setenv("VS_RRR_FUSED_PACK", "0")
+    b = pack_session_from_frames(*args, device=cuda, mode=mode)
+    torch.cuda.synchronize()
+    for k in ("mean_X_Tv", "std_X_Tv"):
+        sel = torch.as_tensor(np.asarray(sidx), device=cuda).long()
+        assert torch.equal(a["setup"][k].view(120, F)[sel], b["setup"][k].view(120, F)[sel]), k
+    for which in (0, 1):
+        sa, sb = a["X"][which], b["X"][which]
+        sa.wait_ready(); sb.wait_ready()
+        C1 = sa.C1
+        if mode == "exact":
+            assert torch.equal(sa.Xa[:, :, :C1].view(torch.int16), sb.Xa[:, :, :C1].view(torch.int16))
+        else:
+            assert torch.equal(sa.exact["Xc"][:, :C1].view(torch.int16), sb.exact["Xc"][:, :C1].view(torch.int16))
+        if which == 0:
+            Kp = (sa.K + 15) // 16 * 16
+            assert torch.equal(sa.Xb[:, :sa.T * Kp].view(torch.int16), sb.Xb[:, :sa.T * Kp].view(torch.int16))
+            for k in ("isdT", "qT"):
+                assert torch.equal(sa.exact[k], sb.exact[k]), k
+        assert torch.equal(sa.xl, sb.xl)

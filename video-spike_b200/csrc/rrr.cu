@@ -347,6 +347,169 @@ __global__ void __launch_bounds__(256) pack_u8_exact_kernel(const uint8_t* __res
   }
 }
 
+// ------------------------------------------------------------------ fused R0 loader: statistics + pack, ONE read of the frames
+// Block (t, 128-feature chunk): the K trials of one selected frame's chunk (K x 128 bytes, 51 KB at K = 400) are staged in
+// shared memory with 128-bit global loads; the exact integer column sums give mean / clipped std (src/utils/utils.py:107-112,
+// kStats: train split) or the caller's statistics are read (other splits); then every operand of the split is produced from
+// the staged bytes with 128-bit stores:
+//   Xa : z as hi + lo half planes          (EXACT mode)     row t*K + k, 8 features per store
+//   Xc : the exact integers, same layout   (DENSE mode)
+//   Xi : the exact integers transposed     (train split)    row c, 8 trials per store (a feature row receives its whole
+//                                                           bin -- K contiguous values -- from one block), pad trials zeroed
+// The old path read the frames twice (colstats_kernel at 0.26 of the HBM peak, then the pack at 0.49) and wrote the
+// transposed operand in 64-byte pieces.  Requires C1 % 4 == 0 (row starts are then 4-byte aligned: the 16-byte global words
+// are shifted into place by whole 32-bit lanes) and K * 128 bytes of shared memory; other shapes use the two-kernel path.
+template <bool kStats>
+__global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ sorted_idx,
+                                                         double* __restrict__ mean, double* __restrict__ sd, long long Tf, long long K,
+                                                         long long T, long long C1, long long ldc, long long ldr, uint16_t* __restrict__ Xa,
+                                                         uint16_t* __restrict__ Xc, uint16_t* __restrict__ Xi, float* __restrict__ xl,
+                                                         int* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t raw[];            // [K][128]
+  __shared__ float s_m[128], s_dl[128], s_istd[128];
+  __shared__ unsigned long long s_s1[2][128], s_s2[2][128];
+  __shared__ bool s_const[128];
+  const long long t = blockIdx.x, c0 = (long long)blockIdx.y * 128, Kp = (K + 15) / 16 * 16;
+  const long long f = sorted_idx[t];
+  const long long pa = K * T * ldc;
+  // ---- phase 1: stage the chunk.  9 aligned 16-byte words cover 128 bytes at any 4-byte shift; 28 rows per pass
+  {
+    const int wq = threadIdx.x % 9, rr = threadIdx.x / 9;
+    for (long long k = rr; k < K && rr < 28; k += 28) {
+      const uint8_t* rowp = frames + (k * Tf + f) * C1 + c0;
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(rowp) & ~(uintptr_t)15;
+      const uint8_t* wp = reinterpret_cast<const uint8_t*>(a0) + 16 * wq;
+      const long long off = wp - rowp;                         // position of this word's first byte inside the chunk: multiple of 4
+      if (off > -16 && off < 128) {
+        // the word may reach before the chunk / past the end of the row (never past the allocation for interior rows; the
+        // last row of the buffer is guarded by reading only words that start inside the row)
+        const bool safe = (c0 + off >= 0) && (c0 + off + 16 <= C1);
+        uint32_t v[4];
+        if (safe) {
+          const uint4 u = ld_stream_u4(reinterpret_cast<const uint4*>(wp));
+          v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long cc = c0 + off + 4 * i;
+            v[i] = (cc >= 0 && cc + 4 <= C1) ? __ldg(reinterpret_cast<const uint32_t*>(wp + 4 * i)) : 0u;
+          }
+        }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(raw + k * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long p = off + 4 * i;
+          if (p >= 0 && p < 128) dst[p >> 2] = v[i];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 1b: statistics of the 128 columns (two threads per column over the trial parities; integer sums are exact)
+  {
+    const int c = threadIdx.x & 127, par = threadIdx.x >> 7;
+    if constexpr (kStats) {
+      unsigned long long s1 = 0, s2 = 0;
+      for (long long k = par; k < K; k += 2) {
+        const unsigned v = raw[k * 128 + c];
+        s1 += v; s2 += v * v;
+      }
+      s_s1[par][c] = s1; s_s2[par][c] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const long long cg = c0 + c;
+      double m = 0.0, sdev = 1.0;
+      if (cg < C1) {
+        const long long col = f * C1 + cg;
+        if constexpr (kStats) {
+          const double s1 = (double)(s_s1[0][c] + s_s1[1][c]), s2 = (double)(s_s2[0][c] + s_s2[1][c]);
+          m = s1 / (double)K;
+          const double var = ((double)K * s2 - s1 * s1) / ((double)K * (double)K);     // exact integer moments
+          sdev = sqrt(var > 0.0 ? var : 0.0);
+          sdev = sdev < 1e-8 ? 1e-8 : sdev;
+          mean[col] = m; sd[col] = sdev;
+        } else {
+          m = mean[col]; sdev = sd[col];
+        }
+      }
+      const double mi = rint(m);
+      s_m[c] = (float)mi; s_dl[c] = (float)(m - mi); s_istd[c] = (float)(1.0 / sdev); s_const[c] = !(sdev > 1e-8);
+    }
+    __syncthreads();
+  }
+  // ---- phase 2a: row-major operands, 8 features (one 128-bit store) per thread: 16 threads per trial row
+  bool ovf = false;
+  if (Xa || Xc) {
+    const int q8 = (threadIdx.x & 15) * 8, r16 = threadIdx.x >> 4;
+    for (long long k = r16; k < K; k += 16) {
+      const long long c = c0 + q8;
+      if (c >= C1) continue;
+      const uint2 b8 = *reinterpret_cast<const uint2*>(raw + k * 128 + q8);
+      uint32_t hi[4], lo[4], xi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float xc[2], zf[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = 2 * i + e;
+          const unsigned byte = ((j < 4 ? b8.x : b8.y) >> (8 * (j & 3))) & 0xff;
+          const bool in = c + j < C1;
+          xc[e] = in ? (float)byte - s_m[q8 + j] : 0.f;
+          zf[e] = in ? (xc[e] - s_dl[q8 + j]) * s_istd[q8 + j] : 0.f;
+          if (in && (Xa ? !(fabsf(zf[e]) <= 65504.f) : (s_const[q8 + j] && xc[e] != 0.f))) ovf = true;
+        }
+        const __half2 h = __floats2half2_rn(zf[0], zf[1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(zf[0] - hf.x, zf[1] - hf.y);
+        const __half2 x = __floats2half2_rn(xc[0], xc[1]);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h); lo[i] = *reinterpret_cast<const uint32_t*>(&l); xi[i] = *reinterpret_cast<const uint32_t*>(&x);
+      }
+      const long long o = (t * K + k) * ldc + c;             // ldc % 64 == 0, c % 8 == 0: 16-byte aligned; the pad columns c >= C1 stay unread
+      if (Xa) {
+        *reinterpret_cast<uint4*>(Xa + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(Xa + pa + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      if (Xc) *reinterpret_cast<uint4*>(Xc + o) = make_uint4(xi[0], xi[1], xi[2], xi[3]);
+    }
+  }
+  // ---- phase 2b: transposed integer operand.  Thread = (4 features, 8 trials): 8 conflict-free 32-bit shared-memory reads, four
+  // 128-bit stores (one per feature row; the neighbouring 8-trial groups of a row come from the same block, so L2 merges
+  // the half sectors before they reach DRAM); pad trials K <= k < Kp are written as zeros
+  if (Xi) {
+    const long long ngrp = Kp / 8;
+    for (long long e = threadIdx.x; e < 32 * ngrp; e += 256) {
+      const int c4 = (int)(e & 31) * 4;
+      const long long k8 = (e >> 5) * 8;
+      uint32_t wd[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < K) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * 128 + c4) : 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (c0 + c4 + i >= C1) continue;
+        const float m = s_m[c4 + i];
+        uint32_t w[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float a[2];
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int j = 2 * jj + e2;
+            a[e2] = (k8 + j < K) ? (float)((wd[j] >> (8 * i)) & 0xff) - m : 0.f;
+            if (s_const[c4 + i] && a[e2] != 0.f) ovf = true;
+          }
+          const __half2 x = __floats2half2_rn(a[0], a[1]);
+          w[jj] = *reinterpret_cast<const uint32_t*>(&x);
+        }
+        *reinterpret_cast<uint4*>(Xi + (c0 + c4 + i) * ldr + t * Kp + k8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  if (ovf && overflow) atomicOr(overflow, 1);
+  if (blockIdx.y == 0)
+    for (long long k = threadIdx.x; k < K; k += 256) xl[t * K + k] = 1.0f;
+}
+
 // zeros in the pad trials K <= k < Kp of every time bin of Xb (one thread per (plane, c, t))
 __global__ void __launch_bounds__(256) pad_zero_kernel(uint16_t* __restrict__ Xb, long long rows, long long T, long long K, long long Kp,
                                                        long long ldr) {
@@ -1292,7 +1455,7 @@ static int closure_dense(const vs_rrr_dims& d, const uint16_t* Xi, const ExactAr
   VS_LAUNCH(small_mats_kernel, r * r + 1, 256, 0, st, w.Gp, w.gp_blocks, V, r, (long long)d.T, w.G, w.W);
   dim3 ge((unsigned)w.KB, (unsigned)d.T, (unsigned)ceil_div(d.N, 32));
   VS_LAUNCH((epi_d_kernel<false>), ge, 256, 0, st, w.Z, w.Npad, w.M1, w.ldm, y, ex.y_lo, xl, V, b, (long long)d.K, (long long)d.T, (long long)d.N,
-            w.Npad, r, (long long)d.ldr, dU ? w.RV : (uint16_t*)nullptr, (double*)w.sse_part, (double*)w.db_part, (double*)nullptr, w.Kp);
+            w.Npad, r, (long long)d.ldr, (dU || dV) ? w.RV : (uint16_t*)nullptr, (double*)w.sse_part, (double*)w.db_part, (double*)nullptr, w.Kp);
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
   VS_LAUNCH(reduce_part_kernel<double>, g2, 128, 0, st, (const double*)w.sse_part, (const double*)w.db_part, b, w.KB, (long long)d.T,
             (long long)d.N, l2, db, w.sse_tn, w.SR, w.Npad);
@@ -1467,6 +1630,52 @@ extern "C" int vs_rrr_pack_u8_exact(const uint8_t* frames, int64_t Tf, const int
   }
   if (out->isd) {
     VS_REQUIRE(out->qh && out->isdmax, VS_ERR_INVALID, "vs_rrr_pack_u8_exact: isd, qh and isdmax go together");
+    const long long Tq = round_up(d.T, 16);
+    VS_CHECK_CUDA(cudaMemsetAsync(const_cast<float*>(out->isdmax), 0, (size_t)d.T * 4, (cudaStream_t)stream));
+    VS_LAUNCH(exact_stats2_kernel, (unsigned)ceil_div(Tq * d.ldc, 256), 256, 0, stream, sorted_idx, mean, std_clipped, (long long)d.T, Tq,
+              (long long)d.C1, (long long)d.ldc, const_cast<float*>(out->isd), const_cast<uint16_t*>(out->qh),
+              reinterpret_cast<unsigned*>(const_cast<float*>(out->isdmax)));
+  }
+  return VS_OK;
+}
+
+// Fused R0 loader (pack_fused_kernel): ONE read of the frames per split.  compute_stats != 0 (train split): mean / std_clipped
+// of the SELECTED frames sorted_idx[t] are computed and written (rows of the (Tf, C1) tables that are not selected are left
+// untouched); compute_stats == 0: they are read.  Same outputs as vs_rrr_pack_u8_exact.
+extern "C" int vs_rrr_pack_u8_fused(const uint8_t* frames, int64_t Tf, const int32_t* sorted_idx, double* mean, double* std_clipped,
+                                    int compute_stats, vs_rrr_dims d, uint16_t* Xa, const vs_rrr_exact_ops* out, float* xl,
+                                    int32_t* overflow_flag, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT || d.mode == VS_RRR_MODE_DENSE, VS_ERR_INVALID, "vs_rrr_pack_u8_fused: dims.mode must be an exact-operand mode");
+  VS_REQUIRE(frames && sorted_idx && mean && std_clipped && out && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8_fused: bad arguments");
+  VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT ? Xa != nullptr : out->Xc != nullptr, VS_ERR_INVALID,
+             "vs_rrr_pack_u8_fused: the forward operand of the mode is missing (Xa for EXACT, ops.Xc for DENSE)");
+  const size_t smem = (size_t)d.K * 128;
+  VS_REQUIRE(d.C1 % 4 == 0 && ((uintptr_t)frames & 3) == 0 && smem <= 200 * 1024, VS_ERR_UNSUPPORTED,
+             "vs_rrr_pack_u8_fused: needs C1 %% 4 == 0, 4-byte aligned frames and K <= 1600 (use vs_rrr_colstats + vs_rrr_pack_u8_exact)");
+  uint16_t* Xi = const_cast<uint16_t*>(out->Xi);
+  uint16_t* Xc = d.mode == VS_RRR_MODE_DENSE ? const_cast<uint16_t*>(out->Xc) : nullptr;
+  uint16_t* Xz = d.mode == VS_RRR_MODE_EXACT ? Xa : nullptr;
+  dim3 grid((unsigned)d.T, (unsigned)ceil_div(d.C1, 128));
+  VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8_fused: too many columns");
+  if (compute_stats) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(pack_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH(pack_fused_kernel<true>, grid, 256, smem, stream, frames, sorted_idx, mean, std_clipped, (long long)Tf, (long long)d.K,
+              (long long)d.T, (long long)d.C1, (long long)d.ldc, (long long)d.ldr, Xz, Xc, Xi, xl, overflow_flag);
+  } else {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(pack_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH(pack_fused_kernel<false>, grid, 256, smem, stream, frames, sorted_idx, mean, std_clipped, (long long)Tf, (long long)d.K,
+              (long long)d.T, (long long)d.C1, (long long)d.ldc, (long long)d.ldr, Xz, Xc, Xi, xl, overflow_flag);
+  }
+  if (out->isdT) {
+    const long long ldt = round_up(d.T, 4);
+    VS_REQUIRE(out->ldt == ldt && out->qT, VS_ERR_INVALID, "vs_rrr_pack_u8_fused: ops.ldt must be vs_rrr_ldt(T); isdT and qT go together");
+    VS_LAUNCH(exact_stats_kernel, (unsigned)ceil_div(d.C1 * ldt, 256), 256, 0, stream, sorted_idx, mean, std_clipped, (long long)d.T,
+              (long long)d.C1, ldt, const_cast<float*>(out->isdT), const_cast<float*>(out->qT));
+  }
+  if (out->isd) {
+    VS_REQUIRE(out->qh && out->isdmax, VS_ERR_INVALID, "vs_rrr_pack_u8_fused: isd, qh and isdmax go together");
     const long long Tq = round_up(d.T, 16);
     VS_CHECK_CUDA(cudaMemsetAsync(const_cast<float*>(out->isdmax), 0, (size_t)d.T * 4, (cudaStream_t)stream));
     VS_LAUNCH(exact_stats2_kernel, (unsigned)ceil_div(Tq * d.ldc, 256), 256, 0, stream, sorted_idx, mean, std_clipped, (long long)d.T, Tq,

@@ -577,11 +577,16 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                     fr = fr[:, idx.long()].contiguous()
                     Tf_dev, idx_dev = T, idx_compact
             cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
+            # fused loader (one read of the frames: statistics + pack per time bin) when every frame on the device is a
+            # selected one; otherwise the two-kernel path (statistics of all Tf frames, then the pack)
+            fused = (exact and Tf_dev == T and F % 4 == 0 and K * 128 <= 200 * 1024 and fr.data_ptr() % 4 == 0
+                     and os.environ.get("VS_RRR_FUSED_PACK", "1") != "0")
             if which == 0:
                 compact_stats = Tf_dev == T and Tf != T
                 mean = torch.empty(Tf_dev * F, dtype=torch.float64, device=device)
                 sd = torch.empty_like(mean)
-                vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf_dev * F, vs.ptr(mean), vs.ptr(sd), st))
+                if not fused:
+                    vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf_dev * F, vs.ptr(mean), vs.ptr(sd), st))
                 sm = torch.empty_like(cnt)
                 vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
                 my = torch.empty(T * N, dtype=torch.float64, device=device)
@@ -593,9 +598,14 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                 tw = (lambda k: vs.ptr(ex[k]) if (which == 0 and k in ex) else None)      # tables are written with the train split only
                 out = vs.RrrExactOps(vs.ptr(Xb) if Xb is not None else None, tw("isdT"), tw("qT"), ldt, None,
                                      vs.ptr(ex["Xc"]) if dense else None, tw("isd"), tw("qh"), tw("isdmax"))
-                vs.check(vs.lib.vs_rrr_pack_u8_exact(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d,
-                                                     vs.ptr(Xa) if Xa is not None else None, ctypes.byref(out), vs.ptr(xl),
-                                                     vs.ptr(overflow), st))
+                if fused:
+                    vs.check(vs.lib.vs_rrr_pack_u8_fused(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), int(which == 0), d,
+                                                         vs.ptr(Xa) if Xa is not None else None, ctypes.byref(out), vs.ptr(xl),
+                                                         vs.ptr(overflow), st))
+                else:
+                    vs.check(vs.lib.vs_rrr_pack_u8_exact(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d,
+                                                         vs.ptr(Xa) if Xa is not None else None, ctypes.byref(out), vs.ptr(xl),
+                                                         vs.ptr(overflow), st))
                 vs.check(vs.lib.vs_rrr_smooth_y2(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y),
                                                  vs.ptr(ex["y_lo"]), st))
             else:

@@ -102,6 +102,7 @@ def _load():
         "vs_rrr_ldt": (i64, [i64]),
         "vs_rrr_exact_supported": (C.c_int, [i64, i64, i64, i64, i64]),
         "vs_rrr_pack_u8_exact": (C.c_int, [vp, i64, vp, vp, vp, RrrDims, vp, C.POINTER(RrrExactOps), vp, vp, vp]),
+        "vs_rrr_pack_u8_fused": (C.c_int, [vp, i64, vp, vp, vp, i32, RrrDims, vp, C.POINTER(RrrExactOps), vp, vp, vp]),
         "vs_rrr_closure_exact": (C.c_int, [RrrDims, vp, C.POINTER(RrrExactOps), vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, sz, vp]),
         "vs_rrr_predict_exact": (C.c_int, [RrrDims, C.POINTER(RrrExactOps), vp, vp, vp, vp, vp, vp, sz, vp]),
         "vs_colstats_f32": (C.c_int, [vp, i64, i64, vp, vp, vp]),
