@@ -59,8 +59,14 @@ def peaks():
 def ncu_traffic(key, field="bytes_per_launch_avg"):
     """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
-            ent = json.load(fh).get(key)
+        ent = None
+        for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                with open(path) as fh:
+                    ent = json.load(fh).get(key)
+            if ent:
+                break
         return int(ent[field]) if ent and field in ent else None            # bytes per launch
     except Exception:
         return None
@@ -287,14 +293,20 @@ def reference_arm(args, rank, world):
 
 # ----------------------------------------------------------------------------- configs
 def rrr_mode_of(args):
-    return "classic" if (args.mode == "classic" or (args.mode is None and args.planes is not None)) else "exact"
+    if args.mode == "classic" or (args.mode is None and args.planes is not None):
+        return "classic"
+    return args.mode or os.environ.get("VS_RRR_MODE") or "exact"
 
 
 def rrr_config(args, world):
-    exact = rrr_mode_of(args) == "exact"
+    mode = rrr_mode_of(args)
+    exact = mode in ("exact", "dense")
     joint = world > 1 and not args.independent
     planes = 2 if exact else (args.planes or 1)
-    if exact:
+    if mode == "dense":
+        fmt = ("dense: both contractions per time bin on the exact integer frames (half): forward x hi+lo coefficient planes generated on chip, "
+               "backward and dV pass x hi+lo residual planes; fp32 accumulate in TMEM, float64 epilogues")
+    elif exact:
         fmt = ("exact: forward operand = z-score as hi+lo IEEE-half planes (3 plane products), backward operand = exact integer frames "
                "(half) x hi+lo residual planes, fp32 accumulate in TMEM, float64 epilogues")
     else:
@@ -303,7 +315,7 @@ def rrr_config(args, world):
     return {"workload": "rrr_joint_fit, shared V across sessions (BASELINE configs[2])" if joint else "rrr_single_session_fit (BASELINE configs[1])",
             "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
-            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_mode": "exact" if exact else "classic", "operand_planes": planes,
+            "neurons": args.neurons, "rank": 3, "l2": 100, "operand_mode": mode, "operand_planes": planes,
             "operand_format": fmt,
             "lbfgs": f"1 step, max_iter 20 (20 closure evals), history {hist}, "
                      + ("device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else "host-driven")
@@ -449,40 +461,63 @@ def run_rrr(args, rank, world, local):
     evals = (model.n_closure_evals - evals0) / args.steps
     value = world * K * FRAMES_PER_TRIAL / (ms * 1e-3)
 
-    # roofline of the dominant kernel (the forward tcgen05 GEMM, Z = X U): algorithmic FLOPs (2*K*T*C*N per
-    # contraction, i.e. the dense formulation) summed over the launches of the timed region / their summed duration.
-    # With VS_RRR_DENSE=0 the factorised backward GEMM runs under the same tag and is counted the same way.
+    # roofline of the dominant kernels: algorithmic FLOPs (2*K*T*C*N per contraction, i.e. the dense formulation)
+    # or bytes, summed over the launches of the timed region / their summed event-bracketed duration.
     C = F + 1
     Np16 = (N + 15) // 16 * 16
-    plane_passes = 1 if model_planes == 1 else (3 if model_planes == 2 else 6)
-    n_contr = 1 if n_bwd > 0 else 2                             # contractions per closure evaluation under tag 0
-    algo_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * C * N) + 2.0 * Kt * 100 * C * N)
-    exec_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * F * 3 * Np16) + 2.0 * Kt * 100 * F * 3 * Np16) * plane_passes
+    Kp = (K + 15) // 16 * 16
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    key = f"rrr_K{K}_F{F}_N{N}_planes{model_planes}" + ("_exact" if mode == "exact" else "")
-    roof = {"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (forward Z = X U; tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair"
-                                         + (f"; {plane_passes} plane products per launch)" if plane_passes > 1 else ")"),
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-            "traffic": ncu_traffic(key), "traffic_unit": "bytes/launch (ncu dram read+write of an EARLIER run of this command, profiles/; not measured in this run)",
-            "peak_source": f"{pk_kind} bf16_tflops_sustained",
-            "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
-            "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
-            "note": "achieved counts ALGORITHMIC flops of the dense formulation (2*K*T*C*N per contraction); the factorised forward executes "
-                    f"r=3x that per plane product and {plane_passes} plane product(s) (executed_tflops)"}
+    key = f"rrr_K{K}_F{F}_N{N}_" + (mode if mode != "classic" else f"planes{model_planes}")
+    tu = "bytes/launch (ncu dram read+write of an EARLIER run of this command, profiles/r02_ncu_traffic.json; not measured in this run)"
+    r_planes = 2 if mode in ("exact", "dense") else 1
+    bwd_bytes = 2.0 * F * 100 * Kp + 2.0 * r_planes * Np16 * 100 * Kp + 4.0 * F * 3 * Np16      # operand + R planes + G out
+    blocks = []
+    if mode == "dense":
+        n_fwd, fwd_ms, _, _ = vs.profile_read(3)              # rrr_fwd_dense_pair_kernel: train closures + the evaluation split
+        n_dv, dv_ms, _, _ = vs.profile_read(4)                # dV pass of the dense backward kernel
+        fl = args.steps * (evals * 2.0 * K * 100 * F * N + 2.0 * Kt * 100 * F * N)
+        ach = fl / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
+        blocks.append({"bound": "tensor", "kernel": "vs::tc::rrr_fwd_dense_pair_kernel (yhat_t = Xc_t beta'_t^T per time bin: exact integer A by TMA, hi+lo "
+                                                    "coefficient tiles generated on chip, tcgen05 cta_group::2 UMMA 256xN, 3 bins per CTA pair)",
+                       "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                       "traffic": ncu_traffic(key, "fwd_bytes_per_launch"), "traffic_unit": tu, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+                       "launches": n_fwd, "avg_launch_ms": fwd_ms / max(n_fwd, 1), "share_of_step": fwd_ms / (ms * args.steps),
+                       "executed_tflops": 2.0 * ach * (256.0 * ((K + 255) // 256) / K),
+                       "hbm_view": {"algorithmic_bytes_per_launch": 2.0 * K * 100 * F, "achieved_gbs": 2.0 * K * 100 * F * args.steps * evals / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0,
+                                    "peak_gbs": pk["hbm_gbs"]},
+                       "note": "achieved counts the ALGORITHMIC flops 2*K*T*C*N once; the kernel executes two plane products (hi, lo) on 256-row tiles (executed_tflops)"})
+        if n_dv > 0:
+            bw = bwd_bytes * n_dv / (dv_ms * 1e-3) / 1e9
+            blocks.append({"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel<dV> (dV: the D_t = Xc_t^T R_t tiles contracted with the U slab held in registers/TMEM)",
+                           "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"], "traffic": ncu_traffic(key, "dv_bytes_per_launch"),
+                           "launches": n_dv, "avg_launch_ms": dv_ms / n_dv, "share_of_step": dv_ms / (ms * args.steps)})
+    else:
+        plane_passes = 1 if model_planes == 1 else (3 if model_planes == 2 else 6)
+        n_contr = 1 if n_bwd > 0 else 2                             # contractions per closure evaluation under tag 0
+        algo_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * C * N) + 2.0 * Kt * 100 * C * N)
+        exec_flops = args.steps * (evals * n_contr * (2.0 * K * 100 * F * 3 * Np16) + 2.0 * Kt * 100 * F * 3 * Np16) * plane_passes
+        ach = algo_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        blocks.append({"bound": "tensor", "kernel": "vs::tc::gemm_tn_pair_kernel (forward Z = X U; tcgen05 cta_group::2 kind::f16, UMMA 256xN over a CTA pair"
+                                                    + (f"; {plane_passes} plane products per launch)" if plane_passes > 1 else ")"),
+                       "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                       "traffic": ncu_traffic(key), "traffic_unit": tu, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+                       "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
+                       "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
+                       "note": "achieved counts ALGORITHMIC flops of the dense formulation (2*K*T*C*N per contraction); the factorised forward executes "
+                               f"r=3x that per plane product and {plane_passes} plane product(s) (executed_tflops)"})
     if n_bwd > 0:
-        # second kernel of the closure: the per-time-bin dense backward streams the backward operand once
-        Kp = (K + 15) // 16 * 16
-        r_planes = 2 if mode == "exact" else 1
-        bwd_bytes = 2.0 * F * 100 * Kp + 2.0 * r_planes * Np16 * 100 * Kp + 4.0 * F * 3 * Np16      # operand + R planes + G out
         bw = bwd_bytes * n_bwd / (bwd_ms * 1e-3) / 1e9
-        roof["backward"] = {"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel (dU: D_t = X_t^T R_t per time bin in TMEM, rank-one updates in registers"
-                                                      + ("; exact integer operand x hi+lo residual planes)" if mode == "exact" else ")"),
-                            "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"],
-                            "traffic": ncu_traffic(key, "bwd_bytes_per_launch"), "launches": n_bwd, "avg_launch_ms": bwd_ms / n_bwd,
-                            "share_of_step": bwd_ms / (ms * args.steps),
-                            "algorithmic_tflops": 2.0 * K * 100 * C * N * n_bwd / (bwd_ms * 1e-3) / 1e12}
+        blocks.append({"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel (dU: D_t = X_t^T R_t per time bin in TMEM, rank-one updates in registers"
+                                                 + ("; exact integer operand x hi+lo residual planes)" if r_planes == 2 else ")"),
+                       "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"],
+                       "traffic": ncu_traffic(key, "bwd_bytes_per_launch"), "launches": n_bwd, "avg_launch_ms": bwd_ms / n_bwd,
+                       "share_of_step": bwd_ms / (ms * args.steps),
+                       "algorithmic_tflops": 2.0 * K * 100 * C * N * n_bwd / (bwd_ms * 1e-3) / 1e12})
+    # the top-level object is the kernel with the largest share of the step; the others ride along under "other_kernels"
+    blocks.sort(key=lambda x: -x["share_of_step"])
+    roof = blocks[0]
+    roof["other_kernels"] = blocks[1:]
 
     # ---- parity of the timed configuration (outside every timed region) against an INDEPENDENT float64 dense fit on the
     # GPU (the reference's formulation in torch: einsum + autograd + torch.optim.LBFGS), same session
@@ -753,7 +788,8 @@ def main():
     ap.add_argument("--trials-test", dest="trials_test", type=int, default=80)
     ap.add_argument("--features", type=int, default=110 * 166)
     ap.add_argument("--neurons", type=int, default=144)
-    ap.add_argument("--mode", default=None, choices=["exact", "classic"], help="rrr operand mode (default exact; --planes implies classic)")
+    ap.add_argument("--mode", default=None, choices=["exact", "dense", "classic"],
+                    help="rrr operand mode (default: VS_RRR_MODE or exact; --planes implies classic)")
     ap.add_argument("--planes", type=int, default=None, help="rrr classic mode: residual planes of the 16-bit operands")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--input-dim", dest="input_dim", type=int, default=120 * 128 * 128)

@@ -660,7 +660,9 @@ def test_rrr_exact_mode_whole_fit_small_vs_oracle(vs, cuda, mode):
     assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=1e-5)
     _, _, pred = model.predict_y_fr(td, "session", 1)
     _, _, pred_o = ro.predict_y_fr(p_o, td_o, "session", 1)
-    np.testing.assert_allclose(pred.cpu().numpy(), pred_o, rtol=1e-4, atol=1e-6)
+    # single predictions: the un-line-searched fit amplifies the last bits of a closure evaluation by 3-4 orders of magnitude
+    # (DESIGN.md "RRR precision"), so elementwise agreement is looser than that of the sums BASELINE.json puts a tolerance on
+    np.testing.assert_allclose(pred.cpu().numpy(), pred_o, rtol=2e-3, atol=1e-3)
     ev, ev_o = ro.eval_session(pred.cpu().numpy(), gt), ro.eval_session(pred_o, gt)
     assert ev["co_bps"] == pytest.approx(ev_o["co_bps"], rel=1e-3, abs=1e-6)
     assert ev["r2"] == pytest.approx(ev_o["r2"], rel=1e-3, abs=1e-6)

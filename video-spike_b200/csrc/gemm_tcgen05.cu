@@ -979,7 +979,7 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     for (int t = 0; t < p.T; ++t) {
       const int buf = t & 1;
       if (sct && (t & 3) == 0) sc4 = __ldg(reinterpret_cast<const float4*>(sct + t));      // ldt % 4 == 0, rows padded to ldt
-      const float sc = (t & 3) == 0 ? sc4.x : ((t & 3) == 1 ? sc4.y : ((t & 3) == 2 ? sc4.z : sc4.w));
+      float sc = (t & 3) == 0 ? sc4.x : ((t & 3) == 1 ? sc4.y : ((t & 3) == 2 ? sc4.z : sc4.w));
       mbar_wait(bar_dfull0 + 8u * buf, (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const float v0 = vsm[t] * sc, v1 = vsm[p.T + t] * sc, v2 = vsm[2 * p.T + t] * sc;
@@ -1025,7 +1025,8 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           for (int i = 0; i < kN; ++i) {
             if (i < 8 || two) {
               const int col = (c * 8 + i) < W ? (c * 8 + i) : 0;
-              const float dv = __uint_as_float(d[slot][i]);
+              // columns past N hold whatever the pad rows of the residual operand contain (never written): 0 * NaN must not happen
+              const float dv = (hsel * W + c * 8 + i) < p.N ? __uint_as_float(d[slot][i]) : 0.f;
               p0 = fmaf(__uint_as_float(a0[slot][i]), dv, p0);
               p1 = fmaf(g1[col], dv, p1);
               p2 = fmaf(g2[col], dv, p2);
@@ -1036,7 +1037,9 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             if (r + 2 == kRounds) release_d();
           }
         }
-        // the 1/std of this row and bin (sc), then the sum over the warp's 32 feature rows
+        // the 1/std of this row and bin (sc), then the sum over the warp's 32 feature rows.  Rows past C1 do not exist: a
+        // phantom second tile of the last pair (odd tile count) re-reads the last real tile and must not be counted twice
+        if (m_tile * BM + q * 32 + lane >= p.C1) sc = 0.f;
         p0 *= sc; p1 *= sc; p2 *= sc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
