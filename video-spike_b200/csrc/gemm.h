@@ -69,8 +69,11 @@ struct DenseFwdDesc {
   long long ldu = 0;            // multiple of 64, >= C1
   const double* V = nullptr;    // (3, T)
   const float* bscale = nullptr;  // [T] power-of-two scales of the generated tiles
-  float* Y = nullptr;           // (K*T, ldy) fp32
+  float* Y = nullptr;           // (K*T, ldy) fp32; with splits > 1: `splits` partial matrices at split_stride elements
   long long ldy = 0;
+  int splits = 1;               // accumulation runs over the feature dimension (bounds the fp32 TMEM truncation drift)
+  long long split_stride = 0;
+  int* splits_out = nullptr;
 };
 bool rrr_fwd_dense_supported(const DenseFwdDesc& g);
 int rrr_fwd_dense(const DenseFwdDesc& g, cudaStream_t stream);

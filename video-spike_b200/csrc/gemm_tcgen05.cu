@@ -1130,6 +1130,8 @@ struct DenseFwdParams {
   int K, T, C1, N, Npad;
   int n_rt;                  // 256-trial row tiles per time bin
   int num_kb;                // 64-feature k-blocks
+  int kb_per_split;          // k-blocks per accumulation run (blockIdx.y selects the run; its partial goes to Y + run * split_stride)
+  long long split_stride;
   const float* U32;          // [N][ldu][3] fp32, zero past C1
   const float* isd;          // [T][ldu] fp32: 1/std[t,c], zero past C1
   long long ldu;
@@ -1169,6 +1171,11 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
   const int t0 = grp * FWD_BINS;
   const int nbins = (p.T - t0) < FWD_BINS ? (p.T - t0) : FWD_BINS;
   const int row0 = rt * 256 + rank * BM;                       // first trial of this CTA's 128 rows
+  // accumulation run of this CTA pair: the fp32 accumulator is truncated at every MMA, so a long contraction drifts by
+  // ~(#MMA steps) * 2^-24 of its running magnitude; the host splits the 18,260-feature contraction into a few runs whose
+  // partial tiles the epilogue kernel adds in float64
+  const int kb0 = (int)blockIdx.y * p.kb_per_split;
+  const int kb1 = (kb0 + p.kb_per_split) < p.num_kb ? (kb0 + p.kb_per_split) : p.num_kb;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -1194,7 +1201,7 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
     // ===== TMA producer: this CTA's 128 trials of each of the bins, one 64-feature box per bin and k-block =====
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = 0; kb < p.num_kb; ++kb) {
+    for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
       if (elect_one()) {
         if (rank == 0) mbar_arrive_expect_tx(bar_fullA0 + 8u * s, 2u * (uint32_t)nbins * A_TILE_BYTES);
@@ -1213,7 +1220,7 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
       const uint32_t stage16 = stage_bytes >> 4, a16 = A_TILE_BYTES >> 4, b16 = b_bytes >> 4, boff16 = (FWD_BINS * A_TILE_BYTES) >> 4;
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_fullA0 + 8u * s, ph);
         mbar_wait(bar_fullB0 + 8u * s, ph);
         tc_fence_after();
@@ -1225,12 +1232,12 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
             const uint32_t dcol = tmem_base + (uint32_t)(b * p.Npad);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              tc_mma_pair(dcol, da + (uint64_t)(k * 2), dl + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              tc_mma_pair(dcol, da + (uint64_t)(k * 2), dl + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
               tc_mma_pair(dcol, da + (uint64_t)(k * 2), dh + (uint64_t)(k * 2), idesc, 1u);
             }
           }
           tc_commit_pair(bar_empty0 + 8u * s);
-          if (kb == p.num_kb - 1) tc_commit_pair(bar_done);
+          if (kb == kb1 - 1) tc_commit_pair(bar_done);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -1252,7 +1259,7 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
     const uint32_t fullB_leader0 = mapa_cluster(bar_fullB0, 0);
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = 0; kb < p.num_kb; ++kb) {
+    for (int kb = kb0; kb < kb1; ++kb) {
       const long long c0 = (long long)kb * 64 + q * 8;
       // 1/std of the 8 features of this chunk, per bin
       float4 sa[FWD_BINS][2];
@@ -1316,7 +1323,7 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
     for (int b = 0; b < nbins; ++b) {
       const float inv = 1.0f / __ldg(p.bscale + t0 + b);
       const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(b * p.Npad + hsel * W);
-      float* yrow = p.Y + ((long long)(t0 + b) * p.K + k) * p.ldy + hsel * W;
+      float* yrow = p.Y + (long long)blockIdx.y * p.split_stride + ((long long)(t0 + b) * p.K + k) * p.ldy + hsel * W;
       for (int c = 0; c < W; c += 8) {
         uint32_t d[8];
         tc_ld8_issue(ta + (uint32_t)c, d);
@@ -1513,6 +1520,13 @@ int rrr_fwd_dense(const DenseFwdDesc& g, cudaStream_t stream) {
   p.K = (int)g.K; p.T = (int)g.T; p.C1 = (int)g.C1; p.N = (int)g.N; p.Npad = (int)g.Npad;
   p.n_rt = (int)ceil_div(g.K, 256);
   p.num_kb = (int)ceil_div(g.C1, 64);
+  int splits = g.splits > 0 ? g.splits : 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (int)ceil_div(p.num_kb, splits);
+  splits = (int)ceil_div(p.num_kb, p.kb_per_split);          // no empty run
+  p.split_stride = g.split_stride;
+  VS_REQUIRE(splits == 1 || g.split_stride >= g.K * g.T * g.ldy, VS_ERR_INVALID, "dense RRR forward: split_stride too small");
+  if (g.splits_out) *g.splits_out = splits;
   p.U32 = g.U32; p.isd = g.isd; p.ldu = g.ldu; p.V = g.V; p.bscale = g.bscale; p.Y = g.Y; p.ldy = g.ldy;
   Operand a; a.ptr = g.Xc; a.rows = g.K * g.T; a.k = g.C1; a.ld = g.ldc;
   CUtensorMap tmA;
@@ -1523,7 +1537,7 @@ int rrr_fwd_dense(const DenseFwdDesc& g, cudaStream_t stream) {
   const size_t smem = (size_t)CTRL_BYTES + 1024 + 2 * stage_bytes;
   VS_REQUIRE(smem <= 227 * 1024, VS_ERR_UNSUPPORTED, "dense RRR forward: tile too large for shared memory");
   const int items = (int)ceil_div(g.T, FWD_BINS) * p.n_rt;
-  dim3 grid(2 * (unsigned)items, 1, 1);
+  dim3 grid(2 * (unsigned)items, (unsigned)splits, 1);
   prof_begin(PROF_RRR_FWD, stream);
   VS_CHECK_CUDA(cudaFuncSetAttribute(rrr_fwd_dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   VS_LAUNCH(rrr_fwd_dense_pair_kernel, grid, FWD_THREADS, smem, stream, tmA, p);
