@@ -370,6 +370,35 @@ int vs_lbfgs_dev_update(vs_lbfgs_dev* state, const double* loss, double lr, doub
 int vs_lbfgs_dev_direction(vs_lbfgs_dev* state, int64_t n, const double* g, void* hist, int64_t hist_stride, int hist_f32,
                            double* x, void* stream);
 
+/* ---- compact history (device-driven, float64): ONE stored vector per closure evaluation -- the basis b_0 = g_0,
+ * b_l = g_l - g_(l-1) -- instead of the (s_i, y_i) pair; the steps s_i live as coefficient rows over the basis and every
+ * inner product of the two-loop recursion is a contraction of the basis Gram matrix P.  Same decisions, same order as
+ * vs_lbfgs_dev_update (= torch.optim.LBFGS.step); both passes stream nb vectors instead of 2m and no step vector is
+ * written: about half the HBM traffic.  At most VS_LBFGS_CMAX closure evaluations over the life of the state (done = 7
+ * when the basis is full); history slot l of `hist` holds b_l.                                                       */
+#define VS_LBFGS_CMAX 64
+typedef struct {
+  int32_t m, nb;         /* curvature pairs in memory; basis vectors stored (= closure evaluations seen) */
+  int32_t n_iter, total_iter, func_evals, cur_evals, done, have_prev, have_s, pad0;
+  int32_t iy[VS_LBFGS_CMAX];                 /* pair i's y is basis vector iy[i] */
+  double H_diag, prev_loss, loss, t, gtd, dmax;
+  double coef[VS_LBFGS_CMAX + 2];            /* [0] = cg (weight of g), [1+l] = weight of b_l in the direction */
+  double Acur[VS_LBFGS_CMAX];                /* coefficients of the latest step s = t*d */
+  double out[8 + 3 * VS_LBFGS_CMAX];         /* scalars of the dots pass */
+  double P[VS_LBFGS_CMAX * VS_LBFGS_CMAX];   /* basis Gram matrix */
+  double A[VS_LBFGS_CMAX * VS_LBFGS_CMAX];   /* row i: coefficients of s_i */
+  double SY[VS_LBFGS_CMAX * VS_LBFGS_CMAX], YY[VS_LBFGS_CMAX * VS_LBFGS_CMAX];
+} vs_lbfgs_cdev;
+int vs_lbfgs_cdev_init_host(vs_lbfgs_cdev* state_host);
+size_t vs_lbfgs_cdev_state_bytes(void);
+size_t vs_lbfgs_cdev_workspace(int64_t n);
+int vs_lbfgs_cdev_dots(vs_lbfgs_cdev* state, int64_t n, const double* g, const double* g_prev, double* hist,
+                       int64_t hist_stride, void* workspace, size_t workspace_bytes, void* stream);
+int vs_lbfgs_cdev_update(vs_lbfgs_cdev* state, const double* loss, double lr, double tolerance_grad, double tolerance_change,
+                         int max_eval, int first_eval, void* stream);
+int vs_lbfgs_cdev_direction(vs_lbfgs_cdev* state, int64_t n, const double* g, double* hist, int64_t hist_stride, double* x,
+                            void* stream);
+
 /* HOST: the two-loop recursion of torch.optim.LBFGS in coefficient space, between the two device passes.  Inputs are
  * the inner products vs_lbfgs_dots gathered (SY[i*ld+j] = s_i.y_j, YY[i*ld+j] = y_i.y_j, sg[i] = s_i.g,
  * yg[i] = y_i.g, gg = g.g) and torch's H_diag; coef_out (2m+1) receives [cg, cs_0.., cy_0..] for

@@ -227,3 +227,50 @@ def test_rrr_fit_device_driven(vs, cuda):
     assert out[True][1] == out[False][1] == 20
     assert out[True][0] == pytest.approx(out[False][0], rel=1e-8)
     np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-6, atol=1e-9)
+
+
+# ----------------------------------------------------------------------------- compact history (one stored vector per evaluation)
+@pytest.mark.parametrize("steps,max_iter", [(1, 20), (3, 7), (2, 1), (1, 50)])
+def test_compact_history_lbfgs_matches_torch(vs, cuda, steps, max_iter):
+    """FusedLBFGS(compact=True): the basis {g_0, y_0, y_1, ...} + its Gram matrix instead of the (s_i, y_i) pairs.
+    Same trajectory as torch.optim.LBFGS (to rounding), same logical counters, over several step() calls."""
+    from optim import FusedLBFGS
+    make = _problem(cuda, seed=5)
+    res = {}
+    for name in ("torch", "compact"):
+        ps, f = make()
+        opt = torch.optim.LBFGS(ps, max_iter=max_iter) if name == "torch" else FusedLBFGS(ps, max_iter=max_iter, device_driven=True, compact=True)
+        losses = []
+
+        def closure():
+            opt.zero_grad()
+            loss = f()
+            loss.backward()
+            losses.append(loss.detach().clone())
+            return loss
+        for _ in range(steps):
+            opt.step(closure)
+        st = opt.state[ps[0]]
+        res[name] = ([float(l) for l in losses], torch.cat([p.detach().reshape(-1) for p in ps]).cpu().numpy(), st["func_evals"], st["n_iter"])
+    assert res["compact"][2:] == res["torch"][2:]
+    k = len(res["torch"][0])                       # the device-driven loop keeps calling the closure after termination (no-ops)
+    np.testing.assert_allclose(res["compact"][0][:k], res["torch"][0], rtol=1e-8)
+    np.testing.assert_allclose(res["compact"][1], res["torch"][1], rtol=1e-6, atol=1e-9)
+
+
+def test_rrr_fit_compact_history(vs, cuda):
+    """One RRR fit (rrr.py:164-202) with the compact-history optimiser against the (s, y)-pair device-driven one."""
+    from model.rrr import RRRGD, train_model
+    from optim import FusedLBFGS
+    td = small_rrr_problem(seed=7, K=30, Kt=10, F=150, N=12)
+    out = {}
+    for compact in (False, True):
+        m = RRRGD(td, 3, l2=100.0, planes=3); m.to(cuda)
+        opt = FusedLBFGS(m.model.parameters(), device_driven=True, compact=compact)
+        _, res = train_model(m, td, opt, "tmp", save=False)
+        out[compact] = (float(res["mse_val_mean"]), m.n_closure_evals, m.model["e1_U"].detach().cpu().numpy())
+    assert out[True][1] == out[False][1] == 20
+    assert out[True][0] == pytest.approx(out[False][0], rel=1e-8)
+    np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-6, atol=1e-9)
+    with pytest.raises(vs.VsError):
+        FusedLBFGS(m.model.parameters(), device_driven=False, compact=True)

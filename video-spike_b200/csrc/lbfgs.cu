@@ -117,10 +117,18 @@ template <typename HT, bool kVec>
 __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __restrict__ g, const double* __restrict__ gp,
                                                    const HT* __restrict__ s_new, HT* __restrict__ y_out,
                                                    const HT* __restrict__ hist, long long stride, const Slots slots, int nh,
-                                                   int nout, double* __restrict__ part, const vs_lbfgs_dev* __restrict__ dev) {
+                                                   int nout, double* __restrict__ part, const vs_lbfgs_dev* __restrict__ dev,
+                                                   const vs_lbfgs_cdev* __restrict__ cdev) {
   extern __shared__ double red[];          // [nout][8 warps]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int m_dev = 0;
+  if (cdev) {  // compact history: the basis {g_0, y_0, y_1, ...} lives in slots 0 .. nb-1; this pass appends y_new (g_0 on the first one)
+    if (cdev->done) return;
+    nh = cdev->nb;
+    if (!cdev->have_prev) gp = nullptr;
+    s_new = nullptr;
+    y_out = const_cast<HT*>(hist) + (long long)cdev->nb * stride;
+  }
   if (dev) {   // device-driven optimiser: everything that depends on its decisions comes from the state
     if (dev->done) return;
     m_dev = dev->m;
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __
     s_new = dev->have_s ? hist + (long long)dev->s_cur * stride : nullptr;
     y_out = (dev->have_prev && dev->have_s) ? const_cast<HT*>(hist) + (long long)dev->y_next * stride : nullptr;
   }
-  auto slot_of = [&](int h) -> int { return dev ? (h < m_dev ? dev->s_slots[h] : dev->y_slots[h - m_dev]) : slots.s[h]; };
+  auto slot_of = [&](int h) -> int { return cdev ? h : (dev ? (h < m_dev ? dev->s_slots[h] : dev->y_slots[h - m_dev]) : slots.s[h]); };
   const int nvalid = kBase + 3 * nh;       // outputs this launch produces (nout is the stride of the partial rows)
   const long long i0 = (long long)blockIdx.x * kChunk + 4 * threadIdx.x;
   D4 gv[kGroups], yv[kGroups], sv[kGroups];
@@ -225,12 +233,16 @@ __global__ void __launch_bounds__(256) dots_kernel(long long n, const double* __
 // out[o] = sum (max for o == 2) over the chunk partials: one block per output, thread t takes chunks t, t+128, ...
 // and the 128 lane sums are combined by a fixed tree, so the result does not depend on scheduling
 __global__ void __launch_bounds__(128) dots_reduce_kernel(const double* __restrict__ part, int chunks, int nout, double* __restrict__ out,
-                                                          vs_lbfgs_dev* __restrict__ dev) {
+                                                          vs_lbfgs_dev* __restrict__ dev, vs_lbfgs_cdev* __restrict__ cdev) {
   __shared__ double sh[128];
   const int o = blockIdx.x;
   if (dev) {
     if (dev->done || o >= kBase + 6 * dev->m) return;
     out = dev->out;
+  }
+  if (cdev) {
+    if (cdev->done || o >= kBase + 3 * cdev->nb) return;
+    out = cdev->out;
   }
   const bool is_max = (o == 2);
   double s = 0.0;
@@ -256,11 +268,23 @@ template <typename HT, bool kVec>
 __global__ void __launch_bounds__(256) direction_kernel(long long n, const double* __restrict__ g, const HT* __restrict__ hist,
                                                         long long stride, const Slots slots, int nh, const CoefT<HT> coef, double cg,
                                                         double t, double* __restrict__ x, HT* __restrict__ s_out,
-                                                        unsigned long long* __restrict__ dmax_bits, vs_lbfgs_dev* __restrict__ dev) {
+                                                        unsigned long long* __restrict__ dmax_bits, vs_lbfgs_dev* __restrict__ dev,
+                                                        vs_lbfgs_cdev* __restrict__ cdev) {
   __shared__ double sh[8];
   __shared__ HT s_coef[2 * VS_LBFGS_MAX_HIST];
   __shared__ const HT* s_ptr[2 * VS_LBFGS_MAX_HIST];
-  if (dev) {   // device-driven optimiser: coefficients, slots, step length and destination come from the state
+  if (cdev) {  // compact history: d = cg*g + sum_l coef[1+l] * basis_l; the step s = t*d is kept as coefficients only (no store)
+    if (cdev->done) return;
+    nh = cdev->nb;
+    for (int h = threadIdx.x; h < nh; h += 256) {
+      s_coef[h] = (HT)cdev->coef[1 + h];
+      s_ptr[h] = hist + (long long)h * stride;
+    }
+    cg = cdev->coef[0];
+    t = cdev->t;
+    s_out = nullptr;
+    dmax_bits = reinterpret_cast<unsigned long long*>(&cdev->dmax);
+  } else if (dev) {   // device-driven optimiser: coefficients, slots, step length and destination come from the state
     if (dev->done) return;
     const int md = dev->m;
     nh = 2 * md;
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(256) direction_kernel(long long n, const doubl
       sd.v[q] = t * fma(cg, gv.v[q], (double)acc[q]);
       if (i + q < n) m = fmax(m, fabs(sd.v[q]));
     }
-    store4<kVec>(s_out, i, n, sd);
+    if (s_out) store4<kVec>(s_out, i, n, sd);
     if (x) {
       if (kVec && i + 3 < n) {
         double2* xp = reinterpret_cast<double2*>(x + i);
@@ -456,6 +480,157 @@ __global__ void __launch_bounds__(128) update_kernel(vs_lbfgs_dev* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ compact history (device-driven, float64)
+// Every vector torch.optim.LBFGS keeps -- the steps s_i = t_i d_i, the gradient differences y_i, the direction d -- lies
+// in the span of the evaluated gradients.  Keep ONE vector per closure evaluation, the basis b_0 = g_0, b_l = g_l - g_(l-1)
+// (the y vectors themselves, formed exactly as before), its Gram matrix P, and the steps as COEFFICIENT rows over the
+// basis: each pass then streams nb vectors instead of the 2m of the (s_i, y_i) scheme, and no step vector is written.
+//   dots pass      appends b_nb = g - g_prev, out[8+3l+{0,1}] = b_l.g, b_l.b_nb; out[3] = b_nb.b_nb, out[6] = b_nb.g
+//   update         P grows by one row/column; s.y, s.g, y.y, y.g of the two-loop recursion are contractions of P and the
+//                  coefficient rows; same decisions in the same order as update_kernel (= torch.optim.LBFGS.step)
+//   direction pass d = cg*g + sum_l coef[1+l] b_l;  x += t*d;  the new step's coefficients are t*(cg + coef[1+l])
+//                  because g = sum_l b_l
+constexpr int CB = VS_LBFGS_CMAX;
+
+__global__ void __launch_bounds__(128) update_compact_kernel(vs_lbfgs_cdev* __restrict__ d, const double* __restrict__ loss_ptr, double lr,
+                                                             double tol_g, double tol_c, int max_eval, int first_eval) {
+  __shared__ double sP[32 * 32], sA[32 * 32], sSY[32 * 32], sYY[32 * 32];
+  __shared__ double pg[CB], sg[CB], yg[CB], al[CB], ro[CB], cs[CB], cy[CB];
+  __shared__ int s_go, s_nb, s_m, s_small;
+  if (threadIdx.x == 0) {
+    s_go = 0;
+    if (first_eval) { d->n_iter = 0; d->cur_evals = 0; d->done = 0; }
+    if (!d->done) {
+      const double* out = d->out;
+      const int nbn = d->nb;                                    // index of the vector the dots pass just appended
+      if (nbn >= CB) {
+        d->done = 7;                                            // basis full: the caller must use the (s, y) scheme
+      } else {
+        for (int l = 0; l < nbn; ++l) {
+          const double v = out[kBase + 3 * l + 1];
+          d->P[l * CB + nbn] = v; d->P[nbn * CB + l] = v;
+        }
+        d->P[nbn * CB + nbn] = out[3];
+        d->nb = nbn + 1;
+        s_go = 1;
+      }
+    }
+    s_nb = d->nb; s_m = d->m;
+    s_small = (d->nb <= 32) ? 1 : 0;
+    __threadfence_block();
+  }
+  __syncthreads();
+  if (!s_go) return;
+  const int nb = s_nb;
+  const bool small = s_small != 0;
+  if (small) {   // stage the Gram matrix and the coefficient rows: the O(m^2 nb) algebra below is a dependent chain on one thread
+    for (int e = threadIdx.x; e < nb * nb; e += 128) sP[(e / nb) * 32 + (e % nb)] = d->P[(e / nb) * CB + (e % nb)];
+    for (int e = threadIdx.x; e < s_m * nb; e += 128) sA[(e / nb) * 32 + (e % nb)] = d->A[(e / nb) * CB + (e % nb)];
+    for (int e = threadIdx.x; e < s_m * s_m; e += 128) {
+      sSY[(e / s_m) * 32 + (e % s_m)] = d->SY[(e / s_m) * CB + (e % s_m)];
+      sYY[(e / s_m) * 32 + (e % s_m)] = d->YY[(e / s_m) * CB + (e % s_m)];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double* P = small ? sP : d->P;
+  double* A = small ? sA : d->A;
+  double* SY = small ? sSY : d->SY;
+  double* YY = small ? sYY : d->YY;
+  const int ld = small ? 32 : CB;
+  const double* out = d->out;
+  const double loss = *loss_ptr;
+  d->loss = loss;
+  d->cur_evals += 1;
+  d->func_evals += 1;
+  if (first_eval) {
+    if (out[2] <= tol_g) { d->done = 1; return; }
+  } else {
+    if (d->cur_evals >= max_eval) d->done = 3;
+    else if (out[2] <= tol_g) d->done = 4;
+    else if (d->dmax <= tol_c) d->done = 5;
+    else if (fabs(loss - d->prev_loss) < tol_c) d->done = 6;
+    if (d->done) return;
+  }
+  d->n_iter += 1;
+  d->total_iter += 1;
+  const int nn = nb - 1;                                        // the newest basis vector = y_new
+  for (int l = 0; l < nn; ++l) pg[l] = out[kBase + 3 * l];
+  pg[nn] = out[6];
+  int m = d->m;
+  double Hd = d->H_diag;
+  if (d->total_iter == 1) {
+    Hd = 1.0;
+  } else if (d->have_prev && d->have_s) {
+    // the step s = t*d taken before this evaluation, as coefficients over the basis it was built from (indices < nn)
+    double ys = 0.0;
+    for (int l = 0; l < nn; ++l) ys += d->Acur[l] * P[l * ld + nn];
+    const double yy = P[nn * ld + nn];
+    if (ys > 1e-10 && m < CB) {
+      for (int i = 0; i < m; ++i) {
+        double a = 0.0, b2 = 0.0;
+        for (int l = 0; l < nn; ++l) { a += A[i * ld + l] * P[l * ld + nn]; b2 += d->Acur[l] * P[l * ld + d->iy[i]]; }
+        const double c = P[d->iy[i] * ld + nn];
+        d->SY[i * CB + m] = a;                                    // s_i . y_new
+        d->SY[m * CB + i] = b2;                                   // s_new . y_i
+        d->YY[i * CB + m] = c; d->YY[m * CB + i] = c;
+        if (small) { SY[i * ld + m] = a; SY[m * ld + i] = b2; YY[i * ld + m] = c; YY[m * ld + i] = c; }
+      }
+      d->SY[m * CB + m] = ys; d->YY[m * CB + m] = yy;
+      if (small) { SY[m * ld + m] = ys; YY[m * ld + m] = yy; }
+      for (int l = 0; l < CB; ++l) { const double v = l < nn ? d->Acur[l] : 0.0; d->A[m * CB + l] = v; if (small && l < 32) A[m * ld + l] = v; }
+      d->iy[m] = nn;
+      m += 1;
+      Hd = ys / yy;
+    }
+    d->have_s = 0;
+  }
+  d->m = m;
+  d->H_diag = Hd;
+  for (int i = 0; i < m; ++i) {
+    double a = 0.0;
+    for (int l = 0; l < nb; ++l) a += A[i * ld + l] * pg[l];
+    sg[i] = a;
+    yg[i] = pg[d->iy[i]];
+  }
+  // two-loop recursion in coefficient space (statement order of update_direction / csrc/host_lbfgs.cpp)
+  const double gg = out[0], g1 = out[1];
+  for (int i = 0; i < m; ++i) ro[i] = 1.0 / SY[i * ld + i];
+  for (int i = m - 1; i >= 0; --i) {
+    double sq = -sg[i];
+    for (int j = i + 1; j < m; ++j) sq -= al[j] * SY[i * ld + j];
+    al[i] = sq * ro[i];
+  }
+  for (int i = 0; i < m; ++i) {
+    double yr = -yg[i];
+    for (int j = 0; j < m; ++j) yr -= al[j] * YY[i * ld + j];
+    yr *= Hd;
+    for (int j = 0; j < i; ++j) yr += cs[j] * SY[j * ld + i];
+    cs[i] = al[i] - yr * ro[i];
+  }
+  double dot_s = 0.0, dot_y = 0.0;
+  for (int i = 0; i < m; ++i) cy[i] = -Hd * al[i];
+  for (int i = 0; i < m; ++i) dot_s += cs[i] * sg[i];
+  for (int i = 0; i < m; ++i) dot_y += cy[i] * yg[i];
+  d->gtd = m ? -Hd * gg + dot_s + dot_y : -Hd * gg;
+  d->prev_loss = loss;
+  d->have_prev = 1;
+  d->t = d->total_iter == 1 ? fmin(1.0, 1.0 / g1) * lr : lr;
+  if (d->gtd > -tol_c) { d->done = 2; return; }
+  // d over the basis (the cg*g term is taken from the gradient buffer by the direction pass)
+  const double cg = -Hd;
+  d->coef[0] = cg;
+  for (int l = 0; l < nb; ++l) {
+    double c = 0.0;
+    for (int i = 0; i < m; ++i) c += cs[i] * A[i * ld + l];
+    d->coef[1 + l] = c;
+  }
+  for (int i = 0; i < m; ++i) d->coef[1 + d->iy[i]] += cy[i];
+  for (int l = 0; l < nb; ++l) d->Acur[l] = d->t * (cg + d->coef[1 + l]);        // g = sum_l b_l
+  d->have_s = 1;
+  d->dmax = 0.0;
+}
+
 }  // namespace lbfgs
 }  // namespace vs
 
@@ -472,17 +647,17 @@ extern "C" size_t vs_lbfgs_workspace(int64_t n, int m) {
 template <typename HT>
 static int launch_dots(long long n, const double* g, const double* g_prev, const void* s_new, void* y_out, const void* hist,
                        long long hist_stride, const Slots& sl, int nh, int nout, double* part, int chunks, void* stream,
-                       const vs_lbfgs_dev* dev = nullptr) {
+                       const vs_lbfgs_dev* dev = nullptr, const vs_lbfgs_cdev* cdev = nullptr) {
   const size_t smem = (size_t)nout * 8 * sizeof(double);
   // 128-bit loads need every vector base 16-byte aligned (hist slots: pitch a multiple of 4 elements)
   const bool vec = ((((uintptr_t)g | (uintptr_t)g_prev | (uintptr_t)s_new | (uintptr_t)y_out | (uintptr_t)hist) & 15) == 0) &&
-                   (hist_stride % 4 == 0 || (nh == 0 && !dev));
+                   (hist_stride % 4 == 0 || (nh == 0 && !dev && !cdev));
   if (vec) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<HT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dots_kernel<HT, true>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part, dev);
+    VS_LAUNCH((dots_kernel<HT, true>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part, dev, cdev);
   } else {
     VS_CHECK_CUDA(cudaFuncSetAttribute(dots_kernel<HT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_LAUNCH((dots_kernel<HT, false>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part, dev);
+    VS_LAUNCH((dots_kernel<HT, false>), chunks, 256, smem, stream, n, g, g_prev, (const HT*)s_new, (HT*)y_out, (const HT*)hist, hist_stride, sl, nh, nout, part, dev, cdev);
   }
   return VS_OK;
 }
@@ -504,7 +679,7 @@ extern "C" int vs_lbfgs_dots(int64_t n, const double* g, const double* g_prev, c
   int rc = hist_f32 ? launch_dots<float>(n, g, g_prev, s_new, y_out, hist, hist_stride, sl, nh, nout, part, chunks, stream)
                     : launch_dots<double>(n, g, g_prev, s_new, y_out, hist, hist_stride, sl, nh, nout, part, chunks, stream);
   if (rc) return rc;
-  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, out, (vs_lbfgs_dev*)nullptr);
+  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, out, (vs_lbfgs_dev*)nullptr, (vs_lbfgs_cdev*)nullptr);
   return VS_OK;
 }
 
@@ -524,13 +699,13 @@ extern "C" int vs_lbfgs_direction(int64_t n, const double* g, const void* hist, 
   if (hist_f32) {
     CoefT<float> cf;
     for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = (float)coef_host[i];
-    if (vec) { VS_LAUNCH((direction_kernel<float, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (float*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
-    else { VS_LAUNCH((direction_kernel<float, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (float*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
+    if (vec) { VS_LAUNCH((direction_kernel<float, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (float*)s_out, dm, (vs_lbfgs_dev*)nullptr, (vs_lbfgs_cdev*)nullptr); }
+    else { VS_LAUNCH((direction_kernel<float, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (float*)s_out, dm, (vs_lbfgs_dev*)nullptr, (vs_lbfgs_cdev*)nullptr); }
   } else {
     CoefT<double> cf;
     for (int i = 0; i < 2 * m + 1; ++i) cf.c[i] = coef_host[i];
-    if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (double*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
-    else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (double*)s_out, dm, (vs_lbfgs_dev*)nullptr); }
+    if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (double*)s_out, dm, (vs_lbfgs_dev*)nullptr, (vs_lbfgs_cdev*)nullptr); }
+    else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 2 * m, cf, coef_host[0], t, x, (double*)s_out, dm, (vs_lbfgs_dev*)nullptr, (vs_lbfgs_cdev*)nullptr); }
   }
   return VS_OK;
 }
@@ -567,7 +742,7 @@ extern "C" int vs_lbfgs_dev_dots(vs_lbfgs_dev* state, int64_t n, const double* g
   int rc = hist_f32 ? launch_dots<float>(n, g, g_prev, nullptr, nullptr, hist, hist_stride, sl, 0, nout, part, chunks, stream, state)
                     : launch_dots<double>(n, g, g_prev, nullptr, nullptr, hist, hist_stride, sl, 0, nout, part, chunks, stream, state);
   if (rc) return rc;
-  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, (double*)nullptr, state);
+  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, (double*)nullptr, state, (vs_lbfgs_cdev*)nullptr);
   return VS_OK;
 }
 
@@ -591,13 +766,68 @@ extern "C" int vs_lbfgs_dev_direction(vs_lbfgs_dev* state, int64_t n, const doub
   if (hist_f32) {
     CoefT<float> cf;
     cf.c[0] = 0.f;
-    if (vec) { VS_LAUNCH((direction_kernel<float, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (float*)nullptr, (unsigned long long*)nullptr, state); }
-    else { VS_LAUNCH((direction_kernel<float, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (float*)nullptr, (unsigned long long*)nullptr, state); }
+    if (vec) { VS_LAUNCH((direction_kernel<float, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (float*)nullptr, (unsigned long long*)nullptr, state, (vs_lbfgs_cdev*)nullptr); }
+    else { VS_LAUNCH((direction_kernel<float, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const float*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (float*)nullptr, (unsigned long long*)nullptr, state, (vs_lbfgs_cdev*)nullptr); }
   } else {
     CoefT<double> cf;
     cf.c[0] = 0.0;
-    if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, state); }
-    else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, state); }
+    if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, state, (vs_lbfgs_cdev*)nullptr); }
+    else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, state, (vs_lbfgs_cdev*)nullptr); }
   }
+  return VS_OK;
+}
+
+
+// ------------------------------------------------------------------ compact-history entry points (float64 history only)
+extern "C" int vs_lbfgs_cdev_init_host(vs_lbfgs_cdev* st) {
+  if (!st) return VS_ERR_INVALID;
+  memset(st, 0, sizeof(*st));
+  st->H_diag = 1.0;
+  return VS_OK;
+}
+
+extern "C" size_t vs_lbfgs_cdev_state_bytes(void) { return sizeof(vs_lbfgs_cdev); }
+
+extern "C" size_t vs_lbfgs_cdev_workspace(int64_t n) {
+  if (n <= 0) return 0;
+  return (size_t)num_chunks(n) * (kBase + 3 * (size_t)VS_LBFGS_CMAX) * sizeof(double) + 64;
+}
+
+extern "C" int vs_lbfgs_cdev_dots(vs_lbfgs_cdev* state, int64_t n, const double* g, const double* g_prev, double* hist,
+                                  int64_t hist_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(state && n > 0 && g && g_prev && hist && hist_stride >= n, VS_ERR_INVALID, "vs_lbfgs_cdev_dots: bad arguments");
+  VS_REQUIRE(workspace && workspace_bytes >= vs_lbfgs_cdev_workspace(n) && ((uintptr_t)workspace & 7) == 0, VS_ERR_WORKSPACE,
+             "vs_lbfgs_cdev_dots: workspace too small or misaligned");
+  VS_REQUIRE(n < (1ll << 40), VS_ERR_UNSUPPORTED, "vs_lbfgs_cdev_dots: vector too long");
+  const int nout = kBase + 3 * VS_LBFGS_CMAX;
+  const int chunks = num_chunks(n);
+  double* part = reinterpret_cast<double*>(workspace);
+  Slots sl;
+  sl.s[0] = 0;
+  int rc = launch_dots<double>(n, g, g_prev, nullptr, nullptr, hist, hist_stride, sl, 0, nout, part, chunks, stream, nullptr, state);
+  if (rc) return rc;
+  VS_LAUNCH(dots_reduce_kernel, (unsigned)nout, 128, 0, stream, part, chunks, nout, (double*)nullptr, (vs_lbfgs_dev*)nullptr, state);
+  return VS_OK;
+}
+
+extern "C" int vs_lbfgs_cdev_update(vs_lbfgs_cdev* state, const double* loss, double lr, double tolerance_grad, double tolerance_change,
+                                    int max_eval, int first_eval, void* stream) {
+  VS_REQUIRE(state && loss, VS_ERR_INVALID, "vs_lbfgs_cdev_update: null pointer");
+  VS_LAUNCH(update_compact_kernel, 1, 128, 0, stream, state, loss, lr, tolerance_grad, tolerance_change, max_eval, first_eval);
+  return VS_OK;
+}
+
+extern "C" int vs_lbfgs_cdev_direction(vs_lbfgs_cdev* state, int64_t n, const double* g, double* hist, int64_t hist_stride, double* x,
+                                       void* stream) {
+  VS_REQUIRE(state && n > 0 && g && hist && x && hist_stride >= n, VS_ERR_INVALID, "vs_lbfgs_cdev_direction: bad arguments");
+  long long blocks = ceil_div(n, 256 * 4);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  Slots sl;
+  sl.s[0] = 0;
+  const bool vec = ((((uintptr_t)g | (uintptr_t)hist | (uintptr_t)x) & 15) == 0) && hist_stride % 4 == 0;
+  CoefT<double> cf;
+  cf.c[0] = 0.0;
+  if (vec) { VS_LAUNCH((direction_kernel<double, true>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, (vs_lbfgs_dev*)nullptr, state); }
+  else { VS_LAUNCH((direction_kernel<double, false>), (unsigned)blocks, 256, 0, stream, (long long)n, g, (const double*)hist, (long long)hist_stride, sl, 0, cf, 0.0, 0.0, x, (double*)nullptr, (unsigned long long*)nullptr, (vs_lbfgs_dev*)nullptr, state); }
   return VS_OK;
 }

@@ -156,11 +156,19 @@ class FusedLBFGS(torch.optim.Optimizer):
     (model.rrr.RRRGD.loss_and_grad does); autograd closures work too (`zero_grad()` zeroes the views)."""
 
     def __init__(self, params, lr=1, max_iter=20, max_eval=None, tolerance_grad=1e-7, tolerance_change=1e-9,
-                 history_size=100, line_search_fn=None, history_dtype=torch.float64, device_driven=False):
+                 history_size=100, line_search_fn=None, history_dtype=torch.float64, device_driven=False, compact=False):
+        """`compact=True` (device-driven, float64 history): ONE stored vector per closure evaluation -- the gradient
+        differences -- instead of the (s_i, y_i) pairs; the steps live as coefficient rows and every inner product of
+        the recursion comes from the basis Gram matrix (csrc/lbfgs.cu "compact history").  Same decisions in the same
+        order, about half the HBM traffic of the vector passes; at most vs.LBFGS_CMAX closure evaluations over the life
+        of the optimiser (the reference runs one step of <= 25)."""
         if history_dtype not in (torch.float64, torch.float32):
             raise ValueError("history_dtype must be torch.float64 or torch.float32")
         self._hdtype = history_dtype
         self._device_driven = bool(device_driven)
+        self._compact = bool(compact)
+        if self._compact and (not self._device_driven or history_dtype != torch.float64 or history_size < vs.LBFGS_CMAX):
+            raise vs.VsError("FusedLBFGS(compact=True) needs device_driven=True, a float64 history and history_size >= %d" % vs.LBFGS_CMAX)
         self._dev = None
         if line_search_fn is not None:
             raise vs.VsError("FusedLBFGS implements the fixed-step variant only (the reference never sets line_search_fn)")
@@ -354,11 +362,82 @@ class FusedLBFGS(torch.optim.Optimizer):
     def _reduce_dev_scalars(self):
         """Hook (parallel.ShardedLBFGS): combine the state's `out` block and `dmax` across ranks on the device."""
 
+    def _dots_call(self, sp, n, g_ptr, gp_ptr, hist_ptr, stride, f32, dev):
+        """One dots pass over `n` elements starting at the given device addresses (classic or compact state)."""
+        if dev.get("compact"):
+            vs.check(vs.lib.vs_lbfgs_cdev_dots(sp, n, g_ptr, gp_ptr, hist_ptr, stride, vs.ptr(dev["ws"]), dev["ws"].numel(), vs.stream()))
+        else:
+            vs.check(vs.lib.vs_lbfgs_dev_dots(sp, n, g_ptr, gp_ptr, hist_ptr, stride, f32, vs.ptr(dev["ws"]), dev["ws"].numel(), vs.stream()))
+
     def _dev_dots(self, sp, n, g, g_prev, hist, f32, dev):
-        """vs_lbfgs_dev_dots over the whole flat vector (parallel.ShardedLBFGS restricts the inner products of the
+        """The dots pass over the whole flat vector (parallel.ShardedLBFGS restricts the inner products of the
         replicated prefix to rank 0)."""
-        vs.check(vs.lib.vs_lbfgs_dev_dots(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), hist.shape[1], f32, vs.ptr(dev["ws"]),
-                                          dev["ws"].numel(), vs.stream()))
+        self._dots_call(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), hist.shape[1], f32, dev)
+
+    def _cdev_state(self, need_slots):
+        """Device buffer holding a vs_lbfgs_cdev (+ float64 views of its `out` block and `dmax`) and the basis vectors."""
+        dev_t = self._flat["x"].device
+        n = self._flat["n"]
+        npad = (n + 3) // 4 * 4
+        need_slots = min(need_slots, vs.LBFGS_CMAX)
+        if self._dev is None:
+            host = vs.LbfgsCDev()
+            vs.check(vs.lib.vs_lbfgs_cdev_init_host(C.byref(host)))
+            raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(dev_t)
+            k = 8 + 3 * vs.LBFGS_CMAX
+            self._dev = {"raw": raw, "n_slots": need_slots, "host": host, "compact": True,
+                         "out": raw[vs.LbfgsCDev.out.offset:vs.LbfgsCDev.out.offset + 8 * k].view(torch.float64),
+                         "dmax": raw[vs.LbfgsCDev.dmax.offset:vs.LbfgsCDev.dmax.offset + 8].view(torch.float64),
+                         "ws": torch.empty(int(vs.lib.vs_lbfgs_cdev_workspace(n)), dtype=torch.uint8, device=dev_t)}
+            self._hist = torch.empty((need_slots, npad), dtype=torch.float64, device=dev_t)
+        elif need_slots > self._dev["n_slots"]:
+            grown = torch.empty((need_slots, npad), dtype=torch.float64, device=dev_t)
+            grown[:self._dev["n_slots"]].copy_(self._hist)
+            self._hist = grown
+            self._dev["n_slots"] = need_slots
+        return self._dev
+
+    @torch.no_grad()
+    def _step_compact(self, closure):
+        closure = torch.enable_grad()(closure)
+        group = self.param_groups[0]
+        lr, max_iter, max_eval = float(group["lr"]), group["max_iter"], group["max_eval"]
+        tol_g, tol_c = float(group["tolerance_grad"]), float(group["tolerance_change"])
+        fl = self._bind()
+        n = fl["n"]
+        state = self.state[self._params[0]]
+        nb_now = self._dev["host"].nb if self._dev is not None else 0
+        if nb_now + max_iter > vs.LBFGS_CMAX:
+            raise vs.VsError("FusedLBFGS(compact=True): more than %d closure evaluations over the life of the optimiser; "
+                             "use compact=False" % vs.LBFGS_CMAX)
+        dev = self._cdev_state(nb_now + max_iter + 1)
+        hist = self._hist
+        sp, st = vs.ptr(dev["raw"]), vs.stream
+        orig_loss = None
+        head = vs.LbfgsCDev.coef.offset
+        for it in range(max_iter):
+            prev = state.get("prev_buf")
+            if prev is not None and fl["cur"] == prev:
+                self._point_grads(1 - prev)
+            loss_t = closure()
+            if orig_loss is None:
+                orig_loss = loss_t
+            g = fl["g"][fl["cur"]]
+            g_prev = fl["g"][1 - fl["cur"]]
+            lt = torch.as_tensor(loss_t).detach().reshape(1).double()
+            self._dev_dots(sp, n, g, g_prev, hist, 0, dev)
+            self._reduce_dev_scalars()
+            vs.check(vs.lib.vs_lbfgs_cdev_update(sp, vs.ptr(lt), lr, tol_g, tol_c, int(max_eval), int(it == 0), st()))
+            vs.check(vs.lib.vs_lbfgs_cdev_direction(sp, n, vs.ptr(g), vs.ptr(hist), hist.shape[1], vs.ptr(fl["x"]), st()))
+            state["prev_buf"] = fl["cur"]
+        raw = dev["raw"][:head].cpu().numpy().tobytes()               # the only synchronisation of the step
+        host = vs.LbfgsCDev.from_buffer_copy(raw.ljust(C.sizeof(vs.LbfgsCDev), b"\0"))
+        dev["host"] = host
+        if host.done == 7:
+            raise vs.VsError("FusedLBFGS(compact=True): basis full (vs.LBFGS_CMAX evaluations)")
+        state["func_evals"], state["n_iter"] = int(host.func_evals), int(host.total_iter)
+        state["dev_done"] = int(host.done)
+        return orig_loss
 
     @torch.no_grad()
     def _step_device_driven(self, closure):
@@ -397,6 +476,8 @@ class FusedLBFGS(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure):
+        if self._device_driven and self._compact:
+            return self._step_compact(closure)
         if self._device_driven:
             return self._step_device_driven(closure)
         import numpy as np

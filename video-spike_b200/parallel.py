@@ -61,18 +61,16 @@ class ShardedLBFGS(FusedLBFGS):
     #      host read: dots (local shard) -> ONE all-gather of every rank's scalar block -> ordered combine -> update -> direction
     def _dev_dots(self, sp, n, g, g_prev, hist, f32, dev):
         ns = self._n_shared
-        lib, st = vs.lib, vs.stream()
-        wsp, wsn, stride = vs.ptr(dev["ws"]), dev["ws"].numel(), hist.shape[1]
+        stride = hist.shape[1]
         if self._rank == 0 or self._world == 1 or ns == 0:
-            vs.check(lib.vs_lbfgs_dev_dots(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), stride, f32, wsp, wsn, st))
+            self._dots_call(sp, n, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), stride, f32, dev)
             return
         # rank != 0: the replicated prefix still gets its y = g - g_prev written (the history must be complete on every
         # rank), but its inner products are rank 0's to count: that pass's scalars are overwritten by the local pass
         esz = 4 if f32 else 8
-        vs.check(lib.vs_lbfgs_dev_dots(sp, ns, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), stride, f32, wsp, wsn, st))
+        self._dots_call(sp, ns, vs.ptr(g), vs.ptr(g_prev), vs.ptr(hist), stride, f32, dev)
         if n > ns:
-            vs.check(lib.vs_lbfgs_dev_dots(sp, n - ns, g.data_ptr() + 8 * ns, g_prev.data_ptr() + 8 * ns, hist.data_ptr() + esz * ns,
-                                           stride, f32, wsp, wsn, st))
+            self._dots_call(sp, n - ns, g.data_ptr() + 8 * ns, g_prev.data_ptr() + 8 * ns, hist.data_ptr() + esz * ns, stride, f32, dev)
         else:
             dev["out"].zero_()
 
@@ -147,7 +145,8 @@ def train_joint_model(model, train_data_local, model_fname="tmp", save=False, gr
         history_dtype = torch.float32 if model.planes == 1 else torch.float64
     if device_driven is None:
         device_driven = os.environ.get("VS_LBFGS_DEVICE", "1") != "0" and model.model["V"].is_cuda
-    optimizer = ShardedLBFGS(shared, local, group=group, history_dtype=history_dtype, device_driven=device_driven)
+    compact = bool(device_driven and history_dtype == torch.float64 and os.environ.get("VS_LBFGS_COMPACT", "0") != "0")
+    optimizer = ShardedLBFGS(shared, local, group=group, history_dtype=history_dtype, device_driven=device_driven, compact=compact)
     optimizer.closure_overwrites_grads = True
 
     def closure():

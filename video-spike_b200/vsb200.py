@@ -53,6 +53,21 @@ class LbfgsDev(C.Structure):
                 ("SY", C.c_double * (LBFGS_MAX_HIST * LBFGS_MAX_HIST)), ("YY", C.c_double * (LBFGS_MAX_HIST * LBFGS_MAX_HIST))]
 
 
+LBFGS_CMAX = 64
+
+
+class LbfgsCDev(C.Structure):
+    """vs_lbfgs_cdev: device-resident state of the compact-history L-BFGS (include/vs_b200.h)."""
+    _fields_ = [("m", C.c_int32), ("nb", C.c_int32), ("n_iter", C.c_int32), ("total_iter", C.c_int32), ("func_evals", C.c_int32),
+                ("cur_evals", C.c_int32), ("done", C.c_int32), ("have_prev", C.c_int32), ("have_s", C.c_int32), ("pad0", C.c_int32),
+                ("iy", C.c_int32 * LBFGS_CMAX),
+                ("H_diag", C.c_double), ("prev_loss", C.c_double), ("loss", C.c_double), ("t", C.c_double), ("gtd", C.c_double),
+                ("dmax", C.c_double),
+                ("coef", C.c_double * (LBFGS_CMAX + 2)), ("Acur", C.c_double * LBFGS_CMAX), ("out", C.c_double * (8 + 3 * LBFGS_CMAX)),
+                ("P", C.c_double * (LBFGS_CMAX * LBFGS_CMAX)), ("A", C.c_double * (LBFGS_CMAX * LBFGS_CMAX)),
+                ("SY", C.c_double * (LBFGS_CMAX * LBFGS_CMAX)), ("YY", C.c_double * (LBFGS_CMAX * LBFGS_CMAX))]
+
+
 class RrrDims(C.Structure):
     _fields_ = [("K", C.c_int64), ("T", C.c_int64), ("C1", C.c_int64), ("N", C.c_int64), ("r", C.c_int64),
                 ("planes", C.c_int32), ("ldc", C.c_int64), ("ldr", C.c_int64), ("fmt", C.c_int32), ("mode", C.c_int32)]
@@ -118,6 +133,12 @@ def _load():
         "vs_lbfgs_dev_dots": (C.c_int, [vp, i64, vp, vp, vp, i64, i32, vp, sz, vp]),
         "vs_lbfgs_dev_update": (C.c_int, [vp, vp, dbl, dbl, dbl, i32, i32, i32, vp]),
         "vs_lbfgs_dev_direction": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
+        "vs_lbfgs_cdev_init_host": (C.c_int, [C.POINTER(LbfgsCDev)]),
+        "vs_lbfgs_cdev_state_bytes": (sz, []),
+        "vs_lbfgs_cdev_workspace": (sz, [i64]),
+        "vs_lbfgs_cdev_dots": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, sz, vp]),
+        "vs_lbfgs_cdev_update": (C.c_int, [vp, vp, dbl, dbl, dbl, i32, i32, vp]),
+        "vs_lbfgs_cdev_direction": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
         "vs_host_lbfgs_two_loop": (C.c_int, [i32, dbl, vp, vp, vp, vp, i32, dbl, vp, vp]),
         "vs_host_rng_seed": (C.c_int, [vp, C.c_uint32]),
         "vs_host_rng_normal": (C.c_int, [vp, i64, dbl, vp, i32]),
