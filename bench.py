@@ -393,10 +393,16 @@ def fp64_dense_reference(ftr, ctr, fte, cte, sidx, dev, perturb_seed=1):
         pred = torch.einsum("ktc,nct->ktn", Xte, beta)
         val = float(((pred - yte) ** 2).sum())
         pred_fr = (pred.cpu().numpy() * sy + my)              # src/model/rrr.py:136-142 (predict_y_fr)
-    del Xtr, Xte, beta, pred
+    del beta, pred
+    # (3) one more evaluation at the END of the fit, where the gradient is small (dV is then a small difference of large sums)
+    end = {"U": U.detach().clone(), "b": b.detach().clone(), "V": V.detach().clone()}
+    opt.zero_grad()
+    l = loss_fn(); l.backward()
+    probe_end = (float(l.detach()), {"U": U.grad.clone(), "b": b.grad.clone(), "V": V.grad.clone()})
+    del Xtr, Xte
     torch.cuda.empty_cache()
     return {"val_sse": val, "evals": len(trace), "probe": probe, "start": start, "first_loss": trace[0], "last_loss": trace[-1],
-            "pred_test_fr": pred_fr}
+            "pred_test_fr": pred_fr, "end": end, "probe_end": probe_end}
 
 
 # ----------------------------------------------------------------------------- RRR workload

@@ -34,6 +34,12 @@ for nm in names:
         m.model["s_U"].copy_(ref["start"]["U"]); m.model["s_b"].copy_(ref["start"]["b"]); m.model["V"].copy_(ref["start"]["V"])
     l1 = float(m.loss_and_grad(td, 0)); lref, gref = ref["probe"]
     ge = {k: float((m.model[n_].grad - gref[k]).norm() / gref[k].norm()) for k, n_ in (("U", "s_U"), ("b", "s_b"), ("V", "V"))}
+    # the same at the END point of the reference fit (small gradient)
+    with torch.no_grad():
+        m.model["s_U"].copy_(ref["end"]["U"]); m.model["s_b"].copy_(ref["end"]["b"]); m.model["V"].copy_(ref["end"]["V"])
+    l2_ = float(m.loss_and_grad(td, 0)); lref2, gref2 = ref["probe_end"]
+    ge2 = {k: float((m.model[n_].grad - gref2[k]).norm() / gref2[k].norm()) for k, n_ in (("U", "s_U"), ("b", "s_b"), ("V", "V"))}
+    gn2 = {k: float(gref2[k].norm()) for k in gref2}
     m2 = RRRGD(td, 3, l2=100.0, planes=planes, operand=operand); m2.to(dev)
     losses = []
     o = m2.make_optimizer(history_dtype=hd)
@@ -44,6 +50,7 @@ for nm in names:
     val = float(torch.sum(m2.compute_MSE_RRRGD(td, 1)["s"]))
     fit_ms = (time.perf_counter() - t1) * 1e3
     print(f"{nm:8s} hist={str(hd)[6:]:8s} val SSE {val:.4f} rel diff {abs(val-ref_val)/ref_val:.3e} | per-eval loss rel {abs(l1-lref)/abs(lref):.2e} "
-          f"grad rel-L2 U {ge['U']:.2e} b {ge['b']:.2e} V {ge['V']:.2e} | fit {fit_ms:.1f} ms", flush=True)
+          f"grad rel-L2 U {ge['U']:.2e} b {ge['b']:.2e} V {ge['V']:.2e} | END point: loss rel {abs(l2_-lref2)/abs(lref2):.2e} grad rel-L2 "
+          f"U {ge2['U']:.2e} b {ge2['b']:.2e} V {ge2['V']:.2e} (|g| U {gn2['U']:.2e} b {gn2['b']:.2e} V {gn2['V']:.2e}) | fit {fit_ms:.1f} ms", flush=True)
     del m, m2, td, entry, o
     torch.cuda.empty_cache()

@@ -56,7 +56,7 @@ struct DenseBwdDesc {
   //   dvpart[((cta * 8 + w) * T + t) * 3 + j], cta < rrr_bwd_dense_ctas(C1), w < 8  (G is not written)
   const float* dv_U32 = nullptr;  // [N][dv_ldu][3] fp32
   long long dv_ldu = 0, dv_N = 0;
-  float* dvpart = nullptr;
+  double* dvpart = nullptr;
 };
 inline long long rrr_bwd_dense_ctas(long long C1) { return 2 * ((C1 + 255) / 256); }
 // Dense-per-time-bin RRR forward (rrr_fwd_dense_pair_kernel): Y[(t,k), n] = sum_c Xc[(t,k), c] * (U[n,c,:] . V[:,t]) * isd[t,c],

@@ -810,7 +810,7 @@ struct DensePairParams {
   const float* U32;          // [N][ldu][3] fp32
   long long ldu;
   int N;
-  float* dvpart;
+  double* dvpart;
 };
 
 __device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t* r) {
@@ -1012,7 +1012,8 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           tc_ld8_issue(t_g0 + (uint32_t)(c * 8), a0[slot]);
           if (c + 1 < HW8) { tc_ld8_issue(td + (uint32_t)(c * 8 + 8), d[slot] + 8); tc_ld8_issue(t_g0 + (uint32_t)(c * 8 + 8), a0[slot] + 8); }
         };
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+        // dV is a small difference of large sums (2.6 M products per entry): eight columns at a time in fp32, then float64
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
         issue_dv(0, 0);
         tc_wait_ld();
         if (kRounds == 1) release_d();
@@ -1022,14 +1023,19 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const bool two = (c + 1 < HW8);
           if (r + 1 < kRounds) issue_dv(r + 1, slot ^ 1);
 #pragma unroll
-          for (int i = 0; i < kN; ++i) {
-            if (i < 8 || two) {
-              const int col = (c * 8 + i) < W ? (c * 8 + i) : 0;
-              // columns past N hold whatever the pad rows of the residual operand contain (never written): 0 * NaN must not happen
-              const float dv = (hsel * W + c * 8 + i) < p.N ? __uint_as_float(d[slot][i]) : 0.f;
-              p0 = fmaf(__uint_as_float(a0[slot][i]), dv, p0);
-              p1 = fmaf(g1[col], dv, p1);
-              p2 = fmaf(g2[col], dv, p2);
+          for (int i8 = 0; i8 < kN; i8 += 8) {
+            if (i8 == 0 || two) {
+              float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+              for (int i = i8; i < i8 + 8; ++i) {
+                const int col = (c * 8 + i) < W ? (c * 8 + i) : 0;
+                // columns past N hold whatever the pad rows of the residual operand contain (never written): 0 * NaN must not happen
+                const float dv = (hsel * W + c * 8 + i) < p.N ? __uint_as_float(d[slot][i]) : 0.f;
+                p0 = fmaf(__uint_as_float(a0[slot][i]), dv, p0);
+                p1 = fmaf(g1[col], dv, p1);
+                p2 = fmaf(g2[col], dv, p2);
+              }
+              q0 += (double)p0; q1 += (double)p1; q2 += (double)p2;
             }
           }
           if (r + 1 < kRounds) {
@@ -1040,16 +1046,16 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         // the 1/std of this row and bin (sc), then the sum over the warp's 32 feature rows.  Rows past C1 do not exist: a
         // phantom second tile of the last pair (odd tile count) re-reads the last real tile and must not be counted twice
         if (m_tile * BM + q * 32 + lane >= p.C1) sc = 0.f;
-        p0 *= sc; p1 *= sc; p2 *= sc;
+        q0 *= (double)sc; q1 *= (double)sc; q2 *= (double)sc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-          p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-          p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          q2 += __shfl_xor_sync(0xffffffffu, q2, o);
         }
         if (lane == 0) {
-          float* o3 = p.dvpart + (((long long)blockIdx.x * 8 + (warp - 4)) * p.T + t) * 3;
-          o3[0] = p0; o3[1] = p1; o3[2] = p2;
+          double* o3 = p.dvpart + (((long long)blockIdx.x * 8 + (warp - 4)) * p.T + t) * 3;
+          o3[0] = q0; o3[1] = q1; o3[2] = q2;
         }
         continue;
       }

@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
   AT sse = (AT)0, sdb = (AT)0;
   constexpr int RPW = kEpiRows / 8;   // rows per warp
   // all loads of the block's tile are issued before the first use
-  float z[RPW][RMAX];
+  AT z[RPW][RMAX];
   AT yv[RPW];
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
@@ -731,16 +731,16 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
     const bool ok = k < K && n < N;
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
-      z[i][j] = 0.f;
+      z[i][j] = (AT)0;
       if (ok && j < r) {
         const float* zp = Z + d * ldz + (long long)j * Npad + n;
         if (splits == 1) {
-          z[i][j] = __ldg(zp);
-        } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator
+          z[i][j] = (AT)__ldg(zp);
+        } else {  // split-K partials (high-precision mode): ordered sum, wide accumulator; the loads are independent
           double zs = 0.0;
-#pragma unroll 1
-          for (int sp = 0; sp < splits; ++sp) zs += (double)zp[(long long)sp * split_stride];
-          z[i][j] = (float)zs;
+#pragma unroll 4
+          for (int sp = 0; sp < splits; ++sp) zs += (double)__ldg(zp + (long long)sp * split_stride);
+          z[i][j] = (AT)zs;
         }
       }
     }
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
       AT acc = (AT)xls[rl] * bn;
 #pragma unroll
       for (int j = 0; j < RMAX; ++j)
-        if (j < r) acc = fma(vt[j], (AT)z[i][j], acc);
+        if (j < r) acc = fma(vt[j], z[i][j], acc);
       if constexpr (kPredict) {
         yhat[(k * T + t) * N + n] = (double)acc;
       } else {
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
         sdb = fma((AT)xls[rl], res, sdb);
 #pragma unroll
         for (int j = 0; j < RMAX; ++j)
-          if (j < r) pvacc[j] = fma(res, (AT)z[i][j], pvacc[j]);
+          if (j < r) pvacc[j] = fma(res, z[i][j], pvacc[j]);
       }
     }
     if constexpr (!kPredict) Rs[rl][lane] = res;
@@ -1169,26 +1169,32 @@ __global__ void __launch_bounds__(256) epi_d_kernel(const float* __restrict__ Y,
   }
 }
 
-// dV[j,t] += 2 * ( sum over the dV pass's partials  -  sum_n SR[t,n] M1[t][j][n] )       (one thread per (j, t), ordered sums)
-__global__ void __launch_bounds__(128) dv_reduce_kernel(const float* __restrict__ dvpart, long long nparts, const float* __restrict__ SR,
+// dV[j,t] += 2 * ( sum over the dV pass's partials  -  sum_n SR[t,n] M1[t][j][n] ):  one block per (j, t); the partials are
+// summed in a fixed order (thread i takes partials i, i+128, ..., then a fixed tree)
+__global__ void __launch_bounds__(128) dv_reduce_kernel(const double* __restrict__ dvpart, long long nparts, const float* __restrict__ SR,
                                                         const double* __restrict__ M1, long long ldm, long long T, long long N,
                                                         long long Npad, int r, double* __restrict__ dV) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)r * T) return;
+  __shared__ double sh[128];
+  const long long e = blockIdx.x;
   const long long j = e / T, t = e % T;
   double s = 0.0;
-#pragma unroll 8
-  for (long long q = 0; q < nparts; ++q) s += (double)dvpart[(q * T + t) * 3 + j];
-  double corr = 0.0;
-  for (long long n = 0; n < N; ++n) corr = fma((double)SR[t * Npad + n], M1[t * ldm + j * Npad + n], corr);
-  dV[e] += 2.0 * (s - corr);
+  for (long long q = threadIdx.x; q < nparts; q += 128) s += dvpart[(q * T + t) * 3 + j];
+  for (long long n = threadIdx.x; n < N; n += 128) s -= (double)SR[t * Npad + n] * M1[t * ldm + j * Npad + n];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 64; h > 0; h >>= 1) {
+    if (threadIdx.x < h) sh[threadIdx.x] += sh[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dV[e] += 2.0 * sh[0];
 }
 
 // ------------------------------------------------------------------ host orchestration
 struct Ws {
   uint16_t *Ub, *RV;
   float *Z, *Gacc, *SR;
-  float *U32, *bscale, *dvpart;   // dense-forward mode
+  float *U32, *bscale;            // dense-forward mode
+  double* dvpart;
   unsigned* umax;
   double* M1;
   long long ldm, dv_parts;
@@ -1217,9 +1223,9 @@ static int hp_splits(long long k_elems, int planes, int mode) {
     // exact-operand modes: a few accumulation runs.  The truncation of the fp32 accumulator is the largest error left in a
     // closure evaluation (per-evaluation loss error ~1.3e-8 per MMA step of full magnitude); the whole fit tolerates the
     // smooth part of it, but its path-dependent part is amplified like operand noise (profiles/r02_parity_*.txt).
-    // VS_RRR_RUN_EXACT = k-blocks per run (default 72: 4 runs at 18,260 features).
+    // VS_RRR_RUN_EXACT = k-blocks per run (default 144: 2 runs at 18,260 features; profiles/r02_parity_probes.txt).
     static int runx = -1;
-    if (runx < 0) { const char* e = getenv("VS_RRR_RUN_EXACT"); runx = e ? atoi(e) : 72; if (runx <= 0) runx = 1 << 30; }
+    if (runx < 0) { const char* e = getenv("VS_RRR_RUN_EXACT"); runx = e ? atoi(e) : 144; if (runx <= 0) runx = 1 << 30; }
     long long sx = ceil_div(ceil_div(k_elems, 64), runx);
     return (int)(sx < 1 ? 1 : (sx > 64 ? 64 : sx));
   }
@@ -1261,7 +1267,7 @@ static Ws carve(const vs_rrr_dims& d, void* base) {
     w.bscale = (float*)take((size_t)d.T * 4);
     w.umax = (unsigned*)take(64);
     w.M1 = (double*)take((size_t)d.T * w.ldm * 8);
-    w.dvpart = (float*)take((size_t)w.dv_parts * d.T * 3 * 4);
+    w.dvpart = (double*)take((size_t)w.dv_parts * d.T * 3 * 8);
   }
   w.bal = take(tc::balance_ws_bytes());
   w.Gp = (double*)take((size_t)w.gp_blocks * d.r * d.r * 8);
@@ -1489,7 +1495,7 @@ static int closure_dense(const vs_rrr_dims& d, const uint16_t* Xi, const ExactAr
     dv.dv_U32 = w.U32; dv.dv_ldu = d.ldc; dv.dv_N = d.N; dv.dvpart = w.dvpart;
     rc = tc::rrr_bwd_dense(dv, st);
     if (rc) return rc;
-    VS_LAUNCH(dv_reduce_kernel, (unsigned)ceil_div((long long)r * d.T, 128), 128, 0, st, w.dvpart, w.dv_parts, w.SR, w.M1, w.ldm, (long long)d.T,
+    VS_LAUNCH(dv_reduce_kernel, (unsigned)((long long)r * d.T), 128, 0, st, w.dvpart, w.dv_parts, w.SR, w.M1, w.ldm, (long long)d.T,
               (long long)d.N, w.Npad, r, dV);
   }
   if (dU) {
