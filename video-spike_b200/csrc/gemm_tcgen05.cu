@@ -1126,11 +1126,14 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // read; A = Xc (exact integers frame - round(mean), half) comes by TMA.  A CTA pair (cta_group::2, UMMA 256 x Npad) owns
 // 256 trials of three bins: 3 accumulators of Npad columns in TMEM (3 * 144 = 432 of 512).  Each CTA generates the B rows
 // of HALF of the neurons.  beta and Z never exist in HBM.
-// warp 0 TMA (A tiles), warp 1 MMA issue, warps 3..11 B generators, warps 4..11 drain the accumulators at the end.
-constexpr int FWD_THREADS = 384;
+// warp 0 TMA (A tiles), warp 1 MMA issue, warps 2..19 B generators (one (neuron, 16-byte chunk) item per thread and
+// k-block at N = 144: the generation is ~7 instructions per coefficient, 4,500 warp instructions per k-block against
+// 1,728 clocks of tensor work, so it needs all four schedulers busy), warps 4..11 drain the accumulators at the end.
+constexpr int FWD_THREADS = 640;
 constexpr int FWD_BINS = 3;
-constexpr int FWD_GEN_WARPS = 9;
-constexpr int FWD_GEN_THREADS = FWD_GEN_WARPS * 32;     // 288: 8 sixteen-byte chunks x 36 neuron slots
+constexpr int FWD_GEN_WARP0 = 2;
+constexpr int FWD_GEN_WARPS = 18;
+constexpr int FWD_GEN_THREADS = FWD_GEN_WARPS * 32;     // 576: 8 sixteen-byte chunks x 72 neuron slots
 
 struct DenseFwdParams {
   int K, T, C1, N, Npad;
@@ -1250,9 +1253,9 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
       }
     }
   }
-  if (warp >= 3) {
-    // ===== B generators: thread = (16-byte chunk q of the 128-byte row, neuron slot ns); neurons ns, ns + 36, ... of this half =====
-    const int g = threadIdx.x - 96;
+  if (warp >= FWD_GEN_WARP0) {
+    // ===== B generators: thread = (16-byte chunk q of the 128-byte row, neuron slot ns); neurons ns, ns + 72, ... of this half =====
+    const int g = threadIdx.x - 32 * FWD_GEN_WARP0;
     const int q = g & 7, ns = g >> 3;
     float v[FWD_BINS][3], bs[FWD_BINS];
 #pragma unroll
@@ -1319,7 +1322,7 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
       if (++s == kStages) { s = 0; ph ^= 1u; }
     }
   }
-  if (warp >= 4) {
+  if (warp >= 4 && warp < 12) {
     // ===== drain: Y[(t, k), n] = accumulator / scale; TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 =====
     mbar_wait(bar_done, 0);
     tc_fence_after();
