@@ -21,6 +21,25 @@ mb = RRRGD({"s": eb}, 3, l2=100.0); mb.to(dev)
 opt = ma.make_optimizer()
 it = [0]
 
+# float64 truth at the same parameters (the reference's formulation: einsum + autograd)
+from scipy.ndimage import gaussian_filter1d
+sid = torch.as_tensor(np.asarray(sidx), device=dev)
+X = ftr.to(dev).reshape(K, 120, -1).double()
+mean = X.mean(0); std = X.std(0, unbiased=False).clamp_min(1e-8)
+Xtr = torch.cat([(X - mean) / std, torch.ones(K, 120, 1, dtype=torch.float64, device=dev)], 2)[:, sid]
+del X
+ys = gaussian_filter1d(ctr.numpy().astype(np.float64), 2, axis=1)
+ytr = torch.from_numpy((ys - ys.mean(0)) / np.clip(ys.std(0), 1e-8, None)).to(dev)
+
+
+def truth():
+    U = ma.model["s_U"].detach().clone().requires_grad_(True); V = ma.model["V"].detach().clone().requires_grad_(True)
+    b = ma.model["s_b"].detach().clone().requires_grad_(True)
+    beta = torch.cat([U @ V, b], 1)
+    l = ((torch.einsum("ktc,nct->ktn", Xtr, beta) - ytr) ** 2).sum() + 100.0 * (beta ** 2).sum()
+    l.backward()
+    return float(l), {"U": U.grad, "b": b.grad, "V": V.grad}
+
 def closure():
     opt.zero_grad()
     la = ma.loss_and_grad({"s": ea}, 0)
@@ -31,6 +50,11 @@ def closure():
     gb = {k: mb.model[k].grad.clone() for k in mb.model}
     lb2 = mb.loss_and_grad({"s": eb}, 0)
     same = float(lb) == float(lb2) and all(torch.equal(gb[k], mb.model[k].grad) for k in gb)
+    lt, gt = truth()
+    ea_ = {k.split("_")[-1]: float((ma.model[k].grad - gt[k.split("_")[-1]]).norm() / gt[k.split("_")[-1]].norm()) for k in ma.model}
+    eb_ = {k.split("_")[-1]: float((gb[k] - gt[k.split("_")[-1]]).norm() / gt[k.split("_")[-1]].norm()) for k in ma.model}
+    print(f"        vs float64: |gV| {float(gt['V'].norm()):.3e} |gU| {float(gt['U'].norm()):.3e} | {A}: loss {abs(float(la)-lt)/lt:.1e} U {ea_['U']:.1e} V {ea_['V']:.1e} "
+          f"| {B}: loss {abs(float(lb)-lt)/lt:.1e} U {eb_['U']:.1e} V {eb_['V']:.1e}", flush=True)
     d = {k.split("_")[-1]: float((mb.model[k].grad - ma.model[k].grad).norm() / ma.model[k].grad.norm()) for k in ma.model}
     dm = {k.split("_")[-1]: float((mb.model[k].grad - ma.model[k].grad).abs().max() / ma.model[k].grad.abs().max()) for k in ma.model}
     print(f"eval {it[0]:2d} loss {float(la):.6e} | {B} vs {A}: loss rel {abs(float(lb)-float(la))/abs(float(la)):.2e} grad rel-L2 U {d['U']:.2e} b {d['b']:.2e} V {d['V']:.2e} "

@@ -8,6 +8,14 @@ namespace vs {
 constexpr int kMaxPass = 6;   // plane products accumulated into one tile (3 planes -> 6 products)
 constexpr int kMaxBN = 448;   // widest accumulator tile the tcgen05 kernel keeps in TMEM
 
+// Layout of the fp32 copy of U that the dense-forward generator streams (rank 3): for every 64-feature block kb and neuron n
+// a 768-byte record of 6 x 8 float4; float4 (i, q) holds values 4i..4i+3 of the 24 = 8 features x 3 ranks that generator
+// lane q (features 8q..8q+7 of the block) needs, so the 8 lanes of a neuron read 128 contiguous bytes per load.
+__host__ __device__ inline long long u32g_index(long long n, long long c, int j, long long N) {
+  const long long flat = (c & 7) * 3 + j;
+  return (((((c >> 6) * N + n) * 6 + (flat >> 2)) * 8 + ((c & 63) >> 3)) << 2) + (flat & 3);
+}
+
 namespace tc {
 // K-major operand: rows x k elements, pitch ld (elements), optionally several residual planes
 struct Operand {
@@ -54,7 +62,7 @@ struct DenseBwdDesc {
   long long ldt = 0;
   // dV pass (dense-forward mode, where no Z exists): the same D_t tiles contracted with U instead of accumulated with V:
   //   dvpart[((cta * 8 + w) * T + t) * 3 + j], cta < rrr_bwd_dense_ctas(C1), w < 8  (G is not written)
-  const float* dv_U32 = nullptr;  // [N][dv_ldu][3] fp32
+  const float* dv_U32 = nullptr;  // fp32 copy of U, u32g_index layout
   long long dv_ldu = 0, dv_N = 0;
   double* dvpart = nullptr;
 };
@@ -64,7 +72,7 @@ inline long long rrr_bwd_dense_ctas(long long C1) { return 2 * ((C1 + 255) / 256
 struct DenseFwdDesc {
   const void* Xc = nullptr;     // (K*T, ldc) IEEE half, EXACT integers frame - round(mean), row t*K + k
   long long K = 0, T = 0, C1 = 0, N = 0, Npad = 0, ldc = 0;
-  const float* U32 = nullptr;   // [N][ldu][3] fp32, zero for C1 <= c < ldu
+  const float* U32 = nullptr;   // fp32 copy of U in the u32g_index layout (zero for C1 <= c < ldu)
   const float* isd = nullptr;   // [T][ldu] fp32, zero for C1 <= c < ldu
   long long ldu = 0;            // multiple of 64, >= C1
   const double* V = nullptr;    // (3, T)

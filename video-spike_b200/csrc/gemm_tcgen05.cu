@@ -965,8 +965,9 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const int n = hsel * W + c8 * 8 + i;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f;
           if (n < p.N) {
-            const float* up = p.U32 + ((long long)n * p.ldu + srow) * 3;
-            a0 = __ldg(up); a1 = __ldg(up + 1); a2 = __ldg(up + 2);
+            a0 = __ldg(p.U32 + u32g_index(n, srow, 0, p.N));
+            a1 = __ldg(p.U32 + u32g_index(n, srow, 1, p.N));
+            a2 = __ldg(p.U32 + u32g_index(n, srow, 2, p.N));
           }
           u0[i] = __float_as_uint(a0); g1[c8 * 8 + i] = a1; g2[c8 * 8 + i] = a2;
         }
@@ -1284,10 +1285,11 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
         const int n = rank * h + nl;
         float u[24];
         if (n < p.N) {
-          const float4* up = reinterpret_cast<const float4*>(p.U32 + ((long long)n * p.ldu + c0) * 3);
+          // u32g_index layout: record (kb, n) = 6 x 8 float4, lane q takes float4 (i, q): 128 contiguous bytes per 8 lanes
+          const float4* up = reinterpret_cast<const float4*>(p.U32) + (((long long)kb * p.N + n) * 6) * 8 + q;
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
-            const float4 w = __ldg(up + i);
+            const float4 w = __ldg(up + i * 8);
             u[4 * i] = w.x; u[4 * i + 1] = w.y; u[4 * i + 2] = w.z; u[4 * i + 3] = w.w;
           }
         } else {

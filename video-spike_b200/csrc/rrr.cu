@@ -605,9 +605,9 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
   for (int q = 0; q < kPrepC; ++q) {
     const long long c = c0 + q;
     if (c >= C1) {
-      // dense forward operand: [n][ldu][r] fp32 with zeros in the pad columns (its generator reads whole 64-feature blocks)
+      // dense forward operand (u32g_index layout, rank 3) with zeros in the pad columns: its generator reads whole 64-feature blocks
       if (U32 && c < ldu)
-        for (int j = 0; j < r; ++j) U32[(n * ldu + c) * r + j] = 0.f;
+        for (int j = 0; j < r; ++j) U32[u32g_index(n, c, j, N)] = 0.f;
       continue;
     }
     double u[RMAX];
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
     if (U32) {
 #pragma unroll
       for (int j = 0; j < RMAX; ++j)
-        if (j < r) { const float uf = (float)u[j]; U32[(n * ldu + c) * r + j] = uf; um = fmaxf(um, fabsf(uf)); }
+        if (j < r) { const float uf = (float)u[j]; U32[u32g_index(n, c, j, N)] = uf; um = fmaxf(um, fabsf(uf)); }
     }
 #pragma unroll
     for (int j = 0; j < RMAX; ++j) {
@@ -1215,18 +1215,19 @@ static int hp_splits(long long k_elems, int planes, int mode) {
   // experiment hook: VS_RRR_RUN=<k-blocks per TMEM accumulation run> forces split-K in the single-plane mode too
   static int run1 = -1;
   if (run1 < 0) { const char* e = getenv("VS_RRR_RUN"); run1 = e ? atoi(e) : 0; }
-  // exact-operand mode: one TMEM run.  The truncation of the fp32 accumulator acts as a smooth relative shrink of the
-  // prediction (~1e-4 over 3400 MMA steps), to which the fit is insensitive, unlike to operand rounding noise
-  // (profiles/r02_precision_sim_full.txt: shrink 6e-5 -> 1e-5 on the final validation SSE); split-K partial tiles would
-  // cost more HBM traffic than the GEMM itself.
   if (mode == VS_RRR_MODE_EXACT || mode == VS_RRR_MODE_DENSE) {
     // exact-operand modes: a few accumulation runs.  The truncation of the fp32 accumulator is the largest error left in a
-    // closure evaluation (per-evaluation loss error ~1.3e-8 per MMA step of full magnitude); the whole fit tolerates the
-    // smooth part of it, but its path-dependent part is amplified like operand noise (profiles/r02_parity_*.txt).
-    // VS_RRR_RUN_EXACT = k-blocks per run (default 144: 2 runs at 18,260 features; profiles/r02_parity_probes.txt).
-    static int runx = -1;
-    if (runx < 0) { const char* e = getenv("VS_RRR_RUN_EXACT"); runx = e ? atoi(e) : 144; if (runx <= 0) runx = 1 << 30; }
-    long long sx = ceil_div(ceil_div(k_elems, 64), runx);
+    // closure evaluation (per-evaluation loss error ~1.3e-8 per MMA step of full magnitude).
+    // The drift is mostly a relative SHRINK of the prediction.  Near the V ~ 0 plateau the fit visits after its first steps
+    // (|dV| falls from 1e7 to ~10 while sum |R Z| stays ~1e7) the shrink biases the residual by -eps * yhat, i.e. dV by a
+    // non-cancelling -2 eps (Z^T Z) V: measured 0.5 (4 runs of the factorised forward would give ~0.25) against |dV| = 10
+    // (profiles/r02_mode_diff_probe.txt).  Hence: VS_RRR_RUN_EXACT / VS_RRR_RUN_DENSE = k-blocks per run, defaults 72 (4 runs
+    // of the factorised forward at 18,260 features) and 36 (8 runs of the dense forward, whose hi/lo products interleave and
+    // truncate twice per k-step; its partial matrices are a third of the size).
+    static int runx = -1, rund = -1;
+    if (runx < 0) { const char* e = getenv("VS_RRR_RUN_EXACT"); runx = e ? atoi(e) : 72; if (runx <= 0) runx = 1 << 30; }
+    if (rund < 0) { const char* e = getenv("VS_RRR_RUN_DENSE"); rund = e ? atoi(e) : 36; if (rund <= 0) rund = 1 << 30; }
+    long long sx = ceil_div(ceil_div(k_elems, 64), mode == VS_RRR_MODE_DENSE ? rund : runx);
     return (int)(sx < 1 ? 1 : (sx > 64 ? 64 : sx));
   }
   if (planes < 2) {

@@ -287,7 +287,7 @@ class RRRGD():
         if device_driven is None:     # decisions on the device, no host sync per iteration (optim.FusedLBFGS); VS_LBFGS_DEVICE=0 disables
             device_driven = os.environ.get("VS_LBFGS_DEVICE", "1") != "0"
         # float64 history: one vector per evaluation instead of a pair (half the traffic of the vector passes); VS_LBFGS_COMPACT=0 disables
-        compact = bool(device_driven and history_dtype == torch.float64 and os.environ.get("VS_LBFGS_COMPACT", "0") != "0")
+        compact = bool(device_driven and history_dtype == torch.float64 and os.environ.get("VS_LBFGS_COMPACT", "1") != "0")
         opt = FusedLBFGS(self.model.parameters(), history_dtype=history_dtype, device_driven=device_driven, compact=compact)
         opt.closure_overwrites_grads = True     # loss_and_grad writes every gradient element (see there): zero_grad() need not memset
         return opt

@@ -145,7 +145,7 @@ def train_joint_model(model, train_data_local, model_fname="tmp", save=False, gr
         history_dtype = torch.float32 if model.planes == 1 else torch.float64
     if device_driven is None:
         device_driven = os.environ.get("VS_LBFGS_DEVICE", "1") != "0" and model.model["V"].is_cuda
-    compact = bool(device_driven and history_dtype == torch.float64 and os.environ.get("VS_LBFGS_COMPACT", "0") != "0")
+    compact = bool(device_driven and history_dtype == torch.float64 and os.environ.get("VS_LBFGS_COMPACT", "1") != "0")
     optimizer = ShardedLBFGS(shared, local, group=group, history_dtype=history_dtype, device_driven=device_driven, compact=compact)
     optimizer.closure_overwrites_grads = True
 
