@@ -191,12 +191,25 @@ def sorted_idx_42():
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle)
-def _cpu_rrr_problem(K_s, Kt_s, F, N, seed=0):
-    from oracle import rrr_oracle as ro
-    ftr, ctr, fte, cte = rrr_inputs(K_s, Kt_s, F, N, seed, pinned=False)
-    data, _ = ro.preprocess_session([ftr.numpy(), fte.numpy()], [ctr.numpy().astype(np.float64), cte.numpy().astype(np.float64)],
-                                    sorted_idx_42())
-    return {"s": data}
+def _cpu_rrr_problem(K, Kt, F, N_s, seed=0):
+    """The reference's float64 train_data (src/train_rrr.py:108-171) for ALL K trials and all F features but only N_s
+    neurons.  Frame selection first (the statistics of a frame depend on that frame alone), in place, to bound host memory."""
+    from scipy.ndimage import gaussian_filter1d
+    sidx = sorted_idx_42()
+    ftr, ctr, fte, cte = rrr_inputs(K, Kt, F, N_s, seed, pinned=False)
+    Xs = []
+    mean = std = None
+    for fr in (ftr, fte):
+        x = np.empty((fr.shape[0], len(sidx), F + 1), dtype=np.float64)
+        x[:, :, :F] = fr.numpy()[:, sidx]
+        if mean is None:
+            mean = x[:, :, :F].mean(0); std = np.clip(x[:, :, :F].std(0), 1e-8, None)
+        x[:, :, :F] -= mean; x[:, :, :F] /= std
+        x[:, :, F] = 1.0
+        Xs.append(x)
+    ys = [gaussian_filter1d(c.numpy().astype(np.float64), 2, axis=1) for c in (ctr, cte)]
+    my, sy = ys[0].mean(0), np.clip(ys[0].std(0), 1e-8, None)
+    return {"s": {"X": Xs, "y": [(y - my) / sy for y in ys]}}
 
 
 def _cpu_rrr_fit(td):
@@ -221,22 +234,38 @@ def _cpu_rrr_fit(td):
     return time.perf_counter() - t0, n_eval[0], val
 
 
-def cpu_rrr_sample(F, N, n_fits, n_warm, budget_s, K_full):
-    """Host-core baseline on a BOUNDED sample: K_s trials at full C and N, chosen from one calibration evaluation so that
-    (n_warm + n_fits) whole fits take about budget_s seconds (the cost of a fit is linear in the number of trials, so
-    frames/s measured on K_s trials is the frames/s of the full-size fit).  Returns a dict."""
+def cpu_rrr_sample(F, N, n_fits, n_warm, budget_s, K, Kt):
+    """Host-core baseline on a BOUNDED sample of the workload: ALL K trials and all F features, but only N_s of the N neurons.
+    The terms of the reference's fit scale with the neuron count (beta = (N, C, T) built twice per closure evaluation, the
+    einsum K*T*C*N and its backward, the L-BFGS vectors N*C*r) up to a per-evaluation constant (einsum's handling of X):
+    two calibration evaluations (4 and 12 neurons) give the affine model  eval_s = a + b * neurons,  N_s is chosen from it so
+    that (n_warm + n_fits) whole fits take about budget_s seconds, and the measured fit time is carried to N neurons by
+    (a + b N) / (a + b N_s).  (Sampling TRIALS instead would leave the beta term, ~2 s per evaluation at N = 144, unsampled:
+    a 4-trial fit takes as long as a 40-trial one.)"""
     from oracle import rrr_oracle as ro
     torch.set_num_threads(os.cpu_count() or 1)
-    K0 = 8
-    td0 = _cpu_rrr_problem(K0, 2, F, N)
-    p0 = ro.rrr_init(td0, 3)
-    ro.loss_and_grad_autograd(p0, td0, 100.0)                    # warm-up (allocator, threads)
-    t0 = time.perf_counter()
-    ro.loss_and_grad_autograd(p0, td0, 100.0)
-    per_trial_eval = (time.perf_counter() - t0) / K0
-    K_s = int(budget_s / ((n_warm + n_fits) * 21.5 * per_trial_eval))
-    K_s = max(4, min(K_full, K_s))
-    td = _cpu_rrr_problem(K_s, max(2, K_s // 5), F, N)
+
+    full = _cpu_rrr_problem(K, Kt, F, N)                          # X does not depend on the neuron count: built once
+
+    def sub(n):
+        return {"s": {"X": full["s"]["X"], "y": [np.ascontiguousarray(y[:, :, :n]) for y in full["s"]["y"]]}}
+
+    def eval_s(n):
+        td = sub(n)
+        p = ro.rrr_init(td, 3)
+        ro.loss_and_grad_autograd(p, td, 100.0)                  # warm-up (allocator, threads)
+        t0 = time.perf_counter()
+        ro.loss_and_grad_autograd(p, td, 100.0)
+        return time.perf_counter() - t0
+
+    n_lo, n_hi = min(N, 4), min(N, 12)
+    t_lo, t_hi = eval_s(n_lo), eval_s(n_hi)
+    b = max((t_hi - t_lo) / max(n_hi - n_lo, 1), 1e-9)           # seconds per evaluation per neuron
+    a = max(t_lo - b * n_lo, 0.0)                                # seconds per evaluation independent of the neuron count
+    per_fit = budget_s / (n_warm + n_fits)
+    N_s = int((per_fit / 22.0 - a) / b)
+    N_s = max(1, min(N, N_s))
+    td = sub(N_s)
     for _ in range(n_warm):
         _cpu_rrr_fit(td)
     secs, evals = [], 0
@@ -244,8 +273,11 @@ def cpu_rrr_sample(F, N, n_fits, n_warm, budget_s, K_full):
         dt, evals, _ = _cpu_rrr_fit(td)
         secs.append(dt)
     fit_s = float(np.mean(secs))
-    return {"value": K_s * FRAMES_PER_TRIAL / fit_s, "fit_s": fit_s, "trials": K_s, "trials_val": max(2, K_s // 5), "evals": evals,
-            "fits_timed": n_fits, "fits_warmup": n_warm, "calibration_s_per_trial_eval": per_trial_eval}
+    factor = (a + b * N_s) / (a + b * N)                          # measured fit time -> full neuron count (affine model)
+    return {"value": K * FRAMES_PER_TRIAL / fit_s * factor, "fit_s": fit_s, "fit_s_each": [round(x, 2) for x in secs], "neurons": N_s,
+            "evals": evals, "fits_timed": n_fits, "fits_warmup": n_warm, "factor": factor,
+            "calibration": {f"eval_s_at_{n_lo}_neurons": t_lo, f"eval_s_at_{n_hi}_neurons": t_hi, "a_s_per_eval": a, "b_s_per_eval_per_neuron": b},
+            "fit_s_full_size_estimate": fit_s / factor}
 
 
 def cpu_linear_sample(B, D, N, steps=2):
@@ -268,15 +300,20 @@ def reference_arm(args, rank, world):
         return
     cores = os.cpu_count() or 1
     if args.workload != "linear":
-        r = cpu_rrr_sample(args.features, args.neurons, max(1, args.steps), max(0, args.warmup), args.ref_budget, args.trials)
+        r = cpu_rrr_sample(args.features, args.neurons, max(1, args.steps), max(0, args.warmup), args.ref_budget, args.trials, args.trials_test)
         sample = (f"oracle whole fits (CPU port of src/model/rrr.py:164-202: autograd closure, torch fp64, + L-BFGS vector work + validation "
-                  f"pass) on {r['trials']} train / {r['trials_val']} val trials x 120 frames at full C={args.features + 1}, N={args.neurons}: "
-                  f"{r['fits_warmup']} warm-up + {r['fits_timed']} timed fits of {r['evals']} closure evaluations, {r['fit_s']:.2f} s per fit; "
-                  f"the cost of a fit is linear in the trial count, so frames/s on the sample is the full-size figure")
+                  f"pass) on ALL {args.trials} train / {args.trials_test} val trials x 120 frames at full C={args.features + 1}, for {r['neurons']} of the "
+                  f"{args.neurons} neurons: {r['fits_warmup']} warm-up + {r['fits_timed']} timed fits of {r['evals']} closure evaluations, "
+                  f"{r['fit_s']:.2f} s per fit; carried to {args.neurons} neurons with the affine model eval_s = a + b*neurons calibrated in "
+                  f"this run ({r['calibration']}): value = measured frames/s x {r['factor']:.4f} (full-size fit estimate "
+                  f"{r['fit_s_full_size_estimate']:.0f} s)")
         cfg = rrr_config(args, world)
-        cfg.update({"trials_train": r["trials"], "trials_test": r["trials_val"], "sessions": 1, "parallelism": f"host cores x{cores}",
-                    "operand_mode": "float64 (reference)", "lbfgs": "1 step, max_iter 20 (oracle restatement of torch.optim.LBFGS)",
-                    "sample_of_trials_train": args.trials, "extrapolated": False})
+        cfg.update({"neurons": r["neurons"], "neurons_full": args.neurons, "sessions": 1, "parallelism": f"host cores x{cores}",
+                    "operand_mode": "float64 (reference)", "operand_planes": None, "operand_format": "float64",
+                    "lbfgs": "1 step, max_iter 20 (oracle restatement of torch.optim.LBFGS)",
+                    "extrapolated": r["neurons"] < args.neurons,
+                    "extrapolation": {"sampled": "neurons", "run": r["neurons"], "full": args.neurons, "factor_on_value": r["factor"],
+                                      "model": "eval_s = a + b * neurons, two calibration evaluations in this run", "calibration": r["calibration"]}})
         v, ms = r["value"], r["fit_s"] * 1e3
     else:
         v, dt = cpu_linear_sample(args.batch, args.input_dim, args.neurons, steps=max(1, min(args.steps, 3)))
@@ -598,11 +635,13 @@ def run_rrr(args, rank, world, local):
         return None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_rrr_sample(F, N, 1, 0, args.cpu_budget, K)
+        r = cpu_rrr_sample(F, N, 1, 0, args.cpu_budget, K, Kt)
         cpu = {"value": r["value"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle whole fit (CPU port of src/model/rrr.py:164-202, torch fp64 autograd closure + L-BFGS + validation pass) on "
-                         f"{r['trials']} train / {r['trials_val']} val trials x 120 frames at full C={C}, N={N}: 1 fit of {r['evals']} closure "
-                         f"evaluations, {r['fit_s']:.1f} s; cost is linear in the trial count"}
+               "sample": f"oracle whole fit (CPU port of src/model/rrr.py:164-202, torch fp64 autograd closure + L-BFGS + validation pass) on ALL "
+                         f"{K} train / {Kt} val trials x 120 frames at full C={C}, for {r['neurons']} of the {N} neurons: 1 fit of {r['evals']} closure "
+                         f"evaluations, {r['fit_s']:.1f} s; carried to {N} neurons with eval_s = a + b*neurons calibrated in this run: value = measured x {r['factor']:.4f}",
+               "extrapolated": r["neurons"] < N, "neurons_run": r["neurons"], "factor_on_value": r["factor"], "calibration": r["calibration"],
+               "fit_s_full_size_estimate": r["fit_s_full_size_estimate"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if model_fmt == 1 else "bf16",

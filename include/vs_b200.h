@@ -435,7 +435,7 @@ int vs_gemm_tn(const void* A, const void* B, float* C, int64_t M, int64_t N, int
 int64_t vs_launch_count(void);
 void vs_launch_count_reset(void);
 /* Per-kernel device timing for the roofline report: when enabled, the dominant kernels (tag 0 = the
- * tcgen05 GEMM, tag 1 = fused dW+AdamW, tag 2 = the dense RRR backward) are bracketed by CUDA events on the launching stream.
+ * tcgen05 GEMM, tag 1 = fused dW+AdamW, tag 2 = the dense RRR backward, tag 3 = the dense RRR forward, tag 4 = its dV pass) are bracketed by CUDA events on the launching stream.
  * vs_profile_read sums the recorded intervals of one tag and returns how many there were. */
 void vs_profile_enable(int on);
 int64_t vs_profile_read(int tag, double* total_ms, double* min_ms, double* max_ms);
