@@ -18,7 +18,7 @@ python - <<PY
 import json
 for nm in ("joint", "indep", "both"):
     try:
-        d = json.load(open("gpurun_out/r02m_%s_$N.json" % nm))
+        d = json.loads([l for l in open("gpurun_out/r02m_%s_$N.json" % nm) if l.startswith("{")][-1])
         print(nm, "n_gpus", d["n_gpus"], "ms", round(d["ms_per_step"], 2), "value", round(d["value"]), "e2e ms", round(d["e2e"]["ms_per_step"], 1), d["config"]["parallelism"][:60],
               "| linear", (d.get("linear") or {}).get("ms_per_step"))
     except Exception as e:
