@@ -338,7 +338,8 @@ def rrr_mode_of(args):
 def rrr_config(args, world):
     mode = rrr_mode_of(args)
     exact = mode in ("exact", "dense")
-    joint = world > 1 and not args.independent
+    strong = world > 1 and getattr(args, "strong", False)
+    joint = world > 1 and not args.independent and not strong
     planes = 2 if exact else (args.planes or 1)
     if mode == "dense":
         fmt = ("dense: both contractions per time bin on the exact integer frames (half): forward x hi+lo coefficient planes generated on chip, "
@@ -349,7 +350,8 @@ def rrr_config(args, world):
     else:
         fmt = (os.environ.get("VS_RRR_OPERAND") or "bf16") + f" x {planes} plane(s) (16-bit tensor-core operands, fp32 accumulate in TMEM)"
     hist = "float64" if planes > 1 else "float32"
-    return {"workload": "rrr_joint_fit, shared V across sessions (BASELINE configs[2])" if joint else "rrr_single_session_fit (BASELINE configs[1])",
+    return {"workload": "rrr_joint_fit, shared V across sessions (BASELINE configs[2])" if joint else
+                        ("rrr_single_session_fit (BASELINE configs[1]), trials sharded over the GPUs" if strong else "rrr_single_session_fit (BASELINE configs[1])"),
             "trials_train": args.trials, "trials_test": args.trials_test,
             "frames_per_trial": FRAMES_PER_TRIAL, "frame_shape": "1x110x166", "features": args.features, "time_bins": 100,
             "neurons": args.neurons, "rank": 3, "l2": 100, "operand_mode": mode, "operand_planes": planes,
@@ -357,8 +359,10 @@ def rrr_config(args, world):
             "lbfgs": f"1 step, max_iter 20 (20 closure evals), history {hist}, "
                      + ("device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else "host-driven")
                      + (", inner products sharded over the ranks" if joint else ""),
-            "sessions": world,
-            "parallelism": (f"joint model over {world} sessions, one per GPU: shared V; per closure evaluation ONE NCCL all-reduce of [dV, loss], "
+            "sessions": 1 if strong else world,
+            "parallelism": (f"ONE session, trials sharded over {world} GPUs ({args.trials // world} train trials each), parameters and L-BFGS state replicated: "
+                            f"per closure evaluation ONE NCCL all-reduce of the flat gradient ({(args.neurons * (args.features + 1) * 3 + 300 + args.neurons * 100) * 8 / 1e6:.0f} MB float64) and one of the loss"
+                            if strong else f"joint model over {world} sessions, one per GPU: shared V; per closure evaluation ONE NCCL all-reduce of [dV, loss], "
                             f"per L-BFGS iteration ONE NCCL all-gather of the {8 + 6 * 100 + 1} optimiser scalars (stream-ordered, no host sync)"
                             if joint else (f"independent sessions, one per GPU x{world} (no collective)" if world > 1 else "single GPU")),
             "l2_cache": "operands (>= 1.46 GB per pass) exceed the 126 MB L2; no flush needed"}
@@ -453,20 +457,34 @@ def run_rrr(args, rank, world, local):
     mode = rrr_mode_of(args)
     planes = None if mode == "exact" else (args.planes or 1)
     sidx = sorted_idx_42()
-    ftr, ctr, fte, cte = rrr_inputs(K, Kt, F, N, seed=rank, pinned=True)
+    strong = world > 1 and args.strong            # ONE session, its trials sharded over the ranks (every rank generates the same session)
+    ftr, ctr, fte, cte = rrr_inputs(K, Kt, F, N, seed=0 if strong else rank, pinned=True)
+    if strong:
+        cut = lambda n: (n * rank // world, n * (rank + 1) // world)
+        (ka, kb), (ta, tb) = cut(K), cut(Kt)
+        ftr_l, ctr_l, fte_l, cte_l = ftr[ka:kb], ctr[ka:kb], fte[ta:tb], cte[ta:tb]
     # bytes that cross PCIe per fit: the 100 selected frames of every trial (vs_h2d_select_frames) + the spike counts
     h2d = (ftr.numel() + fte.numel()) // ftr.shape[1] * len(sidx) + 4 * (ctr.numel() + cte.numel())
+    if strong:
+        from parallel import pack_trial_shard, build_trial_sharded_model, fit_trial_sharded
+        h2d = (ftr_l.numel() + fte_l.numel()) // ftr.shape[1] * len(sidx) + 4 * (ctr_l.numel() + cte_l.numel())
 
     # ---- resident-input measurement: operands packed once, fit repeated
-    entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, mode=mode)
+    if strong:
+        entry = pack_trial_shard(ftr_l, ctr_l, fte_l, cte_l, sidx, 3, planes=planes or 1, device=dev, mode=mode)
+    else:
+        entry = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, mode=mode)
     # N > 1 (BASELINE configs[2]): ONE model over all ranks' sessions with a shared V (src/model/rrr.py:37-49); rank r holds
     # session r's U, b and operands; [dV, loss] all-reduced per evaluation, the L-BFGS scalars all-gathered per iteration
-    joint = world > 1 and not args.independent
+    joint = world > 1 and not args.independent and not strong
     eid = f"s{rank:02d}" if joint else "s"
     plan = [(f"s{r:02d}", N, F + 1, 100) for r in range(world)] if joint else None
     td = {eid: entry}
-    model = RRRGD(td, 3, l2=100.0, planes=planes, init_plan=plan)
-    model.to(dev)
+    if strong:
+        model = build_trial_sharded_model(entry, 100.0, 3, eid=eid)
+    else:
+        model = RRRGD(td, 3, l2=100.0, planes=planes, init_plan=plan)
+        model.to(dev)
     model_fmt, model_planes = model.fmt, model.planes
     init = {k: v.detach().clone() for k, v in model.model.items()}
     if joint:
@@ -476,7 +494,9 @@ def run_rrr(args, rank, world, local):
         with torch.no_grad():
             for k, v in init.items():
                 model.model[k].copy_(v)
-        if joint:
+        if strong:
+            _, res = fit_trial_sharded(model, entry, eid=eid)
+        elif joint:
             _, res = train_joint_model(model, td)
         else:
             opt = model.make_optimizer()                   # what train_model_main builds (rrr.py:199 semantics)
@@ -504,7 +524,11 @@ def run_rrr(args, rank, world, local):
     n_dv, dv_ms, _, _ = vs.profile_read(4)                    # dV pass of the dense backward kernel (dense mode)
     vs.lib.vs_profile_enable(0)
     evals = (model.n_closure_evals - evals0) / args.steps
-    value = world * K * FRAMES_PER_TRIAL / (ms * 1e-3)
+    n_sessions = 1 if strong else world
+    value = n_sessions * K * FRAMES_PER_TRIAL / (ms * 1e-3)
+    K_full, Kt_full = K, Kt
+    if strong:                                      # the kernels below ran on this rank's shard of the trials
+        K, Kt = kb - ka, tb - ta
 
     # roofline of the dominant kernels: algorithmic FLOPs (2*K*T*C*N per contraction, i.e. the dense formulation)
     # or bytes, summed over the launches of the timed region / their summed event-bracketed duration.
@@ -565,7 +589,14 @@ def run_rrr(args, rank, world, local):
     # ---- parity of the timed configuration (outside every timed region) against an INDEPENDENT float64 dense fit on the
     # GPU (the reference's formulation in torch: einsum + autograd + torch.optim.LBFGS), same session
     parity = None
-    if rank == 0 and not args.no_parity and not joint:
+    if rank == 0 and not args.no_parity and strong:
+        ref = fp64_dense_reference(ftr, ctr, fte, cte, sidx, dev)
+        parity = {"reference": "float64 dense fit of the WHOLE session on one GPU (torch einsum + autograd + torch.optim.LBFGS; src/model/rrr.py:79-155,164-202)",
+                  "fit_val_sse": float(mse), "fit_val_sse_fp64": ref["val_sse"], "fit_rel_diff": abs(float(mse) - ref["val_sse"]) / ref["val_sse"],
+                  "tolerance": 1e-3, "within_tolerance": bool(abs(float(mse) - ref["val_sse"]) / ref["val_sse"] <= 1e-3), "fp64_evals": ref["evals"]}
+        del ref
+        torch.cuda.empty_cache()
+    if rank == 0 and not args.no_parity and not joint and not strong:
         ref = fp64_dense_reference(ftr, ctr, fte, cte, sidx, dev)
         with torch.no_grad():
             model.model["s_U"].copy_(ref["start"]["U"]); model.model["s_b"].copy_(ref["start"]["b"]); model.model["V"].copy_(ref["start"]["V"])
@@ -591,7 +622,11 @@ def run_rrr(args, rank, world, local):
             return _e2e_fit()
 
     def _e2e_fit():
-        if joint:
+        if strong:
+            ent = pack_trial_shard(ftr_l, ctr_l, fte_l, cte_l, sidx, 3, planes=planes or 1, device=dev, mode=mode)
+            m = build_trial_sharded_model(ent, 100.0, 3, eid=eid)
+            _, res = fit_trial_sharded(m, ent, eid=eid)
+        elif joint:
             ent = pack_session_from_frames(ftr, ctr, fte, cte, sidx, 3, planes=planes, device=dev, mode=mode)
             m = RRRGD({eid: ent}, 3, l2=100.0, planes=planes, init_plan=plan, device=dev)
             _, res = train_joint_model(m, {eid: ent})
@@ -616,11 +651,13 @@ def run_rrr(args, rank, world, local):
     gc.enable()
     mean_s = max_over_ranks(float(np.mean(each)) * 1e-3, world, dev)
     med_s = max_over_ranks(float(np.median(each)) * 1e-3, world, dev)
-    e2e = {"value": world * K * FRAMES_PER_TRIAL / mean_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+    K, Kt = K_full, Kt_full
+    e2e = {"value": n_sessions * K * FRAMES_PER_TRIAL / mean_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
            "ms_per_step": mean_s * 1e3, "statistic": f"mean of {n_e2e} consecutive calls (max over ranks)",
-           "median_ms_per_step": med_s * 1e3, "value_at_median": world * K * FRAMES_PER_TRIAL / med_s,
+           "median_ms_per_step": med_s * 1e3, "value_at_median": n_sessions * K * FRAMES_PER_TRIAL / med_s,
            "ms_each_rank0": [round(x, 2) for x in each],
-           "path": ("pack_session_from_frames(pinned uint8 frames) -> RRRGD(init_plan) -> parallel.train_joint_model -> float(mse_val_mean)" if joint
+           "path": ("parallel.pack_trial_shard(this rank's trials, pinned uint8 frames) -> build_trial_sharded_model -> fit_trial_sharded -> float(mse_val_mean)" if strong
+                    else "pack_session_from_frames(pinned uint8 frames) -> RRRGD(init_plan) -> parallel.train_joint_model -> float(mse_val_mean)" if joint
                     else "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)")}
 
     # ---- the reference's own entry point: train_model_main(train_data) with the float64 numpy arrays train_rrr.py builds
@@ -643,7 +680,7 @@ def run_rrr(args, rank, world, local):
                "extrapolated": r["neurons"] < N, "neurons_run": r["neurons"], "factor_on_value": r["factor"], "calibration": r["calibration"],
                "fit_s_full_size_estimate": r["fit_s_full_size_estimate"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f16" if model_fmt == 1 else "bf16",
             "data": "synthetic", "config": rrr_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "closure_evals_per_step": evals, "val_sse": float(mse), "val_sse_e2e": val, "parity": parity}
@@ -850,6 +887,7 @@ def main():
     ap.add_argument("--dropin-e2e", dest="dropin_e2e", type=int, default=2, help="samples of the float64-numpy drop-in e2e (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="rrr, N > 1: ONE session with its trials sharded over the ranks (gradient all-reduce per evaluation)")
     ap.add_argument("--independent", action="store_true", help="rrr, N > 1: independent per-session fits instead of the joint shared-V model")
     ap.add_argument("--joint", action="store_true", help="(default for N > 1; kept for compatibility)")
     args = ap.parse_args()

@@ -33,6 +33,8 @@ def test_joint_shared_v_model_on_two_gpus_equals_one_gpu(device_driven):
     assert "bit-identical across ranks: True" in out
 
 
-def test_one_session_trial_sharded_on_two_gpus_equals_one_gpu():
-    """the trials of ONE session over 2 ranks (global z-score statistics, gradient all-reduce)."""
-    _torchrun("trial_shard_check.py", port=29621)
+@pytest.mark.parametrize("mode", ["classic", "exact"])
+def test_one_session_trial_sharded_on_two_gpus_equals_one_gpu(mode):
+    """the trials of ONE session over 2 ranks (global z-score statistics, gradient all-reduce), in the
+    classic 3-plane layout and in the default exact-operand layout."""
+    _torchrun("trial_shard_check.py", env={"MODE": mode}, port=29621 + (mode == "exact"))

@@ -490,12 +490,14 @@ def train_model_main(train_data, l2, n_comp, model_fname, save=True, planes=None
 # R0 on the device: the preprocessing of src/train_rrr.py:108-171 for the video modalities, from raw
 # uint8 frames, without ever forming the float64 (K, T, C) matrix on the host.
 def pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=None,
-                             smooth_w=2.0, device=None, operand=None, mode=None):
+                             smooth_w=2.0, device=None, operand=None, mode=None, stats_hook=None):
     """frames_*: uint8 (K, Tf, ...) torch tensors (pinned host or CUDA); counts_*: (K, T, N) spike counts.
     Mirrors train_rrr.py: y smoothed with gaussian_filter1d(sigma=smooth_w, axis=1); X and y z-scored with
     the TRAIN statistics (std clipped at 1e-8); ones column; frames `sorted_idx` selected AFTER the z-score.
     Returns the per-session entry of the `train_data` dict RRRGD consumes, with device-resident splits.
-    `mode` (see rrr_mode): "exact" unless `planes` is given (then "classic" with that many planes)."""
+    `mode` (see rrr_mode): "exact" unless `planes` is given (then "classic" with that many planes).
+    `stats_hook(mean, sd, my, sy, K) -> (mean, sd, my, sy)`: called once with the TRAIN statistics (frames and smoothed
+    counts, float64, std clipped) before anything is z-scored; parallel.pack_trial_shard combines the ranks' statistics there."""
     vs.require_b200()
     if mode is None:
         mode = "classic" if planes is not None else rrr_mode(None)
@@ -587,7 +589,7 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                 compact_stats = Tf_dev == T and Tf != T
                 mean = torch.empty(Tf_dev * F, dtype=torch.float64, device=device)
                 sd = torch.empty_like(mean)
-                if not fused:
+                if not fused or stats_hook is not None:
                     vs.check(vs.lib.vs_rrr_colstats(vs.ptr(fr), K, Tf_dev * F, vs.ptr(mean), vs.ptr(sd), st))
                 sm = torch.empty_like(cnt)
                 vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), None, None, vs.ptr(sm), st))
@@ -595,13 +597,16 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                 sy = torch.empty_like(my)
                 vs.check(vs.lib.vs_colstats_f32(vs.ptr(sm), K, T * N, vs.ptr(my), vs.ptr(sy), st))
                 del sm
+                if stats_hook is not None:
+                    mean, sd, my, sy = (t.contiguous() for t in stats_hook(mean, sd, my, sy, K))
             if exact:
                 import ctypes
                 tw = (lambda k: vs.ptr(ex[k]) if (which == 0 and k in ex) else None)      # tables are written with the train split only
                 out = vs.RrrExactOps(vs.ptr(Xb) if Xb is not None else None, tw("isdT"), tw("qT"), ldt, None,
                                      vs.ptr(ex["Xc"]) if dense else None, tw("isd"), tw("qh"), tw("isdmax"))
                 if fused:
-                    vs.check(vs.lib.vs_rrr_pack_u8_fused(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), int(which == 0), d,
+                    vs.check(vs.lib.vs_rrr_pack_u8_fused(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd),
+                                                         int(which == 0 and stats_hook is None), d,
                                                          vs.ptr(Xa) if Xa is not None else None, ctypes.byref(out), vs.ptr(xl),
                                                          vs.ptr(overflow), st))
                 else:

@@ -182,12 +182,22 @@ def _combine_stats(mean, std, k_local, group=None):
 
 
 def pack_trial_shard(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, planes=1, smooth_w=2.0,
-                     device=None, operand=None, group=None):
+                     device=None, operand=None, group=None, mode=None):
     """`model.rrr.pack_session_from_frames` for THIS rank's trials of a session whose trials are spread over the ranks:
     the z-score statistics (frames and smoothed counts) are those of the WHOLE train split (three small all-reduces),
-    so every rank's operands are exactly the rows it would own in the single-GPU pack."""
-    from model.rrr import _PackedSplit, _op_dtype, operand_format
+    so every rank's operands are exactly the rows it would own in the single-GPU pack.
+    mode "exact" / "dense": the exact-operand layouts of pack_session_from_frames (its loader, with the combined statistics);
+    mode None / "classic": `planes` planes of the z-score."""
+    from model.rrr import _PackedSplit, _op_dtype, operand_format, pack_session_from_frames
     vs.require_b200()
+    if mode not in (None, "classic"):
+        def hook(mean, sd, my, sy, K):
+            if world()[1] > 1:
+                mean, sd, _ = _combine_stats(mean, sd, K, group)
+                my, sy, _ = _combine_stats(my, sy, K, group)
+            return mean, sd, my, sy
+        return pack_session_from_frames(frames_train, counts_train, frames_test, counts_test, sorted_idx, n_comp, smooth_w=smooth_w,
+                                        device=device, mode=mode, stats_hook=hook)
     device = device or torch.device("cuda")
     st = vs.stream()
     idx = torch.as_tensor(np.asarray(sorted_idx), dtype=torch.int32).to(device)
@@ -231,17 +241,16 @@ def pack_trial_shard(frames_train, counts_train, frames_test, counts_test, sorte
             "setup": {"mean_X_Tv": mean, "std_X_Tv": sd, "mean_y_TN": my.reshape(T, -1), "std_y_TN": sy.reshape(T, -1)}}
 
 
-def train_trial_sharded(entry_local, l2, n_comp, eid="session", planes=1, operand=None, group=None, history_dtype=None):
-    """`train_model_main` (rrr.py:192-202) for ONE session whose trials are sharded over the ranks.
-    Parameters and the whole L-BFGS state are replicated; each closure evaluation runs on the local trials with
-    l2 / world (the penalty is linear in l2, so the ranks' losses and gradients SUM to the single-GPU ones) followed by
-    ONE all-reduce of [flat gradient, loss]; every rank then takes the identical L-BFGS step."""
+def build_trial_sharded_model(entry_local, l2, n_comp, eid="session", planes=None, operand=None, group=None):
+    """The replicated RRRGD model of a trial-sharded session: l2 / world (the penalty is linear in l2, so the ranks' losses
+    and gradients SUM to the single-GPU ones), b = mean over ALL trials of the session (rrr.py:47, local sums all-reduced)."""
     from model.rrr import RRRGD, get_device
     rank, ws = world()
     td = {eid: entry_local}
+    if planes is None:
+        planes = entry_local["X"][0].dims.planes                   # the layout the shard was packed in
     model = RRRGD(td, n_comp, l2=l2 / ws, planes=planes, operand=operand)
     device = get_device()
-    # b = mean over ALL trials of the session (rrr.py:47): combine the local means
     yl = entry_local["y"][0]
     kk = torch.tensor([float(yl.shape[0])], dtype=torch.float64, device=yl.device)
     bsum = yl.double().sum(0).T.unsqueeze(1).contiguous()
@@ -251,6 +260,15 @@ def train_trial_sharded(entry_local, l2, n_comp, eid="session", planes=1, operan
     with torch.no_grad():
         model.model[f"{eid}_b"].copy_((bsum / kk).cpu())
     model.to(device)
+    return model
+
+
+def fit_trial_sharded(model, entry_local, eid="session", group=None, history_dtype=None):
+    """One L-BFGS step (rrr.py:164-190) of a trial-sharded session + the validation SSE over all ranks' validation trials.
+    Parameters and the whole L-BFGS state are replicated; each closure evaluation runs on the local trials followed by
+    ONE all-reduce of [flat gradient] and one of the loss; every rank then takes the identical L-BFGS step."""
+    rank, ws = world()
+    td = {eid: entry_local}
     optimizer = model.make_optimizer(history_dtype=history_dtype)
 
     def closure():
@@ -275,3 +293,10 @@ def train_trial_sharded(entry_local, l2, n_comp, eid="session", planes=1, operan
         dist.all_reduce(total, group=group)
         dist.all_reduce(per_neuron, group=group)
     return model, {"mses_val": {eid: per_neuron}, "mse_val_mean": total}
+
+
+def train_trial_sharded(entry_local, l2, n_comp, eid="session", planes=None, operand=None, group=None, history_dtype=None):
+    """`train_model_main` (rrr.py:192-202) for ONE session whose trials are sharded over the ranks
+    (build_trial_sharded_model + fit_trial_sharded)."""
+    model = build_trial_sharded_model(entry_local, l2, n_comp, eid, planes, operand, group)
+    return fit_trial_sharded(model, entry_local, eid, group, history_dtype)
