@@ -368,8 +368,10 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
   extern __shared__ __align__(16) uint8_t raw[];            // [K][128]
   __shared__ float s_m[128], s_dl[128], s_istd[128];
   __shared__ unsigned long long s_s1[2][128], s_s2[2][128];
-  __shared__ bool s_const[128];
-  const long long t = blockIdx.x, c0 = (long long)blockIdx.y * 128, Kp = (K + 15) / 16 * 16;
+  __shared__ unsigned s_vmin[2][128], s_vmax[2][128];
+  // chunk index fastest: consecutive blocks read neighbouring 128-byte pieces of the same frame rows, so the 128-byte DRAM
+  // lines a piece straddles (row starts are only 4-byte aligned) are shared through L2 instead of being fetched twice
+  const long long t = blockIdx.y, c0 = (long long)blockIdx.x * 128, Kp = (K + 15) / 16 * 16;
   const long long f = sorted_idx[t];
   const long long pa = K * T * ldc;
   // ---- phase 1: stage the chunk.  9 aligned 16-byte words cover 128 bytes at any 4-byte shift; 28 rows per pass
@@ -405,17 +407,20 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
     }
   }
   __syncthreads();
-  // ---- phase 1b: statistics of the 128 columns (two threads per column over the trial parities; integer sums are exact)
+  // ---- phase 1b: statistics of the 128 columns (two threads per column over the trial parities; integer sums are exact).
+  // The column extremes decide the overflow flag here, once per column, instead of per element in the store loops: z is a
+  // non-decreasing function of the byte value, so its largest magnitude is at the smallest or the largest byte.
   {
     const int c = threadIdx.x & 127, par = threadIdx.x >> 7;
-    if constexpr (kStats) {
-      unsigned long long s1 = 0, s2 = 0;
-      for (long long k = par; k < K; k += 2) {
-        const unsigned v = raw[k * 128 + c];
-        s1 += v; s2 += v * v;
-      }
-      s_s1[par][c] = s1; s_s2[par][c] = s2;
+    unsigned long long s1 = 0, s2 = 0;
+    unsigned vmin = 255u, vmax = 0u;
+    for (long long k = par; k < K; k += 2) {
+      const unsigned v = raw[k * 128 + c];
+      if constexpr (kStats) { s1 += v; s2 += v * v; }
+      vmin = min(vmin, v); vmax = max(vmax, v);
     }
+    s_s1[par][c] = s1; s_s2[par][c] = s2;
+    s_vmin[par][c] = vmin; s_vmax[par][c] = vmax;
     __syncthreads();
     if (threadIdx.x < 128) {
       const long long cg = c0 + c;
@@ -434,43 +439,58 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
         }
       }
       const double mi = rint(m);
-      s_m[c] = (float)mi; s_dl[c] = (float)(m - mi); s_istd[c] = (float)(1.0 / sdev); s_const[c] = !(sdev > 1e-8);
+      const float fm = (float)mi, fdl = (float)(m - mi), fis = (float)(1.0 / sdev);
+      const bool cst = !(sdev > 1e-8);
+      s_m[c] = fm; s_dl[c] = fdl; s_istd[c] = fis;
+      if (cg < C1) {
+        const float x0 = (float)min(s_vmin[0][c], s_vmin[1][c]) - fm, x1 = (float)max(s_vmax[0][c], s_vmax[1][c]) - fm;
+        const float z0 = (x0 - fdl) * fis, z1 = (x1 - fdl) * fis;
+        const bool zbad = !(fabsf(z0) <= 65504.f) || !(fabsf(z1) <= 65504.f);      // a half plane of z would overflow
+        const bool cbad = cst && (x0 != 0.f || x1 != 0.f);                          // a constant train column that varies here
+        if (overflow && ((Xa && zbad) || (!Xa && Xc && cbad) || (Xi && cbad))) atomicOr(overflow, 1);
+      }
     }
     __syncthreads();
   }
-  // ---- phase 2a: row-major operands, 8 features (one 128-bit store) per thread: 16 threads per trial row
-  bool ovf = false;
+  // ---- phase 2a: row-major operands, 8 features (one 128-bit store) per thread: 16 threads per trial row.
+  // byte -> float without the conversion pipe: the byte is placed in the mantissa of 2^23 and 2^23 + round(mean) is subtracted
+  // (both exact), which is the integer operand; z = (that - frac(mean)) / std in the same two roundings as the reference pack.
   if (Xa || Xc) {
     const int q8 = (threadIdx.x & 15) * 8, r16 = threadIdx.x >> 4;
-    for (long long k = r16; k < K; k += 16) {
-      const long long c = c0 + q8;
-      if (c >= C1) continue;
-      const uint2 b8 = *reinterpret_cast<const uint2*>(raw + k * 128 + q8);
-      uint32_t hi[4], lo[4], xi[4];
+    const long long c = c0 + q8;
+    if (c < C1) {
+      float bm[8], dl[8], is[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float xc[2], zf[2];
+      for (int j = 0; j < 8; ++j) {   // columns past C1 (last chunk): staged bytes 0, mean 0, std 1 -> zeros are written
+        bm[j] = 8388608.f + s_m[q8 + j]; dl[j] = s_dl[q8 + j]; is[j] = s_istd[q8 + j];
+      }
+      for (long long k = r16; k < K; k += 16) {
+        const uint2 b8 = *reinterpret_cast<const uint2*>(raw + k * 128 + q8);
+        uint32_t hi[4], lo[4], xi[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = 2 * i + e;
-          const unsigned byte = ((j < 4 ? b8.x : b8.y) >> (8 * (j & 3))) & 0xff;
-          const bool in = c + j < C1;
-          xc[e] = in ? (float)byte - s_m[q8 + j] : 0.f;
-          zf[e] = in ? (xc[e] - s_dl[q8 + j]) * s_istd[q8 + j] : 0.f;
-          if (in && (Xa ? !(fabsf(zf[e]) <= 65504.f) : (s_const[q8 + j] && xc[e] != 0.f))) ovf = true;
+        for (int i = 0; i < 4; ++i) {
+          float xc[2], zf[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * i + e;
+            const unsigned wv = j < 4 ? b8.x : b8.y;
+            const float raw_f = __uint_as_float(__byte_perm(wv, 0x4b000000u, 0x7540 + (j & 3)));   // 2^23 + byte
+            xc[e] = raw_f - bm[j];
+            zf[e] = (xc[e] - dl[j]) * is[j];
+          }
+          const __half2 h = __floats2half2_rn(zf[0], zf[1]);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(zf[0] - hf.x, zf[1] - hf.y);
+          const __half2 x = __floats2half2_rn(xc[0], xc[1]);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&h); lo[i] = *reinterpret_cast<const uint32_t*>(&l); xi[i] = *reinterpret_cast<const uint32_t*>(&x);
         }
-        const __half2 h = __floats2half2_rn(zf[0], zf[1]);
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(zf[0] - hf.x, zf[1] - hf.y);
-        const __half2 x = __floats2half2_rn(xc[0], xc[1]);
-        hi[i] = *reinterpret_cast<const uint32_t*>(&h); lo[i] = *reinterpret_cast<const uint32_t*>(&l); xi[i] = *reinterpret_cast<const uint32_t*>(&x);
+        const long long o = (t * K + k) * ldc + c;             // ldc % 64 == 0, c % 8 == 0: 16-byte aligned; the pad columns c >= C1 stay unread
+        if (Xa) {
+          *reinterpret_cast<uint4*>(Xa + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(Xa + pa + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (Xc) *reinterpret_cast<uint4*>(Xc + o) = make_uint4(xi[0], xi[1], xi[2], xi[3]);
       }
-      const long long o = (t * K + k) * ldc + c;             // ldc % 64 == 0, c % 8 == 0: 16-byte aligned; the pad columns c >= C1 stay unread
-      if (Xa) {
-        *reinterpret_cast<uint4*>(Xa + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(Xa + pa + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      if (Xc) *reinterpret_cast<uint4*>(Xc + o) = make_uint4(xi[0], xi[1], xi[2], xi[3]);
     }
   }
   // ---- phase 2b: transposed integer operand.  Thread = (4 features, 8 trials): 8 conflict-free 32-bit shared-memory reads, four
@@ -483,11 +503,12 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
       const long long k8 = (e >> 5) * 8;
       uint32_t wd[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < K) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * 128 + c4) : 0u;
+      for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < K) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * 128 + c4) : 0xffffffffu;
+      const bool full = k8 + 8 <= K;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (c0 + c4 + i >= C1) continue;
-        const float m = s_m[c4 + i];
+        const float bm = 8388608.f + s_m[c4 + i];
         uint32_t w[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -495,8 +516,8 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
 #pragma unroll
           for (int e2 = 0; e2 < 2; ++e2) {
             const int j = 2 * jj + e2;
-            a[e2] = (k8 + j < K) ? (float)((wd[j] >> (8 * i)) & 0xff) - m : 0.f;
-            if (s_const[c4 + i] && a[e2] != 0.f) ovf = true;
+            a[e2] = __uint_as_float(__byte_perm(wd[j], 0x4b000000u, 0x7540 + i)) - bm;
+            if (!full && k8 + j >= K) a[e2] = 0.f;
           }
           const __half2 x = __floats2half2_rn(a[0], a[1]);
           w[jj] = *reinterpret_cast<const uint32_t*>(&x);
@@ -505,8 +526,7 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
       }
     }
   }
-  if (ovf && overflow) atomicOr(overflow, 1);
-  if (blockIdx.y == 0)
+  if (blockIdx.x == 0)
     for (long long k = threadIdx.x; k < K; k += 256) xl[t * K + k] = 1.0f;
 }
 
@@ -601,8 +621,49 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
 #pragma unroll
   for (int e = 0; e < RMAX * RMAX; ++e) g[e] = 0.0;
   float um = 0.f;
+  // fast path (rank 3, two half planes, a full group of 4 features, even C1): the 12 doubles of the group arrive as six
+  // 128-bit loads and every (plane, component) row receives its 4 features as ONE 8-byte store
+  bool done = false;
+  if constexpr (RMAX == 3) {
+    if (planes == 2 && fmt == VS_OPERAND_F16 && c0 + kPrepC <= C1 && (C1 & 1) == 0) {
+      const double2* up = reinterpret_cast<const double2*>(U + (n * C1 + c0) * 3);
+      double u[12];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const double2 v2 = __ldg(up + i); u[2 * i] = v2.x; u[2 * i + 1] = v2.y; }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        uint16_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double v = u[3 * q + j] * uscale;
+          const __half h = __float2half_rn((float)v);
+          hi[q] = __half_as_ushort(h);
+          lo[q] = __half_as_ushort(__float2half_rn((float)(v - (double)__half2float(h))));
+        }
+        const long long o = ((long long)j * Npad + n) * ldc + c0;
+        *reinterpret_cast<uint2*>(Ub + o) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+        *reinterpret_cast<uint2*>(Ub + pu + o) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+      }
+      if (U32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { const float uf = (float)u[3 * q + j]; U32[u32g_index(n, c0 + q, j, N)] = uf; um = fmaxf(um, fabsf(uf)); }
+      }
+      if (Gp) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 3; ++j) g[i * 3 + j] = fma(u[3 * q + i], u[3 * q + j], g[i * 3 + j]);
+      }
+      done = true;
+    }
+  }
 #pragma unroll
   for (int q = 0; q < kPrepC; ++q) {
+    if (done) break;
     const long long c = c0 + q;
     if (c >= C1) {
       // dense forward operand (u32g_index layout, rank 3) with zeros in the pad columns: its generator reads whole 64-feature blocks
@@ -846,6 +907,114 @@ __global__ void __launch_bounds__(256) epi_f_kernel(const float* __restrict__ Z,
   }
 }
 
+// The same epilogue for the exact-operand training closure (rank 3, N % 4 == 0, dense backward, two IEEE-half residual
+// planes), laid out for memory-level parallelism: epi_f_kernel<.., double> above keeps 128 registers per thread and reads Z in
+// 128-byte pieces -- 0.31 ms at 19 % of the HBM peak for 0.46 GB (profiles/r02_ncu_full_exact.csv).  Here a block owns 64
+// trials of one time bin and ALL neurons (32 at a time in shared memory); a thread item is (trial, 4 neurons): 3 * splits independent 128-bit loads of the
+// Z partials (one 576-byte run per trial and j at N = 144) summed in float64, then yhat, the residual, the dV partial.
+// The residual tile goes through shared memory (float64) for the per-neuron SSE / db sums (ordered over the trials) and
+// the transposed 128-byte stores of the two residual planes.
+constexpr int kFxRows = 64;
+constexpr int kFxHalf = 32;                             // trials staged in shared memory at a time
+__global__ void __launch_bounds__(256) epi_fx_kernel(const float* __restrict__ Z, long long ldz, int splits, long long split_stride,
+                                                     const float* __restrict__ y, const float* __restrict__ y_lo, const float* __restrict__ xl,
+                                                     const double* __restrict__ V, const double* __restrict__ b, long long K, long long T,
+                                                     long long N, long long Npad, long long ldr, uint16_t* __restrict__ RV,
+                                                     double* __restrict__ sse_part, double* __restrict__ db_part, double* __restrict__ pv_part,
+                                                     long long Kp, double zscale) {
+  extern __shared__ double fx_rs[];                     // [kFxHalf][N + 1]
+  __shared__ double bs[160];
+  __shared__ double pvs[8][3];
+  __shared__ float xls[kFxRows];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long kb = blockIdx.x, t = blockIdx.y, KB = gridDim.x;
+  const long long k0 = kb * kFxRows, d0 = t * K + k0;
+  const int NQ = (int)(N >> 2), NS = (int)N + 1;
+  const double v0 = V[t] * zscale, v1 = V[T + t] * zscale, v2 = V[2 * T + t] * zscale;      // Z = zscale^-1 * X U (prep_u_kernel)
+  if (threadIdx.x < kFxRows) xls[threadIdx.x] = (k0 + threadIdx.x < K) ? xl[d0 + threadIdx.x] : 0.f;
+  for (int n = threadIdx.x; n < N; n += 256) bs[n] = b[(long long)n * T + t];
+  double pv0 = 0.0, pv1 = 0.0, pv2 = 0.0;
+  double cs0 = 0.0, cs1 = 0.0;                          // thread n < N: SSE and sum xl * R of neuron n over the block's trials
+  const long long prd = Npad * ldr;
+  for (int half = 0; half < kFxRows / kFxHalf; ++half) {
+    __syncthreads();                                    // xls / bs ready (first pass); the previous half's tile fully consumed
+    for (int item = threadIdx.x; item < kFxHalf * NQ; item += 256) {
+      const int rl = item / NQ, n4 = item - rl * NQ, row = half * kFxHalf + rl;
+      const long long k = k0 + row;
+      double res[4] = {0.0, 0.0, 0.0, 0.0};
+      if (k < K) {
+        const float* zp = Z + (d0 + row) * ldz + 4 * n4;
+        double z[3][4];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[j][e] = 0.0;
+#pragma unroll 4
+        for (int sp = 0; sp < splits; ++sp) {           // ordered sum of the accumulation runs, wide accumulator
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(zp + (long long)sp * split_stride + (long long)j * Npad));
+            z[j][0] += (double)q.x; z[j][1] += (double)q.y; z[j][2] += (double)q.z; z[j][3] += (double)q.w;
+          }
+        }
+        const long long yo = (k * T + t) * N + 4 * n4;
+        const float4 yh = __ldg(reinterpret_cast<const float4*>(y + yo));
+        const float4 yl = __ldg(reinterpret_cast<const float4*>(y_lo + yo));
+        const double yy[4] = {(double)yh.x + (double)yl.x, (double)yh.y + (double)yl.y, (double)yh.z + (double)yl.z, (double)yh.w + (double)yl.w};
+        const double xv = (double)xls[row];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          double acc = xv * bs[4 * n4 + e];
+          acc = fma(v0, z[0][e], acc); acc = fma(v1, z[1][e], acc); acc = fma(v2, z[2][e], acc);
+          const double rr = acc - yy[e];
+          res[e] = rr;
+          pv0 = fma(rr, z[0][e], pv0); pv1 = fma(rr, z[1][e], pv1); pv2 = fma(rr, z[2][e], pv2);
+        }
+      }
+      double* dst = fx_rs + rl * NS + 4 * n4;
+      dst[0] = res[0]; dst[1] = res[1]; dst[2] = res[2]; dst[3] = res[3];
+    }
+    __syncthreads();
+    // per-neuron sums, trials added in order
+    for (int n = threadIdx.x; n < N; n += 256) {       // N <= 160: at most one neuron per thread
+#pragma unroll 8
+      for (int rl = 0; rl < kFxHalf; ++rl) {
+        const double rr = fx_rs[rl * NS + n];
+        cs0 = fma(rr, rr, cs0);
+        cs1 = fma((double)xls[half * kFxHalf + rl], rr, cs1);
+      }
+    }
+    // residual planes R[n][t*Kp + k] (hi, then lo = R - hi): a half warp = the 16 trial pairs of this half (64 contiguous
+    // bytes per neuron and plane), the two half warps of warp w take neurons 2w and 2w + 1 (+16, +32, ...); columns follow
+    // Xb, zeros in the pad K <= k < Kp (the tile is zero there); Kp and k0 are even, so the pair stores are aligned
+    const int pr = lane & 15;
+    const long long ka = k0 + half * kFxHalf + 2 * pr;
+    if (ka < Kp) {
+      uint16_t* base = RV + t * Kp + ka;
+      for (int n = 2 * w + (lane >> 4); n < N; n += 16) {
+        const float ra = (float)fx_rs[(2 * pr) * NS + n], rb = (float)fx_rs[(2 * pr + 1) * NS + n];
+        const __half2 h = __floats2half2_rn(ra, rb);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(ra - hf.x, rb - hf.y);
+        *reinterpret_cast<uint32_t*>(base + (long long)n * ldr) = *reinterpret_cast<const uint32_t*>(&h);
+        *reinterpret_cast<uint32_t*>(base + prd + (long long)n * ldr) = *reinterpret_cast<const uint32_t*>(&l);
+      }
+    }
+  }
+  for (int n = threadIdx.x; n < N; n += 256) {
+    sse_part[(t * KB + kb) * N + n] = cs0;
+    db_part[(t * KB + kb) * N + n] = cs1;
+  }
+  pv0 = warp_sum(pv0); pv1 = warp_sum(pv1); pv2 = warp_sum(pv2);
+  if (lane == 0) { pvs[w][0] = pv0; pvs[w][1] = pv1; pvs[w][2] = pv2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double sj = 0.0;
+    for (int w2 = 0; w2 < 8; ++w2) sj += pvs[w2][threadIdx.x];
+    pv_part[(t * KB + kb) * 3 + threadIdx.x] = sj * zscale;
+  }
+}
+
 // per (t, n): db and SSE from the per-block partials (ordered sum over the trial blocks); sr (may be NULL) receives
 // sum_k xl*R = the column sums of the residual the exact-operand backward's mean correction needs
 template <typename AT>
@@ -1036,6 +1205,93 @@ __global__ void __launch_bounds__(256) epi_b_kernel(const float* __restrict__ Ga
         double reg = 0.0;
         for (int jj = 0; jj < r; ++jj) reg += u[jj] * Ws[jj * r + j];
         gp[j] = 2.0 * (double)Gs[j][lane][nl] + 2.0 * l2 * reg;
+      }
+    }
+  }
+}
+
+// epi_b_kernel<false, 4, true> for the exact-operand closure at rank 3 with a register-tiled correction: the rank-T
+// correction is a small GEMM  corr[c, (j,n)] = sum_t qT[c,t] * (V[j,t] SR[t,n])  (789 M fused multiply-adds at C1 = 18,260,
+// N = 144, T = 100); the kernel above spends ~3 shared-memory reads per 4 of them (0.178 ms, issue-bound at 69 %:
+// profiles/r02_ncu_full_exact.csv).  Here a block owns 64 features x 32 neurons and a thread 8 features x 3 components of
+// one neuron: per four time bins 8 broadcast 128-bit reads of q and 12 reads of the products P = V SR feed 96 FMAs.
+__global__ void __launch_bounds__(256) epi_bx_kernel(const float* __restrict__ Gacc, long long ldg, const double* __restrict__ U,
+                                                     const double* __restrict__ W, long long C1, long long N, long long Npad, double l2,
+                                                     double* __restrict__ dU, const float* __restrict__ qT, long long ldt,
+                                                     const float* __restrict__ SR, const double* __restrict__ V, long long T) {
+  __shared__ __align__(16) float qs[64][36];
+  __shared__ float ps[32][3][32];
+  __shared__ float Gs[3][64][33];
+  __shared__ double Ws[9];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long c0 = (long long)blockIdx.x * 64, n0 = (long long)blockIdx.y * 32;
+  if (threadIdx.x < 9) Ws[threadIdx.x] = W[threadIdx.x];
+  float corr[8][3];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) corr[i][0] = corr[i][1] = corr[i][2] = 0.f;
+  for (long long t0 = 0; t0 < T; t0 += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+      const int a = e >> 5, tq = e & 31;
+      const long long c = c0 + a, tt = t0 + tq;
+      qs[a][tq] = (c < C1 && tt < T) ? __ldg(qT + c * ldt + tt) : 0.f;
+    }
+    for (int e = threadIdx.x; e < 32 * 3 * 32; e += 256) {
+      const int tq = e / 96, j = (e / 32) % 3, nl = e & 31;
+      const long long tt = t0 + tq, nn = n0 + nl;
+      ps[tq][j][nl] = (tt < T && nn < N) ? (float)V[(long long)j * T + tt] * __ldg(SR + tt * Npad + nn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int t4 = 0; t4 < 8; ++t4) {
+      float pv[4][3];
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pv[tt][j] = ps[4 * t4 + tt][j][lane];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&qs[w + 8 * i][4 * t4]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          corr[i][j] = fmaf(q4.x, pv[0][j], corr[i][j]);
+          corr[i][j] = fmaf(q4.y, pv[1][j], corr[i][j]);
+          corr[i][j] = fmaf(q4.z, pv[2][j], corr[i][j]);
+          corr[i][j] = fmaf(q4.w, pv[3][j], corr[i][j]);
+        }
+      }
+    }
+  }
+  {
+    const long long n = n0 + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cl = w + 8 * i;
+      const long long c = c0 + cl;
+      const bool ok = c < C1 && n < N;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Gs[j][cl][lane] = ok ? (float)((double)__ldg(Gacc + c * ldg + (long long)j * Npad + n) - (double)corr[i][j]) : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int cl = 32 * cc + lane;
+    const long long c = c0 + cl;
+    if (c >= C1) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int nl = w + 8 * i;
+      const long long n = n0 + nl;
+      if (n >= N) continue;
+      const double* up = U + (n * C1 + c) * 3;
+      double* gp = dU + (n * C1 + c) * 3;
+      const double u0 = up[0], u1 = up[1], u2 = up[2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double reg = u0 * Ws[j] + u1 * Ws[3 + j] + u2 * Ws[6 + j];
+        gp[j] = 2.0 * (double)Gs[j][cl][nl] + 2.0 * l2 * reg;
       }
     }
   }
@@ -1434,7 +1690,7 @@ static int dense_forward(const vs_rrr_dims& d, const ExactArgs& ex, const Ws& w,
   VS_REQUIRE(ex.Xc && ex.isd && ex.qh && ex.isdmax, VS_ERR_INVALID, "vs_rrr_closure_exact: the dense-forward mode needs Xc, isd, qh and isdmax");
   VS_CHECK_CUDA(cudaMemsetAsync(w.umax, 0, 4, st));
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
-  VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
+  VS_LAUNCH(prep_u_kernel<3>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
             want_gram ? w.Gp : (double*)nullptr, kExactUScale, w.U32, (long long)d.ldc, w.umax);
   VS_LAUNCH(bscale_kernel, (unsigned)ceil_div(d.T, 128), 128, 0, st, w.umax, ex.isdmax, V, r, (long long)d.T, w.bscale);
   // M1 partials (split-K of the (T x C1) x (C1 x 3 Npad) product over ~all SMs) live in the Gacc buffer until reduced
@@ -1502,9 +1758,9 @@ static int closure_dense(const vs_rrr_dims& d, const uint16_t* Xi, const ExactAr
   if (dU) {
     rc = tc::rrr_bwd_dense(dd, st);
     if (rc) return rc;
-    dim3 g4((unsigned)ceil_div(d.C1, 32), (unsigned)ceil_div(d.N, 32));
-    VS_LAUNCH((epi_b_kernel<false, 4, true>), g4, 256, 0, st, w.Gacc, w.ldz, 1, (long long)d.C1 * w.ldz, U, w.W, (long long)d.C1, (long long)d.N,
-              w.Npad, r, l2, dU, ex.qT, ex.ldt, w.SR, V, (long long)d.T);
+    dim3 gx((unsigned)ceil_div(d.C1, 64), (unsigned)ceil_div(d.N, 32));
+    VS_LAUNCH(epi_bx_kernel, gx, 256, 0, st, w.Gacc, w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, l2, dU, ex.qT, ex.ldt, w.SR, V,
+              (long long)d.T);
   }
   return VS_OK;
 }
@@ -1532,7 +1788,9 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
   if (dense_fwd) return closure_dense(d, Xb, ex, xl, y, U, V, b, l2, loss, sse_n, dU, dV, db, w, st);
   // stage 0: U planes + Gram partials, then G and W = V V^T
   dim3 g0((unsigned)ceil_div(d.C1, 256 * kPrepC), (unsigned)d.N);
-  if (r <= 4) {
+  if (r == 3) {
+    VS_LAUNCH(prep_u_kernel<3>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale, u32, ldu, umax);
+  } else if (r <= 4) {
     VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale, u32, ldu, umax);
   } else {
     VS_LAUNCH(prep_u_kernel<kMaxR>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub, w.Gp, uscale, u32, ldu, umax);
@@ -1556,11 +1814,23 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
 #define VS_EPI_F(RM, AT) VS_LAUNCH((epi_f_kernel<false, RM, AT>), ge, 256, 0, st, w.Z, w.ldz, sf, KT * w.ldz, y, ex.y_lo, xl, V, b,       \
                                    (long long)d.K, (long long)d.T, (long long)d.N, w.Npad, r, d.planes, (int)d.fmt, (long long)d.ldr, w.RV,   \
                                    (AT*)w.sse_part, (AT*)w.db_part, (AT*)w.pv_part, nullptr, w.Kp, dense ? 1 : 0, 1.0 / uscale)
-  if (exact) { if (r <= 4) { VS_EPI_F(4, double); } else { VS_EPI_F(kMaxR, double); } }
+  // exact-operand training closure at rank 3: the wide-load epilogue (one block per 64 trials x all neurons: NT = 1)
+  static int fx_env = -1;
+  if (fx_env < 0) { const char* e = getenv("VS_RRR_EPI_FX"); fx_env = e ? atoi(e) : 1; }
+  const size_t fx_smem = (size_t)kFxHalf * (d.N + 1) * 8;
+  const bool use_fx = exact && dense && r == 3 && d.N % 4 == 0 && d.N <= 160 && d.planes == 2 && d.fmt == VS_OPERAND_F16 && ex.y_lo && fx_env != 0 &&
+                      kFxRows == kEpiRows && fx_smem <= 96 * 1024;
+  if (use_fx) {
+    static bool fx_attr = false;
+    if (!fx_attr) { VS_CHECK_CUDA(cudaFuncSetAttribute(epi_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); fx_attr = true; }
+    dim3 gx((unsigned)w.KB, (unsigned)d.T);
+    VS_LAUNCH(epi_fx_kernel, gx, 256, fx_smem, st, w.Z, w.ldz, sf, KT * w.ldz, y, ex.y_lo, xl, V, b, (long long)d.K, (long long)d.T, (long long)d.N,
+              w.Npad, (long long)d.ldr, w.RV, (double*)w.sse_part, (double*)w.db_part, (double*)w.pv_part, w.Kp, 1.0 / uscale);
+  } else if (exact) { if (r <= 4) { VS_EPI_F(4, double); } else { VS_EPI_F(kMaxR, double); } }
   else { if (r <= 4) { VS_EPI_F(4, float); } else { VS_EPI_F(kMaxR, float); } }
 #undef VS_EPI_F
   dim3 g2((unsigned)ceil_div(d.N, 128), (unsigned)d.T);
-  const long long NT = ceil_div(d.N, 32);
+  const long long NT = use_fx ? 1 : ceil_div(d.N, 32);
   if (exact) {
     VS_LAUNCH(reduce_part_kernel<double>, g2, 128, 0, st, (const double*)w.sse_part, (const double*)w.db_part, b, w.KB, (long long)d.T,
               (long long)d.N, l2, db, w.sse_tn, w.SR, w.Npad);
@@ -1580,7 +1850,13 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
     const bool fast = d.planes == 1 && sb == 1;
 #define VS_EPI_B(FAST, RM, CORR) VS_LAUNCH((epi_b_kernel<FAST, RM, CORR>), g4, 256, 0, st, w.Gacc, w.ldz, sb, (long long)d.C1 * w.ldz, U, w.W, \
                                            (long long)d.C1, (long long)d.N, w.Npad, r, l2, dU, ex.qT, ex.ldt, w.SR, V, (long long)d.T)
-    if (exact) { if (r <= 4) { VS_EPI_B(false, 4, true); } else { VS_EPI_B(false, kMaxR, true); } }
+    static int bx_env = -1;
+    if (bx_env < 0) { const char* e = getenv("VS_RRR_EPI_BX"); bx_env = e ? atoi(e) : 1; }
+    if (exact && r == 3 && sb == 1 && bx_env != 0) {
+      dim3 gx((unsigned)ceil_div(d.C1, 64), (unsigned)ceil_div(d.N, 32));
+      VS_LAUNCH(epi_bx_kernel, gx, 256, 0, st, w.Gacc, w.ldz, U, w.W, (long long)d.C1, (long long)d.N, w.Npad, l2, dU, ex.qT, ex.ldt, w.SR, V,
+                (long long)d.T);
+    } else if (exact) { if (r <= 4) { VS_EPI_B(false, 4, true); } else { VS_EPI_B(false, kMaxR, true); } }
     else if (r <= 4) { if (fast) { VS_EPI_B(true, 4, false); } else { VS_EPI_B(false, 4, false); } }
     else { if (fast) { VS_EPI_B(true, kMaxR, false); } else { VS_EPI_B(false, kMaxR, false); } }
 #undef VS_EPI_B
@@ -1679,8 +1955,8 @@ extern "C" int vs_rrr_pack_u8_fused(const uint8_t* frames, int64_t Tf, const int
   uint16_t* Xi = const_cast<uint16_t*>(out->Xi);
   uint16_t* Xc = d.mode == VS_RRR_MODE_DENSE ? const_cast<uint16_t*>(out->Xc) : nullptr;
   uint16_t* Xz = d.mode == VS_RRR_MODE_EXACT ? Xa : nullptr;
-  dim3 grid((unsigned)d.T, (unsigned)ceil_div(d.C1, 128));
-  VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8_fused: too many columns");
+  dim3 grid((unsigned)ceil_div(d.C1, 128), (unsigned)d.T);
+  VS_REQUIRE(grid.y <= 65535u, VS_ERR_UNSUPPORTED, "vs_rrr_pack_u8_fused: too many time bins");
   if (compute_stats) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(pack_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_LAUNCH(pack_fused_kernel<true>, grid, 256, smem, stream, frames, sorted_idx, mean, std_clipped, (long long)Tf, (long long)d.K,
@@ -1741,7 +2017,10 @@ extern "C" int vs_rrr_predict(vs_rrr_dims d, const uint16_t* Xa, const float* xl
   VS_REQUIRE(d.mode != VS_RRR_MODE_DENSE, VS_ERR_INVALID, "vs_rrr_predict: dense-forward splits go through vs_rrr_predict_exact");
   const double uscale = d.mode == VS_RRR_MODE_EXACT ? kExactUScale : 1.0;
   float* u32 = nullptr; long long ldu = 0; unsigned* umax = nullptr;
-  if (d.r <= 4) {
+  if (d.r == 3) {
+    VS_LAUNCH(prep_u_kernel<3>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
+              (double*)nullptr, uscale, u32, ldu, umax);
+  } else if (d.r <= 4) {
     VS_LAUNCH(prep_u_kernel<4>, g0, 256, 0, st, U, (long long)d.N, w.Npad, (long long)d.C1, (int)d.r, d.planes, (int)d.fmt, (long long)d.ldc, w.Ub,
               (double*)nullptr, uscale, u32, ldu, umax);
   } else {
