@@ -14,12 +14,13 @@ run() {  # name, extra args
 run joint "--workload rrr --dropin-e2e 0"
 run indep "--workload rrr --independent --dropin-e2e 0"
 run both ""
+run strong "--workload rrr --strong --dropin-e2e 0"
 python - <<PY
 import json
-for nm in ("joint", "indep", "both"):
+for nm in ("joint", "indep", "both", "strong"):
     try:
         d = json.loads([l for l in open("gpurun_out/r02m_%s_$N.json" % nm) if l.startswith("{")][-1])
-        print(nm, "n_gpus", d["n_gpus"], "ms", round(d["ms_per_step"], 2), "value", round(d["value"]), "e2e ms", round(d["e2e"]["ms_per_step"], 1), d["config"]["parallelism"][:60],
+        print(nm, "n_gpus", d["n_gpus"], "ms", round(d["ms_per_step"], 2), "value", round(d["value"]), "e2e ms", round(d["e2e"]["ms_per_step"], 1), d["config"]["parallelism"][:60], "scaling", d["scaling"], "parity", (d.get("parity") or {}).get("fit_rel_diff"),
               "| linear", (d.get("linear") or {}).get("ms_per_step"))
     except Exception as e:
         print(nm, "unreadable", e)
