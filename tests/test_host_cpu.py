@@ -300,3 +300,28 @@ def test_bench_clock_sampler_filters_the_timed_region(monkeypatch):
     assert out["samples_in_timed_region"] == 0 and out["samples"] == 1 and out["sm_mhz"] == 1700.0 and out["reasons"] == []
     s3 = bench.ClockSampler(0)                  # nvidia-smi missing: reported, not fatal
     assert s3.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_bench_reference_arm_prints_one_json_line_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours): runs without a GPU and without the CUDA library,
+    prints ONE JSON line with the contract's keys, and reports the neuron sample it actually ran with its extrapolation."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--trials", "16",
+                        "--trials-test", "8", "--features", "256", "--neurons", "16", "--ref-budget", "2"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "training video frames/sec" and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["gpu_launches"] == 0 and d["dtype"] == "f64"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    cb, cfg = d["cpu_baseline"], d["config"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert 1 <= cfg["neurons"] <= cfg["neurons_full"] == 16
+    ext = cfg["extrapolation"]
+    assert ext["sampled"] == "neurons" and ext["run"] == cfg["neurons"] and 0 < ext["factor_on_value"] <= 1.0
+    assert cfg["extrapolated"] == (cfg["neurons"] < 16)
