@@ -657,7 +657,7 @@ def run_rrr(args, rank, world, local):
            "median_ms_per_step": med_s * 1e3, "value_at_median": n_sessions * K * FRAMES_PER_TRIAL / med_s,
            "ms_each_rank0": [round(x, 2) for x in each],
            "path": ("parallel.pack_trial_shard(this rank's trials, pinned uint8 frames) -> build_trial_sharded_model -> fit_trial_sharded -> float(mse_val_mean)" if strong
-                    else "pack_session_from_frames(pinned uint8 frames) -> RRRGD(init_plan) -> parallel.train_joint_model -> float(mse_val_mean)" if joint
+                    else "pack_session_from_frames(pinned uint8 frames) -> RRRGD(init_plan: own U and the kept V drawn every call; the other ranks' sessions are jumped over with stream positions remembered from the warm-up calls) -> parallel.train_joint_model -> float(mse_val_mean)" if joint
                     else "model.rrr.train_model_from_frames(pinned uint8 frames) -> float(mse_val_mean)")}
 
     # ---- the reference's own entry point: train_model_main(train_data) with the float64 numpy arrays train_rrr.py builds

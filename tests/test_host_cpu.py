@@ -325,3 +325,36 @@ def test_bench_reference_arm_prints_one_json_line_on_cpu():
     ext = cfg["extrapolation"]
     assert ext["sampled"] == "neurons" and ext["run"] == cfg["neurons"] and 0 < ext["factor_on_value"] <= 1.0
     assert cfg["extrapolated"] == (cfg["neurons"] < 16)
+
+
+def test_rrr_init_stream_marks_reproduce_the_sequential_draw(monkeypatch):
+    """RRRGD(init_plan=...) on a rank that owns ONE session of a joint model: jumping over the foreign sessions with the
+    remembered stream positions gives bit-identical U, V and numpy global state to drawing and dropping them
+    (src/model/rrr.py:35-49: one global stream, U then V per session, the last V kept)."""
+    import model.rrr as mr
+    rng = np.random.default_rng(0)
+    plan = [("a", 5, 40, 7), ("b", 3, 33, 7), ("c", 4, 21, 7), ("d", 6, 18, 7)]
+
+    def td(eid):
+        _, N, C, T = next(p for p in plan if p[0] == eid)
+        return {eid: {"X": [rng.standard_normal((6, T, C)), rng.standard_normal((3, T, C))],
+                      "y": [rng.standard_normal((6, T, N)), rng.standard_normal((3, T, N))]}}
+
+    for own in ("a", "b", "c", "d"):
+        data = td(own)
+        monkeypatch.setenv("VS_RRR_STREAM_MARKS", "0")
+        ref = mr.RRRGD(data, 3, l2=1.0, init_plan=plan)
+        st_ref = np.random.get_state()
+        monkeypatch.setenv("VS_RRR_STREAM_MARKS", "1")
+        for _ in range(2):                       # first pass may record the marks, the second one uses them
+            got = mr.RRRGD(data, 3, l2=1.0, init_plan=plan)
+            st = np.random.get_state()
+            for k in ref.model:
+                assert torch.equal(ref.model[k], got.model[k]), (own, k)
+            assert st[2:] == st_ref[2:] and np.array_equal(st[1], st_ref[1])
+    assert any(k[2] == "U" for k in mr._STREAM_MARKS) and any(k[2] == "V" for k in mr._STREAM_MARKS)
+    # the whole joint model in one process equals the reference's own stream for the first session
+    np.random.seed(0)
+    U0 = np.random.normal(size=(5, 39, 3)) / np.sqrt(7 * 3)
+    full = mr.RRRGD({**td("a"), **td("b"), **td("c"), **td("d")}, 3, l2=1.0)
+    assert np.array_equal(full.model["a_U"].detach().numpy(), U0)

@@ -79,6 +79,15 @@ def get_device():
 
 _SIDE_STREAMS = {}
 _PINNED_STAGES = {}
+# positions of the init stream (LegacyNormalStream.snapshot) after a given sequence of session draws from seed 0:
+# key (shapes of the sessions drawn so far, n_comp, "U" | "V") -- see RRRGD.__init__
+_STREAM_MARKS = {}
+
+
+def _stream_cache_enabled():
+    if len(_STREAM_MARKS) > 4096:
+        _STREAM_MARKS.clear()
+    return os.environ.get("VS_RRR_STREAM_MARKS", "1") != "0"
 
 
 def _pinned_stage(numel):
@@ -242,9 +251,29 @@ class RRRGD():
             init_plan = [(eid, train_data[eid]['y'][0].shape[2], train_data[eid]['X'][0].shape[2], train_data[eid]['y'][0].shape[1])
                          for eid in train_data]
         self.eids = [eid for eid, *_ in init_plan if eid in train_data]
-        for eid, N, ncoef, T in init_plan:
+        # Sessions of the plan that live on OTHER ranks only advance the stream.  The stream position after a given sequence
+        # of draws is a pure function of seed 0 and the shapes, so it is remembered (2.5 KB per position, _STREAM_MARKS) the
+        # first time it is reached: later models with the same plan jump over foreign sessions instead of drawing and
+        # dropping ~8 M normals for each of them (on n ranks that was n x the host work, all ranks competing for the same
+        # cores).  A rank's own U and the V that is kept are always drawn.
+        shapes = tuple((int(N), int(ncoef), int(T)) for _, N, ncoef, T in init_plan)
+        last = len(init_plan) - 1
+        for i, (eid, N, ncoef, T) in enumerate(init_plan):
             scale = float(np.sqrt(T * ncomp))
-            if device is not None and eid in train_data:
+            own = eid in train_data
+            if not own:
+                # the furthest remembered position up to the next draw that is needed: the next own session's U, or the last V
+                nxt = next((j for j in range(i + 1, len(init_plan)) if init_plan[j][0] in train_data), None)
+                target = (nxt - 1, "V") if nxt is not None else (last, "U")
+                mark = _STREAM_MARKS.get((shapes[:target[0] + 1], int(ncomp), target[1])) if target[0] >= i else None
+                if mark is not None and _stream_cache_enabled():
+                    rng.restore(mark)
+                    if nxt is None:                             # positioned after the last session's U: its V is the one kept
+                        V = rng.normal((ncomp, init_plan[last][3]), float(np.sqrt(init_plan[last][3] * ncomp)))
+                        _STREAM_MARKS[(shapes, int(ncomp), "V")] = rng.snapshot()
+                        break
+                    continue                                     # positioned after session nxt - 1: the loop resumes at nxt
+            if device is not None and own:
                 stage = _pinned_stage(N * (ncoef - 1) * ncomp)
                 rng.normal((N, ncoef - 1, ncomp), scale, out=stage["buf"])
                 U = torch.empty((N, ncoef - 1, ncomp), dtype=torch.float64, device=device)
@@ -252,8 +281,10 @@ class RRRGD():
                 stage["event"].record(torch.cuda.current_stream(device))
             else:
                 U = rng.normal((N, ncoef - 1, ncomp), scale)
+            _STREAM_MARKS.setdefault((shapes[:i + 1], int(ncomp), "U"), rng.snapshot())
             V = rng.normal((ncomp, T), scale)                  # redrawn per eid, the last one is kept (rrr.py:43,49)
-            if eid not in train_data:
+            _STREAM_MARKS.setdefault((shapes[:i + 1], int(ncomp), "V"), rng.snapshot())
+            if not own:
                 continue
             _y = train_data[eid]['y'][0]       # (K, T, N)
             if isinstance(_y, torch.Tensor):   # targets already on the device (pack_session_from_frames)

@@ -258,6 +258,15 @@ class LegacyNormalStream:
         check(lib.vs_host_rng_normal(self._state, count, float(divisor), C.c_void_p(ptr), int(threads)))
         return out
 
+    def snapshot(self) -> bytes:
+        """The generator's whole state (position in the stream), e.g. to resume later from this point."""
+        return bytes(self._state.raw)
+
+    def restore(self, blob: bytes):
+        if len(blob) != self.STATE_BYTES:
+            raise VsError("LegacyNormalStream.restore: wrong state size")
+        C.memmove(self._state, blob, self.STATE_BYTES)
+
     def export_to_numpy(self):
         """Leave numpy's GLOBAL RandomState exactly where the reference's draws would have left it."""
         import numpy as np
