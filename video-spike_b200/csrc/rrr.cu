@@ -359,16 +359,18 @@ __global__ void __launch_bounds__(256) pack_u8_exact_kernel(const uint8_t* __res
 // The old path read the frames twice (colstats_kernel at 0.26 of the HBM peak, then the pack at 0.49) and wrote the
 // transposed operand in 64-byte pieces.  Requires C1 % 4 == 0 (row starts are then 4-byte aligned: the 16-byte global words
 // are shifted into place by whole 32-bit lanes) and K * 128 bytes of shared memory; other shapes use the two-kernel path.
+constexpr int kPackRow = 136;
 template <bool kStats>
-__global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ sorted_idx,
+__global__ void __launch_bounds__(256, 3) pack_fused_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ sorted_idx,
                                                          double* __restrict__ mean, double* __restrict__ sd, long long Tf, long long K,
                                                          long long T, long long C1, long long ldc, long long ldr, uint16_t* __restrict__ Xa,
                                                          uint16_t* __restrict__ Xc, uint16_t* __restrict__ Xi, float* __restrict__ xl,
                                                          int* __restrict__ overflow) {
-  extern __shared__ __align__(16) uint8_t raw[];            // [K][128]
+  extern __shared__ __align__(16) uint8_t raw[];            // [K][kPackRow]: 128 staged bytes per trial, rows 136 bytes apart
+  //                                                           (two banks of skew per row: the 16-byte staging stores of a warp span 3-4 rows)
   __shared__ float s_m[128], s_dl[128], s_istd[128];
-  __shared__ unsigned long long s_s1[2][128], s_s2[2][128];
-  __shared__ unsigned s_vmin[2][128], s_vmax[2][128];
+  __shared__ unsigned s_s1[8][128], s_s2[8][128];
+  __shared__ unsigned s_vmin[8][32], s_vmax[8][32];
   // chunk index fastest: consecutive blocks read neighbouring 128-byte pieces of the same frame rows, so the 128-byte DRAM
   // lines a piece straddles (row starts are only 4-byte aligned) are shared through L2 instead of being fetched twice
   const long long t = blockIdx.y, c0 = (long long)blockIdx.x * 128, Kp = (K + 15) / 16 * 16;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
             v[i] = (cc >= 0 && cc + 4 <= C1) ? __ldg(reinterpret_cast<const uint32_t*>(wp + 4 * i)) : 0u;
           }
         }
-        uint32_t* dst = reinterpret_cast<uint32_t*>(raw + k * 128);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(raw + k * kPackRow);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const long long p = off + 4 * i;
@@ -407,28 +409,41 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
     }
   }
   __syncthreads();
-  // ---- phase 1b: statistics of the 128 columns (two threads per column over the trial parities; integer sums are exact).
+  // ---- phase 1b: statistics of the 128 columns (integer sums are exact).
   // The column extremes decide the overflow flag here, once per column, instead of per element in the store loops: z is a
   // non-decreasing function of the byte value, so its largest magnitude is at the smallest or the largest byte.
   {
-    const int c = threadIdx.x & 127, par = threadIdx.x >> 7;
-    unsigned long long s1 = 0, s2 = 0;
-    unsigned vmin = 255u, vmax = 0u;
-    for (long long k = par; k < K; k += 2) {
-      const unsigned v = raw[k * 128 + c];
-      if constexpr (kStats) { s1 += v; s2 += v * v; }
-      vmin = min(vmin, v); vmax = max(vmax, v);
+    // thread = (4 adjacent columns, one of 8 trial phases): one 32-bit shared-memory word per trial; 32-bit sums are exact
+    // for K/8 * 65025 < 2^32; the byte-wise extremes come from the SIMD-in-word min / max
+    const int q4 = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    unsigned a1[4] = {0u, 0u, 0u, 0u}, a2[4] = {0u, 0u, 0u, 0u};
+    unsigned wmin = 0xffffffffu, wmax = 0u;
+    for (long long k = grp; k < K; k += 8) {
+      const unsigned wv = *reinterpret_cast<const unsigned*>(raw + k * kPackRow + 4 * q4);
+      if constexpr (kStats) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned v = (wv >> (8 * i)) & 0xffu;
+          a1[i] += v; a2[i] += v * v;
+        }
+      }
+      wmin = __vminu4(wmin, wv); wmax = __vmaxu4(wmax, wv);
     }
-    s_s1[par][c] = s1; s_s2[par][c] = s2;
-    s_vmin[par][c] = vmin; s_vmax[par][c] = vmax;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s_s1[grp][4 * q4 + i] = a1[i]; s_s2[grp][4 * q4 + i] = a2[i]; }
+    s_vmin[grp][q4] = wmin; s_vmax[grp][q4] = wmax;
     __syncthreads();
+    const int c = threadIdx.x & 127;
     if (threadIdx.x < 128) {
       const long long cg = c0 + c;
       double m = 0.0, sdev = 1.0;
       if (cg < C1) {
         const long long col = f * C1 + cg;
         if constexpr (kStats) {
-          const double s1 = (double)(s_s1[0][c] + s_s1[1][c]), s2 = (double)(s_s2[0][c] + s_s2[1][c]);
+          unsigned long long t1 = 0, t2 = 0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { t1 += s_s1[g][c]; t2 += s_s2[g][c]; }
+          const double s1 = (double)t1, s2 = (double)t2;
           m = s1 / (double)K;
           const double var = ((double)K * s2 - s1 * s1) / ((double)K * (double)K);     // exact integer moments
           sdev = sqrt(var > 0.0 ? var : 0.0);
@@ -443,7 +458,13 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
       const bool cst = !(sdev > 1e-8);
       s_m[c] = fm; s_dl[c] = fdl; s_istd[c] = fis;
       if (cg < C1) {
-        const float x0 = (float)min(s_vmin[0][c], s_vmin[1][c]) - fm, x1 = (float)max(s_vmax[0][c], s_vmax[1][c]) - fm;
+        unsigned bmin = 255u, bmax = 0u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          bmin = min(bmin, (s_vmin[g][c >> 2] >> (8 * (c & 3))) & 0xffu);
+          bmax = max(bmax, (s_vmax[g][c >> 2] >> (8 * (c & 3))) & 0xffu);
+        }
+        const float x0 = (float)bmin - fm, x1 = (float)bmax - fm;
         const float z0 = (x0 - fdl) * fis, z1 = (x1 - fdl) * fis;
         const bool zbad = !(fabsf(z0) <= 65504.f) || !(fabsf(z1) <= 65504.f);      // a half plane of z would overflow
         const bool cbad = cst && (x0 != 0.f || x1 != 0.f);                          // a constant train column that varies here
@@ -465,7 +486,7 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
         bm[j] = 8388608.f + s_m[q8 + j]; dl[j] = s_dl[q8 + j]; is[j] = s_istd[q8 + j];
       }
       for (long long k = r16; k < K; k += 16) {
-        const uint2 b8 = *reinterpret_cast<const uint2*>(raw + k * 128 + q8);
+        const uint2 b8 = *reinterpret_cast<const uint2*>(raw + k * kPackRow + q8);
         uint32_t hi[4], lo[4], xi[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -503,7 +524,7 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const uint8_t* __restri
       const long long k8 = (e >> 5) * 8;
       uint32_t wd[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < K) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * 128 + c4) : 0xffffffffu;
+      for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < K) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * kPackRow + c4) : 0xffffffffu;
       const bool full = k8 + 8 <= K;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1231,15 +1252,23 @@ __global__ void __launch_bounds__(256) epi_bx_kernel(const float* __restrict__ G
   for (int i = 0; i < 8; ++i) corr[i][0] = corr[i][1] = corr[i][2] = 0.f;
   for (long long t0 = 0; t0 < T; t0 += 32) {
     __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
-      const int a = e >> 5, tq = e & 31;
-      const long long c = c0 + a, tt = t0 + tq;
-      qs[a][tq] = (c < C1 && tt < T) ? __ldg(qT + c * ldt + tt) : 0.f;
+    // fill: thread = (row a = w + 8 i, column lane) of both tiles; V[j, t] is read once per row and broadcast
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int a = w + 8 * i;
+      const long long c = c0 + a, tt = t0 + lane;
+      qs[a][lane] = (c < C1 && tt < T) ? __ldg(qT + c * ldt + tt) : 0.f;
     }
-    for (int e = threadIdx.x; e < 32 * 3 * 32; e += 256) {
-      const int tq = e / 96, j = (e / 32) % 3, nl = e & 31;
-      const long long tt = t0 + tq, nn = n0 + nl;
-      ps[tq][j][nl] = (tt < T && nn < N) ? (float)V[(long long)j * T + tt] * __ldg(SR + tt * Npad + nn) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int tq = w + 8 * i;
+      const long long tt = t0 + tq, nn = n0 + lane;
+      const bool ok = tt < T && nn < N;
+      const float sv = ok ? __ldg(SR + tt * Npad + nn) : 0.f;
+      const long long tc = tt < T ? tt : T - 1;
+      ps[tq][0][lane] = (float)V[tc] * sv;
+      ps[tq][1][lane] = (float)V[T + tc] * sv;
+      ps[tq][2][lane] = (float)V[2 * T + tc] * sv;
     }
     __syncthreads();
 #pragma unroll 2
@@ -1949,7 +1978,7 @@ extern "C" int vs_rrr_pack_u8_fused(const uint8_t* frames, int64_t Tf, const int
   VS_REQUIRE(frames && sorted_idx && mean && std_clipped && out && xl && Tf >= d.T, VS_ERR_INVALID, "vs_rrr_pack_u8_fused: bad arguments");
   VS_REQUIRE(d.mode == VS_RRR_MODE_EXACT ? Xa != nullptr : out->Xc != nullptr, VS_ERR_INVALID,
              "vs_rrr_pack_u8_fused: the forward operand of the mode is missing (Xa for EXACT, ops.Xc for DENSE)");
-  const size_t smem = (size_t)d.K * 128;
+  const size_t smem = (size_t)d.K * kPackRow;
   VS_REQUIRE(d.C1 % 4 == 0 && ((uintptr_t)frames & 3) == 0 && smem <= 200 * 1024, VS_ERR_UNSUPPORTED,
              "vs_rrr_pack_u8_fused: needs C1 %% 4 == 0, 4-byte aligned frames and K <= 1600 (use vs_rrr_colstats + vs_rrr_pack_u8_exact)");
   uint16_t* Xi = const_cast<uint16_t*>(out->Xi);

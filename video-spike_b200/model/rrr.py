@@ -614,7 +614,7 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
             cnt = torch.as_tensor(cnt).to(device, non_blocking=True).float().contiguous()
             # fused loader (one read of the frames: statistics + pack per time bin) when every frame on the device is a
             # selected one; otherwise the two-kernel path (statistics of all Tf frames, then the pack)
-            fused = (exact and Tf_dev == T and F % 4 == 0 and K * 128 <= 200 * 1024 and fr.data_ptr() % 4 == 0
+            fused = (exact and Tf_dev == T and F % 4 == 0 and K * 136 <= 200 * 1024 and fr.data_ptr() % 4 == 0
                      and os.environ.get("VS_RRR_FUSED_PACK", "1") != "0")
             if which == 0:
                 compact_stats = Tf_dev == T and Tf != T
