@@ -218,13 +218,16 @@ class _PackedSplit:
 
 
 class RRRGD():
-    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None, operand=None, device=None):
+    def __init__(self, train_data, ncomp, l2=0., planes=None, engine=None, init_plan=None, operand=None, device=None, draw=True):
         """`init_plan` (session-sharded joint model, parallel.py): [(eid, N, ncoef, T)] of ALL sessions of the joint
         model in the reference's iteration order.  The init stream is drawn for every session in that order so that
         this rank's U_s and the shared V are bit-identical to the single-process joint model; sessions that are not
         in `train_data` are drawn and dropped.
         `device`: create the parameters directly on that CUDA device -- the init stream is generated into a pinned
-        staging buffer and uploaded asynchronously, instead of CPU parameters + a later blocking `.to(device)`."""
+        staging buffer and uploaded asynchronously, instead of CPU parameters + a later blocking `.to(device)`.
+        `draw=False` (replicated models, parallel.build_trial_sharded_model): U and V are left unset -- another rank draws
+        them and broadcasts; numpy's global state is still moved to where the draws would have left it when that position
+        is known (_STREAM_MARKS)."""
         self.l2 = l2
         self.eids = list(train_data.keys())
         self.withbias = True
@@ -258,6 +261,25 @@ class RRRGD():
         # cores).  A rank's own U and the V that is kept are always drawn.
         shapes = tuple((int(N), int(ncoef), int(T)) for _, N, ncoef, T in init_plan)
         last = len(init_plan) - 1
+        if not draw:
+            for eid, N, ncoef, T in init_plan:
+                if eid not in train_data:
+                    continue
+                _y = train_data[eid]['y'][0]
+                b = (_y.double().mean(0).T.unsqueeze(1).contiguous() if isinstance(_y, torch.Tensor)
+                     else np.ascontiguousarray(np.expand_dims(_y.mean(0).T, 1)))
+                U = (torch.empty((N, ncoef - 1, ncomp), dtype=torch.float64, device=device) if device is not None
+                     else np.empty((N, ncoef - 1, ncomp)))
+                params[f"{eid}_U"] = np2param(U)
+                params[f"{eid}_b"] = np2param(b)
+                self.N += N
+            V = np.zeros((ncomp, init_plan[last][3]))
+            mark = _STREAM_MARKS.get((shapes, int(ncomp), "V"))
+            if mark is not None:
+                rng.restore(mark)
+            else:
+                rng = None                                       # position unknown: numpy's global state is left alone
+            init_plan = []                                       # nothing is drawn below
         for i, (eid, N, ncoef, T) in enumerate(init_plan):
             scale = float(np.sqrt(T * ncomp))
             own = eid in train_data
@@ -294,7 +316,8 @@ class RRRGD():
             params[f"{eid}_U"] = np2param(U)
             params[f"{eid}_b"] = np2param(b)
             self.N += N
-        rng.export_to_numpy()
+        if rng is not None:
+            rng.export_to_numpy()
         params['V'] = np2param(V)
         self.n_comp, self.T = params['V'].shape
         self.model = nn.ParameterDict(params)
