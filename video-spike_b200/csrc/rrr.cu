@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(256) prep_u_kernel(const double* __restrict__ 
   // 128-bit loads and every (plane, component) row receives its 4 features as ONE 8-byte store
   bool done = false;
   if constexpr (RMAX == 3) {
-    if (planes == 2 && fmt == VS_OPERAND_F16 && c0 + kPrepC <= C1 && (C1 & 1) == 0) {
+    if (planes == 2 && fmt == VS_OPERAND_F16 && c0 + kPrepC <= C1 && (C1 & 1) == 0 && (reinterpret_cast<uintptr_t>(U) & 15) == 0) {
       const double2* up = reinterpret_cast<const double2*>(U + (n * C1 + c0) * 3);
       double u[12];
 #pragma unroll
@@ -1848,6 +1848,7 @@ static int closure_impl(vs_rrr_dims d, const uint16_t* Xa, const uint16_t* Xb, c
   if (fx_env < 0) { const char* e = getenv("VS_RRR_EPI_FX"); fx_env = e ? atoi(e) : 1; }
   const size_t fx_smem = (size_t)kFxHalf * (d.N + 1) * 8;
   const bool use_fx = exact && dense && r == 3 && d.N % 4 == 0 && d.N <= 160 && d.planes == 2 && d.fmt == VS_OPERAND_F16 && ex.y_lo && fx_env != 0 &&
+                      (((uintptr_t)y | (uintptr_t)ex.y_lo) & 15) == 0 &&
                       kFxRows == kEpiRows && fx_smem <= 96 * 1024;
   if (use_fx) {
     static bool fx_attr = false;
