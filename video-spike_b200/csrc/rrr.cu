@@ -435,19 +435,24 @@ __global__ void __launch_bounds__(256, 3) pack_fused_kernel(const uint8_t* __res
     // thread = (4 adjacent columns, one of 8 trial phases): one 32-bit shared-memory word per trial; 32-bit sums are exact
     // for K/8 * 65025 < 2^32; the byte-wise extremes come from the SIMD-in-word min / max
     const int q4 = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    unsigned a1[4] = {0u, 0u, 0u, 0u}, a2[4] = {0u, 0u, 0u, 0u};
+    // first moments in two packed accumulators of 16-bit lanes (columns 0|2 and 1|3: at most K/8 * 255 < 65536 per lane,
+    // K <= 1505 by the shared-memory bound); second moments one dp4a per column (the other three bytes masked off)
+    unsigned p02 = 0u, p13 = 0u, a2[4] = {0u, 0u, 0u, 0u};
     unsigned wmin = 0xffffffffu, wmax = 0u;
-    for (long long k = grp; k < K; k += 8) {
+    const int Ks = (int)K;
+    for (int k = grp; k < Ks; k += 8) {
       const unsigned wv = *reinterpret_cast<const unsigned*>(raw + k * kPackRow + 4 * q4);
       if constexpr (kStats) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const unsigned v = (wv >> (8 * i)) & 0xffu;
-          a1[i] += v; a2[i] += v * v;
-        }
+        p02 += wv & 0x00ff00ffu;
+        p13 += (wv >> 8) & 0x00ff00ffu;
+        a2[0] = __dp4a(wv & 0x000000ffu, wv, a2[0]);
+        a2[1] = __dp4a(wv & 0x0000ff00u, wv, a2[1]);
+        a2[2] = __dp4a(wv & 0x00ff0000u, wv, a2[2]);
+        a2[3] = __dp4a(wv & 0xff000000u, wv, a2[3]);
       }
       wmin = __vminu4(wmin, wv); wmax = __vmaxu4(wmax, wv);
     }
+    const unsigned a1[4] = {p02 & 0xffffu, p13 & 0xffffu, p02 >> 16, p13 >> 16};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { s_s1[grp][4 * q4 + i] = a1[i]; s_s2[grp][4 * q4 + i] = a2[i]; }
     s_vmin[grp][q4] = wmin; s_vmax[grp][q4] = wmax;
@@ -504,7 +509,8 @@ __global__ void __launch_bounds__(256, 3) pack_fused_kernel(const uint8_t* __res
       for (int j = 0; j < 8; ++j) {   // columns past C1 (last chunk): staged bytes 0, mean 0, std 1 -> zeros are written
         bm[j] = 8388608.f + s_m[q8 + j]; dl[j] = s_dl[q8 + j]; is[j] = s_istd[q8 + j];
       }
-      for (long long k = r16; k < K; k += 16) {
+      const int Ki = (int)K;
+      for (int k = r16; k < Ki; k += 16) {
         const uint2 b8 = *reinterpret_cast<const uint2*>(raw + k * kPackRow + q8);
         uint32_t hi[4], lo[4], xi[4];
 #pragma unroll
@@ -537,32 +543,54 @@ __global__ void __launch_bounds__(256, 3) pack_fused_kernel(const uint8_t* __res
   // 128-bit stores (one per feature row; the neighbouring 8-trial groups of a row come from the same block, so L2 merges
   // the half sectors before they reach DRAM); pad trials K <= k < Kp are written as zeros
   if (Xi) {
-    const long long ngrp = Kp / 8;
-    for (long long e = threadIdx.x; e < 32 * ngrp; e += 256) {
-      const int c4 = (int)(e & 31) * 4;
-      const long long k8 = (e >> 5) * 8;
+    const int ngrp = (int)(Kp / 8), Ki = (int)K;
+    for (int e = threadIdx.x; e < 32 * ngrp; e += 256) {
+      const int c4 = (e & 31) * 4;
+      const int k8 = (e >> 5) * 8;
+      const int ncol = (int)((C1 - c0 - c4) < 4 ? (C1 - c0 - c4) : 4);      // valid features of this thread's four
+      if (ncol <= 0) continue;
+      uint16_t* dst = Xi + (c0 + c4) * ldr + t * Kp + k8;
       uint32_t wd[8];
+      if (k8 + 8 <= Ki) {
+        // all 8 trials exist: no per-element guards
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < K) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * kPackRow + c4) : 0xffffffffu;
-      const bool full = k8 + 8 <= K;
+        for (int j = 0; j < 8; ++j) wd[j] = *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * kPackRow + c4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (c0 + c4 + i >= C1) continue;
-        const float bm = 8388608.f + s_m[c4 + i];
-        uint32_t w[4];
+        for (int i = 0; i < 4; ++i) {
+          if (i >= ncol) break;
+          const float bm = 8388608.f + s_m[c4 + i];
+          uint32_t w[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float a[2];
-#pragma unroll
-          for (int e2 = 0; e2 < 2; ++e2) {
-            const int j = 2 * jj + e2;
-            a[e2] = __uint_as_float(__byte_perm(wd[j], 0x4b000000u, 0x7540 + i)) - bm;
-            if (!full && k8 + j >= K) a[e2] = 0.f;
+          for (int jj = 0; jj < 4; ++jj) {
+            const float a0 = __uint_as_float(__byte_perm(wd[2 * jj], 0x4b000000u, 0x7540 + i)) - bm;
+            const float a1 = __uint_as_float(__byte_perm(wd[2 * jj + 1], 0x4b000000u, 0x7540 + i)) - bm;
+            const __half2 x = __floats2half2_rn(a0, a1);
+            w[jj] = *reinterpret_cast<const uint32_t*>(&x);
           }
-          const __half2 x = __floats2half2_rn(a[0], a[1]);
-          w[jj] = *reinterpret_cast<const uint32_t*>(&x);
+          *reinterpret_cast<uint4*>(dst + (long long)i * ldr) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(Xi + (c0 + c4 + i) * ldr + t * Kp + k8) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        // the group holding the last trials and the zero pad K <= k < Kp
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < Ki) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * kPackRow + c4) : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i >= ncol) break;
+          const float bm = 8388608.f + s_m[c4 + i];
+          uint32_t w[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float a[2];
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int j = 2 * jj + e2;
+              a[e2] = (k8 + j < Ki) ? __uint_as_float(__byte_perm(wd[j], 0x4b000000u, 0x7540 + i)) - bm : 0.f;
+            }
+            const __half2 x = __floats2half2_rn(a[0], a[1]);
+            w[jj] = *reinterpret_cast<const uint32_t*>(&x);
+          }
+          *reinterpret_cast<uint4*>(dst + (long long)i * ldr) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
   }
