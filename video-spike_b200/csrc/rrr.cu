@@ -543,54 +543,43 @@ __global__ void __launch_bounds__(256, 3) pack_fused_kernel(const uint8_t* __res
   // 128-bit stores (one per feature row; the neighbouring 8-trial groups of a row come from the same block, so L2 merges
   // the half sectors before they reach DRAM); pad trials K <= k < Kp are written as zeros
   if (Xi) {
-    const int ngrp = (int)(Kp / 8), Ki = (int)K;
+    // thread = (4 features, 16 trials): every store pair covers ONE whole 32-byte sector of a feature row (8-trial pieces
+    // left half sectors for L2 to merge; the ones it evicted first came back as DRAM read-modify-writes)
+    const int ngrp = (int)(Kp / 16), Ki = (int)K;
     for (int e = threadIdx.x; e < 32 * ngrp; e += 256) {
       const int c4 = (e & 31) * 4;
-      const int k8 = (e >> 5) * 8;
+      const int k16 = (e >> 5) * 16;
       const int ncol = (int)((C1 - c0 - c4) < 4 ? (C1 - c0 - c4) : 4);      // valid features of this thread's four
       if (ncol <= 0) continue;
-      uint16_t* dst = Xi + (c0 + c4) * ldr + t * Kp + k8;
-      uint32_t wd[8];
-      if (k8 + 8 <= Ki) {
-        // all 8 trials exist: no per-element guards
+      uint16_t* dst = Xi + (c0 + c4) * ldr + t * Kp + k16;
+      uint32_t wd[16];
+      const bool full = k16 + 16 <= Ki;
+      if (full) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wd[j] = *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * kPackRow + c4);
+        for (int j = 0; j < 16; ++j) wd[j] = *reinterpret_cast<const uint32_t*>(raw + (k16 + j) * kPackRow + c4);
+      } else {      // the group holding the last trials and the zero pad K <= k < Kp
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i >= ncol) break;
-          const float bm = 8388608.f + s_m[c4 + i];
-          uint32_t w[4];
+        for (int j = 0; j < 16; ++j) wd[j] = (k16 + j < Ki) ? *reinterpret_cast<const uint32_t*>(raw + (k16 + j) * kPackRow + c4) : 0u;
+      }
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float a0 = __uint_as_float(__byte_perm(wd[2 * jj], 0x4b000000u, 0x7540 + i)) - bm;
-            const float a1 = __uint_as_float(__byte_perm(wd[2 * jj + 1], 0x4b000000u, 0x7540 + i)) - bm;
-            const __half2 x = __floats2half2_rn(a0, a1);
-            w[jj] = *reinterpret_cast<const uint32_t*>(&x);
+      for (int i = 0; i < 4; ++i) {
+        if (i >= ncol) break;
+        const float bm = 8388608.f + s_m[c4 + i];
+        uint32_t w[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float a0 = __uint_as_float(__byte_perm(wd[2 * jj], 0x4b000000u, 0x7540 + i)) - bm;
+          float a1 = __uint_as_float(__byte_perm(wd[2 * jj + 1], 0x4b000000u, 0x7540 + i)) - bm;
+          if (!full) {
+            if (k16 + 2 * jj >= Ki) a0 = 0.f;
+            if (k16 + 2 * jj + 1 >= Ki) a1 = 0.f;
           }
-          *reinterpret_cast<uint4*>(dst + (long long)i * ldr) = make_uint4(w[0], w[1], w[2], w[3]);
+          const __half2 x = __floats2half2_rn(a0, a1);
+          w[jj] = *reinterpret_cast<const uint32_t*>(&x);
         }
-      } else {
-        // the group holding the last trials and the zero pad K <= k < Kp
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wd[j] = (k8 + j < Ki) ? *reinterpret_cast<const uint32_t*>(raw + (k8 + j) * kPackRow + c4) : 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i >= ncol) break;
-          const float bm = 8388608.f + s_m[c4 + i];
-          uint32_t w[4];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            float a[2];
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-              const int j = 2 * jj + e2;
-              a[e2] = (k8 + j < Ki) ? __uint_as_float(__byte_perm(wd[j], 0x4b000000u, 0x7540 + i)) - bm : 0.f;
-            }
-            const __half2 x = __floats2half2_rn(a[0], a[1]);
-            w[jj] = *reinterpret_cast<const uint32_t*>(&x);
-          }
-          *reinterpret_cast<uint4*>(dst + (long long)i * ldr) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        uint4* o = reinterpret_cast<uint4*>(dst + (long long)i * ldr);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
   }
