@@ -722,3 +722,31 @@ def test_fused_loader_matches_two_kernel_path(vs, cuda, monkeypatch, mode, K, F)
             for k in ("isdT", "qT"):
                 assert torch.equal(sa.exact[k], sb.exact[k]), k
         assert torch.equal(sa.xl, sb.xl)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_loader_reports_train_constant_features_that_vary_elsewhere(vs, cuda, monkeypatch, fused):
+    """a feature that is constant in the train split has its std clipped to 1e-8 (src/utils/utils.py:110); a
+    test frame that differs there becomes ~1e8 after the z-score and leaves the IEEE-half range.  Both loaders (fused:
+    decided once per column from the column extremes; two-kernel: per element) must raise the flag for the test split and
+    for that split only; a feature that is constant EVERYWHERE is zero after the z-score and raises nothing."""
+    from model.rrr import pack_session_from_frames
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=3, K=24, Kt=9, F=160, N=8, raw=True)
+    Xtr[:, :, 5] = 7; Xte[:, :, 5] = 7                      # constant in both splits: harmless
+    Xtr[:, :, 131] = 200                                      # constant in train ...
+    monkeypatch.setenv("VS_RRR_FUSED_PACK", fused)
+    args = lambda te: (torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(te), torch.from_numpy(yte), sidx, 3)
+    Xte_ok = Xte.copy(); Xte_ok[:, :, 131] = 200
+    ok = pack_session_from_frames(*args(Xte_ok), device=cuda, mode="exact")
+    torch.cuda.synchronize()
+    for sp in ok["X"]:
+        sp.wait_ready()
+        assert int(sp.overflow.item()) == 0
+    assert torch.all(ok["X"][0].Xa[:, :, 5].view(torch.int16) == 0) and torch.all(ok["X"][1].Xa[:, :, 131].view(torch.int16) == 0)
+    bad = pack_session_from_frames(*args(Xte), device=cuda, mode="exact")      # ... and varying in test
+    torch.cuda.synchronize()
+    bad["X"][1].wait_ready()
+    assert int(bad["X"][0].overflow.item()) == 0
+    assert int(bad["X"][1].overflow.item()) == 1
+    with pytest.raises(vs.VsError):
+        bad["X"][1].check_range()
