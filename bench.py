@@ -358,6 +358,8 @@ def rrr_config(args, world):
             "operand_format": fmt,
             "lbfgs": f"1 step, max_iter 20 (20 closure evals), history {hist}, "
                      + ("device-driven" if os.environ.get("VS_LBFGS_DEVICE", "1") != "0" else "host-driven")
+                     + (", compact history (one vector per evaluation)" if (hist == "float64" and os.environ.get("VS_LBFGS_DEVICE", "1") != "0"
+                                                                             and os.environ.get("VS_LBFGS_COMPACT", "1") != "0") else "")
                      + (", inner products sharded over the ranks" if joint else ""),
             "sessions": 1 if strong else world,
             "parallelism": (f"ONE session, trials sharded over {world} GPUs ({args.trials // world} train trials each), parameters and L-BFGS state replicated: "
@@ -571,8 +573,14 @@ def run_rrr(args, rank, world, local):
                        "traffic": ncu_traffic(key), "traffic_unit": tu, "peak_source": f"{pk_kind} bf16_tflops_sustained",
                        "launches": n_gemm, "avg_launch_ms": gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (ms * args.steps),
                        "executed_tflops": exec_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
+                       "executed_frac": (exec_flops / (gemm_ms * 1e-3) / 1e12 / peak) if (gemm_ms > 0 and peak) else None,
+                       "algorithmic_bytes_per_launch": 2.0 * K * 100 * (F + 4) * (2 if model_planes >= 2 else 1)      # A planes once
+                                                       + 2.0 * 3 * Np16 * (F + 4) * (2 if model_planes >= 2 else 1)          # B planes
+                                                       + 4.0 * K * 100 * 3 * Np16 * (-(-(-(-F // 64)) // int(os.environ.get('VS_RRR_RUN_EXACT', '72') or 72)) if mode == 'exact' else 1),   # Z partial tiles (accumulation runs) out
                        "note": "achieved counts ALGORITHMIC flops of the dense formulation (2*K*T*C*N per contraction); the factorised forward executes "
-                               f"r=3x that per plane product and {plane_passes} plane product(s) (executed_tflops)"})
+                               f"r=3x that per plane product and {plane_passes} plane product(s) (executed_tflops, executed_frac: the kernel is "
+                               "bound by the tensor pipe, 88.8 % active under ncu).  traffic exceeds the algorithmic bytes because the hi plane of X "
+                               "is read by two of the three plane products (DESIGN.md section 8)"})
     if n_bwd > 0:
         bw = bwd_bytes * n_bwd / (bwd_ms * 1e-3) / 1e9
         blocks.append({"bound": "hbm", "kernel": "vs::tc::rrr_bwd_dense_pair_kernel (dU: D_t = X_t^T R_t per time bin in TMEM, rank-one updates in registers"
