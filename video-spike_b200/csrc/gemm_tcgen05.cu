@@ -1127,14 +1127,14 @@ rrr_bwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // read; A = Xc (exact integers frame - round(mean), half) comes by TMA.  A CTA pair (cta_group::2, UMMA 256 x Npad) owns
 // 256 trials of three bins: 3 accumulators of Npad columns in TMEM (3 * 144 = 432 of 512).  Each CTA generates the B rows
 // of HALF of the neurons.  beta and Z never exist in HBM.
-// warp 0 TMA (A tiles), warp 1 MMA issue, warps 2..19 B generators (one (neuron, 16-byte chunk) item per thread and
-// k-block at N = 144: the generation is ~7 instructions per coefficient, 4,500 warp instructions per k-block against
-// 1,728 clocks of tensor work, so it needs all four schedulers busy), warps 4..11 drain the accumulators at the end.
-constexpr int FWD_THREADS = 640;
+// warp 0 TMA (A tiles), warp 1 MMA issue, warps 2..10 B generators (item = (neuron, 16-byte chunk): two per thread and
+// k-block at N = 144, the next item's U record requested while the current one is computed), warps 2..9 drain the
+// accumulators at the end.
+constexpr int FWD_THREADS = 352;
 constexpr int FWD_BINS = 3;
 constexpr int FWD_GEN_WARP0 = 2;
-constexpr int FWD_GEN_WARPS = 18;
-constexpr int FWD_GEN_THREADS = FWD_GEN_WARPS * 32;     // 576: 8 sixteen-byte chunks x 72 neuron slots
+constexpr int FWD_GEN_WARPS = 9;
+constexpr int FWD_GEN_THREADS = FWD_GEN_WARPS * 32;     // 288: 8 sixteen-byte chunks x 36 neuron slots
 
 struct DenseFwdParams {
   int K, T, C1, N, Npad;
@@ -1255,66 +1255,86 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
     }
   }
   if (warp >= FWD_GEN_WARP0) {
-    // ===== B generators: thread = (16-byte chunk q of the 128-byte row, neuron slot ns); neurons ns, ns + 72, ... of this half =====
+    // ===== B generators: thread = (16-byte chunk q of the 128-byte row, neuron slot ns); items (k-block, neuron ns + 36 it)
+    // are walked in one flat sequence and the U record of the NEXT item is requested before the current one is computed:
+    // with one item per thread and k-block nothing overlapped the L2 latency of the record (ncu: tensor pipe 33 %, issue 33 %)
     const int g = threadIdx.x - 32 * FWD_GEN_WARP0;
     const int q = g & 7, ns = g >> 3;
-    float v[FWD_BINS][3], bs[FWD_BINS];
+    constexpr int kSlots = FWD_GEN_THREADS / 8;
+    const int NI = (h + kSlots - 1) / kSlots;                  // items per thread and k-block (2 at N = 144)
+    float v[FWD_BINS][3];
 #pragma unroll
     for (int b = 0; b < FWD_BINS; ++b) {
       const int t = (t0 + b) < p.T ? (t0 + b) : (p.T - 1);
-      bs[b] = __ldg(p.bscale + t);
+      const float bsc = __ldg(p.bscale + t);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) v[b][j] = (float)p.V[(long long)j * p.T + t] * bs[b];     // scale folded into V (power of two: exact)
+      for (int j = 0; j < 3; ++j) v[b][j] = (float)p.V[(long long)j * p.T + t] * bsc;       // scale folded into V (power of two: exact)
     }
     const uint32_t fullB_leader0 = mapa_cluster(bar_fullB0, 0);
+    // u32g_index layout: record (kb, n) = 6 x 8 float4, lane q takes float4 (i, q): 128 contiguous bytes per 8 lanes
+    auto load_u = [&](int kb, int it, float4 (&dst)[6]) {
+      const int nl = ns + kSlots * it;
+      const int n = rank * h + nl;
+      if (nl < h && n < p.N) {
+        const float4* up = reinterpret_cast<const float4*>(p.U32) + (((long long)kb * p.N + n) * 6) * 8 + q;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[i] = __ldg(up + i * 8);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 un[6];
+    if (kb0 < kb1) load_u(kb0, 0, un);
     int s = 0;
     uint32_t ph = 0;
     for (int kb = kb0; kb < kb1; ++kb) {
       const long long c0 = (long long)kb * 64 + q * 8;
-      // 1/std of the 8 features of this chunk, per bin
-      float4 sa[FWD_BINS][2];
+      float4 sa[FWD_BINS][2];                                  // 1/std of the 8 features of this chunk, per bin (L1-resident after the first warp)
+      uint32_t bt0 = 0;
+      for (int it = 0; it < NI; ++it) {
+        float4 uc[6];
 #pragma unroll
-      for (int b = 0; b < FWD_BINS; ++b) {
-        const int t = (t0 + b) < p.T ? (t0 + b) : (p.T - 1);
-        const float4* ip = reinterpret_cast<const float4*>(p.isd + (long long)t * p.ldu + c0);
-        sa[b][0] = __ldg(ip); sa[b][1] = __ldg(ip + 1);
-      }
-      mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
-      const uint32_t bt0 = tiles0 + s * stage_bytes + FWD_BINS * A_TILE_BYTES;
-      for (int nl = ns; nl < h; nl += FWD_GEN_THREADS / 8) {
-        const int n = rank * h + nl;
-        float u[24];
-        if (n < p.N) {
-          // u32g_index layout: record (kb, n) = 6 x 8 float4, lane q takes float4 (i, q): 128 contiguous bytes per 8 lanes
-          const float4* up = reinterpret_cast<const float4*>(p.U32) + (((long long)kb * p.N + n) * 6) * 8 + q;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const float4 w = __ldg(up + i * 8);
-            u[4 * i] = w.x; u[4 * i + 1] = w.y; u[4 * i + 2] = w.z; u[4 * i + 3] = w.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 24; ++i) u[i] = 0.f;
+        for (int i = 0; i < 6; ++i) uc[i] = un[i];
+        {   // request the next item's record
+          int kbn = kb, itn = it + 1;
+          if (itn == NI) { itn = 0; ++kbn; }
+          if (kbn < kb1) load_u(kbn, itn, un);
         }
-        const uint32_t roff = (uint32_t)(nl >> 3) * 1024u + (uint32_t)(nl & 7) * 128u + ((uint32_t)(q ^ (nl & 7)) << 4);   // SWIZZLE_128B
+        if (it == 0) {
 #pragma unroll
-        for (int b = 0; b < FWD_BINS; ++b) {
-          if (b < nbins) {
-            const float sc[8] = {sa[b][0].x, sa[b][0].y, sa[b][0].z, sa[b][0].w, sa[b][1].x, sa[b][1].y, sa[b][1].z, sa[b][1].w};
-            float f[8];
+          for (int b = 0; b < FWD_BINS; ++b) {
+            const int t = (t0 + b) < p.T ? (t0 + b) : (p.T - 1);
+            const float4* ip = reinterpret_cast<const float4*>(p.isd + (long long)t * p.ldu + c0);
+            sa[b][0] = __ldg(ip); sa[b][1] = __ldg(ip + 1);
+          }
+          mbar_wait(bar_empty0 + 8u * s, ph ^ 1u);
+          bt0 = tiles0 + s * stage_bytes + FWD_BINS * A_TILE_BYTES;
+        }
+        const int nl = ns + kSlots * it;
+        if (nl < h) {
+          const float u[24] = {uc[0].x, uc[0].y, uc[0].z, uc[0].w, uc[1].x, uc[1].y, uc[1].z, uc[1].w, uc[2].x, uc[2].y, uc[2].z, uc[2].w,
+                               uc[3].x, uc[3].y, uc[3].z, uc[3].w, uc[4].x, uc[4].y, uc[4].z, uc[4].w, uc[5].x, uc[5].y, uc[5].z, uc[5].w};
+          const uint32_t roff = (uint32_t)(nl >> 3) * 1024u + (uint32_t)(nl & 7) * 128u + ((uint32_t)(q ^ (nl & 7)) << 4);   // SWIZZLE_128B
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              f[i] = fmaf(u[3 * i + 2], v[b][2], fmaf(u[3 * i + 1], v[b][1], u[3 * i] * v[b][0])) * sc[i];
-            uint32_t hi[4], lo[4];
+          for (int b = 0; b < FWD_BINS; ++b) {
+            if (b < nbins) {
+              const float sc[8] = {sa[b][0].x, sa[b][0].y, sa[b][0].z, sa[b][0].w, sa[b][1].x, sa[b][1].y, sa[b][1].z, sa[b][1].w};
+              float f[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              hi[i] = pack_h2(f[2 * i], f[2 * i + 1]);
-              const float2 hf = unpack_h2(hi[i]);
-              lo[i] = pack_h2(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+              for (int i = 0; i < 8; ++i)
+                f[i] = fmaf(u[3 * i + 2], v[b][2], fmaf(u[3 * i + 1], v[b][1], u[3 * i] * v[b][0])) * sc[i];
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                hi[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+                const float2 hf = unpack_h2(hi[i]);
+                lo[i] = pack_h2(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+              }
+              const uint32_t dst = bt0 + (uint32_t)(2 * b) * b_bytes + roff;
+              sts128(dst, hi[0], hi[1], hi[2], hi[3]);
+              sts128(dst + b_bytes, lo[0], lo[1], lo[2], lo[3]);
             }
-            const uint32_t dst = bt0 + (uint32_t)(2 * b) * b_bytes + roff;
-            sts128(dst, hi[0], hi[1], hi[2], hi[3]);
-            sts128(dst + b_bytes, lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
@@ -1324,11 +1344,11 @@ rrr_fwd_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const DenseFw
       if (++s == kStages) { s = 0; ph ^= 1u; }
     }
   }
-  if (warp >= 4 && warp < 12) {
-    // ===== drain: Y[(t, k), n] = accumulator / scale; TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 =====
+  if (warp >= 2 && warp < 10) {
+    // ===== drain: Y[(t, k), n] = accumulator / scale; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     mbar_wait(bar_done, 0);
     tc_fence_after();
-    const int qd = warp & 3, hsel = (warp - 4) >> 2;
+    const int qd = warp & 3, hsel = (warp - 2) >> 2;
     const int W = h;                                           // columns per thread (Npad / 2, a multiple of 8)
     const int k = row0 + qd * 32 + lane;
     for (int b = 0; b < nbins; ++b) {
