@@ -11,7 +11,8 @@ ONE JSON line.  The top level is the RRR workload (config.workload); the Linear 
           N > 1 GPUs (BASELINE configs[2]): ONE joint model over N sessions, one per GPU, with a shared V
           (rrr.py:37-49): [dV, loss] are all-reduced per closure evaluation and the L-BFGS scalars all-gathered per
           iteration (NCCL, stream-ordered: the optimiser stays device-driven).  --independent: N separate fits instead
-          (what train_rrr.py:179-187 runs; no data-path collective).
+          (what train_rrr.py:179-187 runs; no data-path collective).  --strong: ONE session with its trials sharded over
+          the N GPUs (gradient all-reduce per evaluation; "scaling": "strong").
   linear  BASELINE configs[0]/[3]: `Linear` MLP train step (src/trainer/base.py:147-154), B=16, D=120*128*128, N=144:
           frames/s = B*120 / step time.  N > 1: row-parallel first layer (each rank owns 1/N of the pixels of W0 and of
           every frame; one 16 KB all-reduce per step), strong scaling.
@@ -21,8 +22,10 @@ ONE JSON line.  The top level is the RRR workload (config.workload); the Linear 
            of a fixed number of calls (median and every sample listed beside it).
 `roofline`: dominant kernel, event-bracketed inside the timed region (vs_profile_*), vs MEASURED_PEAKS.json.
 `parity` : the timed mode against an independent float64 dense fit (torch einsum + autograd + torch.optim.LBFGS on the GPU).
-`cpu_baseline`: the oracle (CPU port of the reference) timed on the host cores on a bounded sample.
---impl reference: only that CPU arm (whole fits on a bounded sample of trials), printed in the same JSON shape.
+`cpu_baseline`: the oracle (CPU port of the reference) timed on the host cores on a bounded sample: whole fits on all
+           trials and features for a sample of the NEURONS, carried to the full neuron count by an affine model calibrated
+           in the run (`extrapolated`, `factor_on_value`, `calibration` are in the line).
+--impl reference: only that CPU arm, printed in the same JSON shape (rank 0 alone under torchrun).
 """
 from __future__ import annotations
 
