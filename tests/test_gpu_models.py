@@ -750,3 +750,40 @@ def test_loader_reports_train_constant_features_that_vary_elsewhere(vs, cuda, mo
     assert int(bad["X"][1].overflow.item()) == 1
     with pytest.raises(vs.VsError):
         bad["X"][1].check_range()
+
+
+def test_rrr_exact_mode_wide_session_runs_in_neuron_groups(vs, cuda):
+    """More neurons than one launch of the exact-operand kernels holds (160; BASELINE lists sessions with N = 436): the
+    default mode evaluates the session group by group -- the model is separable over neurons given V -- instead of falling
+    back to the three-plane classic mode.  One closure evaluation (loss, every gradient, per-neuron SSE), predictions and
+    the whole fit against the float64 oracle."""
+    from model.rrr import RRRGD, pack_session_from_frames, train_model_from_frames
+    Xtr, Xte, ytr, yte, sidx = small_rrr_problem(seed=11, K=40, Kt=12, F=160, N=170, raw=True)
+    data, _ = ro.preprocess_session([Xtr, Xte], [ytr, yte], sidx)
+    td_o = {"s": data}
+    params = ro.rrr_init(td_o, 3)
+    rng = np.random.default_rng(4)
+    for k in params:
+        params[k] = params[k] + 0.05 * rng.standard_normal(params[k].shape)
+    loss_o, g_o, sse_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 0)
+    args = (torch.from_numpy(Xtr), torch.from_numpy(ytr), torch.from_numpy(Xte), torch.from_numpy(yte), sidx)
+    entry = pack_session_from_frames(*args, 3, device=cuda)
+    sp = entry["X"][0]
+    assert sp.dims.mode == vs.RRR_MODE_EXACT and [(a, b) for a, b, *_ in sp.neuron_groups()] == [(0, 96), (96, 170)]
+    td = {"s": entry}
+    m = RRRGD(td, 3, l2=100.0); m.to(cuda)
+    assert m.exact
+    _params_to_model(m, params, cuda)
+    assert float(m.loss_and_grad(td, 0)) == pytest.approx(loss_o, rel=2e-6)
+    for k in g_o:
+        got = m.model[k].grad.cpu().numpy()
+        assert np.abs(got - g_o[k]).max() <= 2e-5 * np.abs(g_o[k]).max(), k
+    np.testing.assert_allclose(m.compute_MSE_RRRGD(td, 0)["s"].cpu().numpy(), sse_o["s"], rtol=1e-5)
+    _, yv, yhat = m.predict_y(td, "s", 1)
+    _, _, sse_val_o = ro.loss_and_grad_lowrank(params, td_o, 100.0, 1)
+    np.testing.assert_allclose(((yhat - yv) ** 2).sum((0, 1)).cpu().numpy(), sse_val_o["s"], rtol=1e-5)
+    # whole fit through the public entry point
+    _, mse_o, _ = ro.train_model_main({"session": data}, 100.0, 3)
+    model, mse, _ = train_model_from_frames(*args, l2=100.0, n_comp=3)
+    assert model.exact
+    assert float(mse["mse_val_mean"]) == pytest.approx(mse_o["mse_val_mean"], rel=1e-4)

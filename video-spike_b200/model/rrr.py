@@ -79,6 +79,17 @@ def get_device():
 
 _SIDE_STREAMS = {}
 _PINNED_STAGES = {}
+
+
+def _neuron_group_bounds(N, limit=160):
+    """Neuron ranges of at most `limit` (sizes a multiple of 16 where possible) covering 0..N."""
+    if N <= limit:
+        return [(0, N)]
+    ng = -(-N // 144)
+    size = -(-(-(-N // ng)) // 16) * 16
+    return [(g, min(N, g + size)) for g in range(0, N, size)]
+
+
 # positions of the init stream (LegacyNormalStream.snapshot) after a given sequence of session draws from seed 0:
 # key (shapes of the sessions drawn so far, n_comp, "U" | "V") -- see RRRGD.__init__
 _STREAM_MARKS = {}
@@ -175,12 +186,19 @@ class _PackedSplit:
         self._keep = None
         return self
 
-    def exact_ops(self):
-        """ctypes vs_rrr_exact_ops of this split (the tensors stay referenced by self.exact)."""
+    def exact_ops(self, y_lo=None):
+        """ctypes vs_rrr_exact_ops of this split (the tensors stay referenced by self.exact); `y_lo`: a neuron group's own."""
         ex = self.exact
         g = lambda k: vs.ptr(ex.get(k)) if ex.get(k) is not None else None      # noqa: E731
-        return vs.RrrExactOps(vs.ptr(self.Xb) if self.Xb is not None else None, g("isdT"), g("qT"), int(ex["ldt"]), g("y_lo"),
-                              g("Xc"), g("isd"), g("qh"), g("isdmax"))
+        return vs.RrrExactOps(vs.ptr(self.Xb) if self.Xb is not None else None, g("isdT"), g("qT"), int(ex["ldt"]),
+                              vs.ptr(y_lo) if y_lo is not None else g("y_lo"), g("Xc"), g("isd"), g("qh"), g("isdmax"))
+
+    def neuron_groups(self):
+        """[(n0, n1, dims, y, y_lo)] -- the exact-operand kernels hold at most 160 neurons per launch; wider sessions
+        (BASELINE: N = 436) are evaluated group by group: the model is separable over neurons given V (loss, the l2 term and
+        dV are sums over neurons; U, b, dU, db of a group are contiguous slices)."""
+        ex = self.exact or {}
+        return ex.get("groups") or [(0, self.N, self.dims, self.y, ex.get("y_lo"))]
 
     def __del__(self):
         ev = getattr(self, "ready", None)
@@ -422,14 +440,22 @@ class RRRGD():
         dU = db = None
         if want_grad:
             dU, db = self._grad_buffer(U), self._grad_buffer(b)
-        ws = self._workspace(sp.dims)
         if sp.dims.mode != vs.RRR_MODE_CLASSIC:
             import ctypes
-            ops = sp.exact_ops()
-            vs.check(vs.lib.vs_rrr_closure_exact(sp.dims, vs.ptr(sp.Xa), ctypes.byref(ops), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
-                                                 vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
-                                                 vs.ptr(dV), vs.ptr(db), vs.ptr(ws), ws.numel(), vs.stream()))
+            groups = sp.neuron_groups()
+            lossg = loss if len(groups) == 1 else torch.empty(len(groups), dtype=torch.float64, device=dev)
+            for gi, (n0, n1, dg, yg, ylog) in enumerate(groups):
+                ws = self._workspace(dg)
+                ops = sp.exact_ops(ylog)
+                sl = lambda t_: vs.ptr(t_[n0:n1]) if t_ is not None else None      # noqa: E731  (contiguous neuron slices)
+                vs.check(vs.lib.vs_rrr_closure_exact(dg, vs.ptr(sp.Xa), ctypes.byref(ops), vs.ptr(sp.xl), vs.ptr(yg), sl(U.data),
+                                                     vs.ptr(V.data), sl(b.data), float(self.l2), vs.ptr(lossg[gi:gi + 1]), sl(sse), sl(dU),
+                                                     vs.ptr(dV), sl(db), vs.ptr(ws), ws.numel(), vs.stream()))
+            if len(groups) > 1:
+                # every group's scalar carries the V-only part of nothing (the l2 term is <U_g^T U_g, V V^T> + |b_g|^2): plain sum
+                loss = lossg.sum().reshape(1)
             return loss[0], sse, dU, db
+        ws = self._workspace(sp.dims)
         vs.check(vs.lib.vs_rrr_closure(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.Xb), vs.ptr(sp.xl), vs.ptr(sp.y), vs.ptr(U.data),
                                        vs.ptr(V.data), vs.ptr(b.data), float(self.l2), vs.ptr(loss), vs.ptr(sse), vs.ptr(dU),
                                        vs.ptr(dV), vs.ptr(db), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
@@ -470,13 +496,23 @@ class RRRGD():
         sp.wait_ready()
         U, b, V = self.model[f"{eid}_U"], self.model[f"{eid}_b"], self.model['V']
         yhat = torch.empty((sp.K, sp.T, sp.N), dtype=torch.float64, device=V.device)
-        ws = self._workspace(sp.dims)
-        if sp.dims.mode == vs.RRR_MODE_DENSE:
+        groups = sp.neuron_groups() if sp.dims.mode != vs.RRR_MODE_CLASSIC else None
+        if groups is not None and len(groups) > 1:
+            for n0, n1, dg, _, _ in groups:
+                ws = self._workspace(dg)
+                yg = torch.empty((sp.K, sp.T, n1 - n0), dtype=torch.float64, device=V.device)
+                vs.check(vs.lib.vs_rrr_predict(dg, vs.ptr(sp.Xa), vs.ptr(sp.xl), vs.ptr(U.data[n0:n1]), vs.ptr(V.data), vs.ptr(b.data[n0:n1]),
+                                               vs.ptr(yg), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
+                yhat[:, :, n0:n1] = yg
+            ws = None
+        elif sp.dims.mode == vs.RRR_MODE_DENSE:
+            ws = self._workspace(sp.dims)
             import ctypes
             ops = sp.exact_ops()
             vs.check(vs.lib.vs_rrr_predict_exact(sp.dims, ctypes.byref(ops), vs.ptr(sp.xl), vs.ptr(U.data), vs.ptr(V.data), vs.ptr(b.data),
                                                  vs.ptr(yhat), vs.ptr(ws), ws.numel(), vs.stream()))
         else:
+            ws = self._workspace(sp.dims)
             vs.check(vs.lib.vs_rrr_predict(sp.dims, vs.ptr(sp.Xa), vs.ptr(sp.xl), vs.ptr(U.data), vs.ptr(V.data), vs.ptr(b.data),
                                            vs.ptr(yhat), self.engine, vs.ptr(ws), ws.numel(), vs.stream()))
         Xraw = data[eid]['X'][k]
@@ -562,7 +598,10 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
         # shapes outside the exact-operand kernels (rank != 3, more than 160 neurons, <= 128 features): the parity mode is
         # then the classic layout with 3 residual planes
         Kq, Fq, Nq = int(frames_train.shape[0]), int(frames_train[0, 0].numel()), int(counts_train.shape[2])
-        if not vs.lib.vs_rrr_exact_supported(Kq, len(np.asarray(sorted_idx)), Fq, Nq, n_comp):
+        bounds = _neuron_group_bounds(Nq)
+        if len(bounds) > 1:
+            dense = False                       # neuron groups are evaluated by the factorised exact closure
+        if not vs.lib.vs_rrr_exact_supported(Kq, len(np.asarray(sorted_idx)), Fq, max(b1 - b0 for b0, b1 in bounds), n_comp):
             exact, planes = False, 3
     if exact:
         planes, operand = 2, "f16"
@@ -673,6 +712,11 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
                 vs.check(vs.lib.vs_rrr_pack_u8(vs.ptr(fr), Tf_dev, vs.ptr(idx_dev), vs.ptr(mean), vs.ptr(sd), d, vs.ptr(Xa), vs.ptr(Xb),
                                                vs.ptr(xl), vs.ptr(overflow), st))
                 vs.check(vs.lib.vs_rrr_smooth_y(vs.ptr(cnt), K, T, N, float(smooth_w), vs.ptr(my), vs.ptr(sy), vs.ptr(y), st))
+            if exact and len(_neuron_group_bounds(N)) > 1:
+                ex["groups"] = []
+                for n0, n1 in _neuron_group_bounds(N):
+                    dg = vs.RrrDims(K, T, F, n1 - n0, n_comp, planes, d.ldc, d.ldr, fmt, d.mode)
+                    ex["groups"].append((n0, n1, dg, y[:, :, n0:n1].contiguous(), ex["y_lo"][:, :, n0:n1].contiguous()))
             sp = _PackedSplit.from_device(d, Xa, Xb, xl, y, overflow, exact=ex)
             if which == 1:
                 sp._keep = (idx, idx_compact, idx_dev, mean, sd, my, sy)
