@@ -595,8 +595,9 @@ def pack_session_from_frames(frames_train, counts_train, frames_test, counts_tes
     exact = mode in ("exact", "dense")
     dense = mode == "dense"
     if exact:
-        # shapes outside the exact-operand kernels (rank != 3, more than 160 neurons, <= 128 features): the parity mode is
-        # then the classic layout with 3 residual planes
+        # sessions wider than one launch of the exact-operand kernels (160 neurons) are evaluated in neuron groups
+        # (_PackedSplit.neuron_groups); shapes outside those kernels altogether (rank != 3, <= 128 features): the parity mode
+        # is then the classic layout with 3 residual planes
         Kq, Fq, Nq = int(frames_train.shape[0]), int(frames_train[0, 0].numel()), int(counts_train.shape[2])
         bounds = _neuron_group_bounds(Nq)
         if len(bounds) > 1:
