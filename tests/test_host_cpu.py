@@ -358,3 +358,16 @@ def test_rrr_init_stream_marks_reproduce_the_sequential_draw(monkeypatch):
     U0 = np.random.normal(size=(5, 39, 3)) / np.sqrt(7 * 3)
     full = mr.RRRGD({**td("a"), **td("b"), **td("c"), **td("d")}, 3, l2=1.0)
     assert np.array_equal(full.model["a_U"].detach().numpy(), U0)
+
+
+def test_neuron_group_bounds_cover_wide_sessions():
+    """model.rrr._neuron_group_bounds: contiguous ranges of at most 160 neurons covering 0..N, one range up to 160."""
+    from model.rrr import _neuron_group_bounds
+    for N in (1, 16, 144, 160, 161, 300, 436, 450, 1024):
+        b = _neuron_group_bounds(N)
+        assert b[0][0] == 0 and b[-1][1] == N
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert all(0 < n1 - n0 <= 160 for n0, n1 in b)
+        assert (len(b) == 1) == (N <= 160)
+        assert all(n0 % 16 == 0 for n0, _ in b)                # group starts keep U / dU slices 16-byte aligned
+    assert _neuron_group_bounds(436) == [(0, 112), (112, 224), (224, 336), (336, 436)]
